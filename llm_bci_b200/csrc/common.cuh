@@ -1,0 +1,156 @@
+// Shared device/host helpers for the NDT1 sm_100a kernels.
+// Everything here is internal; the public surface is include/ndt1_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------
+// Error plumbing: every C-ABI entry returns 0 on success; the message of the
+// last failure on the calling thread is kept for ndt1_last_error().
+// ---------------------------------------------------------------------------
+void ndt1_set_error(const char* fmt, ...);
+
+#define NDT1_CUDA_CHECK(expr)                                                   \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      ndt1_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,              \
+                     cudaGetErrorString(_e));                                   \
+      return 1;                                                                 \
+    }                                                                           \
+  } while (0)
+
+#define NDT1_CHECK_LAUNCH() NDT1_CUDA_CHECK(cudaGetLastError())
+
+#define NDT1_REQUIRE(cond, ...)                                                 \
+  do {                                                                          \
+    if (!(cond)) {                                                              \
+      ndt1_set_error(__VA_ARGS__);                                              \
+      return 2;                                                                 \
+    }                                                                           \
+  } while (0)
+
+#define NDT1_TRY(expr)                                                          \
+  do {                                                                          \
+    int _rc = (expr);                                                           \
+    if (_rc != 0) return _rc;                                                   \
+  } while (0)
+
+static inline int ndt1_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+// Type helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float load_as_f32(const void* p, long long i, int is_bf16) {
+  return is_bf16 ? __bfloat162float(((const bf16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void store_from_f32(void* p, long long i, int is_bf16, float v) {
+  if (is_bf16) ((bf16*)p)[i] = __float2bfloat16_rn(v);
+  else ((float*)p)[i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// Warp / block reductions
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10, counter based.  One call yields 4 uniform u32 for the 4
+// consecutive elements [4*ctr, 4*ctr+3] of logical stream `stream`.
+// Dropout keeps an element iff its u32 >= threshold(p) (see drop_threshold).
+// Forward and backward kernels index by ELEMENT, never by thread, so the mask
+// is reproducible whatever the launch geometry.
+// ---------------------------------------------------------------------------
+struct Philox4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_t ctr, uint64_t stream) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32);
+  uint32_t c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+  return o;
+}
+
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  // keep iff u32 >= thr  ->  P(drop) = thr / 2^32
+  double t = (double)p * 4294967296.0;
+  if (t <= 0.0) return 0u;
+  if (t >= 4294967295.0) return 4294967295u;
+  return (uint32_t)t;
+}
+
+// keep-scale (0 or 1/(1-p)) of one element of a dropout site
+__device__ __forceinline__ float drop_scale_1(uint64_t seed, uint64_t stream, uint64_t elem, uint32_t thr, float inv_keep) {
+  Philox4 r = philox4x32_10(seed, elem >> 2, stream);
+  uint32_t u = (elem & 3) == 0 ? r.x : (elem & 3) == 1 ? r.y : (elem & 3) == 2 ? r.z : r.w;
+  return u >= thr ? inv_keep : 0.f;
+}
+
+// Box-Muller on two u32 -> two N(0,1)
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+  const float u2 = (float)b * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  n0 = r * c; n1 = r * s;
+}
+
+// ---------------------------------------------------------------------------
+// Activations (forward and derivative)
+// ---------------------------------------------------------------------------
+enum { ACT_NONE = 0, ACT_SOFTSIGN = 1, ACT_GELU = 2, ACT_RELU = 3 };
+// derivative selectors for backward epilogues
+enum { DACT_NONE = 0, DACT_SOFTSIGN_FROM_OUT = 1, DACT_GELU_FROM_IN = 2, DACT_RELU_FROM_OUT = 3 };
+
+__device__ __forceinline__ float act_apply(int act, float v) {
+  switch (act) {
+    case ACT_SOFTSIGN: return v / (1.0f + fabsf(v));
+    case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    case ACT_RELU: return fmaxf(v, 0.f);
+    default: return v;
+  }
+}
+__device__ __forceinline__ float dact_apply(int dact, float saved) {
+  switch (dact) {
+    case DACT_SOFTSIGN_FROM_OUT: { float t = 1.0f - fabsf(saved); return t * t; }
+    case DACT_GELU_FROM_IN: {
+      const float cdf = 0.5f * (1.0f + erff(saved * 0.70710678118654752f));
+      const float pdf = 0.3989422804014327f * expf(-0.5f * saved * saved);
+      return cdf + saved * pdf;
+    }
+    case DACT_RELU_FROM_OUT: return saved > 0.f ? 1.f : 0.f;
+    default: return 1.f;
+  }
+}
