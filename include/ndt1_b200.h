@@ -1,0 +1,207 @@
+/* ndt1_b200.h -- C ABI of the B200-native NDT1 hot path.
+ *
+ * Drop-in boundary for the data-parallel hot path of colehurwitz/llm_bci:
+ * the NDT1 neural-encoder forward and backward over binned spike trains.
+ * The reference implements this path as PyTorch module calls; each entry
+ * point below cites the reference code it replaces (paths relative to the
+ * reference checkout).  The reference-side binding is a ctypes stub, see
+ * INTEGRATION.md; llm_bci_b200/_C.py is that stub in this repository.
+ *
+ * Conventions
+ *   - every function returns 0 on success; otherwise ndt1_last_error() holds
+ *     a message for the calling thread (the Python shim raises RuntimeError);
+ *   - all pointers are DEVICE pointers unless stated otherwise; tensors are
+ *     contiguous row-major with the shapes given; integer tensors are int64
+ *     exactly as the reference's collate produces them;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the
+ *     device; no global state besides the engine object;
+ *   - built for sm_100a only; there is no CPU fallback.
+ */
+#ifndef NDT1_B200_H
+#define NDT1_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDT1_ABI_VERSION 1
+
+/* activations (transformers ACT2FN names used by configs/ndt1.yaml) */
+enum { NDT1_ACT_IDENTITY = 0, NDT1_ACT_SOFTSIGN = 1, NDT1_ACT_GELU = 2, NDT1_ACT_RELU = 3 };
+/* training method, models/ndt1.py:480-491 */
+enum { NDT1_METHOD_CTC = 0, NDT1_METHOD_MLM = 1, NDT1_METHOD_AUTOREGRESSIVE = 2 };
+/* loss, models/ndt1.py:507-517 */
+enum { NDT1_LOSS_CTC = 0, NDT1_LOSS_POISSON_LOG = 1, NDT1_LOSS_POISSON_RATE = 2, NDT1_LOSS_MSE = 3 };
+/* arithmetic */
+enum { NDT1_PRECISION_FP32 = 0, NDT1_PRECISION_BF16 = 1 };
+/* masker modes, models/masker.py:54-83 */
+enum { NDT1_MASK_TEMPORAL = 0, NDT1_MASK_NEURON = 1, NDT1_MASK_RANDOM = 2, NDT1_MASK_COSMOOTH = 3 };
+
+const char* ndt1_last_error(void);
+int ndt1_abi_version(void);
+
+/* ------------------------------------------------------------------------
+ * Stand-alone operators (each is one or two kernel launches)
+ * ---------------------------------------------------------------------- */
+
+/* SmoothAndNoise.forward, models/ndt1.py:92-107.
+ * out[b,t,n] = sum_i taps[i]*x[b,t+i-(K-1)/2,n] + white_sd*W[b,t,n] + offset_sd*O[b,n]
+ * taps: HOST pointer, K odd (0 = no smoothing).  white/offset: injected N(0,1)
+ * draws (device) or NULL; with NULL and use_philox != 0 the kernel draws its own. */
+int ndt1_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps_host, int K, float white_sd,
+                      float offset_sd, const float* white, const float* offset, int use_philox, uint64_t seed, void* stream);
+
+/* Masker.forward given its random draws, models/masker.py:44-104, in place on
+ * spikes (B,T,N).  mask_draw has the mode's own shape ((B,T) temporal, (B,N)
+ * neuron/region, (B,T,N) random, (N) co-smooth); zero_draw/random_draw (B,T,N)
+ * are the Bernoulli(zero_ratio)/(random_ratio) draws, all as uint8 0/1; rand
+ * (B,T,N) uniform [0,1).  mask_out (B,T,N) int64 receives the mask; targets_mask
+ * (B,T,N) int64, if given, is OR-ed (models/ndt1.py:424-427).  scratch: 4 bytes. */
+int ndt1_masker_apply(float* spikes, int B, int T, int N, int mode, int timespan, const uint8_t* mask_draw,
+                      const uint8_t* zero_draw, const uint8_t* random_draw, const float* rand, int64_t* mask_out,
+                      int64_t* targets_mask, void* scratch, void* stream);
+/* device-side draws for the masker's fast path (own Philox streams) */
+int ndt1_bernoulli_u8(uint8_t* out, int64_t n, float prob, uint64_t seed, uint64_t stream_id, void* stream);
+int ndt1_uniform_f32(float* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream);
+
+/* padded_array, data_utils/datasets.py:191-221, on the device: ragged rows
+ * stored back to back (row b = src[offsets[b]..offsets[b+1]) in units of
+ * `inner` elements) -> dst (B, P, inner).  Rows shorter than `pad_to` are padded
+ * with `value` on the left or right up to `pad_to`; the first P entries are kept.
+ * The reference uses pad_to = P = min(truncate, max(max_len, min_length)).
+ * elem_size 4 (float32) or 8 (int64). */
+int ndt1_pad_pack(const void* src, const int64_t* offsets, void* dst, int B, int P, int inner, int elem_size, int side_left,
+                  int pad_to, double value, void* stream);
+
+/* nn.LogSoftmax + nn.CTCLoss(reduction="none").sum(), models/ndt1.py:499,517,581.
+ * logits (B,L,V) -> logp (B,L,V); per-trial nll (B); *loss += sum; optional
+ * dlogits (B,L,V) = d loss / d logits scaled by *dloss (NULL = 1).
+ * workspace: ndt1_ctc_workspace_bytes(B,L,S) bytes. */
+size_t ndt1_ctc_workspace_bytes(int B, int L, int S);
+int ndt1_ctc_loss(const float* logits, float* logp, const int64_t* targets, const int64_t* input_lengths,
+                  const int64_t* target_lengths, int B, int L, int V, int S, int blank, int zero_infinity, void* workspace,
+                  float* nll, float* loss, float* dlogits, const float* dloss, void* stream);
+/* argmax + format_ctc, main.py:69 and utils/eval_bci.py:41-48.  out_ids (B,L) padded with -1, out_len (B). */
+int ndt1_ctc_greedy_decode(const float* logp, int B, int L, int V, int blank, int64_t* out_ids, int64_t* out_len, void* stream);
+
+/* masked Poisson-NLL / MSE, models/ndt1.py:508-515,548-578.  *loss += sum, *count += weights. */
+int ndt1_recon_loss(const float* pred, const float* target, float* dpred, const int64_t* targets_mask, const int64_t* pad_mask,
+                    int B, int T, int N, int loss_kind, int shift_by_one, int relu_out, float* loss, int64_t* count,
+                    const float* dloss, void* stream);
+
+/* nn.LayerNorm (eps 1e-5), models/ndt1.py:309-311,402.  fp32 in/out. */
+int ndt1_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int64_t rows,
+                       int H, float eps, void* stream);
+
+/* y = act(x W^T + b) in fp32 (CUDA cores) or bf16 tensor cores (tcgen05); x (M,K), W (N,K).
+ * Replaces the nn.Linear calls of models/ndt1.py:130,140,219-221,247-257,494. */
+int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K, int act, int precision,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* torch.optim.AdamW step on one flat buffer, models/trainer.py:229,340. */
+int ndt1_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------
+ * The encoder + head engine: everything of NDT1.forward after the masker
+ * (models/ndt1.py:429-450, 542-589) and its backward, as one call each.
+ * ---------------------------------------------------------------------- */
+
+typedef struct ndt1_engine ndt1_engine;
+
+typedef struct {
+  int32_t abi_version;       /* NDT1_ABI_VERSION */
+  int32_t precision;         /* NDT1_PRECISION_* */
+  /* embedder, configs/ndt1.yaml:34-53 */
+  int32_t n_channels, input_dim, max_F;
+  int32_t embed_bias, embed_act, pos;
+  int32_t stack_active, stack_size, stack_stride;
+  int32_t block_token, day_token, n_blocks, n_days, adapt;
+  /* transformer, configs/ndt1.yaml:56-71 */
+  int32_t n_layers, hidden, n_heads, inter, attention_bias, mlp_bias, mlp_act;
+  int32_t use_rope;
+  float rope_theta;
+  /* context, configs/ndt1.yaml:21-24 */
+  int32_t context_forward, context_backward;
+  /* factors, configs/ndt1.yaml:74-81 */
+  int32_t factors_active, factors_size, factors_act, factors_bias;
+  /* head + loss */
+  int32_t method, loss_kind, n_outputs, blank_id, zero_infinity, decoder_relu;
+  /* dropout probabilities (0 disables a site) */
+  float p_embed, p_transformer, p_factors;
+  /* capacity of the activation arena */
+  int32_t max_batch, max_T, max_targets;
+} ndt1_config;
+
+/* Parameter / gradient pointer tables, in the order of the reference's
+ * state_dict; absent tensors are NULL. */
+#define NDT1_MAX_LAYERS 32
+typedef struct {
+  float* embed_w; float* embed_b;      /* embed_spikes (D, N), (D); adapt: n_days copies back to back */
+  float* proj_w;  float* proj_b;       /* stack_projection (H, S*D) or projection (H, D) */
+  float* pos_w;                        /* embed_pos (max_F, H) */
+  float* block_emb; float* day_emb;    /* (n_blocks, H), (n_days, H) */
+  struct {
+    float *ln1_w, *ln1_b, *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b, *ln2_w, *ln2_b, *up_w, *up_b, *down_w, *down_b;
+  } layer[NDT1_MAX_LAYERS];
+  float* out_norm_w; float* out_norm_b;
+  float* factors_w; float* factors_b;  /* out_proj.proj.0 */
+  float* dec_w; float* dec_b;          /* decoder.0 (n_outputs, H or factors_size) */
+} ndt1_tensors;
+
+typedef struct {
+  const float* spikes;            /* (B,T,N) after smoothing/noise/masking */
+  const int64_t* spikes_mask;     /* (B,T) 1 = valid */
+  const int64_t* spikes_timestamp;/* (B,T) */
+  const int64_t* spikes_lengths;  /* (B) */
+  const int64_t* block_idx;       /* (B) or NULL */
+  const int64_t* day_idx;         /* (B) or NULL */
+  const int64_t* targets;         /* ctc: (B,S) */
+  const int64_t* targets_lengths; /* ctc: (B) */
+  const float* recon_targets;     /* mlm/autoregressive: (B,T,N) original spikes */
+  const int64_t* targets_mask;    /* mlm: (B,T,N) from the masker */
+  int32_t B, T, S;
+  int32_t training;               /* dropout on */
+  int32_t need_backward;          /* keep activations and loss gradients for ndt1_engine_backward */
+  int32_t encoder_only;           /* stop after the encoder (NeuralEncoder.forward, models/ndt1.py:408-450): no head, no loss */
+  uint64_t seed;                  /* Philox key of this step's dropout */
+} ndt1_batch;
+
+typedef struct {
+  float* loss;                    /* (1) sum loss */
+  int64_t* n_examples;            /* (1) */
+  float* preds;                   /* ctc: (B,L',V) log-probs; ssl: (B,T,N) (log-)rates */
+  int64_t* out_mask;              /* (B,L) stacked padding mask incl. prefix tokens, or NULL */
+  int64_t* loss_mask;             /* mlm: (B,T,N) targets_mask & padding, or NULL */
+  int64_t* out_lengths;           /* (B) get_stacked_lens(spikes_lengths), or NULL */
+  float* features;                /* (B,L',H_out) encoder output, or NULL */
+} ndt1_outputs;
+
+int ndt1_engine_create(const ndt1_config* cfg, ndt1_engine** out);
+void ndt1_engine_destroy(ndt1_engine* e);
+size_t ndt1_engine_arena_bytes(const ndt1_engine* e);
+/* output sequence length for T input bins: 1 + (T - size) / stride when stacking (models/ndt1.py:138-140) */
+int ndt1_engine_out_len(const ndt1_engine* e, int T);
+/* forward; activations stay in the engine for the matching backward */
+int ndt1_engine_forward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_batch* batch, const ndt1_outputs* out, void* stream);
+/* backward of the last forward: grads->X += dloss * dLoss/dX (buffers are caller-zeroed) */
+int ndt1_engine_backward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_tensors* grads, const float* dloss, void* stream);
+/* Gradient stages of the last backward in completion order: 0 = decoder + out_norm,
+ * 1..n_layers = layers n_layers-1..0, n_layers+1 = embedder.  ndt1_engine_wait_stage makes
+ * `stream` wait (cudaStreamWaitEvent) until that stage's gradients are final, so a bucketed
+ * all-reduce on a side stream overlaps the rest of the backward (DDP semantics,
+ * models/trainer.py:258-262,339). */
+int ndt1_engine_stage_count(const ndt1_engine* e);
+int ndt1_engine_wait_stage(ndt1_engine* e, int stage, void* stream);
+/* number of kernels launched by the last forward+backward (bench.py gpu_launches) */
+int64_t ndt1_engine_launch_count(const ndt1_engine* e);
+/* keep-scale (0 or 1/(1-p)) of a dropout site, for tests: site 0 embed, 1+4*l attn-probs, 2+4*l attn-out, 3+4*l mlp */
+int ndt1_dropout_scales(float* out, int64_t n, float p, uint64_t seed, uint64_t site, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDT1_B200_H */

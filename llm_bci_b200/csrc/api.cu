@@ -1,0 +1,104 @@
+// C-ABI wrappers of the stand-alone operators declared in include/ndt1_b200.h.
+#include "../../include/ndt1_b200.h"
+#include "kernels.cuh"
+
+extern "C" {
+
+int ndt1_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps_host, int K, float white_sd,
+                      float offset_sd, const float* white, const float* offset, int use_philox, uint64_t seed, void* stream) {
+  return k_smooth_noise(x, out, B, T, N, taps_host, K, white_sd, offset_sd, white, offset, use_philox, seed, (cudaStream_t)stream);
+}
+
+int ndt1_masker_apply(float* spikes, int B, int T, int N, int mode, int timespan, const uint8_t* mask_draw, const uint8_t* zero_draw,
+                      const uint8_t* random_draw, const float* rand, int64_t* mask_out, int64_t* targets_mask, void* scratch,
+                      void* stream) {
+  NDT1_REQUIRE(spikes && mask_draw && zero_draw && random_draw && rand && scratch, "masker_apply: null argument");
+  return k_masker_apply(spikes, B, T, N, mode, timespan, mask_draw, zero_draw, random_draw, rand, (long long*)mask_out,
+                        (long long*)targets_mask, (unsigned int*)scratch, (cudaStream_t)stream);
+}
+int ndt1_bernoulli_u8(uint8_t* out, int64_t n, float prob, uint64_t seed, uint64_t stream_id, void* stream) {
+  return k_bernoulli_u8(out, n, prob, seed, stream_id, (cudaStream_t)stream);
+}
+int ndt1_uniform_f32(float* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream) {
+  return k_uniform_f32(out, n, seed, stream_id, (cudaStream_t)stream);
+}
+
+int ndt1_pad_pack(const void* src, const int64_t* offsets, void* dst, int B, int P, int inner, int elem_size, int side_left, int full,
+                  double value, void* stream) {
+  return k_pad_pack(src, (const long long*)offsets, dst, B, P, inner, elem_size, side_left, full, value, (cudaStream_t)stream);
+}
+
+size_t ndt1_ctc_workspace_bytes(int B, int L, int S) { return k_ctc_workspace_floats(B, L, S) * sizeof(float); }
+
+int ndt1_ctc_loss(const float* logits, float* logp, const int64_t* targets, const int64_t* input_lengths, const int64_t* target_lengths,
+                  int B, int L, int V, int S, int blank, int zero_infinity, void* workspace, float* nll, float* loss, float* dlogits,
+                  const float* dloss, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  NDT1_TRY(k_log_softmax(logits, logp, (long long)B * L, V, s));
+  return k_ctc_fwd_bwd(logp, (const long long*)targets, (const long long*)input_lengths, (const long long*)target_lengths, B, L, V, S,
+                       blank, zero_infinity, (float*)workspace, nll, loss, dlogits, dloss, s);
+}
+int ndt1_ctc_greedy_decode(const float* logp, int B, int L, int V, int blank, int64_t* out_ids, int64_t* out_len, void* stream) {
+  return k_ctc_greedy_decode(logp, B, L, V, blank, (long long*)out_ids, (long long*)out_len, (cudaStream_t)stream);
+}
+
+int ndt1_recon_loss(const float* pred, const float* target, float* dpred, const int64_t* targets_mask, const int64_t* pad_mask, int B,
+                    int T, int N, int loss_kind, int shift_by_one, int relu_out, float* loss, int64_t* count, const float* dloss,
+                    void* stream) {
+  return k_recon_loss(pred, target, dpred, (const long long*)targets_mask, (const long long*)pad_mask, B, T, N, loss_kind, shift_by_one,
+                      relu_out, loss, (long long*)count, dloss, (cudaStream_t)stream);
+}
+
+int ndt1_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int64_t rows, int H,
+                       float eps, void* stream) {
+  return k_layernorm_fwd<float>(x, gamma, beta, y, mean, rstd, rows, H, eps, (cudaStream_t)stream);
+}
+
+int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K, int act, int precision,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  GemmProblem p;
+  p.mode = GEMM_NT; p.M = M; p.N = N; p.nb_out = 1; p.nchunk = 1; p.chunk_k = K;
+  p.a_row_shift = p.a_col_shift = p.b_row_shift = p.b_col_shift = 0; p.b_chunk_n = N; p.split_k = 1;
+  p.epi = gemm_epilogue_default();
+  p.epi.out = y; p.epi.ldc = N; p.epi.bias = bias;
+  p.epi.act = act == NDT1_ACT_SOFTSIGN ? ACT_SOFTSIGN : act == NDT1_ACT_GELU ? ACT_GELU : act == NDT1_ACT_RELU ? ACT_RELU : ACT_NONE;
+  if (precision == NDT1_PRECISION_FP32) {
+    p.A = {x, 0, 1, M, K, K}; p.B = {w, 0, 1, N, K, K};
+    return gemm_simt_launch(p, 0, s);
+  }
+  const int ldk = (K + 7) / 8 * 8;
+  const size_t need = ((size_t)M * ldk + (size_t)N * ldk) * sizeof(bf16) + 512;
+  NDT1_REQUIRE(workspace && workspace_bytes >= need, "linear_fwd: bf16 mode needs %zu workspace bytes", need);
+  bf16* xa = (bf16*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  bf16* wa = (bf16*)(((uintptr_t)(xa + (size_t)M * ldk) + 255) & ~(uintptr_t)255);
+  NDT1_TRY(k_cast_f32_bf16(x, xa, M, K, K, ldk, s));
+  NDT1_TRY(k_cast_f32_bf16(w, wa, N, K, K, ldk, s));
+  p.A = {xa, 0, 1, M, K, ldk}; p.B = {wa, 0, 1, N, K, ldk};
+  return gemm_tc_launch(p, s);
+}
+
+int ndt1_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  return k_adamw(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream);
+}
+
+namespace {
+__global__ void dropout_scales_kernel(float* out, long long n, float p, unsigned long long seed, unsigned long long site) {
+  const uint32_t thr = drop_threshold(p);
+  const float ik = 1.0f / (1.0f - p);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = drop_scale_1(seed, site, (unsigned long long)i, thr, ik);
+}
+}  // namespace
+
+int ndt1_dropout_scales(float* out, int64_t n, float p, uint64_t seed, uint64_t site, void* stream) {
+  if (n == 0) return 0;
+  NDT1_REQUIRE(p >= 0.f && p < 1.f, "dropout_scales: p must be in [0,1)");
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  dropout_scales_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, n, p, seed, site);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

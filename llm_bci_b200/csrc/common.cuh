@@ -25,7 +25,13 @@ void ndt1_set_error(const char* fmt, ...);
     }                                                                           \
   } while (0)
 
-#define NDT1_CHECK_LAUNCH() NDT1_CUDA_CHECK(cudaGetLastError())
+// every kernel launch goes through this macro, so the counter is exact
+extern thread_local long long g_ndt1_launches;
+#define NDT1_CHECK_LAUNCH()                                                     \
+  do {                                                                          \
+    ++g_ndt1_launches;                                                          \
+    NDT1_CUDA_CHECK(cudaGetLastError());                                        \
+  } while (0)
 
 #define NDT1_REQUIRE(cond, ...)                                                 \
   do {                                                                          \

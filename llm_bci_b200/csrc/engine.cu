@@ -1,0 +1,648 @@
+// The NDT1 encoder + head engine: NeuralEncoder.forward after the masker,
+// the decoder and the loss (models/ndt1.py:429-450, 542-589) and the whole
+// backward, as two C-ABI calls that only enqueue kernels on the caller's
+// stream.  Activations needed by the backward live in one arena sized at
+// creation (bump allocated, 256-byte aligned): nothing is allocated, freed or
+// synchronised per step, so a step can be captured in a CUDA graph.
+//
+// Data layout in HBM (T = float in NDT1_PRECISION_FP32, bf16 in _BF16):
+//   residual stream   x[2*layers+1]  fp32 (B*L, H)      LayerNorm inputs, kept for backward
+//   LN outputs        h1[l], h2[l], hn  T (B*L, H)      GEMM A operands / wgrad B operands
+//   qkv[l]            T (B*L, 3H)  q|k|v packed so one GEMM (N = 3H) produces it
+//   att[l], attd[l]   T (B*L, H)   attention output before / after output dropout
+//   u[l], g[l]        T (B*L, I)   MLP pre-activation / activation
+//   emb               T (B*T, D)   softsign(embed_spikes(x)); the stack projection
+//                                  reads it as (B, T/stride, stride*D) shifted windows
+//   bf16 mode keeps bf16 copies of the weights (QKV concatenated) refreshed per forward.
+#include "../../include/ndt1_b200.h"
+#include "kernels.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+namespace {
+
+constexpr int kUnbounded = 1 << 29;
+
+struct Arena {
+  char* base = nullptr; size_t cap = 0, off = 0;
+  template <typename U> U* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    U* p = (U*)(base ? base + off : nullptr);
+    off += n * sizeof(U);
+    return p;
+  }
+};
+
+template <typename T> struct IsBf16 { static constexpr int v = 0; };
+template <> struct IsBf16<bf16> { static constexpr int v = 1; };
+
+}  // namespace
+
+struct ndt1_engine {
+  ndt1_config c;
+  long long launches = 0;
+  cudaEvent_t stage_ev[NDT1_MAX_LAYERS + 2] = {};   // gradient stages of the last backward, in completion order
+  int n_stages() const { return c.n_layers + 2; }
+  virtual ~ndt1_engine() {}
+  virtual int forward(const ndt1_tensors* P, const ndt1_batch* b, const ndt1_outputs* o, cudaStream_t s) = 0;
+  virtual int backward(const ndt1_tensors* P, const ndt1_tensors* G, const float* dloss, cudaStream_t s) = 0;
+  virtual size_t arena_bytes() const = 0;
+  int out_len(int T) const { return c.stack_active ? (T - c.stack_size) / c.stack_stride + 1 : T; }
+};
+
+namespace {
+
+template <typename T>
+struct Engine : ndt1_engine {
+  static constexpr int kBf16 = IsBf16<T>::v;
+  Arena ar;
+  bool force_simt = false;
+  int n_prefix = 0;
+  // arena views ------------------------------------------------------------
+  T* xin = nullptr; int ldN = 0;
+  T* emb = nullptr;
+  std::vector<float*> xs;           // 2L+1 residual snapshots
+  std::vector<float*> mean, rstd;   // 2L+1
+  std::vector<T*> h1, h2, qkv, att, attd, u, g;
+  std::vector<float*> lse;
+  T* hn = nullptr; T* fac = nullptr; T* fpre = nullptr;
+  float* logits = nullptr; float* logp = nullptr; float* dlogits = nullptr; float* nll = nullptr; float* ctc_ws = nullptr;
+  long long* key_valid = nullptr; long long* out_lens = nullptr;
+  float* feat32 = nullptr;
+  // backward scratch
+  float* dX = nullptr; T* dY = nullptr; T* dH = nullptr; T* dU = nullptr; T* dA = nullptr; T* dqkv = nullptr; T* dlog = nullptr;
+  T* dEmb = nullptr; T* dhn = nullptr; T* dfac = nullptr;
+  float* delta = nullptr; float* ln_part = nullptr;
+  int ldV = 0;
+  // bf16 weight copies
+  bf16* w_emb = nullptr; bf16* w_proj = nullptr; bf16* w_fac = nullptr; bf16* w_dec = nullptr;
+  std::vector<bf16*> w_qkv, w_o, w_up, w_down;
+  std::vector<float*> b_qkv;
+  // state of the last forward
+  int B = 0, Tn = 0, Tp = 0, L = 0, S = 0, training = 0; unsigned long long seed = 0; bool have_fwd = false;
+  const float* spikes_ptr = nullptr; const long long* ts_ptr = nullptr; const long long* block_ptr = nullptr; const long long* day_ptr = nullptr;
+
+  size_t arena_bytes() const override { return ar.cap; }
+
+  void carve() {
+    const ndt1_config& k = c;
+    const int Bm = k.max_batch, Tm = k.max_T;
+    const int Lm = n_prefix + out_len(Tm);
+    const long long Mm = (long long)Bm * Lm, MT = (long long)Bm * Tm;
+    const int H = k.hidden, I = k.inter, D = k.input_dim, NL = k.n_layers;
+    const int Hout = k.factors_active ? k.factors_size : H;
+    ldN = (k.n_channels + 7) / 8 * 8;
+    ldV = (k.n_outputs + 7) / 8 * 8;
+    const long long Mout = (k.method == NDT1_METHOD_CTC) ? (long long)Bm * out_len(Tm) : Mm;
+    if (kBf16) xin = ar.take<T>(MT * ldN);
+    emb = ar.take<T>(MT * D);
+    xs.resize(2 * NL + 1); mean.resize(2 * NL + 1); rstd.resize(2 * NL + 1);
+    for (int i = 0; i < 2 * NL + 1; ++i) { xs[i] = ar.take<float>(Mm * H); mean[i] = ar.take<float>(Mm); rstd[i] = ar.take<float>(Mm); }
+    h1.resize(NL); h2.resize(NL); qkv.resize(NL); att.resize(NL); attd.resize(NL); u.resize(NL); g.resize(NL); lse.resize(NL);
+    for (int l = 0; l < NL; ++l) {
+      h1[l] = ar.take<T>(Mm * H); h2[l] = ar.take<T>(Mm * H); qkv[l] = ar.take<T>(Mm * 3 * H);
+      att[l] = ar.take<T>(Mm * H); attd[l] = (k.p_transformer > 0.f) ? ar.take<T>(Mm * H) : att[l];
+      u[l] = ar.take<T>(Mm * I); g[l] = ar.take<T>(Mm * I); lse[l] = ar.take<float>((long long)Bm * k.n_heads * Lm);
+    }
+    hn = ar.take<T>(Mm * H);
+    if (k.factors_active) { fac = ar.take<T>(Mm * Hout); fpre = ar.take<T>(Mm * Hout); dfac = ar.take<T>(Mm * Hout); }
+    logits = ar.take<float>(Mout * k.n_outputs); logp = ar.take<float>(Mout * k.n_outputs); dlogits = ar.take<float>(Mout * k.n_outputs);
+    nll = ar.take<float>(Bm);
+    if (k.method == NDT1_METHOD_CTC) ctc_ws = ar.take<float>(k_ctc_workspace_floats(Bm, out_len(Tm), k.max_targets));
+    key_valid = ar.take<long long>(Mm); out_lens = ar.take<long long>(Bm);
+    feat32 = ar.take<float>(Mm * Hout);
+    dX = ar.take<float>(Mm * H); dY = ar.take<T>(Mm * H); dH = ar.take<T>(Mm * H); dU = ar.take<T>(Mm * I); dA = ar.take<T>(Mm * H);
+    dqkv = ar.take<T>(Mm * 3 * H); dlog = ar.take<T>(Mout * ldV); dEmb = ar.take<T>(MT * D); dhn = ar.take<T>(Mm * H);
+    delta = ar.take<float>((long long)Bm * k.n_heads * Lm);
+    ln_part = (float*)ar.take<char>(k_layernorm_bwd_partials_bytes(H));
+    if (kBf16) {
+      const int KP = k.stack_active ? k.stack_size * D : D;
+      w_emb = ar.take<bf16>((long long)D * ldN); w_proj = ar.take<bf16>((long long)H * KP);
+      if (k.factors_active) w_fac = ar.take<bf16>((long long)Hout * H);
+      w_dec = ar.take<bf16>((long long)k.n_outputs * Hout);
+      w_qkv.resize(NL); w_o.resize(NL); w_up.resize(NL); w_down.resize(NL); b_qkv.resize(NL);
+      for (int l = 0; l < NL; ++l) {
+        w_qkv[l] = ar.take<bf16>(3LL * H * H); w_o[l] = ar.take<bf16>((long long)H * H);
+        w_up[l] = ar.take<bf16>((long long)I * H); w_down[l] = ar.take<bf16>((long long)H * I);
+        b_qkv[l] = ar.take<float>(3 * H);
+      }
+    }
+  }
+
+  int init() {
+    n_prefix = (c.block_token ? 1 : 0) + (c.day_token ? 1 : 0);
+    const char* fs = getenv("NDT1_FORCE_SIMT");
+    force_simt = fs && fs[0] == '1';
+    carve();                       // dry run: sizes only
+    ar.cap = ar.off + 256; ar.off = 0;
+    NDT1_CUDA_CHECK(cudaMalloc((void**)&ar.base, ar.cap));
+    NDT1_CUDA_CHECK(cudaMemset(ar.base, 0, ar.cap));
+    carve();
+    for (int i = 0; i < n_stages(); ++i) NDT1_CUDA_CHECK(cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming));
+    if (kBf16 && !force_simt) NDT1_TRY(gemm_tc_init());
+    return 0;
+  }
+  ~Engine() override {
+    for (int i = 0; i < NDT1_MAX_LAYERS + 2; ++i) if (stage_ev[i]) cudaEventDestroy(stage_ev[i]);
+    if (ar.base) cudaFree(ar.base);
+  }
+
+  // ---- GEMM helpers -------------------------------------------------------
+  int run(GemmProblem& p, cudaStream_t s) {
+    if (kBf16 && !force_simt) return gemm_tc_launch(p, s);
+    return gemm_simt_launch(p, kBf16, s);
+  }
+  static GemmOperand op(const void* ptr, long long bs, int nb, int rows, int cols, int ld) {
+    GemmOperand o; o.ptr = ptr; o.batch_stride = bs; o.nbatch = nb; o.rows = rows; o.cols = cols; o.ld = ld; return o;
+  }
+  static GemmProblem prob(int mode, int M, int N, int K) {
+    GemmProblem p;
+    p.mode = mode; p.M = M; p.N = N; p.nb_out = 1; p.nchunk = 1; p.chunk_k = K;
+    p.a_row_shift = p.a_col_shift = p.b_row_shift = p.b_col_shift = 0; p.b_chunk_n = N; p.split_k = 1;
+    p.epi = gemm_epilogue_default();
+    return p;
+  }
+  // y[M,N] = epi(a[M,K] w[N,K]^T)
+  int linear_fwd(const T* a, int lda, const void* w, int ldw, int M, int N, int K, GemmEpilogue e, cudaStream_t s) {
+    GemmProblem p = prob(GEMM_NT, M, N, K);
+    p.A = op(a, 0, 1, M, K, lda); p.B = op(w, 0, 1, N, K, ldw); p.epi = e;
+    return run(p, s);
+  }
+  // dx[M,K] = epi(dy[M,N] w[N,K])
+  int linear_dgrad(const T* dy, int lddy, const void* w, int ldw, int M, int N, int K, GemmEpilogue e, cudaStream_t s) {
+    GemmProblem p = prob(GEMM_NN, M, K, N);
+    p.A = op(dy, 0, 1, M, N, lddy); p.B = op(w, 0, 1, N, K, ldw); p.epi = e;
+    return run(p, s);
+  }
+  // dw[N,K] += dy[M,N]^T a[M,K]
+  int linear_wgrad(const T* dy, int lddy, const T* a, int lda, float* dw, int lddw, int M, int N, int K, cudaStream_t s) {
+    if (!dw) return 0;
+    GemmProblem p = prob(GEMM_TN, N, K, M);
+    p.A = op(dy, 0, 1, M, N, lddy); p.B = op(a, 0, 1, M, K, lda);
+    p.epi.out = dw; p.epi.ldc = lddw; p.epi.accumulate = 1;
+    p.split_k = pick_split(ndt1_cdiv(N, 128) * ndt1_cdiv(K, K > 128 ? 256 : (K > 64 ? 128 : 64)), ndt1_cdiv(M, 64));
+    return run(p, s);
+  }
+  // split the reduction so that tiles*split fills whole waves of 148 SMs
+  int pick_split(int tiles, int kblocks) const {
+    if (!(kBf16 && !force_simt)) { int sp = 148 / (tiles > 0 ? tiles : 1); return sp > 8 ? 8 : (sp < 1 ? 1 : sp); }
+    int best = 1; double best_eff = 0.0;
+    for (int sp = 1; sp <= 64 && sp * 4 <= kblocks; ++sp) {
+      const int t = tiles * sp, waves = (t + 147) / 148;
+      const double eff = (double)t / (waves * 148.0);
+      if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
+    }
+    return best;
+  }
+  const void* W(const float* master, const bf16* copy) const { return kBf16 ? (const void*)copy : (const void*)master; }
+
+  unsigned long long site_attn_p(int l) const { return 1 + 4ull * l; }
+  unsigned long long site_attn_o(int l) const { return 2 + 4ull * l; }
+  unsigned long long site_mlp(int l) const { return 3 + 4ull * l; }
+
+  int act_code(int a) const { return a == NDT1_ACT_SOFTSIGN ? ACT_SOFTSIGN : a == NDT1_ACT_GELU ? ACT_GELU : a == NDT1_ACT_RELU ? ACT_RELU : ACT_NONE; }
+  // derivative selector given what the forward kept (out = activation value, in = pre-activation)
+  int dact_from_out(int a) const { return a == NDT1_ACT_SOFTSIGN ? DACT_SOFTSIGN_FROM_OUT : a == NDT1_ACT_RELU ? DACT_RELU_FROM_OUT : DACT_NONE; }
+
+  void ctx(int& f, int& b) const {
+    if (c.context_forward == -2 && c.context_backward == -2) { f = kUnbounded; b = kUnbounded; return; }
+    f = c.context_forward >= -1 ? c.context_forward : kUnbounded;
+    b = c.context_backward >= -1 ? c.context_backward : kUnbounded;
+  }
+
+  // ---- forward ------------------------------------------------------------
+  int forward(const ndt1_tensors* P, const ndt1_batch* bt, const ndt1_outputs* o, cudaStream_t s) override {
+    const ndt1_config& k = c;
+    const long long launches0 = g_ndt1_launches;
+    have_fwd = false;
+    NDT1_REQUIRE(bt->B >= 0 && bt->B <= k.max_batch, "engine: batch %d exceeds max_batch %d", bt->B, k.max_batch);
+    NDT1_REQUIRE(bt->T <= k.max_T, "engine: %d bins exceed max_T %d", bt->T, k.max_T);
+    NDT1_REQUIRE(!k.stack_active || bt->T >= k.stack_size, "engine: %d bins are fewer than the stack size %d", bt->T, k.stack_size);
+    NDT1_REQUIRE(bt->T <= k.max_F || !k.pos, "engine: %d bins exceed max_F %d", bt->T, k.max_F);
+    NDT1_REQUIRE(k.method != NDT1_METHOD_CTC || bt->S <= k.max_targets, "engine: %d targets exceed max_targets %d", bt->S, k.max_targets);
+    B = bt->B; Tn = bt->T; Tp = out_len(Tn); L = n_prefix + Tp; S = bt->S; training = bt->training; seed = bt->seed;
+    spikes_ptr = bt->spikes; ts_ptr = (const long long*)bt->spikes_timestamp; block_ptr = (const long long*)bt->block_idx; day_ptr = (const long long*)bt->day_idx;
+    if (B == 0) { have_fwd = true; return 0; }
+    const int H = k.hidden, I = k.inter, D = k.input_dim, N = k.n_channels, NL = k.n_layers, V = k.n_outputs;
+    const int Hout = k.factors_active ? k.factors_size : H;
+    const long long M = (long long)B * L, MT = (long long)B * Tn;
+    const float pe = training ? k.p_embed : 0.f, ptr_ = training ? k.p_transformer : 0.f;
+
+    // 0. precision staging: bf16 copies of the weights and of the input
+    if (kBf16) {
+      NDT1_TRY(k_cast_f32_bf16(bt->spikes, (bf16*)xin, MT, N, N, ldN, s));
+      NDT1_TRY(k_cast_f32_bf16(P->embed_w, w_emb, D, N, N, ldN, s));
+      const int KP = k.stack_active ? k.stack_size * D : D;
+      NDT1_TRY(k_cast_f32_bf16(P->proj_w, w_proj, H, KP, KP, KP, s));
+      for (int l = 0; l < NL; ++l) {
+        const auto& q = P->layer[l];
+        NDT1_TRY(k_cast_f32_bf16(q.q_w, w_qkv[l], H, H, H, H, s));
+        NDT1_TRY(k_cast_f32_bf16(q.k_w, w_qkv[l] + (long long)H * H, H, H, H, H, s));
+        NDT1_TRY(k_cast_f32_bf16(q.v_w, w_qkv[l] + 2LL * H * H, H, H, H, H, s));
+        NDT1_TRY(k_cast_f32_bf16(q.o_w, w_o[l], H, H, H, H, s));
+        NDT1_TRY(k_cast_f32_bf16(q.up_w, w_up[l], I, H, H, H, s));
+        NDT1_TRY(k_cast_f32_bf16(q.down_w, w_down[l], H, I, I, I, s));
+        if (k.attention_bias) {
+          NDT1_CUDA_CHECK(cudaMemcpyAsync(b_qkv[l], q.q_b, H * 4, cudaMemcpyDeviceToDevice, s));
+          NDT1_CUDA_CHECK(cudaMemcpyAsync(b_qkv[l] + H, q.k_b, H * 4, cudaMemcpyDeviceToDevice, s));
+          NDT1_CUDA_CHECK(cudaMemcpyAsync(b_qkv[l] + 2 * H, q.v_b, H * 4, cudaMemcpyDeviceToDevice, s));
+        }
+      }
+      if (k.factors_active) NDT1_TRY(k_cast_f32_bf16(P->factors_w, w_fac, Hout, H, H, H, s));
+      NDT1_TRY(k_cast_f32_bf16(P->dec_w, w_dec, V, Hout, Hout, Hout, s));
+    }
+    const T* x_in = kBf16 ? xin : (const T*)bt->spikes;
+    const int ldx = kBf16 ? ldN : N;
+
+    // 1. channel embedding + activation   (models/ndt1.py:170-176)
+    {
+      GemmEpilogue e = gemm_epilogue_default();
+      e.out = emb; e.out_bf16 = kBf16; e.ldc = D; e.bias = k.embed_bias ? P->embed_b : nullptr; e.act = act_code(k.embed_act);
+      NDT1_TRY(linear_fwd(x_in, ldx, W(P->embed_w, w_emb), kBf16 ? ldN : N, (int)MT, D, N, e, s));
+    }
+    // 2. stack projection / projection + position table + embedding dropout  (models/ndt1.py:179-203)
+    float* x0 = xs[0];
+    {
+      GemmEpilogue e = gemm_epilogue_default();
+      e.out = x0 + (long long)n_prefix * H; e.out_bf16 = 0; e.ldc = H; e.c_batch_stride = (long long)L * H;
+      e.bias = P->proj_b;
+      if (k.pos) { e.gather_tab = P->pos_w; e.gather_idx = ts_ptr; e.gather_idx_stride = Tn; e.gather_ld = H; }
+      if (pe > 0.f && n_prefix == 0) { e.drop_p = pe; e.drop_seed = seed; e.drop_stream = 0; }
+      GemmProblem p;
+      if (k.stack_active) {
+        NDT1_REQUIRE(k.stack_size % k.stack_stride == 0, "engine: stack size %d must be a multiple of the stride %d", k.stack_size, k.stack_stride);
+        const int K4 = k.stack_stride * D, nch = k.stack_size / k.stack_stride;
+        p = prob(GEMM_NT, Tp, H, K4);
+        p.nb_out = B; p.nchunk = nch; p.a_row_shift = 1; p.b_col_shift = K4;
+        p.A = op(emb, (long long)Tn * D, B, Tn / k.stack_stride, K4, K4);
+        p.B = op(W(P->proj_w, w_proj), 0, 1, H, nch * K4, nch * K4);
+      } else {
+        p = prob(GEMM_NT, Tp, H, D);
+        p.nb_out = B;
+        p.A = op(emb, (long long)Tn * D, B, Tn, D, D);
+        p.B = op(W(P->proj_w, w_proj), 0, 1, H, D, D);
+      }
+      p.epi = e;
+      NDT1_TRY(run(p, s));
+      int slot = 0;
+      if (k.day_token) { NDT1_TRY(k_token_rows(P->day_emb, day_ptr, x0, B, L, H, slot, s)); ++slot; }
+      if (k.block_token) { NDT1_TRY(k_token_rows(P->block_emb, block_ptr, x0, B, L, H, slot, s)); ++slot; }
+      if (pe > 0.f && n_prefix > 0) NDT1_TRY(k_grad_prep<float>(x0, x0, M, H, pe, seed, 0, nullptr, nullptr, 0, 1, 0, 0, s));
+    }
+    NDT1_TRY(k_stack_mask((const long long*)bt->spikes_mask, key_valid, B, Tn, Tp, k.stack_active ? k.stack_size : 0, k.stack_active ? k.stack_stride : 1,
+                          n_prefix, s));
+    if (o->out_mask) NDT1_CUDA_CHECK(cudaMemcpyAsync(o->out_mask, key_valid, M * 8, cudaMemcpyDeviceToDevice, s));
+
+    // 3. transformer layers  (models/ndt1.py:317-330)
+    NDT1_REQUIRE(!k.use_rope, "engine: use_rope is not implemented in this build");
+    int cf, cb; ctx(cf, cb);
+    for (int l = 0; l < NL; ++l) {
+      const auto& q = P->layer[l];
+      float* xa = xs[2 * l]; float* xm = xs[2 * l + 1]; float* xo = xs[2 * l + 2];
+      NDT1_TRY(k_layernorm_fwd<T>(xa, q.ln1_w, q.ln1_b, h1[l], mean[2 * l], rstd[2 * l], M, H, 1e-5f, s));
+      if (kBf16) {
+        GemmEpilogue e = gemm_epilogue_default();
+        e.out = qkv[l]; e.out_bf16 = 1; e.ldc = 3 * H; e.bias = k.attention_bias ? b_qkv[l] : nullptr;
+        NDT1_TRY(linear_fwd(h1[l], H, w_qkv[l], H, (int)M, 3 * H, H, e, s));
+      } else {
+        const float* ws[3] = {q.q_w, q.k_w, q.v_w}; const float* bs[3] = {q.q_b, q.k_b, q.v_b};
+        for (int j = 0; j < 3; ++j) {
+          GemmEpilogue e = gemm_epilogue_default();
+          e.out = qkv[l] + (long long)j * H; e.out_bf16 = 0; e.ldc = 3 * H; e.bias = k.attention_bias ? bs[j] : nullptr;
+          NDT1_TRY(linear_fwd(h1[l], H, ws[j], H, (int)M, H, H, e, s));
+        }
+      }
+      AttnParams ap;
+      ap.qkv = qkv[l]; ap.out = att[l]; ap.out_drop = (ptr_ > 0.f) ? attd[l] : att[l]; ap.lse = lse[l]; ap.key_valid = key_valid;
+      ap.B = B; ap.L = L; ap.H = H; ap.nh = k.n_heads; ap.hd = H / k.n_heads; ap.ctx_fwd = cf; ap.ctx_bwd = cb;
+      ap.scale = 1.0f / sqrtf((float)(H / k.n_heads)); ap.p_attn = ptr_; ap.p_out = ptr_;
+      ap.seed = seed; ap.stream_attn = site_attn_p(l); ap.stream_out = site_attn_o(l);
+      ap.dout = nullptr; ap.dqkv = nullptr; ap.delta = nullptr;
+      NDT1_TRY(k_attention_fwd<T>(ap, s));
+      {
+        GemmEpilogue e = gemm_epilogue_default();
+        e.out = xm; e.ldc = H; e.bias = k.attention_bias ? q.o_b : nullptr; e.resid = xa;
+        NDT1_TRY(linear_fwd((const T*)ap.out_drop, H, W(q.o_w, kBf16 ? w_o[l] : nullptr), H, (int)M, H, H, e, s));
+      }
+      NDT1_TRY(k_layernorm_fwd<T>(xm, q.ln2_w, q.ln2_b, h2[l], mean[2 * l + 1], rstd[2 * l + 1], M, H, 1e-5f, s));
+      {
+        GemmEpilogue e = gemm_epilogue_default();
+        e.out = g[l]; e.out_bf16 = kBf16; e.ldc = I; e.bias = k.mlp_bias ? q.up_b : nullptr; e.act = act_code(k.mlp_act);
+        e.out2 = u[l]; e.out2_bf16 = kBf16;
+        NDT1_TRY(linear_fwd(h2[l], H, W(q.up_w, kBf16 ? w_up[l] : nullptr), H, (int)M, I, H, e, s));
+      }
+      {
+        GemmEpilogue e = gemm_epilogue_default();
+        e.out = xo; e.ldc = H; e.bias = k.mlp_bias ? q.down_b : nullptr; e.resid = xm;
+        if (ptr_ > 0.f) { e.drop_p = ptr_; e.drop_seed = seed; e.drop_stream = site_mlp(l); }
+        NDT1_TRY(linear_fwd(g[l], I, W(q.down_w, kBf16 ? w_down[l] : nullptr), I, (int)M, H, I, e, s));
+      }
+    }
+    // 4. output norm, factors, head   (models/ndt1.py:442-450, 545)
+    NDT1_TRY(k_layernorm_fwd<T>(xs[2 * NL], P->out_norm_w, P->out_norm_b, hn, mean[2 * NL], rstd[2 * NL], M, H, 1e-5f, s));
+    const T* head_in = hn; int head_ld = H;
+    if (k.factors_active) {
+      NDT1_REQUIRE(!(training && k.p_factors > 0.f), "engine: dropout in the factors projection is not implemented in this build");
+      GemmEpilogue e = gemm_epilogue_default();
+      e.out = fac; e.out_bf16 = kBf16; e.ldc = Hout; e.bias = k.factors_bias ? P->factors_b : nullptr; e.act = act_code(k.factors_act);
+      e.out2 = fpre; e.out2_bf16 = kBf16;
+      NDT1_TRY(linear_fwd(hn, H, W(P->factors_w, w_fac), H, (int)M, Hout, H, e, s));
+      head_in = fac; head_ld = Hout;
+    }
+    if (o->features) {
+      // fp32 copy of the encoder output without the prefix tokens
+      if (k.factors_active) {
+        NDT1_TRY((k_scale_cast_features(head_in, feat32, M, Hout, s)));
+      } else {
+        NDT1_TRY(k_layernorm_fwd<float>(xs[2 * NL], P->out_norm_w, P->out_norm_b, feat32, mean[2 * NL], rstd[2 * NL], M, H, 1e-5f, s));
+      }
+      NDT1_CUDA_CHECK(cudaMemcpy2DAsync(o->features, (size_t)Tp * Hout * 4, feat32 + (long long)n_prefix * Hout, (size_t)L * Hout * 4,
+                                        (size_t)Tp * Hout * 4, B, cudaMemcpyDeviceToDevice, s));
+    }
+    if (bt->encoder_only) {
+      NDT1_CUDA_CHECK(cudaMemsetAsync(o->loss, 0, sizeof(float), s));
+      launches = g_ndt1_launches - launches0;
+      return 0;
+    }
+    {
+      GemmProblem p = prob(GEMM_NT, Tp, V, Hout);
+      p.nb_out = B;
+      p.A = op(head_in + (long long)n_prefix * head_ld, (long long)L * head_ld, B, Tp, Hout, head_ld);
+      p.B = op(W(P->dec_w, w_dec), 0, 1, V, Hout, Hout);
+      p.epi.out = logits; p.epi.ldc = V; p.epi.c_batch_stride = (long long)Tp * V; p.epi.bias = P->dec_b;
+      NDT1_TRY(run(p, s));
+    }
+    // 5. loss   (models/ndt1.py:548-589)
+    NDT1_CUDA_CHECK(cudaMemsetAsync(o->loss, 0, sizeof(float), s));
+    NDT1_TRY(k_stacked_lens((const long long*)bt->spikes_lengths, out_lens, B, k.stack_active, k.stack_size, k.stack_stride, s));
+    if (o->out_lengths) NDT1_CUDA_CHECK(cudaMemcpyAsync(o->out_lengths, out_lens, B * 8, cudaMemcpyDeviceToDevice, s));
+    const long long Mo = (long long)B * Tp;
+    if (k.method == NDT1_METHOD_CTC) {
+      NDT1_REQUIRE(bt->targets && bt->targets_lengths, "engine: ctc needs targets and targets_lengths");
+      NDT1_TRY(k_log_softmax(logits, logp, Mo, V, s));
+      NDT1_TRY(k_ctc_fwd_bwd(logp, (const long long*)bt->targets, out_lens, (const long long*)bt->targets_lengths, B, Tp, V, S, k.blank_id, k.zero_infinity, ctc_ws, nll,
+                             o->loss, bt->need_backward ? dlogits : nullptr, nullptr, s));
+      if (o->preds) NDT1_CUDA_CHECK(cudaMemcpyAsync(o->preds, logp, Mo * V * 4, cudaMemcpyDeviceToDevice, s));
+      if (o->n_examples) NDT1_TRY(k_set_i64((long long*)o->n_examples, B, s));
+    } else {
+      NDT1_REQUIRE(bt->recon_targets, "engine: mlm/autoregressive need the original spikes as targets");
+      NDT1_REQUIRE(k.method != NDT1_METHOD_MLM || bt->targets_mask, "engine: mlm needs the masker's targets_mask");
+      NDT1_REQUIRE(n_prefix == 0 && !k.stack_active, "engine: ssl methods need unstacked inputs without prefix tokens");
+      if (k.decoder_relu) NDT1_TRY(k_relu_inplace(logits, Mo * V, s));
+      if (o->n_examples) NDT1_CUDA_CHECK(cudaMemsetAsync(o->n_examples, 0, 8, s));
+      NDT1_TRY(k_recon_loss(logits, bt->recon_targets, bt->need_backward ? dlogits : nullptr, (const long long*)bt->targets_mask, key_valid, B,
+                            Tn, V, k.loss_kind, k.method == NDT1_METHOD_AUTOREGRESSIVE, k.decoder_relu, o->loss, (long long*)o->n_examples,
+                            nullptr, s));
+      if (o->preds) NDT1_CUDA_CHECK(cudaMemcpyAsync(o->preds, logits, Mo * V * 4, cudaMemcpyDeviceToDevice, s));
+      if (o->loss_mask && k.method == NDT1_METHOD_MLM)
+        NDT1_TRY(k_and_mask((const long long*)bt->targets_mask, key_valid, (long long*)o->loss_mask, B, Tn, V, s));
+    }
+    have_fwd = bt->need_backward != 0;
+    launches = g_ndt1_launches - launches0;
+    return 0;
+  }
+
+  int k_scale_cast_features(const T* in, float* out, long long rows, int cols, cudaStream_t s) {
+    // T -> fp32 copy (only used for the optional `features` output with an active factors projection)
+    GemmEpilogue e = gemm_epilogue_default();
+    (void)e;
+    if (!kBf16) { NDT1_CUDA_CHECK(cudaMemcpyAsync(out, in, rows * cols * 4, cudaMemcpyDeviceToDevice, s)); return 0; }
+    NDT1_REQUIRE(false, "engine: `features` with an active factors projection needs NDT1_PRECISION_FP32 in this build");
+    return 0;
+  }
+
+  // ---- backward -----------------------------------------------------------
+  int backward(const ndt1_tensors* P, const ndt1_tensors* G, const float* dloss, cudaStream_t s) override {
+    const ndt1_config& k = c;
+    NDT1_REQUIRE(have_fwd, "engine: backward without a matching forward (need_backward = 1)");
+    const long long launches0 = g_ndt1_launches;
+    if (B == 0) return 0;
+    const int H = k.hidden, I = k.inter, D = k.input_dim, N = k.n_channels, NL = k.n_layers, V = k.n_outputs;
+    const int Hout = k.factors_active ? k.factors_size : H;
+    const long long M = (long long)B * L, MT = (long long)B * Tn, Mo = (long long)B * Tp;
+    const float pe = training ? k.p_embed : 0.f, ptr_ = training ? k.p_transformer : 0.f;
+
+    // head
+    NDT1_TRY(k_scale_cast_pad<T>(dlogits, dlog, Mo, V, ldV, dloss, s));
+    if (G->dec_b) NDT1_TRY(k_colsum<T>(dlog, G->dec_b, Mo, V, ldV, s));
+    const T* head_in = k.factors_active ? fac : hn; const int head_ld = k.factors_active ? Hout : H;
+    T* d_head_in = k.factors_active ? dfac : dhn;
+    if (n_prefix > 0) NDT1_CUDA_CHECK(cudaMemsetAsync(d_head_in, 0, M * head_ld * sizeof(T), s));
+    if (G->dec_w) {
+      GemmProblem p = prob(GEMM_TN, V, Hout, Tp);
+      p.nchunk = B;
+      p.A = op(dlog, (long long)Tp * ldV, B, Tp, V, ldV);
+      p.B = op(head_in + (long long)n_prefix * head_ld, (long long)L * head_ld, B, Tp, Hout, head_ld);
+      p.epi.out = G->dec_w; p.epi.ldc = Hout; p.epi.accumulate = 1;
+      if (n_prefix == 0) {  // rows are contiguous across trials: one long reduction
+        p.nchunk = 1; p.chunk_k = (int)Mo;
+        p.A = op(dlog, 0, 1, (int)Mo, V, ldV); p.B = op(head_in, 0, 1, (int)Mo, Hout, head_ld);
+      }
+      const int kb = p.nchunk * ndt1_cdiv(p.chunk_k, 64);
+      p.split_k = kb >= 32 ? 16 : 1;
+      if (!(kBf16 && !force_simt) && p.split_k > 8) p.split_k = 8;
+      NDT1_TRY(run(p, s));
+    }
+    {
+      GemmProblem p = prob(GEMM_NN, Tp, Hout, V);
+      p.nb_out = B;
+      p.A = op(dlog, (long long)Tp * ldV, B, Tp, V, ldV);
+      p.B = op(W(P->dec_w, w_dec), 0, 1, V, Hout, Hout);
+      p.epi.out = d_head_in + (long long)n_prefix * head_ld; p.epi.out_bf16 = kBf16; p.epi.ldc = head_ld; p.epi.c_batch_stride = (long long)L * head_ld;
+      if (k.factors_active) {
+        // through the factors activation: needs the pre-activation for gelu, the output otherwise
+        if (k.factors_act == NDT1_ACT_GELU) { p.epi.dact = DACT_GELU_FROM_IN; p.epi.dact_in = fpre; }
+        else { p.epi.dact = dact_from_out(k.factors_act); p.epi.dact_in = fac; }
+        p.epi.dact_in_bf16 = kBf16;
+      }
+      NDT1_TRY(run(p, s));
+    }
+    if (k.factors_active) {
+      if (G->factors_b && k.factors_bias) NDT1_TRY(k_colsum<T>(dfac, G->factors_b, M, Hout, Hout, s));
+      NDT1_TRY(linear_wgrad(dfac, Hout, hn, H, G->factors_w, H, (int)M, Hout, H, s));
+      GemmEpilogue e = gemm_epilogue_default();
+      e.out = dhn; e.out_bf16 = kBf16; e.ldc = H;
+      NDT1_TRY(linear_dgrad(dfac, Hout, W(P->factors_w, w_fac), H, (int)M, Hout, H, e, s));
+    }
+    // out_norm
+    NDT1_CUDA_CHECK(cudaMemsetAsync(dX, 0, M * H * sizeof(float), s));
+    NDT1_TRY(k_layernorm_bwd<T>(dhn, xs[2 * NL], P->out_norm_w, mean[2 * NL], rstd[2 * NL], dX, G->out_norm_w, G->out_norm_b, dY, ptr_, seed,
+                                site_mlp(NL - 1), M, H, ln_part, s));
+    NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[0], s));   // decoder + out_norm gradients complete
+    int cf, cb; ctx(cf, cb);
+    for (int l = NL - 1; l >= 0; --l) {
+      const auto& q = P->layer[l]; const auto& gq = G->layer[l];
+      // MLP: x_out = x_mid + drop(down(act(up(h2))))      dY = T(dX * mlp mask)
+      if (gq.down_b && k.mlp_bias) NDT1_TRY(k_colsum<T>(dY, gq.down_b, M, H, H, s));
+      NDT1_TRY(linear_wgrad(dY, H, g[l], I, gq.down_w, I, (int)M, H, I, s));
+      {
+        GemmEpilogue e = gemm_epilogue_default();
+        e.out = dU; e.out_bf16 = kBf16; e.ldc = I;
+        if (k.mlp_act == NDT1_ACT_GELU) { e.dact = DACT_GELU_FROM_IN; e.dact_in = u[l]; }
+        else { e.dact = dact_from_out(k.mlp_act); e.dact_in = g[l]; }
+        e.dact_in_bf16 = kBf16;
+        NDT1_TRY(linear_dgrad(dY, H, W(q.down_w, kBf16 ? w_down[l] : nullptr), I, (int)M, H, I, e, s));
+      }
+      if (gq.up_b && k.mlp_bias) NDT1_TRY(k_colsum<T>(dU, gq.up_b, M, I, I, s));
+      NDT1_TRY(linear_wgrad(dU, I, h2[l], H, gq.up_w, H, (int)M, I, H, s));
+      {
+        GemmEpilogue e = gemm_epilogue_default();
+        e.out = dH; e.out_bf16 = kBf16; e.ldc = H;
+        NDT1_TRY(linear_dgrad(dU, I, W(q.up_w, kBf16 ? w_up[l] : nullptr), H, (int)M, I, H, e, s));
+      }
+      NDT1_TRY(k_layernorm_bwd<T>(dH, xs[2 * l + 1], q.ln2_w, mean[2 * l + 1], rstd[2 * l + 1], dX, gq.ln2_w, gq.ln2_b, dY, 0.f, seed, 0, M, H,
+                                  ln_part, s));
+      // attention block: x_mid = x_in + out_proj(drop(att))      dY = T(dX)
+      const T* ad = (ptr_ > 0.f) ? attd[l] : att[l];
+      if (gq.o_b && k.attention_bias) NDT1_TRY(k_colsum<T>(dY, gq.o_b, M, H, H, s));
+      NDT1_TRY(linear_wgrad(dY, H, ad, H, gq.o_w, H, (int)M, H, H, s));
+      {
+        GemmEpilogue e = gemm_epilogue_default();
+        e.out = dA; e.out_bf16 = kBf16; e.ldc = H;
+        if (ptr_ > 0.f) { e.drop_p = ptr_; e.drop_bwd = 1; e.drop_seed = seed; e.drop_stream = site_attn_o(l); }
+        NDT1_TRY(linear_dgrad(dY, H, W(q.o_w, kBf16 ? w_o[l] : nullptr), H, (int)M, H, H, e, s));
+      }
+      AttnParams ap;
+      ap.qkv = qkv[l]; ap.out = att[l]; ap.out_drop = (void*)ad; ap.lse = lse[l]; ap.key_valid = key_valid;
+      ap.B = B; ap.L = L; ap.H = H; ap.nh = k.n_heads; ap.hd = H / k.n_heads; ap.ctx_fwd = cf; ap.ctx_bwd = cb;
+      ap.scale = 1.0f / sqrtf((float)(H / k.n_heads)); ap.p_attn = ptr_; ap.p_out = ptr_;
+      ap.seed = seed; ap.stream_attn = site_attn_p(l); ap.stream_out = site_attn_o(l);
+      ap.dout = dA; ap.dqkv = dqkv; ap.delta = delta;
+      NDT1_TRY(k_attention_bwd<T>(ap, s));
+      float* gw[3] = {gq.q_w, gq.k_w, gq.v_w}; float* gb[3] = {gq.q_b, gq.k_b, gq.v_b};
+      for (int j = 0; j < 3; ++j) {
+        if (gb[j] && k.attention_bias) NDT1_TRY(k_colsum<T>(dqkv + (long long)j * H, gb[j], M, H, 3 * H, s));
+        NDT1_TRY(linear_wgrad(dqkv + (long long)j * H, 3 * H, h1[l], H, gw[j], H, (int)M, H, H, s));
+      }
+      if (kBf16) {
+        GemmEpilogue e = gemm_epilogue_default();
+        e.out = dH; e.out_bf16 = 1; e.ldc = H;
+        NDT1_TRY(linear_dgrad(dqkv, 3 * H, w_qkv[l], H, (int)M, 3 * H, H, e, s));
+      } else {
+        const float* ws[3] = {q.q_w, q.k_w, q.v_w};
+        for (int j = 0; j < 3; ++j) {
+          GemmEpilogue e = gemm_epilogue_default();
+          e.out = dH; e.out_bf16 = 0; e.ldc = H; e.accumulate = j > 0;
+          NDT1_TRY(linear_dgrad(dqkv + (long long)j * H, 3 * H, ws[j], H, (int)M, H, H, e, s));
+        }
+      }
+      const bool first = (l == 0);
+      NDT1_TRY(k_layernorm_bwd<T>(dH, xs[2 * l], q.ln1_w, mean[2 * l], rstd[2 * l], dX, gq.ln1_w, gq.ln1_b, first ? (T*)nullptr : dY,
+                                  first ? 0.f : ptr_, seed, first ? 0 : site_mlp(l - 1), M, H, ln_part, s));
+      NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[NL - l], s));   // layer l gradients complete
+    }
+    // embedding: dX is the gradient w.r.t. the (dropped) embedding output.
+    // One pass: apply the embedding dropout mask, cast for the GEMMs, scatter into the position table.
+    NDT1_TRY(k_grad_prep<T>(dX, dY, M, H, pe, seed, 0, (k.pos && G->pos_w) ? G->pos_w : nullptr, ts_ptr, H, L, Tn, n_prefix, s));
+    if (n_prefix > 0) {
+      int slot = 0;
+      if (k.day_token) { if (G->day_emb) NDT1_TRY(k_token_rows_grad<T>(G->day_emb, day_ptr, dY, B, L, H, slot, s)); ++slot; }
+      if (k.block_token) { if (G->block_emb) NDT1_TRY(k_token_rows_grad<T>(G->block_emb, block_ptr, dY, B, L, H, slot, s)); ++slot; }
+      NDT1_CUDA_CHECK(cudaMemset2DAsync(dY, (size_t)L * H * sizeof(T), 0, (size_t)n_prefix * H * sizeof(T), B, s));
+    }
+    if (G->proj_b) NDT1_TRY(k_colsum<T>(dY, G->proj_b, M, H, H, s));
+    const T* dE = dY + (long long)n_prefix * H;
+    const int eact = k.embed_act;
+    NDT1_REQUIRE(eact != NDT1_ACT_GELU, "engine: gelu as the embedder activation is not implemented in this build");
+    if (k.stack_active) {
+      const int K4 = k.stack_stride * D, nch = k.stack_size / k.stack_stride, R4 = Tn / k.stack_stride;
+      if (G->proj_w) {
+        GemmProblem p = prob(GEMM_TN, H, nch * K4, Tp);
+        p.nchunk = B; p.b_chunk_n = K4; p.b_row_shift = 1;
+        p.A = op(dE, (long long)L * H, B, Tp, H, H);
+        p.B = op(emb, (long long)Tn * D, B, R4, K4, K4);
+        p.epi.out = G->proj_w; p.epi.ldc = nch * K4; p.epi.accumulate = 1;
+        p.split_k = (B >= 8 && kBf16 && !force_simt) ? 2 : 1;
+        NDT1_TRY(run(p, s));
+      }
+      if (Tn % k.stack_stride != 0) NDT1_CUDA_CHECK(cudaMemsetAsync(dEmb, 0, MT * D * sizeof(T), s));
+      GemmProblem p = prob(GEMM_NN, R4, K4, H);
+      p.nb_out = B; p.nchunk = nch; p.a_row_shift = -1; p.b_col_shift = K4;
+      p.A = op(dE, (long long)L * H, B, Tp, H, H);
+      p.B = op(W(P->proj_w, w_proj), 0, 1, H, nch * K4, nch * K4);
+      p.epi.out = dEmb; p.epi.out_bf16 = kBf16; p.epi.ldc = K4; p.epi.c_batch_stride = (long long)Tn * D;
+      p.epi.dact = dact_from_out(eact); p.epi.dact_in = emb; p.epi.dact_in_bf16 = kBf16;
+      NDT1_TRY(run(p, s));
+    } else {
+      if (G->proj_w) {
+        GemmProblem p = prob(GEMM_TN, H, D, Tp);
+        p.nchunk = B;
+        p.A = op(dE, (long long)L * H, B, Tp, H, H);
+        p.B = op(emb, (long long)Tn * D, B, Tn, D, D);
+        p.epi.out = G->proj_w; p.epi.ldc = D; p.epi.accumulate = 1;
+        NDT1_TRY(run(p, s));
+      }
+      GemmProblem p = prob(GEMM_NN, Tp, D, H);
+      p.nb_out = B;
+      p.A = op(dE, (long long)L * H, B, Tp, H, H);
+      p.B = op(W(P->proj_w, w_proj), 0, 1, H, D, D);
+      p.epi.out = dEmb; p.epi.out_bf16 = kBf16; p.epi.ldc = D; p.epi.c_batch_stride = (long long)Tn * D;
+      p.epi.dact = dact_from_out(eact); p.epi.dact_in = emb; p.epi.dact_in_bf16 = kBf16;
+      NDT1_TRY(run(p, s));
+    }
+    if (G->embed_b && k.embed_bias) NDT1_TRY(k_colsum<T>(dEmb, G->embed_b, MT, D, D, s));
+    if (G->embed_w) {
+      const T* x_in = kBf16 ? xin : (const T*)spikes_ptr;
+      const int ldx = kBf16 ? ldN : N;
+      GemmProblem p = prob(GEMM_TN, D, N, (int)MT);
+      p.A = op(dEmb, 0, 1, (int)MT, D, D); p.B = op(x_in, 0, 1, (int)MT, N, ldx);
+      p.epi.out = G->embed_w; p.epi.ldc = N; p.epi.accumulate = 1;
+      const int kb = ndt1_cdiv(MT, 64);
+      int split = kb / 8; if (split > 64) split = 64; if (split < 1) split = 1;
+      if (!(kBf16 && !force_simt) && split > 8) split = 8;
+      p.split_k = split;
+      NDT1_TRY(run(p, s));
+    }
+    NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[NL + 1], s));     // embedding gradients complete
+    launches += g_ndt1_launches - launches0;
+    return 0;
+  }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int ndt1_abi_version(void) { return NDT1_ABI_VERSION; }
+
+int ndt1_engine_create(const ndt1_config* cfg, ndt1_engine** out) {
+  NDT1_REQUIRE(cfg && out, "engine_create: null argument");
+  NDT1_REQUIRE(cfg->abi_version == NDT1_ABI_VERSION, "engine_create: ABI version %d, library is %d", cfg->abi_version, NDT1_ABI_VERSION);
+  NDT1_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= NDT1_MAX_LAYERS, "engine_create: n_layers %d outside [1,%d]", cfg->n_layers, NDT1_MAX_LAYERS);
+  NDT1_REQUIRE(cfg->hidden % cfg->n_heads == 0, "engine_create: Hidden dim is not multiple of head size");
+  NDT1_REQUIRE(!cfg->adapt, "engine_create: per-day embedding (adapt) is not implemented in this build");
+  NDT1_REQUIRE(cfg->max_batch > 0 && cfg->max_T > 0, "engine_create: max_batch / max_T must be positive");
+  NDT1_REQUIRE(cfg->hidden % 8 == 0 && cfg->inter % 8 == 0 && cfg->input_dim % 8 == 0, "engine_create: hidden, inter and input_dim must be multiples of 8");
+  ndt1_engine* e = nullptr;
+  int rc;
+  if (cfg->precision == NDT1_PRECISION_BF16) { auto* t = new Engine<bf16>(); t->c = *cfg; rc = t->init(); e = t; }
+  else if (cfg->precision == NDT1_PRECISION_FP32) { auto* t = new Engine<float>(); t->c = *cfg; rc = t->init(); e = t; }
+  else { NDT1_REQUIRE(false, "engine_create: unknown precision %d", cfg->precision); }
+  if (rc) { delete e; return rc; }
+  *out = e;
+  return 0;
+}
+void ndt1_engine_destroy(ndt1_engine* e) { delete e; }
+size_t ndt1_engine_arena_bytes(const ndt1_engine* e) { return e->arena_bytes(); }
+int ndt1_engine_out_len(const ndt1_engine* e, int T) { return e->out_len(T); }
+int ndt1_engine_forward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_batch* batch, const ndt1_outputs* out, void* stream) {
+  NDT1_REQUIRE(e && params && batch && out && out->loss, "engine_forward: null argument");
+  return e->forward(params, batch, out, (cudaStream_t)stream);
+}
+int ndt1_engine_backward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_tensors* grads, const float* dloss, void* stream) {
+  NDT1_REQUIRE(e && params && grads, "engine_backward: null argument");
+  return e->backward(params, grads, dloss, (cudaStream_t)stream);
+}
+int64_t ndt1_engine_launch_count(const ndt1_engine* e) { return e->launches; }
+int ndt1_engine_stage_count(const ndt1_engine* e) { return e->n_stages(); }
+int ndt1_engine_wait_stage(ndt1_engine* e, int stage, void* stream) {
+  NDT1_REQUIRE(e && stage >= 0 && stage < e->n_stages(), "engine_wait_stage: stage %d out of range", stage);
+  NDT1_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, e->stage_ev[stage], 0));
+  return 0;
+}
+
+}  // extern "C"

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 static thread_local char g_err[1024] = "";
+thread_local long long g_ndt1_launches = 0;
 
 void ndt1_set_error(const char* fmt, ...) {
   va_list ap;

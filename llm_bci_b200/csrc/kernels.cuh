@@ -1,0 +1,73 @@
+// Internal launcher declarations (one per kernel family).  Every launcher
+// returns 0 on success and records a message via ndt1_set_error otherwise.
+#pragma once
+#include "common.cuh"
+#include "gemm_common.cuh"
+
+// elementwise.cu
+int k_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps, int K, float white_sd, float offset_sd,
+                   const float* white, const float* offset, int use_philox, unsigned long long seed, cudaStream_t stream);
+int k_masker_apply(float* spikes, int B, int T, int N, int mode, int timespan, const unsigned char* mask_draw,
+                   const unsigned char* zero_draw, const unsigned char* random_draw, const float* rand, long long* mask_out,
+                   long long* targets_mask, unsigned int* scratch, cudaStream_t stream);
+int k_bernoulli_u8(unsigned char* out, long long n, float prob, unsigned long long seed, unsigned long long stream_id, cudaStream_t stream);
+int k_uniform_f32(float* out, long long n, unsigned long long seed, unsigned long long stream_id, cudaStream_t stream);
+int k_pad_pack(const void* src, const long long* offsets, void* dst, int B, int P, int inner, int elem_size, int side_left, int full,
+               double value, cudaStream_t stream);
+int k_cast_f32_bf16(const float* in, bf16* out, long long rows, int cols, long long ld_in, long long ld_out, cudaStream_t stream);
+template <typename T> int k_colsum(const T* in, float* out, long long rows, int cols, long long ld, cudaStream_t stream);
+template <typename T>
+int k_grad_prep(const float* g, T* out, long long rows, int cols, float drop_p, unsigned long long seed, unsigned long long stream_id,
+                float* dtab, const long long* idx, int tab_ld, int rows_per_b, long long idx_stride, int prefix, cudaStream_t stream);
+int k_recon_loss(const float* pred, const float* target, float* dpred, const long long* tmask, const long long* pmask, int B, int T,
+                 int N, int kind, int shift, int relu_out, float* loss, long long* count, const float* dloss, cudaStream_t stream);
+int k_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd, int step,
+            float gscale, cudaStream_t stream);
+int k_stack_mask(const long long* mask, long long* out, int B, int T, int Tp, int size, int stride, int n_prefix, cudaStream_t stream);
+int k_token_rows(const float* table, const long long* idx, float* x, int B, int L, int H, int slot, cudaStream_t stream);
+template <typename T> int k_token_rows_grad(float* dtable, const long long* idx, const T* dx, int B, int L, int H, int slot, cudaStream_t stream);
+template <typename T> int k_scale_cast_pad(const float* in, T* out, long long rows, int cols, int ld_out, const float* scale, cudaStream_t stream);
+int k_stacked_lens(const long long* lens, long long* out, int B, int stack, int size, int stride, cudaStream_t stream);
+int k_set_i64(long long* p, long long v, cudaStream_t stream);
+int k_relu_inplace(float* x, long long n, cudaStream_t stream);
+int k_and_mask(const long long* tmask, const long long* pmask, long long* out, int B, int T, int N, cudaStream_t stream);
+
+// layernorm.cu
+template <typename T>
+int k_layernorm_fwd(const float* x, const float* gamma, const float* beta, T* y, float* mean, float* rstd, long long rows, int H,
+                    float eps, cudaStream_t stream);
+// dres (fp32, in/out) += LN'(dy);  optional out_lp = T(dres_new * dropscale)
+template <typename T>
+int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float* mean, const float* rstd, float* dres, float* dgamma,
+                    float* dbeta, T* out_lp, float drop_p, unsigned long long seed, unsigned long long stream_id, long long rows, int H,
+                    float* partials, cudaStream_t stream);
+size_t k_layernorm_bwd_partials_bytes(int H);
+
+// attention.cu (CUDA-core path, both precisions)
+struct AttnParams {
+  const void* qkv;          // (B*L, 3H): q | k | v, head h at columns h*hd
+  void* out;                // (B*L, H) attention output (pre output-dropout)
+  void* out_drop;           // (B*L, H) after output dropout (== out when p_out == 0)
+  float* lse;               // (B, nh, L)
+  const long long* key_valid;  // (B, L)
+  int B, L, H, nh, hd;
+  int ctx_fwd, ctx_bwd;     // effective band half-widths (INT_MAX/2 = unbounded); self may be excluded by -1
+  float scale;
+  float p_attn, p_out;
+  unsigned long long seed, stream_attn, stream_out;
+  // backward
+  const void* dout;         // (B*L, H) gradient w.r.t. out_drop input of out_proj (already through output dropout)
+  void* dqkv;               // (B*L, 3H)
+  float* delta;             // (B, nh, L) scratch
+};
+template <typename T> int k_attention_fwd(const AttnParams& p, cudaStream_t stream);
+template <typename T> int k_attention_bwd(const AttnParams& p, cudaStream_t stream);
+
+// ctc.cu
+int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaStream_t stream);
+// log-probs (B, L, V); per-trial NLL summed into *loss; dlogits = (softmax - posterior) * (*dloss) for t < len
+int k_ctc_fwd_bwd(const float* logp, const long long* targets, const long long* in_len, const long long* tgt_len, int B, int L, int V,
+                  int S, int blank, int zero_infinity, float* alpha_ws, float* nll, float* loss, float* dlogits, const float* dloss,
+                  cudaStream_t stream);
+size_t k_ctc_workspace_floats(int B, int L, int S);
+int k_ctc_greedy_decode(const float* logp, int B, int L, int V, int blank, long long* out_ids, long long* out_len, cudaStream_t stream);

@@ -1,0 +1,144 @@
+"""The caller side of the hot path: model registry and the data-parallel step.
+
+Mirrors what the reference's ``Trainer`` does around ``model(**model_inputs)``
+(models/trainer.py:32-36, 149-150, 161-171, 227-262, 332-354), without Accelerate:
+
+* ``NAME2MODEL`` -- the registry the trainer config's ``model_class`` selects from;
+* ``DataParallelTrainer`` -- one process per GPU, trials sharded across ranks
+  (``split_batches=True``: the global batch is split contiguously), every rank
+  holds a full fp32 replica, gradients are all-reduced in buckets over NCCL on
+  a side stream that waits on the engine's per-stage events (so communication
+  overlaps the rest of the backward) and divided by the world size (DDP's mean
+  of per-rank gradients of the per-rank SUM loss), then one fused AdamW kernel
+  updates the flat parameter buffer.  OneCycle-cosine / linear / step learning
+  rate as in models/trainer.py:239-253.
+"""
+from __future__ import annotations
+
+import inspect
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _C
+from .ndt1 import NDT1
+
+NAME2MODEL = {"NDT1": NDT1}
+
+
+def get_model_inputs(model) -> List[str]:
+    """Names of the forward parameters = collate keys (models/trainer.py:161-171)."""
+    return [k for k in inspect.signature(model.forward).parameters.keys() if k not in ("noise", "masker_draws")]
+
+
+def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[str, torch.Tensor]:
+    """Contiguous split of every tensor along dim 0 (Accelerate ``split_batches=True``, trainer.py:79)."""
+    out = {}
+    for k, v in batch.items():
+        if torch.is_tensor(v):
+            n = v.shape[0]
+            per = n // world
+            out[k] = v[rank * per:(rank + 1) * per] if rank < world - 1 else v[rank * per:]
+        else:
+            out[k] = v
+    return out
+
+
+def onecycle_cos_lr(step: int, total_steps: int, max_lr: float, pct_start: float, div_factor: float,
+                    final_div_factor: float = 1e4) -> float:
+    """torch OneCycleLR(anneal_strategy='cos') value at optimizer step ``step`` (trainer.py:239-246)."""
+    initial, min_lr = max_lr / div_factor, max_lr / div_factor / final_div_factor
+    up_end = float(pct_start * total_steps) - 1.0
+    down_end = float(total_steps) - 1.0
+
+    def cos(a, b, pct):
+        return b + (a - b) / 2.0 * (math.cos(math.pi * pct) + 1.0)
+
+    if step <= up_end or up_end >= down_end:
+        return cos(initial, max_lr, step / up_end) if up_end > 0 else max_lr
+    return cos(max_lr, min_lr, (step - up_end) / (down_end - up_end))
+
+
+class DataParallelTrainer:
+    """Owns the flat parameter / gradient / AdamW-state buffers of one rank."""
+
+    def __init__(self, model: NDT1, lr: float = 1e-3, wd: float = 5e-5, eps: float = 1e-8, betas=(0.9, 0.999),
+                 scheduler: Optional[str] = None, total_steps: int = 1, warmup_pct: float = 0.0, div_factor: float = 25.0,
+                 gamma: float = 0.95, process_group=None, bucket_layers: int = 1):
+        self.model = model
+        self.lr, self.wd, self.eps, self.betas = lr, wd, eps, betas
+        self.scheduler, self.total_steps, self.warmup_pct, self.div_factor, self.gamma = scheduler, total_steps, warmup_pct, div_factor, gamma
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.step_count = 0
+        self.bucket_layers = max(1, bucket_layers)
+        offs, total = model._grad_offsets()
+        table, _ = model._params()
+        dev = next(model.parameters()).device
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._stage_of: Dict[int, int] = {}
+        n_layers = model.config.encoder.transformer.n_layers
+        spans: Dict[int, List[int]] = {}
+        with torch.no_grad():
+            for slot, p in table:
+                if p is None:
+                    continue
+                o = offs[id(p)]
+                self.flat_param[o:o + p.numel()].copy_(p.detach().reshape(-1))
+                p.data = self.flat_param[o:o + p.numel()].view_as(p)     # parameters become views of the flat buffer
+                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+                if slot.startswith("layer."):
+                    stage = n_layers - int(slot.split(".")[1])
+                elif slot in ("out_norm_w", "out_norm_b", "factors_w", "factors_b", "dec_w", "dec_b"):
+                    stage = 0
+                else:
+                    stage = n_layers + 1
+                lo, hi = spans.get(stage, (o, o))
+                spans[stage] = [min(lo, o), max(hi, o + (p.numel() + 63) // 64 * 64)]
+        model.invalidate_param_cache()
+        self.buckets = [(st, spans[st][0], spans[st][1]) for st in sorted(spans)]   # completion order
+        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._ones = torch.ones((), dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------
+    def current_lr(self) -> float:
+        if self.scheduler == "cosine":
+            return onecycle_cos_lr(self.step_count, self.total_steps, self.lr, self.warmup_pct, self.div_factor)
+        if self.scheduler == "linear":
+            return onecycle_cos_lr(self.step_count, self.total_steps, self.lr, self.warmup_pct, self.div_factor)
+        if self.scheduler == "step":
+            return self.lr * (self.gamma ** self.step_count)
+        return self.lr
+
+    def all_reduce_gradients(self) -> None:
+        """Bucketed all-reduce (sum) on the side stream; each bucket waits for its backward stage."""
+        if self.world == 1:
+            return
+        L = _C.lib()
+        with torch.cuda.stream(self.comm_stream):
+            for stage, lo, hi in self.buckets:
+                _C.check(L.ndt1_engine_wait_stage(self.model._engine, stage, self.comm_stream.cuda_stream), "ndt1_engine_wait_stage")
+                dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def train_step(self, batch: Dict[str, torch.Tensor]):
+        """forward + backward + gradient all-reduce + AdamW on this rank's shard.  Returns the NDT1Output."""
+        m = self.model
+        m.train()
+        self.flat_grad.zero_()
+        out = m.forward_backward(batch, self.flat_grad, self._ones)
+        self.all_reduce_gradients()
+        self.optimizer_step()
+        return out
+
+    def optimizer_step(self) -> None:
+        self.step_count += 1
+        b1, b2 = self.betas
+        _C.check(_C.lib().ndt1_adamw_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+                                          self.exp_avg_sq.data_ptr(), self.flat_param.numel(), float(self.current_lr()), b1, b2, self.eps,
+                                          self.wd, self.step_count, 1.0 / self.world, _C.stream_ptr()), "ndt1_adamw_step")

@@ -1,0 +1,293 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED
+reference (colehurwitz/llm_bci, mounted read-only at /root/reference) on the CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference has no tests or fixtures of its own, so
+these files are what pins the oracle (oracle/ndt1_oracle.py) and, through it,
+the CUDA path.  Nothing here is imported by the product.
+
+Work-arounds applied to the environment, not to the reference sources:
+  * scipy>=1.13 removed ``scipy.signal.gaussian`` (used at models/ndt1.py:87):
+    alias it to ``scipy.signal.windows.gaussian``.
+  * ``editdistance`` is absent: a stub module lets utils/eval_bci.py import so
+    that ``format_ctc`` (eval_bci.py:41-48) can be called.
+  * mlm needs the masker entry to be *named* ``active`` (ndt1.py:481 reads
+    ``config.encoder.masker.active`` although ``masker`` is a dict of maskers).
+"""
+import os
+import sys
+import types
+import copy
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def import_reference():
+    os.chdir(REF)
+    sys.path.insert(0, REF)
+    import scipy.signal
+    import scipy.signal.windows
+    scipy.signal.gaussian = scipy.signal.windows.gaussian
+    sys.modules.setdefault("editdistance", types.ModuleType("editdistance"))
+    from utils.config_utils import update_config, DictConfig
+    from models.ndt1 import NDT1, create_context_mask
+    from models.masker import Masker
+    from data_utils.datasets import pad_collate_fn, padded_array
+    from utils.eval_bci import format_ctc
+    return dict(update_config=update_config, DictConfig=DictConfig, NDT1=NDT1, Masker=Masker,
+                create_context_mask=create_context_mask, pad_collate_fn=pad_collate_fn, padded_array=padded_array,
+                format_ctc=format_ctc)
+
+
+def small_ctc_overrides():
+    return {"encoder": {
+        "embedder": {"n_channels": 16, "input_dim": 16, "max_F": 64, "dropout": 0.0,
+                     "stack": {"active": True, "size": 32, "stride": 4}},
+        "transformer": {"n_layers": 2, "hidden_size": 64, "n_heads": 4, "inter_size": 64, "dropout": 0.0},
+        "smooth_and_noise": {"noise": False},
+    }}
+
+
+def make_ctc_batch(B, T, N, seed, S_lo=3, S_hi=8):
+    g = torch.Generator().manual_seed(seed)
+    spikes = torch.randn(B, T, N, generator=g)
+    lens = torch.randint(int(0.6 * T), T + 1, (B,), generator=g)
+    lens[0] = T
+    t = torch.arange(T)[None, :]
+    mask = (t < lens[:, None]).to(torch.int64)
+    spikes = spikes * mask[:, :, None]
+    ts = t.expand(B, T) * mask
+    tl = torch.randint(S_lo, S_hi + 1, (B,), generator=g)
+    S = int(tl.max())
+    tg = torch.randint(1, 41, (B, S), generator=g)
+    tg = tg * (torch.arange(S)[None, :] < tl[:, None])
+    return dict(spikes=spikes, spikes_mask=mask, spikes_timestamp=ts, spikes_lengths=lens, targets=tg,
+                targets_lengths=tl)
+
+
+def flat(prefix, d):
+    return {f"{prefix}/{k}": (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def run_ref(model, batch, train=False, seed=None):
+    model.train(train)
+    model.zero_grad()
+    if seed is not None:
+        torch.manual_seed(seed)
+    b = {k: v.clone() for k, v in batch.items()}
+    out = model(**b)
+    out.loss.backward()
+    grads = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
+    return out, grads
+
+
+def main():
+    R = import_reference()
+    update_config, NDT1 = R["update_config"], R["NDT1"]
+    torch.set_num_threads(8)
+
+    # ------------------------------------------------------------------ 1. small CTC, eval-like numerics
+    trainer = update_config("configs/trainer_ctc_ndt1.yaml", None)
+    cfg = update_config(copy.deepcopy(dict(trainer.model)), small_ctc_overrides())
+    torch.manual_seed(11)
+    model = NDT1(cfg, **trainer.method.model_kwargs)
+    batch = make_ctc_batch(3, 120, 16, seed=5)
+    out, grads = run_ref(model, batch, train=True)   # train mode; dropout 0, noise off, masker inactive
+    d = {}
+    d.update(flat("param", dict(model.state_dict())))
+    d.update(flat("batch", batch))
+    d.update(flat("grad", grads))
+    d["out/loss"] = out.loss.detach().numpy()
+    d["out/preds"] = out.preds.detach().numpy()
+    d["out/n_examples"] = out.n_examples.numpy()
+    d["out/decoded"] = np.array([len(R["format_ctc"](p.argmax(-1).tolist(), list(range(41)), 0)) for p in out.preds.detach()])
+    dec = [R["format_ctc"](p.argmax(-1).tolist(), list(range(41)), 0) for p in out.preds.detach()]
+    d["out/decoded_flat"] = np.array([x for s in dec for x in s] + [-1], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "ctc_small.npz"), **d)
+    print("ctc_small loss", float(out.loss))
+
+    # ------------------------------------------------------------------ 2. small CTC with injected noise (train mode)
+    cfg_n = update_config(copy.deepcopy(dict(cfg)), {"encoder": {"smooth_and_noise": {"noise": True}}})
+    cfg_n["encoder"]["from_pt"] = None
+    torch.manual_seed(11)
+    model_n = NDT1(cfg_n, **trainer.method.model_kwargs)
+    out_n, grads_n = run_ref(model_n, batch, train=True, seed=123)
+    torch.manual_seed(123)
+    white = torch.randn(3, 120, 16)
+    offset = torch.randn(3, 1, 16)
+    d = {"noise/white": white.numpy(), "noise/offset": offset.numpy(), "out/loss": out_n.loss.detach().numpy(),
+         "out/preds": out_n.preds.detach().numpy()}
+    d.update(flat("grad", {k: v for k, v in grads_n.items() if k.endswith("stack_projection.weight") or k.endswith("decoder.0.bias")
+                           or k.endswith("embed_spikes.weight")}))
+    np.savez_compressed(os.path.join(HERE, "ctc_small_noise.npz"), **d)
+    print("ctc_small_noise loss", float(out_n.loss))
+
+    # ------------------------------------------------------------------ 3. small masked-LM (SSL) with a temporal masker
+    mk = {"active": True, "mode": "temporal", "ratio": 0.3, "zero_ratio": 0.8, "random_ratio": 0.5, "expand_prob": 1.0,
+          "max_timespan": 3, "regions": None, "channels": None}
+    ssl_over = {"encoder": {
+        "masker": {"active": mk},
+        "embedder": {"n_channels": 24, "input_dim": 16, "max_F": 64, "dropout": 0.0, "stack": {"active": False}},
+        "transformer": {"n_layers": 2, "hidden_size": 64, "n_heads": 4, "inter_size": 64, "dropout": 0.0},
+        "smooth_and_noise": {"noise": False},
+        "context": {"forward": 2, "backward": 5},
+    }}
+    cfg_s = update_config("configs/ndt1.yaml", ssl_over)
+    del cfg_s["encoder"]["masker"]["neuron"]
+    torch.manual_seed(12)
+    model_s = NDT1(cfg_s, method_name="mlm", loss="poisson_nll", log_input=True)
+    g = torch.Generator().manual_seed(9)
+    B, T, N = 4, 40, 24
+    sp = torch.poisson(torch.full((B, T, N), 0.6), generator=g)
+    lens = torch.tensor([40, 33, 40, 25])
+    msk = (torch.arange(T)[None] < lens[:, None]).to(torch.int64)
+    sp = sp * msk[:, :, None]
+    sbatch = dict(spikes=sp, spikes_mask=msk, spikes_timestamp=torch.arange(T)[None].expand(B, T) * msk, spikes_lengths=lens)
+    out_s, grads_s = run_ref(model_s, sbatch, train=True, seed=321)
+    # replay the draws: CPU generator order
+    torch.manual_seed(321)
+    expand = bool(torch.bernoulli(torch.tensor(mk["expand_prob"]).float()))
+    timespan = int(torch.randint(1, mk["max_timespan"] + 1, (1,)).item()) if expand else 1
+    ratio = mk["ratio"] / timespan
+    m_draw = torch.bernoulli(torch.full((B, T), ratio))
+    z_draw = torch.bernoulli(torch.full((B, T, N), mk["zero_ratio"]))
+    r_draw = torch.bernoulli(torch.full((B, T, N), mk["random_ratio"]))
+    rnd = torch.rand((B, T, N))
+    d = {}
+    d.update(flat("param", dict(model_s.state_dict())))
+    d.update(flat("batch", sbatch))
+    d.update(flat("grad", grads_s))
+    d.update({"draw/mask": m_draw.numpy(), "draw/zero": z_draw.numpy(), "draw/random": r_draw.numpy(), "draw/rand": rnd.numpy(),
+              "draw/timespan": np.array(timespan), "out/loss": out_s.loss.detach().numpy(), "out/preds": out_s.preds.detach().numpy(),
+              "out/n_examples": out_s.n_examples.numpy(), "out/mask": out_s.mask.numpy()})
+    np.savez_compressed(os.path.join(HERE, "mlm_small.npz"), **d)
+    print("mlm_small loss", float(out_s.loss), "n", int(out_s.n_examples), "timespan", timespan)
+
+    # ------------------------------------------------------------------ 4. masker modes, bit exact
+    Masker, DictConfig = R["Masker"], R["DictConfig"]
+    d = {}
+    B, T, N = 3, 17, 10
+    base = torch.randn(B, T, N, generator=torch.Generator().manual_seed(3)) * 2 + 1
+    modes = {
+        "temporal1": dict(mode="temporal", ratio=0.4, zero_ratio=0.7, random_ratio=0.6, expand_prob=0.0, max_timespan=1),
+        "temporal4": dict(mode="temporal", ratio=0.5, zero_ratio=0.5, random_ratio=1.0, expand_prob=1.0, max_timespan=4),
+        "neuron": dict(mode="neuron", ratio=0.3, zero_ratio=1.0, random_ratio=1.0, expand_prob=0.0, max_timespan=1),
+        "random": dict(mode="random", ratio=0.25, zero_ratio=0.3, random_ratio=0.5, expand_prob=0.0, max_timespan=1),
+        "cosmooth": dict(mode="co-smooth", ratio=0.0, zero_ratio=0.9, random_ratio=0.2, expand_prob=0.0, max_timespan=1,
+                         channels=[1, 4, 9]),
+    }
+    for name, mc in modes.items():
+        full = dict(active=True, regions=None, channels=None)
+        full.update(mc)
+        for seed in (0, 1, 2, 7):
+            mkr = Masker(DictConfig(full))
+            mkr.train()
+            torch.manual_seed(seed)
+            so, mo = mkr(base.clone())
+            torch.manual_seed(seed)
+            ts = 1
+            if full["mode"] == "temporal":
+                if torch.bernoulli(torch.tensor(full["expand_prob"]).float()):
+                    ts = int(torch.randint(1, full["max_timespan"] + 1, (1,)).item())
+                probs = torch.full((B, T), full["ratio"] / ts)
+            elif full["mode"] == "neuron":
+                probs = torch.full((B, N), full["ratio"])
+            elif full["mode"] == "random":
+                probs = torch.full((B, T, N), full["ratio"])
+            else:
+                probs = torch.zeros(N)
+                for c in full["channels"]:
+                    probs[c] = 1
+            md = torch.bernoulli(probs)
+            zd = torch.bernoulli(torch.full((B, T, N), full["zero_ratio"]))
+            rd = torch.bernoulli(torch.full((B, T, N), full["random_ratio"]))
+            rn = torch.rand((B, T, N))
+            key = f"{name}/{seed}"
+            d.update({f"{key}/mask_draw": md.numpy(), f"{key}/zero": zd.numpy().astype(np.uint8),
+                      f"{key}/random": rd.numpy().astype(np.uint8), f"{key}/rand": rn.numpy(), f"{key}/timespan": np.array(ts),
+                      f"{key}/out_spikes": so.numpy(), f"{key}/out_mask": mo.numpy()})
+    d["base"] = base.numpy()
+    d["modes"] = np.array(list(modes.keys()))
+    d["mode_names"] = np.array([modes[k]["mode"] for k in modes])
+    np.savez_compressed(os.path.join(HERE, "masker.npz"), **d)
+
+    # ------------------------------------------------------------------ 5. collate
+    rng = np.random.default_rng(0)
+    rows = []
+    for L, S in ((50, 5), (37, 9), (44, 3)):
+        rows.append({"spikes": rng.standard_normal((L, 6)).astype(np.float32), "spikes_mask": np.ones(L, dtype=np.int64),
+                     "spikes_timestamp": np.arange(L, dtype=np.int64), "spikes_lengths": np.asarray(L, dtype=np.int64),
+                     "targets": rng.integers(1, 41, S).astype(np.int64), "targets_lengths": np.asarray(S, dtype=np.int64),
+                     "sentence": "abc", "extra": rng.standard_normal((L, 2)).astype(np.float32)})
+    d = {}
+    pads = {
+        "right": {k: dict(dim=0, side="right", value=0, truncate=None, min_length=None) for k in ("spikes", "spikes_mask", "spikes_timestamp", "targets")},
+        "left_trunc": {k: dict(dim=0, side="left", value=-1, truncate=40, min_length=None) for k in ("spikes", "spikes_mask", "spikes_timestamp", "targets")},
+        "minlen": {k: dict(dim=0, side="right", value=0, truncate=64, min_length=60) for k in ("spikes", "spikes_mask", "spikes_timestamp")},
+    }
+    model_inputs = ["spikes", "spikes_mask", "spikes_timestamp", "spikes_lengths", "targets", "targets_lengths"]
+    for name, pd in pads.items():
+        padded, unused = R["pad_collate_fn"](copy.deepcopy(rows), model_inputs, pd)
+        for k, v in padded.items():
+            if torch.is_tensor(v):
+                d[f"{name}/{k}"] = v.numpy()
+            elif isinstance(v, list) and torch.is_tensor(v[0]):
+                for i, vi in enumerate(v):
+                    d[f"{name}/{k}/{i}"] = vi.numpy()
+        d[f"{name}/unused_keys"] = np.array(sorted(unused.keys()))
+    for i, r in enumerate(rows):
+        for k, v in r.items():
+            if isinstance(v, np.ndarray):
+                d[f"row{i}/{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "collate.npz"), **d)
+
+    # ------------------------------------------------------------------ 6. context band + greedy collapse
+    d = {}
+    for cf, cb in ((-2, -2), (0, -2), (-2, 0), (-1, -1), (3, 1), (0, 0), (-1, 4), (2, -1)):
+        d[f"band/{cf}/{cb}"] = R["create_context_mask"](cf, cb, 12).numpy()
+    seqs = [[0, 0, 3, 3, 0, 3, 4, 4, 0, 0, 5, 3], [1, 0, 1, 0, 1], [0, 0, 0], [7, 7, 7, 2, 2, 7], []]
+    for i, s in enumerate(seqs):
+        d[f"ctc_in/{i}"] = np.array(s, dtype=np.int64)
+        d[f"ctc_out/{i}"] = np.array(R["format_ctc"](s, list(range(41)), 0), dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "index_ops.npz"), **d)
+
+    # ------------------------------------------------------------------ 7. full-size model (config 2 architecture), B=4
+    trainer = update_config("configs/trainer_ctc_ndt1.yaml", None)
+    cfg_f = update_config(copy.deepcopy(dict(trainer.model)), {"encoder": {
+        "embedder": {"dropout": 0.0}, "transformer": {"dropout": 0.0}, "smooth_and_noise": {"noise": False}}})
+    torch.manual_seed(1)
+    model_f = NDT1(cfg_f, **trainer.method.model_kwargs)
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle.ndt1_oracle import synthetic_ctc_batch
+    fb = synthetic_ctc_batch(B=4, T=1000, N=256, seed=1)
+    out_f, grads_f = run_ref(model_f, fb, train=True)
+    d = {"out/loss": out_f.loss.detach().numpy(), "out/preds_rows": out_f.preds.detach().numpy()[:, ::40, :],
+         "out/preds_sum": out_f.preds.detach().double().sum().numpy(),
+         "out/argmax": out_f.preds.detach().argmax(-1).numpy()}
+    names = list(dict(model_f.named_parameters()).keys())
+    d["names"] = np.array(names)
+    d["param_sum"] = np.array([float(p.detach().double().sum()) for p in model_f.parameters()])
+    d["param_abs"] = np.array([float(p.detach().double().abs().sum()) for p in model_f.parameters()])
+    d["grad_norm"] = np.array([float(grads_f[n].double().norm()) for n in names])
+    d["grad_absmax"] = np.array([float(grads_f[n].abs().max()) for n in names])
+    # a few full gradients that are small enough to keep
+    for n in ("decoder.0.weight", "decoder.0.bias", "encoder.out_norm.weight", "encoder.layers.0.ln1.weight",
+              "encoder.layers.4.mlp.down_proj.bias", "encoder.layers.2.attn.query.bias", "encoder.embedder.embed_spikes.weight",
+              "encoder.embedder.stack_projection.bias"):
+        d[f"grad/{n}"] = grads_f[n].numpy()
+    d["grad_slice/encoder.layers.0.attn.value.weight"] = grads_f["encoder.layers.0.attn.value.weight"][:8, :].numpy()
+    d["grad_slice/encoder.embedder.stack_projection.weight"] = grads_f["encoder.embedder.stack_projection.weight"][:4, :].numpy()
+    d["grad_slice/encoder.embedder.embed_pos.weight"] = grads_f["encoder.embedder.embed_pos.weight"][:4, :].numpy()
+    np.savez_compressed(os.path.join(HERE, "ctc_full_b4.npz"), **d)
+    print("ctc_full_b4 loss", float(out_f.loss))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,199 @@
+"""CPU tests of the host logic: config system, C-ABI surface, host collate, init/
+checkpoint compatibility, LR schedule, and the data-parallel semantics on gloo."""
+import os
+import re
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import llm_bci_b200 as lb  # noqa: E402
+from llm_bci_b200 import _C  # noqa: E402
+from llm_bci_b200.trainer import onecycle_cos_lr, shard_batch, get_model_inputs  # noqa: E402
+
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_config_merge_and_include():
+    tr = lb.default_trainer_config()
+    assert tr.model.model_class == "NDT1" and tr.model.encoder.embedder.stack.size == 32
+    cfg = lb.update_config(tr.model, {"encoder": {"embedder": {"n_channels": 99}, "new": {"x": 1}}})
+    assert cfg.encoder.embedder.n_channels == 99 and cfg.encoder.new.x == 1
+    assert tr.model.encoder.embedder.n_channels == 256      # the default was not mutated
+    cfg.encoder.embedder.n_channels = 7                     # main.py:230-231 style assignment sticks
+    assert cfg["encoder"]["embedder"]["n_channels"] == 7
+    kw = lb.config_from_kwargs({"a.b": "1.e-3", "a.c": "true", "d": "[1,2]", "e": "none", "f": "-3"})
+    assert kw.a.b == 1e-3 and kw.a.c is True and kw.d == [1, 2] and kw.e is None and kw.f == -3
+    with pytest.raises(KeyError):
+        _ = cfg.encoder.masker.active
+
+
+def test_c_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ndt1_b200.h")).read()
+    declared = set(re.findall(r"\b(ndt1_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ndt1_engine", "ndt1_config", "ndt1_tensors", "ndt1_batch", "ndt1_outputs"}
+    assert declared, "no declarations parsed"
+    L = _C.lib()                                             # loads without a GPU
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/ndt1_b200.h but not exported"
+        assert name in _C.PROTOTYPES, f"{name} has no ctypes prototype"
+    assert L.ndt1_abi_version() == _C.ABI_VERSION
+
+
+def test_forward_signature_is_the_api():
+    tr = lb.default_trainer_config()
+    model = lb.NAME2MODEL[tr.model.model_class](tr.model, **tr.method.model_kwargs)
+    assert get_model_inputs(model) == ["spikes", "spikes_mask", "spikes_timestamp", "spikes_lengths", "targets", "targets_lengths",
+                                       "block_idx", "day_idx"]
+    with pytest.raises(RuntimeError):                        # no CPU fallback
+        model(torch.zeros(1, 64, 256), torch.ones(1, 64, dtype=torch.int64), torch.zeros(1, 64, dtype=torch.int64), torch.tensor([64]),
+              torch.ones(1, 2, dtype=torch.int64), torch.tensor([2]))
+
+
+def test_unknown_method_and_ssl_asserts():
+    tr = lb.default_trainer_config()
+    with pytest.raises(Exception):
+        lb.NDT1(tr.model, method_name="nope")
+    with pytest.raises(AssertionError):                      # stacked inputs can't pretrain (ndt1.py:482)
+        mk = dict(active=True, mode="temporal", ratio=0.3, zero_ratio=1.0, random_ratio=1.0, expand_prob=0.0, max_timespan=1, regions=None, channels=None)
+        lb.NDT1(lb.update_config(tr.model, {"encoder": {"masker": {"active": mk}}}), method_name="mlm", loss="poisson_nll", log_input=True)
+
+
+def test_init_matches_reference_rng_order():
+    g = dict(np.load(os.path.join(G, "ctc_small.npz")))
+    cfg = lb.update_config(lb.default_model_config(), {"encoder": {
+        "embedder": {"n_channels": 16, "input_dim": 16, "max_F": 64, "dropout": 0.0, "stack": {"active": True, "size": 32, "stride": 4}},
+        "transformer": {"n_layers": 2, "hidden_size": 64, "n_heads": 4, "inter_size": 64, "dropout": 0.0},
+        "smooth_and_noise": {"noise": False}}})
+    torch.manual_seed(11)
+    model = lb.NDT1(cfg, method_name="ctc", vocab_size=41, blank_id=0, zero_infinity=True)
+    sd = model.state_dict()
+    ref = {k[len("param/"):]: v for k, v in g.items() if k.startswith("param/")}
+    assert list(sd.keys()) == list(ref.keys())
+    for k in sd:
+        assert np.array_equal(sd[k].numpy(), ref[k]), k     # bit-identical initialisation incl. fixup scaling
+
+
+def test_checkpoint_files_and_round_trip():
+    cfg = lb.update_config(lb.default_model_config(), {"encoder": {
+        "embedder": {"n_channels": 16, "input_dim": 16, "max_F": 64}, "transformer": {"n_layers": 1, "hidden_size": 32, "n_heads": 2, "inter_size": 32}}})
+    kw = dict(method_name="ctc", vocab_size=41, blank_id=0, zero_infinity=True)
+    torch.manual_seed(0)
+    a = lb.NDT1(cfg, **kw)
+    with tempfile.TemporaryDirectory() as d:
+        a.save_checkpoint(d)
+        assert sorted(os.listdir(d)) == ["decoder.bin", "encoder.bin", "encoder_config.pth"]
+        torch.manual_seed(5)
+        b = lb.NDT1(cfg, **kw)
+        b.load_checkpoint(d)
+        for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+            assert ka == kb and torch.equal(va, vb)
+        warm = lb.update_config(cfg, {"encoder": {"from_pt": d}})
+        c = lb.NDT1(warm, **kw)                               # warm start, ndt1.py:468-476,503-504
+        assert torch.equal(c.decoder[0].weight, a.decoder[0].weight)
+        enc_cfg = torch.load(os.path.join(d, "encoder_config.pth"), weights_only=False)
+        assert isinstance(enc_cfg, dict) and enc_cfg["embedder"]["n_channels"] == 16
+
+
+def test_host_collate_matches_reference_golden():
+    g = dict(np.load(os.path.join(G, "collate.npz")))
+    rows = []
+    order = ["spikes", "spikes_mask", "spikes_timestamp", "spikes_lengths", "targets", "targets_lengths", "sentence", "extra"]
+    for i in range(3):
+        r = {k[len(f"row{i}/"):]: v for k, v in g.items() if k.startswith(f"row{i}/")}
+        r["sentence"] = "abc"
+        rows.append({k: r[k] for k in order})
+    mi = ["spikes", "spikes_mask", "spikes_timestamp", "spikes_lengths", "targets", "targets_lengths"]
+    pads = {
+        "right": {k: dict(dim=0, side="right", value=0, truncate=None, min_length=None) for k in ("spikes", "spikes_mask", "spikes_timestamp", "targets")},
+        "left_trunc": {k: dict(dim=0, side="left", value=-1, truncate=40, min_length=None) for k in ("spikes", "spikes_mask", "spikes_timestamp", "targets")},
+        "minlen": {k: dict(dim=0, side="right", value=0, truncate=64, min_length=60) for k in ("spikes", "spikes_mask", "spikes_timestamp")},
+    }
+    for name, pd in pads.items():
+        padded, unused = lb.pad_collate_fn(rows, mi, pd)
+        assert sorted(unused.keys()) == list(g[f"{name}/unused_keys"])
+        for k, v in padded.items():
+            if torch.is_tensor(v):
+                assert np.array_equal(v.numpy(), g[f"{name}/{k}"]) and v.numpy().dtype == g[f"{name}/{k}"].dtype, (name, k)
+            else:
+                for i, vi in enumerate(v):
+                    assert np.array_equal(vi.numpy(), g[f"{name}/{k}/{i}"])
+    with pytest.raises(AssertionError):                      # min_length above truncate (datasets.py:201-205)
+        lb.padded_array([np.zeros(3)], truncate=2, min_length=5)
+    with pytest.raises(Exception):
+        lb.padded_array([np.zeros(3)], side="up")
+
+
+def test_format_ctc_quirk():
+    g = dict(np.load(os.path.join(G, "index_ops.npz")))
+    vocab = list(range(41))
+    for i in range(5):
+        assert lb.format_ctc(g[f"ctc_in/{i}"].tolist(), vocab, 0) == g[f"ctc_out/{i}"].tolist()
+    assert lb.format_ctc([1, 0, 1], vocab, 0) == [1]        # `last` only moves on emission
+
+
+def test_context_mask_matches_reference():
+    g = dict(np.load(os.path.join(G, "index_ops.npz")))
+    for key in [k for k in g if k.startswith("band/")]:
+        _, cf, cb = key.split("/")
+        assert np.array_equal(lb.create_context_mask(int(cf), int(cb), 12).numpy(), g[key]), key
+
+
+def test_onecycle_matches_torch():
+    lin = torch.nn.Linear(1, 1)
+    opt = torch.optim.AdamW(lin.parameters(), lr=1e-3)
+    sch = torch.optim.lr_scheduler.OneCycleLR(opt, total_steps=50, max_lr=1e-3, pct_start=0.2, anneal_strategy="cos", div_factor=25)
+    for step in range(50):
+        assert abs(opt.param_groups[0]["lr"] - onecycle_cos_lr(step, 50, 1e-3, 0.2, 25)) < 1e-12
+        opt.step()
+        if step < 49:
+            sch.step()
+
+
+def test_shard_batch_is_contiguous_split():
+    b = {"x": torch.arange(10), "y": torch.arange(20).view(10, 2), "s": "keep"}
+    parts = [shard_batch(b, r, 2) for r in range(2)]
+    assert torch.equal(torch.cat([p["x"] for p in parts]), b["x"]) and parts[0]["x"].tolist() == [0, 1, 2, 3, 4]
+    assert parts[1]["s"] == "keep"
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import ndt1_oracle as O
+    from test_oracle_golden import small_ctc_cfg, CTC_KW, sub, load
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = load("ctc_small.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g, "param").items()}
+    batch = {k: torch.from_numpy(v) for k, v in sub(g, "batch").items()}
+    batch = {k: torch.cat([v, v[:1]]) for k, v in batch.items()}           # 4 trials -> 2 per rank
+    shard = shard_batch(batch, rank, world)
+    _, grads = O.ndt1_loss_and_grads(params, small_ctc_cfg(), CTC_KW, shard, training=True)
+    names = sorted(grads)
+    flat = torch.cat([grads[n].reshape(-1) for n in names])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)                             # bucketed sum ...
+    flat /= world                                                          # ... then DDP's mean over ranks
+    if rank == 0:
+        _, full = O.ndt1_loss_and_grads(params, small_ctc_cfg(), CTC_KW, batch, training=True)
+        ref = torch.cat([full[n].reshape(-1) for n in names]) / world       # (1/world) * grad of the global SUM loss
+        q.put(float((flat - ref).abs().max() / ref.abs().max()))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_semantics_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    err = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert err < 1e-5

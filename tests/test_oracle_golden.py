@@ -1,0 +1,197 @@
+"""The oracle (oracle/ndt1_oracle.py) against golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ndt1_oracle as O  # noqa: E402
+from llm_bci_b200.config import default_model_config, update_config  # noqa: E402
+
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def load(name):
+    return dict(np.load(os.path.join(G, name), allow_pickle=False))
+
+
+def sub(d, prefix):
+    return {k[len(prefix) + 1:]: v for k, v in d.items() if k.startswith(prefix + "/")}
+
+
+def small_ctc_cfg():
+    return update_config(default_model_config(), {"encoder": {
+        "embedder": {"n_channels": 16, "input_dim": 16, "max_F": 64, "dropout": 0.0,
+                     "stack": {"active": True, "size": 32, "stride": 4}},
+        "transformer": {"n_layers": 2, "hidden_size": 64, "n_heads": 4, "inter_size": 64, "dropout": 0.0},
+        "smooth_and_noise": {"noise": False}}})
+
+
+CTC_KW = dict(method_name="ctc", vocab_size=41, blank_id=0, zero_infinity=True)
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+def test_ctc_small_loss_preds_grads():
+    g = load("ctc_small.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g, "param").items()}
+    batch = {k: torch.from_numpy(v) for k, v in sub(g, "batch").items()}
+    out, grads = O.ndt1_loss_and_grads(params, small_ctc_cfg(), CTC_KW, batch, training=True)
+    assert abs(float(out["loss"]) - float(g["out/loss"])) <= 2e-5 * abs(float(g["out/loss"]))
+    assert rel(out["preds"].detach().numpy(), g["out/preds"]) < 2e-5
+    gscale = max(np.abs(v).max() for v in sub(g, "grad").values())
+    for name, ref in sub(g, "grad").items():
+        got = grads[name].numpy()
+        tol = 5e-5 * max(np.abs(ref).max(), 1e-3 * gscale)
+        assert np.abs(got - ref).max() <= tol, name
+    # greedy decode identical
+    dec = [O.format_ctc(p.argmax(-1).tolist(), 0) for p in out["preds"].detach()]
+    flat = np.array([x for s in dec for x in s] + [-1], dtype=np.int64)
+    assert np.array_equal(flat, g["out/decoded_flat"])
+
+
+def test_ctc_small_fp64_matches_reference_fp32():
+    g = load("ctc_small.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g, "param").items()}
+    batch = {k: torch.from_numpy(v) for k, v in sub(g, "batch").items()}
+    out, grads = O.ndt1_loss_and_grads(params, small_ctc_cfg(), CTC_KW, batch, dtype=torch.float64, training=True)
+    assert abs(float(out["loss"]) - float(g["out/loss"])) <= 1e-5 * abs(float(g["out/loss"]))
+
+
+def test_ctc_small_injected_noise():
+    g0 = load("ctc_small.npz")
+    g = load("ctc_small_noise.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g0, "param").items()}
+    batch = {k: torch.from_numpy(v) for k, v in sub(g0, "batch").items()}
+    cfg = update_config(small_ctc_cfg(), {"encoder": {"smooth_and_noise": {"noise": True}}})
+    noise = {"white": torch.from_numpy(g["noise/white"]), "offset": torch.from_numpy(g["noise/offset"])}
+    out, grads = O.ndt1_loss_and_grads(params, cfg, CTC_KW, batch, training=True, noise=noise)
+    assert abs(float(out["loss"]) - float(g["out/loss"])) <= 2e-5 * abs(float(g["out/loss"]))
+    assert rel(out["preds"].detach().numpy(), g["out/preds"]) < 2e-5
+    for name, ref in sub(g, "grad").items():
+        assert rel(grads[name].numpy(), ref) < 1e-4, name
+
+
+def mlm_cfg():
+    mk = {"active": True, "mode": "temporal", "ratio": 0.3, "zero_ratio": 0.8, "random_ratio": 0.5, "expand_prob": 1.0,
+          "max_timespan": 3, "regions": None, "channels": None}
+    cfg = update_config(default_model_config(), {"encoder": {
+        "masker": {"active": mk},
+        "embedder": {"n_channels": 24, "input_dim": 16, "max_F": 64, "dropout": 0.0, "stack": {"active": False}},
+        "transformer": {"n_layers": 2, "hidden_size": 64, "n_heads": 4, "inter_size": 64, "dropout": 0.0},
+        "smooth_and_noise": {"noise": False},
+        "context": {"forward": 2, "backward": 5}}})
+    del cfg["encoder"]["masker"]["neuron"]
+    return cfg
+
+
+def test_mlm_small_with_masker():
+    g = load("mlm_small.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g, "param").items()}
+    batch = {k: torch.from_numpy(v) for k, v in sub(g, "batch").items()}
+    draws = [dict(mask=g["draw/mask"], zero=g["draw/zero"], random=g["draw/random"], rand=g["draw/rand"],
+                  timespan=int(g["draw/timespan"]))]
+    out, grads = O.ndt1_loss_and_grads(params, mlm_cfg(), dict(method_name="mlm", loss="poisson_nll", log_input=True), batch,
+                                       training=True, masker_draws=draws)
+    assert int(out["n_examples"]) == int(g["out/n_examples"])
+    assert np.array_equal(out["mask"].numpy(), g["out/mask"])
+    assert abs(float(out["loss"]) - float(g["out/loss"])) <= 2e-5 * abs(float(g["out/loss"]))
+    assert rel(out["preds"].detach().numpy(), g["out/preds"]) < 2e-5
+    gscale = max(np.abs(v).max() for v in sub(g, "grad").values())
+    for name, ref in sub(g, "grad").items():
+        tol = 5e-5 * max(np.abs(ref).max(), 1e-3 * gscale)
+        assert np.abs(grads[name].numpy() - ref).max() <= tol, name
+
+
+def test_masker_bit_exact():
+    g = load("masker.npz")
+    base = g["base"]
+    for name, mode in zip(g["modes"], g["mode_names"]):
+        for seed in (0, 1, 2, 7):
+            k = f"{name}/{seed}"
+            so, mo = O.masker_apply(base, str(mode), g[f"{k}/mask_draw"], g[f"{k}/zero"], g[f"{k}/random"], g[f"{k}/rand"],
+                                    int(g[f"{k}/timespan"]))
+            assert np.array_equal(mo, g[f"{k}/out_mask"]), k
+            assert np.array_equal(so.view(np.uint32), g[f"{k}/out_spikes"].view(np.uint32)), k
+
+
+def test_collate_bit_exact():
+    g = load("collate.npz")
+    rows = []
+    for i in range(3):
+        r = sub(g, f"row{i}")
+        r["sentence"] = "abc"
+        rows.append(r)
+    order = ["spikes", "spikes_mask", "spikes_timestamp", "spikes_lengths", "targets", "targets_lengths", "sentence", "extra"]
+    rows = [{k: r[k] for k in order} for r in rows]
+    model_inputs = ["spikes", "spikes_mask", "spikes_timestamp", "spikes_lengths", "targets", "targets_lengths"]
+    pads = {
+        "right": {k: dict(dim=0, side="right", value=0, truncate=None, min_length=None) for k in ("spikes", "spikes_mask", "spikes_timestamp", "targets")},
+        "left_trunc": {k: dict(dim=0, side="left", value=-1, truncate=40, min_length=None) for k in ("spikes", "spikes_mask", "spikes_timestamp", "targets")},
+        "minlen": {k: dict(dim=0, side="right", value=0, truncate=64, min_length=60) for k in ("spikes", "spikes_mask", "spikes_timestamp")},
+    }
+    for name, pd in pads.items():
+        padded, unused = O.pad_collate(rows, model_inputs, pd)
+        assert sorted(unused.keys()) == list(g[f"{name}/unused_keys"])
+        for k, v in padded.items():
+            if isinstance(v, np.ndarray):
+                assert v.dtype == g[f"{name}/{k}"].dtype and np.array_equal(v, g[f"{name}/{k}"]), (name, k)
+            else:
+                for i, vi in enumerate(v):
+                    assert np.array_equal(vi, g[f"{name}/{k}/{i}"]), (name, k, i)
+
+
+def test_context_band_and_greedy_collapse():
+    g = load("index_ops.npz")
+    for key in [k for k in g if k.startswith("band/")]:
+        _, cf, cb = key.split("/")
+        assert np.array_equal(O.context_band(int(cf), int(cb), 12), g[key]), key
+    for i in range(5):
+        assert O.format_ctc(g[f"ctc_in/{i}"].tolist(), 0) == g[f"ctc_out/{i}"].tolist()
+
+
+def test_ctc_numpy_matches_torch():
+    torch.manual_seed(0)
+    T, V = 23, 41
+    lp = torch.log_softmax(torch.randn(T, V, dtype=torch.float64), -1)
+    for tgt, tl, il in (([3, 3, 7, 1], 4, 23), ([5], 1, 9), ([2, 2, 2], 3, 4), ([], 0, 11), ([1, 2, 3, 4, 5, 6], 6, 6)):
+        logits = torch.randn(T, V, dtype=torch.float64, requires_grad=True)
+        lsm = torch.log_softmax(logits, -1)
+        tt = torch.tensor(tgt + [0] * (6 - len(tgt)), dtype=torch.int64)[None]
+        loss = torch.nn.functional.ctc_loss(lsm[:, None, :], tt, torch.tensor([il]), torch.tensor([tl]), blank=0,
+                                            reduction="none", zero_infinity=True).sum()
+        loss.backward()
+        nll, grad = O.ctc_loss_np(lsm.detach().numpy(), np.array(tgt + [0] * (6 - len(tgt))), il, tl, 0, True)
+        assert abs(nll - float(loss)) < 1e-9 * max(1.0, abs(nll))
+        assert np.abs(grad - logits.grad.numpy()).max() < 1e-9
+
+
+@pytest.mark.slow
+def test_full_size_b4_matches_reference():
+    g = load("ctc_full_b4.npz")
+    from llm_bci_b200.ndt1 import NDT1
+    from llm_bci_b200.config import default_trainer_config
+    tr = default_trainer_config()
+    cfg = update_config(tr["model"], {"encoder": {"embedder": {"dropout": 0.0}, "transformer": {"dropout": 0.0},
+                                                  "smooth_and_noise": {"noise": False}}})
+    torch.manual_seed(1)
+    model = NDT1(cfg, **tr["method"]["model_kwargs"], device="cpu", engine=False)
+    names = [n for n, _ in model.named_parameters()]
+    assert names == list(g["names"])
+    psum = np.array([float(p.detach().double().sum()) for p in model.parameters()])
+    assert np.allclose(psum, g["param_sum"], rtol=1e-9, atol=1e-9)   # same init order and RNG consumption
+    params = {k: v.detach() for k, v in model.state_dict().items()}
+    batch = O.synthetic_ctc_batch(B=4, T=1000, N=256, seed=1)
+    out, grads = O.ndt1_loss_and_grads(params, cfg, tr["method"]["model_kwargs"], batch, training=True)
+    assert abs(float(out["loss"]) - float(g["out/loss"])) <= 2e-5 * abs(float(g["out/loss"]))
+    gn = np.array([float(grads[n].double().norm()) for n in names])
+    scale = g["grad_norm"].max()
+    assert np.all(np.abs(gn - g["grad_norm"]) <= 2e-4 * np.maximum(g["grad_norm"], 1e-4 * scale))
