@@ -101,6 +101,15 @@ int ndt1_layernorm_fwd(const float* x, const float* gamma, const float* beta, fl
 int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K, int act, int precision,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* F.scaled_dot_product_attention with the reference's mask (models/ndt1.py:276-290, 30-41, 435-437),
+ * bf16 in/out: qkv (B*L, 3H) packed q|k|v, out/out_drop (B*L, H) before/after the output dropout,
+ * lse (B, heads, L).  With dout (gradient w.r.t. out) the backward runs too: dqkv (B*L, 3H),
+ * delta_ws (B, heads, L) scratch.  use_tensor_cores selects the tcgen05 kernels (head size 128,
+ * L <= 256) or the CUDA-core kernels. */
+int ndt1_attention_bf16(const void* qkv, void* out, void* out_drop, float* lse, const int64_t* key_valid, int B, int L, int H, int n_heads,
+                        int context_forward, int context_backward, float p_attn, float p_out, uint64_t seed, uint64_t site_attn,
+                        uint64_t site_out, const void* dout, void* dqkv, float* delta_ws, int use_tensor_cores, void* stream);
+
 /* torch.optim.AdamW step on one flat buffer, models/trainer.py:229,340. */
 int ndt1_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
@@ -198,6 +207,12 @@ int ndt1_engine_stage_count(const ndt1_engine* e);
 int ndt1_engine_wait_stage(ndt1_engine* e, int stage, void* stream);
 /* number of kernels launched by the last forward+backward (bench.py gpu_launches) */
 int64_t ndt1_engine_launch_count(const ndt1_engine* e);
+/* Measurement hooks (bench.py): between begin and end every tensor-core GEMM launch is bracketed by
+ * CUDA events on its own stream; end returns the summed algorithmic FLOPs, device milliseconds and
+ * the number of launches.  ndt1_launch_counter: kernels launched by this library on the calling thread. */
+int ndt1_profile_gemm_begin(void);
+int ndt1_profile_gemm_end(double* flops, double* ms, int64_t* launches);
+int64_t ndt1_launch_counter(void);
 /* keep-scale (0 or 1/(1-p)) of a dropout site, for tests: site 0 embed, 1+4*l attn-probs, 2+4*l attn-out, 3+4*l mlp */
 int ndt1_dropout_scales(float* out, int64_t n, float p, uint64_t seed, uint64_t site, void* stream);
 

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "ndt1_recon_loss": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "ndt1_layernorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p]),
     "ndt1_linear_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "ndt1_attention_bf16": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _u64, _u64, _u64, _p, _p, _p, _i, _p]),
     "ndt1_adamw_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _p]),
     "ndt1_engine_create": (_i, [C.POINTER(Config), C.POINTER(_p)]),
     "ndt1_engine_destroy": (None, [_p]),
@@ -87,6 +88,9 @@ PROTOTYPES = {
     "ndt1_engine_launch_count": (_i64, [_p]),
     "ndt1_engine_stage_count": (_i, [_p]),
     "ndt1_engine_wait_stage": (_i, [_p, _i, _p]),
+    "ndt1_profile_gemm_begin": (_i, []),
+    "ndt1_profile_gemm_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "ndt1_launch_counter": (_i64, []),
     "ndt1_dropout_scales": (_i, [_p, _i64, _f, _u64, _u64, _p]),
 }
 

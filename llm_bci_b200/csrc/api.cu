@@ -78,6 +78,28 @@ int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y,
   return gemm_tc_launch(p, s);
 }
 
+int ndt1_attention_bf16(const void* qkv, void* out, void* out_drop, float* lse, const int64_t* key_valid, int B, int L, int H, int n_heads,
+                        int context_forward, int context_backward, float p_attn, float p_out, uint64_t seed, uint64_t site_attn,
+                        uint64_t site_out, const void* dout, void* dqkv, float* delta_ws, int use_tensor_cores, void* stream) {
+  AttnParams ap;
+  ap.qkv = qkv; ap.out = out; ap.out_drop = out_drop ? out_drop : out; ap.lse = lse; ap.key_valid = (const long long*)key_valid;
+  ap.B = B; ap.L = L; ap.H = H; ap.nh = n_heads; ap.hd = H / n_heads;
+  const int unb = 1 << 29;
+  if (context_forward == -2 && context_backward == -2) { ap.ctx_fwd = unb; ap.ctx_bwd = unb; }
+  else { ap.ctx_fwd = context_forward >= -1 ? context_forward : unb; ap.ctx_bwd = context_backward >= -1 ? context_backward : unb; }
+  ap.scale = 1.0f / sqrtf((float)ap.hd); ap.p_attn = p_attn; ap.p_out = p_out; ap.seed = seed; ap.stream_attn = site_attn; ap.stream_out = site_out;
+  ap.dout = dout; ap.dqkv = dqkv; ap.delta = delta_ws;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool tcp = use_tensor_cores && k_attention_tc_supported(ap);
+  NDT1_REQUIRE(!use_tensor_cores || tcp, "attention_bf16: tensor-core path needs head size 128 and at most 256 tokens");
+  if (tcp) NDT1_TRY(k_attention_tc_fwd(ap, s)); else NDT1_TRY(k_attention_fwd<bf16>(ap, s));
+  if (dout) {
+    NDT1_REQUIRE(dqkv && delta_ws, "attention_bf16: backward needs dqkv and delta_ws");
+    if (tcp) NDT1_TRY(k_attention_tc_bwd(ap, s)); else NDT1_TRY(k_attention_bwd<bf16>(ap, s));
+  }
+  return 0;
+}
+
 int ndt1_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int step, float grad_scale, void* stream) {
   return k_adamw(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream);
@@ -91,6 +113,15 @@ __global__ void dropout_scales_kernel(float* out, long long n, float p, unsigned
     out[i] = drop_scale_1(seed, site, (unsigned long long)i, thr, ik);
 }
 }  // namespace
+
+int ndt1_profile_gemm_begin(void) { return gemm_tc_profile_begin(); }
+int ndt1_profile_gemm_end(double* flops, double* ms, int64_t* launches) {
+  long long n = 0;
+  const int rc = gemm_tc_profile_end(flops, ms, &n);
+  *launches = n;
+  return rc;
+}
+int64_t ndt1_launch_counter(void) { return g_ndt1_launches; }
 
 int ndt1_dropout_scales(float* out, int64_t n, float p, uint64_t seed, uint64_t site, void* stream) {
   if (n == 0) return 0;

@@ -313,6 +313,17 @@ int k_attention_bwd(const AttnParams& p, cudaStream_t stream) {
   return 0;
 }
 
+template <typename T>
+int k_attention_delta(const AttnParams& p, cudaStream_t stream) {
+  const long long rows = (long long)p.B * p.L * p.nh;
+  if (rows == 0) return 0;
+  attn_delta_kernel<T><<<ndt1_cdiv(rows, 8), 256, 0, stream>>>(p);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+template int k_attention_delta<float>(const AttnParams&, cudaStream_t);
+template int k_attention_delta<bf16>(const AttnParams&, cudaStream_t);
+
 template int k_attention_fwd<float>(const AttnParams&, cudaStream_t);
 template int k_attention_fwd<bf16>(const AttnParams&, cudaStream_t);
 template int k_attention_bwd<float>(const AttnParams&, cudaStream_t);

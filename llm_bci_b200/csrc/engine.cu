@@ -57,7 +57,8 @@ template <typename T>
 struct Engine : ndt1_engine {
   static constexpr int kBf16 = IsBf16<T>::v;
   Arena ar;
-  bool force_simt = false;
+  bool force_simt = false;      // NDT1_FORCE_SIMT=1: every GEMM and the attention on the CUDA cores (debug)
+  bool simt_attention = false;  // NDT1_SIMT_ATTENTION=1: only the attention on the CUDA cores
   int n_prefix = 0;
   // arena views ------------------------------------------------------------
   T* xin = nullptr; int ldN = 0;
@@ -134,6 +135,8 @@ struct Engine : ndt1_engine {
     n_prefix = (c.block_token ? 1 : 0) + (c.day_token ? 1 : 0);
     const char* fs = getenv("NDT1_FORCE_SIMT");
     force_simt = fs && fs[0] == '1';
+    const char* sa = getenv("NDT1_SIMT_ATTENTION");
+    simt_attention = sa && sa[0] == '1';
     carve();                       // dry run: sizes only
     ar.cap = ar.off + 256; ar.off = 0;
     NDT1_CUDA_CHECK(cudaMalloc((void**)&ar.base, ar.cap));
@@ -219,7 +222,7 @@ struct Engine : ndt1_engine {
     NDT1_REQUIRE(bt->B >= 0 && bt->B <= k.max_batch, "engine: batch %d exceeds max_batch %d", bt->B, k.max_batch);
     NDT1_REQUIRE(bt->T <= k.max_T, "engine: %d bins exceed max_T %d", bt->T, k.max_T);
     NDT1_REQUIRE(!k.stack_active || bt->T >= k.stack_size, "engine: %d bins are fewer than the stack size %d", bt->T, k.stack_size);
-    NDT1_REQUIRE(bt->T <= k.max_F || !k.pos, "engine: %d bins exceed max_F %d", bt->T, k.max_F);
+    NDT1_REQUIRE(!k.pos || out_len(bt->T) <= k.max_F, "engine: %d positions exceed max_F %d", out_len(bt->T), k.max_F);
     NDT1_REQUIRE(k.method != NDT1_METHOD_CTC || bt->S <= k.max_targets, "engine: %d targets exceed max_targets %d", bt->S, k.max_targets);
     B = bt->B; Tn = bt->T; Tp = out_len(Tn); L = n_prefix + Tp; S = bt->S; training = bt->training; seed = bt->seed;
     spikes_ptr = bt->spikes; ts_ptr = (const long long*)bt->spikes_timestamp; block_ptr = (const long long*)bt->block_idx; day_ptr = (const long long*)bt->day_idx;
@@ -319,7 +322,8 @@ struct Engine : ndt1_engine {
       ap.scale = 1.0f / sqrtf((float)(H / k.n_heads)); ap.p_attn = ptr_; ap.p_out = ptr_;
       ap.seed = seed; ap.stream_attn = site_attn_p(l); ap.stream_out = site_attn_o(l);
       ap.dout = nullptr; ap.dqkv = nullptr; ap.delta = nullptr;
-      NDT1_TRY(k_attention_fwd<T>(ap, s));
+      if (kBf16 && !force_simt && !simt_attention && k_attention_tc_supported(ap)) NDT1_TRY(k_attention_tc_fwd(ap, s));
+      else NDT1_TRY(k_attention_fwd<T>(ap, s));
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = xm; e.ldc = H; e.bias = k.attention_bias ? q.o_b : nullptr; e.resid = xa;
@@ -509,7 +513,8 @@ struct Engine : ndt1_engine {
       ap.scale = 1.0f / sqrtf((float)(H / k.n_heads)); ap.p_attn = ptr_; ap.p_out = ptr_;
       ap.seed = seed; ap.stream_attn = site_attn_p(l); ap.stream_out = site_attn_o(l);
       ap.dout = dA; ap.dqkv = dqkv; ap.delta = delta;
-      NDT1_TRY(k_attention_bwd<T>(ap, s));
+      if (kBf16 && !force_simt && !simt_attention && k_attention_tc_supported(ap)) NDT1_TRY(k_attention_tc_bwd(ap, s));
+      else NDT1_TRY(k_attention_bwd<T>(ap, s));
       float* gw[3] = {gq.q_w, gq.k_w, gq.v_w}; float* gb[3] = {gq.q_b, gq.k_b, gq.v_b};
       for (int j = 0; j < 3; ++j) {
         if (gb[j] && k.attention_bias) NDT1_TRY(k_colsum<T>(dqkv + (long long)j * H, gb[j], M, H, 3 * H, s));

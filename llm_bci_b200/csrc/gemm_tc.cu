@@ -12,10 +12,11 @@
 //   GEMM_NN  A K-major,  B MN-major     (data gradients, reads the forward weight)
 //   GEMM_TN  A MN-major, B MN-major     (weight gradients, split over the reduction)
 // so no transposed copy of a weight or an activation is ever materialised.
-#include <cuda.h>
+#include "tc_common.cuh"
 #include "gemm_common.cuh"
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 namespace {
 
@@ -31,95 +32,11 @@ struct TcParams {
   int a_row_shift, a_col_shift, b_row_shift, b_col_shift, b_chunk_n;
   int split_k;
   int m_tiles, n_tiles, total_tiles;
+  int chunk_k_valid;                   // reduction length per chunk in elements (for FLOP accounting)
   GemmEpilogue epi;
 };
 
-// ---------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap, never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor (SWIZZLE_128B, sm_100 "version 1").
-//   K-major : rows of 128 B; 8-row groups SBO = 1024 B apart; LBO unused
-//   MN-major: 64-element (128 B) column chunks, LBO = bytes between chunks,
-//             8-k-row groups SBO = 1024 B apart
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
-  return d;
-}
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
+using namespace tc;
 
 // ---------------------------------------------------------------------------
 // Epilogue over 8 consecutive columns of one row (vector path).
@@ -412,6 +329,12 @@ struct MapKeyHash {
 };
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
+// optional per-launch timing of the tensor-core GEMM (bench.py roofline): CUDA events on the launch stream
+struct ProfRec { cudaEvent_t e0, e1; double flops; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+size_t g_prof_used = 0;
+
 int make_map(const GemmOperand& o, int box_cols, int box_rows, CUtensorMap* out) {
   NDT1_REQUIRE(((uintptr_t)o.ptr & 15) == 0, "gemm_tc: operand pointer not 16-byte aligned");
   NDT1_REQUIRE(o.ld % 8 == 0, "gemm_tc: operand row stride %d not a multiple of 8 elements", o.ld);
@@ -446,8 +369,20 @@ int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp
     attr_set = true;
   }
   const int grid = tp.total_tiles < g_num_sms ? tp.total_tiles : g_num_sms;
+  ProfRec* rec = nullptr;
+  if (g_prof_on) {
+    if (g_prof_used == g_prof.size()) {
+      ProfRec r; r.flops = 0;
+      NDT1_CUDA_CHECK(cudaEventCreate(&r.e0)); NDT1_CUDA_CHECK(cudaEventCreate(&r.e1));
+      g_prof.push_back(r);
+    }
+    rec = &g_prof[g_prof_used++];
+    rec->flops = 2.0 * tp.M * (double)tp.N * (double)tp.nchunk * tp.chunk_k_valid * (tp.mode == GEMM_TN ? 1 : tp.nb_out);
+    NDT1_CUDA_CHECK(cudaEventRecord(rec->e0, stream));
+  }
   gemm_tc_kernel<BN, MODE><<<grid, kThreads, SMEM, stream>>>(ma, mb, tp);
   NDT1_CHECK_LAUNCH();
+  if (rec) NDT1_CUDA_CHECK(cudaEventRecord(rec->e1, stream));
   return 0;
 }
 
@@ -459,6 +394,8 @@ int launch_mode(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const TcPa
 }
 
 }  // namespace
+
+int tc_make_map(const GemmOperand& o, int box_cols, int box_rows, CUtensorMap* out) { return make_map(o, box_cols, box_rows, out); }
 
 int gemm_tc_init() {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -493,7 +430,7 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
 
   TcParams tp;
   tp.mode = p.mode; tp.M = p.M; tp.N = p.N; tp.nb_out = p.nb_out;
-  tp.nchunk = p.nchunk; tp.kb_per_chunk = ndt1_cdiv(p.chunk_k, BK);
+  tp.nchunk = p.nchunk; tp.kb_per_chunk = ndt1_cdiv(p.chunk_k, BK); tp.chunk_k_valid = p.chunk_k;
   tp.a_row_shift = p.a_row_shift; tp.a_col_shift = p.a_col_shift;
   tp.b_row_shift = p.b_row_shift; tp.b_col_shift = p.b_col_shift;
   tp.b_chunk_n = p.b_chunk_n > 0 ? p.b_chunk_n : p.N;
@@ -515,4 +452,22 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   NDT1_TRY(make_map(p.A, BK, BM, &ma));
   NDT1_TRY(make_map(p.B, BK, bn, &mb));
   return launch_mode<GEMM_NT>(bn, ma, mb, tp, stream);
+}
+
+// ---- profiling hooks (C ABI wrappers in api.cu) ----
+int gemm_tc_profile_begin() {
+  g_prof_used = 0; g_prof_on = true;
+  return 0;
+}
+int gemm_tc_profile_end(double* flops, double* ms, long long* launches) {
+  g_prof_on = false;
+  double f = 0, t = 0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    NDT1_CUDA_CHECK(cudaEventSynchronize(g_prof[i].e1));
+    float m = 0;
+    NDT1_CUDA_CHECK(cudaEventElapsedTime(&m, g_prof[i].e0, g_prof[i].e1));
+    f += g_prof[i].flops; t += m;
+  }
+  *flops = f; *ms = t; *launches = (long long)g_prof_used;
+  return 0;
 }

@@ -62,6 +62,11 @@ struct AttnParams {
 };
 template <typename T> int k_attention_fwd(const AttnParams& p, cudaStream_t stream);
 template <typename T> int k_attention_bwd(const AttnParams& p, cudaStream_t stream);
+template <typename T> int k_attention_delta(const AttnParams& p, cudaStream_t stream);
+// attention_tc.cu (tcgen05 path: bf16, head size 128, at most 256 tokens)
+bool k_attention_tc_supported(const AttnParams& p);
+int k_attention_tc_fwd(const AttnParams& p, cudaStream_t stream);
+int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream);
 
 // ctc.cu
 int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaStream_t stream);

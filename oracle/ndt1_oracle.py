@@ -308,7 +308,12 @@ _ACTS: Dict[str, Callable[[torch.Tensor], torch.Tensor]] = {
 
 def _drop(x: torch.Tensor, site: str, drop_scales: Optional[dict]) -> torch.Tensor:
     """Dropout with an injected keep-scale tensor (0 or 1/(1-p)); absent -> identity."""
-    if drop_scales is None or site not in drop_scales:
+    if drop_scales is None:
+        return x
+    if "torch_dropout" in drop_scales:     # CPU-baseline mode: the reference's own nn.Dropout / SDPA dropout cost
+        p = drop_scales["torch_dropout"]["embed" if site == "embed" else "transformer"]
+        return F.dropout(x, p, True) if p > 0 else x
+    if site not in drop_scales:
         return x
     return x * drop_scales[site].to(x.dtype).reshape(x.shape)
 

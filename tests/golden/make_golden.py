@@ -92,6 +92,14 @@ def main():
     R = import_reference()
     update_config, NDT1 = R["update_config"], R["NDT1"]
     torch.set_num_threads(8)
+    only_full = "--only-full" in sys.argv
+    if not only_full:
+        small_cases(R)
+    full_case(R)
+
+
+def small_cases(R):
+    update_config, NDT1 = R["update_config"], R["NDT1"]
 
     # ------------------------------------------------------------------ 1. small CTC, eval-like numerics
     trainer = update_config("configs/trainer_ctc_ndt1.yaml", None)
@@ -258,6 +266,10 @@ def main():
         d[f"ctc_out/{i}"] = np.array(R["format_ctc"](s, list(range(41)), 0), dtype=np.int64)
     np.savez_compressed(os.path.join(HERE, "index_ops.npz"), **d)
 
+
+
+def full_case(R):
+    update_config, NDT1 = R["update_config"], R["NDT1"]
     # ------------------------------------------------------------------ 7. full-size model (config 2 architecture), B=4
     trainer = update_config("configs/trainer_ctc_ndt1.yaml", None)
     cfg_f = update_config(copy.deepcopy(dict(trainer.model)), {"encoder": {
@@ -285,8 +297,23 @@ def main():
     d["grad_slice/encoder.layers.0.attn.value.weight"] = grads_f["encoder.layers.0.attn.value.weight"][:8, :].numpy()
     d["grad_slice/encoder.embedder.stack_projection.weight"] = grads_f["encoder.embedder.stack_projection.weight"][:4, :].numpy()
     d["grad_slice/encoder.embedder.embed_pos.weight"] = grads_f["encoder.embedder.embed_pos.weight"][:4, :].numpy()
+    # the same model and batch in float64 (the reference module runs in double): the
+    # higher-precision target for the 1e-4 check of the fp32 CUDA mode
+    model_d = NDT1(cfg_f, **trainer.method.model_kwargs).double()
+    model_d.load_state_dict({k: v.double() for k, v in model_f.state_dict().items()})
+    fbd = {k: (v.double() if v.is_floating_point() else v) for k, v in fb.items()}
+    out_d, grads_d = run_ref(model_d, fbd, train=True)
+    d["out64/loss"] = out_d.loss.detach().numpy()
+    d["grad_norm64"] = np.array([float(grads_d[n].norm()) for n in names])
+    for n in ("decoder.0.weight", "decoder.0.bias", "encoder.out_norm.weight", "encoder.layers.0.ln1.weight",
+              "encoder.layers.4.mlp.down_proj.bias", "encoder.layers.2.attn.query.bias", "encoder.embedder.embed_spikes.weight",
+              "encoder.embedder.stack_projection.bias"):
+        d[f"grad64/{n}"] = grads_d[n].numpy().astype(np.float32)   # fp64 result rounded once to fp32 for storage
+    d["grad64_slice/encoder.layers.0.attn.value.weight"] = grads_d["encoder.layers.0.attn.value.weight"][:8, :].numpy().astype(np.float32)
+    d["grad64_slice/encoder.embedder.stack_projection.weight"] = grads_d["encoder.embedder.stack_projection.weight"][:4, :].numpy().astype(np.float32)
+    d["grad64_slice/encoder.embedder.embed_pos.weight"] = grads_d["encoder.embedder.embed_pos.weight"][:4, :].numpy().astype(np.float32)
     np.savez_compressed(os.path.join(HERE, "ctc_full_b4.npz"), **d)
-    print("ctc_full_b4 loss", float(out_f.loss))
+    print("ctc_full_b4 loss", float(out_f.loss), "fp64", float(out_d.loss))
 
 
 if __name__ == "__main__":
