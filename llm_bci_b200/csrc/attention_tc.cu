@@ -52,10 +52,9 @@ struct PhiloxRow {   // cached Philox block for consecutive element indices
     seed = s; stream = st; ctr = ~0ull; thr = drop_threshold(p); ik = 1.0f / (1.0f - p);
   }
   __device__ __forceinline__ float scale(unsigned long long elem) {
-    const unsigned long long c = elem >> 2;
+    const unsigned long long c = elem >> 3;
     if (c != ctr) { ctr = c; r = philox4x32_10(seed, c, stream); }
-    const uint32_t u = (elem & 3) == 0 ? r.x : (elem & 3) == 1 ? r.y : (elem & 3) == 2 ? r.z : r.w;
-    return u >= thr ? ik : 0.f;
+    return philox_u16(r, (int)(elem & 7)) >= thr ? ik : 0.f;
   }
 };
 
@@ -188,11 +187,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 4; ++i) { v[i] = __uint_as_float(raw[j + i]) * inv; ob[j + i] = __float2bfloat16_rn(v[i]); }
         if (p.p_out > 0.f) {
-          const Philox4 r = philox4x32_10(p.seed, (unsigned long long)(o + j) >> 2, p.stream_out);
-          od[j + 0] = __float2bfloat16_rn(v[0] * (r.x >= thr_o ? iko : 0.f));
-          od[j + 1] = __float2bfloat16_rn(v[1] * (r.y >= thr_o ? iko : 0.f));
-          od[j + 2] = __float2bfloat16_rn(v[2] * (r.z >= thr_o ? iko : 0.f));
-          od[j + 3] = __float2bfloat16_rn(v[3] * (r.w >= thr_o ? iko : 0.f));
+          float ds[4];
+          drop_scale_4(p.seed, p.stream_out, (unsigned long long)(o + j), thr_o, iko, ds);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) od[j + i] = __float2bfloat16_rn(v[i] * ds[i]);
         }
       }
 #pragma unroll

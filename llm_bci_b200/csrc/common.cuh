@@ -81,9 +81,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------
-// Philox4x32-10, counter based.  One call yields 4 uniform u32 for the 4
-// consecutive elements [4*ctr, 4*ctr+3] of logical stream `stream`.
-// Dropout keeps an element iff its u32 >= threshold(p) (see drop_threshold).
+// Philox4x32-10, counter based: (seed, counter, stream) -> 4 uniform u32.
 // Forward and backward kernels index by ELEMENT, never by thread, so the mask
 // is reproducible whatever the launch geometry.
 // ---------------------------------------------------------------------------
@@ -108,19 +106,39 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_
   return o;
 }
 
+// Dropout draws use 16 bits per element: one Philox block (4 x u32 = 8 x u16) covers the 8
+// consecutive elements [8*ctr, 8*ctr+7].  An element is kept iff its u16 >= drop_threshold(p),
+// i.e. P(drop) = round(p * 65536) / 65536 (|error| < 8e-6).
 __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
-  // keep iff u32 >= thr  ->  P(drop) = thr / 2^32
-  double t = (double)p * 4294967296.0;
+  double t = (double)p * 65536.0 + 0.5;
   if (t <= 0.0) return 0u;
-  if (t >= 4294967295.0) return 4294967295u;
+  if (t >= 65535.0) return 65535u;
   return (uint32_t)t;
+}
+__device__ __forceinline__ uint32_t philox_u16(const Philox4& r, int lane) {   // lane in [0, 8)
+  const uint32_t w = (lane >> 1) == 0 ? r.x : (lane >> 1) == 1 ? r.y : (lane >> 1) == 2 ? r.z : r.w;
+  return (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
 // keep-scale (0 or 1/(1-p)) of one element of a dropout site
 __device__ __forceinline__ float drop_scale_1(uint64_t seed, uint64_t stream, uint64_t elem, uint32_t thr, float inv_keep) {
-  Philox4 r = philox4x32_10(seed, elem >> 2, stream);
-  uint32_t u = (elem & 3) == 0 ? r.x : (elem & 3) == 1 ? r.y : (elem & 3) == 2 ? r.z : r.w;
-  return u >= thr ? inv_keep : 0.f;
+  const Philox4 r = philox4x32_10(seed, elem >> 3, stream);
+  return philox_u16(r, (int)(elem & 7)) >= thr ? inv_keep : 0.f;
+}
+// keep-scales of the 4 consecutive elements starting at elem (elem % 4 == 0)
+__device__ __forceinline__ void drop_scale_4(uint64_t seed, uint64_t stream, uint64_t elem, uint32_t thr, float ik, float* o) {
+  const Philox4 r = philox4x32_10(seed, elem >> 3, stream);
+  const uint32_t w0 = (elem & 4) ? r.z : r.x, w1 = (elem & 4) ? r.w : r.y;
+  o[0] = (w0 & 0xFFFFu) >= thr ? ik : 0.f; o[1] = (w0 >> 16) >= thr ? ik : 0.f;
+  o[2] = (w1 & 0xFFFFu) >= thr ? ik : 0.f; o[3] = (w1 >> 16) >= thr ? ik : 0.f;
+}
+// keep-scales of the 8 consecutive elements starting at elem (elem % 8 == 0)
+__device__ __forceinline__ void drop_scale_8(uint64_t seed, uint64_t stream, uint64_t elem, uint32_t thr, float ik, float* o) {
+  const Philox4 r = philox4x32_10(seed, elem >> 3, stream);
+  o[0] = (r.x & 0xFFFFu) >= thr ? ik : 0.f; o[1] = (r.x >> 16) >= thr ? ik : 0.f;
+  o[2] = (r.y & 0xFFFFu) >= thr ? ik : 0.f; o[3] = (r.y >> 16) >= thr ? ik : 0.f;
+  o[4] = (r.z & 0xFFFFu) >= thr ? ik : 0.f; o[5] = (r.z >> 16) >= thr ? ik : 0.f;
+  o[6] = (r.w & 0xFFFFu) >= thr ? ik : 0.f; o[7] = (r.w >> 16) >= thr ? ik : 0.f;
 }
 
 // Box-Muller on two u32 -> two N(0,1)

@@ -39,99 +39,140 @@ __global__ void log_softmax_kernel(const float* __restrict__ logits, float* __re
 
 struct CtcParams {
   const float* logp; const long long* targets; const long long* in_len; const long long* tgt_len;
-  int B, L, V, S, blank, zero_infinity;
+  int B, L, V, S, blank, zero_infinity, lp_in_smem;
   float* alpha; float* nll; float* dlogits; const float* dloss;
 };
 
+constexpr int kRenorm = 8;   // re-centre the alpha/beta rows every kRenorm frames
+
+__device__ __forceinline__ float block_max(float v, float* red, int nwarps) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float m = -INFINITY;
+  for (int w = 0; w < nwarps; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  return m;
+}
+
+// One CTA per trial, one thread per state of the extended label sequence.
+// Rows are kept re-centred (alpha_hat = alpha - C_t, beta_hat = beta - D_t with the offsets in double),
+// so the fp32 log-space values stay O(10) instead of O(loss): posteriors keep ~1e-6 relative accuracy
+// where plain fp32 log-space CTC (torch's kernel included) loses ~3e-5 on a 250-frame utterance.
 __global__ void ctc_kernel(const CtcParams p) {
-  extern __shared__ float sm[];
-  const int b = blockIdx.x;
-  const int LX = 2 * p.S + 1;                  // allocated states per trial
-  int* ext = (int*)sm;                         // [LX]
-  float* row0 = sm + LX;                       // [LX + 2] (two leading -inf pads)
-  float* row1 = row0 + LX + 2;
-  float* post = row1 + LX + 2;                 // [V]
-  __shared__ float s_ll;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int b = blockIdx.x, tid = threadIdx.x, nwarps = blockDim.x >> 5;
+  const int LX = 2 * p.S + 1;
+  double* Cs = (double*)sm_raw;                     // [L] forward offsets
+  float* row0 = (float*)(Cs + p.L);                 // [LX + 4] (2 pads each side)
+  float* row1 = row0 + LX + 4;
+  float* post = row1 + LX + 4;                      // [2][V]
+  float* red = post + 2 * p.V;                      // [32]
+  float* lp_s = red + 32;                           // [L*V] when it fits
+  __shared__ double s_ll;
 
   int S = (int)p.tgt_len[b];
-  if (S < 0) S = 0;
-  if (S > p.S) S = p.S;
+  S = S < 0 ? 0 : (S > p.S ? p.S : S);
   const int Lx = 2 * S + 1;
-  long long tn_ll = p.in_len[b];
-  int Tn = tn_ll > p.L ? p.L : (int)tn_ll;
-  const float* lp = p.logp + (long long)b * p.L * p.V;
+  const long long tn_ll = p.in_len[b];
+  const int Tn = tn_ll > p.L ? p.L : (int)tn_ll;
+  const float* lp_g = p.logp + (long long)b * p.L * p.V;
+  const float* lp = p.lp_in_smem ? lp_s : lp_g;
   float* alpha = p.alpha + (long long)b * p.L * LX;
   float* dl = p.dlogits ? p.dlogits + (long long)b * p.L * p.V : nullptr;
 
-  for (int s = threadIdx.x; s < Lx; s += blockDim.x) ext[s] = (s & 1) ? (int)p.targets[(long long)b * p.S + (s >> 1)] : p.blank;
-  if (threadIdx.x < 2) { row0[threadIdx.x] = -INFINITY; row1[threadIdx.x] = -INFINITY; }
+  if (p.lp_in_smem) for (int i = tid; i < p.L * p.V; i += blockDim.x) lp_s[i] = lp_g[i];
+  for (int i = tid; i < 2 * (LX + 4); i += blockDim.x) row0[i] = -INFINITY;
+  for (int i = tid; i < 2 * p.V; i += blockDim.x) post[i] = 0.f;
+  const int s = tid;
+  const bool live = s < Lx;
+  const int my = live ? ((s & 1) ? (int)p.targets[(long long)b * p.S + (s >> 1)] : p.blank) : p.blank;
+  const int my_m2 = (live && s >= 2) ? ((s & 1) ? (int)p.targets[(long long)b * p.S + ((s - 2) >> 1)] : p.blank) : -1;
+  const int my_p2 = (s + 2 < Lx) ? ((s & 1) ? (int)p.targets[(long long)b * p.S + ((s + 2) >> 1)] : p.blank) : -1;
+  const bool skip_b = live && s >= 2 && my != p.blank && my != my_m2;       // alpha: s-2 -> s allowed
+  const bool skip_f = (s + 2 < Lx) && my_p2 != p.blank && my_p2 != my;       // beta:  s -> s+2 allowed
   __syncthreads();
 
-  float ll = -INFINITY;
+  double ll = -INFINITY;
   if (Tn > 0) {
     float* prev = row0 + 2; float* cur = row1 + 2;
-    // t = 0
-    for (int s = threadIdx.x; s < Lx; s += blockDim.x) {
-      const float a = (s < 2) ? lp[ext[s]] : -INFINITY;
-      prev[s] = a; alpha[s] = a;
-    }
+    double Coff = 0.0;
+    float a = (live && s < 2) ? lp[my] : -INFINITY;
+    if (live) { prev[s] = a; alpha[s] = a; }
+    if (tid == 0) Cs[0] = 0.0;
     __syncthreads();
     for (int t = 1; t < Tn; ++t) {
-      for (int s = threadIdx.x; s < Lx; s += blockDim.x) {
-        const float e = lp[(long long)t * p.V + ext[s]];
-        float a = lse2(prev[s], prev[s - 1]);
-        if (s >= 2 && ext[s] != p.blank && ext[s] != ext[s - 2]) a = lse2(a, prev[s - 2]);
+      a = -INFINITY;
+      if (live) {
+        const float e = lp[(long long)t * p.V + my];
+        a = lse2(prev[s], prev[s - 1]);
+        if (skip_b) a = lse2(a, prev[s - 2]);
         a = (a == -INFINITY) ? -INFINITY : a + e;
-        cur[s] = a; alpha[(long long)t * LX + s] = a;
       }
+      if ((t % kRenorm) == kRenorm - 1) {
+        const float mx = block_max(a, red, nwarps);
+        if (mx != -INFINITY) { a = (a == -INFINITY) ? a : a - mx; Coff += (double)mx; }
+      }
+      if (live) { cur[s] = a; alpha[(long long)t * LX + s] = a; }
+      if (tid == 0) Cs[t] = Coff;
       __syncthreads();
       float* tmp = prev; prev = cur; cur = tmp;
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       float v = prev[Lx - 1];
       if (Lx > 1) v = lse2(v, prev[Lx - 2]);
-      s_ll = v;
+      s_ll = (v == -INFINITY) ? -INFINITY : Coff + (double)v;
     }
     __syncthreads();
     ll = s_ll;
   } else if (S == 0) {
-    ll = 0.f;
+    ll = 0.0;
   }
-  const bool feasible = ll != -INFINITY && ll == ll;
-  if (threadIdx.x == 0) p.nll[b] = feasible ? -ll : (p.zero_infinity ? 0.f : INFINITY);
+  const bool feasible = (ll != -INFINITY) && (ll == ll);
+  if (tid == 0) p.nll[b] = feasible ? (float)(-ll) : (p.zero_infinity ? 0.f : INFINITY);
   if (!dl) return;
   const float gs = p.dloss ? *p.dloss : 1.f;
-  // rows beyond the input length (and infeasible trials) receive zero gradient
   const int t_zero_from = (feasible && Tn > 0) ? Tn : 0;
-  for (long long e = (long long)t_zero_from * p.V + threadIdx.x; e < (long long)p.L * p.V; e += blockDim.x) dl[e] = 0.f;
+  for (long long e = (long long)t_zero_from * p.V + tid; e < (long long)p.L * p.V; e += blockDim.x) dl[e] = 0.f;
   if (!feasible || Tn <= 0) return;
 
-  // backward sweep; beta rows padded with two trailing -inf
-  float* prev = row0; float* cur = row1;       // use [0, Lx) + 2 trailing pads
+  // backward sweep: rows indexed from 0 with two trailing -inf pads
   __syncthreads();
-  for (int s = threadIdx.x; s < Lx + 2; s += blockDim.x) { prev[s] = -INFINITY; cur[s] = -INFINITY; }
+  for (int i = tid; i < 2 * (LX + 4); i += blockDim.x) row0[i] = -INFINITY;
   __syncthreads();
+  float* prev = row0; float* cur = row1;
+  double Doff = 0.0;
   for (int t = Tn - 1; t >= 0; --t) {
-    for (int c = threadIdx.x; c < p.V; c += blockDim.x) post[c] = 0.f;
-    __syncthreads();
-    for (int s = threadIdx.x; s < Lx; s += blockDim.x) {
-      const float e = lp[(long long)t * p.V + ext[s]];
-      float bt;
+    const float al = live ? alpha[(long long)t * LX + s] : -INFINITY;      // issued early, consumed after the recursion
+    float bt = -INFINITY, e = 0.f;
+    if (live) {
+      e = lp[(long long)t * p.V + my];
       if (t == Tn - 1) {
         bt = (s >= Lx - 2) ? e : -INFINITY;
       } else {
-        float a = lse2(prev[s], prev[s + 1]);
-        if (s + 2 < Lx && ext[s + 2] != p.blank && ext[s + 2] != ext[s]) a = lse2(a, prev[s + 2]);
-        bt = (a == -INFINITY) ? -INFINITY : a + e;
+        float v = lse2(prev[s], prev[s + 1]);
+        if (skip_f) v = lse2(v, prev[s + 2]);
+        bt = (v == -INFINITY) ? -INFINITY : v + e;
       }
+    }
+    if (((Tn - 1 - t) % kRenorm) == kRenorm - 1) {
+      const float mx = block_max(bt, red, nwarps);
+      if (mx != -INFINITY) { bt = (bt == -INFINITY) ? bt : bt - mx; Doff += (double)mx; }
+    }
+    if (live) {
       cur[s] = bt;
-      const float ab = alpha[(long long)t * LX + s] + bt;
-      if (ab != -INFINITY) atomicAdd(&post[ext[s]], expf(ab - e - ll));
+      if (al != -INFINITY && bt != -INFINITY) {
+        const float k = (float)(Cs[t] + Doff - ll);
+        atomicAdd(&post[(t & 1) * p.V + my], expf(al + bt - e + k));
+      }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < p.V; c += blockDim.x) dl[(long long)t * p.V + c] = (expf(lp[(long long)t * p.V + c]) - post[c]) * gs;
+    if (tid < p.V) {
+      float* pp = &post[(t & 1) * p.V + tid];
+      dl[(long long)t * p.V + tid] = (expf(lp[(long long)t * p.V + tid]) - *pp) * gs;
+      *pp = 0.f;
+    }
     float* tmp = prev; prev = cur; cur = tmp;
-    __syncthreads();
   }
 }
 
@@ -174,13 +215,19 @@ int k_ctc_fwd_bwd(const float* logp, const long long* targets, const long long* 
                   cudaStream_t stream) {
   if (B == 0) return 0;
   NDT1_REQUIRE(blank >= 0 && blank < V, "ctc: blank id %d outside the vocabulary (%d)", blank, V);
-  CtcParams p{logp, targets, in_len, tgt_len, B, L, V, S, blank, zero_infinity, alpha_ws, nll, dlogits, dloss};
   const int LX = 2 * S + 1;
   int threads = ((LX + 31) / 32) * 32;
   if (threads < 64) threads = 64;
-  if (threads > 512) threads = 512;
-  const size_t smem = (size_t)(LX + 2 * (LX + 2) + V) * sizeof(float);
-  NDT1_REQUIRE(smem <= 48 * 1024, "ctc: target length %d too long for one CTA", S);
+  NDT1_REQUIRE(threads <= 1024, "ctc: target length %d too long for one CTA (max 511 labels)", S);
+  NDT1_REQUIRE(V <= threads, "ctc: vocabulary %d larger than the CTA (%d threads)", V, threads);
+  const size_t base = (size_t)L * sizeof(double) + (size_t)(2 * (LX + 4) + 2 * V + 32) * sizeof(float);
+  const size_t with_lp = base + (size_t)L * V * sizeof(float);
+  const int lp_in_smem = with_lp <= 200 * 1024;
+  const size_t smem = lp_in_smem ? with_lp : base;
+  NDT1_REQUIRE(smem <= 200 * 1024, "ctc: %d frames x %d labels do not fit one CTA", L, S);
+  CtcParams p{logp, targets, in_len, tgt_len, B, L, V, S, blank, zero_infinity, lp_in_smem, alpha_ws, nll, dlogits, dloss};
+  static size_t attr = 0;
+  if (smem > attr) { NDT1_CUDA_CHECK(cudaFuncSetAttribute(ctc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
   ctc_kernel<<<B, threads, smem, stream>>>(p);
   NDT1_CHECK_LAUNCH();
   if (loss) {

@@ -209,7 +209,8 @@ int k_masker_apply(float* spikes, int B, int T, int N, int mode, int timespan, c
 // Device Bernoulli / uniform draws for the masker's fast path (own Philox stream).
 namespace {
 __global__ void bernoulli_u8_kernel(unsigned char* out, long long n, float prob, unsigned long long seed, unsigned long long stream) {
-  const uint32_t thr = drop_threshold(prob);  // P(u < thr) = prob
+  const double tt = (double)prob * 4294967296.0;
+  const uint32_t thr = tt <= 0.0 ? 0u : (tt >= 4294967295.0 ? 4294967295u : (uint32_t)tt);  // P(u < thr) = prob
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n; i += (long long)gridDim.x * blockDim.x) {
     Philox4 r = philox4x32_10(seed, i, stream);
     const uint32_t u[4] = {r.x, r.y, r.z, r.w};
@@ -377,8 +378,9 @@ __global__ void grad_prep_kernel(const float* __restrict__ g, T* __restrict__ ou
     const int c = (int)(i % (cols / 4)) * 4;
     float4 v = *(const float4*)(g + r * cols + c);
     if (drop_p > 0.f) {
-      const Philox4 q = philox4x32_10(seed, (unsigned long long)(r * cols + c) >> 2, stream_id);
-      v.x *= q.x >= thr ? ik : 0.f; v.y *= q.y >= thr ? ik : 0.f; v.z *= q.z >= thr ? ik : 0.f; v.w *= q.w >= thr ? ik : 0.f;
+      float ds[4];
+      drop_scale_4(seed, stream_id, (unsigned long long)(r * cols + c), thr, ik, ds);
+      v.x *= ds[0]; v.y *= ds[1]; v.z *= ds[2]; v.w *= ds[3];
     }
     if (out) {
       out[r * cols + c + 0] = from_f32<T>(v.x); out[r * cols + c + 1] = from_f32<T>(v.y);

@@ -76,14 +76,10 @@ __device__ __forceinline__ void epilogue_vec8(const GemmEpilogue& e, int n_total
   }
   if (e.drop_p > 0.f) {
     const unsigned long long elem = ((unsigned long long)b * rows_c + r) * (unsigned long long)n_total + n;
-    const uint32_t thr = drop_threshold(e.drop_p);
-    const float ik = 1.0f / (1.0f - e.drop_p);
-    const Philox4 r0 = philox4x32_10(e.drop_seed, elem >> 2, e.drop_stream);
-    const Philox4 r1 = philox4x32_10(e.drop_seed, (elem >> 2) + 1, e.drop_stream);
-    v[0] *= r0.x >= thr ? ik : 0.f; v[1] *= r0.y >= thr ? ik : 0.f;
-    v[2] *= r0.z >= thr ? ik : 0.f; v[3] *= r0.w >= thr ? ik : 0.f;
-    v[4] *= r1.x >= thr ? ik : 0.f; v[5] *= r1.y >= thr ? ik : 0.f;
-    v[6] *= r1.z >= thr ? ik : 0.f; v[7] *= r1.w >= thr ? ik : 0.f;
+    float ds[8];
+    drop_scale_8(e.drop_seed, e.drop_stream, elem, drop_threshold(e.drop_p), 1.0f / (1.0f - e.drop_p), ds);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= ds[i];
   }
   if (e.dact != DACT_NONE) {
     float s[8];

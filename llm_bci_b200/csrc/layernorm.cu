@@ -124,8 +124,9 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float
         *(float4*)dr = o;
         if (out_lp) {
           if (drop_p > 0.f) {
-            const Philox4 q = philox4x32_10(seed, (unsigned long long)(r * H + c * 4) >> 2, stream_id);
-            o.x *= q.x >= thr ? ik : 0.f; o.y *= q.y >= thr ? ik : 0.f; o.z *= q.z >= thr ? ik : 0.f; o.w *= q.w >= thr ? ik : 0.f;
+            float ds[4];
+            drop_scale_4(seed, stream_id, (unsigned long long)(r * H + c * 4), thr, ik, ds);
+            o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
           }
           store4<T>(out_lp + r * H + c * 4, o.x, o.y, o.z, o.w);
         }
