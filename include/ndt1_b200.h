@@ -103,9 +103,12 @@ int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y,
 
 /* F.scaled_dot_product_attention with the reference's mask (models/ndt1.py:276-290, 30-41, 435-437),
  * bf16 in/out: qkv (B*L, 3H) packed q|k|v, out/out_drop (B*L, H) before/after the output dropout,
- * lse (B, heads, L).  With dout (gradient w.r.t. out) the backward runs too: dqkv (B*L, 3H),
- * delta_ws (B, heads, L) scratch.  use_tensor_cores selects the tcgen05 kernels (head size 128,
+ * lse (B, heads, L).  With dout (gradient w.r.t. out) the backward runs too: dqkv (B*L, 3H).
+ * delta_ws: scratch of ndt1_attention_workspace_bytes(B, L, heads) bytes, 16-byte aligned (row sums for
+ * the backward + the keep bits of the probability dropout; required for the backward and for the
+ * tensor-core forward with p_attn > 0).  use_tensor_cores selects the tcgen05 kernels (head size 128,
  * L <= 256) or the CUDA-core kernels. */
+size_t ndt1_attention_workspace_bytes(int B, int L, int n_heads);
 int ndt1_attention_bf16(const void* qkv, void* out, void* out_drop, float* lse, const int64_t* key_valid, int B, int L, int H, int n_heads,
                         int context_forward, int context_backward, float p_attn, float p_out, uint64_t seed, uint64_t site_attn,
                         uint64_t site_out, const void* dout, void* dqkv, float* delta_ws, int use_tensor_cores, void* stream);

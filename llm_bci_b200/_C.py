@@ -77,6 +77,7 @@ PROTOTYPES = {
     "ndt1_recon_loss": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "ndt1_layernorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p]),
     "ndt1_linear_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "ndt1_attention_workspace_bytes": (_sz, [_i, _i, _i]),
     "ndt1_attention_bf16": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _u64, _u64, _u64, _p, _p, _p, _i, _p]),
     "ndt1_adamw_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _p]),
     "ndt1_engine_create": (_i, [C.POINTER(Config), C.POINTER(_p)]),

@@ -78,6 +78,11 @@ int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y,
   return gemm_tc_launch(p, s);
 }
 
+size_t ndt1_attention_workspace_bytes(int B, int L, int n_heads) {
+  const size_t nrow = ((size_t)B * n_heads * L + 3) / 4 * 4;
+  return nrow * 4 + (size_t)B * n_heads * L * 8 * 4;
+}
+
 int ndt1_attention_bf16(const void* qkv, void* out, void* out_drop, float* lse, const int64_t* key_valid, int B, int L, int H, int n_heads,
                         int context_forward, int context_backward, float p_attn, float p_out, uint64_t seed, uint64_t site_attn,
                         uint64_t site_out, const void* dout, void* dqkv, float* delta_ws, int use_tensor_cores, void* stream) {
@@ -89,9 +94,13 @@ int ndt1_attention_bf16(const void* qkv, void* out, void* out_drop, float* lse, 
   else { ap.ctx_fwd = context_forward >= -1 ? context_forward : unb; ap.ctx_bwd = context_backward >= -1 ? context_backward : unb; }
   ap.scale = 1.0f / sqrtf((float)ap.hd); ap.p_attn = p_attn; ap.p_out = p_out; ap.seed = seed; ap.stream_attn = site_attn; ap.stream_out = site_out;
   ap.dout = dout; ap.dqkv = dqkv; ap.delta = delta_ws;
+  // workspace layout: delta (B, heads, L) floats, then the keep bits (B, heads, L, 8) u32 on a 16-byte boundary
+  const long long nrow = ((long long)B * n_heads * L + 3) / 4 * 4;
+  ap.drop_bits = delta_ws ? (unsigned int*)(delta_ws + nrow) : nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   const bool tcp = use_tensor_cores && k_attention_tc_supported(ap);
   NDT1_REQUIRE(!use_tensor_cores || tcp, "attention_bf16: tensor-core path needs head size 128 and at most 256 tokens");
+  NDT1_REQUIRE(!(tcp && p_attn > 0.f) || delta_ws, "attention_bf16: the tensor-core path with dropout needs the workspace");
   if (tcp) NDT1_TRY(k_attention_tc_fwd(ap, s)); else NDT1_TRY(k_attention_fwd<bf16>(ap, s));
   if (dout) {
     NDT1_REQUIRE(dqkv && delta_ws, "attention_bf16: backward needs dqkv and delta_ws");

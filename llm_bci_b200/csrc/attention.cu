@@ -130,7 +130,17 @@ __global__ void attn_delta_kernel(const AttnParams p) {
   const T* o = (const T*)p.out + bi * p.H + h * p.hd;
   const T* g = (const T*)p.dout + bi * p.H + h * p.hd;
   float s = 0.f;
-  for (int d = lane; d < p.hd; d += 32) s += to_f32(o[d]) * to_f32(g[d]);
+  if (sizeof(T) == 2 && (p.hd & 3) == 0 && (p.H & 3) == 0) {      // 8-byte loads of 4 bf16
+    for (int d = lane * 4; d < p.hd; d += 128) {
+      const uint2 a = *(const uint2*)((const bf16*)o + d), c = *(const uint2*)((const bf16*)g + d);
+      const __nv_bfloat162 a0 = *(const __nv_bfloat162*)&a.x, a1 = *(const __nv_bfloat162*)&a.y;
+      const __nv_bfloat162 c0 = *(const __nv_bfloat162*)&c.x, c1 = *(const __nv_bfloat162*)&c.y;
+      s += __low2float(a0) * __low2float(c0) + __high2float(a0) * __high2float(c0) + __low2float(a1) * __low2float(c1) +
+           __high2float(a1) * __high2float(c1);
+    }
+  } else {
+    for (int d = lane; d < p.hd; d += 32) s += to_f32(o[d]) * to_f32(g[d]);
+  }
   s = warp_sum(s);
   const int b = (int)(bi / p.L), i = (int)(bi % p.L);
   if (lane == 0) p.delta[((long long)b * p.nh + h) * p.L + i] = s;

@@ -26,7 +26,7 @@ int tc_make_map(const GemmOperand& o, int box_cols, int box_rows, CUtensorMap* o
 
 namespace {
 
-constexpr int HD = 128, LMAX = 256, TQ = 128, NTHREADS = 128;
+constexpr int HD = 128, LMAX = 256, TQ = 128, NTHREADS = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct TcAttn {
@@ -34,32 +34,75 @@ struct TcAttn {
   int cf, cb;
 };
 
-__device__ __forceinline__ bool allowed(int cf, int cb, const unsigned char* kv, int i, int j) {
-  return (i == j) || ((j <= i + cf) && (j >= i - cb) && kv[j] != 0);
+// ---------------------------------------------------------------------------
+// Small device helpers.  The elementwise part of every kernel is what bounds it (the
+// contractions are ~2K tensor-core cycles per CTA), so the mask is evaluated as 32-bit
+// words (one bit per key) and the dropout mask of the probabilities is drawn ONCE in the
+// forward (Philox, 16 bits per element) and kept as a bit matrix (B, heads, L, 8 x u32)
+// that both backward kernels read.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-
-// store 8 consecutive bf16 of row `row`, columns [col, col+8) of a [128][.] operand kept as 64-column SW128 sub-tiles of 16 KB
-__device__ __forceinline__ void st_row8(uint8_t* tile, int row, int col, const float* v) {
-  __align__(16) bf16 o[8];
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// bits j of [lo, hi] intersected with [0, 31]
+__device__ __forceinline__ uint32_t range_bits(int lo, int hi) {
+  lo = max(lo, 0); hi = min(hi, 31);
+  return (lo > hi) ? 0u : ((0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo));
+}
+// allowed keys [c0, c0+32) of query i:  (i == j) || (j <= i + cf && j >= i - cb && key_valid[j])
+__device__ __forceinline__ uint32_t query_mask_word(int i, int c0, int cf, int cb, uint32_t kv_word, int L) {
+  if (i >= L) return 0u;
+  uint32_t w = kv_word & range_bits(i - cb - c0, i + cf - c0);
+  const int d = i - c0;
+  if (d >= 0 && d < 32) w |= 1u << d;
+  return w;
+}
+// allowed queries [c0, c0+32) of key j (the same predicate, transposed)
+__device__ __forceinline__ uint32_t key_mask_word(int j, int c0, int cf, int cb, bool kv_j, int L) {
+  if (j >= L) return 0u;
+  uint32_t w = kv_j ? range_bits(j - cf - c0, min(j + cb, L - 1) - c0) : 0u;
+  const int d = j - c0;
+  if (d >= 0 && d < 32) w |= 1u << d;
+  return w;
+}
+__device__ __forceinline__ uint32_t keep_bits8(const Philox4& r, uint32_t thr) {
+  uint32_t m = 0;
+  m |= ((r.x & 0xFFFFu) >= thr) ? 1u : 0u;  m |= ((r.x >> 16) >= thr) ? 2u : 0u;
+  m |= ((r.y & 0xFFFFu) >= thr) ? 4u : 0u;  m |= ((r.y >> 16) >= thr) ? 8u : 0u;
+  m |= ((r.z & 0xFFFFu) >= thr) ? 16u : 0u; m |= ((r.z >> 16) >= thr) ? 32u : 0u;
+  m |= ((r.w & 0xFFFFu) >= thr) ? 64u : 0u; m |= ((r.w >> 16) >= thr) ? 128u : 0u;
+  return m;
+}
+// keep bits of the 32 consecutive elements [e0, e0+32) of a dropout site (any alignment); same draws as drop_scale_1
+__device__ __forceinline__ uint32_t keep_word32(unsigned long long seed, unsigned long long stream, unsigned long long e0, uint32_t thr,
+                                                bool aligned) {
+  const unsigned long long c = e0 >> 3;
+  const int sh = (int)(e0 & 7);
+  unsigned long long bits = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(v[i]);
-  *(uint4*)(tile + (col >> 6) * 16384 + sw128_offset(row, col & 63)) = *(const uint4*)o;
+  for (int i = 0; i < 4; ++i) bits |= (unsigned long long)keep_bits8(philox4x32_10(seed, c + i, stream), thr) << (8 * i);
+  if (!aligned) bits |= (unsigned long long)keep_bits8(philox4x32_10(seed, c + 4, stream), thr) << 32;
+  return (uint32_t)(bits >> sh);
 }
-
-struct PhiloxRow {   // cached Philox block for consecutive element indices
-  unsigned long long seed, stream, ctr; Philox4 r; uint32_t thr; float ik;
-  __device__ __forceinline__ void init(unsigned long long s, unsigned long long st, float p) {
-    seed = s; stream = st; ctr = ~0ull; thr = drop_threshold(p); ik = 1.0f / (1.0f - p);
-  }
-  __device__ __forceinline__ float scale(unsigned long long elem) {
-    const unsigned long long c = elem >> 3;
-    if (c != ctr) { ctr = c; r = philox4x32_10(seed, c, stream); }
-    return philox_u16(r, (int)(elem & 7)) >= thr ? ik : 0.f;
-  }
-};
+// 16-byte store of 8 bf16 at (row, col % 8 == 0) of a [128][.] operand kept as 64-column SW128 sub-tiles of 16 KB
+__device__ __forceinline__ void st_row8(uint8_t* tile, int row, int col, const float* v) {
+  const uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  *(uint4*)(tile + (col >> 6) * 16384 + row * 128 + (((((col & 63) >> 3) ^ row) & 7) << 4)) = o;
+}
+__device__ __forceinline__ void st_global8(bf16* dst, const float* v) {
+  *(uint4*)dst = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
 
 // ---------------------------------------------------------------------------
-// forward
+// forward.  256 threads: warp w owns TMEM lanes 32*(w%4).. (one query row per lane) and the
+// key columns [128*(w/4), +128) of that row; the two halves of a row meet through smem.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map256, const TcAttn a) {
@@ -69,15 +112,22 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   uint8_t* sK = sQ + 32768;           // 2 x [256 x 64]   64 KB   (later: P as 4 x [128 x 64])
   uint8_t* sV = sK + 65536;           // 2 x [256 x 64]   64 KB
   uint8_t* sP = sK;
-  unsigned char* s_kv = sV + 65536;   // [256]
-  uint64_t* bars = (uint64_t*)(s_kv + 256);   // qk, v, s, o
+  float* s_m = (float*)(sV + 65536);  // [2][128] row maxima of the two column halves
+  float* s_l = s_m + 256;             // [2][128] row sums
+  uint32_t* s_kvw = (uint32_t*)(s_l + 256);   // [8] key_valid bits
+  uint64_t* bars = (uint64_t*)(s_kvw + 8);    // qk, v, s, o
   uint32_t* tmem_slot = (uint32_t*)(bars + 4);
 
   const AttnParams& p = a.p;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
   const int L = p.L, H = p.H;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  for (int j = tid; j < LMAX; j += NTHREADS) s_kv[j] = (j < L && p.key_valid[(long long)b * L + j] != 0) ? 1 : 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  {
+    const int j = warp * 32 + lane;
+    const uint32_t w = __ballot_sync(0xffffffffu, j < L && p.key_valid[(long long)b * L + j] != 0);
+    if (lane == 0) s_kvw[warp] = w;
+  }
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -110,50 +160,65 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   mbar_wait(&bars[2], 0);
   tc_fence_after();
 
-  const int qi = q0 + tid;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const int row = quarter * 32 + lane;
+  const int qi = q0 + row;
+  const int cbase = half * 128;
+  const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
   const float sl2 = p.scale * kLog2e;
-  float m = -INFINITY;
-  for (int c0 = 0; c0 < LMAX; c0 += 32) {
-    if (c0 >= L) break;
-    uint32_t raw[32];
-    tmem_ld32(trow + c0, raw);
-    tmem_ld_wait();
+  uint32_t mw[4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int kj = c0 + j;
-      if (qi < L && kj < L && allowed(a.cf, a.cb, s_kv, qi, kj)) m = fmaxf(m, __uint_as_float(raw[j]));
-    }
-  }
-  const float m_s = (m == -INFINITY) ? 0.f : m * sl2;
-  float l = 0.f;
-  PhiloxRow ph;
-  ph.init(p.seed, p.stream_attn, p.p_attn);
-  const unsigned long long ebase = (((unsigned long long)b * p.nh + h) * L + qi) * (unsigned long long)L;
-  for (int c0 = 0; c0 < LMAX; c0 += 32) {
-    float pv[32];
-    if (c0 < L) {
+  for (int c = 0; c < 4; ++c) mw[c] = query_mask_word(qi, cbase + 32 * c, a.cf, a.cb, s_kvw[half * 4 + c], L);
+  float m = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int c0 = cbase + 32 * c;
+    if (c0 < L) {                                     // warp-uniform
       uint32_t raw[32];
       tmem_ld32(trow + c0, raw);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int kj = c0 + j;
-        float v = 0.f;
-        if (qi < L && kj < L && allowed(a.cf, a.cb, s_kv, qi, kj)) {
-          v = exp2f(__uint_as_float(raw[j]) * sl2 - m_s);
-          l += v;
-          if (p.p_attn > 0.f) v *= ph.scale(ebase + kj);
-        }
-        pv[j] = v;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) pv[j] = 0.f;
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, (mw[c] >> j) & 1u ? __uint_as_float(raw[j]) : -INFINITY);
     }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) st_row8(sP, tid, c0 + g * 8, pv + g * 8);
   }
+  s_m[half * 128 + row] = m;
+  __syncthreads();
+  m = fmaxf(s_m[row], s_m[128 + row]);
+  const float m_s = (m == -INFINITY) ? 0.f : m * sl2;
+  float l = 0.f;
+  const bool drop = p.p_attn > 0.f;
+  const uint32_t thr = drop_threshold(p.p_attn);
+  const float ik = drop ? 1.0f / (1.0f - p.p_attn) : 1.f;
+  const long long bh_row = ((long long)b * p.nh + h) * L + qi;
+  const unsigned long long ebase = (unsigned long long)bh_row * (unsigned long long)L;
+  const bool aligned = (L & 7) == 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int c0 = cbase + 32 * c;
+    if (c0 < L) {
+      uint32_t kw = 0xFFFFFFFFu;
+      if (drop) {
+        kw = keep_word32(p.seed, p.stream_attn, ebase + c0, thr, aligned);
+        if (p.drop_bits && qi < L) p.drop_bits[bh_row * 8 + (c0 >> 5)] = kw;
+      }
+      uint32_t raw[32];
+      tmem_ld32(trow + c0, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float pv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = g * 8 + i;
+          const float s = fmaf(__uint_as_float(raw[j]), sl2, -m_s);
+          const float e = ex2f((mw[c] >> j) & 1u ? s : -INFINITY);
+          l += e;
+          pv[i] = (kw >> j) & 1u ? e * ik : 0.f;
+        }
+        st_row8(sP, row, c0 + g * 8, pv);
+      }
+    }
+  }
+  s_l[half * 128 + row] = l;
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -169,42 +234,39 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
     tc_commit(&bars[3]);
   }
   __syncwarp();
+  l = s_l[row] + s_l[128 + row];
   mbar_wait(&bars[3], 0);
   tc_fence_after();
   const float inv = (l > 0.f) ? 1.f / l : 0.f;
   const uint32_t thr_o = drop_threshold(p.p_out);
   const float iko = p.p_out > 0.f ? 1.0f / (1.0f - p.p_out) : 1.f;
-  for (int c0 = 0; c0 < HD; c0 += 32) {
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c0 = half * 64 + cc * 32;
     uint32_t raw[32];
     tmem_ld32(trow + 256 + c0, raw);
     tmem_ld_wait();
     if (qi < L) {
       const long long o = ((long long)b * L + qi) * H + h * HD + c0;
-      __align__(16) bf16 ob[32], od[32];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float v[4];
+      for (int g = 0; g < 4; ++g) {
+        float v[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { v[i] = __uint_as_float(raw[j + i]) * inv; ob[j + i] = __float2bfloat16_rn(v[i]); }
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g * 8 + i]) * inv;
+        st_global8((bf16*)p.out + o + g * 8, v);
         if (p.p_out > 0.f) {
-          float ds[4];
-          drop_scale_4(p.seed, p.stream_out, (unsigned long long)(o + j), thr_o, iko, ds);
+          float ds[8];
+          drop_scale_8(p.seed, p.stream_out, (unsigned long long)(o + g * 8), thr_o, iko, ds);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) od[j + i] = __float2bfloat16_rn(v[i] * ds[i]);
+          for (int i = 0; i < 8; ++i) v[i] *= ds[i];
+          st_global8((bf16*)p.out_drop + o + g * 8, v);
+        } else if (p.out_drop != p.out) {
+          st_global8((bf16*)p.out_drop + o + g * 8, v);
         }
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) *(uint4*)((bf16*)p.out + o + g * 8) = *(const uint4*)(ob + g * 8);
-      if (p.p_out > 0.f) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) *(uint4*)((bf16*)p.out_drop + o + g * 8) = *(const uint4*)(od + g * 8);
-      } else if (p.out_drop != p.out) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) *(uint4*)((bf16*)p.out_drop + o + g * 8) = *(const uint4*)(ob + g * 8);
       }
     }
   }
-  if (qi < L) p.lse[((long long)b * p.nh + h) * L + qi] = m * p.scale + logf(l);
+  if (half == 0 && qi < L) p.lse[bh_row] = m * p.scale + logf(l);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
@@ -223,15 +285,20 @@ attn_tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
   uint8_t* sK = sdO + 32768;          // 64 KB
   uint8_t* sV = sK + 65536;           // 64 KB
   uint8_t* sdS = sQ;
-  unsigned char* s_kv = sV + 65536;
-  uint64_t* bars = (uint64_t*)(s_kv + 256);   // loads, s, o
+  uint32_t* s_kvw = (uint32_t*)(sV + 65536);  // [8]
+  uint64_t* bars = (uint64_t*)(s_kvw + 8);    // loads, s, o
   uint32_t* tmem_slot = (uint32_t*)(bars + 4);
 
   const AttnParams& p = a.p;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
   const int L = p.L, H = p.H;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  for (int j = tid; j < LMAX; j += NTHREADS) s_kv[j] = (j < L && p.key_valid[(long long)b * L + j] != 0) ? 1 : 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  {
+    const int j = warp * 32 + lane;
+    const uint32_t w = __ballot_sync(0xffffffffu, j < L && p.key_valid[(long long)b * L + j] != 0);
+    if (lane == 0) s_kvw[warp] = w;
+  }
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -265,41 +332,48 @@ attn_tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
     tc_commit(&bars[1]);
   }
   __syncwarp();
+
+  const int row = quarter * 32 + lane;
+  const int qi = q0 + row;
+  const int cbase = half * 128;
+  const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+  const float sl2 = p.scale * kLog2e;
+  const long long bh_row = ((long long)b * p.nh + h) * L + qi;
+  const float lse2 = qi < L ? p.lse[bh_row] * kLog2e : 0.f;
+  const float del = qi < L ? p.delta[bh_row] : 0.f;
+  const bool drop = p.p_attn > 0.f;
+  const float ik = drop ? 1.0f / (1.0f - p.p_attn) : 1.f;
+  uint32_t mw[4], kw[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int c0 = cbase + 32 * c;
+    mw[c] = query_mask_word(qi, c0, a.cf, a.cb, s_kvw[half * 4 + c], L);
+    kw[c] = (drop && qi < L && c0 < L) ? p.drop_bits[bh_row * 8 + (c0 >> 5)] : 0xFFFFFFFFu;
+  }
   mbar_wait(&bars[1], 0);
   tc_fence_after();
-
-  const int qi = q0 + tid;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-  const float sl2 = p.scale * kLog2e;
-  const float lse2 = qi < L ? p.lse[((long long)b * p.nh + h) * L + qi] * kLog2e : 0.f;
-  const float del = qi < L ? p.delta[((long long)b * p.nh + h) * L + qi] : 0.f;
-  PhiloxRow ph;
-  ph.init(p.seed, p.stream_attn, p.p_attn);
-  const unsigned long long ebase = (((unsigned long long)b * p.nh + h) * L + qi) * (unsigned long long)L;
-  for (int c0 = 0; c0 < LMAX; c0 += 32) {
-    float ds[32];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int c0 = cbase + 32 * c;
     if (c0 < L) {
       uint32_t rs[32], rp[32];
       tmem_ld32(trow + c0, rs);
       tmem_ld32(trow + 256 + c0, rp);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int kj = c0 + j;
-        float v = 0.f;
-        if (qi < L && kj < L && allowed(a.cf, a.cb, s_kv, qi, kj)) {
-          const float pr = exp2f(__uint_as_float(rs[j]) * sl2 - lse2);
-          const float dm = p.p_attn > 0.f ? ph.scale(ebase + kj) : 1.f;
-          v = pr * (__uint_as_float(rp[j]) * dm - del) * p.scale;
+      for (int g = 0; g < 4; ++g) {
+        float ds[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = g * 8 + i;
+          const float s = fmaf(__uint_as_float(rs[j]), sl2, -lse2);
+          const float pr = ex2f((mw[c] >> j) & 1u ? s : -INFINITY) * p.scale;
+          const float t = (kw[c] >> j) & 1u ? __uint_as_float(rp[j]) * ik : 0.f;
+          ds[i] = pr * (t - del);
         }
-        ds[j] = v;
+        st_row8(sdS, row, c0 + g * 8, ds);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) ds[j] = 0.f;
     }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) st_row8(sdS, tid, c0 + g * 8, ds + g * 8);
   }
   fence_async_smem();
   tc_fence_before();
@@ -315,17 +389,16 @@ attn_tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
   __syncwarp();
   mbar_wait(&bars[2], 0);
   tc_fence_after();
-  for (int c0 = 0; c0 < HD; c0 += 32) {
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c0 = half * 64 + cc * 32;
     uint32_t raw[32];
     tmem_ld32(trow + c0, raw);
     tmem_ld_wait();
     if (qi < L) {
-      __align__(16) bf16 ob[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) ob[j] = __float2bfloat16_rn(__uint_as_float(raw[j]));
       bf16* o = (bf16*)p.dqkv + ((long long)b * L + qi) * 3 * H + h * HD + c0;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) *(uint4*)(o + g * 8) = *(const uint4*)(ob + g * 8);
+      for (int g = 0; g < 4; ++g) st_global8(o + g * 8, (const float*)raw + g * 8);
     }
   }
   tc_fence_before();
@@ -334,7 +407,8 @@ attn_tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
 }
 
 // ---------------------------------------------------------------------------
-// backward, key side: dK, dV (accumulated over the query tiles in TMEM)
+// backward, key side: dK, dV (accumulated over the query tiles in TMEM).
+// Lanes are keys here; warp w owns keys 32*(w%4).. of the tile and the query columns [64*(w/4), +64).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap mapdo, const TcAttn a) {
@@ -346,17 +420,16 @@ attn_tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_c
   uint8_t* sdO = sQ + 32768;
   uint8_t* sPt = sdO + 32768;         // 2 x [128 keys x 64 q]
   uint8_t* sdSt = sPt + 32768;
-  float* s_lse = (float*)(sdSt + 32768);   // [128]
-  float* s_del = s_lse + 128;              // [128]
-  unsigned char* s_kv = (unsigned char*)(s_del + 128);
-  uint64_t* bars = (uint64_t*)(s_kv + 256);   // kv, q, s, acc
+  float2* s_ld = (float2*)(sdSt + 32768);          // [128] (lse * log2e, delta) of the query tile
+  uint32_t* s_bits = (uint32_t*)(s_ld + 128);      // [128][4] keep bits (query row, 32-key word of this key tile)
+  uint64_t* bars = (uint64_t*)(s_bits + 512);      // kv, q, s, acc
   uint32_t* tmem_slot = (uint32_t*)(bars + 4);
 
   const AttnParams& p = a.p;
   const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * TQ;
   const int L = p.L, H = p.H;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  for (int j = tid; j < LMAX; j += NTHREADS) s_kv[j] = (j < L && p.key_valid[(long long)b * L + j] != 0) ? 1 : 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, half = warp >> 2;
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -367,13 +440,14 @@ attn_tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_c
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int nq = (L + TQ - 1) / TQ;
-  const int kj = k0 + tid;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const int row = quarter * 32 + lane;
+  const int kj = k0 + row;
+  const bool kv_j = kj < L && p.key_valid[(long long)b * L + kj] != 0;
+  const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
   const float sl2 = p.scale * kLog2e;
-  const uint32_t thr = drop_threshold(p.p_attn);
-  const float ik = p.p_attn > 0.f ? 1.0f / (1.0f - p.p_attn) : 1.f;
-  const float* lse_g = p.lse + ((long long)b * p.nh + h) * L;
-  const float* del_g = p.delta + ((long long)b * p.nh + h) * L;
+  const bool drop = p.p_attn > 0.f;
+  const float ik = drop ? 1.0f / (1.0f - p.p_attn) : 1.f;
+  const long long bh0 = ((long long)b * p.nh + h) * L;
 
   for (int it = 0; it < nq; ++it) {
     const int q0 = it * TQ;
@@ -382,8 +456,11 @@ attn_tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_c
     __syncthreads();
     if (tid < TQ) {
       const int qq = q0 + tid;
-      s_lse[tid] = qq < L ? lse_g[qq] * kLog2e : 0.f;
-      s_del[tid] = qq < L ? del_g[qq] : 0.f;
+      s_ld[tid] = qq < L ? make_float2(p.lse[bh0 + qq] * kLog2e, p.delta[bh0 + qq]) : make_float2(0.f, 0.f);
+      if (drop) {
+        const uint4 w = qq < L ? *(const uint4*)(p.drop_bits + (bh0 + qq) * 8 + (k0 >> 5)) : make_uint4(0u, 0u, 0u, 0u);
+        *(uint4*)(s_bits + tid * 4) = w;
+      }
     }
     if (tid == 0) {
       if (it == 0) {
@@ -410,38 +487,36 @@ attn_tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_c
       }
       tc_commit(&bars[2]);
     }
-    __syncthreads();                 // s_lse / s_del visible
+    __syncthreads();                 // s_ld / s_bits visible
     mbar_wait(&bars[2], it & 1);
     tc_fence_after();
-    for (int c0 = 0; c0 < TQ; c0 += 32) {
-      float pt[32], dst[32];
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c0 = half * 64 + cc * 32;          // query column of the tile
       if (q0 + c0 < L) {
+        const uint32_t mw = key_mask_word(kj, q0 + c0, a.cf, a.cb, kv_j, L);
         uint32_t rs[32], rp[32];
         tmem_ld32(trow + c0, rs);
         tmem_ld32(trow + 128 + c0, rp);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int qi = q0 + c0 + j;
-          float pd = 0.f, ds = 0.f;
-          if (qi < L && kj < L && allowed(a.cf, a.cb, s_kv, qi, kj)) {
-            const float pr = exp2f(__uint_as_float(rs[j]) * sl2 - s_lse[c0 + j]);
+        for (int g = 0; g < 4; ++g) {
+          float pt[8], dst[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int j = g * 8 + i;
+            const float2 ld = s_ld[c0 + j];
+            const float s = fmaf(__uint_as_float(rs[j]), sl2, -ld.x);
+            const float pr = ex2f((mw >> j) & 1u ? s : -INFINITY);
             float dm = 1.f;
-            if (p.p_attn > 0.f) {
-              const unsigned long long e = (((unsigned long long)b * p.nh + h) * L + qi) * (unsigned long long)L + kj;
-              dm = drop_scale_1(p.seed, p.stream_attn, e, thr, ik);
-            }
-            pd = pr * dm;
-            ds = pr * (__uint_as_float(rp[j]) * dm - s_del[c0 + j]) * p.scale;
+            if (drop) dm = (s_bits[(c0 + j) * 4 + quarter] >> lane) & 1u ? ik : 0.f;
+            pt[i] = pr * dm;
+            dst[i] = pr * p.scale * (__uint_as_float(rp[j]) * dm - ld.y);
           }
-          pt[j] = pd; dst[j] = ds;
+          st_row8(sPt, row, c0 + g * 8, pt);
+          st_row8(sdSt, row, c0 + g * 8, dst);
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { pt[j] = 0.f; dst[j] = 0.f; }
       }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) { st_row8(sPt, tid, c0 + g * 8, pt + g * 8); st_row8(sdSt, tid, c0 + g * 8, dst + g * 8); }
     }
     fence_async_smem();
     tc_fence_before();
@@ -465,18 +540,18 @@ attn_tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_c
   }
   mbar_wait(&bars[3], (nq - 1) & 1);
   tc_fence_after();
-  for (int half = 0; half < 2; ++half) {       // 0: dV (cols 256..), 1: dK (cols 384..)
-    for (int c0 = 0; c0 < HD; c0 += 32) {
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {       // 0: dV (cols 256..), 1: dK (cols 384..)
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c0 = half * 64 + cc * 32;
       uint32_t raw[32];
-      tmem_ld32(trow + 256 + half * 128 + c0, raw);
+      tmem_ld32(trow + 256 + which * 128 + c0, raw);
       tmem_ld_wait();
       if (kj < L) {
-        __align__(16) bf16 ob[32];
+        bf16* o = (bf16*)p.dqkv + ((long long)b * L + kj) * 3 * H + (which == 0 ? 2 * H : H) + h * HD + c0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) ob[j] = __float2bfloat16_rn(__uint_as_float(raw[j]));
-        bf16* o = (bf16*)p.dqkv + ((long long)b * L + kj) * 3 * H + (half == 0 ? 2 * H : H) + h * HD + c0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) *(uint4*)(o + g * 8) = *(const uint4*)(ob + g * 8);
+        for (int g = 0; g < 4; ++g) st_global8(o + g * 8, (const float*)raw + g * 8);
       }
     }
   }
@@ -496,9 +571,9 @@ int make_maps(const AttnParams& p, CUtensorMap* m128, CUtensorMap* m256, CUtenso
   return 0;
 }
 
-constexpr int SMEM_FWD = 32768 + 65536 + 65536 + 256 + 64 + 1024;
-constexpr int SMEM_BQ = 32768 * 2 + 65536 * 2 + 256 + 64 + 1024;
-constexpr int SMEM_BKV = 32768 * 6 + 1024 + 256 + 64 + 1024;
+constexpr int SMEM_FWD = 32768 + 65536 + 65536 + 2048 + 32 + 64 + 1024;
+constexpr int SMEM_BQ = 32768 * 2 + 65536 * 2 + 32 + 64 + 1024;
+constexpr int SMEM_BKV = 32768 * 6 + 1024 + 2048 + 64 + 1024;
 
 }  // namespace
 

@@ -67,6 +67,7 @@ struct Engine : ndt1_engine {
   std::vector<float*> mean, rstd;   // 2L+1
   std::vector<T*> h1, h2, qkv, att, attd, u, g;
   std::vector<float*> lse;
+  std::vector<unsigned int*> dropbits;   // keep bits of the attention-probability dropout (tensor-core path)
   T* hn = nullptr; T* fac = nullptr; T* fpre = nullptr;
   float* logits = nullptr; float* logp = nullptr; float* dlogits = nullptr; float* nll = nullptr; float* ctc_ws = nullptr;
   long long* key_valid = nullptr; long long* out_lens = nullptr;
@@ -100,11 +101,12 @@ struct Engine : ndt1_engine {
     emb = ar.take<T>(MT * D);
     xs.resize(2 * NL + 1); mean.resize(2 * NL + 1); rstd.resize(2 * NL + 1);
     for (int i = 0; i < 2 * NL + 1; ++i) { xs[i] = ar.take<float>(Mm * H); mean[i] = ar.take<float>(Mm); rstd[i] = ar.take<float>(Mm); }
-    h1.resize(NL); h2.resize(NL); qkv.resize(NL); att.resize(NL); attd.resize(NL); u.resize(NL); g.resize(NL); lse.resize(NL);
+    h1.resize(NL); h2.resize(NL); qkv.resize(NL); att.resize(NL); attd.resize(NL); u.resize(NL); g.resize(NL); lse.resize(NL); dropbits.resize(NL);
     for (int l = 0; l < NL; ++l) {
       h1[l] = ar.take<T>(Mm * H); h2[l] = ar.take<T>(Mm * H); qkv[l] = ar.take<T>(Mm * 3 * H);
       att[l] = ar.take<T>(Mm * H); attd[l] = (k.p_transformer > 0.f) ? ar.take<T>(Mm * H) : att[l];
       u[l] = ar.take<T>(Mm * I); g[l] = ar.take<T>(Mm * I); lse[l] = ar.take<float>((long long)Bm * k.n_heads * Lm);
+      dropbits[l] = (kBf16 && k.p_transformer > 0.f) ? ar.take<unsigned int>((long long)Bm * k.n_heads * Lm * 8) : nullptr;
     }
     hn = ar.take<T>(Mm * H);
     if (k.factors_active) { fac = ar.take<T>(Mm * Hout); fpre = ar.take<T>(Mm * Hout); dfac = ar.take<T>(Mm * Hout); }
@@ -321,7 +323,7 @@ struct Engine : ndt1_engine {
       ap.B = B; ap.L = L; ap.H = H; ap.nh = k.n_heads; ap.hd = H / k.n_heads; ap.ctx_fwd = cf; ap.ctx_bwd = cb;
       ap.scale = 1.0f / sqrtf((float)(H / k.n_heads)); ap.p_attn = ptr_; ap.p_out = ptr_;
       ap.seed = seed; ap.stream_attn = site_attn_p(l); ap.stream_out = site_attn_o(l);
-      ap.dout = nullptr; ap.dqkv = nullptr; ap.delta = nullptr;
+      ap.dout = nullptr; ap.dqkv = nullptr; ap.delta = nullptr; ap.drop_bits = dropbits[l];
       if (kBf16 && !force_simt && !simt_attention && k_attention_tc_supported(ap)) NDT1_TRY(k_attention_tc_fwd(ap, s));
       else NDT1_TRY(k_attention_fwd<T>(ap, s));
       {
@@ -512,7 +514,7 @@ struct Engine : ndt1_engine {
       ap.B = B; ap.L = L; ap.H = H; ap.nh = k.n_heads; ap.hd = H / k.n_heads; ap.ctx_fwd = cf; ap.ctx_bwd = cb;
       ap.scale = 1.0f / sqrtf((float)(H / k.n_heads)); ap.p_attn = ptr_; ap.p_out = ptr_;
       ap.seed = seed; ap.stream_attn = site_attn_p(l); ap.stream_out = site_attn_o(l);
-      ap.dout = dA; ap.dqkv = dqkv; ap.delta = delta;
+      ap.dout = dA; ap.dqkv = dqkv; ap.delta = delta; ap.drop_bits = dropbits[l];
       if (kBf16 && !force_simt && !simt_attention && k_attention_tc_supported(ap)) NDT1_TRY(k_attention_tc_bwd(ap, s));
       else NDT1_TRY(k_attention_bwd<T>(ap, s));
       float* gw[3] = {gq.q_w, gq.k_w, gq.v_w}; float* gb[3] = {gq.q_b, gq.k_b, gq.v_b};

@@ -59,6 +59,8 @@ struct AttnParams {
   const void* dout;         // (B*L, H) gradient w.r.t. out_drop input of out_proj (already through output dropout)
   void* dqkv;               // (B*L, 3H)
   float* delta;             // (B, nh, L) scratch
+  // tensor-core path, p_attn > 0: keep bits of the probability dropout, written by the forward, read by the backward
+  unsigned int* drop_bits;  // (B, nh, L, 8) u32: bit j%32 of word j/32 = key j kept
 };
 template <typename T> int k_attention_fwd(const AttnParams& p, cudaStream_t stream);
 template <typename T> int k_attention_bwd(const AttnParams& p, cudaStream_t stream);

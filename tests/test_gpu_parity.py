@@ -443,7 +443,7 @@ def _attention_case(B, L, nh, cf, cb, p_attn, p_out, use_tc, seed=11, valid=None
     out, outd = torch.empty(B * L, H, dtype=torch.bfloat16, device=DEV), torch.empty(B * L, H, dtype=torch.bfloat16, device=DEV)
     lse = torch.empty(B, nh, L, device=DEV)
     dqkv = torch.zeros(B * L, 3 * H, dtype=torch.bfloat16, device=DEV)
-    delta = torch.empty(B, nh, L, device=DEV)
+    delta = torch.empty(_C.lib().ndt1_attention_workspace_bytes(B, L, nh) // 4, device=DEV)
     _C.check(_C.lib().ndt1_attention_bf16(qkv.data_ptr(), out.data_ptr(), outd.data_ptr(), lse.data_ptr(), kvd.data_ptr(), B, L, H, nh, cf, cb,
                                           p_attn, p_out, seed, 1, 2, dout.data_ptr(), dqkv.data_ptr(), delta.data_ptr(), int(use_tc),
                                           _C.stream_ptr()), "ndt1_attention_bf16")
