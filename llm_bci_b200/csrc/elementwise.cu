@@ -321,6 +321,41 @@ int k_cast_f32_bf16(const float* in, bf16* out, long long rows, int cols, long l
   return 0;
 }
 
+// All the bf16 weight copies of a forward in ONE launch: up to CAST_MAX_SEGS contiguous fp32 -> bf16 segments
+// (element counts multiples of 8), flattened into 2048-element chunks; a block finds its segment by a short scan.
+namespace {
+__global__ void __launch_bounds__(256) cast_multi_kernel(const CastSegs segs) {
+  for (long long chunk = blockIdx.x; chunk < segs.total_chunks; chunk += gridDim.x) {
+    int k = 0;
+    while (k + 1 < segs.n && chunk >= segs.first_chunk[k + 1]) ++k;
+    const long long e0 = (chunk - segs.first_chunk[k]) * 2048 + (long long)threadIdx.x * 8;
+    if (e0 < segs.count[k]) {
+      const float4 a = *(const float4*)(segs.src[k] + e0), b = *(const float4*)(segs.src[k] + e0 + 4);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+      uint4 o; o.x = *(uint32_t*)&p0; o.y = *(uint32_t*)&p1; o.z = *(uint32_t*)&p2; o.w = *(uint32_t*)&p3;
+      *(uint4*)(segs.dst[k] + e0) = o;
+    }
+  }
+}
+}  // namespace
+
+int k_cast_multi(CastSegs& segs, cudaStream_t stream) {
+  if (segs.n == 0) return 0;
+  long long chunks = 0;
+  for (int i = 0; i < segs.n; ++i) {
+    NDT1_REQUIRE(segs.count[i] % 8 == 0 && ((uintptr_t)segs.src[i] & 15) == 0 && ((uintptr_t)segs.dst[i] & 15) == 0,
+                 "cast_multi: segment %d is not 8-element / 16-byte aligned", i);
+    segs.first_chunk[i] = chunks;
+    chunks += (segs.count[i] + 2047) / 2048;
+  }
+  segs.total_chunks = chunks;
+  const int blocks = (int)(chunks < 148 * 16 ? chunks : 148 * 16);
+  cast_multi_kernel<<<blocks, 256, 0, stream>>>(segs);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+
 // ===========================================================================
 // Column sums (bias gradients): out[c] += sum_r in[r, c]
 // grid (cols/32, row-chunks); 32x8 threads; each warp-row strides the rows.
@@ -347,10 +382,54 @@ __global__ void colsum_kernel(const T* __restrict__ in, float* __restrict__ out,
 }
 }  // namespace
 
+namespace {
+// 8 columns per thread (one 16-byte load of bf16, two of fp32); grid (cols/256, row-chunks); 32x8 threads
+template <typename T>
+__global__ void colsum8_kernel(const T* __restrict__ in, float* __restrict__ out, long long rows, int cols, long long ld) {
+  __shared__ float sm[8][32][9];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < cols) {
+    const long long per = (rows + gridDim.y - 1) / gridDim.y;
+    const long long r0 = (long long)blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      if (sizeof(T) == 2) {
+        const uint4 raw = *(const uint4*)((const bf16*)in + r * ld + c);
+        const __nv_bfloat162* h = (const __nv_bfloat162*)&raw;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[2 * i] += __low2float(h[i]); acc[2 * i + 1] += __high2float(h[i]); }
+      } else {
+        const float4 a = *(const float4*)((const float*)in + r * ld + c), b = *(const float4*)((const float*)in + r * ld + c + 4);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[threadIdx.y][threadIdx.x][i] = acc[i];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;        // 256 threads <-> 256 columns of the block
+  const int cc = blockIdx.x * 256 + t;
+  if (cc < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) v += sm[y][t >> 3][t & 7];
+    atomicAdd(out + cc, v);
+  }
+}
+}  // namespace
+
 template <typename T>
 int k_colsum(const T* in, float* out, long long rows, int cols, long long ld, cudaStream_t stream) {
   if (rows * cols == 0) return 0;
   dim3 block(32, 8);
+  if (cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)in & 15) == 0) {
+    int chunks8 = (int)(rows / 128); if (chunks8 < 1) chunks8 = 1;
+    const int gx = ndt1_cdiv(cols, 256);
+    while (chunks8 > 1 && (long long)chunks8 * gx > 148 * 4) --chunks8;
+    colsum8_kernel<T><<<dim3(gx, chunks8), block, 0, stream>>>(in, out, rows, cols, ld);
+    NDT1_CHECK_LAUNCH();
+    return 0;
+  }
   int chunks = (int)(rows / 256); if (chunks < 1) chunks = 1; if (chunks > 64) chunks = 64;
   dim3 grid(ndt1_cdiv(cols, 32), chunks);
   colsum_kernel<T><<<grid, block, 0, stream>>>(in, out, rows, cols, ld);

@@ -192,13 +192,11 @@ struct Engine : ndt1_engine {
   // split the reduction so that tiles*split fills whole waves of 148 SMs
   int pick_split(int tiles, int kblocks) const {
     if (!(kBf16 && !force_simt)) { int sp = 148 / (tiles > 0 ? tiles : 1); return sp > 8 ? 8 : (sp < 1 ? 1 : sp); }
-    int best = 1; double best_eff = 0.0;
-    for (int sp = 1; sp <= 64 && sp * 4 <= kblocks; ++sp) {
-      const int t = tiles * sp, waves = (t + 147) / 148;
-      const double eff = (double)t / (waves * 148.0);
-      if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
-    }
-    return best;
+    // every split adds a full fp32 red.add pass over the output (the L2 atomics are what bounds these kernels),
+    // so take the largest split that still fits ONE wave of CTAs
+    int best = 148 / (tiles > 0 ? tiles : 1);
+    while (best > 1 && best * 4 > kblocks) --best;
+    return best < 1 ? 1 : best;
   }
   const void* W(const float* master, const bf16* copy) const { return kBf16 ? (const void*)copy : (const void*)master; }
 
@@ -237,25 +235,36 @@ struct Engine : ndt1_engine {
     // 0. precision staging: bf16 copies of the weights and of the input
     if (kBf16) {
       NDT1_TRY(k_cast_f32_bf16(bt->spikes, (bf16*)xin, MT, N, N, ldN, s));
-      NDT1_TRY(k_cast_f32_bf16(P->embed_w, w_emb, D, N, N, ldN, s));
+      CastSegs cs; cs.n = 0;
+      // contiguous matrices go through ONE multi-segment launch; anything ragged through the strided kernel
+      auto add = [&](const float* src, bf16* dst, long long rows, int cols, long long ld_out) -> int {
+        const long long cnt = rows * cols;
+        if (ld_out == cols && cnt % 8 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && cs.n < CAST_MAX_SEGS) {
+          cs.src[cs.n] = src; cs.dst[cs.n] = dst; cs.count[cs.n] = cnt; ++cs.n;
+          return 0;
+        }
+        return k_cast_f32_bf16(src, dst, rows, cols, cols, ld_out, s);
+      };
+      NDT1_TRY(add(P->embed_w, w_emb, D, N, ldN));
       const int KP = k.stack_active ? k.stack_size * D : D;
-      NDT1_TRY(k_cast_f32_bf16(P->proj_w, w_proj, H, KP, KP, KP, s));
+      NDT1_TRY(add(P->proj_w, w_proj, H, KP, KP));
       for (int l = 0; l < NL; ++l) {
         const auto& q = P->layer[l];
-        NDT1_TRY(k_cast_f32_bf16(q.q_w, w_qkv[l], H, H, H, H, s));
-        NDT1_TRY(k_cast_f32_bf16(q.k_w, w_qkv[l] + (long long)H * H, H, H, H, H, s));
-        NDT1_TRY(k_cast_f32_bf16(q.v_w, w_qkv[l] + 2LL * H * H, H, H, H, H, s));
-        NDT1_TRY(k_cast_f32_bf16(q.o_w, w_o[l], H, H, H, H, s));
-        NDT1_TRY(k_cast_f32_bf16(q.up_w, w_up[l], I, H, H, H, s));
-        NDT1_TRY(k_cast_f32_bf16(q.down_w, w_down[l], H, I, I, I, s));
-        if (k.attention_bias) {
+        NDT1_TRY(add(q.q_w, w_qkv[l], H, H, H));
+        NDT1_TRY(add(q.k_w, w_qkv[l] + (long long)H * H, H, H, H));
+        NDT1_TRY(add(q.v_w, w_qkv[l] + 2LL * H * H, H, H, H));
+        NDT1_TRY(add(q.o_w, w_o[l], H, H, H));
+        NDT1_TRY(add(q.up_w, w_up[l], I, H, H));
+        NDT1_TRY(add(q.down_w, w_down[l], H, I, I));
+        if (k.attention_bias && !(q.k_b == q.q_b + H && q.v_b == q.k_b + H)) {   // scattered biases: gather them once
           NDT1_CUDA_CHECK(cudaMemcpyAsync(b_qkv[l], q.q_b, H * 4, cudaMemcpyDeviceToDevice, s));
           NDT1_CUDA_CHECK(cudaMemcpyAsync(b_qkv[l] + H, q.k_b, H * 4, cudaMemcpyDeviceToDevice, s));
           NDT1_CUDA_CHECK(cudaMemcpyAsync(b_qkv[l] + 2 * H, q.v_b, H * 4, cudaMemcpyDeviceToDevice, s));
         }
       }
-      if (k.factors_active) NDT1_TRY(k_cast_f32_bf16(P->factors_w, w_fac, Hout, H, H, H, s));
-      NDT1_TRY(k_cast_f32_bf16(P->dec_w, w_dec, V, Hout, Hout, Hout, s));
+      if (k.factors_active) NDT1_TRY(add(P->factors_w, w_fac, Hout, H, H));
+      NDT1_TRY(add(P->dec_w, w_dec, V, Hout, Hout));
+      NDT1_TRY(k_cast_multi(cs, s));
     }
     const T* x_in = kBf16 ? xin : (const T*)bt->spikes;
     const int ldx = kBf16 ? ldN : N;
@@ -308,7 +317,8 @@ struct Engine : ndt1_engine {
       NDT1_TRY(k_layernorm_fwd<T>(xa, q.ln1_w, q.ln1_b, h1[l], mean[2 * l], rstd[2 * l], M, H, 1e-5f, s));
       if (kBf16) {
         GemmEpilogue e = gemm_epilogue_default();
-        e.out = qkv[l]; e.out_bf16 = 1; e.ldc = 3 * H; e.bias = k.attention_bias ? b_qkv[l] : nullptr;
+        const bool packed_bias = (q.k_b == q.q_b + H && q.v_b == q.k_b + H);   // flat parameter arena: q|k|v biases adjacent
+        e.out = qkv[l]; e.out_bf16 = 1; e.ldc = 3 * H; e.bias = k.attention_bias ? (packed_bias ? q.q_b : b_qkv[l]) : nullptr;
         NDT1_TRY(linear_fwd(h1[l], H, w_qkv[l], H, (int)M, 3 * H, H, e, s));
       } else {
         const float* ws[3] = {q.q_w, q.k_w, q.v_w}; const float* bs[3] = {q.q_b, q.k_b, q.v_b};
@@ -388,7 +398,7 @@ struct Engine : ndt1_engine {
       NDT1_REQUIRE(bt->targets && bt->targets_lengths, "engine: ctc needs targets and targets_lengths");
       NDT1_TRY(k_log_softmax(logits, logp, Mo, V, s));
       NDT1_TRY(k_ctc_fwd_bwd(logp, (const long long*)bt->targets, out_lens, (const long long*)bt->targets_lengths, B, Tp, V, S, k.blank_id, k.zero_infinity, ctc_ws, nll,
-                             o->loss, bt->need_backward ? dlogits : nullptr, nullptr, s));
+                             o->loss, bt->need_backward ? dlogits : nullptr, nullptr, s, kBf16));
       if (o->preds) NDT1_CUDA_CHECK(cudaMemcpyAsync(o->preds, logp, Mo * V * 4, cudaMemcpyDeviceToDevice, s));
       if (o->n_examples) NDT1_TRY(k_set_i64((long long*)o->n_examples, B, s));
     } else {
@@ -473,14 +483,14 @@ struct Engine : ndt1_engine {
     }
     // out_norm
     NDT1_CUDA_CHECK(cudaMemsetAsync(dX, 0, M * H * sizeof(float), s));
+    // every LayerNorm backward also emits the column sums of the operand it hands to the next GEMM pair = that layer's bias gradient
     NDT1_TRY(k_layernorm_bwd<T>(dhn, xs[2 * NL], P->out_norm_w, mean[2 * NL], rstd[2 * NL], dX, G->out_norm_w, G->out_norm_b, dY, ptr_, seed,
-                                site_mlp(NL - 1), M, H, ln_part, s));
+                                site_mlp(NL - 1), M, H, ln_part, s, k.mlp_bias ? G->layer[NL - 1].down_b : nullptr));
     NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[0], s));   // decoder + out_norm gradients complete
     int cf, cb; ctx(cf, cb);
     for (int l = NL - 1; l >= 0; --l) {
       const auto& q = P->layer[l]; const auto& gq = G->layer[l];
       // MLP: x_out = x_mid + drop(down(act(up(h2))))      dY = T(dX * mlp mask)
-      if (gq.down_b && k.mlp_bias) NDT1_TRY(k_colsum<T>(dY, gq.down_b, M, H, H, s));
       NDT1_TRY(linear_wgrad(dY, H, g[l], I, gq.down_w, I, (int)M, H, I, s));
       {
         GemmEpilogue e = gemm_epilogue_default();
@@ -488,9 +498,11 @@ struct Engine : ndt1_engine {
         if (k.mlp_act == NDT1_ACT_GELU) { e.dact = DACT_GELU_FROM_IN; e.dact_in = u[l]; }
         else { e.dact = dact_from_out(k.mlp_act); e.dact_in = g[l]; }
         e.dact_in_bf16 = kBf16;
+        const bool fuse_cs = kBf16 && !force_simt && gq.up_b && k.mlp_bias && I % 8 == 0;
+        if (fuse_cs) e.colsum = gq.up_b;
         NDT1_TRY(linear_dgrad(dY, H, W(q.down_w, kBf16 ? w_down[l] : nullptr), I, (int)M, H, I, e, s));
+        if (!fuse_cs && gq.up_b && k.mlp_bias) NDT1_TRY(k_colsum<T>(dU, gq.up_b, M, I, I, s));
       }
-      if (gq.up_b && k.mlp_bias) NDT1_TRY(k_colsum<T>(dU, gq.up_b, M, I, I, s));
       NDT1_TRY(linear_wgrad(dU, I, h2[l], H, gq.up_w, H, (int)M, I, H, s));
       {
         GemmEpilogue e = gemm_epilogue_default();
@@ -498,10 +510,9 @@ struct Engine : ndt1_engine {
         NDT1_TRY(linear_dgrad(dU, I, W(q.up_w, kBf16 ? w_up[l] : nullptr), H, (int)M, I, H, e, s));
       }
       NDT1_TRY(k_layernorm_bwd<T>(dH, xs[2 * l + 1], q.ln2_w, mean[2 * l + 1], rstd[2 * l + 1], dX, gq.ln2_w, gq.ln2_b, dY, 0.f, seed, 0, M, H,
-                                  ln_part, s));
+                                  ln_part, s, k.attention_bias ? gq.o_b : nullptr));
       // attention block: x_mid = x_in + out_proj(drop(att))      dY = T(dX)
       const T* ad = (ptr_ > 0.f) ? attd[l] : att[l];
-      if (gq.o_b && k.attention_bias) NDT1_TRY(k_colsum<T>(dY, gq.o_b, M, H, H, s));
       NDT1_TRY(linear_wgrad(dY, H, ad, H, gq.o_w, H, (int)M, H, H, s));
       {
         GemmEpilogue e = gemm_epilogue_default();
@@ -518,9 +529,17 @@ struct Engine : ndt1_engine {
       if (kBf16 && !force_simt && !simt_attention && k_attention_tc_supported(ap)) NDT1_TRY(k_attention_tc_bwd(ap, s));
       else NDT1_TRY(k_attention_bwd<T>(ap, s));
       float* gw[3] = {gq.q_w, gq.k_w, gq.v_w}; float* gb[3] = {gq.q_b, gq.k_b, gq.v_b};
-      for (int j = 0; j < 3; ++j) {
-        if (gb[j] && k.attention_bias) NDT1_TRY(k_colsum<T>(dqkv + (long long)j * H, gb[j], M, H, 3 * H, s));
-        NDT1_TRY(linear_wgrad(dqkv + (long long)j * H, 3 * H, h1[l], H, gw[j], H, (int)M, H, H, s));
+      // flat gradient arena: q|k|v weights (and biases) adjacent -> one (3H x H) weight gradient, one bias reduction
+      if (gb[0] && gb[1] == gb[0] + H && gb[2] == gb[1] + H && k.attention_bias) {
+        NDT1_TRY(k_colsum<T>(dqkv, gb[0], M, 3 * H, 3 * H, s));
+      } else {
+        for (int j = 0; j < 3; ++j)
+          if (gb[j] && k.attention_bias) NDT1_TRY(k_colsum<T>(dqkv + (long long)j * H, gb[j], M, H, 3 * H, s));
+      }
+      if (gw[0] && gw[1] == gw[0] + (long long)H * H && gw[2] == gw[1] + (long long)H * H) {
+        NDT1_TRY(linear_wgrad(dqkv, 3 * H, h1[l], H, gw[0], H, (int)M, 3 * H, H, s));
+      } else {
+        for (int j = 0; j < 3; ++j) NDT1_TRY(linear_wgrad(dqkv + (long long)j * H, 3 * H, h1[l], H, gw[j], H, (int)M, H, H, s));
       }
       if (kBf16) {
         GemmEpilogue e = gemm_epilogue_default();
@@ -536,7 +555,8 @@ struct Engine : ndt1_engine {
       }
       const bool first = (l == 0);
       NDT1_TRY(k_layernorm_bwd<T>(dH, xs[2 * l], q.ln1_w, mean[2 * l], rstd[2 * l], dX, gq.ln1_w, gq.ln1_b, first ? (T*)nullptr : dY,
-                                  first ? 0.f : ptr_, seed, first ? 0 : site_mlp(l - 1), M, H, ln_part, s));
+                                  first ? 0.f : ptr_, seed, first ? 0 : site_mlp(l - 1), M, H, ln_part, s,
+                                  (!first && k.mlp_bias) ? G->layer[l - 1].down_b : nullptr));
       NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[NL - l], s));   // layer l gradients complete
     }
     // embedding: dX is the gradient w.r.t. the (dropped) embedding output.
@@ -551,6 +571,8 @@ struct Engine : ndt1_engine {
     if (G->proj_b) NDT1_TRY(k_colsum<T>(dY, G->proj_b, M, H, H, s));
     const T* dE = dY + (long long)n_prefix * H;
     const int eact = k.embed_act;
+    // (not in the stacked layout: there one output row of the overlap-add GEMM holds `stride` bins)
+    const bool fuse_embed_cs = kBf16 && !force_simt && G->embed_b && k.embed_bias && D % 8 == 0 && !k.stack_active;
     NDT1_REQUIRE(eact != NDT1_ACT_GELU, "engine: gelu as the embedder activation is not implemented in this build");
     if (k.stack_active) {
       const int K4 = k.stack_stride * D, nch = k.stack_size / k.stack_stride, R4 = Tn / k.stack_stride;
@@ -570,6 +592,7 @@ struct Engine : ndt1_engine {
       p.B = op(W(P->proj_w, w_proj), 0, 1, H, nch * K4, nch * K4);
       p.epi.out = dEmb; p.epi.out_bf16 = kBf16; p.epi.ldc = K4; p.epi.c_batch_stride = (long long)Tn * D;
       p.epi.dact = dact_from_out(eact); p.epi.dact_in = emb; p.epi.dact_in_bf16 = kBf16;
+      if (fuse_embed_cs) p.epi.colsum = G->embed_b;
       NDT1_TRY(run(p, s));
     } else {
       if (G->proj_w) {
@@ -586,9 +609,10 @@ struct Engine : ndt1_engine {
       p.B = op(W(P->proj_w, w_proj), 0, 1, H, D, D);
       p.epi.out = dEmb; p.epi.out_bf16 = kBf16; p.epi.ldc = D; p.epi.c_batch_stride = (long long)Tn * D;
       p.epi.dact = dact_from_out(eact); p.epi.dact_in = emb; p.epi.dact_in_bf16 = kBf16;
+      if (fuse_embed_cs) p.epi.colsum = G->embed_b;
       NDT1_TRY(run(p, s));
     }
-    if (G->embed_b && k.embed_bias) NDT1_TRY(k_colsum<T>(dEmb, G->embed_b, MT, D, D, s));
+    if (!fuse_embed_cs && G->embed_b && k.embed_bias) NDT1_TRY(k_colsum<T>(dEmb, G->embed_b, MT, D, D, s));
     if (G->embed_w) {
       const T* x_in = kBf16 ? xin : (const T*)spikes_ptr;
       const int ldx = kBf16 ? ldN : N;

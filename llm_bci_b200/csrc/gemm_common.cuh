@@ -56,6 +56,7 @@ struct GemmEpilogue {
   const void* dact_in;      // indexed like out
   int dact_in_bf16;
   int accumulate;           // 1: out (fp32) += value (atomic when split)
+  float* colsum;            // optional (tensor-core kernel only): colsum[n] += sum over rows and trials of the stored value
 };
 
 struct GemmProblem {
@@ -78,7 +79,7 @@ static inline GemmEpilogue gemm_epilogue_default() {
   e.gather_tab = nullptr; e.gather_idx = nullptr; e.gather_idx_stride = 0; e.gather_ld = 0;
   e.drop_p = 0.f; e.drop_bwd = 0; e.drop_seed = 0; e.drop_stream = 0;
   e.resid = nullptr; e.dact = DACT_NONE; e.dact_in = nullptr; e.dact_in_bf16 = 0;
-  e.accumulate = 0;
+  e.accumulate = 0; e.colsum = nullptr;
   return e;
 }
 

@@ -3,7 +3,9 @@
 // tcgen05.ld epilogue.  Persistent, warp specialised:
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..5  epilogue: TMEM -> registers -> fused epilogue -> global
+//   warps 2..9  epilogue: TMEM -> registers -> swizzled smem transpose ->
+//               fused epilogue with row-contiguous (128 B per 8 lanes) global
+//               reads / writes; two warps per TMEM lane quarter
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main
 // loop of tile i+1.  Tile = 128 x BN (BN in {64,128,256}), BLOCK_K = 64.
 //
@@ -14,6 +16,7 @@
 // so no transposed copy of a weight or an activation is ever materialised.
 #include "tc_common.cuh"
 #include "gemm_common.cuh"
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -22,8 +25,10 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = one 128-byte swizzle row
-constexpr int kThreads = 192;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kEpiWarps = 8;           // two warps per TMEM lane quarter, each owning half of the tile's columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kSmemPipe = 192 * 1024;  // operand ring
+constexpr int kStageTile = 32 * 32 * 4;   // per-warp staging tile of the epilogue: 32 rows x 32 fp32
 
 struct TcParams {
   int mode;
@@ -38,102 +43,236 @@ struct TcParams {
 
 using namespace tc;
 
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  __nv_bfloat162 x = __floats2bfloat162_rn(a, b), y = __floats2bfloat162_rn(c, d);
+  uint2 o; o.x = *(uint32_t*)&x; o.y = *(uint32_t*)&y;
+  return o;
+}
+__device__ __forceinline__ float4 unpack4_bf16(uint2 r) {
+  const __nv_bfloat162 x = *(const __nv_bfloat162*)&r.x, y = *(const __nv_bfloat162*)&r.y;
+  return make_float4(__low2float(x), __high2float(x), __low2float(y), __high2float(y));
+}
+
+
+// GELU(erf) and its derivative for the tensor-core (bf16) mode: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7,
+// far below bf16 resolution) on the MUFU pipe (one ex2, one rcp) instead of erff/expf -- the epilogue of the MLP
+// GEMMs is ALU-bound otherwise.  The strict fp32 mode (gemm_simt.cu) keeps erff.
+__device__ __forceinline__ void gelu_parts(float v, float& cdf, float& e) {
+  const float z = fabsf(v) * 0.70710678118654752f;
+  e = __expf(-z * z);                                   // exp(-v^2 / 2)
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  const float erf_abs = fmaf(-q * t, e, 1.0f);
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, v));
+}
+__device__ __forceinline__ float act_fast(int act, float v) {
+  if (act == ACT_GELU) { float cdf, e; gelu_parts(v, cdf, e); return v * cdf; }
+  return act_apply(act, v);
+}
+__device__ __forceinline__ float dact_fast(int dact, float saved) {
+  if (dact == DACT_GELU_FROM_IN) { float cdf, e; gelu_parts(saved, cdf, e); return fmaf(saved * 0.3989422804014327f, e, cdf); }
+  return dact_apply(dact, saved);
+}
+
 // ---------------------------------------------------------------------------
-// Epilogue over 8 consecutive columns of one row (vector path).
+// Epilogue.  tcgen05.ld hands every lane one ROW of the accumulator; storing that
+// directly makes each warp instruction touch 32 different rows (32 L1 wavefronts
+// for 512 bytes).  Instead each warp transposes its 32x32 fp32 chunk through a
+// private, XOR-swizzled shared-memory tile so that 8 consecutive lanes cover 128
+// contiguous bytes of one output row: the residual / saved-activation / position
+// table reads and the output stores are all full-line accesses.  The side input
+// of chunk i+1 is loaded into registers before chunk i is processed (and the first
+// chunk of the next tile before the accumulator barrier is waited on), so its
+// latency hides behind the tensor-core main loop.
+//
+// Lane l owns columns 4*(l%8)..+3 of rows (l/8)+4*i, i = 0..7, of the chunk.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_vec8(const GemmEpilogue& e, int n_total, int rows_c, const float* acc,
-                                              int b, int r, int n) {
-  const long long idx = (long long)b * e.c_batch_stride + (long long)r * e.ldc + n;
-  float v[8];
+enum { SIDE_NONE = 0, SIDE_RESID = 1, SIDE_DACT = 2, SIDE_GATHER = 3 };
+
+struct EpiCtx {
+  int side_kind;
+  bool vec_ok;
+};
+
+struct ChunkAt {          // where a (tile, chunk) lands in the output
+  int bt, r0, n;          // trial, first row of this warp's 32-row strip, first column of this lane
+  bool live;
+};
+
+__device__ __forceinline__ void side_load(const GemmEpilogue& e, const EpiCtx& cx, const TcParams& p, const ChunkAt& at, int lane,
+                                          float4* side) {
+  if (cx.side_kind == SIDE_NONE || !cx.vec_ok || !at.live || at.n >= p.N) return;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = acc[i] * e.alpha;
-  if (e.bias) {
-    const float4 b0 = *(const float4*)(e.bias + n), b1 = *(const float4*)(e.bias + n + 4);
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
-  if (e.out2) {
-    if (e.out2_bf16) {
-      __align__(16) bf16 o[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(v[i]);
-      *(uint4*)((bf16*)e.out2 + idx) = *(const uint4*)o;
-    } else {
-      *(float4*)((float*)e.out2 + idx) = make_float4(v[0], v[1], v[2], v[3]);
-      *(float4*)((float*)e.out2 + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  for (int i = 0; i < 8; ++i) {
+    const int r = at.r0 + (lane >> 3) + 4 * i;
+    if (r < p.M) {
+      const long long idx = (long long)at.bt * e.c_batch_stride + (long long)r * e.ldc + at.n;
+      if (cx.side_kind == SIDE_RESID) {
+        side[i] = __ldg((const float4*)(e.resid + idx));
+      } else if (cx.side_kind == SIDE_DACT) {
+        if (e.dact_in_bf16) {
+          const uint2 t = __ldg((const uint2*)((const bf16*)e.dact_in + idx));
+          side[i].x = __uint_as_float(t.x); side[i].y = __uint_as_float(t.y);
+        } else {
+          side[i] = __ldg((const float4*)((const float*)e.dact_in + idx));
+        }
+      } else {
+        const long long g = __ldg(e.gather_idx + (long long)at.bt * e.gather_idx_stride + r);
+        side[i] = __ldg((const float4*)(e.gather_tab + g * e.gather_ld + at.n));
+      }
     }
+  }
+}
+
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiCtx& cx, const TcParams& p, const ChunkAt& at, int lane,
+                                               const float4* acc, const float4* side) {
+  if (!at.live) return;
+  if (!cx.vec_ok) {        // ragged shapes (the 41-column head): element-wise, still row-contiguous across lanes
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = at.r0 + (lane >> 3) + 4 * i;
+      if (r >= p.M) continue;
+      const float a[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (at.n + j < p.N) gemm_epilogue_store(e, p.N, p.M, a[j], at.bt, r, at.n + j);
+    }
+    return;
+  }
+  const bool col_ok = at.n < p.N;      // N % 4 == 0 on this path
+  float4 v[8];
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e.bias && col_ok) bias4 = __ldg((const float4*)(e.bias + at.n));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i].x = fmaf(acc[i].x, e.alpha, bias4.x); v[i].y = fmaf(acc[i].y, e.alpha, bias4.y);
+    v[i].z = fmaf(acc[i].z, e.alpha, bias4.z); v[i].w = fmaf(acc[i].w, e.alpha, bias4.w);
+  }
+  // element offset of row i: idx0 + i * (4 * ldc); row-valid bits
+  const long long idx0 = (long long)at.bt * e.c_batch_stride + (long long)(at.r0 + (lane >> 3)) * e.ldc + at.n;
+  const long long ld4 = 4 * e.ldc;
+  uint32_t okm = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) okm |= (col_ok && (at.r0 + (lane >> 3) + 4 * i) < p.M) ? (1u << i) : 0u;
+#define idx(i) (idx0 + (i) * ld4)
+#define ok(i) ((okm >> (i)) & 1u)
+  if (e.out2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (ok(i)) {
+        if (e.out2_bf16) *(uint2*)((bf16*)e.out2 + idx(i)) = pack4_bf16(v[i].x, v[i].y, v[i].z, v[i].w);
+        else *(float4*)((float*)e.out2 + idx(i)) = v[i];
+      }
   }
   if (e.act != ACT_NONE) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = act_apply(e.act, v[i]);
+    for (int i = 0; i < 8; ++i) {
+      v[i].x = act_fast(e.act, v[i].x); v[i].y = act_fast(e.act, v[i].y);
+      v[i].z = act_fast(e.act, v[i].z); v[i].w = act_fast(e.act, v[i].w);
+    }
   }
   if (e.gather_tab) {
-    const long long g = e.gather_idx[(long long)b * e.gather_idx_stride + r];
-    const float* t = e.gather_tab + g * e.gather_ld + n;
-    const float4 t0 = *(const float4*)t, t1 = *(const float4*)(t + 4);
-    v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
-    v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cx.side_kind == SIDE_GATHER) t = side[i];
+      else if (ok(i)) {
+        const int r = at.r0 + (lane >> 3) + 4 * i;
+        const long long g = __ldg(e.gather_idx + (long long)at.bt * e.gather_idx_stride + r);
+        t = __ldg((const float4*)(e.gather_tab + g * e.gather_ld + at.n));
+      }
+      if (ok(i)) { v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w; }
+    }
   }
   if (e.drop_p > 0.f) {
-    const unsigned long long elem = ((unsigned long long)b * rows_c + r) * (unsigned long long)n_total + n;
-    float ds[8];
-    drop_scale_8(e.drop_seed, e.drop_stream, elem, drop_threshold(e.drop_p), 1.0f / (1.0f - e.drop_p), ds);
+    // One Philox block covers 8 consecutive elements = the columns of a lane PAIR.  The even lane draws the block of
+    // row 2k, the odd lane the block of row 2k+1, and they swap halves: one Philox per 8 elements, as in the forward
+    // of every other kernel that shares these streams.
+    const uint32_t thr = drop_threshold(e.drop_p);
+    const float ik = 1.0f / (1.0f - e.drop_p);
+    const bool odd = lane & 1;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= ds[i];
+    for (int k = 0; k < 4; ++k) {
+      const int r = at.r0 + (lane >> 3) + 4 * (2 * k + (odd ? 1 : 0));
+      const unsigned long long elem = ((unsigned long long)at.bt * p.M + r) * (unsigned long long)p.N + (unsigned)(at.n & ~7);
+      const Philox4 ph = philox4x32_10(e.drop_seed, elem >> 3, e.drop_stream);
+      const uint32_t s0 = odd ? ph.x : ph.z, s1 = odd ? ph.y : ph.w;
+      const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+      const uint32_t a0 = odd ? r0 : ph.x, a1 = odd ? r1 : ph.y;     // row 2k
+      const uint32_t b0 = odd ? ph.z : r0, b1 = odd ? ph.w : r1;     // row 2k+1
+      float4& va = v[2 * k]; float4& vb = v[2 * k + 1];
+      va.x *= (a0 & 0xFFFFu) >= thr ? ik : 0.f; va.y *= (a0 >> 16) >= thr ? ik : 0.f;
+      va.z *= (a1 & 0xFFFFu) >= thr ? ik : 0.f; va.w *= (a1 >> 16) >= thr ? ik : 0.f;
+      vb.x *= (b0 & 0xFFFFu) >= thr ? ik : 0.f; vb.y *= (b0 >> 16) >= thr ? ik : 0.f;
+      vb.z *= (b1 & 0xFFFFu) >= thr ? ik : 0.f; vb.w *= (b1 >> 16) >= thr ? ik : 0.f;
+    }
   }
   if (e.dact != DACT_NONE) {
-    float s[8];
-    if (e.dact_in_bf16) {
-      __align__(16) bf16 t[8];
-      *(uint4*)t = *(const uint4*)((const bf16*)e.dact_in + idx);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s[i] = __bfloat162float(t[i]);
-    } else {
-      const float4 s0 = *(const float4*)((const float*)e.dact_in + idx);
-      const float4 s1 = *(const float4*)((const float*)e.dact_in + idx + 4);
-      s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+    for (int i = 0; i < 8; ++i) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cx.side_kind == SIDE_DACT) {
+        s = e.dact_in_bf16 ? unpack4_bf16(make_uint2(__float_as_uint(side[i].x), __float_as_uint(side[i].y))) : side[i];
+      } else if (ok(i)) {
+        s = e.dact_in_bf16 ? unpack4_bf16(__ldg((const uint2*)((const bf16*)e.dact_in + idx(i))))
+                           : __ldg((const float4*)((const float*)e.dact_in + idx(i)));
+      }
+      v[i].x *= dact_fast(e.dact, s.x); v[i].y *= dact_fast(e.dact, s.y);
+      v[i].z *= dact_fast(e.dact, s.z); v[i].w *= dact_fast(e.dact, s.w);
     }
+  }
+  if (e.resid) {           // always the prefetched side input when present
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= dact_apply(e.dact, s[i]);
+    for (int i = 0; i < 8; ++i)
+      if (ok(i)) { v[i].x += side[i].x; v[i].y += side[i].y; v[i].z += side[i].z; v[i].w += side[i].w; }
   }
-  if (e.resid) {
-    const float4 r0 = *(const float4*)(e.resid + idx), r1 = *(const float4*)(e.resid + idx + 4);
-    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-  }
-  if (e.accumulate) {
-    red_add_v4((float*)e.out + idx, v[0], v[1], v[2], v[3]);
-    red_add_v4((float*)e.out + idx + 4, v[4], v[5], v[6], v[7]);
-  } else if (e.out_bf16) {
-    __align__(16) bf16 o[8];
+  if (e.colsum) {          // bias gradient of the producing layer: column sums of this chunk, one red per column per warp
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(v[i]);
-    *(uint4*)((bf16*)e.out + idx) = *(const uint4*)o;
-  } else {
-    *(float4*)((float*)e.out + idx) = make_float4(v[0], v[1], v[2], v[3]);
-    *(float4*)((float*)e.out + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    for (int i = 0; i < 8; ++i)
+      if (ok(i)) { cs.x += v[i].x; cs.y += v[i].y; cs.z += v[i].z; cs.w += v[i].w; }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+      cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+    }
+    if (lane < 8 && col_ok) red_add_v4(e.colsum + at.n, cs.x, cs.y, cs.z, cs.w);
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (!ok(i)) continue;
+    if (e.accumulate) red_add_v4((float*)e.out + idx(i), v[i].x, v[i].y, v[i].z, v[i].w);
+    else if (e.out_bf16) *(uint2*)((bf16*)e.out + idx(i)) = pack4_bf16(v[i].x, v[i].y, v[i].z, v[i].w);
+    else *(float4*)((float*)e.out + idx(i)) = v[i];
+  }
+#undef idx
+#undef ok
 }
 
 // ---------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------
 template <int BN, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)   // 10 warps: 3 share one SM sub-partition -> 168 registers per thread
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGES = kSmemBudget / STAGE_BYTES;
+  constexpr int STAGES = kSmemPipe / STAGE_BYTES;
   constexpr bool A_MN = (MODE == GEMM_TN);
   constexpr bool B_MN = (MODE != GEMM_NT);
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr int NCH = BN / 64;                         // 32-column chunks per epilogue warp
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint8_t* stage_tiles = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = (uint64_t*)(stage_tiles + kEpiWarps * kStageTile);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
@@ -146,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -243,50 +382,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps =====================
+    const int ew = warp - 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                     // which half of the tile's columns
+    uint8_t* stg = stage_tiles + ew * kStageTile;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const GemmEpilogue& e = p.epi;
+    EpiCtx cx;
+    cx.vec_ok = (p.N % 4 == 0) && (e.ldc % 4 == 0) && (e.c_batch_stride % 4 == 0) && (e.gather_tab == nullptr || e.gather_ld % 4 == 0) &&
+                (e.drop_p <= 0.f || p.N % 8 == 0);
+    cx.side_kind = e.resid ? SIDE_RESID : (e.dact != DACT_NONE ? SIDE_DACT : (e.gather_tab ? SIDE_GATHER : SIDE_NONE));
     int acc_stage = 0; uint32_t acc_phase = 0;
-    const bool vec_ok = (p.N % 8 == 0) && (p.epi.ldc % 8 == 0) && (p.epi.c_batch_stride % 8 == 0) &&
-                        (p.epi.gather_tab == nullptr || p.epi.gather_ld % 4 == 0);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+
+    auto locate = [&](int tile, int c) {
+      ChunkAt at;
+      at.live = tile < p.total_tiles;
       const int nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
       const int bz = rest / p.m_tiles;
-      const int bt = (MODE == GEMM_TN) ? 0 : bz;
-      const int m0 = mt * BM, n0 = nt * BN;
-      bool empty_split = false;
+      at.bt = (MODE == GEMM_TN) ? 0 : bz;
+      at.r0 = mt * BM + q * 32;
+      at.n = nt * BN + half * (BN / 2) + c * 32 + (lane & 7) * 4;
       if (MODE == GEMM_TN && p.split_k > 1) {
         const int per = (total_kb + p.split_k - 1) / p.split_k;
-        empty_split = (bz * per >= total_kb);
+        if (bz * per >= total_kb) at.live = false;       // empty split: nothing to add
       }
+      return at;
+    };
+
+    float4 side_cur[8], side_nxt[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) side_cur[i] = side_nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    side_load(e, cx, p, locate(blockIdx.x, 0), lane, side_cur);
+
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tc_fence_after();
-      const int r = m0 + q * 32 + lane;
-      const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= p.N) break;                // warp-uniform
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * BN + half * (BN / 2));
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const ChunkAt at = locate(tile, c);
         uint32_t raw[32];
-        tmem_ld32(taddr_row + c0, raw);
+        tmem_ld32(taddr_row + c * 32, raw);
+        // side input of the next chunk (or of the next tile's first chunk) while the TMEM load is in flight
+        const ChunkAt nx = (c + 1 < NCH) ? locate(tile, c + 1) : locate(tile + gridDim.x, 0);
+        side_load(e, cx, p, nx, lane, side_nxt);
         tmem_ld_wait();
-        if (r < p.M && !empty_split) {
-          const float* acc = (const float*)raw;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + c0 + g * 8;
-            if (vec_ok && n + 8 <= p.N) {
-              epilogue_vec8(p.epi, p.N, p.M, acc + g * 8, bt, r, n);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (n + i < p.N) gemm_epilogue_store(p.epi, p.N, p.M, acc[g * 8 + i], bt, r, n + i);
-            }
-          }
+        if (c == NCH - 1) {                         // accumulator fully read: hand the TMEM stage back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc_stage]);
         }
+        // transpose through the swizzled staging tile: lane = row -> lane = (row group, 4-column group)
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const uint32_t a = stg_u32 + lane * 128 + (((c4 ^ lane) & 7) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(raw[4 * c4]), "r"(raw[4 * c4 + 1]), "r"(raw[4 * c4 + 2]),
+                       "r"(raw[4 * c4 + 3]) : "memory");
+        }
+        __syncwarp();
+        float4 acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = (lane >> 3) + 4 * i;
+          acc[i] = *(const float4*)(stg + rr * 128 + ((((lane & 7) ^ rr) & 7) << 4));
+        }
+        __syncwarp();
+        epilogue_chunk(e, cx, p, at, lane, acc, side_cur);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) side_cur[i] = side_nxt[i];
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc_stage]);
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   }
@@ -357,8 +523,9 @@ int make_map(const GemmOperand& o, int box_cols, int box_rows, CUtensorMap* out)
 template <int BN, int MODE>
 int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
   constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;
-  constexpr int STAGES = kSmemBudget / STAGE_BYTES;
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
+  constexpr int STAGES = kSmemPipe / STAGE_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + kEpiWarps * kStageTile + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
+  static_assert(SMEM <= 227 * 1024, "gemm_tc: shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -420,7 +587,11 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
                  "gemm_tc: GEMM_TN reduction rows must be bounded by the A operand (rows=%d chunk_k=%d)", p.A.rows, p.chunk_k);
     NDT1_REQUIRE(p.b_chunk_n > 0, "gemm_tc: b_chunk_n must be set for GEMM_TN");
   }
+  NDT1_REQUIRE(!p.epi.colsum || (p.N % 8 == 0 && p.epi.ldc % 4 == 0 && p.epi.c_batch_stride % 4 == 0),
+               "gemm_tc: the fused column sum needs a vectorisable output (N=%d)", p.N);
   int bn = p.N > 128 ? 256 : (p.N > 64 ? 128 : 64);
+  static const int force_bn = getenv("NDT1_GEMM_BN") ? atoi(getenv("NDT1_GEMM_BN")) : 0;   // tile-shape experiments only
+  if (force_bn == 64 || force_bn == 128 || force_bn == 256) bn = force_bn < bn ? force_bn : bn;
   if (p.mode == GEMM_TN && p.b_chunk_n % bn != 0) bn = (p.b_chunk_n % 128 == 0) ? 128 : 64;
   NDT1_REQUIRE(p.mode != GEMM_TN || p.b_chunk_n % bn == 0 || p.b_chunk_n >= p.N, "gemm_tc: b_chunk_n=%d incompatible with tile", p.b_chunk_n);
 

@@ -15,6 +15,12 @@ int k_uniform_f32(float* out, long long n, unsigned long long seed, unsigned lon
 int k_pad_pack(const void* src, const long long* offsets, void* dst, int B, int P, int inner, int elem_size, int side_left, int full,
                double value, cudaStream_t stream);
 int k_cast_f32_bf16(const float* in, bf16* out, long long rows, int cols, long long ld_in, long long ld_out, cudaStream_t stream);
+constexpr int CAST_MAX_SEGS = 64;
+struct CastSegs {            // fp32 -> bf16 copies done by one launch (k_cast_multi fills first_chunk / total_chunks)
+  const float* src[CAST_MAX_SEGS]; bf16* dst[CAST_MAX_SEGS]; long long count[CAST_MAX_SEGS]; long long first_chunk[CAST_MAX_SEGS];
+  long long total_chunks; int n;
+};
+int k_cast_multi(CastSegs& segs, cudaStream_t stream);
 template <typename T> int k_colsum(const T* in, float* out, long long rows, int cols, long long ld, cudaStream_t stream);
 template <typename T>
 int k_grad_prep(const float* g, T* out, long long rows, int cols, float drop_p, unsigned long long seed, unsigned long long stream_id,
@@ -40,7 +46,7 @@ int k_layernorm_fwd(const float* x, const float* gamma, const float* beta, T* y,
 template <typename T>
 int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float* mean, const float* rstd, float* dres, float* dgamma,
                     float* dbeta, T* out_lp, float drop_p, unsigned long long seed, unsigned long long stream_id, long long rows, int H,
-                    float* partials, cudaStream_t stream);
+                    float* partials, cudaStream_t stream, float* colsum_out = nullptr);   // colsum_out[c] += sum_r out_lp[r, c]
 size_t k_layernorm_bwd_partials_bytes(int H);
 
 // attention.cu (CUDA-core path, both precisions)
@@ -75,6 +81,6 @@ int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaS
 // log-probs (B, L, V); per-trial NLL summed into *loss; dlogits = (softmax - posterior) * (*dloss) for t < len
 int k_ctc_fwd_bwd(const float* logp, const long long* targets, const long long* in_len, const long long* tgt_len, int B, int L, int V,
                   int S, int blank, int zero_infinity, float* alpha_ws, float* nll, float* loss, float* dlogits, const float* dloss,
-                  cudaStream_t stream);
+                  cudaStream_t stream, int fast_math = 0);
 size_t k_ctc_workspace_floats(int B, int L, int S);
 int k_ctc_greedy_decode(const float* logp, int B, int L, int V, int blank, long long* out_ids, long long* out_len, cudaStream_t stream);

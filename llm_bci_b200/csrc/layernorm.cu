@@ -74,42 +74,54 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
   }
 }
 
+// Backward.  One warp per row, 8 warps per CTA, one CTA per SM (persistent over rows): every lane issues the
+// whole row's loads (dy, x AND the residual gradient) before the first reduction, so a warp keeps 10 KB in flight
+// and the 8 warps of an SM cover the HBM latency.  The affine gradients are accumulated in registers over the
+// rows of the warp, folded through shared memory once per CTA and added to dgamma / dbeta with red.global.
+constexpr int LNB_WARPS = 8;    // two warps per SM sub-partition: up to 255 registers per thread
+
 template <typename T>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
 ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
               const float* __restrict__ rstd, float* __restrict__ dres, T* __restrict__ out_lp, float drop_p, unsigned long long seed,
-              unsigned long long stream_id, long long rows, int H, float* __restrict__ partials) {
-  extern __shared__ float sm[];   // [2][H]
+              unsigned long long stream_id, long long rows, int H, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ colsum_out) {
+  extern __shared__ float sm[];   // [2][H] affine gradients, then [4][H/4] column sums of out_lp (plane j = column 4c+j)
   const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  const long long warp0 = (long long)blockIdx.x * LNB_WARPS + (threadIdx.x >> 5);
   const int nv = H / 4;
-  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sm[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
-  float4 dg[LN_MAXV], db[LN_MAXV], gm[LN_MAXV];
+  float* sm_cs = sm + 2 * H;
+  float4 dg[LN_MAXV], db[LN_MAXV];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f); db[i] = dg[i];
-    const int c = lane + 32 * i;
-    gm[i] = c < nv ? *(const float4*)(gamma + c * 4) : dg[i];
-  }
+  for (int i = 0; i < LN_MAXV; ++i) { dg[i] = make_float4(0.f, 0.f, 0.f, 0.f); db[i] = dg[i]; }
   const uint32_t thr = drop_threshold(drop_p);
   const float ik = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
-  for (long long r = warp0; r < rows; r += (long long)gridDim.x * LN_WARPS) {
+  for (long long r = warp0; r < rows; r += (long long)gridDim.x * LNB_WARPS) {
+    float4 d[LN_MAXV], xv[LN_MAXV], o[LN_MAXV];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        d[i] = load4<T>(dy + r * H + c * 4);
+        xv[i] = *(const float4*)(x + r * H + c * 4);
+        o[i] = *(const float4*)(dres + r * H + c * 4);
+      }
+    }
     const float mu = mean[r], rs = rstd[r];
-    float4 g[LN_MAXV], xh[LN_MAXV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i) {
       const int c = lane + 32 * i;
       if (c < nv) {
-        const float4 d = load4<T>(dy + r * H + c * 4);
-        const float4 xv = *(const float4*)(x + r * H + c * 4);
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
-        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
-        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
-        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
-        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+        const float4 gm = __ldg((const float4*)(gamma + c * 4));
+        xv[i] = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);   // x-hat
+        dg[i].x += d[i].x * xv[i].x; dg[i].y += d[i].y * xv[i].y; dg[i].z += d[i].z * xv[i].z; dg[i].w += d[i].w * xv[i].w;
+        db[i].x += d[i].x; db[i].y += d[i].y; db[i].z += d[i].z; db[i].w += d[i].w;
+        d[i] = make_float4(d[i].x * gm.x, d[i].y * gm.y, d[i].z * gm.z, d[i].w * gm.w);                              // dy * gamma
+        s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+        s2 += d[i].x * xv[i].x + d[i].y * xv[i].y + d[i].z * xv[i].z + d[i].w * xv[i].w;
       }
     }
     const float c1 = warp_sum(s1) / H, c2 = warp_sum(s2) / H;
@@ -117,23 +129,25 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float
     for (int i = 0; i < LN_MAXV; ++i) {
       const int c = lane + 32 * i;
       if (c < nv) {
-        float* dr = dres + r * H + c * 4;
-        float4 o = *(float4*)dr;
-        o.x += rs * (g[i].x - c1 - xh[i].x * c2); o.y += rs * (g[i].y - c1 - xh[i].y * c2);
-        o.z += rs * (g[i].z - c1 - xh[i].z * c2); o.w += rs * (g[i].w - c1 - xh[i].w * c2);
-        *(float4*)dr = o;
+        o[i].x += rs * (d[i].x - c1 - xv[i].x * c2); o[i].y += rs * (d[i].y - c1 - xv[i].y * c2);
+        o[i].z += rs * (d[i].z - c1 - xv[i].z * c2); o[i].w += rs * (d[i].w - c1 - xv[i].w * c2);
+        *(float4*)(dres + r * H + c * 4) = o[i];
         if (out_lp) {
+          float4 q = o[i];
           if (drop_p > 0.f) {
             float ds[4];
             drop_scale_4(seed, stream_id, (unsigned long long)(r * H + c * 4), thr, ik, ds);
-            o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
+            q.x *= ds[0]; q.y *= ds[1]; q.z *= ds[2]; q.w *= ds[3];
           }
-          store4<T>(out_lp + r * H + c * 4, o.x, o.y, o.z, o.w);
+          store4<T>(out_lp + r * H + c * 4, q.x, q.y, q.z, q.w);
+          if (colsum_out) {   // bias gradient of the linear layer that consumed this row's forward counterpart
+            atomicAdd(&sm_cs[c], q.x); atomicAdd(&sm_cs[nv + c], q.y); atomicAdd(&sm_cs[2 * nv + c], q.z); atomicAdd(&sm_cs[3 * nv + c], q.w);
+          }
         }
       }
     }
   }
-  // block reduction of the affine gradients, then one partial row per block
+  // fold the affine gradients of the CTA's warps, then one red.global per column per CTA
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i) {
     const int c = lane + 32 * i;
@@ -143,16 +157,11 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) partials[(long long)blockIdx.x * 2 * H + i] = sm[i];
-}
-
-__global__ void ln_bwd_reduce_kernel(const float* __restrict__ partials, int nblocks, int H, float* dgamma, float* dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * H) return;
-  float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partials[(long long)b * 2 * H + c];
-  if (c < H) dgamma[c] += s;
-  else dbeta[c - H] += s;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, sm[i]);
+    if (dbeta) atomicAdd(dbeta + i, sm[H + i]);
+    if (colsum_out) atomicAdd(colsum_out + (i % nv) * 4 + i / nv, sm_cs[i]);
+  }
 }
 
 int ln_blocks(long long rows) {
@@ -177,14 +186,16 @@ int k_layernorm_fwd(const float* x, const float* gamma, const float* beta, T* y,
 template <typename T>
 int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float* mean, const float* rstd, float* dres, float* dgamma,
                     float* dbeta, T* out_lp, float drop_p, unsigned long long seed, unsigned long long stream_id, long long rows, int H,
-                    float* partials, cudaStream_t stream) {
+                    float* partials, cudaStream_t stream, float* colsum_out) {
   NDT1_REQUIRE(H % 4 == 0 && H <= 128 * LN_MAXV, "layernorm: hidden size %d unsupported (multiple of 4, <= %d)", H, 128 * LN_MAXV);
   if (rows == 0) return 0;
-  const int nb = ln_blocks(rows);
-  ln_bwd_kernel<T><<<nb, LN_WARPS * 32, 2 * H * sizeof(float), stream>>>(dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed, stream_id,
-                                                                          rows, H, partials);
-  NDT1_CHECK_LAUNCH();
-  ln_bwd_reduce_kernel<<<ndt1_cdiv(2 * H, 128), 128, 0, stream>>>(partials, nb, H, dgamma, dbeta);
+  (void)partials;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  long long nb = (rows + LNB_WARPS - 1) / LNB_WARPS;
+  if (nb > sms) nb = sms;
+  ln_bwd_kernel<T><<<(int)nb, LNB_WARPS * 32, 3 * H * sizeof(float), stream>>>(dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed,
+                                                                               stream_id, rows, H, dgamma, dbeta, out_lp ? colsum_out : nullptr);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -192,6 +203,6 @@ int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float
 template int k_layernorm_fwd<float>(const float*, const float*, const float*, float*, float*, float*, long long, int, float, cudaStream_t);
 template int k_layernorm_fwd<bf16>(const float*, const float*, const float*, bf16*, float*, float*, long long, int, float, cudaStream_t);
 template int k_layernorm_bwd<float>(const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*, float,
-                                    unsigned long long, unsigned long long, long long, int, float*, cudaStream_t);
+                                    unsigned long long, unsigned long long, long long, int, float*, cudaStream_t, float*);
 template int k_layernorm_bwd<bf16>(const bf16*, const float*, const float*, const float*, const float*, float*, float*, float*, bf16*, float,
-                                   unsigned long long, unsigned long long, long long, int, float*, cudaStream_t);
+                                   unsigned long long, unsigned long long, long long, int, float*, cudaStream_t, float*);

@@ -84,9 +84,11 @@ static GemmProblem base_problem(int mode, int M, int N, int K) {
 }
 
 int main(int argc, char** argv) {
-  const bool quick = argc > 1;
+  // usage: gemm_selftest [trials]   (default 8; 32 = the benchmark batch)
+  const bool quick = argc > 1 && atoi(argv[1]) <= 0;
+  const int trials = (argc > 1 && atoi(argv[1]) > 0) ? atoi(argv[1]) : 8;
   if (gemm_tc_init()) { printf("init failed: %s\n", ndt1_last_error()); return 1; }
-  const int Bt = quick ? 2 : 8, T = 1000, D = 256, H = 1024, Tp = (T - 32) / 4 + 1;  // 243
+  const int Bt = quick ? 2 : trials, T = 1000, D = 256, H = 1024, Tp = (T - 32) / 4 + 1;  // 243
   const int M = Bt * Tp;
 
   {  // plain NT: y = x W^T + b, fp32 out

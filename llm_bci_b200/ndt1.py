@@ -533,7 +533,18 @@ class NDT1(nn.Module):
         """Offsets (in floats, 256-byte aligned) of every parameter inside one flat gradient buffer."""
         table, _ = self._params()
         offs, off = {}, 0
-        for _, p in table:
+        # arena order: the table's, except that each layer's q|k|v weights (and biases) sit next to each other so the
+        # engine can run one (3H x H) weight-gradient GEMM, one bias reduction and one weight cast for the three
+        rank = {"q_w": 0, "k_w": 1, "v_w": 2, "q_b": 3, "k_b": 4, "v_b": 5}
+        def key(item):
+            i, (slot, _) = item
+            if slot.startswith("layer."):
+                _, l, name = slot.split(".")
+                if name in rank:
+                    return (1, int(l), 0, rank[name])
+                return (1, int(l), 1, i)
+            return (0, 0, 0, i) if i < 7 else (2, 0, 0, i)
+        for _, (_, p) in sorted(enumerate(table), key=key):
             if p is not None:
                 offs[id(p)] = off
                 off += (p.numel() + 63) // 64 * 64
