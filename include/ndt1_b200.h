@@ -201,6 +201,10 @@ int ndt1_engine_out_len(const ndt1_engine* e, int T);
 int ndt1_engine_forward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_batch* batch, const ndt1_outputs* out, void* stream);
 /* backward of the last forward: grads->X += dloss * dLoss/dX (buffers are caller-zeroed) */
 int ndt1_engine_backward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_tensors* grads, const float* dloss, void* stream);
+/* The backward runs its weight-gradient GEMMs on an engine-owned second stream, concurrently with the data-gradient
+ * chain (joined before ndt1_engine_backward's work on `stream` ends).  on = 0 serialises everything on `stream`
+ * (used to time single kernels); default 1, or 0 when NDT1_OVERLAP=0 is set at engine creation. */
+int ndt1_engine_set_overlap(ndt1_engine* e, int on);
 /* Gradient stages of the last backward in completion order: 0 = decoder + out_norm,
  * 1..n_layers = layers n_layers-1..0, n_layers+1 = embedder.  ndt1_engine_wait_stage makes
  * `stream` wait (cudaStreamWaitEvent) until that stage's gradients are final, so a bucketed

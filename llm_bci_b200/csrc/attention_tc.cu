@@ -103,16 +103,23 @@ __device__ __forceinline__ void st_global8(bf16* dst, const float* v) {
 // ---------------------------------------------------------------------------
 // forward.  256 threads: warp w owns TMEM lanes 32*(w%4).. (one query row per lane) and the
 // key columns [128*(w/4), +128) of that row; the two halves of a row meet through smem.
+//
+// Two CTAs share an SM (the kernel is a dependent chain load -> S -> softmax -> PV -> store, so a
+// second resident CTA is what hides it): shared memory holds only Q and ONE 64 KB K/V buffer (V
+// is fetched into it once S = Q K^T has retired), and tensor memory holds 256 columns:
+//   S  fp32  columns [0, 256)
+//   P  bf16  packed two keys per column, written IN PLACE behind each thread's read pointer:
+//            keys [0,128) -> columns [0,64), keys [128,256) -> columns [128,192)
+//   O  fp32  head-dim halves in the columns P leaves free: [64,128) and [192,256)
+// P never touches shared memory: the P V product takes its A operand from tensor memory.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map256, const TcAttn a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                 // 2 x [128 x 64]   32 KB
-  uint8_t* sK = sQ + 32768;           // 2 x [256 x 64]   64 KB   (later: P as 4 x [128 x 64])
-  uint8_t* sV = sK + 65536;           // 2 x [256 x 64]   64 KB
-  uint8_t* sP = sK;
-  float* s_m = (float*)(sV + 65536);  // [2][128] row maxima of the two column halves
+  uint8_t* sKV = sQ + 32768;          // 2 x [256 x 64]   64 KB   K, then V
+  float* s_m = (float*)(sKV + 65536); // [2][128] row maxima of the two column halves
   float* s_l = s_m + 256;             // [2][128] row sums
   uint32_t* s_kvw = (uint32_t*)(s_l + 256);   // [8] key_valid bits
   uint64_t* bars = (uint64_t*)(s_kvw + 8);    // qk, v, s, o
@@ -132,7 +139,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -142,16 +149,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   if (tid == 0) {
     mbar_expect_tx(&bars[0], 32768 + 65536);
     for (int c = 0; c < 2; ++c) tma_load_3d(sQ + c * 16384, &map128, &bars[0], h * HD + 64 * c, q0, b);
-    for (int c = 0; c < 2; ++c) tma_load_3d(sK + c * 32768, &map256, &bars[0], H + h * HD + 64 * c, 0, b);
-    mbar_expect_tx(&bars[1], 65536);
-    for (int c = 0; c < 2; ++c) tma_load_3d(sV + c * 32768, &map256, &bars[1], 2 * H + h * HD + 64 * c, 0, b);
+    for (int c = 0; c < 2; ++c) tma_load_3d(sKV + c * 32768, &map256, &bars[0], H + h * HD + 64 * c, 0, b);
     mbar_wait(&bars[0], 0);
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16(128, 256, false, false);
 #pragma unroll
     for (int ks = 0; ks < HD / 16; ++ks) {
       const uint64_t ad = make_sdesc(smem_u32(sQ) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-      const uint64_t bd = make_sdesc(smem_u32(sK) + (ks >> 2) * 32768 + (ks & 3) * 32, 16, 1024);
+      const uint64_t bd = make_sdesc(smem_u32(sKV) + (ks >> 2) * 32768 + (ks & 3) * 32, 16, 1024);
       tc_mma_bf16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
     }
     tc_commit(&bars[2]);
@@ -159,6 +164,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   __syncwarp();
   mbar_wait(&bars[2], 0);
   tc_fence_after();
+  if (tid == 0) {                           // K is consumed: V takes its place while the softmax runs
+    mbar_expect_tx(&bars[1], 65536);
+    for (int c = 0; c < 2; ++c) tma_load_3d(sKV + c * 32768, &map256, &bars[1], 2 * H + h * HD + 64 * c, 0, b);
+  }
 
   const int row = quarter * 32 + lane;
   const int qi = q0 + row;
@@ -169,15 +178,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
 #pragma unroll
   for (int c = 0; c < 4; ++c) mw[c] = query_mask_word(qi, cbase + 32 * c, a.cf, a.cb, s_kvw[half * 4 + c], L);
   float m = -INFINITY;
-#pragma unroll
+#pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     const int c0 = cbase + 32 * c;
     if (c0 < L) {                                     // warp-uniform
       uint32_t raw[32];
       tmem_ld32(trow + c0, raw);
       tmem_ld_wait();
+      const uint32_t w = mw[c];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) m = fmaxf(m, (mw[c] >> j) & 1u ? __uint_as_float(raw[j]) : -INFINITY);
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, (w >> j) & 1u ? __uint_as_float(raw[j]) : -INFINITY);
     }
   }
   s_m[half * 128 + row] = m;
@@ -191,9 +201,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   const long long bh_row = ((long long)b * p.nh + h) * L + qi;
   const unsigned long long ebase = (unsigned long long)bh_row * (unsigned long long)L;
   const bool aligned = (L & 7) == 0;
-#pragma unroll
+#pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     const int c0 = cbase + 32 * c;
+    uint32_t pk[16];
     if (c0 < L) {
       uint32_t kw = 0xFFFFFFFFu;
       if (drop) {
@@ -203,33 +214,36 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
       uint32_t raw[32];
       tmem_ld32(trow + c0, raw);
       tmem_ld_wait();
+      const uint32_t w = mw[c];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float pv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = g * 8 + i;
-          const float s = fmaf(__uint_as_float(raw[j]), sl2, -m_s);
-          const float e = ex2f((mw[c] >> j) & 1u ? s : -INFINITY);
-          l += e;
-          pv[i] = (kw >> j) & 1u ? e * ik : 0.f;
-        }
-        st_row8(sP, row, c0 + g * 8, pv);
+      for (int j = 0; j < 32; j += 2) {
+        const float s0 = fmaf(__uint_as_float(raw[j]), sl2, -m_s), s1 = fmaf(__uint_as_float(raw[j + 1]), sl2, -m_s);
+        const float e0 = ex2f((w >> j) & 1u ? s0 : -INFINITY), e1 = ex2f((w >> (j + 1)) & 1u ? s1 : -INFINITY);
+        l += e0 + e1;
+        pk[j >> 1] = pack_bf16x2((kw >> j) & 1u ? e0 * ik : 0.f, (kw >> (j + 1)) & 1u ? e1 * ik : 0.f);
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = 0u;
     }
+    // P in place: 16 packed columns behind this thread's read pointer (see the layout above)
+    if (c0 < nks * 16) tmem_st16(trow + cbase + 16 * c, pk);
   }
+  tmem_st_wait();
   s_l[half * 128 + row] = l;
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
     mbar_wait(&bars[1], 0);
     tc_fence_after();
-    constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, true);
     for (int ks = 0; ks < nks; ++ks) {
-      const uint64_t ad = make_sdesc(smem_u32(sP) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-      const uint64_t bd = make_sdesc(smem_u32(sV) + ks * 2048, 32768, 1024);
-      tc_mma_bf16(tmem + 256, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      const uint32_t pa = tmem + (ks < 8 ? ks * 8 : 128 + (ks - 8) * 8);
+#pragma unroll
+      for (int dh = 0; dh < 2; ++dh) {
+        const uint64_t bd = make_sdesc(smem_u32(sKV) + dh * 32768 + ks * 2048, 32768, 1024);
+        tc_mma_bf16_ts(tmem + (dh ? 192 : 64), pa, bd, idesc, ks > 0 ? 1u : 0u);
+      }
     }
     tc_commit(&bars[3]);
   }
@@ -240,11 +254,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   const float inv = (l > 0.f) ? 1.f / l : 0.f;
   const uint32_t thr_o = drop_threshold(p.p_out);
   const float iko = p.p_out > 0.f ? 1.0f / (1.0f - p.p_out) : 1.f;
-#pragma unroll
+#pragma unroll 1
   for (int cc = 0; cc < 2; ++cc) {
-    const int c0 = half * 64 + cc * 32;
+    const int c0 = half * 64 + cc * 32;               // head-dim column
     uint32_t raw[32];
-    tmem_ld32(trow + 256 + c0, raw);
+    tmem_ld32(trow + (half ? 192 : 64) + cc * 32, raw);
     tmem_ld_wait();
     if (qi < L) {
       const long long o = ((long long)b * L + qi) * H + h * HD + c0;
@@ -269,7 +283,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   if (half == 0 && qi < L) p.lse[bh_row] = m * p.scale + logf(l);
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 // ---------------------------------------------------------------------------
@@ -571,7 +585,7 @@ int make_maps(const AttnParams& p, CUtensorMap* m128, CUtensorMap* m256, CUtenso
   return 0;
 }
 
-constexpr int SMEM_FWD = 32768 + 65536 + 65536 + 2048 + 32 + 64 + 1024;
+constexpr int SMEM_FWD = 32768 + 65536 + 2048 + 32 + 64 + 1024;
 constexpr int SMEM_BQ = 32768 * 2 + 65536 * 2 + 32 + 64 + 1024;
 constexpr int SMEM_BKV = 32768 * 6 + 1024 + 2048 + 64 + 1024;
 

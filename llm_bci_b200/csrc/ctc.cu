@@ -3,10 +3,10 @@
 // at models/ndt1.py:493-500,517,581 (conventions: SURVEY.md A.6) and the
 // greedy collapse of utils/eval_bci.py:41-48.
 //
-// One CTA per trial; one thread per state of the extended label sequence
-// (blank, l1, blank, l2, ..., blank) in each of two groups: alpha is swept
-// forward and beta backward AT THE SAME TIME (L dependent steps, not 2 L), then
-// the gradient w.r.t. the LOGITS,
+// One CTA per trial.  The states of the extended label sequence (blank, l1,
+// blank, l2, ..., blank) live in the registers of ONE warp per sweep; alpha is
+// swept forward and beta backward AT THE SAME TIME by two warps (L dependent
+// steps, not 2 L, no block barrier inside), then the gradient w.r.t. the LOGITS,
 //     dlogits[t,c] = (softmax[t,c] - posterior[t,c]) * dloss      (t <  len)
 //                  = 0                                            (t >= len)
 // is emitted by a parallel pass, so no separate log-softmax backward exists.
@@ -32,11 +32,12 @@ __global__ void log_softmax_kernel(const float* __restrict__ logits, float* __re
 
 struct CtcParams {
   const float* logp; const long long* targets; const long long* in_len; const long long* tgt_len;
-  int B, L, V, S, blank, zero_infinity, lp_in_smem, LXP;
+  int B, L, V, S, blank, zero_infinity, lp_in_smem;
   float* alpha; float* beta; float* nll; float* dlogits; const float* dloss;
 };
 
-constexpr int kRenorm = 8;   // re-centre the alpha/beta rows every kRenorm frames
+constexpr int kRenorm = 8;    // re-centre the alpha/beta rows every kRenorm frames
+constexpr int kCtcWarps = 8;
 
 // FAST: MUFU ex2/lg2 (bf16 engine mode); otherwise libm-accurate expf/logf (strict fp32 mode, stand-alone operator)
 template <bool FAST> __device__ __forceinline__ float exp_t(float x) { return FAST ? __expf(x) : expf(x); }
@@ -48,26 +49,120 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
   return m + log_t<FAST>(exp_t<FAST>(a - m) + exp_t<FAST>(b - m) + exp_t<FAST>(c - m));
 }
 
-// One CTA per trial.  The alpha sweep (threads [0, LXP), one per state of the extended label sequence) and the
-// beta sweep (threads [LXP, 2 LXP)) run CONCURRENTLY, one frame per barrier, so the sequential depth is L frames
-// instead of 2 L; both keep their rows in shared memory and stream the re-centred rows to a workspace.  A final,
-// fully parallel pass (one warp per frame) turns alpha + beta into label posteriors and writes the gradient
-// w.r.t. the logits.  Rows are kept re-centred (alpha_hat = alpha - C_t, beta_hat = beta - D_t, offsets in
-// double) so the fp32 log-space values stay O(10) instead of O(loss): posteriors keep ~1e-6 relative accuracy
-// where plain fp32 log-space CTC (torch's kernel included) loses ~3e-5 on a 250-frame utterance.
-template <bool FAST>
-__global__ void ctc_kernel(const CtcParams p) {
+// One sweep (alpha: FWD, beta: !FWD) by ONE warp: lane j keeps the SPT consecutive states [j*SPT, (j+1)*SPT) of the
+// extended label sequence in registers, neighbours across lanes come by shuffle -- no shared memory, no block
+// barrier on the L-step dependent chain.  Rows are re-centred every kRenorm frames (offsets in double) and
+// streamed to the workspace for the posterior pass.
+template <bool FAST, int SPT, bool FWD>
+__device__ __forceinline__ void ctc_sweep(const CtcParams& p, const float* __restrict__ lp, const int* __restrict__ lab, int Lx, int LX, int Tn,
+                                          float* __restrict__ rows, double* __restrict__ offs, float* fin) {
+  const int lane = threadIdx.x & 31;
+  const int s0 = lane * SPT;
+  int my[SPT]; bool live[SPT], skip[SPT];
+#pragma unroll
+  for (int i = 0; i < SPT; ++i) {
+    const int s = s0 + i;
+    live[i] = s < Lx;
+    my[i] = live[i] ? lab[s] : p.blank;
+    if (FWD) skip[i] = live[i] && s >= 2 && my[i] != p.blank && my[i] != lab[s - 2];          // s-2 -> s allowed
+    else skip[i] = live[i] && (s + 2 < Lx) && lab[s + 2] != p.blank && lab[s + 2] != my[i];   // s -> s+2 allowed
+  }
+  float a[SPT], e[SPT];
+  double off = 0.0;
+  const int t0 = FWD ? 0 : Tn - 1;
+#pragma unroll
+  for (int i = 0; i < SPT; ++i) e[i] = lp[t0 * p.V + my[i]];
+  for (int k = 0; k < Tn; ++k) {
+    const int t = FWD ? k : Tn - 1 - k;
+    float v[SPT];
+    if (k == 0) {
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) {
+        const int s = s0 + i;
+        const bool init = FWD ? (s < 2) : (s >= Lx - 2);
+        v[i] = (live[i] && init) ? e[i] : -INFINITY;
+      }
+    } else {
+      // the two states beyond this lane's block, from the neighbouring lane(s)
+      float n1, n2;
+      if (FWD) {
+        n1 = __shfl_up_sync(0xffffffffu, a[SPT - 1], 1);
+        n2 = SPT >= 2 ? __shfl_up_sync(0xffffffffu, a[SPT >= 2 ? SPT - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, a[0], 2);
+        if (lane < 1) n1 = -INFINITY;
+        if (lane < (SPT >= 2 ? 1 : 2)) n2 = -INFINITY;
+      } else {
+        n1 = __shfl_down_sync(0xffffffffu, a[0], 1);
+        n2 = SPT >= 2 ? __shfl_down_sync(0xffffffffu, a[SPT >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, a[0], 2);
+        if (lane > 30) n1 = -INFINITY;
+        if (lane > (SPT >= 2 ? 30 : 29)) n2 = -INFINITY;
+      }
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) {
+        float x1, x2;
+        if (FWD) {
+          x1 = i >= 1 ? a[i >= 1 ? i - 1 : 0] : n1;
+          x2 = i >= 2 ? a[i >= 2 ? i - 2 : 0] : (i == 1 ? n1 : n2);
+        } else {
+          x1 = i + 1 < SPT ? a[i + 1 < SPT ? i + 1 : 0] : n1;
+          x2 = i + 2 < SPT ? a[i + 2 < SPT ? i + 2 : 0] : (i + 2 == SPT ? n1 : n2);
+        }
+        const float r = lse3<FAST>(a[i], x1, skip[i] ? x2 : -INFINITY);
+        v[i] = (live[i] && r != -INFINITY) ? r + e[i] : -INFINITY;
+      }
+    }
+    if (k + 1 < Tn) {                 // next frame's emissions: independent of the recurrence, issued early
+      const int tn = FWD ? t + 1 : t - 1;
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) e[i] = lp[tn * p.V + my[i]];
+    }
+    if ((k % kRenorm) == kRenorm - 1) {
+      float m = v[0];
+#pragma unroll
+      for (int i = 1; i < SPT; ++i) m = fmaxf(m, v[i]);
+      m = warp_max(m);
+      if (m != -INFINITY) {
+#pragma unroll
+        for (int i = 0; i < SPT; ++i) v[i] = (v[i] == -INFINITY) ? v[i] : v[i] - m;
+        off += (double)m;
+      }
+    }
+    float* row = rows + (long long)t * LX + s0;
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+      if (s0 + i < LX) row[i] = v[i];
+      a[i] = v[i];
+    }
+    if (lane == 0) offs[t] = off;
+  }
+  if (FWD) {        // log-likelihood = lse(alpha[Tn-1][Lx-1], alpha[Tn-1][Lx-2]) + offset
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+      if (s0 + i == Lx - 1) fin[0] = a[i];
+      if (s0 + i == Lx - 2) fin[1] = a[i];
+    }
+  }
+}
+
+// One CTA (8 warps) per trial.  Warp 0 sweeps alpha forward while warp 1 sweeps beta backward (L dependent steps,
+// not 2 L); then all warps turn alpha + beta into label posteriors, one frame per warp, and write the gradient
+// w.r.t. the logits.  The posterior of label c sums the states that carry c; the states are grouped by label once
+// per trial (a CSR index built in shared memory), so no atomics are involved and the sums are deterministic.
+// Rows are kept re-centred (alpha_hat = alpha - C_t, beta_hat = beta - D_t) so the fp32 log-space values stay O(10)
+// instead of O(loss): posteriors keep ~1e-6 relative accuracy where plain fp32 log-space CTC (torch's kernel
+// included) loses ~3e-5 on a 250-frame utterance.
+template <bool FAST, int SPT>
+__global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  const int b = blockIdx.x, tid = threadIdx.x, nwarps = blockDim.x >> 5, warp = tid >> 5, lane = tid & 31;
-  const int LX = 2 * p.S + 1, LXP = p.LXP;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int LX = 2 * p.S + 1, LXA = SPT * 32;
   double* Cs = (double*)sm_raw;                     // [L] forward offsets
   double* Ds = Cs + p.L;                            // [L] backward offsets
-  float* rowA = (float*)(Ds + p.L);                 // [2][LX + 4]  (2 -inf pads on the left)
-  float* rowB = rowA + 2 * (LX + 4);                // [2][LX + 4]  (2 -inf pads on the right)
-  float* red = rowB + 2 * (LX + 4);                 // [32]
-  float* post = red + 32;                           // [nwarps][V]
-  int* lab = (int*)(post + nwarps * p.V);           // [LX]
-  float* lp_s = (float*)(lab + LX);                 // [L*V] when it fits
+  float* wbuf = (float*)(Ds + p.L);                 // [warps][LXA] posterior weights of one frame
+  int* lab = (int*)(wbuf + kCtcWarps * LXA);        // [LXA + 2] extended labels
+  int* cstart = lab + LXA + 2;                      // [V + 1] states grouped by label: start offsets ...
+  int* cpos = cstart + p.V + 1;                     // [S]     ... and target positions
+  float* fin = (float*)(cpos + (p.S > 0 ? p.S : 1));   // [2]
+  float* lp_s = fin + 2;                            // [L*V] when it fits
   __shared__ double s_ll;
 
   int S = (int)p.tgt_len[b];
@@ -81,56 +176,39 @@ __global__ void ctc_kernel(const CtcParams p) {
   float* beta = p.beta + (long long)b * p.L * LX;
   float* dl = p.dlogits ? p.dlogits + (long long)b * p.L * p.V : nullptr;
 
-  if (p.lp_in_smem) for (int i = tid; i < p.L * p.V; i += blockDim.x) lp_s[i] = lp_g[i];
-  for (int i = tid; i < 4 * (LX + 4); i += blockDim.x) rowA[i] = -INFINITY;
-  for (int i = tid; i < LX; i += blockDim.x) lab[i] = (i < Lx && (i & 1)) ? (int)p.targets[(long long)b * p.S + (i >> 1)] : p.blank;
+  if (p.lp_in_smem) {
+    for (int i = tid; i < p.L * p.V; i += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(lp_s + i)), "l"(lp_g + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int i = tid; i < LXA + 2; i += blockDim.x) lab[i] = (i < Lx && (i & 1)) ? (int)p.targets[(long long)b * p.S + (i >> 1)] : p.blank;
+  if (tid < 2) fin[tid] = -INFINITY;
   __syncthreads();
-
-  const bool fwd = tid < LXP;                       // alpha group / beta group
-  const int s = fwd ? tid : tid - LXP;
-  const bool live = s < Lx;
-  const int my = live ? lab[s] : p.blank;
-  const bool skip_b = live && s >= 2 && my != p.blank && my != lab[s - 2];                   // alpha: s-2 -> s allowed
-  const bool skip_f = live && (s + 2 < Lx) && lab[s + 2] != p.blank && lab[s + 2] != my;     // beta:  s -> s+2 allowed
-  const int gw0 = fwd ? 0 : LXP / 32, gw1 = fwd ? LXP / 32 : nwarps;                         // this group's warps
+  // group the target positions by label (thread c owns label c; lists stay in target order -> deterministic sums)
+  if (tid < p.V) {
+    int n = 0;
+    for (int j = 0; j < S; ++j) n += (lab[2 * j + 1] == tid);
+    cstart[tid + 1] = n;
+  }
+  if (tid == 0) cstart[0] = 0;
+  __syncthreads();
+  if (tid == 0) for (int c = 0; c < p.V; ++c) cstart[c + 1] += cstart[c];
+  __syncthreads();
+  if (tid < p.V) {
+    int n = cstart[tid];
+    for (int j = 0; j < S; ++j) if (lab[2 * j + 1] == tid) cpos[n++] = j;
+  }
+  if (p.lp_in_smem) asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
 
   double ll = -INFINITY;
   if (Tn > 0) {
-    float* prev = fwd ? rowA + 2 : rowB;
-    float* cur = prev + (LX + 4);
-    double off = 0.0;
-    for (int k = 0; k < Tn; ++k) {
-      const int t = fwd ? k : Tn - 1 - k;
-      float v = -INFINITY;
-      if (live) {
-        const float e = lp[t * p.V + my];
-        if (k == 0) {
-          v = fwd ? (s < 2 ? e : -INFINITY) : (s >= Lx - 2 ? e : -INFINITY);
-        } else {
-          const float x0 = prev[s];
-          const float x1 = fwd ? prev[s - 1] : prev[s + 1];
-          const float x2 = fwd ? (skip_b ? prev[s - 2] : -INFINITY) : (skip_f ? prev[s + 2] : -INFINITY);
-          v = lse3<FAST>(x0, x1, x2);
-          v = (v == -INFINITY) ? -INFINITY : v + e;
-        }
-      }
-      if ((k % kRenorm) == kRenorm - 1) {
-        const float wm = warp_max(v);
-        if (lane == 0) red[warp] = wm;
-        __syncthreads();
-        float mx = -INFINITY;
-        for (int w = gw0; w < gw1; ++w) mx = fmaxf(mx, red[w]);
-        if (mx != -INFINITY) { v = (v == -INFINITY) ? v : v - mx; off += (double)mx; }
-      }
-      if (live) { cur[s] = v; (fwd ? alpha : beta)[(long long)t * LX + s] = v; }
-      if (s == 0) (fwd ? Cs : Ds)[t] = off;
-      __syncthreads();
-      float* tmp = prev; prev = cur; cur = tmp;
-    }
+    if (warp == 0) ctc_sweep<FAST, SPT, true>(p, lp, lab, Lx, LX, Tn, alpha, Cs, fin);
+    else if (warp == 1) ctc_sweep<FAST, SPT, false>(p, lp, lab, Lx, LX, Tn, beta, Ds, fin);
+    __syncthreads();
     if (tid == 0) {
-      float v = prev[Lx - 1];
-      if (Lx > 1) v = lse3<false>(v, prev[Lx - 2], -INFINITY);
-      s_ll = (v == -INFINITY) ? -INFINITY : off + (double)v;
+      const float v = lse3<false>(fin[0], fin[1], -INFINITY);
+      s_ll = (v == -INFINITY) ? -INFINITY : Cs[Tn - 1] + (double)v;
     }
     __syncthreads();
     ll = s_ll;
@@ -146,20 +224,32 @@ __global__ void ctc_kernel(const CtcParams p) {
   if (!feasible || Tn <= 0) return;
 
   // posteriors: one warp per frame.  dlogits[t,c] = (softmax[t,c] - sum_{s: l'(s)=c} alpha beta / (p_t(c) P)) * dloss
-  float* pw = post + warp * p.V;
-  for (int t = warp; t < Tn; t += nwarps) {
-    for (int c = lane; c < p.V; c += 32) pw[c] = 0.f;
-    __syncwarp();
+  float* wb = wbuf + warp * LXA;
+  for (int t = warp; t < Tn; t += kCtcWarps) {
     const float kt = (float)(Cs[t] + Ds[t] - ll);
-    for (int s2 = lane; s2 < Lx; s2 += 32) {
-      const float al = alpha[(long long)t * LX + s2], be = beta[(long long)t * LX + s2];
-      if (al != -INFINITY && be != -INFINITY) {
-        const int c = lab[s2];
-        atomicAdd(&pw[c], exp_t<FAST>(al + be - lp[(long long)t * p.V + c] + kt));
-      }
+    float al[SPT], be[SPT];
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+      const int s2 = lane + 32 * i;
+      al[i] = s2 < Lx ? alpha[(long long)t * LX + s2] : -INFINITY;
+      be[i] = s2 < Lx ? beta[(long long)t * LX + s2] : -INFINITY;
     }
+    float blank_acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+      const int s2 = lane + 32 * i;
+      float w = 0.f;
+      if (al[i] != -INFINITY && be[i] != -INFINITY) w = exp_t<FAST>(al[i] + be[i] - lp[t * p.V + lab[s2]] + kt);
+      wb[s2] = w;
+      if (!(s2 & 1)) blank_acc += w;
+    }
+    blank_acc = warp_sum(blank_acc);
     __syncwarp();
-    for (int c = lane; c < p.V; c += 32) dl[(long long)t * p.V + c] = (exp_t<FAST>(lp[(long long)t * p.V + c]) - pw[c]) * gs;
+    for (int c = lane; c < p.V; c += 32) {
+      float acc = (c == p.blank) ? blank_acc : 0.f;
+      for (int k = cstart[c]; k < cstart[c + 1]; ++k) acc += wb[2 * cpos[k] + 1];
+      dl[(long long)t * p.V + c] = (exp_t<FAST>(lp[t * p.V + c]) - acc) * gs;
+    }
     __syncwarp();
   }
 }
@@ -198,32 +288,48 @@ int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaS
 
 size_t k_ctc_workspace_floats(int B, int L, int S) { return 2 * (size_t)B * L * (2 * S + 1) + B; }
 
+template <bool FAST, int SPT>
+static int ctc_launch(const CtcParams& p, size_t smem, cudaStream_t stream) {
+  static size_t attr = 0;
+  if (smem > attr) {
+    NDT1_CUDA_CHECK(cudaFuncSetAttribute(ctc_kernel<FAST, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  ctc_kernel<FAST, SPT><<<p.B, kCtcWarps * 32, smem, stream>>>(p);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+template <bool FAST>
+static int ctc_dispatch(const CtcParams& p, int spt, size_t smem, cudaStream_t stream) {
+  switch (spt) {
+    case 1: return ctc_launch<FAST, 1>(p, smem, stream);
+    case 2: return ctc_launch<FAST, 2>(p, smem, stream);
+    case 4: return ctc_launch<FAST, 4>(p, smem, stream);
+    case 8: return ctc_launch<FAST, 8>(p, smem, stream);
+    default: return ctc_launch<FAST, 16>(p, smem, stream);
+  }
+}
+
 int k_ctc_fwd_bwd(const float* logp, const long long* targets, const long long* in_len, const long long* tgt_len, int B, int L, int V,
                   int S, int blank, int zero_infinity, float* alpha_ws, float* nll, float* loss, float* dlogits, const float* dloss,
                   cudaStream_t stream, int fast_math) {
   if (B == 0) return 0;
   NDT1_REQUIRE(blank >= 0 && blank < V, "ctc: blank id %d outside the vocabulary (%d)", blank, V);
+  NDT1_REQUIRE(V <= kCtcWarps * 32, "ctc: vocabulary %d larger than the CTA (%d threads)", V, kCtcWarps * 32);
   const int LX = 2 * S + 1;
-  const int LXP = ((LX + 31) / 32) * 32;
-  const int threads = 2 * LXP;
-  NDT1_REQUIRE(threads <= 1024, "ctc: target length %d too long for one CTA (max 255 labels)", S);
-  const int nwarps = threads / 32;
-  const size_t base = (size_t)2 * L * sizeof(double) + (size_t)(4 * (LX + 4) + 32 + nwarps * V + LX) * sizeof(float);
+  int spt = 1;
+  while (spt * 32 < LX) spt *= 2;
+  NDT1_REQUIRE(spt <= 16, "ctc: target length %d too long for one warp per sweep (max 255 labels)", S);
+  const int LXA = spt * 32;
+  const size_t base = (size_t)2 * L * sizeof(double) + (size_t)(kCtcWarps * LXA + (LXA + 2) + (V + 1) + (S > 0 ? S : 1) + 2) * sizeof(float);
   const size_t with_lp = base + (size_t)L * V * sizeof(float);
   const int lp_in_smem = with_lp <= 200 * 1024;
   const size_t smem = lp_in_smem ? with_lp : base;
   NDT1_REQUIRE(smem <= 200 * 1024, "ctc: %d frames x %d labels do not fit one CTA", L, S);
   float* beta_ws = alpha_ws + (size_t)B * L * LX;
-  CtcParams p{logp, targets, in_len, tgt_len, B, L, V, S, blank, zero_infinity, lp_in_smem, LXP, alpha_ws, beta_ws, nll, dlogits, dloss};
-  static size_t attr = 0;
-  if (smem > attr) {
-    NDT1_CUDA_CHECK(cudaFuncSetAttribute(ctc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NDT1_CUDA_CHECK(cudaFuncSetAttribute(ctc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
-  if (fast_math) ctc_kernel<true><<<B, threads, smem, stream>>>(p);
-  else ctc_kernel<false><<<B, threads, smem, stream>>>(p);
-  NDT1_CHECK_LAUNCH();
+  CtcParams p{logp, targets, in_len, tgt_len, B, L, V, S, blank, zero_infinity, lp_in_smem, alpha_ws, beta_ws, nll, dlogits, dloss};
+  if (fast_math) NDT1_TRY(ctc_dispatch<true>(p, spt, smem, stream));
+  else NDT1_TRY(ctc_dispatch<false>(p, spt, smem, stream));
   if (loss) {
     sum_nll_kernel<<<1, 32, 0, stream>>>(nll, B, loss);
     NDT1_CHECK_LAUNCH();

@@ -43,6 +43,7 @@ struct ndt1_engine {
   ndt1_config c;
   long long launches = 0;
   cudaEvent_t stage_ev[NDT1_MAX_LAYERS + 2] = {};   // gradient stages of the last backward, in completion order
+  int overlap = 1;              // weight gradients on a second stream, concurrent with the data-gradient chain
   int n_stages() const { return c.n_layers + 2; }
   virtual ~ndt1_engine() {}
   virtual int forward(const ndt1_tensors* P, const ndt1_batch* b, const ndt1_outputs* o, cudaStream_t s) = 0;
@@ -73,7 +74,12 @@ struct Engine : ndt1_engine {
   long long* key_valid = nullptr; long long* out_lens = nullptr;
   float* feat32 = nullptr;
   // backward scratch
-  float* dX = nullptr; T* dY = nullptr; T* dH = nullptr; T* dU = nullptr; T* dA = nullptr; T* dqkv = nullptr; T* dlog = nullptr;
+  // operands of the weight-gradient GEMMs are kept PER LAYER so that those GEMMs may trail the data-gradient chain
+  float* dX = nullptr; T* dYe = nullptr; T* dH = nullptr; T* dA = nullptr; T* dlog = nullptr;
+  std::vector<T*> dYm, dYa, dUl, dqkvl;
+  cudaStream_t wstream = nullptr;            // weight-gradient stream
+  std::vector<cudaEvent_t> fork_ev; size_t fork_used = 0;
+  cudaEvent_t join_ev = nullptr;
   T* dEmb = nullptr; T* dhn = nullptr; T* dfac = nullptr;
   float* delta = nullptr; float* ln_part = nullptr;
   int ldV = 0;
@@ -115,8 +121,12 @@ struct Engine : ndt1_engine {
     if (k.method == NDT1_METHOD_CTC) ctc_ws = ar.take<float>(k_ctc_workspace_floats(Bm, out_len(Tm), k.max_targets));
     key_valid = ar.take<long long>(Mm); out_lens = ar.take<long long>(Bm);
     feat32 = ar.take<float>(Mm * Hout);
-    dX = ar.take<float>(Mm * H); dY = ar.take<T>(Mm * H); dH = ar.take<T>(Mm * H); dU = ar.take<T>(Mm * I); dA = ar.take<T>(Mm * H);
-    dqkv = ar.take<T>(Mm * 3 * H); dlog = ar.take<T>(Mout * ldV); dEmb = ar.take<T>(MT * D); dhn = ar.take<T>(Mm * H);
+    dX = ar.take<float>(Mm * H); dYe = ar.take<T>(Mm * H); dH = ar.take<T>(Mm * H); dA = ar.take<T>(Mm * H);
+    dYm.resize(NL); dYa.resize(NL); dUl.resize(NL); dqkvl.resize(NL);
+    for (int l = 0; l < NL; ++l) {
+      dYm[l] = ar.take<T>(Mm * H); dYa[l] = ar.take<T>(Mm * H); dUl[l] = ar.take<T>(Mm * I); dqkvl[l] = ar.take<T>(Mm * 3 * H);
+    }
+    dlog = ar.take<T>(Mout * ldV); dEmb = ar.take<T>(MT * D); dhn = ar.take<T>(Mm * H);
     delta = ar.take<float>((long long)Bm * k.n_heads * Lm);
     ln_part = (float*)ar.take<char>(k_layernorm_bwd_partials_bytes(H));
     if (kBf16) {
@@ -145,11 +155,20 @@ struct Engine : ndt1_engine {
     NDT1_CUDA_CHECK(cudaMemset(ar.base, 0, ar.cap));
     carve();
     for (int i = 0; i < n_stages(); ++i) NDT1_CUDA_CHECK(cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming));
+    const char* ov = getenv("NDT1_OVERLAP");
+    overlap = !(ov && ov[0] == '0');
+    NDT1_CUDA_CHECK(cudaStreamCreateWithFlags(&wstream, cudaStreamNonBlocking));
+    fork_ev.resize(6 * c.n_layers + 12);
+    for (auto& e : fork_ev) NDT1_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    NDT1_CUDA_CHECK(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
     if (kBf16 && !force_simt) NDT1_TRY(gemm_tc_init());
     return 0;
   }
   ~Engine() override {
     for (int i = 0; i < NDT1_MAX_LAYERS + 2; ++i) if (stage_ev[i]) cudaEventDestroy(stage_ev[i]);
+    for (auto& e : fork_ev) if (e) cudaEventDestroy(e);
+    if (join_ev) cudaEventDestroy(join_ev);
+    if (wstream) cudaStreamDestroy(wstream);
     if (ar.base) cudaFree(ar.base);
   }
 
@@ -439,9 +458,23 @@ struct Engine : ndt1_engine {
     const long long M = (long long)B * L, MT = (long long)B * Tn, Mo = (long long)B * Tp;
     const float pe = training ? k.p_embed : 0.f, ptr_ = training ? k.p_transformer : 0.f;
 
+    // Weight gradients (and the bias reductions that are not fused elsewhere) go to `ws`: they only need the operand the
+    // data-gradient chain has just produced, so they run concurrently with the rest of that chain and fill the SMs its
+    // persistent kernels leave idle in their last wave.  fork() orders `ws` after everything enqueued on `s` so far.
+    cudaStream_t ws = overlap ? wstream : s;
+    fork_used = 0;
+    auto fork = [&]() -> int {
+      if (!overlap) return 0;
+      NDT1_REQUIRE(fork_used < fork_ev.size(), "engine: out of fork events");
+      cudaEvent_t e = fork_ev[fork_used++];
+      NDT1_CUDA_CHECK(cudaEventRecord(e, s));
+      NDT1_CUDA_CHECK(cudaStreamWaitEvent(ws, e, 0));
+      return 0;
+    };
     // head
     NDT1_TRY(k_scale_cast_pad<T>(dlogits, dlog, Mo, V, ldV, dloss, s));
-    if (G->dec_b) NDT1_TRY(k_colsum<T>(dlog, G->dec_b, Mo, V, ldV, s));
+    NDT1_TRY(fork());
+    if (G->dec_b) NDT1_TRY(k_colsum<T>(dlog, G->dec_b, Mo, V, ldV, ws));
     const T* head_in = k.factors_active ? fac : hn; const int head_ld = k.factors_active ? Hout : H;
     T* d_head_in = k.factors_active ? dfac : dhn;
     if (n_prefix > 0) NDT1_CUDA_CHECK(cudaMemsetAsync(d_head_in, 0, M * head_ld * sizeof(T), s));
@@ -458,7 +491,7 @@ struct Engine : ndt1_engine {
       const int kb = p.nchunk * ndt1_cdiv(p.chunk_k, 64);
       p.split_k = kb >= 32 ? 16 : 1;
       if (!(kBf16 && !force_simt) && p.split_k > 8) p.split_k = 8;
-      NDT1_TRY(run(p, s));
+      NDT1_TRY(run(p, ws));
     }
     {
       GemmProblem p = prob(GEMM_NN, Tp, Hout, V);
@@ -475,8 +508,9 @@ struct Engine : ndt1_engine {
       NDT1_TRY(run(p, s));
     }
     if (k.factors_active) {
-      if (G->factors_b && k.factors_bias) NDT1_TRY(k_colsum<T>(dfac, G->factors_b, M, Hout, Hout, s));
-      NDT1_TRY(linear_wgrad(dfac, Hout, hn, H, G->factors_w, H, (int)M, Hout, H, s));
+      NDT1_TRY(fork());
+      if (G->factors_b && k.factors_bias) NDT1_TRY(k_colsum<T>(dfac, G->factors_b, M, Hout, Hout, ws));
+      NDT1_TRY(linear_wgrad(dfac, Hout, hn, H, G->factors_w, H, (int)M, Hout, H, ws));
       GemmEpilogue e = gemm_epilogue_default();
       e.out = dhn; e.out_bf16 = kBf16; e.ldc = H;
       NDT1_TRY(linear_dgrad(dfac, Hout, W(P->factors_w, w_fac), H, (int)M, Hout, H, e, s));
@@ -484,14 +518,16 @@ struct Engine : ndt1_engine {
     // out_norm
     NDT1_CUDA_CHECK(cudaMemsetAsync(dX, 0, M * H * sizeof(float), s));
     // every LayerNorm backward also emits the column sums of the operand it hands to the next GEMM pair = that layer's bias gradient
-    NDT1_TRY(k_layernorm_bwd<T>(dhn, xs[2 * NL], P->out_norm_w, mean[2 * NL], rstd[2 * NL], dX, G->out_norm_w, G->out_norm_b, dY, ptr_, seed,
+    NDT1_TRY(k_layernorm_bwd<T>(dhn, xs[2 * NL], P->out_norm_w, mean[2 * NL], rstd[2 * NL], dX, G->out_norm_w, G->out_norm_b, dYm[NL - 1], ptr_, seed,
                                 site_mlp(NL - 1), M, H, ln_part, s, k.mlp_bias ? G->layer[NL - 1].down_b : nullptr));
-    NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[0], s));   // decoder + out_norm gradients complete
+    NDT1_TRY(fork());
+    NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[0], ws));   // decoder + out_norm gradients complete
     int cf, cb; ctx(cf, cb);
     for (int l = NL - 1; l >= 0; --l) {
       const auto& q = P->layer[l]; const auto& gq = G->layer[l];
       // MLP: x_out = x_mid + drop(down(act(up(h2))))      dY = T(dX * mlp mask)
-      NDT1_TRY(linear_wgrad(dY, H, g[l], I, gq.down_w, I, (int)M, H, I, s));
+      T* dY = dYm[l]; T* dU = dUl[l]; T* dqkv = dqkvl[l];
+      NDT1_TRY(linear_wgrad(dY, H, g[l], I, gq.down_w, I, (int)M, H, I, ws));      // (ws is already ordered after the LayerNorm backward that wrote dY)
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = dU; e.out_bf16 = kBf16; e.ldc = I;
@@ -501,19 +537,22 @@ struct Engine : ndt1_engine {
         const bool fuse_cs = kBf16 && !force_simt && gq.up_b && k.mlp_bias && I % 8 == 0;
         if (fuse_cs) e.colsum = gq.up_b;
         NDT1_TRY(linear_dgrad(dY, H, W(q.down_w, kBf16 ? w_down[l] : nullptr), I, (int)M, H, I, e, s));
-        if (!fuse_cs && gq.up_b && k.mlp_bias) NDT1_TRY(k_colsum<T>(dU, gq.up_b, M, I, I, s));
+        NDT1_TRY(fork());
+        if (!fuse_cs && gq.up_b && k.mlp_bias) NDT1_TRY(k_colsum<T>(dU, gq.up_b, M, I, I, ws));
       }
-      NDT1_TRY(linear_wgrad(dU, I, h2[l], H, gq.up_w, H, (int)M, I, H, s));
+      NDT1_TRY(linear_wgrad(dU, I, h2[l], H, gq.up_w, H, (int)M, I, H, ws));
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = dH; e.out_bf16 = kBf16; e.ldc = H;
         NDT1_TRY(linear_dgrad(dU, I, W(q.up_w, kBf16 ? w_up[l] : nullptr), H, (int)M, I, H, e, s));
       }
-      NDT1_TRY(k_layernorm_bwd<T>(dH, xs[2 * l + 1], q.ln2_w, mean[2 * l + 1], rstd[2 * l + 1], dX, gq.ln2_w, gq.ln2_b, dY, 0.f, seed, 0, M, H,
+      NDT1_TRY(k_layernorm_bwd<T>(dH, xs[2 * l + 1], q.ln2_w, mean[2 * l + 1], rstd[2 * l + 1], dX, gq.ln2_w, gq.ln2_b, dYa[l], 0.f, seed, 0, M, H,
                                   ln_part, s, k.attention_bias ? gq.o_b : nullptr));
+      dY = dYa[l];
+      NDT1_TRY(fork());
       // attention block: x_mid = x_in + out_proj(drop(att))      dY = T(dX)
       const T* ad = (ptr_ > 0.f) ? attd[l] : att[l];
-      NDT1_TRY(linear_wgrad(dY, H, ad, H, gq.o_w, H, (int)M, H, H, s));
+      NDT1_TRY(linear_wgrad(dY, H, ad, H, gq.o_w, H, (int)M, H, H, ws));
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = dA; e.out_bf16 = kBf16; e.ldc = H;
@@ -528,39 +567,42 @@ struct Engine : ndt1_engine {
       ap.dout = dA; ap.dqkv = dqkv; ap.delta = delta; ap.drop_bits = dropbits[l];
       if (kBf16 && !force_simt && !simt_attention && k_attention_tc_supported(ap)) NDT1_TRY(k_attention_tc_bwd(ap, s));
       else NDT1_TRY(k_attention_bwd<T>(ap, s));
+      NDT1_TRY(fork());
       float* gw[3] = {gq.q_w, gq.k_w, gq.v_w}; float* gb[3] = {gq.q_b, gq.k_b, gq.v_b};
       // flat gradient arena: q|k|v weights (and biases) adjacent -> one (3H x H) weight gradient, one bias reduction
       if (gb[0] && gb[1] == gb[0] + H && gb[2] == gb[1] + H && k.attention_bias) {
-        NDT1_TRY(k_colsum<T>(dqkv, gb[0], M, 3 * H, 3 * H, s));
+        NDT1_TRY(k_colsum<T>(dqkv, gb[0], M, 3 * H, 3 * H, ws));
       } else {
         for (int j = 0; j < 3; ++j)
-          if (gb[j] && k.attention_bias) NDT1_TRY(k_colsum<T>(dqkv + (long long)j * H, gb[j], M, H, 3 * H, s));
+          if (gb[j] && k.attention_bias) NDT1_TRY(k_colsum<T>(dqkv + (long long)j * H, gb[j], M, H, 3 * H, ws));
       }
       if (gw[0] && gw[1] == gw[0] + (long long)H * H && gw[2] == gw[1] + (long long)H * H) {
-        NDT1_TRY(linear_wgrad(dqkv, 3 * H, h1[l], H, gw[0], H, (int)M, 3 * H, H, s));
+        NDT1_TRY(linear_wgrad(dqkv, 3 * H, h1[l], H, gw[0], H, (int)M, 3 * H, H, ws));
       } else {
-        for (int j = 0; j < 3; ++j) NDT1_TRY(linear_wgrad(dqkv + (long long)j * H, 3 * H, h1[l], H, gw[j], H, (int)M, H, H, s));
+        for (int j = 0; j < 3; ++j) NDT1_TRY(linear_wgrad(dqkv + (long long)j * H, 3 * H, h1[l], H, gw[j], H, (int)M, H, H, ws));
       }
       if (kBf16) {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = dH; e.out_bf16 = 1; e.ldc = H;
         NDT1_TRY(linear_dgrad(dqkv, 3 * H, w_qkv[l], H, (int)M, 3 * H, H, e, s));
       } else {
-        const float* ws[3] = {q.q_w, q.k_w, q.v_w};
+        const float* wq[3] = {q.q_w, q.k_w, q.v_w};
         for (int j = 0; j < 3; ++j) {
           GemmEpilogue e = gemm_epilogue_default();
           e.out = dH; e.out_bf16 = 0; e.ldc = H; e.accumulate = j > 0;
-          NDT1_TRY(linear_dgrad(dqkv + (long long)j * H, 3 * H, ws[j], H, (int)M, H, H, e, s));
+          NDT1_TRY(linear_dgrad(dqkv + (long long)j * H, 3 * H, wq[j], H, (int)M, H, H, e, s));
         }
       }
       const bool first = (l == 0);
-      NDT1_TRY(k_layernorm_bwd<T>(dH, xs[2 * l], q.ln1_w, mean[2 * l], rstd[2 * l], dX, gq.ln1_w, gq.ln1_b, first ? (T*)nullptr : dY,
+      NDT1_TRY(k_layernorm_bwd<T>(dH, xs[2 * l], q.ln1_w, mean[2 * l], rstd[2 * l], dX, gq.ln1_w, gq.ln1_b, first ? (T*)nullptr : dYm[first ? 0 : l - 1],
                                   first ? 0.f : ptr_, seed, first ? 0 : site_mlp(l - 1), M, H, ln_part, s,
                                   (!first && k.mlp_bias) ? G->layer[l - 1].down_b : nullptr));
-      NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[NL - l], s));   // layer l gradients complete
+      NDT1_TRY(fork());                                          // also orders ws after this LayerNorm (its affine gradients, next dY)
+      NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[NL - l], ws));   // layer l gradients complete
     }
     // embedding: dX is the gradient w.r.t. the (dropped) embedding output.
     // One pass: apply the embedding dropout mask, cast for the GEMMs, scatter into the position table.
+    T* dY = dYe;
     NDT1_TRY(k_grad_prep<T>(dX, dY, M, H, pe, seed, 0, (k.pos && G->pos_w) ? G->pos_w : nullptr, ts_ptr, H, L, Tn, n_prefix, s));
     if (n_prefix > 0) {
       int slot = 0;
@@ -568,7 +610,8 @@ struct Engine : ndt1_engine {
       if (k.block_token) { if (G->block_emb) NDT1_TRY(k_token_rows_grad<T>(G->block_emb, block_ptr, dY, B, L, H, slot, s)); ++slot; }
       NDT1_CUDA_CHECK(cudaMemset2DAsync(dY, (size_t)L * H * sizeof(T), 0, (size_t)n_prefix * H * sizeof(T), B, s));
     }
-    if (G->proj_b) NDT1_TRY(k_colsum<T>(dY, G->proj_b, M, H, H, s));
+    NDT1_TRY(fork());
+    if (G->proj_b) NDT1_TRY(k_colsum<T>(dY, G->proj_b, M, H, H, ws));
     const T* dE = dY + (long long)n_prefix * H;
     const int eact = k.embed_act;
     // (not in the stacked layout: there one output row of the overlap-add GEMM holds `stride` bins)
@@ -583,7 +626,7 @@ struct Engine : ndt1_engine {
         p.B = op(emb, (long long)Tn * D, B, R4, K4, K4);
         p.epi.out = G->proj_w; p.epi.ldc = nch * K4; p.epi.accumulate = 1;
         p.split_k = (B >= 8 && kBf16 && !force_simt) ? 2 : 1;
-        NDT1_TRY(run(p, s));
+        NDT1_TRY(run(p, ws));
       }
       if (Tn % k.stack_stride != 0) NDT1_CUDA_CHECK(cudaMemsetAsync(dEmb, 0, MT * D * sizeof(T), s));
       GemmProblem p = prob(GEMM_NN, R4, K4, H);
@@ -601,7 +644,7 @@ struct Engine : ndt1_engine {
         p.A = op(dE, (long long)L * H, B, Tp, H, H);
         p.B = op(emb, (long long)Tn * D, B, Tn, D, D);
         p.epi.out = G->proj_w; p.epi.ldc = D; p.epi.accumulate = 1;
-        NDT1_TRY(run(p, s));
+        NDT1_TRY(run(p, ws));
       }
       GemmProblem p = prob(GEMM_NN, Tp, D, H);
       p.nb_out = B;
@@ -612,7 +655,8 @@ struct Engine : ndt1_engine {
       if (fuse_embed_cs) p.epi.colsum = G->embed_b;
       NDT1_TRY(run(p, s));
     }
-    if (!fuse_embed_cs && G->embed_b && k.embed_bias) NDT1_TRY(k_colsum<T>(dEmb, G->embed_b, MT, D, D, s));
+    NDT1_TRY(fork());
+    if (!fuse_embed_cs && G->embed_b && k.embed_bias) NDT1_TRY(k_colsum<T>(dEmb, G->embed_b, MT, D, D, ws));
     if (G->embed_w) {
       const T* x_in = kBf16 ? xin : (const T*)spikes_ptr;
       const int ldx = kBf16 ? ldN : N;
@@ -623,9 +667,13 @@ struct Engine : ndt1_engine {
       int split = kb / 8; if (split > 64) split = 64; if (split < 1) split = 1;
       if (!(kBf16 && !force_simt) && split > 8) split = 8;
       p.split_k = split;
-      NDT1_TRY(run(p, s));
+      NDT1_TRY(run(p, ws));
     }
-    NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[NL + 1], s));     // embedding gradients complete
+    NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[NL + 1], ws));     // embedding gradients complete
+    if (overlap) {                                               // join: the caller's stream sees the whole backward
+      NDT1_CUDA_CHECK(cudaEventRecord(join_ev, ws));
+      NDT1_CUDA_CHECK(cudaStreamWaitEvent(s, join_ev, 0));
+    }
     launches += g_ndt1_launches - launches0;
     return 0;
   }
@@ -669,6 +717,11 @@ int ndt1_engine_backward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_
   return e->backward(params, grads, dloss, (cudaStream_t)stream);
 }
 int64_t ndt1_engine_launch_count(const ndt1_engine* e) { return e->launches; }
+int ndt1_engine_set_overlap(ndt1_engine* e, int on) {
+  NDT1_REQUIRE(e, "engine_set_overlap: null engine");
+  e->overlap = on != 0;
+  return 0;
+}
 int ndt1_engine_stage_count(const ndt1_engine* e) { return e->n_stages(); }
 int ndt1_engine_wait_stage(ndt1_engine* e, int stage, void* stream) {
   NDT1_REQUIRE(e && stage >= 0 && stage < e->n_stages(), "engine_wait_stage: stage %d out of range", stage);

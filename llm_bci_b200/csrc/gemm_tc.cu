@@ -57,25 +57,21 @@ __device__ __forceinline__ float4 unpack4_bf16(uint2 r) {
 // GELU(erf) and its derivative for the tensor-core (bf16) mode: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7,
 // far below bf16 resolution) on the MUFU pipe (one ex2, one rcp) instead of erff/expf -- the epilogue of the MLP
 // GEMMs is ALU-bound otherwise.  The strict fp32 mode (gemm_simt.cu) keeps erff.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void gelu_parts(float v, float& cdf, float& e) {
   const float z = fabsf(v) * 0.70710678118654752f;
-  e = __expf(-z * z);                                   // exp(-v^2 / 2)
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  e = ex2_approx(z * z * -1.4426950408889634f);         // exp(-v^2 / 2)
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float q = fmaf(1.061405429f, t, -1.453152027f);
   q = fmaf(q, t, 1.421413741f);
   q = fmaf(q, t, -0.284496736f);
   q = fmaf(q, t, 0.254829592f);
-  const float erf_abs = fmaf(-q * t, e, 1.0f);
-  cdf = 0.5f * (1.0f + copysignf(erf_abs, v));
+  const float half_erf = fmaf(-0.5f * q * t, e, 0.5f);  // erf(|v|/sqrt2) / 2
+  cdf = 0.5f + copysignf(half_erf, v);
 }
-__device__ __forceinline__ float act_fast(int act, float v) {
-  if (act == ACT_GELU) { float cdf, e; gelu_parts(v, cdf, e); return v * cdf; }
-  return act_apply(act, v);
-}
-__device__ __forceinline__ float dact_fast(int dact, float saved) {
-  if (dact == DACT_GELU_FROM_IN) { float cdf, e; gelu_parts(saved, cdf, e); return fmaf(saved * 0.3989422804014327f, e, cdf); }
-  return dact_apply(dact, saved);
-}
+__device__ __forceinline__ float gelu_fast(float v) { float cdf, e; gelu_parts(v, cdf, e); return v * cdf; }
+__device__ __forceinline__ float dgelu_fast(float x) { float cdf, e; gelu_parts(x, cdf, e); return fmaf(x * 0.3989422804014327f, e, cdf); }
 
 // ---------------------------------------------------------------------------
 // Epilogue.  tcgen05.ld hands every lane one ROW of the accumulator; storing that
@@ -128,17 +124,16 @@ __device__ __forceinline__ void side_load(const GemmEpilogue& e, const EpiCtx& c
 }
 
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiCtx& cx, const TcParams& p, const ChunkAt& at, int lane,
-                                               const float4* acc, const float4* side) {
+                                               const float4* acc, const float4* side, const uint8_t* stg) {
   if (!at.live) return;
   if (!cx.vec_ok) {        // ragged shapes (the 41-column head): element-wise, still row-contiguous across lanes
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
+#pragma unroll 1           // ONE copy of the scalar epilogue (it carries every feature): code size, not speed, matters here
+    for (int ij = 0; ij < 32; ++ij) {
+      const int i = ij >> 2, j = ij & 3;
       const int r = at.r0 + (lane >> 3) + 4 * i;
-      if (r >= p.M) continue;
-      const float a[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (at.n + j < p.N) gemm_epilogue_store(e, p.N, p.M, a[j], at.bt, r, at.n + j);
+      const int rr = (lane >> 3) + 4 * i;              // re-read from the staging tile: no dynamically indexed register array
+      const float a = ((const float*)(stg + rr * 128 + ((((lane & 7) ^ rr) & 7) << 4)))[j];
+      if (r < p.M && at.n + j < p.N) gemm_epilogue_store(e, p.N, p.M, a, at.bt, r, at.n + j);
     }
     return;
   }
@@ -167,12 +162,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
         else *(float4*)((float*)e.out2 + idx(i)) = v[i];
       }
   }
-  if (e.act != ACT_NONE) {
+  if (e.act == ACT_GELU) {          // (the activation switch is hoisted out of the element loops: smaller, branch-free code)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i].x = gelu_fast(v[i].x); v[i].y = gelu_fast(v[i].y); v[i].z = gelu_fast(v[i].z); v[i].w = gelu_fast(v[i].w); }
+  } else if (e.act == ACT_SOFTSIGN) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      v[i].x = act_fast(e.act, v[i].x); v[i].y = act_fast(e.act, v[i].y);
-      v[i].z = act_fast(e.act, v[i].z); v[i].w = act_fast(e.act, v[i].w);
+      v[i].x *= rcp_approx(1.0f + fabsf(v[i].x)); v[i].y *= rcp_approx(1.0f + fabsf(v[i].y));
+      v[i].z *= rcp_approx(1.0f + fabsf(v[i].z)); v[i].w *= rcp_approx(1.0f + fabsf(v[i].w));
     }
+  } else if (e.act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
   }
   if (e.gather_tab) {
 #pragma unroll
@@ -211,6 +212,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
     }
   }
   if (e.dact != DACT_NONE) {
+    float4 sv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -220,8 +222,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
         s = e.dact_in_bf16 ? unpack4_bf16(__ldg((const uint2*)((const bf16*)e.dact_in + idx(i))))
                            : __ldg((const float4*)((const float*)e.dact_in + idx(i)));
       }
-      v[i].x *= dact_fast(e.dact, s.x); v[i].y *= dact_fast(e.dact, s.y);
-      v[i].z *= dact_fast(e.dact, s.z); v[i].w *= dact_fast(e.dact, s.w);
+      sv[i] = s;
+    }
+    if (e.dact == DACT_GELU_FROM_IN) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i].x *= dgelu_fast(sv[i].x); v[i].y *= dgelu_fast(sv[i].y); v[i].z *= dgelu_fast(sv[i].z); v[i].w *= dgelu_fast(sv[i].w);
+      }
+    } else if (e.dact == DACT_SOFTSIGN_FROM_OUT) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t;
+        t = 1.0f - fabsf(sv[i].x); v[i].x *= t * t; t = 1.0f - fabsf(sv[i].y); v[i].y *= t * t;
+        t = 1.0f - fabsf(sv[i].z); v[i].z *= t * t; t = 1.0f - fabsf(sv[i].w); v[i].w *= t * t;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i].x = sv[i].x > 0.f ? v[i].x : 0.f; v[i].y = sv[i].y > 0.f ? v[i].y : 0.f;
+        v[i].z = sv[i].z > 0.f ? v[i].z : 0.f; v[i].w = sv[i].w > 0.f ? v[i].w : 0.f;
+      }
     }
   }
   if (e.resid) {           // always the prefetched side input when present
@@ -252,20 +272,80 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
 #undef ok
 }
 
+
+// ---------------------------------------------------------------------------
+// CTA-pair (cta_group::2) helpers.  Two CTAs of a cluster (the two SMs of a TPC) issue ONE 256 x BN MMA: each holds
+// its 128 rows of A and its half of B's columns in its own shared memory and its 128 accumulator rows in its own
+// tensor memory.  Only the leader (cluster rank 0) issues tcgen05.mma; barriers that the leader waits on live in the
+// leader's shared memory and are signalled remotely (TMA complete_tx of the peer's loads, the peer's epilogue arrive).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p`'s counterpart in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <int CTAS>
+__device__ __forceinline__ void tma_load_3d_g(void* dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1, int c2) {
+  if (CTAS == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  }
+}
+template <int CTAS>
+__device__ __forceinline__ void tc_mma_bf16_g(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (CTAS == 1) {
+    tc_mma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// MMA-completion arrive on the barrier at the same offset in every CTA of the pair
+template <int CTAS>
+__device__ __forceinline__ void tc_commit_g(uint64_t* bar) {
+  if (CTAS == 1) {
+    tc_commit(bar);
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------
-template <int BN, int MODE>
+template <int BN, int MODE, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)   // 10 warps: 3 share one SM sub-partition -> 168 registers per thread
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  constexpr int BNL = BN / CTAS;                       // columns of B held by this CTA
   constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
-  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int B_BYTES = BNL * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGES = kSmemPipe / STAGE_BYTES;
   constexpr bool A_MN = (MODE == GEMM_TN);
   constexpr bool B_MN = (MODE != GEMM_NT);
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr int NCH = BN / 64;                         // 32-column chunks per epilogue warp
 
@@ -280,20 +360,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;     // 0 = leader (issues the MMAs)
+  const int unit = blockIdx.x / CTAS;                          // persistent work unit: a CTA (CTAS = 1) or a CTA pair
+  const int n_units = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();            // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -303,12 +392,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < p.total_tiles; tile += n_units) {
         const int nt = tile % p.n_tiles;
         const int rest = tile / p.n_tiles;
         const int mt = rest % p.m_tiles;
         const int bz = rest / p.m_tiles;          // trial (NT/NN) or split index (TN)
-        const int m0 = mt * BM, n0 = nt * BN;
+        const int m0 = mt * (BM * CTAS) + rank * BM, n0 = nt * BN + rank * BNL;     // this CTA's rows of A / columns of B
         int kb0 = 0, kb1 = total_kb;
         if (MODE == GEMM_TN && p.split_k > 1) {
           const int per = (total_kb + p.split_k - 1) / p.split_k;
@@ -320,25 +409,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          // the pair's loads all complete on the LEADER's barrier (the leader's MMA thread is the only consumer)
+          const uint32_t fb = CTAS == 2 ? mapa_u32(&full_bar[stage], 0) : smem_u32(&full_bar[stage]);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], STAGE_BYTES * CTAS);
           if (MODE == GEMM_TN) {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i)
-              tma_load_3d(sa + i * (64 * BK * 2), &map_a, &full_bar[stage], m0 + 64 * i, kk + p.a_row_shift, j);
+              tma_load_3d_g<CTAS>(sa + i * (64 * BK * 2), &map_a, fb, m0 + 64 * i, kk + p.a_row_shift, j);
             const int cn = n0 / p.b_chunk_n;
             const int nc0 = n0 - cn * p.b_chunk_n;
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_3d(sb + i * (64 * BK * 2), &map_b, &full_bar[stage], nc0 + 64 * i, kk + cn * p.b_row_shift, j);
+            for (int i = 0; i < BNL / 64; ++i)
+              tma_load_3d_g<CTAS>(sb + i * (64 * BK * 2), &map_b, fb, nc0 + 64 * i, kk + cn * p.b_row_shift, j);
           } else {
-            tma_load_3d(sa, &map_a, &full_bar[stage], j * p.a_col_shift + kk, m0 + j * p.a_row_shift, bz);
+            tma_load_3d_g<CTAS>(sa, &map_a, fb, j * p.a_col_shift + kk, m0 + j * p.a_row_shift, bz);
             if (MODE == GEMM_NT) {
-              tma_load_3d(sb, &map_b, &full_bar[stage], j * p.b_col_shift + kk, n0 + j * p.b_row_shift, 0);
+              tma_load_3d_g<CTAS>(sb, &map_b, fb, j * p.b_col_shift + kk, n0 + j * p.b_row_shift, 0);
             } else {
 #pragma unroll
-              for (int i = 0; i < BN / 64; ++i)
-                tma_load_3d(sb + i * (64 * BK * 2), &map_b, &full_bar[stage], n0 + 64 * i + j * p.b_col_shift,
-                            kk + j * p.b_row_shift, 0);
+              for (int i = 0; i < BNL / 64; ++i)
+                tma_load_3d_g<CTAS>(sb + i * (64 * BK * 2), &map_b, fb, n0 + 64 * i + j * p.b_col_shift,
+                                    kk + j * p.b_row_shift, 0);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -346,11 +437,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc_stage = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < p.total_tiles; tile += n_units) {
         int kb0 = 0, kb1 = total_kb;
         if (MODE == GEMM_TN && p.split_k > 1) {
           const int bz = (tile / p.n_tiles) / p.m_tiles;
@@ -371,12 +462,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                         : make_sdesc(sa + k * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? make_sdesc(sb + k * (16 * 128), 64 * BK * 2, 1024)
                                         : make_sdesc(sb + k * 32, 16, 1024);
-            tc_mma_bf16(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16_g<CTAS>(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);           // frees the smem slot when the MMAs retire
+          tc_commit_g<CTAS>(&empty_bar[stage]);     // frees the smem slot (in both CTAs) when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc_stage]);         // accumulator ready for the epilogue
+        tc_commit_g<CTAS>(&tfull_bar[acc_stage]);   // accumulator ready for the epilogue warps (of both CTAs)
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
@@ -402,7 +493,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int mt = rest % p.m_tiles;
       const int bz = rest / p.m_tiles;
       at.bt = (MODE == GEMM_TN) ? 0 : bz;
-      at.r0 = mt * BM + q * 32;
+      at.r0 = mt * (BM * CTAS) + rank * BM + q * 32;
       at.n = nt * BN + half * (BN / 2) + c * 32 + (lane & 7) * 4;
       if (MODE == GEMM_TN && p.split_k > 1) {
         const int per = (total_kb + p.split_k - 1) / p.split_k;
@@ -414,25 +505,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float4 side_cur[8], side_nxt[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) side_cur[i] = side_nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    side_load(e, cx, p, locate(blockIdx.x, 0), lane, side_cur);
+    side_load(e, cx, p, locate(unit, 0), lane, side_cur);
+    const uint32_t tempty_addr0 = CTAS == 2 ? mapa_u32(&tempty_bar[0], 0) : 0u;   // the leader's accumulator-free barriers
 
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < p.total_tiles; tile += n_units) {
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * BN + half * (BN / 2));
-#pragma unroll
+#pragma unroll 1                                   // one copy of the epilogue code: it must stay inside the instruction cache
       for (int c = 0; c < NCH; ++c) {
         const ChunkAt at = locate(tile, c);
         uint32_t raw[32];
         tmem_ld32(taddr_row + c * 32, raw);
         // side input of the next chunk (or of the next tile's first chunk) while the TMEM load is in flight
-        const ChunkAt nx = (c + 1 < NCH) ? locate(tile, c + 1) : locate(tile + gridDim.x, 0);
+        const ChunkAt nx = (c + 1 < NCH) ? locate(tile, c + 1) : locate(tile + n_units, 0);
         side_load(e, cx, p, nx, lane, side_nxt);
         tmem_ld_wait();
         if (c == NCH - 1) {                         // accumulator fully read: hand the TMEM stage back before the stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc_stage]);
+          if (lane == 0) {
+            if (CTAS == 1) mbar_arrive(&tempty_bar[acc_stage]);
+            else mbar_arrive_cluster(tempty_addr0 + acc_stage * 8);
+          }
         }
         // transpose through the swizzled staging tile: lane = row -> lane = (row group, 4-column group)
 #pragma unroll
@@ -449,7 +544,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           acc[i] = *(const float4*)(stg + rr * 128 + ((((lane & 7) ^ rr) & 7) << 4));
         }
         __syncwarp();
-        epilogue_chunk(e, cx, p, at, lane, acc, side_cur);
+        epilogue_chunk(e, cx, p, at, lane, acc, side_cur, stg);
 #pragma unroll
         for (int i = 0; i < 8; ++i) side_cur[i] = side_nxt[i];
       }
@@ -459,9 +554,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();            // nobody leaves (or frees tensor memory) while the peer may still signal it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CTAS == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -520,18 +617,19 @@ int make_map(const GemmOperand& o, int box_cols, int box_rows, CUtensorMap* out)
   return 0;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int CTAS>
 int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
-  constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;
+  constexpr int STAGE_BYTES = BM * BK * 2 + (BN / CTAS) * BK * 2;
   constexpr int STAGES = kSmemPipe / STAGE_BYTES;
   constexpr int SMEM = STAGES * STAGE_BYTES + kEpiWarps * kStageTile + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
   static_assert(SMEM <= 227 * 1024, "gemm_tc: shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    NDT1_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    NDT1_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  const int grid = tp.total_tiles < g_num_sms ? tp.total_tiles : g_num_sms;
+  const int units = g_num_sms / CTAS;
+  const int grid = CTAS * (tp.total_tiles < units ? tp.total_tiles : units);
   ProfRec* rec = nullptr;
   if (g_prof_on) {
     if (g_prof_used == g_prof.size()) {
@@ -543,17 +641,27 @@ int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp
     rec->flops = 2.0 * tp.M * (double)tp.N * (double)tp.nchunk * tp.chunk_k_valid * (tp.mode == GEMM_TN ? 1 : tp.nb_out);
     NDT1_CUDA_CHECK(cudaEventRecord(rec->e0, stream));
   }
-  gemm_tc_kernel<BN, MODE><<<grid, kThreads, SMEM, stream>>>(ma, mb, tp);
+  if (CTAS == 1) {
+    gemm_tc_kernel<BN, MODE, CTAS><<<grid, kThreads, SMEM, stream>>>(ma, mb, tp);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = SMEM; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    NDT1_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, CTAS>, ma, mb, tp));
+  }
   NDT1_CHECK_LAUNCH();
   if (rec) NDT1_CUDA_CHECK(cudaEventRecord(rec->e1, stream));
   return 0;
 }
 
 template <int MODE>
-int launch_mode(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
-  if (bn == 256) return launch_inst<256, MODE>(ma, mb, tp, stream);
-  if (bn == 128) return launch_inst<128, MODE>(ma, mb, tp, stream);
-  return launch_inst<64, MODE>(ma, mb, tp, stream);
+int launch_mode(int bn, int ctas, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
+  if (bn == 256) return ctas == 2 ? launch_inst<256, MODE, 2>(ma, mb, tp, stream) : launch_inst<256, MODE, 1>(ma, mb, tp, stream);
+  if (bn == 128) return launch_inst<128, MODE, 1>(ma, mb, tp, stream);
+  return launch_inst<64, MODE, 1>(ma, mb, tp, stream);
 }
 
 }  // namespace
@@ -581,7 +689,7 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   NDT1_TRY(gemm_tc_init());
   NDT1_REQUIRE(p.M > 0 && p.N > 0 && p.nb_out > 0 && p.nchunk > 0 && p.chunk_k > 0, "gemm_tc: empty problem");
   NDT1_REQUIRE(p.nchunk == 1 || p.mode == GEMM_TN || p.chunk_k % BK == 0, "gemm_tc: chunk_k=%d must be a multiple of %d", p.chunk_k, BK);
-  NDT1_REQUIRE(p.split_k <= 1 || (p.mode == GEMM_TN && p.epi.accumulate), "gemm_tc: split_k only for accumulating GEMM_TN");
+  NDT1_REQUIRE(p.split_k <= 1 || (p.mode == GEMM_TN && p.epi.accumulate), "gemm_tc: split_k only for accumulating GEMM_TN (0 = automatic)");
   if (p.mode == GEMM_TN) {
     NDT1_REQUIRE(p.chunk_k % BK == 0 || p.A.rows <= p.chunk_k + p.a_row_shift,
                  "gemm_tc: GEMM_TN reduction rows must be bounded by the A operand (rows=%d chunk_k=%d)", p.A.rows, p.chunk_k);
@@ -595,14 +703,30 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   if (p.mode == GEMM_TN && p.b_chunk_n % bn != 0) bn = (p.b_chunk_n % 128 == 0) ? 128 : 64;
   NDT1_REQUIRE(p.mode != GEMM_TN || p.b_chunk_n % bn == 0 || p.b_chunk_n >= p.N, "gemm_tc: b_chunk_n=%d incompatible with tile", p.b_chunk_n);
 
+  // CTA pairs (256 x 256 tiles, cta_group::2) whenever the tile is the full 256 columns: half the shared-memory
+  // traffic per SM (each SM stages 128 of the 256 columns of B), which is what bounds the single-CTA main loop
+  static const int force_ctas = getenv("NDT1_GEMM_CTAS") ? atoi(getenv("NDT1_GEMM_CTAS")) : 0;
+  int ctas = (bn == 256 && p.M > BM) ? 2 : 1;
+  if (force_ctas == 1) ctas = 1;
+  const int bm = BM * ctas;
+  const int units = g_num_sms / ctas;
+
   TcParams tp;
   tp.mode = p.mode; tp.M = p.M; tp.N = p.N; tp.nb_out = p.nb_out;
   tp.nchunk = p.nchunk; tp.kb_per_chunk = ndt1_cdiv(p.chunk_k, BK); tp.chunk_k_valid = p.chunk_k;
   tp.a_row_shift = p.a_row_shift; tp.a_col_shift = p.a_col_shift;
   tp.b_row_shift = p.b_row_shift; tp.b_col_shift = p.b_col_shift;
   tp.b_chunk_n = p.b_chunk_n > 0 ? p.b_chunk_n : p.N;
+  tp.m_tiles = ndt1_cdiv(p.M, bm); tp.n_tiles = ndt1_cdiv(p.N, bn);
   tp.split_k = p.split_k > 1 ? p.split_k : 1;
-  tp.m_tiles = ndt1_cdiv(p.M, BM); tp.n_tiles = ndt1_cdiv(p.N, bn);
+  if (p.mode == GEMM_TN && p.split_k == 0 && p.epi.accumulate) {
+    // automatic split of the reduction: every split adds a full fp32 red.add pass over the output (the L2 atomics are
+    // what bounds these kernels), so take the largest split that still fits ONE wave of work units
+    const int tiles = tp.m_tiles * tp.n_tiles, kblocks = tp.nchunk * tp.kb_per_chunk;
+    int sp = units / (tiles > 0 ? tiles : 1);
+    while (sp > 1 && sp * 4 > kblocks) --sp;
+    tp.split_k = sp < 1 ? 1 : sp;
+  }
   tp.total_tiles = tp.m_tiles * tp.n_tiles * (p.mode == GEMM_TN ? tp.split_k : p.nb_out);
   tp.epi = p.epi;
 
@@ -610,15 +734,15 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   if (p.mode == GEMM_TN) {
     NDT1_TRY(make_map(p.A, 64, BK, &ma));
     NDT1_TRY(make_map(p.B, 64, BK, &mb));
-    return launch_mode<GEMM_TN>(bn, ma, mb, tp, stream);
+    return launch_mode<GEMM_TN>(bn, ctas, ma, mb, tp, stream);
   } else if (p.mode == GEMM_NN) {
     NDT1_TRY(make_map(p.A, BK, BM, &ma));
     NDT1_TRY(make_map(p.B, 64, BK, &mb));
-    return launch_mode<GEMM_NN>(bn, ma, mb, tp, stream);
+    return launch_mode<GEMM_NN>(bn, ctas, ma, mb, tp, stream);
   }
   NDT1_TRY(make_map(p.A, BK, BM, &ma));
-  NDT1_TRY(make_map(p.B, BK, bn, &mb));
-  return launch_mode<GEMM_NT>(bn, ma, mb, tp, stream);
+  NDT1_TRY(make_map(p.B, BK, bn / ctas, &mb));
+  return launch_mode<GEMM_NT>(bn, ctas, ma, mb, tp, stream);
 }
 
 // ---- profiling hooks (C ABI wrappers in api.cu) ----

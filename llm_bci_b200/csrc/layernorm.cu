@@ -76,9 +76,19 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
 
 // Backward.  One warp per row, 8 warps per CTA, one CTA per SM (persistent over rows): every lane issues the
 // whole row's loads (dy, x AND the residual gradient) before the first reduction, so a warp keeps 10 KB in flight
-// and the 8 warps of an SM cover the HBM latency.  The affine gradients are accumulated in registers over the
-// rows of the warp, folded through shared memory once per CTA and added to dgamma / dbeta with red.global.
+// and the 8 warps of an SM cover the HBM latency.  The affine gradients (and the column sums of the emitted
+// operand = the next layer's bias gradient) are accumulated in registers over the rows of the warp, folded across
+// the CTA's warps through shared memory (plain stores + a tree, no atomics) and added to the outputs with red.global.
 constexpr int LNB_WARPS = 8;    // two warps per SM sub-partition: up to 255 registers per thread
+
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { typedef float4 type; };
+template <> struct Raw4<bf16> { typedef uint2 type; };
+__device__ __forceinline__ float4 unpack4(float4 r) { return r; }
+__device__ __forceinline__ float4 unpack4(uint2 r) {
+  const __nv_bfloat162 x = *(const __nv_bfloat162*)&r.x, y = *(const __nv_bfloat162*)&r.y;
+  return make_float4(__low2float(x), __high2float(x), __low2float(y), __high2float(y));
+}
 
 template <typename T>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 1)
@@ -86,25 +96,23 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float
               const float* __restrict__ rstd, float* __restrict__ dres, T* __restrict__ out_lp, float drop_p, unsigned long long seed,
               unsigned long long stream_id, long long rows, int H, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ colsum_out) {
-  extern __shared__ float sm[];   // [2][H] affine gradients, then [4][H/4] column sums of out_lp (plane j = column 4c+j)
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * LNB_WARPS + (threadIdx.x >> 5);
+  extern __shared__ float sm[];   // [warps][3][H]: per-warp partial sums of dgamma | dbeta | colsum(out_lp)
+  typedef typename Raw4<T>::type raw_t;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp0 = (long long)blockIdx.x * LNB_WARPS + warp;
   const int nv = H / 4;
-  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  float* sm_cs = sm + 2 * H;
-  float4 dg[LN_MAXV], db[LN_MAXV];
+  float4 dg[LN_MAXV], db[LN_MAXV], cs[LN_MAXV];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) { dg[i] = make_float4(0.f, 0.f, 0.f, 0.f); db[i] = dg[i]; }
+  for (int i = 0; i < LN_MAXV; ++i) { dg[i] = make_float4(0.f, 0.f, 0.f, 0.f); db[i] = dg[i]; cs[i] = dg[i]; }
   const uint32_t thr = drop_threshold(drop_p);
   const float ik = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
   for (long long r = warp0; r < rows; r += (long long)gridDim.x * LNB_WARPS) {
-    float4 d[LN_MAXV], xv[LN_MAXV], o[LN_MAXV];
+    raw_t dr[LN_MAXV]; float4 xv[LN_MAXV], o[LN_MAXV];
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i) {
       const int c = lane + 32 * i;
       if (c < nv) {
-        d[i] = load4<T>(dy + r * H + c * 4);
+        dr[i] = *(const raw_t*)(dy + r * H + c * 4);
         xv[i] = *(const float4*)(x + r * H + c * 4);
         o[i] = *(const float4*)(dres + r * H + c * 4);
       }
@@ -116,12 +124,13 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float
       const int c = lane + 32 * i;
       if (c < nv) {
         const float4 gm = __ldg((const float4*)(gamma + c * 4));
+        const float4 d = unpack4(dr[i]);
         xv[i] = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);   // x-hat
-        dg[i].x += d[i].x * xv[i].x; dg[i].y += d[i].y * xv[i].y; dg[i].z += d[i].z * xv[i].z; dg[i].w += d[i].w * xv[i].w;
-        db[i].x += d[i].x; db[i].y += d[i].y; db[i].z += d[i].z; db[i].w += d[i].w;
-        d[i] = make_float4(d[i].x * gm.x, d[i].y * gm.y, d[i].z * gm.z, d[i].w * gm.w);                              // dy * gamma
-        s1 += d[i].x + d[i].y + d[i].z + d[i].w;
-        s2 += d[i].x * xv[i].x + d[i].y * xv[i].y + d[i].z * xv[i].z + d[i].w * xv[i].w;
+        dg[i].x += d.x * xv[i].x; dg[i].y += d.y * xv[i].y; dg[i].z += d.z * xv[i].z; dg[i].w += d.w * xv[i].w;
+        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+        const float4 g = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);                                // dy * gamma
+        s1 += g.x + g.y + g.z + g.w;
+        s2 += g.x * xv[i].x + g.y * xv[i].y + g.z * xv[i].z + g.w * xv[i].w;
       }
     }
     const float c1 = warp_sum(s1) / H, c2 = warp_sum(s2) / H;
@@ -129,8 +138,10 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float
     for (int i = 0; i < LN_MAXV; ++i) {
       const int c = lane + 32 * i;
       if (c < nv) {
-        o[i].x += rs * (d[i].x - c1 - xv[i].x * c2); o[i].y += rs * (d[i].y - c1 - xv[i].y * c2);
-        o[i].z += rs * (d[i].z - c1 - xv[i].z * c2); o[i].w += rs * (d[i].w - c1 - xv[i].w * c2);
+        const float4 gm = __ldg((const float4*)(gamma + c * 4));
+        const float4 d = unpack4(dr[i]);
+        o[i].x += rs * (d.x * gm.x - c1 - xv[i].x * c2); o[i].y += rs * (d.y * gm.y - c1 - xv[i].y * c2);
+        o[i].z += rs * (d.z * gm.z - c1 - xv[i].z * c2); o[i].w += rs * (d.w * gm.w - c1 - xv[i].w * c2);
         *(float4*)(dres + r * H + c * 4) = o[i];
         if (out_lp) {
           float4 q = o[i];
@@ -140,27 +151,30 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float
             q.x *= ds[0]; q.y *= ds[1]; q.z *= ds[2]; q.w *= ds[3];
           }
           store4<T>(out_lp + r * H + c * 4, q.x, q.y, q.z, q.w);
-          if (colsum_out) {   // bias gradient of the linear layer that consumed this row's forward counterpart
-            atomicAdd(&sm_cs[c], q.x); atomicAdd(&sm_cs[nv + c], q.y); atomicAdd(&sm_cs[2 * nv + c], q.z); atomicAdd(&sm_cs[3 * nv + c], q.w);
-          }
+          cs[i].x += q.x; cs[i].y += q.y; cs[i].z += q.z; cs[i].w += q.w;   // bias gradient of the layer that consumes out_lp
         }
       }
     }
   }
-  // fold the affine gradients of the CTA's warps, then one red.global per column per CTA
+  // fold across the CTA's warps: plain stores, one barrier, column-parallel sums, one red.global per column per CTA
+  float* mine = sm + (size_t)warp * 3 * H;
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i) {
     const int c = lane + 32 * i;
     if (c < nv) {
-      atomicAdd(&sm[c * 4 + 0], dg[i].x); atomicAdd(&sm[c * 4 + 1], dg[i].y); atomicAdd(&sm[c * 4 + 2], dg[i].z); atomicAdd(&sm[c * 4 + 3], dg[i].w);
-      atomicAdd(&sm[H + c * 4 + 0], db[i].x); atomicAdd(&sm[H + c * 4 + 1], db[i].y); atomicAdd(&sm[H + c * 4 + 2], db[i].z); atomicAdd(&sm[H + c * 4 + 3], db[i].w);
+      *(float4*)(mine + c * 4) = dg[i];
+      *(float4*)(mine + H + c * 4) = db[i];
+      *(float4*)(mine + 2 * H + c * 4) = cs[i];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    if (dgamma) atomicAdd(dgamma + i, sm[i]);
-    if (dbeta) atomicAdd(dbeta + i, sm[H + i]);
-    if (colsum_out) atomicAdd(colsum_out + (i % nv) * 4 + i / nv, sm_cs[i]);
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) {
+    float* dst = i < H ? dgamma : (i < 2 * H ? dbeta : colsum_out);
+    if (!dst) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < LNB_WARPS; ++w) v += sm[(size_t)w * 3 * H + i];
+    atomicAdd(dst + (i < H ? i : (i < 2 * H ? i - H : i - 2 * H)), v);
   }
 }
 
@@ -194,7 +208,13 @@ int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   long long nb = (rows + LNB_WARPS - 1) / LNB_WARPS;
   if (nb > sms) nb = sms;
-  ln_bwd_kernel<T><<<(int)nb, LNB_WARPS * 32, 3 * H * sizeof(float), stream>>>(dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed,
+  const size_t smem = (size_t)LNB_WARPS * 3 * H * sizeof(float);
+  static size_t attr[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > attr[sizeof(T) == 2]) {
+    NDT1_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[sizeof(T) == 2] = smem;
+  }
+  ln_bwd_kernel<T><<<(int)nb, LNB_WARPS * 32, smem, stream>>>(dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed,
                                                                                stream_id, rows, H, dgamma, dbeta, out_lp ? colsum_out : nullptr);
   NDT1_CHECK_LAUNCH();
   return 0;
