@@ -15,11 +15,11 @@
 
 namespace {
 
-__global__ void log_softmax_kernel(const float* __restrict__ logits, float* __restrict__ logp, long long rows, int V) {
+__global__ void log_softmax_kernel(const float* __restrict__ logits, float* __restrict__ logp, long long rows, int V, int ld_in) {
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
-  const float* x = logits + r * V;
+  const float* x = logits + r * ld_in;
   float m = -INFINITY;
   for (int c = lane; c < V; c += 32) m = fmaxf(m, x[c]);
   m = warp_max(m);
@@ -39,14 +39,24 @@ struct CtcParams {
 constexpr int kRenorm = 8;    // re-centre the alpha/beta rows every kRenorm frames
 constexpr int kCtcWarps = 8;
 
-// FAST: MUFU ex2/lg2 (bf16 engine mode); otherwise libm-accurate expf/logf (strict fp32 mode, stand-alone operator)
-template <bool FAST> __device__ __forceinline__ float exp_t(float x) { return FAST ? __expf(x) : expf(x); }
-template <bool FAST> __device__ __forceinline__ float log_t(float x) { return FAST ? __logf(x) : logf(x); }
+// FAST (bf16 engine mode): the whole recursion runs in BASE 2 -- log-probabilities are scaled by log2(e) once, so an
+// exponential / logarithm is a single MUFU ex2 / lg2 with no multiply around it.  Otherwise (strict fp32 mode, the
+// stand-alone operator): natural logarithms with libm-accurate expf / logf.
+template <bool FAST> __device__ __forceinline__ float exp_t(float x) {
+  if (FAST) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  return expf(x);
+}
+template <bool FAST> __device__ __forceinline__ float log_t(float x) {
+  if (FAST) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  return logf(x);
+}
+template <bool FAST> __device__ __forceinline__ constexpr float log_unit() { return FAST ? 1.4426950408889634f : 1.0f; }
 template <bool FAST>
 __device__ __forceinline__ float lse3(float a, float b, float c) {
+  // branch-free (the SPT independent recurrences of a lane interleave): all -inf -> exp(-inf) = 0 -> log(0) = -inf
   const float m = fmaxf(a, fmaxf(b, c));
-  if (m == -INFINITY) return -INFINITY;
-  return m + log_t<FAST>(exp_t<FAST>(a - m) + exp_t<FAST>(b - m) + exp_t<FAST>(c - m));
+  const float ms = (m == -INFINITY) ? 0.f : m;
+  return ms + log_t<FAST>(exp_t<FAST>(a - ms) + exp_t<FAST>(b - ms) + exp_t<FAST>(c - ms));
 }
 
 // One sweep (alpha: FWD, beta: !FWD) by ONE warp: lane j keeps the SPT consecutive states [j*SPT, (j+1)*SPT) of the
@@ -54,8 +64,9 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
 // barrier on the L-step dependent chain.  Rows are re-centred every kRenorm frames (offsets in double) and
 // streamed to the workspace for the posterior pass.
 template <bool FAST, int SPT, bool FWD>
-__device__ __forceinline__ void ctc_sweep(const CtcParams& p, const float* __restrict__ lp, const int* __restrict__ lab, int Lx, int LX, int Tn,
-                                          float* __restrict__ rows, double* __restrict__ offs, float* fin) {
+__device__ __forceinline__ void ctc_sweep(const CtcParams& p, const float* __restrict__ lp, float lps, const int* __restrict__ lab, int Lx, int LX,
+                                          int Tn, float* __restrict__ rows, double* __restrict__ offs, float* fin) {
+  // lp: log-probabilities, lps: factor that brings them to the recursion's log unit (1 when lp is already scaled)
   const int lane = threadIdx.x & 31;
   const int s0 = lane * SPT;
   int my[SPT]; bool live[SPT], skip[SPT];
@@ -71,7 +82,7 @@ __device__ __forceinline__ void ctc_sweep(const CtcParams& p, const float* __res
   double off = 0.0;
   const int t0 = FWD ? 0 : Tn - 1;
 #pragma unroll
-  for (int i = 0; i < SPT; ++i) e[i] = lp[t0 * p.V + my[i]];
+  for (int i = 0; i < SPT; ++i) e[i] = lp[t0 * p.V + my[i]] * lps;
   for (int k = 0; k < Tn; ++k) {
     const int t = FWD ? k : Tn - 1 - k;
     float v[SPT];
@@ -96,24 +107,41 @@ __device__ __forceinline__ void ctc_sweep(const CtcParams& p, const float* __res
         if (lane > 30) n1 = -INFINITY;
         if (lane > (SPT >= 2 ? 30 : 29)) n2 = -INFINITY;
       }
+      // the SPT recurrences of a lane are independent: written stage by stage so that their MUFU latencies overlap
+      float x0[SPT], x1[SPT], x2[SPT], ms[SPT], sum[SPT];
 #pragma unroll
       for (int i = 0; i < SPT; ++i) {
-        float x1, x2;
+        x0[i] = a[i];
         if (FWD) {
-          x1 = i >= 1 ? a[i >= 1 ? i - 1 : 0] : n1;
-          x2 = i >= 2 ? a[i >= 2 ? i - 2 : 0] : (i == 1 ? n1 : n2);
+          x1[i] = i >= 1 ? a[i >= 1 ? i - 1 : 0] : n1;
+          x2[i] = i >= 2 ? a[i >= 2 ? i - 2 : 0] : (i == 1 ? n1 : n2);
         } else {
-          x1 = i + 1 < SPT ? a[i + 1 < SPT ? i + 1 : 0] : n1;
-          x2 = i + 2 < SPT ? a[i + 2 < SPT ? i + 2 : 0] : (i + 2 == SPT ? n1 : n2);
+          x1[i] = i + 1 < SPT ? a[i + 1 < SPT ? i + 1 : 0] : n1;
+          x2[i] = i + 2 < SPT ? a[i + 2 < SPT ? i + 2 : 0] : (i + 2 == SPT ? n1 : n2);
         }
-        const float r = lse3<FAST>(a[i], x1, skip[i] ? x2 : -INFINITY);
+        x2[i] = skip[i] ? x2[i] : -INFINITY;
+      }
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) {
+        const float m = fmaxf(x0[i], fmaxf(x1[i], x2[i]));
+        ms[i] = (m == -INFINITY) ? 0.f : m;                   // all -inf -> exp(-inf) = 0 -> log(0) = -inf, no branch
+      }
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) { x0[i] = exp_t<FAST>(x0[i] - ms[i]); x1[i] = exp_t<FAST>(x1[i] - ms[i]); x2[i] = exp_t<FAST>(x2[i] - ms[i]); }
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) sum[i] = x0[i] + x1[i] + x2[i];
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) sum[i] = log_t<FAST>(sum[i]);
+#pragma unroll
+      for (int i = 0; i < SPT; ++i) {
+        const float r = ms[i] + sum[i];
         v[i] = (live[i] && r != -INFINITY) ? r + e[i] : -INFINITY;
       }
     }
     if (k + 1 < Tn) {                 // next frame's emissions: independent of the recurrence, issued early
       const int tn = FWD ? t + 1 : t - 1;
 #pragma unroll
-      for (int i = 0; i < SPT; ++i) e[i] = lp[tn * p.V + my[i]];
+      for (int i = 0; i < SPT; ++i) e[i] = lp[tn * p.V + my[i]] * lps;
     }
     if ((k % kRenorm) == kRenorm - 1) {
       float m = v[0];
@@ -176,11 +204,18 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) 
   float* beta = p.beta + (long long)b * p.L * LX;
   float* dl = p.dlogits ? p.dlogits + (long long)b * p.L * p.V : nullptr;
 
-  if (p.lp_in_smem) {
-    for (int i = tid; i < p.L * p.V; i += blockDim.x)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(lp_s + i)), "l"(lp_g + i) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  constexpr float kUnit = log_unit<FAST>();
+  if (p.lp_in_smem) {              // staged once, already in the recursion's log unit; 8 independent loads in flight per thread
+    const int n = p.L * p.V;
+    for (int i0 = tid; i0 < n; i0 += blockDim.x * 8) {
+      float t8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; t8[u] = i < n ? __ldg(lp_g + i) : 0.f; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < n) lp_s[i] = t8[u] * kUnit; }
+    }
   }
+  const float lps = p.lp_in_smem ? 1.0f : kUnit;
   for (int i = tid; i < LXA + 2; i += blockDim.x) lab[i] = (i < Lx && (i & 1)) ? (int)p.targets[(long long)b * p.S + (i >> 1)] : p.blank;
   if (tid < 2) fin[tid] = -INFINITY;
   __syncthreads();
@@ -198,16 +233,15 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) 
     int n = cstart[tid];
     for (int j = 0; j < S; ++j) if (lab[2 * j + 1] == tid) cpos[n++] = j;
   }
-  if (p.lp_in_smem) asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   double ll = -INFINITY;
   if (Tn > 0) {
-    if (warp == 0) ctc_sweep<FAST, SPT, true>(p, lp, lab, Lx, LX, Tn, alpha, Cs, fin);
-    else if (warp == 1) ctc_sweep<FAST, SPT, false>(p, lp, lab, Lx, LX, Tn, beta, Ds, fin);
+    if (warp == 0) ctc_sweep<FAST, SPT, true>(p, lp, lps, lab, Lx, LX, Tn, alpha, Cs, fin);
+    else if (warp == 1) ctc_sweep<FAST, SPT, false>(p, lp, lps, lab, Lx, LX, Tn, beta, Ds, fin);
     __syncthreads();
     if (tid == 0) {
-      const float v = lse3<false>(fin[0], fin[1], -INFINITY);
+      const float v = lse3<FAST>(fin[0], fin[1], -INFINITY);     // (in the recursion's log unit)
       s_ll = (v == -INFINITY) ? -INFINITY : Cs[Tn - 1] + (double)v;
     }
     __syncthreads();
@@ -216,7 +250,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) 
     ll = 0.0;
   }
   const bool feasible = (ll != -INFINITY) && (ll == ll);
-  if (tid == 0) p.nll[b] = feasible ? (float)(-ll) : (p.zero_infinity ? 0.f : INFINITY);
+  if (tid == 0) p.nll[b] = feasible ? (float)(-ll / (double)kUnit) : (p.zero_infinity ? 0.f : INFINITY);
   if (!dl) return;
   const float gs = p.dloss ? *p.dloss : 1.f;
   const int t_zero_from = (feasible && Tn > 0) ? Tn : 0;
@@ -225,21 +259,28 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) 
 
   // posteriors: one warp per frame.  dlogits[t,c] = (softmax[t,c] - sum_{s: l'(s)=c} alpha beta / (p_t(c) P)) * dloss
   float* wb = wbuf + warp * LXA;
-  for (int t = warp; t < Tn; t += kCtcWarps) {
-    const float kt = (float)(Cs[t] + Ds[t] - ll);
-    float al[SPT], be[SPT];
+  float al[SPT], be[SPT], al_n[SPT], be_n[SPT];
+  auto fetch = [&](int t, float* a_, float* b_) {
 #pragma unroll
     for (int i = 0; i < SPT; ++i) {
       const int s2 = lane + 32 * i;
-      al[i] = s2 < Lx ? alpha[(long long)t * LX + s2] : -INFINITY;
-      be[i] = s2 < Lx ? beta[(long long)t * LX + s2] : -INFINITY;
+      const bool in = t < Tn && s2 < Lx;
+      a_[i] = in ? alpha[(long long)t * LX + s2] : -INFINITY;
+      b_[i] = in ? beta[(long long)t * LX + s2] : -INFINITY;
     }
+  };
+  fetch(warp, al_n, be_n);
+  for (int t = warp; t < Tn; t += kCtcWarps) {
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) { al[i] = al_n[i]; be[i] = be_n[i]; }
+    fetch(t + kCtcWarps, al_n, be_n);           // the next frame's rows fly while this frame is reduced
+    const float kt = (float)(Cs[t] + Ds[t] - ll);
     float blank_acc = 0.f;
 #pragma unroll
     for (int i = 0; i < SPT; ++i) {
       const int s2 = lane + 32 * i;
       float w = 0.f;
-      if (al[i] != -INFINITY && be[i] != -INFINITY) w = exp_t<FAST>(al[i] + be[i] - lp[t * p.V + lab[s2]] + kt);
+      if (al[i] != -INFINITY && be[i] != -INFINITY) w = exp_t<FAST>(al[i] + be[i] - lp[t * p.V + lab[s2]] * lps + kt);
       wb[s2] = w;
       if (!(s2 & 1)) blank_acc += w;
     }
@@ -248,7 +289,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) 
     for (int c = lane; c < p.V; c += 32) {
       float acc = (c == p.blank) ? blank_acc : 0.f;
       for (int k = cstart[c]; k < cstart[c + 1]; ++k) acc += wb[2 * cpos[k] + 1];
-      dl[(long long)t * p.V + c] = (exp_t<FAST>(lp[t * p.V + c]) - acc) * gs;
+      dl[(long long)t * p.V + c] = (exp_t<FAST>(lp[t * p.V + c] * lps) - acc) * gs;
     }
     __syncwarp();
   }
@@ -279,9 +320,9 @@ __global__ void greedy_kernel(const float* logp, int B, int L, int V, int blank,
 
 }  // namespace
 
-int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaStream_t stream) {
+int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaStream_t stream, int ld_in) {
   if (rows == 0) return 0;
-  log_softmax_kernel<<<ndt1_cdiv(rows, 8), 256, 0, stream>>>(logits, logp, rows, V);
+  log_softmax_kernel<<<ndt1_cdiv(rows, 8), 256, 0, stream>>>(logits, logp, rows, V, ld_in > 0 ? ld_in : V);
   NDT1_CHECK_LAUNCH();
   return 0;
 }

@@ -85,6 +85,92 @@ __global__ void smooth_noise_kernel(const SmoothParams p) {
     }
   }
 }
+// Fast path (N % 4 == 0, compile-time tap count): one thread owns FOUR adjacent channels (128-bit loads/stores,
+// a warp reads 512 contiguous bytes) and a strip of SMV_TT bins, sliding a K-deep register window along time; one
+// Philox call per bin yields the four N(0,1) draws of its four channels (same element -> draw mapping as the
+// generic kernel: counter = element / 2 for consecutive element pairs... see white_pair()).
+constexpr int SMV_TT = 25;
+__device__ __forceinline__ void white_quad(unsigned long long seed, unsigned long long e0, float* nz) {
+  // elements e0..e0+3 (e0 % 4 == 0): the generic kernel draws element e from Philox(seed, e >> 1): lane (e & 1) of box_muller(x, y)
+  const Philox4 r0 = philox4x32_10(seed, e0 >> 1, 0x77686974ULL);
+  const Philox4 r1 = philox4x32_10(seed, (e0 >> 1) + 1, 0x77686974ULL);
+  box_muller(r0.x, r0.y, nz[0], nz[1]);
+  box_muller(r1.x, r1.y, nz[2], nz[3]);
+}
+template <int K>
+__global__ void __launch_bounds__(256) smooth_noise_vec_kernel(const SmoothParams p) {
+  const int n4 = blockIdx.x * 64 + (threadIdx.x & 63);          // channel quad
+  const int strip = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int b = blockIdx.z;
+  const int t0 = strip * SMV_TT;
+  if (n4 * 4 >= p.N || t0 >= p.T) return;
+  constexpr int half = (K - 1) / 2;
+  const float4* xb = (const float4*)(p.x + (long long)b * p.T * p.N) + n4;
+  float4* ob = (float4*)(p.out + (long long)b * p.T * p.N) + n4;
+  const int ld4 = p.N / 4;
+  float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.offset_sd != 0.f) {
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < 4; ++c) {
+      const unsigned long long e = (unsigned long long)b * p.N + n4 * 4 + c;
+      if (p.offset) o[c] = p.offset_sd * p.offset[e];
+      else if (p.use_philox) {
+        Philox4 r = philox4x32_10(p.seed, e, 0x6f666673ULL);
+        float a, d; box_muller(r.x, r.y, a, d);
+        o[c] = p.offset_sd * a;
+      }
+    }
+    off = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  float w[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) w[i] = p.w[i];
+  float4 win[K];                                   // win[i] = x[t + i - half]
+#pragma unroll
+  for (int i = 0; i < K - 1; ++i) {
+    const int t = t0 + i - half;
+    win[i + 1] = (t >= 0 && t < p.T) ? __ldg(xb + (long long)t * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll 1
+  for (int j0 = 0; j0 < SMV_TT; j0 += K) {         // K outputs per trip so that the window rotates at compile time
+    float4 nxt[K];                                 // the K rows this trip appends: all loads issued before the first use
+#pragma unroll
+    for (int jj = 0; jj < K; ++jj) {
+      const int tn = t0 + j0 + jj + half;
+      nxt[jj] = (tn >= 0 && tn < p.T && j0 + jj < SMV_TT) ? __ldg(xb + (long long)tn * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int jj = 0; jj < K; ++jj) {
+      const int t = t0 + j0 + jj;
+      // slide: drop the oldest, append x[t + half]
+#pragma unroll
+      for (int i = 0; i < K - 1; ++i) win[i] = win[i + 1];
+      win[K - 1] = nxt[jj];
+      if (j0 + jj < SMV_TT && t < p.T) {
+        float4 acc = off;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          acc.x = fmaf(w[i], win[i].x, acc.x); acc.y = fmaf(w[i], win[i].y, acc.y);
+          acc.z = fmaf(w[i], win[i].z, acc.z); acc.w = fmaf(w[i], win[i].w, acc.w);
+        }
+        if (p.white_sd != 0.f) {
+          const unsigned long long e = ((unsigned long long)b * p.T + t) * p.N + n4 * 4;
+          if (p.white) {
+            const float4 wn = __ldg((const float4*)(p.white + e));
+            acc.x = fmaf(p.white_sd, wn.x, acc.x); acc.y = fmaf(p.white_sd, wn.y, acc.y);
+            acc.z = fmaf(p.white_sd, wn.z, acc.z); acc.w = fmaf(p.white_sd, wn.w, acc.w);
+          } else if (p.use_philox) {
+            float nz[4];
+            white_quad(p.seed, e, nz);
+            acc.x = fmaf(p.white_sd, nz[0], acc.x); acc.y = fmaf(p.white_sd, nz[1], acc.y);
+            acc.z = fmaf(p.white_sd, nz[2], acc.z); acc.w = fmaf(p.white_sd, nz[3], acc.w);
+          }
+        }
+        ob[(long long)t * ld4] = acc;
+      }
+    }
+  }
+}
 }  // namespace
 
 int k_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps, int K, float white_sd, float offset_sd,
@@ -97,6 +183,12 @@ int k_smooth_noise(const float* x, float* out, int B, int T, int N, const float*
   for (int i = 0; i < K; ++i) p.w[i] = taps[i];
   p.white_sd = white_sd; p.offset_sd = offset_sd; p.white = white; p.offset = offset;
   p.use_philox = use_philox; p.seed = seed;
+  if (K == 13 && N % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 && (!white || ((uintptr_t)white & 15) == 0)) {
+    dim3 grid(ndt1_cdiv(N / 4, 64), ndt1_cdiv(ndt1_cdiv(T, SMV_TT), 4), B);     // the reference's default: gaussian(1 + 6 sd, sd = 2)
+    smooth_noise_vec_kernel<13><<<grid, 256, 0, stream>>>(p);
+    NDT1_CHECK_LAUNCH();
+    return 0;
+  }
   dim3 block(128), grid(ndt1_cdiv(N, 128), ndt1_cdiv(T, SM_TT), B);
   smooth_noise_kernel<<<grid, block, 0, stream>>>(p);
   NDT1_CHECK_LAUNCH();

@@ -82,7 +82,7 @@ struct Engine : ndt1_engine {
   cudaEvent_t join_ev = nullptr;
   T* dEmb = nullptr; T* dhn = nullptr; T* dfac = nullptr;
   float* delta = nullptr; float* ln_part = nullptr;
-  int ldV = 0;
+  int ldV = 0, ldL = 0;
   // bf16 weight copies
   bf16* w_emb = nullptr; bf16* w_proj = nullptr; bf16* w_fac = nullptr; bf16* w_dec = nullptr;
   std::vector<bf16*> w_qkv, w_o, w_up, w_down;
@@ -116,7 +116,8 @@ struct Engine : ndt1_engine {
     }
     hn = ar.take<T>(Mm * H);
     if (k.factors_active) { fac = ar.take<T>(Mm * Hout); fpre = ar.take<T>(Mm * Hout); dfac = ar.take<T>(Mm * Hout); }
-    logits = ar.take<float>(Mout * k.n_outputs); logp = ar.take<float>(Mout * k.n_outputs); dlogits = ar.take<float>(Mout * k.n_outputs);
+    ldL = (k.method == NDT1_METHOD_CTC) ? (k.n_outputs + 3) / 4 * 4 : k.n_outputs;   // phoneme logits: rows padded to 16 bytes (vector epilogue)
+    logits = ar.take<float>(Mout * ldL); logp = ar.take<float>(Mout * k.n_outputs); dlogits = ar.take<float>(Mout * k.n_outputs);
     nll = ar.take<float>(Bm);
     if (k.method == NDT1_METHOD_CTC) ctc_ws = ar.take<float>(k_ctc_workspace_floats(Bm, out_len(Tm), k.max_targets));
     key_valid = ar.take<long long>(Mm); out_lens = ar.take<long long>(Bm);
@@ -205,7 +206,8 @@ struct Engine : ndt1_engine {
     GemmProblem p = prob(GEMM_TN, N, K, M);
     p.A = op(dy, 0, 1, M, N, lddy); p.B = op(a, 0, 1, M, K, lda);
     p.epi.out = dw; p.epi.ldc = lddw; p.epi.accumulate = 1;
-    p.split_k = pick_split(ndt1_cdiv(N, 128) * ndt1_cdiv(K, K > 128 ? 256 : (K > 64 ? 128 : 64)), ndt1_cdiv(M, 64));
+    // tensor-core kernel: 0 = let the launcher size the split for one wave of its (CTA or CTA-pair) work units
+    p.split_k = (kBf16 && !force_simt) ? 0 : pick_split(ndt1_cdiv(N, 128) * ndt1_cdiv(K, K > 128 ? 256 : (K > 64 ? 128 : 64)), ndt1_cdiv(M, 64));
     return run(p, s);
   }
   // split the reduction so that tiles*split fills whole waves of 148 SMs
@@ -405,7 +407,7 @@ struct Engine : ndt1_engine {
       p.nb_out = B;
       p.A = op(head_in + (long long)n_prefix * head_ld, (long long)L * head_ld, B, Tp, Hout, head_ld);
       p.B = op(W(P->dec_w, w_dec), 0, 1, V, Hout, Hout);
-      p.epi.out = logits; p.epi.ldc = V; p.epi.c_batch_stride = (long long)Tp * V; p.epi.bias = P->dec_b;
+      p.epi.out = logits; p.epi.ldc = ldL; p.epi.c_batch_stride = (long long)Tp * ldL; p.epi.bias = P->dec_b;
       NDT1_TRY(run(p, s));
     }
     // 5. loss   (models/ndt1.py:548-589)
@@ -415,7 +417,7 @@ struct Engine : ndt1_engine {
     const long long Mo = (long long)B * Tp;
     if (k.method == NDT1_METHOD_CTC) {
       NDT1_REQUIRE(bt->targets && bt->targets_lengths, "engine: ctc needs targets and targets_lengths");
-      NDT1_TRY(k_log_softmax(logits, logp, Mo, V, s));
+      NDT1_TRY(k_log_softmax(logits, logp, Mo, V, s, ldL));
       NDT1_TRY(k_ctc_fwd_bwd(logp, (const long long*)bt->targets, out_lens, (const long long*)bt->targets_lengths, B, Tp, V, S, k.blank_id, k.zero_infinity, ctc_ws, nll,
                              o->loss, bt->need_backward ? dlogits : nullptr, nullptr, s, kBf16));
       if (o->preds) NDT1_CUDA_CHECK(cudaMemcpyAsync(o->preds, logp, Mo * V * 4, cudaMemcpyDeviceToDevice, s));
@@ -491,6 +493,7 @@ struct Engine : ndt1_engine {
       const int kb = p.nchunk * ndt1_cdiv(p.chunk_k, 64);
       p.split_k = kb >= 32 ? 16 : 1;
       if (!(kBf16 && !force_simt) && p.split_k > 8) p.split_k = 8;
+      if (kBf16 && !force_simt) p.split_k = 0;
       NDT1_TRY(run(p, ws));
     }
     {
@@ -534,7 +537,8 @@ struct Engine : ndt1_engine {
         if (k.mlp_act == NDT1_ACT_GELU) { e.dact = DACT_GELU_FROM_IN; e.dact_in = u[l]; }
         else { e.dact = dact_from_out(k.mlp_act); e.dact_in = g[l]; }
         e.dact_in_bf16 = kBf16;
-        const bool fuse_cs = kBf16 && !force_simt && gq.up_b && k.mlp_bias && I % 8 == 0;
+        // (with the second stream the reduction runs there, off the data-gradient chain; fused into the epilogue otherwise)
+        const bool fuse_cs = kBf16 && !force_simt && !overlap && gq.up_b && k.mlp_bias && I % 8 == 0;
         if (fuse_cs) e.colsum = gq.up_b;
         NDT1_TRY(linear_dgrad(dY, H, W(q.down_w, kBf16 ? w_down[l] : nullptr), I, (int)M, H, I, e, s));
         NDT1_TRY(fork());
@@ -625,7 +629,7 @@ struct Engine : ndt1_engine {
         p.A = op(dE, (long long)L * H, B, Tp, H, H);
         p.B = op(emb, (long long)Tn * D, B, R4, K4, K4);
         p.epi.out = G->proj_w; p.epi.ldc = nch * K4; p.epi.accumulate = 1;
-        p.split_k = (B >= 8 && kBf16 && !force_simt) ? 2 : 1;
+        p.split_k = (kBf16 && !force_simt) ? 0 : 1;
         NDT1_TRY(run(p, ws));
       }
       if (Tn % k.stack_stride != 0) NDT1_CUDA_CHECK(cudaMemsetAsync(dEmb, 0, MT * D * sizeof(T), s));
@@ -666,7 +670,7 @@ struct Engine : ndt1_engine {
       const int kb = ndt1_cdiv(MT, 64);
       int split = kb / 8; if (split > 64) split = 64; if (split < 1) split = 1;
       if (!(kBf16 && !force_simt) && split > 8) split = 8;
-      p.split_k = split;
+      p.split_k = (kBf16 && !force_simt) ? 0 : split;
       NDT1_TRY(run(p, ws));
     }
     NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[NL + 1], ws));     // embedding gradients complete

@@ -137,10 +137,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
     }
     return;
   }
-  const bool col_ok = at.n < p.N;      // N % 4 == 0 on this path
-  float4 v[8];
+  const bool col_ok = at.n < p.N;      // a last, partial group of 4 columns is stored whole: the row stride is padded (ldc % 4 == 0)
+  float4 v[8];                         // and its accumulators beyond N are zero (out-of-range operand rows read as zero)
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (e.bias && col_ok) bias4 = __ldg((const float4*)(e.bias + at.n));
+  if (e.bias && col_ok) {
+    if (at.n + 4 <= p.N) bias4 = __ldg((const float4*)(e.bias + at.n));
+    else {
+      bias4.x = __ldg(e.bias + at.n);
+      if (at.n + 1 < p.N) bias4.y = __ldg(e.bias + at.n + 1);
+      if (at.n + 2 < p.N) bias4.z = __ldg(e.bias + at.n + 2);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     v[i].x = fmaf(acc[i].x, e.alpha, bias4.x); v[i].y = fmaf(acc[i].y, e.alpha, bias4.y);
@@ -480,8 +487,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t stg_u32 = smem_u32(stg);
     const GemmEpilogue& e = p.epi;
     EpiCtx cx;
-    cx.vec_ok = (p.N % 4 == 0) && (e.ldc % 4 == 0) && (e.c_batch_stride % 4 == 0) && (e.gather_tab == nullptr || e.gather_ld % 4 == 0) &&
-                (e.drop_p <= 0.f || p.N % 8 == 0);
+    const bool plain = !e.out2 && !e.gather_tab && e.drop_p <= 0.f && e.dact == DACT_NONE && !e.resid && !e.accumulate && !e.colsum;
+    cx.vec_ok = (p.N % 4 == 0 || (plain && e.ldc >= p.N + (4 - p.N % 4))) && (e.ldc % 4 == 0) && (e.c_batch_stride % 4 == 0) &&
+                (e.gather_tab == nullptr || e.gather_ld % 4 == 0) && (e.drop_p <= 0.f || p.N % 8 == 0);
     cx.side_kind = e.resid ? SIDE_RESID : (e.dact != DACT_NONE ? SIDE_DACT : (e.gather_tab ? SIDE_GATHER : SIDE_NONE));
     int acc_stage = 0; uint32_t acc_phase = 0;
 
@@ -660,7 +668,7 @@ int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp
 template <int MODE>
 int launch_mode(int bn, int ctas, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
   if (bn == 256) return ctas == 2 ? launch_inst<256, MODE, 2>(ma, mb, tp, stream) : launch_inst<256, MODE, 1>(ma, mb, tp, stream);
-  if (bn == 128) return launch_inst<128, MODE, 1>(ma, mb, tp, stream);
+  if (bn == 128) return ctas == 2 ? launch_inst<128, MODE, 2>(ma, mb, tp, stream) : launch_inst<128, MODE, 1>(ma, mb, tp, stream);
   return launch_inst<64, MODE, 1>(ma, mb, tp, stream);
 }
 
@@ -703,11 +711,18 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   if (p.mode == GEMM_TN && p.b_chunk_n % bn != 0) bn = (p.b_chunk_n % 128 == 0) ? 128 : 64;
   NDT1_REQUIRE(p.mode != GEMM_TN || p.b_chunk_n % bn == 0 || p.b_chunk_n >= p.N, "gemm_tc: b_chunk_n=%d incompatible with tile", p.b_chunk_n);
 
-  // CTA pairs (256 x 256 tiles, cta_group::2) whenever the tile is the full 256 columns: half the shared-memory
-  // traffic per SM (each SM stages 128 of the 256 columns of B), which is what bounds the single-CTA main loop
+  // CTA pairs (256 x 256 tiles, cta_group::2) halve the shared-memory and L2 traffic per SM (each SM stages 128 of the
+  // 256 columns of B); they are used when the tile is the full 256 columns and pairing does not cost an extra wave.
   static const int force_ctas = getenv("NDT1_GEMM_CTAS") ? atoi(getenv("NDT1_GEMM_CTAS")) : 0;
-  int ctas = (bn == 256 && p.M > BM) ? 2 : 1;
+  int ctas = 1;
+  if (bn >= 128 && p.M > BM) {
+    const long long per = (long long)ndt1_cdiv(p.N, bn) * (p.mode == GEMM_TN ? 1 : p.nb_out);
+    const long long t1 = per * ndt1_cdiv(p.M, BM), t2 = per * ndt1_cdiv(p.M, 2 * BM);
+    const long long w1 = (t1 + g_num_sms - 1) / g_num_sms, w2 = (t2 + g_num_sms / 2 - 1) / (g_num_sms / 2);
+    if (p.mode == GEMM_TN || w2 <= w1) ctas = 2;     // (weight gradients size their split to one wave either way)
+  }
   if (force_ctas == 1) ctas = 1;
+  if (force_ctas == 2 && bn >= 128 && p.M > BM) ctas = 2;
   const int bm = BM * ctas;
   const int units = g_num_sms / ctas;
 
@@ -720,12 +735,16 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   tp.m_tiles = ndt1_cdiv(p.M, bm); tp.n_tiles = ndt1_cdiv(p.N, bn);
   tp.split_k = p.split_k > 1 ? p.split_k : 1;
   if (p.mode == GEMM_TN && p.split_k == 0 && p.epi.accumulate) {
-    // automatic split of the reduction: every split adds a full fp32 red.add pass over the output (the L2 atomics are
-    // what bounds these kernels), so take the largest split that still fits ONE wave of work units
+    // automatic split of the reduction over the work units (CTAs or CTA pairs): fewest waves x (main loop + epilogue);
+    // every split adds a full fp32 red.add pass over the output, which is what the constant term charges
     const int tiles = tp.m_tiles * tp.n_tiles, kblocks = tp.nchunk * tp.kb_per_chunk;
-    int sp = units / (tiles > 0 ? tiles : 1);
-    while (sp > 1 && sp * 4 > kblocks) --sp;
-    tp.split_k = sp < 1 ? 1 : sp;
+    int best = 1; long long best_cost = -1;
+    for (int sp = 1; sp <= 64 && (sp == 1 || sp * 4 <= kblocks); ++sp) {
+      const long long waves = ((long long)tiles * sp + units - 1) / units;
+      const long long cost = waves * (ndt1_cdiv(kblocks, sp) + 10);     // k-blocks per work item + ~10 k-blocks worth of fill / red.add epilogue
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
+    }
+    tp.split_k = best;
   }
   tp.total_tiles = tp.m_tiles * tp.n_tiles * (p.mode == GEMM_TN ? tp.split_k : p.nb_out);
   tp.epi = p.epi;

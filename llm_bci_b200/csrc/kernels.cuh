@@ -77,7 +77,7 @@ int k_attention_tc_fwd(const AttnParams& p, cudaStream_t stream);
 int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream);
 
 // ctc.cu
-int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaStream_t stream);
+int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaStream_t stream, int ld_in = 0);   // ld_in: row stride of logits (0 = V)
 // log-probs (B, L, V); per-trial NLL summed into *loss; dlogits = (softmax - posterior) * (*dloss) for t < len
 int k_ctc_fwd_bwd(const float* logp, const long long* targets, const long long* in_len, const long long* tgt_len, int B, int L, int V,
                   int S, int blank, int zero_infinity, float* alpha_ws, float* nll, float* loss, float* dlogits, const float* dloss,
