@@ -178,6 +178,179 @@ ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float
   }
 }
 
+__device__ __forceinline__ void red_add4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Row-group kernels (H % 128 == 0): a CTA of H/4 threads owns FOUR rows at a time and thread c the 4 columns
+// [4c, 4c+4) of each of them.  Compared with one warp per row this keeps the per-thread state tiny (the affine /
+// bias-gradient accumulators cover 4 columns, not 32), so several CTAs fit an SM and their loads overlap; the row
+// statistics cross the warps through a double-buffered shared-memory table (one barrier per reduction).
+// ---------------------------------------------------------------------------
+constexpr int LNG_ROWS = 4;
+
+// Sum EIGHT per-thread partials over the CTA.  Within a warp the 8 x 32 values are folded with 9 shuffles (each
+// xor step halves the number of values a lane carries instead of reducing them one by one = 40 shuffles); the
+// warps meet in a double-buffered shared-memory table (one barrier); on return lane l of every warp holds the
+// CTA total of partial (l % 8) -- callers fetch total i with __shfl_sync(.., i).
+__device__ __forceinline__ float cta_sum8(const float* v, float* red, int buf, int nwarps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float w[4], u[2], t;
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float send = h16 ? v[j] : v[j + 4], keep = h16 ? v[j + 4] : v[j];
+    w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = h8 ? w[j] : w[j + 2], keep = h8 ? w[j + 2] : w[j];
+    u[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const float send = h4 ? u[0] : u[1], keep = h4 ? u[1] : u[0];
+    t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  float* tab = red + buf * 32 * 8;
+  if ((lane & 3) == 0) tab[warp * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = t;
+  __syncthreads();
+  float s = 0.f;
+  for (int e = lane; e < nwarps * 8; e += 32) s += tab[e];      // entry e belongs to partial e % 8 == lane % 8
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  return s;
+}
+
+static_assert(LNG_ROWS == 4, "cta_sum8 folds exactly eight partials");
+constexpr int LNF_ROWS = 8;   // forward: 8 rows per group (only 4 registers per row: twice the loads in flight, half the barriers)
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 4 : 1) ln_fwd_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean,
+                                                           float* __restrict__ rstd, long long rows, int H, float eps) {
+  __shared__ float red[2 * 32 * 8];
+  const int c = threadIdx.x, nwarps = blockDim.x >> 5;
+  const float4 g = __ldg((const float4*)gamma + c), bt = __ldg((const float4*)beta + c);
+  const float inv_h = 1.0f / H;
+  for (long long r0 = (long long)blockIdx.x * LNF_ROWS; r0 < rows; r0 += (long long)gridDim.x * LNF_ROWS) {
+    float4 v[LNF_ROWS]; float part[LNF_ROWS], mu[LNF_ROWS], var[LNF_ROWS];
+#pragma unroll
+    for (int r = 0; r < LNF_ROWS; ++r) {
+      v[r] = (r0 + r < rows) ? *((const float4*)(x + (r0 + r) * H) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      part[r] = v[r].x + v[r].y + v[r].z + v[r].w;
+    }
+    const float tot1 = cta_sum8(part, red, 0, nwarps) * inv_h;          // lane l: mean of row l % 8
+#pragma unroll
+    for (int r = 0; r < LNF_ROWS; ++r) {
+      mu[r] = __shfl_sync(0xffffffffu, tot1, r);
+      const float a = v[r].x - mu[r], b = v[r].y - mu[r], cc = v[r].z - mu[r], d = v[r].w - mu[r];
+      part[r] = a * a + b * b + cc * cc + d * d;
+    }
+    const float rs_l = 1.0f / sqrtf(cta_sum8(part, red, 1, nwarps) * inv_h + eps);   // computed once per warp, for row l % 8
+    (void)var;
+#pragma unroll
+    for (int r = 0; r < LNF_ROWS; ++r) {
+      const float rs = __shfl_sync(0xffffffffu, rs_l, r);
+      if (r0 + r >= rows) continue;
+      if (c == 0) { mean[r0 + r] = mu[r]; rstd[r0 + r] = rs; }
+      store4<T>(y + (r0 + r) * H + c * 4, (v[r].x - mu[r]) * rs * g.x + bt.x, (v[r].y - mu[r]) * rs * g.y + bt.y,
+                (v[r].z - mu[r]) * rs * g.z + bt.z, (v[r].w - mu[r]) * rs * g.w + bt.w);
+    }
+  }
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1)
+ln_bwd_rows_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, float* __restrict__ dres, T* __restrict__ out_lp, float drop_p, unsigned long long seed,
+                   unsigned long long stream_id, long long rows, int H, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   float* __restrict__ colsum_out) {
+  __shared__ float red[2 * 32 * 8];
+  typedef typename Raw4<T>::type raw_t;
+  const int c = threadIdx.x, lane = c & 31, nwarps = blockDim.x >> 5;
+  const float4 gm = __ldg((const float4*)gamma + c);
+  const float inv_h = 1.0f / H;
+  float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg, cs = dg;
+  const uint32_t thr = drop_threshold(drop_p);
+  const float ik = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
+  int buf = 0;
+  for (long long r0 = (long long)blockIdx.x * LNG_ROWS; r0 < rows; r0 += (long long)gridDim.x * LNG_ROWS) {
+    raw_t dr[LNG_ROWS]; float4 xv[LNG_ROWS], o[LNG_ROWS]; float mu[LNG_ROWS], rs[LNG_ROWS];
+#pragma unroll
+    for (int r = 0; r < LNG_ROWS; ++r) {
+      const bool in = r0 + r < rows;
+      const long long e = (in ? r0 + r : r0) * H + c * 4;
+      dr[r] = *(const raw_t*)(dy + e);
+      xv[r] = *(const float4*)(x + e);
+      o[r] = *(const float4*)(dres + e);
+      mu[r] = mean[in ? r0 + r : r0]; rs[r] = in ? rstd[r0 + r] : 0.f;     // rs = 0 neutralises a row past the end
+    }
+    float part[2 * LNG_ROWS], sums[2 * LNG_ROWS];
+    float4 gd[LNG_ROWS];
+#pragma unroll
+    for (int r = 0; r < LNG_ROWS; ++r) {
+      float4 d = unpack4(dr[r]);
+      if (r0 + r >= rows) d = make_float4(0.f, 0.f, 0.f, 0.f);
+      xv[r] = make_float4((xv[r].x - mu[r]) * rs[r], (xv[r].y - mu[r]) * rs[r], (xv[r].z - mu[r]) * rs[r], (xv[r].w - mu[r]) * rs[r]);   // x-hat
+      dg.x += d.x * xv[r].x; dg.y += d.y * xv[r].y; dg.z += d.z * xv[r].z; dg.w += d.w * xv[r].w;
+      db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
+      gd[r] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);                                                              // dy * gamma
+      part[2 * r] = gd[r].x + gd[r].y + gd[r].z + gd[r].w;
+      part[2 * r + 1] = gd[r].x * xv[r].x + gd[r].y * xv[r].y + gd[r].z * xv[r].z + gd[r].w * xv[r].w;
+    }
+    const float tot = cta_sum8(part, red, buf, nwarps) * inv_h;         // lane l: partial l % 8 of the group
+    buf ^= 1;
+#pragma unroll
+    for (int i = 0; i < 2 * LNG_ROWS; ++i) sums[i] = __shfl_sync(0xffffffffu, tot, i);
+    // dropout keep-scales of out_lp: one Philox block = 8 elements = the columns of a lane pair; the even lane draws the
+    // block of rows 0 / 2, the odd lane of rows 1 / 3, and they swap halves (one Philox per 8 elements)
+    float keep[LNG_ROWS][4];
+    if (out_lp && drop_p > 0.f) {
+      const bool odd = lane & 1;
+#pragma unroll
+      for (int k = 0; k < LNG_ROWS / 2; ++k) {
+        const long long row = r0 + 2 * k + (odd ? 1 : 0);
+        const unsigned long long elem = (unsigned long long)row * H + (unsigned)((c * 4) & ~7);
+        const Philox4 ph = philox4x32_10(seed, elem >> 3, stream_id);
+        const uint32_t s0 = odd ? ph.x : ph.z, s1 = odd ? ph.y : ph.w;
+        const uint32_t q0 = __shfl_xor_sync(0xffffffffu, s0, 1), q1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+        const uint32_t a0 = odd ? q0 : ph.x, a1 = odd ? q1 : ph.y;     // row 2k
+        const uint32_t b0 = odd ? ph.z : q0, b1 = odd ? ph.w : q1;     // row 2k+1
+        keep[2 * k][0] = (a0 & 0xFFFFu) >= thr ? ik : 0.f; keep[2 * k][1] = (a0 >> 16) >= thr ? ik : 0.f;
+        keep[2 * k][2] = (a1 & 0xFFFFu) >= thr ? ik : 0.f; keep[2 * k][3] = (a1 >> 16) >= thr ? ik : 0.f;
+        keep[2 * k + 1][0] = (b0 & 0xFFFFu) >= thr ? ik : 0.f; keep[2 * k + 1][1] = (b0 >> 16) >= thr ? ik : 0.f;
+        keep[2 * k + 1][2] = (b1 & 0xFFFFu) >= thr ? ik : 0.f; keep[2 * k + 1][3] = (b1 >> 16) >= thr ? ik : 0.f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < LNG_ROWS; ++r) {
+      if (r0 + r >= rows) continue;
+      const float c1 = sums[2 * r], c2 = sums[2 * r + 1];
+      o[r].x += rs[r] * (gd[r].x - c1 - xv[r].x * c2); o[r].y += rs[r] * (gd[r].y - c1 - xv[r].y * c2);
+      o[r].z += rs[r] * (gd[r].z - c1 - xv[r].z * c2); o[r].w += rs[r] * (gd[r].w - c1 - xv[r].w * c2);
+      const long long e = (r0 + r) * H + c * 4;
+      *(float4*)(dres + e) = o[r];
+      if (out_lp) {
+        float4 q = o[r];
+        if (drop_p > 0.f) { q.x *= keep[r][0]; q.y *= keep[r][1]; q.z *= keep[r][2]; q.w *= keep[r][3]; }
+        store4<T>(out_lp + e, q.x, q.y, q.z, q.w);
+        cs.x += q.x; cs.y += q.y; cs.z += q.z; cs.w += q.w;     // bias gradient of the layer that consumes out_lp
+      }
+    }
+  }
+  // this thread's accumulators already hold the CTA's sums for its four columns
+  if (dgamma) red_add4(dgamma + c * 4, dg);
+  if (dbeta) red_add4(dbeta + c * 4, db);
+  if (colsum_out && out_lp) red_add4(colsum_out + c * 4, cs);
+}
+
+int g_sms() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  return sms;
+}
 int ln_blocks(long long rows) {
   long long b = (rows + LN_WARPS - 1) / LN_WARPS;
   return (int)(b < LN_MAX_BLOCKS ? b : LN_MAX_BLOCKS);
@@ -192,6 +365,16 @@ int k_layernorm_fwd(const float* x, const float* gamma, const float* beta, T* y,
                     float eps, cudaStream_t stream) {
   NDT1_REQUIRE(H % 4 == 0 && H <= 128 * LN_MAXV, "layernorm: hidden size %d unsupported (multiple of 4, <= %d)", H, 128 * LN_MAXV);
   if (rows == 0) return 0;
+  if (H % 128 == 0 && H <= 4096) {
+    const int threads = H / 4;
+    long long nb = (rows + LNF_ROWS - 1) / LNF_ROWS;
+    const long long cap = (long long)g_sms() * (threads <= 256 ? 4 : 1);
+    if (nb > cap) nb = cap;
+    if (threads <= 256) ln_fwd_rows_kernel<T, 256><<<(int)nb, threads, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, H, eps);
+    else ln_fwd_rows_kernel<T, 1024><<<(int)nb, threads, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, H, eps);
+    NDT1_CHECK_LAUNCH();
+    return 0;
+  }
   ln_fwd_kernel<T><<<ln_blocks(rows), LN_WARPS * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, H, eps);
   NDT1_CHECK_LAUNCH();
   return 0;
@@ -204,8 +387,21 @@ int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float
   NDT1_REQUIRE(H % 4 == 0 && H <= 128 * LN_MAXV, "layernorm: hidden size %d unsupported (multiple of 4, <= %d)", H, 128 * LN_MAXV);
   if (rows == 0) return 0;
   (void)partials;
-  int sms = 148;
-  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int sms = g_sms();
+  if (H % 128 == 0 && H <= 4096) {
+    const int threads = H / 4;
+    long long nbr = (rows + LNG_ROWS - 1) / LNG_ROWS;
+    const long long cap = (long long)sms * (threads <= 256 ? 2 : 1);
+    if (nbr > cap) nbr = cap;
+    if (threads <= 256)
+      ln_bwd_rows_kernel<T, 256><<<(int)nbr, threads, 0, stream>>>(dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed, stream_id, rows, H,
+                                                                    dgamma, dbeta, out_lp ? colsum_out : nullptr);
+    else
+      ln_bwd_rows_kernel<T, 1024><<<(int)nbr, threads, 0, stream>>>(dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed, stream_id, rows, H,
+                                                                     dgamma, dbeta, out_lp ? colsum_out : nullptr);
+    NDT1_CHECK_LAUNCH();
+    return 0;
+  }
   long long nb = (rows + LNB_WARPS - 1) / LNB_WARPS;
   if (nb > sms) nb = sms;
   const size_t smem = (size_t)LNB_WARPS * 3 * H * sizeof(float);

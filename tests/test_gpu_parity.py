@@ -487,3 +487,88 @@ def test_tensor_core_attention_same_dropout_masks_as_cuda_core_path():
         assert d < 2e-2, float(d)
     zeros_a, zeros_b = (a[4] == 0), (b[4] == 0)
     assert (zeros_a == zeros_b).float().mean() > 0.999          # same output-dropout mask
+
+
+# --------------------------------------------------------------------------- kernels added after the first parity suite
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,L", [(3, 9), (40, 120), (100, 243), (200, 420)])
+def test_ctc_register_sweeps_all_state_counts(S, L):
+    """One warp per sweep keeps 1/2/4/8/16 states per lane depending on the target length: every variant against torch."""
+    torch.manual_seed(S)
+    B, V = 4, 41
+    logits = torch.randn(B, L, V) * 2
+    tl = torch.tensor([S, max(S // 2, 1), 1, S])
+    il = torch.tensor([L, L - 3, L // 2, 2 * S + 1 if 2 * S + 1 <= L else L])
+    tg = torch.randint(1, V, (B, S)) * (torch.arange(S)[None] < tl[:, None])
+    Lb = _C.lib()
+    d = lambda t: t.to(DEV).contiguous()
+    lg, tgd, ild, tld = d(logits), d(tg), d(il), d(tl)
+    logp, dl = torch.empty_like(lg), torch.empty_like(lg)
+    nll, loss = torch.empty(B, device=DEV), torch.zeros((), device=DEV)
+    ws = torch.empty(Lb.ndt1_ctc_workspace_bytes(B, L, S), dtype=torch.uint8, device=DEV)
+    _C.check(Lb.ndt1_ctc_loss(lg.data_ptr(), logp.data_ptr(), tgd.data_ptr(), ild.data_ptr(), tld.data_ptr(), B, L, V, S, 0, 1,
+                              ws.data_ptr(), nll.data_ptr(), loss.data_ptr(), dl.data_ptr(), None, _C.stream_ptr()))
+    x = logits.double().requires_grad_(True)
+    ref = torch.nn.functional.ctc_loss(torch.log_softmax(x, -1).transpose(0, 1), tg, il, tl, blank=0, reduction="none", zero_infinity=True)
+    ref.sum().backward()
+    assert (nll.cpu().double() - ref.detach()).abs().max() <= 1e-4 * max(1.0, float(ref.abs().max()))
+    assert (dl.cpu().double() - x.grad).abs().max() < 5e-5
+
+
+@pytest.mark.gpu
+def test_weight_gradient_stream_changes_nothing():
+    """The backward with its weight gradients on the second stream == everything serialised on one stream."""
+    tr = lb.default_trainer_config()
+    cfg = lb.update_config(tr.model, {"encoder": {"embedder": {"dropout": 0.0}, "transformer": {"dropout": 0.0, "n_layers": 2},
+                                                  "smooth_and_noise": {"noise": False}}})
+    torch.manual_seed(3)
+    model = lb.NDT1(cfg, **tr.method.model_kwargs, precision="bf16").to(DEV).train()
+    batch = cuda_batch(O.synthetic_ctc_batch(B=4, T=400, N=256, seed=2))
+    res = []
+    for on in (1, 0):
+        model.zero_grad(set_to_none=True)
+        out = model(**batch)                                   # creates the engine on first use
+        _C.check(_C.lib().ndt1_engine_set_overlap(model._engine, on))
+        model.zero_grad(set_to_none=True)
+        out = model(**batch)
+        out.loss.backward()
+        torch.cuda.synchronize()
+        res.append((float(out.loss), grads_of(model)))
+    _C.check(_C.lib().ndt1_engine_set_overlap(model._engine, 1))
+    assert res[0][0] == res[1][0]
+    for k, v in res[0][1].items():
+        w = res[1][1][k]
+        # the order of the fp32 red.add of split reductions may differ, and one bias gradient is reduced from the bf16
+        # operand (own kernel on the second stream) instead of inside the producing GEMM's fp32 epilogue
+        assert (v - w).abs().max() <= 2e-3 * max(float(w.abs().max()), 1e-6), k
+
+
+@pytest.mark.gpu
+def test_smooth_noise_vector_kernel_matches_oracle_and_generic_path():
+    """N % 4 == 0 with the reference's 13-tap kernel takes the 128-bit path; N = 18 the generic one; same numbers."""
+    torch.manual_seed(4)
+    cfgd = dict(noise=True, smooth_sd=2, white_noise_sd=1.0, constant_offset_sd=0.2)
+    for N in (256, 20, 18):
+        B, T = 3, 131
+        x = torch.randn(B, T, N)
+        white, offset = torch.randn(B, T, N), torch.randn(B, 1, N)
+        ref = O.smooth_and_noise(x, cfgd, True, {"white": white, "offset": offset})
+        mod = lb.ndt1.SmoothAndNoise(lb.DictConfig(cfgd)).to(DEV).train()
+        out = mod(x.to(DEV), {"white": white.to(DEV), "offset": offset.to(DEV)})
+        assert (out.cpu() - ref).abs().max() < 2e-6, N
+
+
+@pytest.mark.gpu
+def test_layernorm_row_group_kernel_matches_torch():
+    """H % 128 == 0 takes the row-group kernels (4 / 8 rows per CTA); ragged row counts exercise the tail."""
+    Lb = _C.lib()
+    for rows, H in ((7, 1024), (243 * 3 + 1, 1024), (50, 256), (9, 64)):
+        torch.manual_seed(rows)
+        x, g, b = torch.randn(rows, H) * 3 + 1, torch.randn(H), torch.randn(H)
+        ref = torch.nn.functional.layer_norm(x.double(), (H,), g.double(), b.double(), 1e-5)
+        xd, gd, bd = x.to(DEV), g.to(DEV), b.to(DEV)
+        y, mean, rstd = torch.empty_like(xd), torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+        _C.check(Lb.ndt1_layernorm_fwd(xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, H, 1e-5,
+                                       _C.stream_ptr()))
+        assert (y.cpu().double() - ref).abs().max() < 5e-6 * float(ref.abs().max()), (rows, H)
+        assert (mean.cpu() - x.mean(1)).abs().max() < 1e-5
