@@ -17,6 +17,7 @@
 // The mask is the predicate of attention.cu; dropout uses the same
 // element-indexed Philox streams, so both implementations draw identical masks.
 // Other shapes use the CUDA-core kernels of attention.cu.
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "kernels.cuh"
 
@@ -32,7 +33,24 @@ constexpr float kLog2e = 1.4426950408889634f;
 struct TcAttn {
   AttnParams p;
   int cf, cb;
+  unsigned long long* dbg;      // optional phase timeline (tools/attn_timeline.py): 32 slots per CTA, globaltimer ns
 };
+
+__device__ __forceinline__ void dbg_mark(const TcAttn& a, int slot) {
+  if (a.dbg) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+    a.dbg[cta * 32 + slot] = t;
+  }
+}
+__device__ __forceinline__ void dbg_smid(const TcAttn& a, int slot) {
+  if (a.dbg) {
+    unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+    a.dbg[cta * 32 + slot] = sm;
+  }
+}
 
 // ---------------------------------------------------------------------------
 // Small device helpers.  The elementwise part of every kernel is what bounds it (the
@@ -153,12 +171,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
     mbar_wait(&bars[0], 0);
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16(128, 256, false, false);
+    const uint64_t qd = make_sdesc(smem_u32(sQ), 16, 1024), kd = make_sdesc(smem_u32(sKV), 16, 1024);
 #pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
-      const uint64_t ad = make_sdesc(smem_u32(sQ) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-      const uint64_t bd = make_sdesc(smem_u32(sKV) + (ks >> 2) * 32768 + (ks & 3) * 32, 16, 1024);
-      tc_mma_bf16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
-    }
+    for (int ks = 0; ks < HD / 16; ++ks)
+      tc_mma_bf16(tmem, sdesc_advance(qd, (ks >> 2) * 16384 + (ks & 3) * 32), sdesc_advance(kd, (ks >> 2) * 32768 + (ks & 3) * 32), idesc,
+                  ks > 0 ? 1u : 0u);
     tc_commit(&bars[2]);
   }
   __syncwarp();
@@ -237,13 +254,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
     mbar_wait(&bars[1], 0);
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, true);
+    const uint64_t vd = make_sdesc(smem_u32(sKV), 32768, 1024);
     for (int ks = 0; ks < nks; ++ks) {
       const uint32_t pa = tmem + (ks < 8 ? ks * 8 : 128 + (ks - 8) * 8);
-#pragma unroll
-      for (int dh = 0; dh < 2; ++dh) {
-        const uint64_t bd = make_sdesc(smem_u32(sKV) + dh * 32768 + ks * 2048, 32768, 1024);
-        tc_mma_bf16_ts(tmem + (dh ? 192 : 64), pa, bd, idesc, ks > 0 ? 1u : 0u);
-      }
+      tc_mma_bf16_ts(tmem + 64, pa, sdesc_advance(vd, ks * 2048), idesc, ks > 0 ? 1u : 0u);
+      tc_mma_bf16_ts(tmem + 192, pa, sdesc_advance(vd, 32768 + ks * 2048), idesc, ks > 0 ? 1u : 0u);
     }
     tc_commit(&bars[3]);
   }
@@ -574,6 +589,224 @@ attn_tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_c
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// ---------------------------------------------------------------------------
+// backward, key side, pipelined: dK, dV of one 128-key tile accumulated over the queries in chunks of 64.
+// Warp-specialised -- warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: 256 compute threads (lane = key) --
+// and software-pipelined over the chunks: while the compute warps turn S^T / dP^T of chunk c into P~^T / dS^T, the
+// tensor core already forms S^T / dP^T of chunk c + 1 (two accumulator buffers) and TMA fetches chunk c + 2 (three
+// shared-memory stages).  P~^T and dS^T never touch shared memory: they are written back IN PLACE into tensor memory
+// (bf16, two queries per column) and consumed from there as the A operand of the dV / dK products.
+// Tensor memory (512 columns):  buffer b in {0,1}: S^T at [128 b, +64), dP^T at [128 b + 64, +64);
+//   P~^T of the thread that owns query columns [32 h, +32) of the chunk: 16 packed columns at S^T + 32 h (its own
+//   read range); dS^T likewise inside dP^T;   dV at [256, 384), dK at [384, 512).
+// ---------------------------------------------------------------------------
+constexpr int KV2_CH = 64, KV2_STAGES = 3, KV2_CWARPS = 16, KV2_THREADS = 64 + 32 * KV2_CWARPS;
+constexpr int SMEM_BKV2 = 65536 + KV2_STAGES * 32768 + LMAX * 8 + LMAX * 16 + 128 + 1024;
+
+__global__ void __launch_bounds__(KV2_THREADS, 1)   // 18 warps: 5 share a sub-partition -> at most 102 registers per thread
+attn_tc_bwd_kv2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map64,
+                       const __grid_constant__ CUtensorMap mapdo64, const __grid_constant__ CUtensorMap mapdqkv, const TcAttn a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sK = smem;                          // 2 x [128 keys x 64 d]   32 KB
+  uint8_t* sV = sK + 32768;
+  uint8_t* sQ = sV + 32768;                    // stages x { Q chunk 2 x [64 q x 64 d] (16 KB), dO chunk (16 KB) }
+  float2* s_ld = (float2*)(sQ + KV2_STAGES * 32768);       // [LMAX] (lse * log2e, delta) of every query
+  uint32_t* s_bits = (uint32_t*)(s_ld + LMAX);             // [LMAX][4] keep bits (query, 32-key word of this key tile)
+  uint64_t* bars = (uint64_t*)(s_bits + LMAX * 4);
+  uint64_t* kv_full = bars;                    // [1]
+  uint64_t* q_full = bars + 1;                 // [3]
+  uint64_t* q_empty = bars + 4;                // [3]
+  uint64_t* s_full = bars + 7;                 // [2]
+  uint64_t* p_full = bars + 9;                 // [2]
+  uint64_t* acc_done = bars + 11;              // [1]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+
+  const AttnParams& p = a.p;
+  const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * TQ;
+  const int L = p.L, H = p.H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nc = (L + KV2_CH - 1) / KV2_CH;
+  const long long bh0 = ((long long)b * p.nh + h) * L;
+  const bool drop = p.p_attn > 0.f;
+
+  if (tid == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < KV2_STAGES; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], KV2_CWARPS); }
+    mbar_init(acc_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the first loads fly while the CTA stages its per-query scalars and allocates tensor memory
+    mbar_expect_tx(kv_full, 65536);
+    for (int c = 0; c < 2; ++c) tma_load_3d(sK + c * 16384, &map128, kv_full, H + h * HD + 64 * c, k0, b);
+    for (int c = 0; c < 2; ++c) tma_load_3d(sV + c * 16384, &map128, kv_full, 2 * H + h * HD + 64 * c, k0, b);
+    for (int c = 0; c < nc && c < KV2_STAGES; ++c) {
+      uint8_t* dq = sQ + c * 32768;
+      mbar_expect_tx(&q_full[c], 32768);
+      for (int d = 0; d < 2; ++d) tma_load_3d(dq + d * 8192, &map64, &q_full[c], h * HD + 64 * d, c * KV2_CH, b);
+      for (int d = 0; d < 2; ++d) tma_load_3d(dq + 16384 + d * 8192, &mapdo64, &q_full[c], h * HD + 64 * d, c * KV2_CH, b);
+    }
+  }
+  if (tid == 0) { dbg_mark(a, 0); dbg_smid(a, 31); }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (tid == 32) dbg_mark(a, 1);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) dbg_mark(a, 2);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int c = KV2_STAGES; c < nc; ++c) {        // (K, V and the first chunks were issued before the CTA-wide setup)
+        const int st = c % KV2_STAGES;
+        mbar_wait(&q_empty[st], ((c / KV2_STAGES) & 1) ^ 1);
+        uint8_t* dq = sQ + st * 32768;
+        mbar_expect_tx(&q_full[st], 32768);
+        for (int d = 0; d < 2; ++d) tma_load_3d(dq + d * 8192, &map64, &q_full[st], h * HD + 64 * d, c * KV2_CH, b);
+        for (int d = 0; d < 2; ++d) tma_load_3d(dq + 16384 + d * 8192, &mapdo64, &q_full[st], h * HD + 64 * d, c * KV2_CH, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, KV2_CH, false, false);
+      constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, false, true);
+      // descriptors are built once; inside the loops an MMA costs one 64-bit add per operand
+      const uint64_t kd = make_sdesc(smem_u32(sK), 16, 1024), vd = make_sdesc(smem_u32(sV), 16, 1024);
+      auto issue_s = [&](int c) {
+        const int st = c % KV2_STAGES, bf = c & 1;
+        mbar_wait(&q_full[st], (c / KV2_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t qd = make_sdesc(smem_u32(sQ + st * 32768), 16, 1024), dod = sdesc_advance(qd, 16384);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          tc_mma_bf16(tmem + bf * 128, sdesc_advance(kd, (ks >> 2) * 16384 + (ks & 3) * 32), sdesc_advance(qd, (ks >> 2) * 8192 + (ks & 3) * 32),
+                      idesc_s, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          tc_mma_bf16(tmem + bf * 128 + 64, sdesc_advance(vd, (ks >> 2) * 16384 + (ks & 3) * 32),
+                      sdesc_advance(dod, (ks >> 2) * 8192 + (ks & 3) * 32), idesc_s, ks > 0 ? 1u : 0u);
+        tc_commit(&s_full[bf]);
+      };
+      mbar_wait(kv_full, 0);
+      dbg_mark(a, 3);
+      issue_s(0);
+      dbg_mark(a, 4);
+      for (int c = 0; c < nc; ++c) {
+        if (c + 1 < nc) issue_s(c + 1);         // (its accumulator buffer was released by the dV/dK products of chunk c - 1, issued before)
+        dbg_mark(a, 17 + c);
+        const int st = c % KV2_STAGES, bf = c & 1;
+        mbar_wait(&p_full[bf], (c >> 1) & 1);
+        tc_fence_after();
+        dbg_mark(a, 21 + c);
+        const uint64_t qm = make_sdesc(smem_u32(sQ + st * 32768), 8192, 1024), dom = sdesc_advance(qm, 16384);   // MN-major views
+#pragma unroll
+        for (int ks = 0; ks < KV2_CH / 16; ++ks)
+          tc_mma_bf16_ts(tmem + 256, tmem + bf * 128 + 16 * ks, sdesc_advance(dom, ks * 2048), idesc_acc, (c > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < KV2_CH / 16; ++ks)
+          tc_mma_bf16_ts(tmem + 384, tmem + bf * 128 + 64 + 16 * ks, sdesc_advance(qm, ks * 2048), idesc_acc, (c > 0 || ks > 0) ? 1u : 0u);
+        tc_commit(&q_empty[st]);                // the chunk's shared-memory stage is free once these retire
+        dbg_mark(a, 12 + c);
+      }
+      tc_commit(acc_done);
+    }
+  } else {
+    // ===================== compute warps: lane = key, 16 query columns of the chunk per thread =====================
+    const int cw = warp - 2;
+    const int quarter = warp & 3, grp = cw >> 2;             // TMEM lane quarter; which 16 of the chunk's 64 queries
+    const int row = quarter * 32 + lane;
+    const int kj = k0 + row;
+    const bool kv_j = kj < L && p.key_valid[(long long)b * L + kj] != 0;
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    const float sl2 = p.scale * kLog2e;
+    const float ik = drop ? 1.0f / (1.0f - p.p_attn) : 1.f;
+    // Idle until the first S^T arrives: stage the per-query scalars of the WHOLE sequence, and turn the forward's
+    // keep bits (one word per query x 32 keys) into key-major words (this key x 32 queries) with warp ballots.
+    for (int q = tid - 64; q < LMAX; q += 32 * KV2_CWARPS)
+      s_ld[q] = q < L ? make_float2(p.lse[bh0 + q] * kLog2e, p.delta[bh0 + q]) : make_float2(0.f, 0.f);
+    for (int q = tid - 64; q < LMAX; q += 32 * KV2_CWARPS) {   // keep bits (query q, the 128 keys of this tile): 4 words per query
+      uint4 w = make_uint4(~0u, ~0u, ~0u, ~0u);
+      if (drop && q < L) w = *(const uint4*)(p.drop_bits + (bh0 + q) * 8 + (k0 >> 5));
+      *(uint4*)(s_bits + q * 4) = w;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * KV2_CWARPS) : "memory");
+    for (int c = 0; c < nc; ++c) {
+      const int bf = c & 1;
+      const int qb = c * KV2_CH + grp * 16;                  // first query of this thread's columns
+      mbar_wait(&s_full[bf], (c >> 1) & 1);
+      tc_fence_after();
+      if (tid == 64) dbg_mark(a, 5 + c);
+      uint32_t pk[8], dk[8];
+      if (qb < L) {                                          // warp-uniform
+        const uint32_t mw = key_mask_word(kj, qb & ~31, a.cf, a.cb, kv_j, L) >> (qb & 31);
+        uint32_t rs[16], rp[16];
+        tmem_ld16(trow + bf * 128 + grp * 16, rs);
+        tmem_ld16(trow + bf * 128 + 64 + grp * 16, rp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          float pt[2], dst[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float2 ld = s_ld[qb + j + u];
+            const float s = fmaf(__uint_as_float(rs[j + u]), sl2, -ld.x);
+            const float pr = ex2f((mw >> (j + u)) & 1u ? s : -INFINITY);
+            const float dm = (s_bits[(qb + j + u) * 4 + quarter] >> lane) & 1u ? ik : 0.f;
+            pt[u] = pr * dm;
+            dst[u] = pr * p.scale * (__uint_as_float(rp[j + u]) * dm - ld.y);
+          }
+          pk[j >> 1] = pack_bf16x2(pt[0], pt[1]);
+          dk[j >> 1] = pack_bf16x2(dst[0], dst[1]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { pk[j] = 0u; dk[j] = 0u; }
+      }
+      tmem_st8(trow + bf * 128 + grp * 16, pk);               // in place: 8 packed columns inside this thread's own 16
+      tmem_st8(trow + bf * 128 + 64 + grp * 16, dk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[bf]);
+    }
+    // ---- epilogue: dV (cols 256..), dK (cols 384..) -> global
+    if (tid == 64) dbg_mark(a, 9);
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    if (tid == 64) dbg_mark(a, 10);
+    // K and V are dead: their buffers stage dK / dV as SWIZZLE_128B tiles for two bulk tensor stores (coalesced, asynchronous,
+    // rows past the sequence end clipped by the tensor map)
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const int c0 = grp * 32;
+      uint32_t r0[32];
+      tmem_ld32(trow + 256 + which * 128 + c0, r0);
+      tmem_ld_wait();
+      uint8_t* tile = which == 0 ? sV : sK;                  // dV over V's buffer, dK over K's
+#pragma unroll
+      for (int g = 0; g < 4; ++g) st_row8(tile, row, c0 + g * 8, (const float*)r0 + g * 8);
+    }
+    fence_async_smem();
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * KV2_CWARPS) : "memory");
+    if (tid == 64) {
+      for (int c = 0; c < 2; ++c) {
+        tma_store_3d(&mapdqkv, sV + c * 16384, 2 * H + h * HD + 64 * c, k0, b);
+        tma_store_3d(&mapdqkv, sK + c * 16384, H + h * HD + 64 * c, k0, b);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    if (tid == 64) dbg_mark(a, 11);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (tid == 32) dbg_mark(a, 16);
+}
+
 int make_maps(const AttnParams& p, CUtensorMap* m128, CUtensorMap* m256, CUtensorMap* mdo) {
   GemmOperand q; q.ptr = p.qkv; q.batch_stride = (long long)p.L * 3 * p.H; q.nbatch = p.B; q.rows = p.L; q.cols = 3 * p.H; q.ld = 3 * p.H;
   NDT1_TRY(tc_make_map(q, 64, 128, m128));
@@ -585,11 +818,14 @@ int make_maps(const AttnParams& p, CUtensorMap* m128, CUtensorMap* m256, CUtenso
   return 0;
 }
 
+unsigned long long* g_attn_dbg = nullptr;
 constexpr int SMEM_FWD = 32768 + 65536 + 2048 + 32 + 64 + 1024;
 constexpr int SMEM_BQ = 32768 * 2 + 65536 * 2 + 32 + 64 + 1024;
 constexpr int SMEM_BKV = 32768 * 6 + 1024 + 2048 + 64 + 1024;
 
 }  // namespace
+
+void k_attention_tc_set_timeline(unsigned long long* buf) { g_attn_dbg = buf; }
 
 bool k_attention_tc_supported(const AttnParams& p) { return p.hd == HD && p.L <= LMAX && p.L >= 1 && p.H % 8 == 0; }
 
@@ -600,7 +836,7 @@ int k_attention_tc_fwd(const AttnParams& p, cudaStream_t stream) {
   NDT1_TRY(make_maps(p, &m128, &m256, nullptr));
   static bool attr = false;
   if (!attr) { NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD)); attr = true; }
-  TcAttn a; a.p = p; a.cf = p.ctx_fwd; a.cb = p.ctx_bwd;
+  TcAttn a; a.p = p; a.cf = p.ctx_fwd; a.cb = p.ctx_bwd; a.dbg = g_attn_dbg;
   dim3 grid(ndt1_cdiv(p.L, TQ), p.nh, p.B);
   attn_tc_fwd_kernel<<<grid, NTHREADS, SMEM_FWD, stream>>>(m128, m256, a);
   NDT1_CHECK_LAUNCH();
@@ -616,12 +852,26 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream) {
   if (!attr) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BQ));
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV));
+    NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV2));
     attr = true;
   }
   NDT1_TRY(k_attention_delta<bf16>(p, stream));
-  TcAttn a; a.p = p; a.cf = p.ctx_fwd; a.cb = p.ctx_bwd;
+  TcAttn a; a.p = p; a.cf = p.ctx_fwd; a.cb = p.ctx_bwd; a.dbg = g_attn_dbg;
   dim3 grid(ndt1_cdiv(p.L, TQ), p.nh, p.B);
-  attn_tc_bwd_kv_kernel<<<grid, NTHREADS, SMEM_BKV, stream>>>(m128, mdo, a);
+  static const bool old_kv = getenv("NDT1_ATTN_BWD_KV1") && getenv("NDT1_ATTN_BWD_KV1")[0] == '1';
+  if (old_kv) {
+    attn_tc_bwd_kv_kernel<<<grid, NTHREADS, SMEM_BKV, stream>>>(m128, mdo, a);
+  } else {
+    CUtensorMap m64, mdo64;
+    GemmOperand q; q.ptr = p.qkv; q.batch_stride = (long long)p.L * 3 * p.H; q.nbatch = p.B; q.rows = p.L; q.cols = 3 * p.H; q.ld = 3 * p.H;
+    GemmOperand d; d.ptr = p.dout; d.batch_stride = (long long)p.L * p.H; d.nbatch = p.B; d.rows = p.L; d.cols = p.H; d.ld = p.H;
+    NDT1_TRY(tc_make_map(q, 64, KV2_CH, &m64));
+    NDT1_TRY(tc_make_map(d, 64, KV2_CH, &mdo64));
+    CUtensorMap mdq;
+    GemmOperand g; g.ptr = p.dqkv; g.batch_stride = (long long)p.L * 3 * p.H; g.nbatch = p.B; g.rows = p.L; g.cols = 3 * p.H; g.ld = 3 * p.H;
+    NDT1_TRY(tc_make_map(g, 64, 128, &mdq));
+    attn_tc_bwd_kv2_kernel<<<grid, KV2_THREADS, SMEM_BKV2, stream>>>(m128, m64, mdo64, mdq, a);
+  }
   NDT1_CHECK_LAUNCH();
   attn_tc_bwd_q_kernel<<<grid, NTHREADS, SMEM_BQ, stream>>>(m128, m256, mdo, a);
   NDT1_CHECK_LAUNCH();

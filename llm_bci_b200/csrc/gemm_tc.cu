@@ -463,14 +463,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
+          // one descriptor per operand and k-block; the four k-steps advance it with a 64-bit add
+          const uint64_t ad0 = A_MN ? make_sdesc(sa, 64 * BK * 2, 1024) : make_sdesc(sa, 16, 1024);
+          const uint64_t bd0 = B_MN ? make_sdesc(sb, 64 * BK * 2, 1024) : make_sdesc(sb, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = A_MN ? make_sdesc(sa + k * (16 * 128), 64 * BK * 2, 1024)
-                                        : make_sdesc(sa + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? make_sdesc(sb + k * (16 * 128), 64 * BK * 2, 1024)
-                                        : make_sdesc(sb + k * 32, 16, 1024);
-            tc_mma_bf16_g<CTAS>(tmem_d, adesc, bdesc, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_bf16_g<CTAS>(tmem_d, sdesc_advance(ad0, A_MN ? k * (16 * 128) : k * 32), sdesc_advance(bd0, B_MN ? k * (16 * 128) : k * 32), IDESC,
+                                (kb > kb0 || k > 0) ? 1u : 0u);
           tc_commit_g<CTAS>(&empty_bar[stage]);     // frees the smem slot (in both CTAs) when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

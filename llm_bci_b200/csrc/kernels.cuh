@@ -75,6 +75,7 @@ template <typename T> int k_attention_delta(const AttnParams& p, cudaStream_t st
 bool k_attention_tc_supported(const AttnParams& p);
 int k_attention_tc_fwd(const AttnParams& p, cudaStream_t stream);
 int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream);
+void k_attention_tc_set_timeline(unsigned long long* buf);   // debugging: per-CTA phase timestamps (32 u64 per CTA), null = off
 
 // ctc.cu
 int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaStream_t stream, int ld_in = 0);   // ld_in: row stride of logits (0 = V)
