@@ -132,7 +132,8 @@ __device__ __forceinline__ void st_global8(bf16* dst, const float* v) {
 // P never touches shared memory: the P V product takes its A operand from tensor memory.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 2)
-attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map256, const TcAttn a) {
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map256,
+                   const __grid_constant__ CUtensorMap mapo, const __grid_constant__ CUtensorMap mapod, const TcAttn a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                 // 2 x [128 x 64]   32 KB
@@ -269,70 +270,95 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   const float inv = (l > 0.f) ? 1.f / l : 0.f;
   const uint32_t thr_o = drop_threshold(p.p_out);
   const float iko = p.p_out > 0.f ? 1.0f / (1.0f - p.p_out) : 1.f;
+  // V is dead: its buffer stages the output tile (and its dropped copy) as SWIZZLE_128B tiles for bulk tensor stores
+  // (coalesced, asynchronous; rows past the sequence end are clipped by the tensor map)
+  uint8_t* sOut = sKV; uint8_t* sOutD = sKV + 32768;
+  const bool two = p.out_drop != p.out;
 #pragma unroll 1
   for (int cc = 0; cc < 2; ++cc) {
     const int c0 = half * 64 + cc * 32;               // head-dim column
     uint32_t raw[32];
     tmem_ld32(trow + (half ? 192 : 64) + cc * 32, raw);
     tmem_ld_wait();
-    if (qi < L) {
-      const long long o = ((long long)b * L + qi) * H + h * HD + c0;
+    const long long o = ((long long)b * L + qi) * H + h * HD + c0;    // element index of the dropout stream
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float v[8];
+    for (int g = 0; g < 4; ++g) {
+      float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g * 8 + i]) * inv;
-        st_global8((bf16*)p.out + o + g * 8, v);
-        if (p.p_out > 0.f) {
-          float ds[8];
-          drop_scale_8(p.seed, p.stream_out, (unsigned long long)(o + g * 8), thr_o, iko, ds);
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g * 8 + i]) * inv;
+      st_row8(sOut, row, c0 + g * 8, v);
+      if (p.p_out > 0.f) {
+        float ds[8];
+        drop_scale_8(p.seed, p.stream_out, (unsigned long long)(o + g * 8), thr_o, iko, ds);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] *= ds[i];
-          st_global8((bf16*)p.out_drop + o + g * 8, v);
-        } else if (p.out_drop != p.out) {
-          st_global8((bf16*)p.out_drop + o + g * 8, v);
-        }
+        for (int i = 0; i < 8; ++i) v[i] *= ds[i];
       }
+      if (two) st_row8(sOutD, row, c0 + g * 8, v);
     }
   }
+  fence_async_smem();
   if (half == 0 && qi < L) p.lse[bh_row] = m * p.scale + logf(l);
   tc_fence_before();
   __syncthreads();
+  if (tid == 32) {
+    for (int c = 0; c < 2; ++c) {
+      tma_store_3d(&mapo, sOut + c * 16384, h * HD + 64 * c, q0, b);
+      if (two) tma_store_3d(&mapod, sOutD + c * 16384, h * HD + 64 * c, q0, b);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 // ---------------------------------------------------------------------------
-// backward, query side: dQ
+// backward, query side: dQ of one 128-query tile against all (<= 256) keys.
+// 512 threads: warp w owns TMEM lanes 32*(w%4).. (one query row per lane) and the 64 key columns [64*(w/4), +64).
+//   S = Q K^T -> columns [0,256), dP = dO V^T -> columns [256,512)   (two 128 x 256 x 16 MMAs per k-step: the largest
+//   shape per instruction -- a tcgen05.mma costs ~60 ns to issue whatever its N);
+//   dS = P (dP dm - delta) scale goes back IN PLACE as bf16 (two keys per column) into the first 32 columns of each
+//   thread's own 64-column range of S; dQ = dS K takes it from tensor memory and accumulates over [256,384) (dP is dead);
+//   the tile leaves through shared memory (Q's buffer) and one bulk tensor store.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1)
+constexpr int BQ_THREADS = 512;
+__global__ void __launch_bounds__(BQ_THREADS, 1)
 attn_tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map256,
-                     const __grid_constant__ CUtensorMap mapdo, const TcAttn a) {
+                     const __grid_constant__ CUtensorMap mapdo, const __grid_constant__ CUtensorMap mapo,
+                     const __grid_constant__ CUtensorMap mapdqkv, const TcAttn a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sQ = smem;                 // 32 KB
-  uint8_t* sdO = sQ + 32768;          // 32 KB   (sQ+sdO later: dS as 4 x [128 x 64])
+  uint8_t* sQ = smem;                 // 32 KB   (later: the dQ tile for the bulk store)
+  uint8_t* sdO = sQ + 32768;          // 32 KB
   uint8_t* sK = sdO + 32768;          // 64 KB
   uint8_t* sV = sK + 65536;           // 64 KB
-  uint8_t* sdS = sQ;
-  uint32_t* s_kvw = (uint32_t*)(sV + 65536);  // [8]
-  uint64_t* bars = (uint64_t*)(s_kvw + 8);    // loads, s, o
+  uint8_t* sO = sV + 65536;           // 32 KB   forward output of the tile: delta = rowsum(dO * O) is formed here, not by a kernel of its own
+  float* s_part = (float*)sQ;                 // [4][128] partial row sums (Q is dead by the time they are formed)
+  uint32_t* s_kvw = (uint32_t*)(sO + 32768);  // [8]
+  uint64_t* bars = (uint64_t*)(s_kvw + 8);    // qk, dov, s, o
   uint32_t* tmem_slot = (uint32_t*)(bars + 4);
 
   const AttnParams& p = a.p;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
   const int L = p.L, H = p.H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, half = warp >> 2;
-  {
+  const int quarter = warp & 3, grp = warp >> 2;          // grp: which 64 of the 256 key columns
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&bars[0], 32768 + 65536);               // the loads fly while the CTA sets itself up
+    for (int c = 0; c < 2; ++c) tma_load_3d(sQ + c * 16384, &map128, &bars[0], h * HD + 64 * c, q0, b);
+    for (int c = 0; c < 2; ++c) tma_load_3d(sK + c * 32768, &map256, &bars[0], H + h * HD + 64 * c, 0, b);
+    mbar_expect_tx(&bars[1], 32768 + 65536 + 32768);
+    for (int c = 0; c < 2; ++c) tma_load_3d(sdO + c * 16384, &mapdo, &bars[1], h * HD + 64 * c, q0, b);
+    for (int c = 0; c < 2; ++c) tma_load_3d(sV + c * 32768, &map256, &bars[1], 2 * H + h * HD + 64 * c, 0, b);
+    for (int c = 0; c < 2; ++c) tma_load_3d(sO + c * 16384, &mapo, &bars[1], h * HD + 64 * c, q0, b);
+  }
+  if (warp < 8) {
     const int j = warp * 32 + lane;
     const uint32_t w = __ballot_sync(0xffffffffu, j < L && p.key_valid[(long long)b * L + j] != 0);
     if (lane == 0) s_kvw[warp] = w;
   }
-  if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -340,99 +366,119 @@ attn_tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
   const int nks = (L + 15) / 16;
 
   if (tid == 0) {
-    mbar_expect_tx(&bars[0], 32768 * 2 + 65536 * 2);
-    for (int c = 0; c < 2; ++c) tma_load_3d(sQ + c * 16384, &map128, &bars[0], h * HD + 64 * c, q0, b);
-    for (int c = 0; c < 2; ++c) tma_load_3d(sdO + c * 16384, &mapdo, &bars[0], h * HD + 64 * c, q0, b);
-    for (int c = 0; c < 2; ++c) tma_load_3d(sK + c * 32768, &map256, &bars[0], H + h * HD + 64 * c, 0, b);
-    for (int c = 0; c < 2; ++c) tma_load_3d(sV + c * 32768, &map256, &bars[0], 2 * H + h * HD + 64 * c, 0, b);
+    constexpr uint32_t idesc = make_idesc_bf16(128, 256, false, false);
+    const uint64_t qd = make_sdesc(smem_u32(sQ), 16, 1024), kd = make_sdesc(smem_u32(sK), 16, 1024);
+    const uint64_t od = make_sdesc(smem_u32(sdO), 16, 1024), vd = make_sdesc(smem_u32(sV), 16, 1024);
     mbar_wait(&bars[0], 0);
     tc_fence_after();
-    constexpr uint32_t idesc = make_idesc_bf16(128, 256, false, false);
 #pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
-      const uint32_t ko = (ks >> 2) * 32768 + (ks & 3) * 32, qo = (ks >> 2) * 16384 + (ks & 3) * 32;
-      tc_mma_bf16(tmem, make_sdesc(smem_u32(sQ) + qo, 16, 1024), make_sdesc(smem_u32(sK) + ko, 16, 1024), idesc, ks > 0 ? 1u : 0u);
-    }
+    for (int ks = 0; ks < HD / 16; ++ks)
+      tc_mma_bf16(tmem, sdesc_advance(qd, (ks >> 2) * 16384 + (ks & 3) * 32), sdesc_advance(kd, (ks >> 2) * 32768 + (ks & 3) * 32), idesc, ks > 0 ? 1u : 0u);
+    mbar_wait(&bars[1], 0);
+    tc_fence_after();
 #pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
-      const uint32_t ko = (ks >> 2) * 32768 + (ks & 3) * 32, qo = (ks >> 2) * 16384 + (ks & 3) * 32;
-      tc_mma_bf16(tmem + 256, make_sdesc(smem_u32(sdO) + qo, 16, 1024), make_sdesc(smem_u32(sV) + ko, 16, 1024), idesc, ks > 0 ? 1u : 0u);
-    }
-    tc_commit(&bars[1]);
+    for (int ks = 0; ks < HD / 16; ++ks)
+      tc_mma_bf16(tmem + 256, sdesc_advance(od, (ks >> 2) * 16384 + (ks & 3) * 32), sdesc_advance(vd, (ks >> 2) * 32768 + (ks & 3) * 32), idesc,
+                  ks > 0 ? 1u : 0u);
+    tc_commit(&bars[2]);
   }
   __syncwarp();
 
   const int row = quarter * 32 + lane;
   const int qi = q0 + row;
-  const int cbase = half * 128;
+  const int cbase = grp * 64;
   const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
   const float sl2 = p.scale * kLog2e;
   const long long bh_row = ((long long)b * p.nh + h) * L + qi;
   const float lse2 = qi < L ? p.lse[bh_row] * kLog2e : 0.f;
-  const float del = qi < L ? p.delta[bh_row] : 0.f;
   const bool drop = p.p_attn > 0.f;
   const float ik = drop ? 1.0f / (1.0f - p.p_attn) : 1.f;
-  uint32_t mw[4], kw[4];
+  uint32_t mw[2], kw[2];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     const int c0 = cbase + 32 * c;
-    mw[c] = query_mask_word(qi, c0, a.cf, a.cb, s_kvw[half * 4 + c], L);
+    mw[c] = query_mask_word(qi, c0, a.cf, a.cb, s_kvw[grp * 2 + c], L);
     kw[c] = (drop && qi < L && c0 < L) ? p.drop_bits[bh_row * 8 + (c0 >> 5)] : 0xFFFFFFFFu;
   }
-  mbar_wait(&bars[1], 0);
+  mbar_wait(&bars[2], 0);
   tc_fence_after();
+  // delta[row] = sum_d dO[row, d] * O[row, d] from the two tiles in shared memory (after S and dP: Q's buffer, now dead, carries the partial sums):
+  // the four threads of a row (grp 0..3) take 32 head-dim columns each and meet through s_part
+  float del;
+  {
+    float acc = 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+    for (int g = 0; g < 4; ++g) {
+      const int col = grp * 32 + g * 8;
+      const uint32_t off = (uint32_t)((col >> 6) * 16384 + row * 128 + (((((col & 63) >> 3) ^ row) & 7) << 4));
+      const uint4 x = *(const uint4*)(sdO + off), y = *(const uint4*)(sO + off);
+      const __nv_bfloat162* xa = (const __nv_bfloat162*)&x; const __nv_bfloat162* ya = (const __nv_bfloat162*)&y;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc += __low2float(xa[i]) * __low2float(ya[i]) + __high2float(xa[i]) * __high2float(ya[i]);
+    }
+    s_part[grp * 128 + row] = acc;
+    __syncthreads();
+    del = s_part[row] + s_part[128 + row] + s_part[256 + row] + s_part[384 + row];
+    if (grp == 0 && qi < L) p.delta[bh_row] = del;          // the key-side kernel (launched after this one) reads it
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
     const int c0 = cbase + 32 * c;
-    if (c0 < L) {
+    uint32_t ds[16];
+    if (c0 < L) {                                            // warp-uniform
       uint32_t rs[32], rp[32];
       tmem_ld32(trow + c0, rs);
       tmem_ld32(trow + 256 + c0, rp);
       tmem_ld_wait();
+      const uint32_t m = mw[c], k = kw[c];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float ds[8];
+      for (int j = 0; j < 32; j += 2) {
+        float v[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = g * 8 + i;
-          const float s = fmaf(__uint_as_float(rs[j]), sl2, -lse2);
-          const float pr = ex2f((mw[c] >> j) & 1u ? s : -INFINITY) * p.scale;
-          const float t = (kw[c] >> j) & 1u ? __uint_as_float(rp[j]) * ik : 0.f;
-          ds[i] = pr * (t - del);
+        for (int u = 0; u < 2; ++u) {
+          const float sv = fmaf(__uint_as_float(rs[j + u]), sl2, -lse2);
+          const float pr = ex2f((m >> (j + u)) & 1u ? sv : -INFINITY) * p.scale;
+          const float t = (k >> (j + u)) & 1u ? __uint_as_float(rp[j + u]) * ik : 0.f;
+          v[u] = pr * (t - del);
         }
-        st_row8(sdS, row, c0 + g * 8, ds);
+        ds[j >> 1] = pack_bf16x2(v[0], v[1]);
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ds[j] = 0u;
     }
+    if (c0 < nks * 16) tmem_st16(trow + cbase + 16 * c, ds);   // keys [c0, c0+32) -> 16 packed columns inside this thread's own range
   }
-  fence_async_smem();
+  tmem_st_wait();
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
-    for (int ks = 0; ks < nks; ++ks)
-      tc_mma_bf16(tmem, make_sdesc(smem_u32(sdS) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                  make_sdesc(smem_u32(sK) + ks * 2048, 32768, 1024), idesc, ks > 0 ? 1u : 0u);
-    tc_commit(&bars[2]);
+    const uint64_t km = make_sdesc(smem_u32(sK), 32768, 1024);          // K as the MN-major operand (rows = keys)
+    for (int ks = 0; ks < nks; ++ks)                                    // 16 keys = 8 packed columns: group ks / 4, offset 8 (ks % 4)
+      tc_mma_bf16_ts(tmem + 256, tmem + (ks >> 2) * 64 + (ks & 3) * 8, sdesc_advance(km, ks * 2048), idesc, ks > 0 ? 1u : 0u);
+    tc_commit(&bars[3]);
   }
   __syncwarp();
-  mbar_wait(&bars[2], 0);
+  mbar_wait(&bars[3], 0);
   tc_fence_after();
-#pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    const int c0 = half * 64 + cc * 32;
-    uint32_t raw[32];
-    tmem_ld32(trow + c0, raw);
+  {
+    uint32_t raw[32];                                        // this thread: row `row`, head-dim columns [32 grp, +32)
+    tmem_ld32(trow + 256 + grp * 32, raw);
     tmem_ld_wait();
-    if (qi < L) {
-      bf16* o = (bf16*)p.dqkv + ((long long)b * L + qi) * 3 * H + h * HD + c0;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) st_global8(o + g * 8, (const float*)raw + g * 8);
-    }
+    for (int g = 0; g < 4; ++g) st_row8(sQ, row, grp * 32 + g * 8, (const float*)raw + g * 8);
   }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (tid == 0) {
+    for (int c = 0; c < 2; ++c) tma_store_3d(&mapdqkv, sQ + c * 16384, h * HD + 64 * c, q0, b);   // rows past the sequence end are clipped
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ---------------------------------------------------------------------------
@@ -820,7 +866,7 @@ int make_maps(const AttnParams& p, CUtensorMap* m128, CUtensorMap* m256, CUtenso
 
 unsigned long long* g_attn_dbg = nullptr;
 constexpr int SMEM_FWD = 32768 + 65536 + 2048 + 32 + 64 + 1024;
-constexpr int SMEM_BQ = 32768 * 2 + 65536 * 2 + 32 + 64 + 1024;
+constexpr int SMEM_BQ = 32768 * 2 + 65536 * 2 + 32768 + 32 + 64 + 1024;
 constexpr int SMEM_BKV = 32768 * 6 + 1024 + 2048 + 64 + 1024;
 
 }  // namespace
@@ -838,7 +884,12 @@ int k_attention_tc_fwd(const AttnParams& p, cudaStream_t stream) {
   if (!attr) { NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD)); attr = true; }
   TcAttn a; a.p = p; a.cf = p.ctx_fwd; a.cb = p.ctx_bwd; a.dbg = g_attn_dbg;
   dim3 grid(ndt1_cdiv(p.L, TQ), p.nh, p.B);
-  attn_tc_fwd_kernel<<<grid, NTHREADS, SMEM_FWD, stream>>>(m128, m256, a);
+  GemmOperand o; o.ptr = p.out; o.batch_stride = (long long)p.L * p.H; o.nbatch = p.B; o.rows = p.L; o.cols = p.H; o.ld = p.H;
+  GemmOperand od = o; od.ptr = p.out_drop;
+  CUtensorMap mo, mod;
+  NDT1_TRY(tc_make_map(o, 64, 128, &mo));
+  NDT1_TRY(tc_make_map(od, 64, 128, &mod));
+  attn_tc_fwd_kernel<<<grid, NTHREADS, SMEM_FWD, stream>>>(m128, m256, mo, mod, a);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -855,25 +906,27 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV2));
     attr = true;
   }
-  NDT1_TRY(k_attention_delta<bf16>(p, stream));
   TcAttn a; a.p = p; a.cf = p.ctx_fwd; a.cb = p.ctx_bwd; a.dbg = g_attn_dbg;
   dim3 grid(ndt1_cdiv(p.L, TQ), p.nh, p.B);
+  GemmOperand g; g.ptr = p.dqkv; g.batch_stride = (long long)p.L * 3 * p.H; g.nbatch = p.B; g.rows = p.L; g.cols = 3 * p.H; g.ld = 3 * p.H;
+  GemmOperand q; q.ptr = p.qkv; q.batch_stride = (long long)p.L * 3 * p.H; q.nbatch = p.B; q.rows = p.L; q.cols = 3 * p.H; q.ld = 3 * p.H;
+  GemmOperand d; d.ptr = p.dout; d.batch_stride = (long long)p.L * p.H; d.nbatch = p.B; d.rows = p.L; d.cols = p.H; d.ld = p.H;
+  GemmOperand o; o.ptr = p.out; o.batch_stride = (long long)p.L * p.H; o.nbatch = p.B; o.rows = p.L; o.cols = p.H; o.ld = p.H;
+  CUtensorMap mdq, mo;
+  NDT1_TRY(tc_make_map(g, 64, 128, &mdq));
+  NDT1_TRY(tc_make_map(o, 64, 128, &mo));
+  // query side first: it also forms delta = rowsum(dO * O), which the key side reads
+  attn_tc_bwd_q_kernel<<<grid, BQ_THREADS, SMEM_BQ, stream>>>(m128, m256, mdo, mo, mdq, a);
+  NDT1_CHECK_LAUNCH();
   static const bool old_kv = getenv("NDT1_ATTN_BWD_KV1") && getenv("NDT1_ATTN_BWD_KV1")[0] == '1';
   if (old_kv) {
     attn_tc_bwd_kv_kernel<<<grid, NTHREADS, SMEM_BKV, stream>>>(m128, mdo, a);
   } else {
     CUtensorMap m64, mdo64;
-    GemmOperand q; q.ptr = p.qkv; q.batch_stride = (long long)p.L * 3 * p.H; q.nbatch = p.B; q.rows = p.L; q.cols = 3 * p.H; q.ld = 3 * p.H;
-    GemmOperand d; d.ptr = p.dout; d.batch_stride = (long long)p.L * p.H; d.nbatch = p.B; d.rows = p.L; d.cols = p.H; d.ld = p.H;
     NDT1_TRY(tc_make_map(q, 64, KV2_CH, &m64));
     NDT1_TRY(tc_make_map(d, 64, KV2_CH, &mdo64));
-    CUtensorMap mdq;
-    GemmOperand g; g.ptr = p.dqkv; g.batch_stride = (long long)p.L * 3 * p.H; g.nbatch = p.B; g.rows = p.L; g.cols = 3 * p.H; g.ld = 3 * p.H;
-    NDT1_TRY(tc_make_map(g, 64, 128, &mdq));
     attn_tc_bwd_kv2_kernel<<<grid, KV2_THREADS, SMEM_BKV2, stream>>>(m128, m64, mdo64, mdq, a);
   }
-  NDT1_CHECK_LAUNCH();
-  attn_tc_bwd_q_kernel<<<grid, NTHREADS, SMEM_BQ, stream>>>(m128, m256, mdo, a);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
