@@ -116,6 +116,11 @@ int ndt1_attention_bf16(const void* qkv, void* out, void* out_drop, float* lse, 
 /* torch.optim.AdamW step on one flat buffer, models/trainer.py:229,340. */
 int ndt1_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* The same update in one pass that also (optionally) writes the bf16 shadow of the parameters (see
+ * ndt1_engine_set_weight_shadow) and clears the gradient for the next step (optimizer.zero_grad, trainer.py:343). */
+int ndt1_adamw_step_fused(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, int step, float grad_scale, void* shadow_bf16, int zero_grad,
+                          void* stream);
 
 /* ------------------------------------------------------------------------
  * The encoder + head engine: everything of NDT1.forward after the masker
@@ -205,6 +210,11 @@ int ndt1_engine_backward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_
  * chain (joined before ndt1_engine_backward's work on `stream` ends).  on = 0 serialises everything on `stream`
  * (used to time single kernels); default 1, or 0 when NDT1_OVERLAP=0 is set at engine creation. */
 int ndt1_engine_set_overlap(ndt1_engine* e, int on);
+/* bf16 mode: the caller keeps a bf16 copy (`shadow_bf16`, n elements, same offsets) of the flat fp32 arena its
+ * parameters live in (`params_fp32`) -- ndt1_adamw_step_fused writes it -- so the forward reads the weights from there
+ * instead of casting them every step.  Weights outside the arena, or a NULL shadow, use the per-forward cast.  The caller
+ * guarantees the shadow matches the parameters whenever ndt1_engine_forward runs. */
+int ndt1_engine_set_weight_shadow(ndt1_engine* e, const float* params_fp32, const void* shadow_bf16, int64_t n);
 /* Gradient stages of the last backward in completion order: 0 = decoder + out_norm,
  * 1..n_layers = layers n_layers-1..0, n_layers+1 = embedder.  ndt1_engine_wait_stage makes
  * `stream` wait (cudaStreamWaitEvent) until that stage's gradients are final, so a bucketed

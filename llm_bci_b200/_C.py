@@ -88,6 +88,8 @@ PROTOTYPES = {
     "ndt1_engine_backward": (_i, [_p, C.POINTER(Tensors), C.POINTER(Tensors), _p, _p]),
     "ndt1_engine_launch_count": (_i64, [_p]),
     "ndt1_engine_set_overlap": (_i, [_p, _i]),
+    "ndt1_engine_set_weight_shadow": (_i, [_p, _p, _p, _i64]),
+    "ndt1_adamw_step_fused": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _p, _i, _p]),
     "ndt1_debug_attention_timeline": (_i, [_p]),
     "ndt1_engine_stage_count": (_i, [_p]),
     "ndt1_engine_wait_stage": (_i, [_p, _i, _p]),

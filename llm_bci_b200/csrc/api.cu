@@ -114,6 +114,12 @@ int ndt1_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
   return k_adamw(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream);
 }
 
+int ndt1_adamw_step_fused(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int step, float grad_scale, void* shadow_bf16, int zero_grad, void* stream) {
+  return k_adamw_fused(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (bf16*)shadow_bf16,
+                       zero_grad, (cudaStream_t)stream);
+}
+
 namespace {
 __global__ void dropout_scales_kernel(float* out, long long n, float p, unsigned long long seed, unsigned long long site) {
   const uint32_t thr = drop_threshold(p);

@@ -681,6 +681,50 @@ int k_adamw(float* p, const float* g, float* m, float* v, long long n, float lr,
   return 0;
 }
 
+// One pass over the flat arenas, four parameters per thread: AdamW + bf16 shadow of the new weights + gradient reset.
+namespace {
+__global__ void __launch_bounds__(256) adamw_fused_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                                                          float4* __restrict__ v, long long n4, float lr, float b1, float b2, float eps,
+                                                          float wd, float bc1, float rbc2, float gscale, uint2* __restrict__ shadow, int zero_grad) {
+  const float decay = 1.f - lr * wd, step = lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = g[i], m4 = m[i], v4 = v[i];
+    float4 p4 = p[i];
+    float4 mo, vo;
+#define NDT1_ADAM1(c)                                                       \
+    {                                                                       \
+      const float gi = g4.c * gscale;                                       \
+      mo.c = b1 * m4.c + (1.f - b1) * gi;                                   \
+      vo.c = b2 * v4.c + (1.f - b2) * gi * gi;                              \
+      p4.c = p4.c * decay - step * (mo.c / (sqrtf(vo.c) * rbc2 + eps));     \
+    }
+    NDT1_ADAM1(x) NDT1_ADAM1(y) NDT1_ADAM1(z) NDT1_ADAM1(w)
+#undef NDT1_ADAM1
+    m[i] = mo; v[i] = vo; p[i] = p4;
+    if (shadow) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(p4.x, p4.y), b = __floats2bfloat162_rn(p4.z, p4.w);
+      uint2 o; o.x = *(uint32_t*)&a; o.y = *(uint32_t*)&b;
+      shadow[i] = o;
+    }
+    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+}  // namespace
+
+int k_adamw_fused(float* p, float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd, int step,
+                  float gscale, bf16* shadow, int zero_grad, cudaStream_t stream) {
+  if (n == 0) return 0;
+  NDT1_REQUIRE(n % 4 == 0 && (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)shadow & 7) == 0,
+               "adamw_fused: the arenas must be 16-byte aligned and a multiple of 4 elements long");
+  const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+  const long long n4 = n / 4;
+  const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  adamw_fused_kernel<<<blocks, 256, 0, stream>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, lr, b1, b2, eps, wd, bc1,
+                                                 1.0f / sqrtf(bc2), gscale, (uint2*)shadow, zero_grad);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+
 // ===========================================================================
 // Small index kernels of the embedding layer
 // ===========================================================================

@@ -44,6 +44,7 @@ struct ndt1_engine {
   long long launches = 0;
   cudaEvent_t stage_ev[NDT1_MAX_LAYERS + 2] = {};   // gradient stages of the last backward, in completion order
   int overlap = 1;              // weight gradients on a second stream, concurrent with the data-gradient chain
+  const float* shadow_src = nullptr; const void* shadow_bf16 = nullptr; long long shadow_n = 0;   // caller-maintained bf16 copy of its parameter arena
   int n_stages() const { return c.n_layers + 2; }
   virtual ~ndt1_engine() {}
   virtual int forward(const ndt1_tensors* P, const ndt1_batch* b, const ndt1_outputs* o, cudaStream_t s) = 0;
@@ -86,6 +87,10 @@ struct Engine : ndt1_engine {
   // bf16 weight copies
   bf16* w_emb = nullptr; bf16* w_proj = nullptr; bf16* w_fac = nullptr; bf16* w_dec = nullptr;
   std::vector<bf16*> w_qkv, w_o, w_up, w_down;
+  // the bf16 weights the GEMMs actually read: the engine's own copies (cast per forward) or, when the caller keeps a bf16
+  // shadow of its flat fp32 parameter arena up to date (ndt1_engine_set_weight_shadow), pointers into that shadow
+  const bf16* u_emb = nullptr; const bf16* u_proj = nullptr; const bf16* u_fac = nullptr; const bf16* u_dec = nullptr;
+  std::vector<const bf16*> u_qkv, u_o, u_up, u_down;
   std::vector<float*> b_qkv;
   // state of the last forward
   int B = 0, Tn = 0, Tp = 0, L = 0, S = 0, training = 0; unsigned long long seed = 0; bool have_fwd = false;
@@ -136,6 +141,7 @@ struct Engine : ndt1_engine {
       if (k.factors_active) w_fac = ar.take<bf16>((long long)Hout * H);
       w_dec = ar.take<bf16>((long long)k.n_outputs * Hout);
       w_qkv.resize(NL); w_o.resize(NL); w_up.resize(NL); w_down.resize(NL); b_qkv.resize(NL);
+      u_qkv.resize(NL); u_o.resize(NL); u_up.resize(NL); u_down.resize(NL);
       for (int l = 0; l < NL; ++l) {
         w_qkv[l] = ar.take<bf16>(3LL * H * H); w_o[l] = ar.take<bf16>((long long)H * H);
         w_up[l] = ar.take<bf16>((long long)I * H); w_down[l] = ar.take<bf16>((long long)H * I);
@@ -257,34 +263,49 @@ struct Engine : ndt1_engine {
     if (kBf16) {
       NDT1_TRY(k_cast_f32_bf16(bt->spikes, (bf16*)xin, MT, N, N, ldN, s));
       CastSegs cs; cs.n = 0;
-      // contiguous matrices go through ONE multi-segment launch; anything ragged through the strided kernel
-      auto add = [&](const float* src, bf16* dst, long long rows, int cols, long long ld_out) -> int {
+      // a weight either comes from the caller's bf16 shadow (no work here) or is cast into the engine's copy:
+      // contiguous matrices through ONE multi-segment launch, anything ragged through the strided kernel
+      int rc_add = 0;
+      auto use = [&](const float* src, bf16* dst, long long rows, int cols, long long ld_out) -> const bf16* {
         const long long cnt = rows * cols;
+        if (shadow_bf16 && ld_out == cols && src >= shadow_src && src + cnt <= shadow_src + shadow_n) {
+          const bf16* sp = (const bf16*)shadow_bf16 + (src - shadow_src);
+          if (((uintptr_t)sp & 15) == 0) return sp;
+        }
         if (ld_out == cols && cnt % 8 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && cs.n < CAST_MAX_SEGS) {
           cs.src[cs.n] = src; cs.dst[cs.n] = dst; cs.count[cs.n] = cnt; ++cs.n;
-          return 0;
+        } else if (!rc_add) {
+          rc_add = k_cast_f32_bf16(src, dst, rows, cols, cols, ld_out, s);
         }
-        return k_cast_f32_bf16(src, dst, rows, cols, cols, ld_out, s);
+        return dst;
       };
-      NDT1_TRY(add(P->embed_w, w_emb, D, N, ldN));
+      u_emb = use(P->embed_w, w_emb, D, N, ldN);
       const int KP = k.stack_active ? k.stack_size * D : D;
-      NDT1_TRY(add(P->proj_w, w_proj, H, KP, KP));
+      u_proj = use(P->proj_w, w_proj, H, KP, KP);
       for (int l = 0; l < NL; ++l) {
         const auto& q = P->layer[l];
-        NDT1_TRY(add(q.q_w, w_qkv[l], H, H, H));
-        NDT1_TRY(add(q.k_w, w_qkv[l] + (long long)H * H, H, H, H));
-        NDT1_TRY(add(q.v_w, w_qkv[l] + 2LL * H * H, H, H, H));
-        NDT1_TRY(add(q.o_w, w_o[l], H, H, H));
-        NDT1_TRY(add(q.up_w, w_up[l], I, H, H));
-        NDT1_TRY(add(q.down_w, w_down[l], H, I, I));
+        const bf16* uq = use(q.q_w, w_qkv[l], H, H, H);
+        const bf16* uk = use(q.k_w, w_qkv[l] + (long long)H * H, H, H, H);
+        const bf16* uv = use(q.v_w, w_qkv[l] + 2LL * H * H, H, H, H);
+        if (uk != uq + (long long)H * H || uv != uk + (long long)H * H) {      // shadow without adjacent q|k|v: fall back to the engine's packed copy
+          NDT1_TRY(k_cast_f32_bf16(q.q_w, w_qkv[l], H, H, H, H, s));
+          NDT1_TRY(k_cast_f32_bf16(q.k_w, w_qkv[l] + (long long)H * H, H, H, H, H, s));
+          NDT1_TRY(k_cast_f32_bf16(q.v_w, w_qkv[l] + 2LL * H * H, H, H, H, H, s));
+          uq = w_qkv[l];
+        }
+        u_qkv[l] = uq;
+        u_o[l] = use(q.o_w, w_o[l], H, H, H);
+        u_up[l] = use(q.up_w, w_up[l], I, H, H);
+        u_down[l] = use(q.down_w, w_down[l], H, I, I);
         if (k.attention_bias && !(q.k_b == q.q_b + H && q.v_b == q.k_b + H)) {   // scattered biases: gather them once
           NDT1_CUDA_CHECK(cudaMemcpyAsync(b_qkv[l], q.q_b, H * 4, cudaMemcpyDeviceToDevice, s));
           NDT1_CUDA_CHECK(cudaMemcpyAsync(b_qkv[l] + H, q.k_b, H * 4, cudaMemcpyDeviceToDevice, s));
           NDT1_CUDA_CHECK(cudaMemcpyAsync(b_qkv[l] + 2 * H, q.v_b, H * 4, cudaMemcpyDeviceToDevice, s));
         }
       }
-      if (k.factors_active) NDT1_TRY(add(P->factors_w, w_fac, Hout, H, H));
-      NDT1_TRY(add(P->dec_w, w_dec, V, Hout, Hout));
+      if (k.factors_active) u_fac = use(P->factors_w, w_fac, Hout, H, H);
+      u_dec = use(P->dec_w, w_dec, V, Hout, Hout);
+      NDT1_TRY(rc_add);
       NDT1_TRY(k_cast_multi(cs, s));
     }
     const T* x_in = kBf16 ? xin : (const T*)bt->spikes;
@@ -294,7 +315,7 @@ struct Engine : ndt1_engine {
     {
       GemmEpilogue e = gemm_epilogue_default();
       e.out = emb; e.out_bf16 = kBf16; e.ldc = D; e.bias = k.embed_bias ? P->embed_b : nullptr; e.act = act_code(k.embed_act);
-      NDT1_TRY(linear_fwd(x_in, ldx, W(P->embed_w, w_emb), kBf16 ? ldN : N, (int)MT, D, N, e, s));
+      NDT1_TRY(linear_fwd(x_in, ldx, W(P->embed_w, u_emb), kBf16 ? ldN : N, (int)MT, D, N, e, s));
     }
     // 2. stack projection / projection + position table + embedding dropout  (models/ndt1.py:179-203)
     float* x0 = xs[0];
@@ -311,12 +332,12 @@ struct Engine : ndt1_engine {
         p = prob(GEMM_NT, Tp, H, K4);
         p.nb_out = B; p.nchunk = nch; p.a_row_shift = 1; p.b_col_shift = K4;
         p.A = op(emb, (long long)Tn * D, B, Tn / k.stack_stride, K4, K4);
-        p.B = op(W(P->proj_w, w_proj), 0, 1, H, nch * K4, nch * K4);
+        p.B = op(W(P->proj_w, u_proj), 0, 1, H, nch * K4, nch * K4);
       } else {
         p = prob(GEMM_NT, Tp, H, D);
         p.nb_out = B;
         p.A = op(emb, (long long)Tn * D, B, Tn, D, D);
-        p.B = op(W(P->proj_w, w_proj), 0, 1, H, D, D);
+        p.B = op(W(P->proj_w, u_proj), 0, 1, H, D, D);
       }
       p.epi = e;
       NDT1_TRY(run(p, s));
@@ -340,7 +361,7 @@ struct Engine : ndt1_engine {
         GemmEpilogue e = gemm_epilogue_default();
         const bool packed_bias = (q.k_b == q.q_b + H && q.v_b == q.k_b + H);   // flat parameter arena: q|k|v biases adjacent
         e.out = qkv[l]; e.out_bf16 = 1; e.ldc = 3 * H; e.bias = k.attention_bias ? (packed_bias ? q.q_b : b_qkv[l]) : nullptr;
-        NDT1_TRY(linear_fwd(h1[l], H, w_qkv[l], H, (int)M, 3 * H, H, e, s));
+        NDT1_TRY(linear_fwd(h1[l], H, u_qkv[l], H, (int)M, 3 * H, H, e, s));
       } else {
         const float* ws[3] = {q.q_w, q.k_w, q.v_w}; const float* bs[3] = {q.q_b, q.k_b, q.v_b};
         for (int j = 0; j < 3; ++j) {
@@ -360,20 +381,20 @@ struct Engine : ndt1_engine {
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = xm; e.ldc = H; e.bias = k.attention_bias ? q.o_b : nullptr; e.resid = xa;
-        NDT1_TRY(linear_fwd((const T*)ap.out_drop, H, W(q.o_w, kBf16 ? w_o[l] : nullptr), H, (int)M, H, H, e, s));
+        NDT1_TRY(linear_fwd((const T*)ap.out_drop, H, W(q.o_w, kBf16 ? u_o[l] : nullptr), H, (int)M, H, H, e, s));
       }
       NDT1_TRY(k_layernorm_fwd<T>(xm, q.ln2_w, q.ln2_b, h2[l], mean[2 * l + 1], rstd[2 * l + 1], M, H, 1e-5f, s));
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = g[l]; e.out_bf16 = kBf16; e.ldc = I; e.bias = k.mlp_bias ? q.up_b : nullptr; e.act = act_code(k.mlp_act);
         e.out2 = u[l]; e.out2_bf16 = kBf16;
-        NDT1_TRY(linear_fwd(h2[l], H, W(q.up_w, kBf16 ? w_up[l] : nullptr), H, (int)M, I, H, e, s));
+        NDT1_TRY(linear_fwd(h2[l], H, W(q.up_w, kBf16 ? u_up[l] : nullptr), H, (int)M, I, H, e, s));
       }
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = xo; e.ldc = H; e.bias = k.mlp_bias ? q.down_b : nullptr; e.resid = xm;
         if (ptr_ > 0.f) { e.drop_p = ptr_; e.drop_seed = seed; e.drop_stream = site_mlp(l); }
-        NDT1_TRY(linear_fwd(g[l], I, W(q.down_w, kBf16 ? w_down[l] : nullptr), I, (int)M, H, I, e, s));
+        NDT1_TRY(linear_fwd(g[l], I, W(q.down_w, kBf16 ? u_down[l] : nullptr), I, (int)M, H, I, e, s));
       }
     }
     // 4. output norm, factors, head   (models/ndt1.py:442-450, 545)
@@ -384,7 +405,7 @@ struct Engine : ndt1_engine {
       GemmEpilogue e = gemm_epilogue_default();
       e.out = fac; e.out_bf16 = kBf16; e.ldc = Hout; e.bias = k.factors_bias ? P->factors_b : nullptr; e.act = act_code(k.factors_act);
       e.out2 = fpre; e.out2_bf16 = kBf16;
-      NDT1_TRY(linear_fwd(hn, H, W(P->factors_w, w_fac), H, (int)M, Hout, H, e, s));
+      NDT1_TRY(linear_fwd(hn, H, W(P->factors_w, u_fac), H, (int)M, Hout, H, e, s));
       head_in = fac; head_ld = Hout;
     }
     if (o->features) {
@@ -406,7 +427,7 @@ struct Engine : ndt1_engine {
       GemmProblem p = prob(GEMM_NT, Tp, V, Hout);
       p.nb_out = B;
       p.A = op(head_in + (long long)n_prefix * head_ld, (long long)L * head_ld, B, Tp, Hout, head_ld);
-      p.B = op(W(P->dec_w, w_dec), 0, 1, V, Hout, Hout);
+      p.B = op(W(P->dec_w, u_dec), 0, 1, V, Hout, Hout);
       p.epi.out = logits; p.epi.ldc = ldL; p.epi.c_batch_stride = (long long)Tp * ldL; p.epi.bias = P->dec_b;
       NDT1_TRY(run(p, s));
     }
@@ -500,7 +521,7 @@ struct Engine : ndt1_engine {
       GemmProblem p = prob(GEMM_NN, Tp, Hout, V);
       p.nb_out = B;
       p.A = op(dlog, (long long)Tp * ldV, B, Tp, V, ldV);
-      p.B = op(W(P->dec_w, w_dec), 0, 1, V, Hout, Hout);
+      p.B = op(W(P->dec_w, u_dec), 0, 1, V, Hout, Hout);
       p.epi.out = d_head_in + (long long)n_prefix * head_ld; p.epi.out_bf16 = kBf16; p.epi.ldc = head_ld; p.epi.c_batch_stride = (long long)L * head_ld;
       if (k.factors_active) {
         // through the factors activation: needs the pre-activation for gelu, the output otherwise
@@ -516,7 +537,7 @@ struct Engine : ndt1_engine {
       NDT1_TRY(linear_wgrad(dfac, Hout, hn, H, G->factors_w, H, (int)M, Hout, H, ws));
       GemmEpilogue e = gemm_epilogue_default();
       e.out = dhn; e.out_bf16 = kBf16; e.ldc = H;
-      NDT1_TRY(linear_dgrad(dfac, Hout, W(P->factors_w, w_fac), H, (int)M, Hout, H, e, s));
+      NDT1_TRY(linear_dgrad(dfac, Hout, W(P->factors_w, u_fac), H, (int)M, Hout, H, e, s));
     }
     // out_norm
     NDT1_CUDA_CHECK(cudaMemsetAsync(dX, 0, M * H * sizeof(float), s));
@@ -540,7 +561,7 @@ struct Engine : ndt1_engine {
         // (with the second stream the reduction runs there, off the data-gradient chain; fused into the epilogue otherwise)
         const bool fuse_cs = kBf16 && !force_simt && !overlap && gq.up_b && k.mlp_bias && I % 8 == 0;
         if (fuse_cs) e.colsum = gq.up_b;
-        NDT1_TRY(linear_dgrad(dY, H, W(q.down_w, kBf16 ? w_down[l] : nullptr), I, (int)M, H, I, e, s));
+        NDT1_TRY(linear_dgrad(dY, H, W(q.down_w, kBf16 ? u_down[l] : nullptr), I, (int)M, H, I, e, s));
         NDT1_TRY(fork());
         if (!fuse_cs && gq.up_b && k.mlp_bias) NDT1_TRY(k_colsum<T>(dU, gq.up_b, M, I, I, ws));
       }
@@ -548,7 +569,7 @@ struct Engine : ndt1_engine {
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = dH; e.out_bf16 = kBf16; e.ldc = H;
-        NDT1_TRY(linear_dgrad(dU, I, W(q.up_w, kBf16 ? w_up[l] : nullptr), H, (int)M, I, H, e, s));
+        NDT1_TRY(linear_dgrad(dU, I, W(q.up_w, kBf16 ? u_up[l] : nullptr), H, (int)M, I, H, e, s));
       }
       NDT1_TRY(k_layernorm_bwd<T>(dH, xs[2 * l + 1], q.ln2_w, mean[2 * l + 1], rstd[2 * l + 1], dX, gq.ln2_w, gq.ln2_b, dYa[l], 0.f, seed, 0, M, H,
                                   ln_part, s, k.attention_bias ? gq.o_b : nullptr));
@@ -561,7 +582,7 @@ struct Engine : ndt1_engine {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = dA; e.out_bf16 = kBf16; e.ldc = H;
         if (ptr_ > 0.f) { e.drop_p = ptr_; e.drop_bwd = 1; e.drop_seed = seed; e.drop_stream = site_attn_o(l); }
-        NDT1_TRY(linear_dgrad(dY, H, W(q.o_w, kBf16 ? w_o[l] : nullptr), H, (int)M, H, H, e, s));
+        NDT1_TRY(linear_dgrad(dY, H, W(q.o_w, kBf16 ? u_o[l] : nullptr), H, (int)M, H, H, e, s));
       }
       AttnParams ap;
       ap.qkv = qkv[l]; ap.out = att[l]; ap.out_drop = (void*)ad; ap.lse = lse[l]; ap.key_valid = key_valid;
@@ -588,7 +609,7 @@ struct Engine : ndt1_engine {
       if (kBf16) {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = dH; e.out_bf16 = 1; e.ldc = H;
-        NDT1_TRY(linear_dgrad(dqkv, 3 * H, w_qkv[l], H, (int)M, 3 * H, H, e, s));
+        NDT1_TRY(linear_dgrad(dqkv, 3 * H, u_qkv[l], H, (int)M, 3 * H, H, e, s));
       } else {
         const float* wq[3] = {q.q_w, q.k_w, q.v_w};
         for (int j = 0; j < 3; ++j) {
@@ -636,7 +657,7 @@ struct Engine : ndt1_engine {
       GemmProblem p = prob(GEMM_NN, R4, K4, H);
       p.nb_out = B; p.nchunk = nch; p.a_row_shift = -1; p.b_col_shift = K4;
       p.A = op(dE, (long long)L * H, B, Tp, H, H);
-      p.B = op(W(P->proj_w, w_proj), 0, 1, H, nch * K4, nch * K4);
+      p.B = op(W(P->proj_w, u_proj), 0, 1, H, nch * K4, nch * K4);
       p.epi.out = dEmb; p.epi.out_bf16 = kBf16; p.epi.ldc = K4; p.epi.c_batch_stride = (long long)Tn * D;
       p.epi.dact = dact_from_out(eact); p.epi.dact_in = emb; p.epi.dact_in_bf16 = kBf16;
       if (fuse_embed_cs) p.epi.colsum = G->embed_b;
@@ -653,7 +674,7 @@ struct Engine : ndt1_engine {
       GemmProblem p = prob(GEMM_NN, Tp, D, H);
       p.nb_out = B;
       p.A = op(dE, (long long)L * H, B, Tp, H, H);
-      p.B = op(W(P->proj_w, w_proj), 0, 1, H, D, D);
+      p.B = op(W(P->proj_w, u_proj), 0, 1, H, D, D);
       p.epi.out = dEmb; p.epi.out_bf16 = kBf16; p.epi.ldc = D; p.epi.c_batch_stride = (long long)Tn * D;
       p.epi.dact = dact_from_out(eact); p.epi.dact_in = emb; p.epi.dact_in_bf16 = kBf16;
       if (fuse_embed_cs) p.epi.colsum = G->embed_b;
@@ -721,6 +742,12 @@ int ndt1_engine_backward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_
   return e->backward(params, grads, dloss, (cudaStream_t)stream);
 }
 int64_t ndt1_engine_launch_count(const ndt1_engine* e) { return e->launches; }
+int ndt1_engine_set_weight_shadow(ndt1_engine* e, const float* params_fp32, const void* shadow_bf16, int64_t n) {
+  NDT1_REQUIRE(e, "engine_set_weight_shadow: null engine");
+  NDT1_REQUIRE(!shadow_bf16 || (params_fp32 && n > 0), "engine_set_weight_shadow: a shadow needs the arena it mirrors");
+  e->shadow_src = shadow_bf16 ? params_fp32 : nullptr; e->shadow_bf16 = shadow_bf16; e->shadow_n = shadow_bf16 ? n : 0;
+  return 0;
+}
 int ndt1_engine_set_overlap(ndt1_engine* e, int on) {
   NDT1_REQUIRE(e, "engine_set_overlap: null engine");
   e->overlap = on != 0;

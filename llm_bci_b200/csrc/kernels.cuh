@@ -29,6 +29,8 @@ int k_recon_loss(const float* pred, const float* target, float* dpred, const lon
                  int N, int kind, int shift, int relu_out, float* loss, long long* count, const float* dloss, cudaStream_t stream);
 int k_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd, int step,
             float gscale, cudaStream_t stream);
+int k_adamw_fused(float* p, float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd, int step,
+                  float gscale, bf16* shadow, int zero_grad, cudaStream_t stream);
 int k_stack_mask(const long long* mask, long long* out, int B, int T, int Tp, int size, int stride, int n_prefix, cudaStream_t stream);
 int k_token_rows(const float* table, const long long* idx, float* x, int B, int L, int H, int slot, cudaStream_t stream);
 template <typename T> int k_token_rows_grad(float* dtable, const long long* idx, const T* dx, int B, int L, int H, int slot, cudaStream_t stream);

@@ -388,6 +388,7 @@ class NDT1(nn.Module):
         self._pstruct = None
         self._last = None
         self._last_out = None
+        self._weight_shadow = None
 
     # ------------------------------------------------------------------ engine plumbing
     def _apply(self, fn, *a, **k):
@@ -443,7 +444,25 @@ class NDT1(nn.Module):
             h = _C._p()
             _C.check(L.ndt1_engine_create(_C.C.byref(cfg), _C.C.byref(h)), "ndt1_engine_create")
             self._engine, self._engine_cap = h, (nb, nt, ns)
+            self._apply_weight_shadow()
         return self._engine
+
+    def set_weight_shadow(self, flat_param: Optional[torch.Tensor], shadow: Optional[torch.Tensor]) -> None:
+        """bf16 mode: `shadow` is a bfloat16 copy (same offsets) of the flat fp32 arena `flat_param` that the parameters
+        are views of; whoever updates the parameters keeps it current (DataParallelTrainer's fused AdamW does), and the
+        engine then reads the weights from it instead of casting them every forward.  None switches it off."""
+        self._weight_shadow = None if shadow is None else (flat_param, shadow)
+        self._apply_weight_shadow()
+
+    def _apply_weight_shadow(self) -> None:
+        if self._engine is None:
+            return
+        ws = getattr(self, "_weight_shadow", None)
+        if ws is None or self.precision != "bf16":
+            _C.check(_C.lib().ndt1_engine_set_weight_shadow(self._engine, None, None, 0), "ndt1_engine_set_weight_shadow")
+        else:
+            _C.check(_C.lib().ndt1_engine_set_weight_shadow(self._engine, ws[0].data_ptr(), ws[1].data_ptr(), ws[0].numel()),
+                     "ndt1_engine_set_weight_shadow")
 
     def __del__(self):
         try:

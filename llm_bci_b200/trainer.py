@@ -101,6 +101,12 @@ class DataParallelTrainer:
                 lo, hi = spans.get(stage, (o, o))
                 spans[stage] = [min(lo, o), max(hi, o + (p.numel() + 63) // 64 * 64)]
         model.invalidate_param_cache()
+        # bf16 mode: the fused AdamW keeps a bf16 copy of the arena current, and the engine reads its weights from it
+        self.shadow = None
+        if dev.type == "cuda" and getattr(model, "precision", "") == "bf16":
+            self.shadow = torch.empty(total, dtype=torch.bfloat16, device=dev)
+            self.refresh_shadow()
+            model.set_weight_shadow(self.flat_param, self.shadow)
         self.buckets = [(st, spans[st][0], spans[st][1]) for st in sorted(spans)]   # completion order
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._ones = torch.ones((), dtype=torch.float32, device=dev)
@@ -126,11 +132,16 @@ class DataParallelTrainer:
                 dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
         torch.cuda.current_stream().wait_stream(self.comm_stream)
 
+    def refresh_shadow(self) -> None:
+        """Call after changing parameters behind the trainer's back (e.g. load_checkpoint)."""
+        if self.shadow is not None:
+            self.shadow.copy_(self.flat_param)
+
     def train_step(self, batch: Dict[str, torch.Tensor]):
-        """forward + backward + gradient all-reduce + AdamW on this rank's shard.  Returns the NDT1Output."""
+        """forward + backward + gradient all-reduce + AdamW on this rank's shard.  Returns the NDT1Output.
+        (The gradient arena starts at zero and the fused optimizer step clears it again, like zero_grad.)"""
         m = self.model
         m.train()
-        self.flat_grad.zero_()
         out = m.forward_backward(batch, self.flat_grad, self._ones)
         self.all_reduce_gradients()
         self.optimizer_step()
@@ -139,6 +150,8 @@ class DataParallelTrainer:
     def optimizer_step(self) -> None:
         self.step_count += 1
         b1, b2 = self.betas
-        _C.check(_C.lib().ndt1_adamw_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
-                                          self.exp_avg_sq.data_ptr(), self.flat_param.numel(), float(self.current_lr()), b1, b2, self.eps,
-                                          self.wd, self.step_count, 1.0 / self.world, _C.stream_ptr()), "ndt1_adamw_step")
+        _C.check(_C.lib().ndt1_adamw_step_fused(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+                                                self.exp_avg_sq.data_ptr(), self.flat_param.numel(), float(self.current_lr()), b1, b2,
+                                                self.eps, self.wd, self.step_count, 1.0 / self.world,
+                                                None if self.shadow is None else self.shadow.data_ptr(), 1, _C.stream_ptr()),
+                 "ndt1_adamw_step_fused")

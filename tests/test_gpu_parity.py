@@ -572,3 +572,47 @@ def test_layernorm_row_group_kernel_matches_torch():
                                        _C.stream_ptr()))
         assert (y.cpu().double() - ref).abs().max() < 5e-6 * float(ref.abs().max()), (rows, H)
         assert (mean.cpu() - x.mean(1)).abs().max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_fused_adamw_matches_torch_writes_shadow_and_clears_gradient():
+    torch.manual_seed(0)
+    n = 4096
+    p0, gr = torch.randn(n), torch.randn(n)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=5e-5, eps=1e-8)
+    p = p0.clone().to(DEV)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    for step in range(1, 4):
+        ref.grad = gr.clone() * step * 0.5                      # grad_scale = 0.5 (two ranks)
+        opt.step()
+        gd = (gr * step).to(DEV)
+        _C.check(_C.lib().ndt1_adamw_step_fused(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 5e-5, step, 0.5,
+                                                shadow.data_ptr(), 1, _C.stream_ptr()))
+        assert float(gd.abs().max()) == 0.0
+    assert (p.cpu() - ref.detach()).abs().max() < 1e-6
+    assert torch.equal(shadow.cpu(), p.cpu().bfloat16())
+
+
+@pytest.mark.gpu
+def test_trainer_weight_shadow_follows_the_parameters():
+    """DataParallelTrainer (bf16): the engine reads the bf16 shadow the fused AdamW maintains; same losses as the per-forward cast."""
+    tr = lb.default_trainer_config()
+    cfg = lb.update_config(tr.model, {"encoder": {"embedder": {"dropout": 0.0}, "transformer": {"dropout": 0.0, "n_layers": 2},
+                                                  "smooth_and_noise": {"noise": False}}})
+    batch = cuda_batch(O.synthetic_ctc_batch(B=4, T=400, N=256, seed=2))
+    runs = []
+    for use_shadow in (True, False):
+        torch.manual_seed(5)
+        model = lb.NDT1(cfg, **tr.method.model_kwargs, precision="bf16").to(DEV)
+        trainer = lb.DataParallelTrainer(model, lr=1e-3, wd=5e-5, eps=1e-8)
+        assert trainer.shadow is not None
+        if not use_shadow:
+            model.set_weight_shadow(None, None)
+        runs.append([float(trainer.train_step(batch).loss) for _ in range(4)])
+        assert torch.equal(trainer.shadow.cpu(), trainer.flat_param.cpu().bfloat16())
+        assert float(trainer.flat_grad.abs().max()) == 0.0      # cleared by the optimizer step
+    assert runs[0][-1] < runs[0][0]
+    for a, b in zip(*runs):
+        assert abs(a - b) <= 1e-3 * abs(b), runs
