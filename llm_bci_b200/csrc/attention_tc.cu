@@ -105,8 +105,8 @@ __device__ __forceinline__ uint32_t keep_word32(unsigned long long seed, unsigne
   const int sh = (int)(e0 & 7);
   unsigned long long bits = 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) bits |= (unsigned long long)keep_bits8(philox4x32_10(seed, c + i, stream), thr) << (8 * i);
-  if (!aligned) bits |= (unsigned long long)keep_bits8(philox4x32_10(seed, c + 4, stream), thr) << 32;
+  for (int i = 0; i < 4; ++i) bits |= (unsigned long long)keep_bits8(philox4x32(seed, c + i, stream), thr) << (8 * i);
+  if (!aligned) bits |= (unsigned long long)keep_bits8(philox4x32(seed, c + 4, stream), thr) << 32;
   return (uint32_t)(bits >> sh);
 }
 // 16-byte store of 8 bf16 at (row, col % 8 == 0) of a [128][.] operand kept as 64-column SW128 sub-tiles of 16 KB

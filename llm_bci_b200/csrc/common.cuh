@@ -81,18 +81,21 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------
-// Philox4x32-10, counter based: (seed, counter, stream) -> 4 uniform u32.
+// Philox4x32, counter based: (seed, counter, stream) -> 4 uniform u32.  SEVEN rounds: the fewest for which the
+// Random123 authors report no BigCrush failure (their default of 10 is a safety margin); dropout masks and additive
+// noise need statistical quality only, and the generator sits in the epilogue of GEMM and attention kernels.
 // Forward and backward kernels index by ELEMENT, never by thread, so the mask
 // is reproducible whatever the launch geometry.
 // ---------------------------------------------------------------------------
 struct Philox4 { uint32_t x, y, z, w; };
+constexpr int kPhiloxRounds = 7;
 
-__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_t ctr, uint64_t stream) {
+__host__ __device__ __forceinline__ Philox4 philox4x32(uint64_t seed, uint64_t ctr, uint64_t stream) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32);
   uint32_t c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kPhiloxRounds; ++r) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
     const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -122,19 +125,19 @@ __device__ __forceinline__ uint32_t philox_u16(const Philox4& r, int lane) {   /
 
 // keep-scale (0 or 1/(1-p)) of one element of a dropout site
 __device__ __forceinline__ float drop_scale_1(uint64_t seed, uint64_t stream, uint64_t elem, uint32_t thr, float inv_keep) {
-  const Philox4 r = philox4x32_10(seed, elem >> 3, stream);
+  const Philox4 r = philox4x32(seed, elem >> 3, stream);
   return philox_u16(r, (int)(elem & 7)) >= thr ? inv_keep : 0.f;
 }
 // keep-scales of the 4 consecutive elements starting at elem (elem % 4 == 0)
 __device__ __forceinline__ void drop_scale_4(uint64_t seed, uint64_t stream, uint64_t elem, uint32_t thr, float ik, float* o) {
-  const Philox4 r = philox4x32_10(seed, elem >> 3, stream);
+  const Philox4 r = philox4x32(seed, elem >> 3, stream);
   const uint32_t w0 = (elem & 4) ? r.z : r.x, w1 = (elem & 4) ? r.w : r.y;
   o[0] = (w0 & 0xFFFFu) >= thr ? ik : 0.f; o[1] = (w0 >> 16) >= thr ? ik : 0.f;
   o[2] = (w1 & 0xFFFFu) >= thr ? ik : 0.f; o[3] = (w1 >> 16) >= thr ? ik : 0.f;
 }
 // keep-scales of the 8 consecutive elements starting at elem (elem % 8 == 0)
 __device__ __forceinline__ void drop_scale_8(uint64_t seed, uint64_t stream, uint64_t elem, uint32_t thr, float ik, float* o) {
-  const Philox4 r = philox4x32_10(seed, elem >> 3, stream);
+  const Philox4 r = philox4x32(seed, elem >> 3, stream);
   o[0] = (r.x & 0xFFFFu) >= thr ? ik : 0.f; o[1] = (r.x >> 16) >= thr ? ik : 0.f;
   o[2] = (r.y & 0xFFFFu) >= thr ? ik : 0.f; o[3] = (r.y >> 16) >= thr ? ik : 0.f;
   o[4] = (r.z & 0xFFFFu) >= thr ? ik : 0.f; o[5] = (r.z >> 16) >= thr ? ik : 0.f;

@@ -37,7 +37,7 @@ __global__ void smooth_noise_kernel(const SmoothParams p) {
     if (p.offset) off = p.offset_sd * p.offset[(long long)b * p.N + n];
     else if (p.use_philox) {
       const unsigned long long e = (unsigned long long)b * p.N + n;
-      Philox4 r = philox4x32_10(p.seed, e, 0x6f666673ULL);
+      Philox4 r = philox4x32(p.seed, e, 0x6f666673ULL);
       float a, c; box_muller(r.x, r.y, a, c);
       off = p.offset_sd * a;
     }
@@ -60,7 +60,7 @@ __global__ void smooth_noise_kernel(const SmoothParams p) {
         const unsigned long long e = ((unsigned long long)b * p.T + t) * p.N + n;
         if (p.white) v += p.white_sd * p.white[e];
         else if (p.use_philox) {
-          Philox4 r = philox4x32_10(p.seed, e >> 1, 0x77686974ULL);
+          Philox4 r = philox4x32(p.seed, e >> 1, 0x77686974ULL);
           float a, c; box_muller(r.x, r.y, a, c);
           v += p.white_sd * ((e & 1) ? c : a);
         }
@@ -76,7 +76,7 @@ __global__ void smooth_noise_kernel(const SmoothParams p) {
         const unsigned long long e = ((unsigned long long)b * p.T + t) * p.N + n;
         if (p.white) v += p.white_sd * p.white[e];
         else if (p.use_philox) {
-          Philox4 r = philox4x32_10(p.seed, e >> 1, 0x77686974ULL);
+          Philox4 r = philox4x32(p.seed, e >> 1, 0x77686974ULL);
           float a, c; box_muller(r.x, r.y, a, c);
           v += p.white_sd * ((e & 1) ? c : a);
         }
@@ -92,8 +92,8 @@ __global__ void smooth_noise_kernel(const SmoothParams p) {
 constexpr int SMV_TT = 25;
 __device__ __forceinline__ void white_quad(unsigned long long seed, unsigned long long e0, float* nz) {
   // elements e0..e0+3 (e0 % 4 == 0): the generic kernel draws element e from Philox(seed, e >> 1): lane (e & 1) of box_muller(x, y)
-  const Philox4 r0 = philox4x32_10(seed, e0 >> 1, 0x77686974ULL);
-  const Philox4 r1 = philox4x32_10(seed, (e0 >> 1) + 1, 0x77686974ULL);
+  const Philox4 r0 = philox4x32(seed, e0 >> 1, 0x77686974ULL);
+  const Philox4 r1 = philox4x32(seed, (e0 >> 1) + 1, 0x77686974ULL);
   box_muller(r0.x, r0.y, nz[0], nz[1]);
   box_muller(r1.x, r1.y, nz[2], nz[3]);
 }
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) smooth_noise_vec_kernel(const SmoothParam
       const unsigned long long e = (unsigned long long)b * p.N + n4 * 4 + c;
       if (p.offset) o[c] = p.offset_sd * p.offset[e];
       else if (p.use_philox) {
-        Philox4 r = philox4x32_10(p.seed, e, 0x6f666673ULL);
+        Philox4 r = philox4x32(p.seed, e, 0x6f666673ULL);
         float a, d; box_muller(r.x, r.y, a, d);
         o[c] = p.offset_sd * a;
       }
@@ -304,7 +304,7 @@ __global__ void bernoulli_u8_kernel(unsigned char* out, long long n, float prob,
   const double tt = (double)prob * 4294967296.0;
   const uint32_t thr = tt <= 0.0 ? 0u : (tt >= 4294967295.0 ? 4294967295u : (uint32_t)tt);  // P(u < thr) = prob
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n; i += (long long)gridDim.x * blockDim.x) {
-    Philox4 r = philox4x32_10(seed, i, stream);
+    Philox4 r = philox4x32(seed, i, stream);
     const uint32_t u[4] = {r.x, r.y, r.z, r.w};
     for (int k = 0; k < 4; ++k)
       if (i * 4 + k < n) out[i * 4 + k] = (prob >= 1.f) ? 1 : (u[k] < thr ? 1 : 0);
@@ -312,7 +312,7 @@ __global__ void bernoulli_u8_kernel(unsigned char* out, long long n, float prob,
 }
 __global__ void uniform_f32_kernel(float* out, long long n, unsigned long long seed, unsigned long long stream) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n; i += (long long)gridDim.x * blockDim.x) {
-    Philox4 r = philox4x32_10(seed, i, stream);
+    Philox4 r = philox4x32(seed, i, stream);
     const uint32_t u[4] = {r.x, r.y, r.z, r.w};
     for (int k = 0; k < 4; ++k)
       if (i * 4 + k < n) out[i * 4 + k] = (float)(u[k] >> 8) * (1.0f / 16777216.0f);

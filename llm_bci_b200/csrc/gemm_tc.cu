@@ -88,6 +88,20 @@ __device__ __forceinline__ float dgelu_fast(float x) { float cdf, e; gelu_parts(
 // ---------------------------------------------------------------------------
 enum { SIDE_NONE = 0, SIDE_RESID = 1, SIDE_DACT = 2, SIDE_GATHER = 3 };
 
+// Epilogue classes: the kernel is instantiated per class with everything else compiled OUT, so that the epilogue of a
+// launch is a few hundred instructions that stay in the instruction cache (the all-features epilogue does not, and
+// instruction-fetch stalls then rival the arithmetic).  EF_* = features a class may use.
+enum {
+  EF_OUT2 = 1, EF_ACT = 2, EF_GATHER = 4, EF_DROP = 8, EF_DACT = 16, EF_RESID = 32, EF_COLSUM = 64, EF_ACCUM = 128, EF_SCALAR = 256,
+  EPI_PLAIN = EF_RESID,                                  // bias (+ fp32 residual): QKV, attention out-proj, plain data gradients
+  EPI_ACT = EF_OUT2 | EF_ACT,                            // bias + activation (+ pre-activation copy): MLP up-proj, channel embedding
+  EPI_DROP = EF_GATHER | EF_DROP | EF_RESID,             // bias (+ position rows) + dropout (+ residual): MLP down-proj, stack projection
+  EPI_DACT = EF_DROP | EF_DACT | EF_COLSUM,              // backward: dropout mask, activation derivative, bias-gradient column sums
+  EPI_ACCUM = EF_ACCUM,                                  // weight gradients: fp32 red.add
+  EPI_ALL = 511                                          // everything, incl. the element-wise path for ragged shapes
+};
+__host__ __device__ constexpr bool ef_has(int cls, int f) { return (cls & f) != 0; }
+
 struct EpiCtx {
   int side_kind;
   bool vec_ok;
@@ -98,24 +112,26 @@ struct ChunkAt {          // where a (tile, chunk) lands in the output
   bool live;
 };
 
+template <int EPI>
 __device__ __forceinline__ void side_load(const GemmEpilogue& e, const EpiCtx& cx, const TcParams& p, const ChunkAt& at, int lane,
                                           float4* side) {
+  if (!ef_has(EPI, EF_RESID | EF_DACT | EF_GATHER)) return;
   if (cx.side_kind == SIDE_NONE || !cx.vec_ok || !at.live || at.n >= p.N) return;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = at.r0 + (lane >> 3) + 4 * i;
     if (r < p.M) {
       const long long idx = (long long)at.bt * e.c_batch_stride + (long long)r * e.ldc + at.n;
-      if (cx.side_kind == SIDE_RESID) {
+      if (ef_has(EPI, EF_RESID) && cx.side_kind == SIDE_RESID) {
         side[i] = __ldg((const float4*)(e.resid + idx));
-      } else if (cx.side_kind == SIDE_DACT) {
+      } else if (ef_has(EPI, EF_DACT) && cx.side_kind == SIDE_DACT) {
         if (e.dact_in_bf16) {
           const uint2 t = __ldg((const uint2*)((const bf16*)e.dact_in + idx));
           side[i].x = __uint_as_float(t.x); side[i].y = __uint_as_float(t.y);
         } else {
           side[i] = __ldg((const float4*)((const float*)e.dact_in + idx));
         }
-      } else {
+      } else if (ef_has(EPI, EF_GATHER)) {
         const long long g = __ldg(e.gather_idx + (long long)at.bt * e.gather_idx_stride + r);
         side[i] = __ldg((const float4*)(e.gather_tab + g * e.gather_ld + at.n));
       }
@@ -123,10 +139,11 @@ __device__ __forceinline__ void side_load(const GemmEpilogue& e, const EpiCtx& c
   }
 }
 
+template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiCtx& cx, const TcParams& p, const ChunkAt& at, int lane,
                                                const float4* acc, const float4* side, const uint8_t* stg) {
   if (!at.live) return;
-  if (!cx.vec_ok) {        // ragged shapes (the 41-column head): element-wise, still row-contiguous across lanes
+  if (ef_has(EPI, EF_SCALAR) && !cx.vec_ok) {        // ragged shapes (the 41-column head): element-wise, still row-contiguous across lanes
 #pragma unroll 1           // ONE copy of the scalar epilogue (it carries every feature): code size, not speed, matters here
     for (int ij = 0; ij < 32; ++ij) {
       const int i = ij >> 2, j = ij & 3;
@@ -161,7 +178,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
   for (int i = 0; i < 8; ++i) okm |= (col_ok && (at.r0 + (lane >> 3) + 4 * i) < p.M) ? (1u << i) : 0u;
 #define idx(i) (idx0 + (i) * ld4)
 #define ok(i) ((okm >> (i)) & 1u)
-  if (e.out2) {
+  if (ef_has(EPI, EF_OUT2) && e.out2) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (ok(i)) {
@@ -169,7 +186,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
         else *(float4*)((float*)e.out2 + idx(i)) = v[i];
       }
   }
-  if (e.act == ACT_GELU) {          // (the activation switch is hoisted out of the element loops: smaller, branch-free code)
+  if (!ef_has(EPI, EF_ACT)) {
+  } else if (e.act == ACT_GELU) {          // (the activation switch is hoisted out of the element loops: smaller, branch-free code)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i].x = gelu_fast(v[i].x); v[i].y = gelu_fast(v[i].y); v[i].z = gelu_fast(v[i].z); v[i].w = gelu_fast(v[i].w); }
   } else if (e.act == ACT_SOFTSIGN) {
@@ -182,7 +200,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
   }
-  if (e.gather_tab) {
+  if (ef_has(EPI, EF_GATHER) && e.gather_tab) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -195,7 +213,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
       if (ok(i)) { v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w; }
     }
   }
-  if (e.drop_p > 0.f) {
+  if (ef_has(EPI, EF_DROP) && e.drop_p > 0.f) {
     // One Philox block covers 8 consecutive elements = the columns of a lane PAIR.  The even lane draws the block of
     // row 2k, the odd lane the block of row 2k+1, and they swap halves: one Philox per 8 elements, as in the forward
     // of every other kernel that shares these streams.
@@ -206,7 +224,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
     for (int k = 0; k < 4; ++k) {
       const int r = at.r0 + (lane >> 3) + 4 * (2 * k + (odd ? 1 : 0));
       const unsigned long long elem = ((unsigned long long)at.bt * p.M + r) * (unsigned long long)p.N + (unsigned)(at.n & ~7);
-      const Philox4 ph = philox4x32_10(e.drop_seed, elem >> 3, e.drop_stream);
+      const Philox4 ph = philox4x32(e.drop_seed, elem >> 3, e.drop_stream);
       const uint32_t s0 = odd ? ph.x : ph.z, s1 = odd ? ph.y : ph.w;
       const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
       const uint32_t a0 = odd ? r0 : ph.x, a1 = odd ? r1 : ph.y;     // row 2k
@@ -218,7 +236,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
       vb.z *= (b1 & 0xFFFFu) >= thr ? ik : 0.f; vb.w *= (b1 >> 16) >= thr ? ik : 0.f;
     }
   }
-  if (e.dact != DACT_NONE) {
+  if (ef_has(EPI, EF_DACT) && e.dact != DACT_NONE) {
     float4 sv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -251,12 +269,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
       }
     }
   }
-  if (e.resid) {           // always the prefetched side input when present
+  if (ef_has(EPI, EF_RESID) && e.resid) {           // always the prefetched side input when present
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (ok(i)) { v[i].x += side[i].x; v[i].y += side[i].y; v[i].z += side[i].z; v[i].w += side[i].w; }
   }
-  if (e.colsum) {          // bias gradient of the producing layer: column sums of this chunk, one red per column per warp
+  if (ef_has(EPI, EF_COLSUM) && e.colsum) {          // bias gradient of the producing layer: column sums of this chunk, one red per column per warp
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -271,7 +289,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (!ok(i)) continue;
-    if (e.accumulate) red_add_v4((float*)e.out + idx(i), v[i].x, v[i].y, v[i].z, v[i].w);
+    if (ef_has(EPI, EF_ACCUM) && e.accumulate) red_add_v4((float*)e.out + idx(i), v[i].x, v[i].y, v[i].z, v[i].w);
     else if (e.out_bf16) *(uint2*)((bf16*)e.out + idx(i)) = pack4_bf16(v[i].x, v[i].y, v[i].z, v[i].w);
     else *(float4*)((float*)e.out + idx(i)) = v[i];
   }
@@ -341,7 +359,7 @@ __device__ __forceinline__ void tc_commit_g(uint64_t* bar) {
 // ---------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------
-template <int BN, int MODE, int CTAS>
+template <int BN, int MODE, int CTAS, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)   // 10 warps: 3 share one SM sub-partition -> 168 registers per thread
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   constexpr int BNL = BN / CTAS;                       // columns of B held by this CTA
@@ -512,7 +530,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float4 side_cur[8], side_nxt[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) side_cur[i] = side_nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    side_load(e, cx, p, locate(unit, 0), lane, side_cur);
+    side_load<EPI>(e, cx, p, locate(unit, 0), lane, side_cur);
     const uint32_t tempty_addr0 = CTAS == 2 ? mapa_u32(&tempty_bar[0], 0) : 0u;   // the leader's accumulator-free barriers
 
     for (int tile = unit; tile < p.total_tiles; tile += n_units) {
@@ -526,7 +544,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tmem_ld32(taddr_row + c * 32, raw);
         // side input of the next chunk (or of the next tile's first chunk) while the TMEM load is in flight
         const ChunkAt nx = (c + 1 < NCH) ? locate(tile, c + 1) : locate(tile + n_units, 0);
-        side_load(e, cx, p, nx, lane, side_nxt);
+        side_load<EPI>(e, cx, p, nx, lane, side_nxt);
         tmem_ld_wait();
         if (c == NCH - 1) {                         // accumulator fully read: hand the TMEM stage back before the stores
           tc_fence_before();
@@ -551,7 +569,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           acc[i] = *(const float4*)(stg + rr * 128 + ((((lane & 7) ^ rr) & 7) << 4));
         }
         __syncwarp();
-        epilogue_chunk(e, cx, p, at, lane, acc, side_cur, stg);
+        epilogue_chunk<EPI>(e, cx, p, at, lane, acc, side_cur, stg);
 #pragma unroll
         for (int i = 0; i < 8; ++i) side_cur[i] = side_nxt[i];
       }
@@ -624,7 +642,7 @@ int make_map(const GemmOperand& o, int box_cols, int box_rows, CUtensorMap* out)
   return 0;
 }
 
-template <int BN, int MODE, int CTAS>
+template <int BN, int MODE, int CTAS, int EPI>
 int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
   constexpr int STAGE_BYTES = BM * BK * 2 + (BN / CTAS) * BK * 2;
   constexpr int STAGES = kSmemPipe / STAGE_BYTES;
@@ -632,7 +650,7 @@ int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp
   static_assert(SMEM <= 227 * 1024, "gemm_tc: shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    NDT1_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    NDT1_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, CTAS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   const int units = g_num_sms / CTAS;
@@ -649,7 +667,7 @@ int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp
     NDT1_CUDA_CHECK(cudaEventRecord(rec->e0, stream));
   }
   if (CTAS == 1) {
-    gemm_tc_kernel<BN, MODE, CTAS><<<grid, kThreads, SMEM, stream>>>(ma, mb, tp);
+    gemm_tc_kernel<BN, MODE, CTAS, EPI><<<grid, kThreads, SMEM, stream>>>(ma, mb, tp);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = SMEM; cfg.stream = stream;
@@ -657,18 +675,62 @@ int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    NDT1_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, CTAS>, ma, mb, tp));
+    NDT1_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, CTAS, EPI>, ma, mb, tp));
   }
   NDT1_CHECK_LAUNCH();
   if (rec) NDT1_CUDA_CHECK(cudaEventRecord(rec->e1, stream));
   return 0;
 }
 
+// the smallest class that covers what this launch asks for (everything else: the all-features instantiation)
+int epilogue_class(const TcParams& tp, int bn) {
+  const GemmEpilogue& e = tp.epi;
+  int need = 0;
+  if (e.out2) need |= EF_OUT2;
+  if (e.act != ACT_NONE) need |= EF_ACT;
+  if (e.gather_tab) need |= EF_GATHER;
+  if (e.drop_p > 0.f) need |= EF_DROP;
+  if (e.dact != DACT_NONE) need |= EF_DACT;
+  if (e.resid) need |= EF_RESID;
+  if (e.colsum) need |= EF_COLSUM;
+  if (e.accumulate) need |= EF_ACCUM;
+  const bool plain = need == 0;
+  const bool vec = (tp.N % 4 == 0 || (plain && e.ldc >= tp.N + (4 - tp.N % 4))) && (e.ldc % 4 == 0) && (e.c_batch_stride % 4 == 0) &&
+                   (e.gather_tab == nullptr || e.gather_ld % 4 == 0) && (e.drop_p <= 0.f || tp.N % 8 == 0);
+  if (!vec || bn != 256) return EPI_ALL;
+  // (only the classes launch_256 instantiates for this operand mode)
+  const int nt[3] = {EPI_PLAIN, EPI_ACT, EPI_DROP}, nn[2] = {EPI_PLAIN, EPI_DACT}, tn[1] = {EPI_ACCUM};
+  const int* classes = tp.mode == GEMM_NT ? nt : (tp.mode == GEMM_NN ? nn : tn);
+  const int n = tp.mode == GEMM_NT ? 3 : (tp.mode == GEMM_NN ? 2 : 1);
+  for (int c = 0; c < n; ++c)
+    if ((need & ~classes[c]) == 0) return classes[c];
+  return EPI_ALL;
+}
+
+template <int MODE, int CTAS>
+int launch_256(int cls, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
+  // classes a mode can meet: forward (NT) plain / activation / dropout; data gradient (NN) plain / derivative; weight gradient (TN) accumulate
+  if (MODE == GEMM_NT) {
+    if (cls == EPI_PLAIN) return launch_inst<256, MODE, CTAS, EPI_PLAIN>(ma, mb, tp, stream);
+    if (cls == EPI_ACT) return launch_inst<256, MODE, CTAS, EPI_ACT>(ma, mb, tp, stream);
+    if (cls == EPI_DROP) return launch_inst<256, MODE, CTAS, EPI_DROP>(ma, mb, tp, stream);
+  } else if (MODE == GEMM_NN) {
+    if (cls == EPI_PLAIN) return launch_inst<256, MODE, CTAS, EPI_PLAIN>(ma, mb, tp, stream);
+    if (cls == EPI_DACT) return launch_inst<256, MODE, CTAS, EPI_DACT>(ma, mb, tp, stream);
+  } else {
+    if (cls == EPI_ACCUM) return launch_inst<256, MODE, CTAS, EPI_ACCUM>(ma, mb, tp, stream);
+  }
+  return launch_inst<256, MODE, CTAS, EPI_ALL>(ma, mb, tp, stream);
+}
+
 template <int MODE>
 int launch_mode(int bn, int ctas, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
-  if (bn == 256) return ctas == 2 ? launch_inst<256, MODE, 2>(ma, mb, tp, stream) : launch_inst<256, MODE, 1>(ma, mb, tp, stream);
-  if (bn == 128) return ctas == 2 ? launch_inst<128, MODE, 2>(ma, mb, tp, stream) : launch_inst<128, MODE, 1>(ma, mb, tp, stream);
-  return launch_inst<64, MODE, 1>(ma, mb, tp, stream);
+  if (bn == 256) {
+    const int cls = epilogue_class(tp, bn);
+    return ctas == 2 ? launch_256<MODE, 2>(cls, ma, mb, tp, stream) : launch_256<MODE, 1>(cls, ma, mb, tp, stream);
+  }
+  if (bn == 128) return ctas == 2 ? launch_inst<128, MODE, 2, EPI_ALL>(ma, mb, tp, stream) : launch_inst<128, MODE, 1, EPI_ALL>(ma, mb, tp, stream);
+  return launch_inst<64, MODE, 1, EPI_ALL>(ma, mb, tp, stream);
 }
 
 }  // namespace

@@ -313,7 +313,7 @@ ln_bwd_rows_kernel(const T* __restrict__ dy, const float* __restrict__ x, const 
       for (int k = 0; k < LNG_ROWS / 2; ++k) {
         const long long row = r0 + 2 * k + (odd ? 1 : 0);
         const unsigned long long elem = (unsigned long long)row * H + (unsigned)((c * 4) & ~7);
-        const Philox4 ph = philox4x32_10(seed, elem >> 3, stream_id);
+        const Philox4 ph = philox4x32(seed, elem >> 3, stream_id);
         const uint32_t s0 = odd ? ph.x : ph.z, s1 = odd ? ph.y : ph.w;
         const uint32_t q0 = __shfl_xor_sync(0xffffffffu, s0, 1), q1 = __shfl_xor_sync(0xffffffffu, s1, 1);
         const uint32_t a0 = odd ? q0 : ph.x, a1 = odd ? q1 : ph.y;     // row 2k
