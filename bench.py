@@ -289,8 +289,12 @@ def run_ours(args):
     L.ndt1_profile_gemm_end(_C.C.byref(fl), _C.C.byref(pms), _C.C.byref(pn))
     L.ndt1_engine_set_overlap(model._engine, 1)
     achieved = fl.value / (pms.value * 1e-3) / 1e12 if pms.value > 0 else 0.0
+    traffic = None                       # DRAM bytes per launch from the committed ncu capture of this same command (tools/gemm_traffic.py)
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMA bf16 GEMM, all shapes of the step)", "achieved": achieved,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src + " sustained",
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src + " sustained",
                 "launches_per_step": pn.value / prof_steps, "gemm_ms_per_step": pms.value / prof_steps,
                 "gemm_share_of_step": (pms.value / prof_steps) / ms_step,
                 "step_tensor_frac": (B * FLOP_PER_TRIAL / (ms_step * 1e-3) / 1e12) / peak_tf}
