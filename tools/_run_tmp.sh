@@ -1,3 +1,3 @@
-NCU="ncu --set full --import-source on --clock-control none"
-timeout 600 $NCU --kernel-name regex:gemm_tc_kernel --launch-skip 230 --launch-count 1 -f -o gpurun_out/prof_dgelu_r34 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_dgelu_r34.log 2>&1
-timeout 600 $NCU --kernel-name regex:gemm_tc_kernel --launch-skip 232 --launch-count 1 -f -o gpurun_out/prof_dgradup_r34 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_dgradup_r34.log 2>&1
+N=$1
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/r01_bench_${N}gpu.json 2> gpurun_out/r01_bench_${N}gpu.err
+tail -c 1500 gpurun_out/r01_bench_${N}gpu.json; tail -n 3 gpurun_out/r01_bench_${N}gpu.err
