@@ -109,6 +109,7 @@ struct EpiCtx {
 
 struct ChunkAt {          // where a (tile, chunk) lands in the output
   int bt, r0, n;          // trial, first row of this warp's 32-row strip, first column of this lane
+  long long rowbase;      // element offset of (trial, this lane's first row, column 0): computed once per tile
   bool live;
 };
 
@@ -121,7 +122,7 @@ __device__ __forceinline__ void side_load(const GemmEpilogue& e, const EpiCtx& c
   for (int i = 0; i < 8; ++i) {
     const int r = at.r0 + (lane >> 3) + 4 * i;
     if (r < p.M) {
-      const long long idx = (long long)at.bt * e.c_batch_stride + (long long)r * e.ldc + at.n;
+      const long long idx = at.rowbase + (long long)i * (4 * e.ldc) + at.n;
       if (ef_has(EPI, EF_RESID) && cx.side_kind == SIDE_RESID) {
         side[i] = __ldg((const float4*)(e.resid + idx));
       } else if (ef_has(EPI, EF_DACT) && cx.side_kind == SIDE_DACT) {
@@ -171,7 +172,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
     v[i].z = fmaf(acc[i].z, e.alpha, bias4.z); v[i].w = fmaf(acc[i].w, e.alpha, bias4.w);
   }
   // element offset of row i: idx0 + i * (4 * ldc); row-valid bits
-  const long long idx0 = (long long)at.bt * e.c_batch_stride + (long long)(at.r0 + (lane >> 3)) * e.ldc + at.n;
+  const long long idx0 = at.rowbase + at.n;
   const long long ld4 = 4 * e.ldc;
   uint32_t okm = 0;
 #pragma unroll
@@ -510,7 +511,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     cx.side_kind = e.resid ? SIDE_RESID : (e.dact != DACT_NONE ? SIDE_DACT : (e.gather_tab ? SIDE_GATHER : SIDE_NONE));
     int acc_stage = 0; uint32_t acc_phase = 0;
 
-    auto locate = [&](int tile, int c) {
+    // tile coordinates (two integer divisions, one 64-bit multiply-add) once per tile, not per chunk
+    auto tile_at = [&](int tile) {
       ChunkAt at;
       at.live = tile < p.total_tiles;
       const int nt = tile % p.n_tiles;
@@ -519,31 +521,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int bz = rest / p.m_tiles;
       at.bt = (MODE == GEMM_TN) ? 0 : bz;
       at.r0 = mt * (BM * CTAS) + rank * BM + q * 32;
-      at.n = nt * BN + half * (BN / 2) + c * 32 + (lane & 7) * 4;
+      at.n = nt * BN + half * (BN / 2) + (lane & 7) * 4;          // chunk 0
+      at.rowbase = (long long)at.bt * e.c_batch_stride + (long long)(at.r0 + (lane >> 3)) * e.ldc;
       if (MODE == GEMM_TN && p.split_k > 1) {
         const int per = (total_kb + p.split_k - 1) / p.split_k;
         if (bz * per >= total_kb) at.live = false;       // empty split: nothing to add
       }
       return at;
     };
+    auto chunk_of = [](ChunkAt t, int c) { t.n += c * 32; return t; };
 
     float4 side_cur[8], side_nxt[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) side_cur[i] = side_nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    side_load<EPI>(e, cx, p, locate(unit, 0), lane, side_cur);
+    ChunkAt t_cur = tile_at(unit);
+    side_load<EPI>(e, cx, p, t_cur, lane, side_cur);
     const uint32_t tempty_addr0 = CTAS == 2 ? mapa_u32(&tempty_bar[0], 0) : 0u;   // the leader's accumulator-free barriers
 
     for (int tile = unit; tile < p.total_tiles; tile += n_units) {
+      const ChunkAt t_nxt = tile_at(tile + n_units);
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * BN + half * (BN / 2));
 #pragma unroll 1                                   // one copy of the epilogue code: it must stay inside the instruction cache
       for (int c = 0; c < NCH; ++c) {
-        const ChunkAt at = locate(tile, c);
+        const ChunkAt at = chunk_of(t_cur, c);
         uint32_t raw[32];
         tmem_ld32(taddr_row + c * 32, raw);
         // side input of the next chunk (or of the next tile's first chunk) while the TMEM load is in flight
-        const ChunkAt nx = (c + 1 < NCH) ? locate(tile, c + 1) : locate(tile + n_units, 0);
+        const ChunkAt nx = (c + 1 < NCH) ? chunk_of(t_cur, c + 1) : t_nxt;
         side_load<EPI>(e, cx, p, nx, lane, side_nxt);
         tmem_ld_wait();
         if (c == NCH - 1) {                         // accumulator fully read: hand the TMEM stage back before the stores
@@ -573,6 +579,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 8; ++i) side_cur[i] = side_nxt[i];
       }
+      t_cur = t_nxt;
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   }
