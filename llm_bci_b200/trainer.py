@@ -139,19 +139,40 @@ class DataParallelTrainer:
 
     def train_step(self, batch: Dict[str, torch.Tensor]):
         """forward + backward + gradient all-reduce + AdamW on this rank's shard.  Returns the NDT1Output.
-        (The gradient arena starts at zero and the fused optimizer step clears it again, like zero_grad.)"""
+        (The gradient arena starts at zero and the fused optimizer step clears it again, like zero_grad.)
+
+        The optimizer does not wait for the end of the backward: every gradient bucket (head, layers L-1..0, embedder) is
+        all-reduced and then UPDATED on the side stream as soon as the engine signals that its gradients are complete, so
+        the HBM-bound AdamW pass runs under the tensor-bound rest of the backward.  Safe because a layer's weights are no
+        longer read once its gradients are complete."""
         m = self.model
         m.train()
         out = m.forward_backward(batch, self.flat_grad, self._ones)
-        self.all_reduce_gradients()
-        self.optimizer_step()
+        if self.comm_stream is None:
+            self.all_reduce_gradients()
+            self.optimizer_step()
+            return out
+        self.step_count += 1
+        lr = float(self.current_lr())
+        L = _C.lib()
+        with torch.cuda.stream(self.comm_stream):
+            for stage, lo, hi in self.buckets:
+                _C.check(L.ndt1_engine_wait_stage(m._engine, stage, self.comm_stream.cuda_stream), "ndt1_engine_wait_stage")
+                if self.world > 1:
+                    dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+                self._adamw(lo, hi, lr, self.comm_stream.cuda_stream)
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
         return out
 
-    def optimizer_step(self) -> None:
-        self.step_count += 1
+    def _adamw(self, lo: int, hi: int, lr: float, stream: int) -> None:
         b1, b2 = self.betas
-        _C.check(_C.lib().ndt1_adamw_step_fused(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
-                                                self.exp_avg_sq.data_ptr(), self.flat_param.numel(), float(self.current_lr()), b1, b2,
-                                                self.eps, self.wd, self.step_count, 1.0 / self.world,
-                                                None if self.shadow is None else self.shadow.data_ptr(), 1, _C.stream_ptr()),
+        fp, bf = 4 * lo, 2 * lo
+        _C.check(_C.lib().ndt1_adamw_step_fused(self.flat_param.data_ptr() + fp, self.flat_grad.data_ptr() + fp, self.exp_avg.data_ptr() + fp,
+                                                self.exp_avg_sq.data_ptr() + fp, hi - lo, lr, b1, b2, self.eps, self.wd, self.step_count,
+                                                1.0 / self.world, None if self.shadow is None else self.shadow.data_ptr() + bf, 1, stream),
                  "ndt1_adamw_step_fused")
+
+    def optimizer_step(self) -> None:
+        """AdamW over the whole arena on the current stream (for callers that drive forward_backward themselves)."""
+        self.step_count += 1
+        self._adamw(0, self.flat_param.numel(), float(self.current_lr()), _C.stream_ptr())
