@@ -121,7 +121,7 @@ int ndt1_adamw_step_fused(float* param, float* grad, float* exp_avg, float* exp_
 }
 
 namespace {
-__global__ void dropout_scales_kernel(float* out, long long n, float p, unsigned long long seed, unsigned long long site) {
+__global__ void dropout_scales_kernel(float* out, long long n, float p, unsigned long long seed, unsigned long long site) { pdl_grid_sync();
   const uint32_t thr = drop_threshold(p);
   const float ik = 1.0f / (1.0f - p);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -143,7 +143,7 @@ int ndt1_dropout_scales(float* out, int64_t n, float p, uint64_t seed, uint64_t 
   if (n == 0) return 0;
   NDT1_REQUIRE(p >= 0.f && p < 1.f, "dropout_scales: p must be in [0,1)");
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  dropout_scales_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, n, p, seed, site);
+  ndt1_launch(dropout_scales_kernel, blocks, 256, 0, (cudaStream_t)stream, out, n, p, seed, site);
   NDT1_CHECK_LAUNCH();
   return 0;
 }

@@ -31,7 +31,7 @@ __device__ __forceinline__ void load_tile(float (*dst)[MAX_HD + 1], const T* bas
 }
 
 template <typename T, int DPER>
-__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p) { pdl_grid_sync();
   extern __shared__ float smem_f[];
   float (*Qs)[MAX_HD + 1] = (float (*)[MAX_HD + 1])smem_f;
   float (*Ks)[MAX_HD + 1] = Qs + TQ;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p
 
 // delta[b,h,i] = sum_d dO[i,d] * O[i,d]   (dO already carries the output-dropout mask)
 template <typename T>
-__global__ void attn_delta_kernel(const AttnParams p) {
+__global__ void attn_delta_kernel(const AttnParams p) { pdl_grid_sync();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (b*L + i)*nh + h
   const int lane = threadIdx.x & 31;
   const long long total = (long long)p.B * p.L * p.nh;
@@ -148,7 +148,7 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 
 // One CTA per key tile: accumulates dK, dV over all query tiles.
 template <typename T, int DPER>
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnParams p) { pdl_grid_sync();
   extern __shared__ float smem_f[];
   float (*Ks)[MAX_HD + 1] = (float (*)[MAX_HD + 1])smem_f;
   float (*Vs)[MAX_HD + 1] = Ks + TK;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnParam
 
 // One CTA per query tile: dQ.
 template <typename T, int DPER>
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnParams p) { pdl_grid_sync();
   extern __shared__ float smem_f[];
   float (*Qs)[MAX_HD + 1] = (float (*)[MAX_HD + 1])smem_f;
   float (*Gs)[MAX_HD + 1] = Qs + TQ;
@@ -292,7 +292,7 @@ int k_attention_fwd(const AttnParams& p, cudaStream_t stream) {
 #define NDT1_ATT_FWD(D)                                                                                                          \
   {                                                                                                                              \
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    attn_fwd_kernel<T, D><<<grid, AT_THREADS, smem, stream>>>(p);                                                                \
+    ndt1_launch(attn_fwd_kernel<T, D>, grid, AT_THREADS, smem, stream, p);                                                                \
   }
   switch (p.hd) { case 16: NDT1_ATT_FWD(4) break; case 32: NDT1_ATT_FWD(8) break; case 64: NDT1_ATT_FWD(16) break; default: NDT1_ATT_FWD(32) }
 #undef NDT1_ATT_FWD
@@ -305,7 +305,7 @@ int k_attention_bwd(const AttnParams& p, cudaStream_t stream) {
   NDT1_TRY(check(p));
   if (p.B * p.L == 0) return 0;
   const long long rows = (long long)p.B * p.L * p.nh;
-  attn_delta_kernel<T><<<ndt1_cdiv(rows, 8), 256, 0, stream>>>(p);
+  ndt1_launch(attn_delta_kernel<T>, ndt1_cdiv(rows, 8), 256, 0, stream, p);
   NDT1_CHECK_LAUNCH();
   const size_t smem_kv = (size_t)(2 * TQ + 2 * TK) * (MAX_HD + 1) * 4 + (size_t)2 * TQ * (TK + 1) * 4;
   const size_t smem_q = (size_t)(2 * TQ + 2 * TK) * (MAX_HD + 1) * 4 + (size_t)TQ * (TK + 1) * 4;
@@ -314,8 +314,8 @@ int k_attention_bwd(const AttnParams& p, cudaStream_t stream) {
   {                                                                                                                              \
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kv_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv)); \
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_q_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));   \
-    attn_bwd_kv_kernel<T, D><<<grid, AT_THREADS, smem_kv, stream>>>(p);                                                          \
-    attn_bwd_q_kernel<T, D><<<grid, AT_THREADS, smem_q, stream>>>(p);                                                            \
+    ndt1_launch(attn_bwd_kv_kernel<T, D>, grid, AT_THREADS, smem_kv, stream, p);                                                          \
+    ndt1_launch(attn_bwd_q_kernel<T, D>, grid, AT_THREADS, smem_q, stream, p);                                                            \
   }
   switch (p.hd) { case 16: NDT1_ATT_BWD(4) break; case 32: NDT1_ATT_BWD(8) break; case 64: NDT1_ATT_BWD(16) break; default: NDT1_ATT_BWD(32) }
 #undef NDT1_ATT_BWD
@@ -327,7 +327,7 @@ template <typename T>
 int k_attention_delta(const AttnParams& p, cudaStream_t stream) {
   const long long rows = (long long)p.B * p.L * p.nh;
   if (rows == 0) return 0;
-  attn_delta_kernel<T><<<ndt1_cdiv(rows, 8), 256, 0, stream>>>(p);
+  ndt1_launch(attn_delta_kernel<T>, ndt1_cdiv(rows, 8), 256, 0, stream, p);
   NDT1_CHECK_LAUNCH();
   return 0;
 }

@@ -133,7 +133,7 @@ __device__ __forceinline__ void st_global8(bf16* dst, const float* v) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map256,
-                   const __grid_constant__ CUtensorMap mapo, const __grid_constant__ CUtensorMap mapod, const TcAttn a) {
+                   const __grid_constant__ CUtensorMap mapo, const __grid_constant__ CUtensorMap mapod, const TcAttn a) { pdl_grid_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                 // 2 x [128 x 64]   32 KB
@@ -324,7 +324,7 @@ constexpr int BQ_THREADS = 512;
 __global__ void __launch_bounds__(BQ_THREADS, 1)
 attn_tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map256,
                      const __grid_constant__ CUtensorMap mapdo, const __grid_constant__ CUtensorMap mapo,
-                     const __grid_constant__ CUtensorMap mapdqkv, const TcAttn a) {
+                     const __grid_constant__ CUtensorMap mapdqkv, const TcAttn a) { pdl_grid_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                 // 32 KB   (later: the dQ tile for the bulk store)
@@ -486,7 +486,7 @@ attn_tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
 // Lanes are keys here; warp w owns keys 32*(w%4).. of the tile and the query columns [64*(w/4), +64).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1)
-attn_tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap mapdo, const TcAttn a) {
+attn_tc_bwd_kv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap mapdo, const TcAttn a) { pdl_grid_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;                 // 2 x [128 keys x 64 d]  32 KB
@@ -651,7 +651,7 @@ constexpr int SMEM_BKV2 = 65536 + KV2_STAGES * 32768 + LMAX * 8 + LMAX * 16 + 12
 
 __global__ void __launch_bounds__(KV2_THREADS, 1)   // 18 warps: 5 share a sub-partition -> at most 102 registers per thread
 attn_tc_bwd_kv2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map64,
-                       const __grid_constant__ CUtensorMap mapdo64, const __grid_constant__ CUtensorMap mapdqkv, const TcAttn a) {
+                       const __grid_constant__ CUtensorMap mapdo64, const __grid_constant__ CUtensorMap mapdqkv, const TcAttn a) { pdl_grid_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sK = smem;                          // 2 x [128 keys x 64 d]   32 KB
@@ -889,7 +889,7 @@ int k_attention_tc_fwd(const AttnParams& p, cudaStream_t stream) {
   CUtensorMap mo, mod;
   NDT1_TRY(tc_make_map(o, 64, 128, &mo));
   NDT1_TRY(tc_make_map(od, 64, 128, &mod));
-  attn_tc_fwd_kernel<<<grid, NTHREADS, SMEM_FWD, stream>>>(m128, m256, mo, mod, a);
+  ndt1_launch(attn_tc_fwd_kernel, grid, NTHREADS, SMEM_FWD, stream, m128, m256, mo, mod, a);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -916,16 +916,16 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream) {
   NDT1_TRY(tc_make_map(g, 64, 128, &mdq));
   NDT1_TRY(tc_make_map(o, 64, 128, &mo));
   // query side first: it also forms delta = rowsum(dO * O), which the key side reads
-  attn_tc_bwd_q_kernel<<<grid, BQ_THREADS, SMEM_BQ, stream>>>(m128, m256, mdo, mo, mdq, a);
+  ndt1_launch(attn_tc_bwd_q_kernel, grid, BQ_THREADS, SMEM_BQ, stream, m128, m256, mdo, mo, mdq, a);
   NDT1_CHECK_LAUNCH();
   static const bool old_kv = getenv("NDT1_ATTN_BWD_KV1") && getenv("NDT1_ATTN_BWD_KV1")[0] == '1';
   if (old_kv) {
-    attn_tc_bwd_kv_kernel<<<grid, NTHREADS, SMEM_BKV, stream>>>(m128, mdo, a);
+    ndt1_launch(attn_tc_bwd_kv_kernel, grid, NTHREADS, SMEM_BKV, stream, m128, mdo, a);
   } else {
     CUtensorMap m64, mdo64;
     NDT1_TRY(tc_make_map(q, 64, KV2_CH, &m64));
     NDT1_TRY(tc_make_map(d, 64, KV2_CH, &mdo64));
-    attn_tc_bwd_kv2_kernel<<<grid, KV2_THREADS, SMEM_BKV2, stream>>>(m128, m64, mdo64, mdq, a);
+    ndt1_launch(attn_tc_bwd_kv2_kernel, grid, KV2_THREADS, SMEM_BKV2, stream, m128, m64, mdo64, mdq, a);
   }
   NDT1_CHECK_LAUNCH();
   return 0;

@@ -47,6 +47,45 @@ extern thread_local long long g_ndt1_launches;
     if (_rc != 0) return _rc;                                                   \
   } while (0)
 
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the library starts with pdl_grid_sync() (before its first global
+// access; the tensor-core GEMM after its barrier / tensor-memory set-up) and every launch goes through ndt1_launch(),
+// which sets cudaLaunchAttributeProgrammaticStreamSerialization: the CTAs of kernel n+1 are scheduled -- and run their
+// prologue -- on SMs that kernel n's last wave has left idle, then block in griddepcontrol.wait until kernel n has
+// completed and flushed.  Safe transitively because EVERY CTA of every kernel waits before it touches global memory:
+// kernel n+1 cannot complete before kernel n, so kernel n+2 (which waits on n+1) never runs ahead of n either.
+// NDT1_PDL=0 in the environment turns the attribute off (plain stream order).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool ndt1_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ndt1_launch_cluster(void (*kernel)(KArgs...), int cluster_x, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (ndt1_pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ndt1_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  return ndt1_launch_cluster(kernel, 1, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+
 static inline int ndt1_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------

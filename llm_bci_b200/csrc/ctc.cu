@@ -15,7 +15,7 @@
 
 namespace {
 
-__global__ void log_softmax_kernel(const float* __restrict__ logits, float* __restrict__ logp, long long rows, int V, int ld_in) {
+__global__ void log_softmax_kernel(const float* __restrict__ logits, float* __restrict__ logp, long long rows, int V, int ld_in) { pdl_grid_sync();
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -179,7 +179,7 @@ __device__ __forceinline__ void ctc_sweep(const CtcParams& p, const float* __res
 // instead of O(loss): posteriors keep ~1e-6 relative accuracy where plain fp32 log-space CTC (torch's kernel
 // included) loses ~3e-5 on a 250-frame utterance.
 template <bool FAST, int SPT>
-__global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) {
+__global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) { pdl_grid_sync();
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int LX = 2 * p.S + 1, LXA = SPT * 32;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) 
   }
 }
 
-__global__ void sum_nll_kernel(const float* nll, int B, float* loss) {
+__global__ void sum_nll_kernel(const float* nll, int B, float* loss) { pdl_grid_sync();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float s = 0.f;
     for (int b = 0; b < B; ++b) s += nll[b];
@@ -304,7 +304,7 @@ __global__ void sum_nll_kernel(const float* nll, int B, float* loss) {
 }
 
 // argmax over V then the reference's collapse: emit when id != last EMITTED id and id != blank.
-__global__ void greedy_kernel(const float* logp, int B, int L, int V, int blank, long long* out_ids, long long* out_len) {
+__global__ void greedy_kernel(const float* logp, int B, int L, int V, int blank, long long* out_ids, long long* out_len) { pdl_grid_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   long long last = -1; int n = 0;
@@ -322,7 +322,7 @@ __global__ void greedy_kernel(const float* logp, int B, int L, int V, int blank,
 
 int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaStream_t stream, int ld_in) {
   if (rows == 0) return 0;
-  log_softmax_kernel<<<ndt1_cdiv(rows, 8), 256, 0, stream>>>(logits, logp, rows, V, ld_in > 0 ? ld_in : V);
+  ndt1_launch(log_softmax_kernel, ndt1_cdiv(rows, 8), 256, 0, stream, logits, logp, rows, V, ld_in > 0 ? ld_in : V);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -336,7 +336,7 @@ static int ctc_launch(const CtcParams& p, size_t smem, cudaStream_t stream) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(ctc_kernel<FAST, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  ctc_kernel<FAST, SPT><<<p.B, kCtcWarps * 32, smem, stream>>>(p);
+  ndt1_launch(ctc_kernel<FAST, SPT>, p.B, kCtcWarps * 32, smem, stream, p);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -372,7 +372,7 @@ int k_ctc_fwd_bwd(const float* logp, const long long* targets, const long long* 
   if (fast_math) NDT1_TRY(ctc_dispatch<true>(p, spt, smem, stream));
   else NDT1_TRY(ctc_dispatch<false>(p, spt, smem, stream));
   if (loss) {
-    sum_nll_kernel<<<1, 32, 0, stream>>>(nll, B, loss);
+    ndt1_launch(sum_nll_kernel, 1, 32, 0, stream, nll, B, loss);
     NDT1_CHECK_LAUNCH();
   }
   return 0;
@@ -380,7 +380,7 @@ int k_ctc_fwd_bwd(const float* logp, const long long* targets, const long long* 
 
 int k_ctc_greedy_decode(const float* logp, int B, int L, int V, int blank, long long* out_ids, long long* out_len, cudaStream_t stream) {
   if (B == 0) return 0;
-  greedy_kernel<<<ndt1_cdiv(B, 64), 64, 0, stream>>>(logp, B, L, V, blank, out_ids, out_len);
+  ndt1_launch(greedy_kernel, ndt1_cdiv(B, 64), 64, 0, stream, logp, B, L, V, blank, out_ids, out_len);
   NDT1_CHECK_LAUNCH();
   return 0;
 }

@@ -25,7 +25,7 @@ struct SmoothParams {
   int use_philox; unsigned long long seed;
 };
 
-__global__ void smooth_noise_kernel(const SmoothParams p) {
+__global__ void smooth_noise_kernel(const SmoothParams p) { pdl_grid_sync();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int t0 = blockIdx.y * SM_TT;
   const int b = blockIdx.z;
@@ -98,7 +98,7 @@ __device__ __forceinline__ void white_quad(unsigned long long seed, unsigned lon
   box_muller(r1.x, r1.y, nz[2], nz[3]);
 }
 template <int K>
-__global__ void __launch_bounds__(256) smooth_noise_vec_kernel(const SmoothParams p) {
+__global__ void __launch_bounds__(256) smooth_noise_vec_kernel(const SmoothParams p) { pdl_grid_sync();
   const int n4 = blockIdx.x * 64 + (threadIdx.x & 63);          // channel quad
   const int strip = blockIdx.y * 4 + (threadIdx.x >> 6);
   const int b = blockIdx.z;
@@ -185,12 +185,12 @@ int k_smooth_noise(const float* x, float* out, int B, int T, int N, const float*
   p.use_philox = use_philox; p.seed = seed;
   if (K == 13 && N % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 && (!white || ((uintptr_t)white & 15) == 0)) {
     dim3 grid(ndt1_cdiv(N / 4, 64), ndt1_cdiv(ndt1_cdiv(T, SMV_TT), 4), B);     // the reference's default: gaussian(1 + 6 sd, sd = 2)
-    smooth_noise_vec_kernel<13><<<grid, 256, 0, stream>>>(p);
+    ndt1_launch(smooth_noise_vec_kernel<13>, grid, 256, 0, stream, p);
     NDT1_CHECK_LAUNCH();
     return 0;
   }
   dim3 block(128), grid(ndt1_cdiv(N, 128), ndt1_cdiv(T, SM_TT), B);
-  smooth_noise_kernel<<<grid, block, 0, stream>>>(p);
+  ndt1_launch(smooth_noise_kernel, grid, block, 0, stream, p);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -241,7 +241,7 @@ __device__ __forceinline__ bool masker_mask_at(const MaskerParams& p, int b, int
   }
 }
 
-__global__ void masker_pass1(const MaskerParams p) {
+__global__ void masker_pass1(const MaskerParams p) { pdl_grid_sync();
   const long long total = (long long)p.B * p.T * p.N;
   float lmax = -INFINITY;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -263,7 +263,7 @@ __global__ void masker_pass1(const MaskerParams p) {
   }
 }
 
-__global__ void masker_pass2(const MaskerParams p) {
+__global__ void masker_pass2(const MaskerParams p) { pdl_grid_sync();
   const long long total = (long long)p.B * p.T * p.N;
   const float mx = ordered_to_f32(*p.max_bits);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -291,16 +291,16 @@ int k_masker_apply(float* spikes, int B, int T, int N, int mode, int timespan, c
   p.mask_out = mask_out; p.targets_mask = targets_mask; p.max_bits = scratch;
   NDT1_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(unsigned int), stream));  // ordered(0) < ordered(-inf)
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  masker_pass1<<<blocks, 256, 0, stream>>>(p);
+  ndt1_launch(masker_pass1, blocks, 256, 0, stream, p);
   NDT1_CHECK_LAUNCH();
-  masker_pass2<<<blocks, 256, 0, stream>>>(p);
+  ndt1_launch(masker_pass2, blocks, 256, 0, stream, p);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
 
 // Device Bernoulli / uniform draws for the masker's fast path (own Philox stream).
 namespace {
-__global__ void bernoulli_u8_kernel(unsigned char* out, long long n, float prob, unsigned long long seed, unsigned long long stream) {
+__global__ void bernoulli_u8_kernel(unsigned char* out, long long n, float prob, unsigned long long seed, unsigned long long stream) { pdl_grid_sync();
   const double tt = (double)prob * 4294967296.0;
   const uint32_t thr = tt <= 0.0 ? 0u : (tt >= 4294967295.0 ? 4294967295u : (uint32_t)tt);  // P(u < thr) = prob
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n; i += (long long)gridDim.x * blockDim.x) {
@@ -310,7 +310,7 @@ __global__ void bernoulli_u8_kernel(unsigned char* out, long long n, float prob,
       if (i * 4 + k < n) out[i * 4 + k] = (prob >= 1.f) ? 1 : (u[k] < thr ? 1 : 0);
   }
 }
-__global__ void uniform_f32_kernel(float* out, long long n, unsigned long long seed, unsigned long long stream) {
+__global__ void uniform_f32_kernel(float* out, long long n, unsigned long long seed, unsigned long long stream) { pdl_grid_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n; i += (long long)gridDim.x * blockDim.x) {
     Philox4 r = philox4x32(seed, i, stream);
     const uint32_t u[4] = {r.x, r.y, r.z, r.w};
@@ -323,14 +323,14 @@ __global__ void uniform_f32_kernel(float* out, long long n, unsigned long long s
 int k_bernoulli_u8(unsigned char* out, long long n, float prob, unsigned long long seed, unsigned long long stream_id, cudaStream_t stream) {
   if (n == 0) return 0;
   const int blocks = (int)((n / 4 + 255) / 256 < 148 * 8 ? (n / 4 + 255) / 256 + 1 : 148 * 8);
-  bernoulli_u8_kernel<<<blocks, 256, 0, stream>>>(out, n, prob, seed, stream_id);
+  ndt1_launch(bernoulli_u8_kernel, blocks, 256, 0, stream, out, n, prob, seed, stream_id);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
 int k_uniform_f32(float* out, long long n, unsigned long long seed, unsigned long long stream_id, cudaStream_t stream) {
   if (n == 0) return 0;
   const int blocks = (int)((n / 4 + 255) / 256 < 148 * 8 ? (n / 4 + 255) / 256 + 1 : 148 * 8);
-  uniform_f32_kernel<<<blocks, 256, 0, stream>>>(out, n, seed, stream_id);
+  ndt1_launch(uniform_f32_kernel, blocks, 256, 0, stream, out, n, seed, stream_id);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -344,7 +344,7 @@ int k_uniform_f32(float* out, long long n, unsigned long long seed, unsigned lon
 // ===========================================================================
 namespace {
 template <typename E>
-__global__ void pad_pack_kernel(const E* src, const long long* offsets, E* dst, int B, int P, int inner, int side_left, int full, E value) {
+__global__ void pad_pack_kernel(const E* src, const long long* offsets, E* dst, int B, int P, int inner, int side_left, int full, E value) { pdl_grid_sync();
   // full = padded length before truncation (max(max_len, min_length)); P = min(truncate, full)
   const long long total = (long long)B * P * inner;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -368,9 +368,9 @@ int k_pad_pack(const void* src, const long long* offsets, void* dst, int B, int 
   if (total == 0) return 0;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   if (elem_size == 4)
-    pad_pack_kernel<float><<<blocks, 256, 0, stream>>>((const float*)src, offsets, (float*)dst, B, P, inner, side_left, full, (float)value);
+    ndt1_launch(pad_pack_kernel<float>, blocks, 256, 0, stream, (const float*)src, offsets, (float*)dst, B, P, inner, side_left, full, (float)value);
   else if (elem_size == 8)
-    pad_pack_kernel<long long><<<blocks, 256, 0, stream>>>((const long long*)src, offsets, (long long*)dst, B, P, inner, side_left, full,
+    ndt1_launch(pad_pack_kernel<long long>, blocks, 256, 0, stream, (const long long*)src, offsets, (long long*)dst, B, P, inner, side_left, full,
                                                            (long long)value);
   else
     NDT1_REQUIRE(false, "pad_pack: element size %d unsupported (4 = float32, 8 = int64)", elem_size);
@@ -382,7 +382,7 @@ int k_pad_pack(const void* src, const long long* offsets, void* dst, int B, int 
 // Casts and small utilities
 // ===========================================================================
 namespace {
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long rows, int cols, long long ld_in, long long ld_out) {
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long rows, int cols, long long ld_in, long long ld_out) { pdl_grid_sync();
   const long long total4 = rows * (cols / 4);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / (cols / 4);
@@ -393,7 +393,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
     *(uint2*)(out + r * ld_out + c) = o;
   }
 }
-__global__ void cast_f32_bf16_scalar_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long rows, int cols, long long ld_in, long long ld_out) {
+__global__ void cast_f32_bf16_scalar_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long rows, int cols, long long ld_in, long long ld_out) { pdl_grid_sync();
   const long long total = rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols; const int c = (int)(i % cols);
@@ -407,8 +407,8 @@ int k_cast_f32_bf16(const float* in, bf16* out, long long rows, int cols, long l
   const bool vec = (cols % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 7) == 0);
   const long long work = vec ? rows * (cols / 4) : rows * cols;
   const int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
-  if (vec) cast_f32_bf16_kernel<<<blocks, 256, 0, stream>>>(in, out, rows, cols, ld_in, ld_out);
-  else cast_f32_bf16_scalar_kernel<<<blocks, 256, 0, stream>>>(in, out, rows, cols, ld_in, ld_out);
+  if (vec) ndt1_launch(cast_f32_bf16_kernel, blocks, 256, 0, stream, in, out, rows, cols, ld_in, ld_out);
+  else ndt1_launch(cast_f32_bf16_scalar_kernel, blocks, 256, 0, stream, in, out, rows, cols, ld_in, ld_out);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -416,7 +416,7 @@ int k_cast_f32_bf16(const float* in, bf16* out, long long rows, int cols, long l
 // All the bf16 weight copies of a forward in ONE launch: up to CAST_MAX_SEGS contiguous fp32 -> bf16 segments
 // (element counts multiples of 8), flattened into 2048-element chunks; a block finds its segment by a short scan.
 namespace {
-__global__ void __launch_bounds__(256) cast_multi_kernel(const CastSegs segs) {
+__global__ void __launch_bounds__(256) cast_multi_kernel(const CastSegs segs) { pdl_grid_sync();
   for (long long chunk = blockIdx.x; chunk < segs.total_chunks; chunk += gridDim.x) {
     int k = 0;
     while (k + 1 < segs.n && chunk >= segs.first_chunk[k + 1]) ++k;
@@ -443,7 +443,7 @@ int k_cast_multi(CastSegs& segs, cudaStream_t stream) {
   }
   segs.total_chunks = chunks;
   const int blocks = (int)(chunks < 148 * 16 ? chunks : 148 * 16);
-  cast_multi_kernel<<<blocks, 256, 0, stream>>>(segs);
+  ndt1_launch(cast_multi_kernel, blocks, 256, 0, stream, segs);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -454,7 +454,7 @@ int k_cast_multi(CastSegs& segs, cudaStream_t stream) {
 // ===========================================================================
 namespace {
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ in, float* __restrict__ out, long long rows, int cols, long long ld) {
+__global__ void colsum_kernel(const T* __restrict__ in, float* __restrict__ out, long long rows, int cols, long long ld) { pdl_grid_sync();
   __shared__ float sm[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
@@ -477,7 +477,7 @@ __global__ void colsum_kernel(const T* __restrict__ in, float* __restrict__ out,
 namespace {
 // 8 columns per thread (one 16-byte load of bf16, two of fp32); grid (cols/256, row-chunks); 32x8 threads
 template <typename T>
-__global__ void colsum8_kernel(const T* __restrict__ in, float* __restrict__ out, long long rows, int cols, long long ld) {
+__global__ void colsum8_kernel(const T* __restrict__ in, float* __restrict__ out, long long rows, int cols, long long ld) { pdl_grid_sync();
   __shared__ float sm[8][32][9];
   const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -518,13 +518,13 @@ int k_colsum(const T* in, float* out, long long rows, int cols, long long ld, cu
     int chunks8 = (int)(rows / 128); if (chunks8 < 1) chunks8 = 1;
     const int gx = ndt1_cdiv(cols, 256);
     while (chunks8 > 1 && (long long)chunks8 * gx > 148 * 4) --chunks8;
-    colsum8_kernel<T><<<dim3(gx, chunks8), block, 0, stream>>>(in, out, rows, cols, ld);
+    ndt1_launch(colsum8_kernel<T>, dim3(gx, chunks8), block, 0, stream, in, out, rows, cols, ld);
     NDT1_CHECK_LAUNCH();
     return 0;
   }
   int chunks = (int)(rows / 256); if (chunks < 1) chunks = 1; if (chunks > 64) chunks = 64;
   dim3 grid(ndt1_cdiv(cols, 32), chunks);
-  colsum_kernel<T><<<grid, block, 0, stream>>>(in, out, rows, cols, ld);
+  ndt1_launch(colsum_kernel<T>, grid, block, 0, stream, in, out, rows, cols, ld);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -540,7 +540,7 @@ namespace {
 template <typename T>
 __global__ void grad_prep_kernel(const float* __restrict__ g, T* __restrict__ out, long long rows, int cols, float drop_p,
                                  unsigned long long seed, unsigned long long stream_id, float* dtab, const long long* idx, int tab_ld,
-                                 int rows_per_b, long long idx_stride, int prefix) {
+                                 int rows_per_b, long long idx_stride, int prefix) { pdl_grid_sync();
   const long long total4 = rows * (cols / 4);
   const uint32_t thr = drop_threshold(drop_p);
   const float ik = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
@@ -574,7 +574,7 @@ int k_grad_prep(const float* g, T* out, long long rows, int cols, float drop_p, 
   if (rows * cols == 0) return 0;
   const long long work = rows * (cols / 4);
   const int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
-  grad_prep_kernel<T><<<blocks, 256, 0, stream>>>(g, out, rows, cols, drop_p, seed, stream_id, dtab, idx, tab_ld, rows_per_b > 0 ? rows_per_b : 1,
+  ndt1_launch(grad_prep_kernel<T>, blocks, 256, 0, stream, g, out, rows, cols, drop_p, seed, stream_id, dtab, idx, tab_ld, rows_per_b > 0 ? rows_per_b : 1,
                                                   idx_stride, prefix);
   NDT1_CHECK_LAUNCH();
   return 0;
@@ -600,7 +600,7 @@ struct ReconParams {
   float* loss; long long* count; const float* dloss;
 };
 
-__global__ void recon_loss_kernel(const ReconParams p) {
+__global__ void recon_loss_kernel(const ReconParams p) { pdl_grid_sync();
   const long long total = (long long)p.B * p.T * p.N;
   float lsum = 0.f; long long cnt = 0;
   const float gs = p.dloss ? *p.dloss : 1.f;
@@ -647,7 +647,7 @@ int k_recon_loss(const float* pred, const float* target, float* dpred, const lon
   if (total == 0) return 0;
   ReconParams p{pred, target, dpred, tmask, pmask, B, T, N, kind, shift, relu_out, loss, count, dloss};
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  recon_loss_kernel<<<blocks, 256, 0, stream>>>(p);
+  ndt1_launch(recon_loss_kernel, blocks, 256, 0, stream, p);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -657,7 +657,7 @@ int k_recon_loss(const float* pred, const float* target, float* dpred, const lon
 // ===========================================================================
 namespace {
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-                             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) {
+                             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale) { pdl_grid_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
     float pi = p[i] * (1.f - lr * wd);
@@ -676,7 +676,7 @@ int k_adamw(float* p, const float* g, float* m, float* v, long long n, float lr,
   if (n == 0) return 0;
   const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  adamw_kernel<<<blocks, 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2, gscale);
+  ndt1_launch(adamw_kernel, blocks, 256, 0, stream, p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2, gscale);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -685,7 +685,7 @@ int k_adamw(float* p, const float* g, float* m, float* v, long long n, float lr,
 namespace {
 __global__ void __launch_bounds__(256) adamw_fused_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                                           float4* __restrict__ v, long long n4, float lr, float b1, float b2, float eps,
-                                                          float wd, float bc1, float rbc2, float gscale, uint2* __restrict__ shadow, int zero_grad) {
+                                                          float wd, float bc1, float rbc2, float gscale, uint2* __restrict__ shadow, int zero_grad) { pdl_grid_sync();
   const float decay = 1.f - lr * wd, step = lr / bc1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 g4 = g[i], m4 = m[i], v4 = v[i];
@@ -719,7 +719,7 @@ int k_adamw_fused(float* p, float* g, float* m, float* v, long long n, float lr,
   const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
   const long long n4 = n / 4;
   const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
-  adamw_fused_kernel<<<blocks, 256, 0, stream>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, lr, b1, b2, eps, wd, bc1,
+  ndt1_launch(adamw_fused_kernel, blocks, 256, 0, stream, (float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, lr, b1, b2, eps, wd, bc1,
                                                  1.0f / sqrtf(bc2), gscale, (uint2*)shadow, zero_grad);
   NDT1_CHECK_LAUNCH();
   return 0;
@@ -730,7 +730,7 @@ int k_adamw_fused(float* p, float* g, float* m, float* v, long long n, float lr,
 // ===========================================================================
 namespace {
 // mask'[b,r] = AND_{k<size} mask[b, r*stride + k]   (models/ndt1.py:182-183)
-__global__ void stack_mask_kernel(const long long* mask, long long* out, int B, int T, int Tp, int size, int stride, int n_prefix) {
+__global__ void stack_mask_kernel(const long long* mask, long long* out, int B, int T, int Tp, int size, int stride, int n_prefix) { pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int L = Tp + n_prefix;
   if (i >= B * L) return;
@@ -745,14 +745,14 @@ __global__ void stack_mask_kernel(const long long* mask, long long* out, int B, 
   out[i] = m;
 }
 // x[b, slot, :] = table[idx[b], :]  (block / day tokens, models/ndt1.py:192-201)
-__global__ void token_rows_kernel(const float* table, const long long* idx, float* x, int B, int L, int H, int slot) {
+__global__ void token_rows_kernel(const float* table, const long long* idx, float* x, int B, int L, int H, int slot) { pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * H) return;
   const int b = i / H, c = i % H;
   x[((long long)b * L + slot) * H + c] = table[idx[b] * H + c];
 }
 template <typename T>
-__global__ void token_rows_grad_kernel(float* dtable, const long long* idx, const T* dx, int B, int L, int H, int slot) {
+__global__ void token_rows_grad_kernel(float* dtable, const long long* idx, const T* dx, int B, int L, int H, int slot) { pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * H) return;
   const int b = i / H, c = i % H;
@@ -763,18 +763,18 @@ __global__ void token_rows_grad_kernel(float* dtable, const long long* idx, cons
 int k_stack_mask(const long long* mask, long long* out, int B, int T, int Tp, int size, int stride, int n_prefix, cudaStream_t stream) {
   const int n = B * (Tp + n_prefix);
   if (n == 0) return 0;
-  stack_mask_kernel<<<ndt1_cdiv(n, 256), 256, 0, stream>>>(mask, out, B, T, Tp, size, stride, n_prefix);
+  ndt1_launch(stack_mask_kernel, ndt1_cdiv(n, 256), 256, 0, stream, mask, out, B, T, Tp, size, stride, n_prefix);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
 int k_token_rows(const float* table, const long long* idx, float* x, int B, int L, int H, int slot, cudaStream_t stream) {
-  token_rows_kernel<<<ndt1_cdiv(B * H, 256), 256, 0, stream>>>(table, idx, x, B, L, H, slot);
+  ndt1_launch(token_rows_kernel, ndt1_cdiv(B * H, 256), 256, 0, stream, table, idx, x, B, L, H, slot);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
 template <typename T>
 int k_token_rows_grad(float* dtable, const long long* idx, const T* dx, int B, int L, int H, int slot, cudaStream_t stream) {
-  token_rows_grad_kernel<T><<<ndt1_cdiv(B * H, 256), 256, 0, stream>>>(dtable, idx, dx, B, L, H, slot);
+  ndt1_launch(token_rows_grad_kernel<T>, ndt1_cdiv(B * H, 256), 256, 0, stream, dtable, idx, dx, B, L, H, slot);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -787,7 +787,7 @@ template int k_token_rows_grad<bf16>(float*, const long long*, const bf16*, int,
 // ---------------------------------------------------------------------------
 namespace {
 template <typename T>
-__global__ void scale_cast_pad_kernel(const float* __restrict__ in, T* __restrict__ out, long long rows, int cols, int ld_out, const float* scale) {
+__global__ void scale_cast_pad_kernel(const float* __restrict__ in, T* __restrict__ out, long long rows, int cols, int ld_out, const float* scale) { pdl_grid_sync();
   const float s = scale ? *scale : 1.f;
   const long long total = rows * ld_out;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -795,16 +795,16 @@ __global__ void scale_cast_pad_kernel(const float* __restrict__ in, T* __restric
     out[i] = from_f32<T>(c < cols ? in[r * cols + c] * s : 0.f);
   }
 }
-__global__ void stacked_lens_kernel(const long long* lens, long long* out, int B, int stack, int size, int stride) {
+__global__ void stacked_lens_kernel(const long long* lens, long long* out, int B, int stack, int size, int stride) { pdl_grid_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   out[b] = stack ? (long long)(1.0f + (float)(lens[b] - size) / (float)stride) : lens[b];
 }
-__global__ void set_i64_kernel(long long* p, long long v) { *p = v; }
-__global__ void relu_inplace_kernel(float* x, long long n) {
+__global__ void set_i64_kernel(long long* p, long long v) { pdl_grid_sync(); *p = v; }
+__global__ void relu_inplace_kernel(float* x, long long n) { pdl_grid_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = fmaxf(x[i], 0.f);
 }
-__global__ void and_mask_kernel(const long long* tmask, const long long* pmask, long long* out, int B, int T, int N) {
+__global__ void and_mask_kernel(const long long* tmask, const long long* pmask, long long* out, int B, int T, int N) { pdl_grid_sync();
   const long long total = (long long)B * T * N;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
     out[e] = tmask[e] & pmask[e / N];
@@ -816,7 +816,7 @@ int k_scale_cast_pad(const float* in, T* out, long long rows, int cols, int ld_o
   const long long total = rows * ld_out;
   if (total == 0) return 0;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  scale_cast_pad_kernel<T><<<blocks, 256, 0, stream>>>(in, out, rows, cols, ld_out, scale);
+  ndt1_launch(scale_cast_pad_kernel<T>, blocks, 256, 0, stream, in, out, rows, cols, ld_out, scale);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -825,19 +825,19 @@ template int k_scale_cast_pad<bf16>(const float*, bf16*, long long, int, int, co
 
 int k_stacked_lens(const long long* lens, long long* out, int B, int stack, int size, int stride, cudaStream_t stream) {
   if (B == 0) return 0;
-  stacked_lens_kernel<<<ndt1_cdiv(B, 128), 128, 0, stream>>>(lens, out, B, stack, size, stride);
+  ndt1_launch(stacked_lens_kernel, ndt1_cdiv(B, 128), 128, 0, stream, lens, out, B, stack, size, stride);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
 int k_set_i64(long long* p, long long v, cudaStream_t stream) {
-  set_i64_kernel<<<1, 1, 0, stream>>>(p, v);
+  ndt1_launch(set_i64_kernel, 1, 1, 0, stream, p, v);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
 int k_relu_inplace(float* x, long long n, cudaStream_t stream) {
   if (n == 0) return 0;
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  relu_inplace_kernel<<<blocks, 256, 0, stream>>>(x, n);
+  ndt1_launch(relu_inplace_kernel, blocks, 256, 0, stream, x, n);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -845,7 +845,7 @@ int k_and_mask(const long long* tmask, const long long* pmask, long long* out, i
   const long long total = (long long)B * T * N;
   if (total == 0) return 0;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  and_mask_kernel<<<blocks, 256, 0, stream>>>(tmask, pmask, out, B, T, N);
+  ndt1_launch(and_mask_kernel, blocks, 256, 0, stream, tmask, pmask, out, B, T, N);
   NDT1_CHECK_LAUNCH();
   return 0;
 }

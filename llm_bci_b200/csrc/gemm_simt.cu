@@ -17,7 +17,7 @@ __device__ __forceinline__ float ld_elem(const GemmOperand& o, int b, int row, i
 }
 
 template <typename T>
-__global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmProblem p) {
+__global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmProblem p) { pdl_grid_sync();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
 
@@ -134,8 +134,8 @@ int gemm_simt_launch(const GemmProblem& p, int in_bf16, cudaStream_t stream) {
   NDT1_REQUIRE(p.M > 0 && p.N > 0 && p.nb_out > 0, "gemm_simt: empty problem M=%d N=%d nb=%d", p.M, p.N, p.nb_out);
   NDT1_REQUIRE(p.split_k <= 1 || p.epi.accumulate, "gemm_simt: split_k needs an accumulating epilogue");
   dim3 grid(ndt1_cdiv(p.N, BN), ndt1_cdiv(p.M, BM) * p.nb_out, p.split_k > 1 ? p.split_k : 1);
-  if (in_bf16) gemm_simt_kernel<bf16><<<grid, NT, 0, stream>>>(p);
-  else gemm_simt_kernel<float><<<grid, NT, 0, stream>>>(p);
+  if (in_bf16) ndt1_launch(gemm_simt_kernel<bf16>, grid, NT, 0, stream, p);
+  else ndt1_launch(gemm_simt_kernel<float>, grid, NT, 0, stream, p);
   NDT1_CHECK_LAUNCH();
   return 0;
 }

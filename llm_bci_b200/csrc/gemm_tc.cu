@@ -411,6 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (CTAS == 2) cluster_sync_all();            // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();       // everything above touched only shared / tensor memory and the kernel parameters
 
   const int total_kb = p.nchunk * p.kb_per_chunk;
 
@@ -673,17 +674,7 @@ int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp
     rec->flops = 2.0 * tp.M * (double)tp.N * (double)tp.nchunk * tp.chunk_k_valid * (tp.mode == GEMM_TN ? 1 : tp.nb_out);
     NDT1_CUDA_CHECK(cudaEventRecord(rec->e0, stream));
   }
-  if (CTAS == 1) {
-    gemm_tc_kernel<BN, MODE, CTAS, EPI><<<grid, kThreads, SMEM, stream>>>(ma, mb, tp);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = SMEM; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    NDT1_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, CTAS, EPI>, ma, mb, tp));
-  }
+  NDT1_CUDA_CHECK(ndt1_launch_cluster(gemm_tc_kernel<BN, MODE, CTAS, EPI>, CTAS, dim3(grid), dim3(kThreads), SMEM, stream, ma, mb, tp));
   NDT1_CHECK_LAUNCH();
   if (rec) NDT1_CUDA_CHECK(cudaEventRecord(rec->e1, stream));
   return 0;

@@ -37,7 +37,7 @@ __device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
 template <typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean,
-                                                              float* __restrict__ rstd, long long rows, int H, float eps) {
+                                                              float* __restrict__ rstd, long long rows, int H, float eps) { pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int nv = H / 4;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 1)
 ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
               const float* __restrict__ rstd, float* __restrict__ dres, T* __restrict__ out_lp, float drop_p, unsigned long long seed,
               unsigned long long stream_id, long long rows, int H, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              float* __restrict__ colsum_out) {
+              float* __restrict__ colsum_out) { pdl_grid_sync();
   extern __shared__ float sm[];   // [warps][3][H]: per-warp partial sums of dgamma | dbeta | colsum(out_lp)
   typedef typename Raw4<T>::type raw_t;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -229,7 +229,7 @@ constexpr int LNF_ROWS = 8;   // forward: 8 rows per group (only 4 registers per
 template <typename T, int NT>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : 1) ln_fwd_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean,
-                                                           float* __restrict__ rstd, long long rows, int H, float eps) {
+                                                           float* __restrict__ rstd, long long rows, int H, float eps) { pdl_grid_sync();
   __shared__ float red[2 * 32 * 8];
   const int c = threadIdx.x, nwarps = blockDim.x >> 5;
   const float4 g = __ldg((const float4*)gamma + c), bt = __ldg((const float4*)beta + c);
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1)
 ln_bwd_rows_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
                    const float* __restrict__ rstd, float* __restrict__ dres, T* __restrict__ out_lp, float drop_p, unsigned long long seed,
                    unsigned long long stream_id, long long rows, int H, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                   float* __restrict__ colsum_out) {
+                   float* __restrict__ colsum_out) { pdl_grid_sync();
   __shared__ float red[2 * 32 * 8];
   typedef typename Raw4<T>::type raw_t;
   const int c = threadIdx.x, lane = c & 31, nwarps = blockDim.x >> 5;
@@ -370,12 +370,12 @@ int k_layernorm_fwd(const float* x, const float* gamma, const float* beta, T* y,
     long long nb = (rows + LNF_ROWS - 1) / LNF_ROWS;
     const long long cap = (long long)g_sms() * (threads <= 256 ? 4 : 1);
     if (nb > cap) nb = cap;
-    if (threads <= 256) ln_fwd_rows_kernel<T, 256><<<(int)nb, threads, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, H, eps);
-    else ln_fwd_rows_kernel<T, 1024><<<(int)nb, threads, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, H, eps);
+    if (threads <= 256) ndt1_launch(ln_fwd_rows_kernel<T, 256>, (int)nb, threads, 0, stream, x, gamma, beta, y, mean, rstd, rows, H, eps);
+    else ndt1_launch(ln_fwd_rows_kernel<T, 1024>, (int)nb, threads, 0, stream, x, gamma, beta, y, mean, rstd, rows, H, eps);
     NDT1_CHECK_LAUNCH();
     return 0;
   }
-  ln_fwd_kernel<T><<<ln_blocks(rows), LN_WARPS * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, H, eps);
+  ndt1_launch(ln_fwd_kernel<T>, ln_blocks(rows), LN_WARPS * 32, 0, stream, x, gamma, beta, y, mean, rstd, rows, H, eps);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -394,10 +394,10 @@ int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float
     const long long cap = (long long)sms * (threads <= 256 ? 2 : 1);
     if (nbr > cap) nbr = cap;
     if (threads <= 256)
-      ln_bwd_rows_kernel<T, 256><<<(int)nbr, threads, 0, stream>>>(dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed, stream_id, rows, H,
+      ndt1_launch(ln_bwd_rows_kernel<T, 256>, (int)nbr, threads, 0, stream, dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed, stream_id, rows, H,
                                                                     dgamma, dbeta, out_lp ? colsum_out : nullptr);
     else
-      ln_bwd_rows_kernel<T, 1024><<<(int)nbr, threads, 0, stream>>>(dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed, stream_id, rows, H,
+      ndt1_launch(ln_bwd_rows_kernel<T, 1024>, (int)nbr, threads, 0, stream, dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed, stream_id, rows, H,
                                                                      dgamma, dbeta, out_lp ? colsum_out : nullptr);
     NDT1_CHECK_LAUNCH();
     return 0;
@@ -410,7 +410,7 @@ int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr[sizeof(T) == 2] = smem;
   }
-  ln_bwd_kernel<T><<<(int)nb, LNB_WARPS * 32, smem, stream>>>(dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed,
+  ndt1_launch(ln_bwd_kernel<T>, (int)nb, LNB_WARPS * 32, smem, stream, dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed,
                                                                                stream_id, rows, H, dgamma, dbeta, out_lp ? colsum_out : nullptr);
   NDT1_CHECK_LAUNCH();
   return 0;
