@@ -93,8 +93,12 @@ def main():
     update_config, NDT1 = R["update_config"], R["NDT1"]
     torch.set_num_threads(8)
     only_full = "--only-full" in sys.argv
+    if "--only-variants" in sys.argv:
+        variant_cases(R)
+        return
     if not only_full:
         small_cases(R)
+        variant_cases(R)
     full_case(R)
 
 
@@ -266,6 +270,44 @@ def small_cases(R):
         d[f"ctc_out/{i}"] = np.array(R["format_ctc"](s, list(range(41)), 0), dtype=np.int64)
     np.savez_compressed(os.path.join(HERE, "index_ops.npz"), **d)
 
+
+VARIANTS = {
+    # name: (model overrides on top of small_ctc_overrides(), needs day_idx)
+    "rope": ({"encoder": {"transformer": {"use_rope": True, "rope_theta": 10000.0}}}, False),
+    "adapt": ({"encoder": {"embedder": {"adapt": True, "n_days": 4}}}, True),
+    "gelu_factors": ({"encoder": {"embedder": {"act": "gelu"},
+                                  "factors": {"active": True, "size": 48, "act": "relu", "bias": True, "dropout": 0.0,
+                                              "fixup_init": True, "init_range": 0.1}}}, False),
+    "rope_adapt_gelu_factors": ({"encoder": {"transformer": {"use_rope": True, "rope_theta": 500.0},
+                                             "embedder": {"adapt": True, "n_days": 3, "act": "gelu", "pos": False},
+                                             "factors": {"active": True, "size": 40, "act": "gelu", "bias": False, "dropout": 0.0,
+                                                         "fixup_init": False, "init_range": 0.1}}}, True),
+}
+
+
+def variant_cases(R):
+    """Options of the path that the shipped yaml leaves off (models/ndt1.py:118-127 adapt, :262-266, 285-286 RoPE, :146 embedder
+    activation, :358-366 factors projection): one small CTC model per combination, outputs of the unmodified reference."""
+    update_config, NDT1 = R["update_config"], R["NDT1"]
+    trainer = update_config("configs/trainer_ctc_ndt1.yaml", None)
+    base = update_config(copy.deepcopy(dict(trainer.model)), small_ctc_overrides())
+    batch = make_ctc_batch(3, 120, 16, seed=5)
+    d = flat("batch", batch)
+    for name, (over, days) in VARIANTS.items():
+        cfg = update_config(copy.deepcopy(dict(base)), over)
+        torch.manual_seed(21)
+        model = NDT1(cfg, **trainer.method.model_kwargs)
+        b = dict(batch)
+        if days:
+            b["day_idx"] = torch.tensor([2, 0, 2])
+            d[f"{name}/day_idx"] = b["day_idx"].numpy()
+        out, grads = run_ref(model, b, train=True)
+        d.update(flat(f"{name}/param", dict(model.state_dict())))
+        d.update(flat(f"{name}/grad", grads))
+        d[f"{name}/out/loss"] = out.loss.detach().numpy()
+        d[f"{name}/out/preds"] = out.preds.detach().numpy()
+        print("variant", name, "loss", float(out.loss))
+    np.savez_compressed(os.path.join(HERE, "ctc_variants.npz"), **d)
 
 
 def full_case(R):

@@ -195,3 +195,41 @@ def test_full_size_b4_matches_reference():
     gn = np.array([float(grads[n].double().norm()) for n in names])
     scale = g["grad_norm"].max()
     assert np.all(np.abs(gn - g["grad_norm"]) <= 2e-4 * np.maximum(g["grad_norm"], 1e-4 * scale))
+
+
+VARIANTS = {
+    "rope": {"encoder": {"transformer": {"use_rope": True, "rope_theta": 10000.0}}},
+    "adapt": {"encoder": {"embedder": {"adapt": True, "n_days": 4}}},
+    "gelu_factors": {"encoder": {"embedder": {"act": "gelu"},
+                                 "factors": {"active": True, "size": 48, "act": "relu", "bias": True, "dropout": 0.0,
+                                             "fixup_init": True, "init_range": 0.1}}},
+    "rope_adapt_gelu_factors": {"encoder": {"transformer": {"use_rope": True, "rope_theta": 500.0},
+                                            "embedder": {"adapt": True, "n_days": 3, "act": "gelu", "pos": False},
+                                            "factors": {"active": True, "size": 40, "act": "gelu", "bias": False, "dropout": 0.0,
+                                                        "fixup_init": False, "init_range": 0.1}}},
+}
+
+
+def variant_case(g, name):
+    """(config, parameters, batch) of one case of tests/golden/ctc_variants.npz."""
+    cfg = update_config(small_ctc_cfg(), VARIANTS[name])
+    params = {k: torch.from_numpy(v) for k, v in sub(g, f"{name}/param").items()}
+    batch = {k: torch.from_numpy(v) for k, v in sub(g, "batch").items()}
+    if f"{name}/day_idx" in g:
+        batch["day_idx"] = torch.from_numpy(g[f"{name}/day_idx"])
+    return cfg, params, batch
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_ctc_variants_rope_adapt_gelu_factors(name):
+    """Options the shipped yaml leaves off: per-day embedding, RoPE, GELU embedder activation, factors projection."""
+    g = load("ctc_variants.npz")
+    cfg, params, batch = variant_case(g, name)
+    out, grads = O.ndt1_loss_and_grads(params, cfg, CTC_KW, batch, training=True)
+    assert abs(float(out["loss"]) - float(g[f"{name}/out/loss"])) <= 2e-5 * abs(float(g[f"{name}/out/loss"]))
+    assert rel(out["preds"].detach().numpy(), g[f"{name}/out/preds"]) < 2e-5
+    ref = sub(g, f"{name}/grad")
+    gscale = max(np.abs(v).max() for v in ref.values())
+    assert set(ref) == set(grads)
+    for k, r in ref.items():
+        assert np.abs(grads[k].numpy() - r).max() <= 5e-5 * max(np.abs(r).max(), 1e-3 * gscale), k
