@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NDT1_ABI_VERSION 1
+#define NDT1_ABI_VERSION 2
 
 /* activations (transformers ACT2FN names used by configs/ndt1.yaml) */
 enum { NDT1_ACT_IDENTITY = 0, NDT1_ACT_SOFTSIGN = 1, NDT1_ACT_GELU = 2, NDT1_ACT_RELU = 3 };
@@ -156,11 +156,15 @@ typedef struct {
 /* Parameter / gradient pointer tables, in the order of the reference's
  * state_dict; absent tensors are NULL. */
 #define NDT1_MAX_LAYERS 32
+#define NDT1_MAX_DAYS 64
 typedef struct {
-  float* embed_w; float* embed_b;      /* embed_spikes (D, N), (D); adapt: n_days copies back to back */
+  float* embed_w; float* embed_b;      /* embed_spikes (D, N), (D); unused (NULL) with adapt */
   float* proj_w;  float* proj_b;       /* stack_projection (H, S*D) or projection (H, D) */
   float* pos_w;                        /* embed_pos (max_F, H) */
   float* block_emb; float* day_emb;    /* (n_blocks, H), (n_days, H) */
+  /* adapt (models/ndt1.py:118-127,170-171): embed_spikes.{d}.weight (D, N) / .bias (D) of day d < n_days <= NDT1_MAX_DAYS;
+   * trial b uses day_idx[b].  Anywhere in memory: the engine packs them per forward and scatters the gradients back. */
+  float* embed_w_day[NDT1_MAX_DAYS]; float* embed_b_day[NDT1_MAX_DAYS];
   struct {
     float *ln1_w, *ln1_b, *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b, *ln2_w, *ln2_b, *up_w, *up_b, *down_w, *down_b;
   } layer[NDT1_MAX_LAYERS];
@@ -222,6 +226,11 @@ int ndt1_engine_set_weight_shadow(ndt1_engine* e, const float* params_fp32, cons
  * models/trainer.py:258-262,339). */
 int ndt1_engine_stage_count(const ndt1_engine* e);
 int ndt1_engine_wait_stage(ndt1_engine* e, int stage, void* stream);
+/* use_rope (models/ndt1.py:44-71, 262-266): the engine builds the (max_F, head_size) cos / sin tables itself at creation
+ * (get_cos_sin in double precision, rounded to fp32).  A caller that wants the exact table values of another
+ * implementation (the Python host passes the ones torch computes, like the reference) overrides them here; device
+ * pointers, `rows` >= max_F rows of head_size floats, copied. */
+int ndt1_engine_set_rope_tables(ndt1_engine* e, const float* cos_table, const float* sin_table, int rows);
 /* number of kernels launched by the last forward+backward (bench.py gpu_launches) */
 int64_t ndt1_engine_launch_count(const ndt1_engine* e);
 /* Measurement hooks (bench.py): between begin and end every tensor-core GEMM launch is bracketed by

@@ -13,8 +13,9 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libndt1_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LAYERS = 32
+MAX_DAYS = 64
 
 ACT = {"identity": 0, "softsign": 1, "gelu": 2, "relu": 3}
 METHOD = {"ctc": 0, "endtoend": 0, "mlm": 1, "autoregressive": 2}
@@ -46,7 +47,7 @@ class LayerTensors(C.Structure):
 
 class Tensors(C.Structure):
     _fields_ = [(n, _p) for n in ("embed_w", "embed_b", "proj_w", "proj_b", "pos_w", "block_emb", "day_emb")] + [
-        ("layer", LayerTensors * MAX_LAYERS)] + [(n, _p) for n in ("out_norm_w", "out_norm_b", "factors_w", "factors_b",
+        ("embed_w_day", _p * MAX_DAYS), ("embed_b_day", _p * MAX_DAYS), ("layer", LayerTensors * MAX_LAYERS)] + [(n, _p) for n in ("out_norm_w", "out_norm_b", "factors_w", "factors_b",
                                                                    "dec_w", "dec_b")]
 
 
@@ -93,6 +94,7 @@ PROTOTYPES = {
     "ndt1_debug_attention_timeline": (_i, [_p]),
     "ndt1_engine_stage_count": (_i, [_p]),
     "ndt1_engine_wait_stage": (_i, [_p, _i, _p]),
+    "ndt1_engine_set_rope_tables": (_i, [_p, _p, _p, _i]),
     "ndt1_profile_gemm_begin": (_i, []),
     "ndt1_profile_gemm_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ndt1_launch_counter": (_i64, []),

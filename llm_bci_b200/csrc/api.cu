@@ -58,6 +58,7 @@ int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y,
                     void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   GemmProblem p;
+  p.b_sel = nullptr;
   p.mode = GEMM_NT; p.M = M; p.N = N; p.nb_out = 1; p.nchunk = 1; p.chunk_k = K;
   p.a_row_shift = p.a_col_shift = p.b_row_shift = p.b_col_shift = 0; p.b_chunk_n = N; p.split_k = 1;
   p.epi = gemm_epilogue_default();

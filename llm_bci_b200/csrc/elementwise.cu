@@ -849,3 +849,121 @@ int k_and_mask(const long long* tmask, const long long* pmask, long long* out, i
   NDT1_CHECK_LAUNCH();
   return 0;
 }
+
+// ---------------------------------------------------------------------------
+// Options of the path that configs/ndt1.yaml leaves off: rotary positions, dropout in front of the factors
+// projection, per-day channel embedding.  Plain coalesced element-wise kernels (none of them is on the benchmark path).
+// ---------------------------------------------------------------------------
+namespace {
+
+// apply_rotary_pos_emb (models/ndt1.py:52-71, 285-286) in place on the q and k sections of the packed (B*L, 3H) buffer:
+//   x'[i] = x[i] cos[pos][i] - x[i + hd/2] sin[pos][i],   x'[i + hd/2] = x[i + hd/2] cos[pos][i] + x[i] sin[pos][i]
+// (cos[pos][i] == cos[pos][i + hd/2]: the table is cat(freqs, freqs)).  inverse = 1 applies the transpose (the backward).
+template <typename T>
+__global__ void rope_kernel(T* __restrict__ qkv, const long long* __restrict__ ts, long long ts_stride, const float* __restrict__ cs,
+                            const float* __restrict__ sn, long long rows, int L, int H, int nh, int hd, int max_F, int inverse) { pdl_grid_sync();
+  const int half = hd >> 1;
+  const long long per_row = 2LL * nh * half;                  // (section, head, i)
+  const long long total = rows * per_row;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long m = e / per_row;
+    const int w = (int)(e - m * per_row);
+    const int i = w % half, h = (w / half) % nh, sec = w / (half * nh);
+    long long pos = ts[(m / L) * ts_stride + (m % L)];
+    pos = pos < 0 ? 0 : (pos >= max_F ? max_F - 1 : pos);
+    const float c = cs[pos * hd + i];
+    const float s = inverse ? -sn[pos * hd + i] : sn[pos * hd + i];
+    T* v = qkv + m * 3LL * H + (long long)sec * H + (long long)h * hd + i;
+    const float x1 = to_f32(v[0]), x2 = to_f32(v[half]);
+    v[0] = from_f32<T>(x1 * c - x2 * s);
+    v[half] = from_f32<T>(x2 * c + x1 * s);
+  }
+}
+
+// x *= keep-scale of dropout site `stream_id` (element index = flat index), in place; the same call on a gradient is the backward
+template <typename T>
+__global__ void dropout_inplace_kernel(T* __restrict__ x, long long n, float p, unsigned long long seed, unsigned long long stream_id) { pdl_grid_sync();
+  const uint32_t thr = drop_threshold(p);
+  const float ik = 1.0f / (1.0f - p);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    x[e] = from_f32<T>(to_f32(x[e]) * drop_scale_1(seed, stream_id, (unsigned long long)e, thr, ik));
+}
+
+// out[sel[b] * out_stride + c] += sum over the rows of trial b of in[b, r, c]   (per-day embedding bias gradient)
+template <typename T>
+__global__ void colsum_sel_kernel(const T* __restrict__ in, float* __restrict__ out, const long long* __restrict__ sel, int n_sel,
+                                  long long out_stride, int rows_per_b, int cols) { pdl_grid_sync();
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const T* p = in + (long long)b * rows_per_b * cols + c;
+  float acc = 0.f;
+  for (int r = 0; r < rows_per_b; ++r) acc += to_f32(p[(long long)r * cols]);
+  long long d = sel[b];
+  d = d < 0 ? 0 : (d >= n_sel ? n_sel - 1 : d);
+  atomicAdd(out + d * out_stride + c, acc);
+}
+
+template <typename T>
+__global__ void cast_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, long long n) { pdl_grid_sync();
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) out[e] = to_f32(in[e]);
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) { pdl_grid_sync();
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) dst[e] += src[e];
+}
+
+inline int ew_blocks(long long n) { return (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8); }
+
+}  // namespace
+
+template <typename T>
+int k_rope(T* qkv, const long long* ts, long long ts_stride, const float* cs, const float* sn, long long rows, int L, int H, int nh,
+           int max_F, int inverse, cudaStream_t stream) {
+  if (rows == 0) return 0;
+  const int hd = H / nh;
+  NDT1_REQUIRE(hd % 2 == 0, "rope: head size %d must be even", hd);
+  ndt1_launch(rope_kernel<T>, ew_blocks(rows * nh * hd), 256, 0, stream, qkv, ts, ts_stride, cs, sn, rows, L, H, nh, hd, max_F, inverse);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+template int k_rope<float>(float*, const long long*, long long, const float*, const float*, long long, int, int, int, int, int, cudaStream_t);
+template int k_rope<bf16>(bf16*, const long long*, long long, const float*, const float*, long long, int, int, int, int, int, cudaStream_t);
+
+template <typename T>
+int k_dropout_inplace(T* x, long long n, float p, unsigned long long seed, unsigned long long stream_id, cudaStream_t stream) {
+  if (n == 0 || p <= 0.f) return 0;
+  ndt1_launch(dropout_inplace_kernel<T>, ew_blocks(n), 256, 0, stream, x, n, p, seed, stream_id);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+template int k_dropout_inplace<float>(float*, long long, float, unsigned long long, unsigned long long, cudaStream_t);
+template int k_dropout_inplace<bf16>(bf16*, long long, float, unsigned long long, unsigned long long, cudaStream_t);
+
+template <typename T>
+int k_colsum_sel(const T* in, float* out, const long long* sel, int n_sel, long long out_stride, int B, int rows_per_b, int cols,
+                 cudaStream_t stream) {
+  if (B == 0 || rows_per_b == 0) return 0;
+  ndt1_launch(colsum_sel_kernel<T>, dim3(ndt1_cdiv(cols, 128), B), 128, 0, stream, in, out, sel, n_sel, out_stride, rows_per_b, cols);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+template int k_colsum_sel<float>(const float*, float*, const long long*, int, long long, int, int, int, cudaStream_t);
+template int k_colsum_sel<bf16>(const bf16*, float*, const long long*, int, long long, int, int, int, cudaStream_t);
+
+int k_add_inplace(float* dst, const float* src, long long n, cudaStream_t stream) {
+  if (n == 0) return 0;
+  ndt1_launch(add_inplace_kernel, ew_blocks(n), 256, 0, stream, dst, src, n);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+
+template <typename T>
+int k_cast_to_f32(const T* in, float* out, long long n, cudaStream_t stream) {
+  if (n == 0) return 0;
+  ndt1_launch(cast_to_f32_kernel<T>, ew_blocks(n), 256, 0, stream, in, out, n);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+template int k_cast_to_f32<float>(const float*, float*, long long, cudaStream_t);
+template int k_cast_to_f32<bf16>(const bf16*, float*, long long, cudaStream_t);

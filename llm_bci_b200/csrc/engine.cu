@@ -16,6 +16,7 @@
 //   bf16 mode keeps bf16 copies of the weights (QKV concatenated) refreshed per forward.
 #include "../../include/ndt1_b200.h"
 #include "kernels.cuh"
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -50,6 +51,7 @@ struct ndt1_engine {
   virtual int forward(const ndt1_tensors* P, const ndt1_batch* b, const ndt1_outputs* o, cudaStream_t s) = 0;
   virtual int backward(const ndt1_tensors* P, const ndt1_tensors* G, const float* dloss, cudaStream_t s) = 0;
   virtual size_t arena_bytes() const = 0;
+  virtual int set_rope_tables(const float* cs, const float* sn, int rows) = 0;
   int out_len(int T) const { return c.stack_active ? (T - c.stack_size) / c.stack_stride + 1 : T; }
 };
 
@@ -64,7 +66,10 @@ struct Engine : ndt1_engine {
   int n_prefix = 0;
   // arena views ------------------------------------------------------------
   T* xin = nullptr; int ldN = 0;
-  T* emb = nullptr;
+  T* emb = nullptr; T* emb_pre = nullptr;      // emb_pre: pre-activation, kept only for a GELU embedder (its derivative needs it)
+  float* rope_cos = nullptr; float* rope_sin = nullptr;   // (max_F, head size), models/ndt1.py:44-53
+  // embedder.adapt: per-day weights / biases packed back to back (T-typed copy refreshed per forward) and their packed gradients
+  T* wd_pack = nullptr; float* bd_pack = nullptr; float* dwd_pack = nullptr; float* dbd_pack = nullptr; int ldW = 0;
   std::vector<float*> xs;           // 2L+1 residual snapshots
   std::vector<float*> mean, rstd;   // 2L+1
   std::vector<T*> h1, h2, qkv, att, attd, u, g;
@@ -110,6 +115,13 @@ struct Engine : ndt1_engine {
     const long long Mout = (k.method == NDT1_METHOD_CTC) ? (long long)Bm * out_len(Tm) : Mm;
     if (kBf16) xin = ar.take<T>(MT * ldN);
     emb = ar.take<T>(MT * D);
+    if (k.embed_act == NDT1_ACT_GELU) emb_pre = ar.take<T>(MT * D);
+    if (k.use_rope) { rope_cos = ar.take<float>((long long)k.max_F * (H / k.n_heads)); rope_sin = ar.take<float>((long long)k.max_F * (H / k.n_heads)); }
+    ldW = kBf16 ? ldN : k.n_channels;
+    if (k.adapt) {
+      wd_pack = ar.take<T>((long long)k.n_days * D * ldW); bd_pack = ar.take<float>((long long)k.n_days * D);
+      dwd_pack = ar.take<float>((long long)k.n_days * D * k.n_channels); dbd_pack = ar.take<float>((long long)k.n_days * D);
+    }
     xs.resize(2 * NL + 1); mean.resize(2 * NL + 1); rstd.resize(2 * NL + 1);
     for (int i = 0; i < 2 * NL + 1; ++i) { xs[i] = ar.take<float>(Mm * H); mean[i] = ar.take<float>(Mm); rstd[i] = ar.take<float>(Mm); }
     h1.resize(NL); h2.resize(NL); qkv.resize(NL); att.resize(NL); attd.resize(NL); u.resize(NL); g.resize(NL); lse.resize(NL); dropbits.resize(NL);
@@ -169,6 +181,29 @@ struct Engine : ndt1_engine {
     for (auto& e : fork_ev) NDT1_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     NDT1_CUDA_CHECK(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
     if (kBf16 && !force_simt) NDT1_TRY(gemm_tc_init());
+    if (c.use_rope) {
+      // get_cos_sin (models/ndt1.py:44-53): inv_freq_i = base^(-2i/dim), angle = t * inv_freq_i, table = cat(angles, angles)
+      const int hd = c.hidden / c.n_heads, half = hd / 2;
+      std::vector<float> hc((size_t)c.max_F * hd), hs((size_t)c.max_F * hd);
+      for (int i = 0; i < half; ++i) {
+        const float inv = (float)(1.0 / pow((double)c.rope_theta, (double)(2 * i) / (double)hd));
+        for (int t = 0; t < c.max_F; ++t) {
+          const float ang = (float)t * inv;
+          hc[(size_t)t * hd + i] = hc[(size_t)t * hd + half + i] = (float)cos((double)ang);
+          hs[(size_t)t * hd + i] = hs[(size_t)t * hd + half + i] = (float)sin((double)ang);
+        }
+      }
+      NDT1_CUDA_CHECK(cudaMemcpy(rope_cos, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
+      NDT1_CUDA_CHECK(cudaMemcpy(rope_sin, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+  }
+  int set_rope_tables(const float* cs, const float* sn, int rows) override {
+    NDT1_REQUIRE(c.use_rope, "engine_set_rope_tables: the engine was created without use_rope");
+    NDT1_REQUIRE(cs && sn && rows >= c.max_F, "engine_set_rope_tables: need cos and sin tables of at least max_F = %d rows", c.max_F);
+    const size_t bytes = (size_t)c.max_F * (c.hidden / c.n_heads) * 4;
+    NDT1_CUDA_CHECK(cudaMemcpy(rope_cos, cs, bytes, cudaMemcpyDeviceToDevice));
+    NDT1_CUDA_CHECK(cudaMemcpy(rope_sin, sn, bytes, cudaMemcpyDeviceToDevice));
     return 0;
   }
   ~Engine() override {
@@ -189,6 +224,7 @@ struct Engine : ndt1_engine {
   }
   static GemmProblem prob(int mode, int M, int N, int K) {
     GemmProblem p;
+    p.b_sel = nullptr;
     p.mode = mode; p.M = M; p.N = N; p.nb_out = 1; p.nchunk = 1; p.chunk_k = K;
     p.a_row_shift = p.a_col_shift = p.b_row_shift = p.b_col_shift = 0; p.b_chunk_n = N; p.split_k = 1;
     p.epi = gemm_epilogue_default();
@@ -230,6 +266,7 @@ struct Engine : ndt1_engine {
   unsigned long long site_attn_p(int l) const { return 1 + 4ull * l; }
   unsigned long long site_attn_o(int l) const { return 2 + 4ull * l; }
   unsigned long long site_mlp(int l) const { return 3 + 4ull * l; }
+  unsigned long long site_factors() const { return 1 + 4ull * c.n_layers; }     // dropout in front of the factors projection (models/ndt1.py:355,372)
 
   int act_code(int a) const { return a == NDT1_ACT_SOFTSIGN ? ACT_SOFTSIGN : a == NDT1_ACT_GELU ? ACT_GELU : a == NDT1_ACT_RELU ? ACT_RELU : ACT_NONE; }
   // derivative selector given what the forward kept (out = activation value, in = pre-activation)
@@ -279,7 +316,7 @@ struct Engine : ndt1_engine {
         }
         return dst;
       };
-      u_emb = use(P->embed_w, w_emb, D, N, ldN);
+      if (!k.adapt) u_emb = use(P->embed_w, w_emb, D, N, ldN);
       const int KP = k.stack_active ? k.stack_size * D : D;
       u_proj = use(P->proj_w, w_proj, H, KP, KP);
       for (int l = 0; l < NL; ++l) {
@@ -308,6 +345,20 @@ struct Engine : ndt1_engine {
       NDT1_TRY(rc_add);
       NDT1_TRY(k_cast_multi(cs, s));
     }
+    if (k.adapt) {
+      // per-day embedding: pack this step's weights / biases back to back (they may live anywhere)
+      NDT1_REQUIRE(k.n_days >= 1 && k.n_days <= NDT1_MAX_DAYS, "engine: n_days %d outside [1,%d]", k.n_days, NDT1_MAX_DAYS);
+      NDT1_REQUIRE(day_ptr, "engine: embedder.adapt needs day_idx");
+      for (int d = 0; d < k.n_days; ++d) {
+        NDT1_REQUIRE(P->embed_w_day[d], "engine: embed_w_day[%d] is null", d);
+        if (kBf16) NDT1_TRY(k_cast_f32_bf16(P->embed_w_day[d], (bf16*)wd_pack + (long long)d * D * ldW, D, N, N, ldW, s));
+        else NDT1_CUDA_CHECK(cudaMemcpyAsync(wd_pack + (long long)d * D * ldW, P->embed_w_day[d], (size_t)D * N * 4, cudaMemcpyDeviceToDevice, s));
+        if (k.embed_bias) {
+          NDT1_REQUIRE(P->embed_b_day[d], "engine: embed_b_day[%d] is null", d);
+          NDT1_CUDA_CHECK(cudaMemcpyAsync(bd_pack + (long long)d * D, P->embed_b_day[d], (size_t)D * 4, cudaMemcpyDeviceToDevice, s));
+        }
+      }
+    }
     const T* x_in = kBf16 ? xin : (const T*)bt->spikes;
     const int ldx = kBf16 ? ldN : N;
 
@@ -315,7 +366,20 @@ struct Engine : ndt1_engine {
     {
       GemmEpilogue e = gemm_epilogue_default();
       e.out = emb; e.out_bf16 = kBf16; e.ldc = D; e.bias = k.embed_bias ? P->embed_b : nullptr; e.act = act_code(k.embed_act);
-      NDT1_TRY(linear_fwd(x_in, ldx, W(P->embed_w, u_emb), kBf16 ? ldN : N, (int)MT, D, N, e, s));
+      if (emb_pre) { e.out2 = emb_pre; e.out2_bf16 = kBf16; }
+      if (!k.adapt) {
+        NDT1_TRY(linear_fwd(x_in, ldx, W(P->embed_w, u_emb), kBf16 ? ldN : N, (int)MT, D, N, e, s));
+      } else {
+        // one GEMM over all trials; trial b reads day_idx[b]'s weight matrix (third TMA coordinate) and bias row
+        GemmProblem p = prob(GEMM_NT, Tn, D, N);
+        p.nb_out = B; p.b_sel = day_ptr;
+        p.A = op(x_in, (long long)Tn * ldx, B, Tn, N, ldx);
+        p.B = op(wd_pack, (long long)D * ldW, k.n_days, D, N, ldW);
+        e.c_batch_stride = (long long)Tn * D;
+        e.bias = k.embed_bias ? bd_pack : nullptr; e.sel = day_ptr; e.sel_n = k.n_days; e.bias_sel_stride = D;
+        p.epi = e;
+        NDT1_TRY(run(p, s));
+      }
     }
     // 2. stack projection / projection + position table + embedding dropout  (models/ndt1.py:179-203)
     float* x0 = xs[0];
@@ -351,7 +415,7 @@ struct Engine : ndt1_engine {
     if (o->out_mask) NDT1_CUDA_CHECK(cudaMemcpyAsync(o->out_mask, key_valid, M * 8, cudaMemcpyDeviceToDevice, s));
 
     // 3. transformer layers  (models/ndt1.py:317-330)
-    NDT1_REQUIRE(!k.use_rope, "engine: use_rope is not implemented in this build");
+    NDT1_REQUIRE(!k.use_rope || (n_prefix == 0 && ts_ptr), "engine: use_rope needs timestamps and no block / day token (the reference indexes cos/sin by the stacked timestamps)");
     int cf, cb; ctx(cf, cb);
     for (int l = 0; l < NL; ++l) {
       const auto& q = P->layer[l];
@@ -370,6 +434,7 @@ struct Engine : ndt1_engine {
           NDT1_TRY(linear_fwd(h1[l], H, ws[j], H, (int)M, H, H, e, s));
         }
       }
+      if (k.use_rope) NDT1_TRY(k_rope<T>(qkv[l], ts_ptr, Tn, rope_cos, rope_sin, M, L, H, k.n_heads, k.max_F, 0, s));
       AttnParams ap;
       ap.qkv = qkv[l]; ap.out = att[l]; ap.out_drop = (ptr_ > 0.f) ? attd[l] : att[l]; ap.lse = lse[l]; ap.key_valid = key_valid;
       ap.B = B; ap.L = L; ap.H = H; ap.nh = k.n_heads; ap.hd = H / k.n_heads; ap.ctx_fwd = cf; ap.ctx_bwd = cb;
@@ -399,9 +464,10 @@ struct Engine : ndt1_engine {
     }
     // 4. output norm, factors, head   (models/ndt1.py:442-450, 545)
     NDT1_TRY(k_layernorm_fwd<T>(xs[2 * NL], P->out_norm_w, P->out_norm_b, hn, mean[2 * NL], rstd[2 * NL], M, H, 1e-5f, s));
+    const float pf = training ? k.p_factors : 0.f;       // NeuralFactorsProjection.forward drops its input whether or not the projection is active
+    NDT1_TRY(k_dropout_inplace<T>(hn, M * H, pf, seed, site_factors(), s));
     const T* head_in = hn; int head_ld = H;
     if (k.factors_active) {
-      NDT1_REQUIRE(!(training && k.p_factors > 0.f), "engine: dropout in the factors projection is not implemented in this build");
       GemmEpilogue e = gemm_epilogue_default();
       e.out = fac; e.out_bf16 = kBf16; e.ldc = Hout; e.bias = k.factors_bias ? P->factors_b : nullptr; e.act = act_code(k.factors_act);
       e.out2 = fpre; e.out2_bf16 = kBf16;
@@ -414,6 +480,7 @@ struct Engine : ndt1_engine {
         NDT1_TRY((k_scale_cast_features(head_in, feat32, M, Hout, s)));
       } else {
         NDT1_TRY(k_layernorm_fwd<float>(xs[2 * NL], P->out_norm_w, P->out_norm_b, feat32, mean[2 * NL], rstd[2 * NL], M, H, 1e-5f, s));
+        NDT1_TRY(k_dropout_inplace<float>(feat32, M * H, pf, seed, site_factors(), s));
       }
       NDT1_CUDA_CHECK(cudaMemcpy2DAsync(o->features, (size_t)Tp * Hout * 4, feat32 + (long long)n_prefix * Hout, (size_t)L * Hout * 4,
                                         (size_t)Tp * Hout * 4, B, cudaMemcpyDeviceToDevice, s));
@@ -462,12 +529,8 @@ struct Engine : ndt1_engine {
   }
 
   int k_scale_cast_features(const T* in, float* out, long long rows, int cols, cudaStream_t s) {
-    // T -> fp32 copy (only used for the optional `features` output with an active factors projection)
-    GemmEpilogue e = gemm_epilogue_default();
-    (void)e;
-    if (!kBf16) { NDT1_CUDA_CHECK(cudaMemcpyAsync(out, in, rows * cols * 4, cudaMemcpyDeviceToDevice, s)); return 0; }
-    NDT1_REQUIRE(false, "engine: `features` with an active factors projection needs NDT1_PRECISION_FP32 in this build");
-    return 0;
+    // T -> fp32 copy (the optional `features` output with an active factors projection)
+    return k_cast_to_f32<T>(in, out, rows * cols, s);
   }
 
   // ---- backward -----------------------------------------------------------
@@ -539,6 +602,7 @@ struct Engine : ndt1_engine {
       e.out = dhn; e.out_bf16 = kBf16; e.ldc = H;
       NDT1_TRY(linear_dgrad(dfac, Hout, W(P->factors_w, u_fac), H, (int)M, Hout, H, e, s));
     }
+    NDT1_TRY(k_dropout_inplace<T>(dhn, M * H, training ? k.p_factors : 0.f, seed, site_factors(), s));
     // out_norm
     NDT1_CUDA_CHECK(cudaMemsetAsync(dX, 0, M * H * sizeof(float), s));
     // every LayerNorm backward also emits the column sums of the operand it hands to the next GEMM pair = that layer's bias gradient
@@ -592,6 +656,7 @@ struct Engine : ndt1_engine {
       ap.dout = dA; ap.dqkv = dqkv; ap.delta = delta; ap.drop_bits = dropbits[l];
       if (kBf16 && !force_simt && !simt_attention && k_attention_tc_supported(ap)) NDT1_TRY(k_attention_tc_bwd(ap, s));
       else NDT1_TRY(k_attention_bwd<T>(ap, s));
+      if (k.use_rope) NDT1_TRY(k_rope<T>(dqkv, ts_ptr, Tn, rope_cos, rope_sin, M, L, H, k.n_heads, k.max_F, 1, s));   // transpose of the rotation
       NDT1_TRY(fork());
       float* gw[3] = {gq.q_w, gq.k_w, gq.v_w}; float* gb[3] = {gq.q_b, gq.k_b, gq.v_b};
       // flat gradient arena: q|k|v weights (and biases) adjacent -> one (3H x H) weight gradient, one bias reduction
@@ -640,8 +705,10 @@ struct Engine : ndt1_engine {
     const T* dE = dY + (long long)n_prefix * H;
     const int eact = k.embed_act;
     // (not in the stacked layout: there one output row of the overlap-add GEMM holds `stride` bins)
-    const bool fuse_embed_cs = kBf16 && !force_simt && G->embed_b && k.embed_bias && D % 8 == 0 && !k.stack_active;
-    NDT1_REQUIRE(eact != NDT1_ACT_GELU, "engine: gelu as the embedder activation is not implemented in this build");
+    const bool fuse_embed_cs = kBf16 && !force_simt && G->embed_b && k.embed_bias && D % 8 == 0 && !k.stack_active && !k.adapt;
+    // derivative of the embedder activation: from the kept pre-activation for GELU, from the output otherwise
+    const int e_dact = eact == NDT1_ACT_GELU ? DACT_GELU_FROM_IN : dact_from_out(eact);
+    const T* e_dact_in = eact == NDT1_ACT_GELU ? emb_pre : emb;
     if (k.stack_active) {
       const int K4 = k.stack_stride * D, nch = k.stack_size / k.stack_stride, R4 = Tn / k.stack_stride;
       if (G->proj_w) {
@@ -659,7 +726,7 @@ struct Engine : ndt1_engine {
       p.A = op(dE, (long long)L * H, B, Tp, H, H);
       p.B = op(W(P->proj_w, u_proj), 0, 1, H, nch * K4, nch * K4);
       p.epi.out = dEmb; p.epi.out_bf16 = kBf16; p.epi.ldc = K4; p.epi.c_batch_stride = (long long)Tn * D;
-      p.epi.dact = dact_from_out(eact); p.epi.dact_in = emb; p.epi.dact_in_bf16 = kBf16;
+      p.epi.dact = e_dact; p.epi.dact_in = e_dact_in; p.epi.dact_in_bf16 = kBf16;
       if (fuse_embed_cs) p.epi.colsum = G->embed_b;
       NDT1_TRY(run(p, s));
     } else {
@@ -676,13 +743,31 @@ struct Engine : ndt1_engine {
       p.A = op(dE, (long long)L * H, B, Tp, H, H);
       p.B = op(W(P->proj_w, u_proj), 0, 1, H, D, D);
       p.epi.out = dEmb; p.epi.out_bf16 = kBf16; p.epi.ldc = D; p.epi.c_batch_stride = (long long)Tn * D;
-      p.epi.dact = dact_from_out(eact); p.epi.dact_in = emb; p.epi.dact_in_bf16 = kBf16;
+      p.epi.dact = e_dact; p.epi.dact_in = e_dact_in; p.epi.dact_in_bf16 = kBf16;
       if (fuse_embed_cs) p.epi.colsum = G->embed_b;
       NDT1_TRY(run(p, s));
     }
     NDT1_TRY(fork());
-    if (!fuse_embed_cs && G->embed_b && k.embed_bias) NDT1_TRY(k_colsum<T>(dEmb, G->embed_b, MT, D, D, ws));
-    if (G->embed_w) {
+    if (k.adapt) {
+      // per-day gradients: trial b adds into day_idx[b]'s packed matrix / bias row, then each day's sum goes to its own tensor
+      const T* x_in = kBf16 ? xin : (const T*)spikes_ptr;
+      const int ldx = kBf16 ? ldN : N;
+      NDT1_CUDA_CHECK(cudaMemsetAsync(dwd_pack, 0, (size_t)k.n_days * D * N * 4, ws));
+      NDT1_CUDA_CHECK(cudaMemsetAsync(dbd_pack, 0, (size_t)k.n_days * D * 4, ws));
+      if (k.embed_bias) NDT1_TRY(k_colsum_sel<T>(dEmb, dbd_pack, day_ptr, k.n_days, D, B, Tn, D, ws));
+      GemmProblem p = prob(GEMM_TN, D, N, Tn);
+      p.nchunk = B; p.split_k = B;
+      p.A = op(dEmb, (long long)Tn * D, B, Tn, D, D); p.B = op(x_in, (long long)Tn * ldx, B, Tn, N, ldx);
+      p.epi.out = dwd_pack; p.epi.ldc = N; p.epi.accumulate = 1;
+      p.epi.sel = day_ptr; p.epi.sel_n = k.n_days; p.epi.c_sel_stride = (long long)D * N;
+      NDT1_TRY(run(p, ws));
+      for (int d = 0; d < k.n_days; ++d) {
+        if (G->embed_w_day[d]) NDT1_TRY(k_add_inplace(G->embed_w_day[d], dwd_pack + (long long)d * D * N, (long long)D * N, ws));
+        if (G->embed_b_day[d] && k.embed_bias) NDT1_TRY(k_add_inplace(G->embed_b_day[d], dbd_pack + (long long)d * D, D, ws));
+      }
+    }
+    if (!fuse_embed_cs && G->embed_b && k.embed_bias && !k.adapt) NDT1_TRY(k_colsum<T>(dEmb, G->embed_b, MT, D, D, ws));
+    if (G->embed_w && !k.adapt) {
       const T* x_in = kBf16 ? xin : (const T*)spikes_ptr;
       const int ldx = kBf16 ? ldN : N;
       GemmProblem p = prob(GEMM_TN, D, N, (int)MT);
@@ -718,7 +803,8 @@ int ndt1_engine_create(const ndt1_config* cfg, ndt1_engine** out) {
   NDT1_REQUIRE(cfg->abi_version == NDT1_ABI_VERSION, "engine_create: ABI version %d, library is %d", cfg->abi_version, NDT1_ABI_VERSION);
   NDT1_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= NDT1_MAX_LAYERS, "engine_create: n_layers %d outside [1,%d]", cfg->n_layers, NDT1_MAX_LAYERS);
   NDT1_REQUIRE(cfg->hidden % cfg->n_heads == 0, "engine_create: Hidden dim is not multiple of head size");
-  NDT1_REQUIRE(!cfg->adapt, "engine_create: per-day embedding (adapt) is not implemented in this build");
+  NDT1_REQUIRE(!cfg->adapt || (cfg->n_days >= 1 && cfg->n_days <= NDT1_MAX_DAYS), "engine_create: adapt needs 1 <= n_days <= %d (got %d)", NDT1_MAX_DAYS, cfg->n_days);
+  NDT1_REQUIRE(!cfg->use_rope || ((cfg->hidden / cfg->n_heads) % 2 == 0 && cfg->max_F > 0), "engine_create: use_rope needs an even head size and max_F > 0");
   NDT1_REQUIRE(cfg->max_batch > 0 && cfg->max_T > 0, "engine_create: max_batch / max_T must be positive");
   NDT1_REQUIRE(cfg->hidden % 8 == 0 && cfg->inter % 8 == 0 && cfg->input_dim % 8 == 0, "engine_create: hidden, inter and input_dim must be multiples of 8");
   ndt1_engine* e = nullptr;
@@ -752,6 +838,10 @@ int ndt1_engine_set_overlap(ndt1_engine* e, int on) {
   NDT1_REQUIRE(e, "engine_set_overlap: null engine");
   e->overlap = on != 0;
   return 0;
+}
+int ndt1_engine_set_rope_tables(ndt1_engine* e, const float* cos_table, const float* sin_table, int rows) {
+  NDT1_REQUIRE(e, "engine_set_rope_tables: null engine");
+  return e->set_rope_tables(cos_table, sin_table, rows);
 }
 int ndt1_engine_stage_count(const ndt1_engine* e) { return e->n_stages(); }
 int ndt1_engine_wait_stage(ndt1_engine* e, int stage, void* stream) {

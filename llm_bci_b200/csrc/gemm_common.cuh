@@ -57,6 +57,11 @@ struct GemmEpilogue {
   int dact_in_bf16;
   int accumulate;           // 1: out (fp32) += value (atomic when split)
   float* colsum;            // optional (tensor-core kernel only): colsum[n] += sum over rows and trials of the stored value
+  // per-day routing (embedder.adapt, models/ndt1.py:118-127,170-171): sel[b] (device, clamped to [0, sel_n)) picks the bias row
+  // of output trial b (NT / NN) or, in GEMM_TN run with split_k = trials, the output matrix the trial's product is added to
+  const long long* sel;
+  int sel_n;
+  long long bias_sel_stride, c_sel_stride;
 };
 
 struct GemmProblem {
@@ -68,6 +73,7 @@ struct GemmProblem {
   int b_row_shift, b_col_shift;
   int b_chunk_n;            // GEMM_TN only (N if unused)
   int split_k;              // GEMM_TN: split the reduction over this many CTAs (needs accumulate)
+  const long long* b_sel;   // GEMM_NT: B operand batch (B.nbatch matrices, B.batch_stride apart) of output trial b = b_sel[b]; null = batch 0
   GemmOperand A, B;
   GemmEpilogue epi;
 };
@@ -80,6 +86,7 @@ static inline GemmEpilogue gemm_epilogue_default() {
   e.drop_p = 0.f; e.drop_bwd = 0; e.drop_seed = 0; e.drop_stream = 0;
   e.resid = nullptr; e.dact = DACT_NONE; e.dact_in = nullptr; e.dact_in_bf16 = 0;
   e.accumulate = 0; e.colsum = nullptr;
+  e.sel = nullptr; e.sel_n = 0; e.bias_sel_stride = 0; e.c_sel_stride = 0;
   return e;
 }
 
@@ -89,9 +96,15 @@ static inline GemmEpilogue gemm_epilogue_default() {
 // Order (backward): v = alpha*acc ; v *= dropmask ; v *= act'(saved)
 __device__ __forceinline__ void gemm_epilogue_store(const GemmEpilogue& e, int n_total, int rows_c,
                                                     float acc, int b, int r, int n) {
-  const long long idx = (long long)b * e.c_batch_stride + (long long)r * e.ldc + n;
+  long long idx = (long long)b * e.c_batch_stride + (long long)r * e.ldc + n;
+  long long bias_off = 0;
+  if (e.sel) {
+    long long d = e.sel[b];
+    d = d < 0 ? 0 : (d >= e.sel_n ? e.sel_n - 1 : d);
+    idx += d * e.c_sel_stride; bias_off = d * e.bias_sel_stride;
+  }
   float v = acc * e.alpha;
-  if (e.bias) v += e.bias[n];
+  if (e.bias) v += e.bias[bias_off + n];
   if (e.out2) store_from_f32(e.out2, idx, e.out2_bf16, v);
   v = act_apply(e.act, v);
   if (e.gather_tab) {

@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmProblem p) { pd
   const int bt = blockIdx.y / m_tiles;     // output trial
   const int m0 = (blockIdx.y % m_tiles) * BM;
   const int n0 = blockIdx.x * BN;
+  int bsel = 0;                            // B operand batch (per-day weights)
+  if (p.b_sel) { const long long d = p.b_sel[bt]; bsel = (int)(d < 0 ? 0 : (d >= p.B.nbatch ? p.B.nbatch - 1 : d)); }
 
   // reduction range of this CTA (split only in GEMM_TN)
   const int kblocks_per_chunk = (p.chunk_k + BK - 1) / BK;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmProblem p) { pd
         for (int q = 0; q < 4; ++q) {
           const int kc = kc0 + k4 + q;
           Bs[k4 + q][row] = (kc < p.chunk_k && n < p.N)
-                                ? ld_elem<T>(p.B, 0, n + j * p.b_row_shift, kc + j * p.b_col_shift)
+                                ? ld_elem<T>(p.B, bsel, n + j * p.b_row_shift, kc + j * p.b_col_shift)
                                 : 0.f;
         }
       } else {  // GEMM_NN: B is [reduce rows][n contiguous]
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmProblem p) { pd
     for (int jn = 0; jn < 4; ++jn) {
       const int n = n0 + tx * 4 + jn;
       if (n >= p.N) continue;
-      gemm_epilogue_store(p.epi, p.N, p.M, acc[i][jn], bt, r, n);
+      gemm_epilogue_store(p.epi, p.N, p.M, acc[i][jn], (p.mode == GEMM_TN && p.epi.sel) ? (int)blockIdx.z : bt, r, n);
     }
   }
 }

@@ -38,6 +38,7 @@ struct TcParams {
   int split_k;
   int m_tiles, n_tiles, total_tiles;
   int chunk_k_valid;                   // reduction length per chunk in elements (for FLOP accounting)
+  const long long* b_sel; int b_sel_n; // per-day B operand batch of an output trial (GEMM_NT), null = batch 0
   GemmEpilogue epi;
 };
 
@@ -110,6 +111,7 @@ struct EpiCtx {
 struct ChunkAt {          // where a (tile, chunk) lands in the output
   int bt, r0, n;          // trial, first row of this warp's 32-row strip, first column of this lane
   long long rowbase;      // element offset of (trial, this lane's first row, column 0): computed once per tile
+  long long bias_off;     // per-day bias row (0 without routing)
   bool live;
 };
 
@@ -159,11 +161,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
   float4 v[8];                         // and its accumulators beyond N are zero (out-of-range operand rows read as zero)
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e.bias && col_ok) {
-    if (at.n + 4 <= p.N) bias4 = __ldg((const float4*)(e.bias + at.n));
+    if (at.n + 4 <= p.N) bias4 = __ldg((const float4*)(e.bias + at.bias_off + at.n));
     else {
-      bias4.x = __ldg(e.bias + at.n);
-      if (at.n + 1 < p.N) bias4.y = __ldg(e.bias + at.n + 1);
-      if (at.n + 2 < p.N) bias4.z = __ldg(e.bias + at.n + 2);
+      bias4.x = __ldg(e.bias + at.bias_off + at.n);
+      if (at.n + 1 < p.N) bias4.y = __ldg(e.bias + at.bias_off + at.n + 1);
+      if (at.n + 2 < p.N) bias4.z = __ldg(e.bias + at.bias_off + at.n + 2);
     }
   }
 #pragma unroll
@@ -425,6 +427,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int mt = rest % p.m_tiles;
         const int bz = rest / p.m_tiles;          // trial (NT/NN) or split index (TN)
         const int m0 = mt * (BM * CTAS) + rank * BM, n0 = nt * BN + rank * BNL;     // this CTA's rows of A / columns of B
+        int bsel = 0;
+        if (MODE == GEMM_NT && p.b_sel) { const long long d = __ldg(p.b_sel + bz); bsel = (int)(d < 0 ? 0 : (d >= p.b_sel_n ? p.b_sel_n - 1 : d)); }
         int kb0 = 0, kb1 = total_kb;
         if (MODE == GEMM_TN && p.split_k > 1) {
           const int per = (total_kb + p.split_k - 1) / p.split_k;
@@ -451,7 +455,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else {
             tma_load_3d_g<CTAS>(sa, &map_a, fb, j * p.a_col_shift + kk, m0 + j * p.a_row_shift, bz);
             if (MODE == GEMM_NT) {
-              tma_load_3d_g<CTAS>(sb, &map_b, fb, j * p.b_col_shift + kk, n0 + j * p.b_row_shift, 0);
+              tma_load_3d_g<CTAS>(sb, &map_b, fb, j * p.b_col_shift + kk, n0 + j * p.b_row_shift, bsel);
             } else {
 #pragma unroll
               for (int i = 0; i < BNL / 64; ++i)
@@ -520,10 +524,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
       const int bz = rest / p.m_tiles;
-      at.bt = (MODE == GEMM_TN) ? 0 : bz;
+      at.bt = (MODE == GEMM_TN && !e.sel) ? 0 : bz;                // (routed GEMM_TN: the split index is the trial)
       at.r0 = mt * (BM * CTAS) + rank * BM + q * 32;
       at.n = nt * BN + half * (BN / 2) + (lane & 7) * 4;          // chunk 0
       at.rowbase = (long long)at.bt * e.c_batch_stride + (long long)(at.r0 + (lane >> 3)) * e.ldc;
+      at.bias_off = 0;
+      if (e.sel && at.live) {
+        long long d = __ldg(e.sel + bz);
+        d = d < 0 ? 0 : (d >= e.sel_n ? e.sel_n - 1 : d);
+        at.rowbase += d * e.c_sel_stride; at.bias_off = d * e.bias_sel_stride;
+      }
       if (MODE == GEMM_TN && p.split_k > 1) {
         const int per = (total_kb + p.split_k - 1) / p.split_k;
         if (bz * per >= total_kb) at.live = false;       // empty split: nothing to add
@@ -762,6 +772,8 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
                  "gemm_tc: GEMM_TN reduction rows must be bounded by the A operand (rows=%d chunk_k=%d)", p.A.rows, p.chunk_k);
     NDT1_REQUIRE(p.b_chunk_n > 0, "gemm_tc: b_chunk_n must be set for GEMM_TN");
   }
+  NDT1_REQUIRE(!p.b_sel || p.mode == GEMM_NT, "gemm_tc: b_sel (per-trial B operand) only for GEMM_NT");
+  NDT1_REQUIRE(!p.epi.sel || p.mode != GEMM_TN || p.split_k == p.nchunk, "gemm_tc: a routed GEMM_TN needs split_k == nchunk (one split per trial)");
   NDT1_REQUIRE(!p.epi.colsum || (p.N % 8 == 0 && p.epi.ldc % 4 == 0 && p.epi.c_batch_stride % 4 == 0),
                "gemm_tc: the fused column sum needs a vectorisable output (N=%d)", p.N);
   int bn = p.N > 128 ? 256 : (p.N > 64 ? 128 : 64);
@@ -791,6 +803,7 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   tp.a_row_shift = p.a_row_shift; tp.a_col_shift = p.a_col_shift;
   tp.b_row_shift = p.b_row_shift; tp.b_col_shift = p.b_col_shift;
   tp.b_chunk_n = p.b_chunk_n > 0 ? p.b_chunk_n : p.N;
+  tp.b_sel = p.b_sel; tp.b_sel_n = p.B.nbatch;
   tp.m_tiles = ndt1_cdiv(p.M, bm); tp.n_tiles = ndt1_cdiv(p.N, bn);
   tp.split_k = p.split_k > 1 ? p.split_k : 1;
   if (p.mode == GEMM_TN && p.split_k == 0 && p.epi.accumulate) {

@@ -38,6 +38,18 @@ template <typename T> int k_scale_cast_pad(const float* in, T* out, long long ro
 int k_stacked_lens(const long long* lens, long long* out, int B, int stack, int size, int stride, cudaStream_t stream);
 int k_set_i64(long long* p, long long v, cudaStream_t stream);
 int k_relu_inplace(float* x, long long n, cudaStream_t stream);
+// options off in the shipped yaml: RoPE (in place on q|k of the packed qkv rows), dropout in front of the factors projection,
+// per-day embedding (bias-gradient column sums routed by day, gradient scatter)
+template <typename T>
+int k_rope(T* qkv, const long long* ts, long long ts_stride, const float* cs, const float* sn, long long rows, int L, int H, int nh,
+           int max_F, int inverse, cudaStream_t stream);
+template <typename T>
+int k_dropout_inplace(T* x, long long n, float p, unsigned long long seed, unsigned long long stream_id, cudaStream_t stream);
+template <typename T>
+int k_colsum_sel(const T* in, float* out, const long long* sel, int n_sel, long long out_stride, int B, int rows_per_b, int cols,
+                 cudaStream_t stream);
+int k_add_inplace(float* dst, const float* src, long long n, cudaStream_t stream);
+template <typename T> int k_cast_to_f32(const T* in, float* out, long long n, cudaStream_t stream);
 int k_and_mask(const long long* tmask, const long long* pmask, long long* out, int B, int T, int N, cudaStream_t stream);
 
 // layernorm.cu

@@ -77,6 +77,7 @@ static void run_case(const char* name, GemmProblem p, size_t out_elems, double f
 
 static GemmProblem base_problem(int mode, int M, int N, int K) {
   GemmProblem p;
+  p.b_sel = nullptr;
   p.mode = mode; p.M = M; p.N = N; p.nb_out = 1; p.nchunk = 1; p.chunk_k = K;
   p.a_row_shift = p.a_col_shift = p.b_row_shift = p.b_col_shift = 0; p.b_chunk_n = N; p.split_k = 1;
   p.epi = gemm_epilogue_default();

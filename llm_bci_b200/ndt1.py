@@ -177,6 +177,12 @@ class NeuralAttention(nn.Module):
         self.attn_dropout = dropout
         self.dropout = nn.Dropout(dropout)
         self.out_proj = nn.Linear(hidden_size, hidden_size, bias=use_bias)
+        if use_rope:   # models/ndt1.py:44-53, 262-266: same op sequence, so the engine gets the reference's table values bit for bit
+            inv_freq = 1.0 / (base ** (torch.arange(0, self.head_size, 2).float() / self.head_size))
+            freqs = torch.einsum("i,j->ij", torch.arange(max_F, dtype=inv_freq.dtype), inv_freq)
+            emb = torch.cat((freqs, freqs), dim=-1)
+            self.register_buffer("cos", emb.cos().to(self.query.weight.dtype), persistent=False)
+            self.register_buffer("sin", emb.sin().to(self.query.weight.dtype), persistent=False)
 
 
 class NeuralEncoderLayer(nn.Module):
@@ -270,9 +276,14 @@ def _flat_param_table(model: "NDT1") -> List[Tuple[str, Optional[torch.nn.Parame
     enc, emb = model.encoder, model.encoder.embedder
     t: List[Tuple[str, Optional[torch.nn.Parameter]]] = []
     es = emb.embed_spikes
-    if isinstance(es, nn.ModuleList):
-        raise RuntimeError("embedder.adapt (per-day embedding) is not implemented in this build")
-    t += [("embed_w", es.weight), ("embed_b", es.bias)]
+    if isinstance(es, nn.ModuleList):      # embedder.adapt: one Linear per day (models/ndt1.py:118-127), routed by day_idx in the engine
+        if len(es) > _C.MAX_DAYS:
+            raise RuntimeError(f"embedder.adapt supports at most {_C.MAX_DAYS} days (n_days = {len(es)})")
+        t += [("embed_w", None), ("embed_b", None)]
+        for d, lin in enumerate(es):
+            t += [(f"embed_w_day.{d}", lin.weight), (f"embed_b_day.{d}", lin.bias)]
+    else:
+        t += [("embed_w", es.weight), ("embed_b", es.bias)]
     pr = emb.stack_projection if emb.stack else emb.projection
     t += [("proj_w", pr.weight), ("proj_b", pr.bias)]
     t += [("pos_w", emb.embed_pos.weight if emb.pos else None)]
@@ -300,6 +311,9 @@ def _fill_tensors(struct: "_C.Tensors", table, ptr_of) -> None:
         if slot.startswith("layer."):
             _, i, name = slot.split(".")
             setattr(struct.layer[int(i)], name, v)
+        elif slot.startswith("embed_w_day.") or slot.startswith("embed_b_day."):
+            name, d = slot.split(".")
+            getattr(struct, name)[int(d)] = v
         else:
             setattr(struct, slot, v)
 
@@ -445,6 +459,11 @@ class NDT1(nn.Module):
             _C.check(L.ndt1_engine_create(_C.C.byref(cfg), _C.C.byref(h)), "ndt1_engine_create")
             self._engine, self._engine_cap = h, (nb, nt, ns)
             self._apply_weight_shadow()
+            if self.config.encoder.transformer.use_rope:
+                a = self.encoder.layers[0].attn
+                dev = next(self.parameters()).device
+                cs, sn = a.cos.to(dev, torch.float32).contiguous(), a.sin.to(dev, torch.float32).contiguous()
+                _C.check(L.ndt1_engine_set_rope_tables(h, cs.data_ptr(), sn.data_ptr(), cs.shape[0]), "ndt1_engine_set_rope_tables")
         return self._engine
 
     def set_weight_shadow(self, flat_param: Optional[torch.Tensor], shadow: Optional[torch.Tensor]) -> None:
@@ -555,6 +574,7 @@ class NDT1(nn.Module):
         # arena order: the table's, except that each layer's q|k|v weights (and biases) sit next to each other so the
         # engine can run one (3H x H) weight-gradient GEMM, one bias reduction and one weight cast for the three
         rank = {"q_w": 0, "k_w": 1, "v_w": 2, "q_b": 3, "k_b": 4, "v_b": 5}
+        first_layer = min(i for i, (slot, _) in enumerate(table) if slot.startswith("layer."))
         def key(item):
             i, (slot, _) = item
             if slot.startswith("layer."):
@@ -562,7 +582,7 @@ class NDT1(nn.Module):
                 if name in rank:
                     return (1, int(l), 0, rank[name])
                 return (1, int(l), 1, i)
-            return (0, 0, 0, i) if i < 7 else (2, 0, 0, i)
+            return (0, 0, 0, i) if i < first_layer else (2, 0, 0, i)
         for _, (_, p) in sorted(enumerate(table), key=key):
             if p is not None:
                 offs[id(p)] = off

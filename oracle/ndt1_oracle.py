@@ -311,7 +311,8 @@ def _drop(x: torch.Tensor, site: str, drop_scales: Optional[dict]) -> torch.Tens
     if drop_scales is None:
         return x
     if "torch_dropout" in drop_scales:     # CPU-baseline mode: the reference's own nn.Dropout / SDPA dropout cost
-        p = drop_scales["torch_dropout"]["embed" if site == "embed" else "transformer"]
+        td = drop_scales["torch_dropout"]
+        p = td.get("factors", 0.0) if site == "factors" else td["embed" if site == "embed" else "transformer"]
         return F.dropout(x, p, True) if p > 0 else x
     if site not in drop_scales:
         return x
@@ -423,8 +424,8 @@ def encoder_forward(
     if n_prefix:
         h = h[:, n_prefix:, :]
     fc = enc_cfg["factors"]
+    h = _drop(h, "factors", drop_scales)       # models/ndt1.py:372: self.proj(self.dropout(x)), proj = Identity when inactive
     if fc["active"]:
-        h = _drop(h, "factors", drop_scales)
         h = _ACTS[fc["act"]](F.linear(h, P("out_proj.proj.0.weight"), P("out_proj.proj.0.bias") if fc["bias"] else None))
     return h, mask, targets_mask
 

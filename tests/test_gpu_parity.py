@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 import llm_bci_b200 as lb  # noqa: E402
 from llm_bci_b200 import _C  # noqa: E402
 from oracle import ndt1_oracle as O  # noqa: E402
-from test_oracle_golden import load, sub, small_ctc_cfg, mlm_cfg, CTC_KW  # noqa: E402
+from test_oracle_golden import load, sub, small_ctc_cfg, mlm_cfg, CTC_KW, VARIANTS, variant_case  # noqa: E402
 
 DEV = "cuda"
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
@@ -316,6 +316,98 @@ def test_full_size_model_b4_matches_reference(precision):
     if precision == "fp32":
         agree = (out.preds.argmax(-1).cpu().numpy() == g["out/argmax"]).mean()
         assert agree >= 0.999, agree     # random-init log-probs are near-uniform; ties may flip
+
+
+# --------------------------------------------------------------------------- options the shipped yaml leaves off
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_ctc_variants_match_reference(name, precision):
+    """Per-day embedding (adapt), RoPE, GELU embedder activation, factors projection: outputs of the unmodified reference."""
+    g = load("ctc_variants.npz")
+    cfg, params, batch = variant_case(g, name)
+    model = build(cfg, CTC_KW, params, precision).train()
+    assert [n for n, _ in model.named_parameters()] == list(sub(g, f"{name}/grad").keys())     # same module tree as the reference
+    out = model(**cuda_batch(batch))
+    out.loss.backward()
+    tol = TOL[precision]
+    ref_loss = float(g[f"{name}/out/loss"])
+    assert abs(float(out.loss) - ref_loss) <= tol * abs(ref_loss)
+    perr = np.abs(out.preds.cpu().double().numpy() - g[f"{name}/out/preds"]).max()
+    assert perr <= (2e-4 if precision == "fp32" else 5e-2), perr
+    gtol = tol
+    if precision == "bf16" and name == "gelu_factors":
+        # ReLU after the factors projection: a unit whose pre-activation is below the bf16 rounding error of its inputs
+        # (|pre| < ~7e-4 here, 0.1 % of the units) flips its 0/1 derivative, and a flipped fraction f costs ~sqrt(f) in
+        # relative L2 of everything upstream -- measured 2-6 %, identical to four digits on the CUDA-core GEMM path
+        # (NDT1_FORCE_SIMT=1), so it is the storage format, not the tensor-core kernels.  The same model with smooth
+        # activations (rope_adapt_gelu_factors) meets 2e-2.
+        gtol = 1e-1
+    check_grads(grads_of(model), sub(g, f"{name}/grad"), gtol)
+
+
+def test_rope_adapt_with_tensor_core_attention_bf16():
+    """RoPE + per-day embedding at head size 128 (the tcgen05 attention and GEMM kernels) against the oracle in fp32."""
+    cfg = lb.update_config(small_ctc_cfg(), {"encoder": {
+        "embedder": {"n_channels": 64, "input_dim": 64, "max_F": 256, "adapt": True, "n_days": 5},
+        "transformer": {"n_layers": 2, "hidden_size": 256, "n_heads": 2, "inter_size": 256, "use_rope": True}}})
+    torch.manual_seed(4)
+    model = lb.NDT1(cfg, **CTC_KW, precision="bf16").to(DEV).train()
+    params = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    batch = O.synthetic_ctc_batch(B=6, T=400, N=64, seed=3)
+    batch["day_idx"] = torch.tensor([4, 0, 2, 2, 0, 4])
+    out = model(**cuda_batch(batch))
+    out.loss.backward()
+    ref_out, ref_grads = O.ndt1_loss_and_grads(params, cfg, CTC_KW, batch, training=True)
+    assert abs(float(out.loss) - float(ref_out["loss"])) <= 2e-2 * abs(float(ref_out["loss"]))
+    got = grads_of(model)
+    assert float(got["encoder.embedder.embed_spikes.1.weight"].abs().max()) == 0.0        # no trial of day 1 or 3
+    assert float(got["encoder.embedder.embed_spikes.3.bias"].abs().max()) == 0.0
+    check_grads(got, {k: v.numpy() for k, v in ref_grads.items()}, 2e-2)
+
+
+@pytest.mark.parametrize("active", [False, True])
+def test_factors_dropout_replays_through_the_oracle(active):
+    """NeuralFactorsProjection drops its input whether or not the projection is active (models/ndt1.py:355,372)."""
+    g = load("ctc_variants.npz")
+    if active:
+        cfg, params, batch_cpu = variant_case(g, "gelu_factors")
+    else:
+        g0 = load("ctc_small.npz")
+        cfg, params = small_ctc_cfg(), {k: torch.from_numpy(v) for k, v in sub(g0, "param").items()}
+        batch_cpu = {k: torch.from_numpy(v) for k, v in sub(g0, "batch").items()}
+    cfg = lb.update_config(cfg, {"encoder": {"factors": {"dropout": 0.3}}})
+    model = build(cfg, CTC_KW, params, "fp32").train()
+    torch.manual_seed(7)
+    out = model(**cuda_batch(batch_cpu))
+    out.loss.backward()
+    torch.manual_seed(7)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    B, L, H = 3, 23, 64
+    t = torch.empty(B * L * H, device=DEV)
+    _C.check(_C.lib().ndt1_dropout_scales(t.data_ptr(), t.numel(), 0.3, seed, 1 + 4 * 2, _C.stream_ptr()))     # site 1 + 4 * n_layers
+    ds = {"factors": t.cpu().view(B, L, H)}
+    assert abs(ds["factors"].ne(0).float().mean().item() - 0.7) < 0.03
+    ref_out, ref_grads = O.ndt1_loss_and_grads(params, cfg, CTC_KW, batch_cpu, training=True, drop_scales=ds)
+    assert abs(float(out.loss) - float(ref_out["loss"])) <= 1e-4 * abs(float(ref_out["loss"]))
+    check_grads(grads_of(model), {k: v.numpy() for k, v in ref_grads.items()}, 1e-4)
+    model.eval()                                                        # eval: the site is off
+    ev = model(**cuda_batch(batch_cpu))
+    ref_ev, _ = O.ndt1_loss_and_grads(params, cfg, CTC_KW, batch_cpu, training=False)
+    assert abs(float(ev.loss) - float(ref_ev["loss"])) <= 1e-4 * abs(float(ref_ev["loss"]))
+
+
+def test_encoder_features_bf16_with_factors():
+    """model.encoder(...) sub-API (models/bci.py:125) with an active factors projection in the bf16 mode."""
+    g = load("ctc_variants.npz")
+    cfg, params, batch_cpu = variant_case(g, "gelu_factors")
+    feats = {}
+    for prec in ("fp32", "bf16"):
+        model = build(cfg, CTC_KW, params, prec).eval()
+        b = cuda_batch(batch_cpu)
+        x, m, _ = model.encoder(b["spikes"], b["spikes_mask"], b["spikes_timestamp"], b["spikes_lengths"])
+        assert x.shape == (3, 23, 48) and x.dtype == torch.float32
+        feats[prec] = x.cpu()
+    assert (feats["bf16"] - feats["fp32"]).abs().max() <= 5e-2 * feats["fp32"].abs().max()
 
 
 # --------------------------------------------------------------------------- dropout, properties at the benchmark size
