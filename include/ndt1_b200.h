@@ -242,6 +242,9 @@ int64_t ndt1_launch_counter(void);
 /* Debugging aid (tools/attn_timeline.py): the tensor-core attention kernels write per-CTA phase timestamps
  * (32 uint64 per CTA, %globaltimer ns) into buf; NULL switches it off. */
 int ndt1_debug_attention_timeline(uint64_t* buf);
+/* The same for the tensor-core GEMM (tools/gemm_timeline.py): 16 uint64 per CTA of every launch while set (each launch
+ * overwrites the previous one's slots). */
+int ndt1_debug_gemm_timeline(uint64_t* buf);
 /* keep-scale (0 or 1/(1-p)) of a dropout site, for tests: site 0 embed, 1+4*l attn-probs, 2+4*l attn-out, 3+4*l mlp */
 int ndt1_dropout_scales(float* out, int64_t n, float p, uint64_t seed, uint64_t site, void* stream);
 

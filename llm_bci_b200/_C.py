@@ -92,6 +92,7 @@ PROTOTYPES = {
     "ndt1_engine_set_weight_shadow": (_i, [_p, _p, _p, _i64]),
     "ndt1_adamw_step_fused": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _p, _i, _p]),
     "ndt1_debug_attention_timeline": (_i, [_p]),
+    "ndt1_debug_gemm_timeline": (_i, [_p]),
     "ndt1_engine_stage_count": (_i, [_p]),
     "ndt1_engine_wait_stage": (_i, [_p, _i, _p]),
     "ndt1_engine_set_rope_tables": (_i, [_p, _p, _p, _i]),

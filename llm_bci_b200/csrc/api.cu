@@ -138,6 +138,7 @@ int ndt1_profile_gemm_end(double* flops, double* ms, int64_t* launches) {
   return rc;
 }
 int64_t ndt1_launch_counter(void) { return g_ndt1_launches; }
+int ndt1_debug_gemm_timeline(uint64_t* buf) { gemm_tc_set_timeline((unsigned long long*)buf); return 0; }
 int ndt1_debug_attention_timeline(uint64_t* buf) { k_attention_tc_set_timeline((unsigned long long*)buf); return 0; }
 
 int ndt1_dropout_scales(float* out, int64_t n, float p, uint64_t seed, uint64_t site, void* stream) {

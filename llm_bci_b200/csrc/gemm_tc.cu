@@ -39,10 +39,19 @@ struct TcParams {
   int m_tiles, n_tiles, total_tiles;
   int chunk_k_valid;                   // reduction length per chunk in elements (for FLOP accounting)
   const long long* b_sel; int b_sel_n; // per-day B operand batch of an output trial (GEMM_NT), null = batch 0
+  unsigned long long* dbg;             // optional per-CTA phase timeline (tools/gemm_timeline.py): 16 slots per CTA, globaltimer ns
   GemmEpilogue epi;
 };
 
 using namespace tc;
+
+__device__ __forceinline__ void dbg_stamp(unsigned long long* dbg, int slot) {
+  if (dbg) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    dbg[(size_t)blockIdx.x * 16 + slot] = t;
+  }
+}
 
 __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
   __nv_bfloat162 x = __floats2bfloat162_rn(a, b), y = __floats2bfloat162_rn(c, d);
@@ -391,6 +400,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;     // 0 = leader (issues the MMAs)
   const int unit = blockIdx.x / CTAS;                          // persistent work unit: a CTA (CTAS = 1) or a CTA pair
   const int n_units = gridDim.x / CTAS;
+  if (threadIdx.x == 0) {
+    dbg_stamp(p.dbg, 0);
+    if (p.dbg) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); p.dbg[(size_t)blockIdx.x * 16 + 15] = smid; }
+  }
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -413,7 +426,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (CTAS == 2) cluster_sync_all();            // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_grid_sync();       // everything above touched only shared / tensor memory and the kernel parameters
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 1);
+  pdl_grid_sync();
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, 2);       // everything above touched only shared / tensor memory and the kernel parameters
 
   const int total_kb = p.nchunk * p.kb_per_chunk;
 
@@ -464,8 +479,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (tile == unit && kb == kb0) dbg_stamp(p.dbg, 3);
         }
       }
+      dbg_stamp(p.dbg, 4);          // all loads issued
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -485,6 +502,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (tile == unit && kb == kb0) dbg_stamp(p.dbg, 5);      // first operands landed
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
           // one descriptor per operand and k-block; the four k-steps advance it with a 64-bit add
@@ -498,6 +516,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit_g<CTAS>(&tfull_bar[acc_stage]);   // accumulator ready for the epilogue warps (of both CTAs)
+        dbg_stamp(p.dbg, 6);                        // (last write wins: issue of the last tile's final MMA)
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
@@ -553,6 +572,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const ChunkAt t_nxt = tile_at(tile + n_units);
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tc_fence_after();
+      if (ew == 0 && lane == 0) { if (tile == unit) dbg_stamp(p.dbg, 7); dbg_stamp(p.dbg, 8); }   // first / last accumulator ready
       const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * BN + half * (BN / 2));
 #pragma unroll 1                                   // one copy of the epilogue code: it must stay inside the instruction cache
       for (int c = 0; c < NCH; ++c) {
@@ -593,6 +613,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       t_cur = t_nxt;
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) dbg_stamp(p.dbg, 9 + (ew & 3));     // epilogue warps done (4 of the 8 recorded)
   }
 
   tc_fence_before();
@@ -602,6 +623,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_after();
     if (CTAS == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (lane == 0) dbg_stamp(p.dbg, 14);
   }
 }
 
@@ -633,6 +655,7 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // optional per-launch timing of the tensor-core GEMM (bench.py roofline): CUDA events on the launch stream
 struct ProfRec { cudaEvent_t e0, e1; double flops; };
+unsigned long long* g_gemm_dbg = nullptr;
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 size_t g_prof_used = 0;
@@ -820,6 +843,7 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   }
   tp.total_tiles = tp.m_tiles * tp.n_tiles * (p.mode == GEMM_TN ? tp.split_k : p.nb_out);
   tp.epi = p.epi;
+  tp.dbg = g_gemm_dbg;
 
   CUtensorMap ma, mb;
   if (p.mode == GEMM_TN) {
@@ -837,6 +861,7 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
 }
 
 // ---- profiling hooks (C ABI wrappers in api.cu) ----
+void gemm_tc_set_timeline(unsigned long long* buf) { g_gemm_dbg = buf; }
 int gemm_tc_profile_begin() {
   g_prof_used = 0; g_prof_on = true;
   return 0;
