@@ -328,7 +328,10 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release at CTA scope): a cluster-scope release compiles to MEMBAR.ALL.GPU, i.e. every epilogue warp would
+  // wait for all of its outstanding global stores and side loads once per tile.  What the leader's MMA thread needs ordered
+  // before it reuses the accumulator stage is the tcgen05.ld of this warp, which tcgen05.wait::ld + fence::before_thread_sync cover.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 template <int CTAS>
 __device__ __forceinline__ void tma_load_3d_g(void* dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1, int c2) {
@@ -603,7 +606,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = (lane >> 3) + 4 * i;
-          acc[i] = *(const float4*)(stg + rr * 128 + ((((lane & 7) ^ rr) & 7) << 4));
+          const uint32_t a = stg_u32 + rr * 128 + ((((lane & 7) ^ rr) & 7) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[i].x), "=f"(acc[i].y), "=f"(acc[i].z), "=f"(acc[i].w) : "r"(a) : "memory");
         }
         __syncwarp();
         epilogue_chunk<EPI>(e, cx, p, at, lane, acc, side_cur, stg);
@@ -618,7 +622,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (CTAS == 2) cluster_sync_all();            // nobody leaves (or frees tensor memory) while the peer may still signal it
+  if (CTAS == 2) {                              // nobody leaves (or frees tensor memory) while the peer may still signal it;
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");    // pure execution barrier: a releasing arrive would be a
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");              // MEMBAR.ALL.GPU, i.e. wait for every store of the epilogue
+  }
   if (warp == 1) {
     tc_fence_after();
     if (CTAS == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
