@@ -103,7 +103,8 @@ enum { SIDE_NONE = 0, SIDE_RESID = 1, SIDE_DACT = 2, SIDE_GATHER = 3 };
 // instruction-fetch stalls then rival the arithmetic).  EF_* = features a class may use.
 enum {
   EF_OUT2 = 1, EF_ACT = 2, EF_GATHER = 4, EF_DROP = 8, EF_DACT = 16, EF_RESID = 32, EF_COLSUM = 64, EF_ACCUM = 128, EF_SCALAR = 256,
-  EPI_PLAIN = EF_RESID,                                  // bias (+ fp32 residual): QKV, attention out-proj, plain data gradients
+  EPI_NONE = 0,                                          // bias only: QKV, plain data gradients (no side input, no side registers)
+  EPI_PLAIN = EF_RESID,                                  // bias + fp32 residual: attention out-proj
   EPI_ACT = EF_OUT2 | EF_ACT,                            // bias + activation (+ pre-activation copy): MLP up-proj, channel embedding
   EPI_DROP = EF_GATHER | EF_DROP | EF_RESID,             // bias (+ position rows) + dropout (+ residual): MLP down-proj, stack projection
   EPI_DACT = EF_DROP | EF_DACT | EF_COLSUM,              // backward: dropout mask, activation derivative, bias-gradient column sums
@@ -121,6 +122,7 @@ struct ChunkAt {          // where a (tile, chunk) lands in the output
   int bt, r0, n;          // trial, first row of this warp's 32-row strip, first column of this lane
   long long rowbase;      // element offset of (trial, this lane's first row, column 0): computed once per tile
   long long bias_off;     // per-day bias row (0 without routing)
+  uint32_t rowmask;       // bit i: row r0 + lane/8 + 4 i of this lane is inside the output (per tile, not per chunk)
   bool live;
 };
 
@@ -129,25 +131,34 @@ __device__ __forceinline__ void side_load(const GemmEpilogue& e, const EpiCtx& c
                                           float4* side) {
   if (!ef_has(EPI, EF_RESID | EF_DACT | EF_GATHER)) return;
   if (cx.side_kind == SIDE_NONE || !cx.vec_ok || !at.live || at.n >= p.N) return;
+  const long long idx0 = at.rowbase + at.n;        // one 64-bit base per chunk; rows are 32-bit offsets from it
+  const uint32_t ld4 = 4u * (uint32_t)e.ldc;
+  if (ef_has(EPI, EF_RESID) && cx.side_kind == SIDE_RESID) {
+    const float* b = e.resid + idx0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = at.r0 + (lane >> 3) + 4 * i;
-    if (r < p.M) {
-      const long long idx = at.rowbase + (long long)i * (4 * e.ldc) + at.n;
-      if (ef_has(EPI, EF_RESID) && cx.side_kind == SIDE_RESID) {
-        side[i] = __ldg((const float4*)(e.resid + idx));
-      } else if (ef_has(EPI, EF_DACT) && cx.side_kind == SIDE_DACT) {
-        if (e.dact_in_bf16) {
-          const uint2 t = __ldg((const uint2*)((const bf16*)e.dact_in + idx));
+    for (int i = 0; i < 8; ++i) if ((at.rowmask >> i) & 1u) side[i] = __ldg((const float4*)(b + i * ld4));
+  } else if (ef_has(EPI, EF_DACT) && cx.side_kind == SIDE_DACT) {
+    if (e.dact_in_bf16) {
+      const bf16* b = (const bf16*)e.dact_in + idx0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if ((at.rowmask >> i) & 1u) {
+          const uint2 t = __ldg((const uint2*)(b + i * ld4));
           side[i].x = __uint_as_float(t.x); side[i].y = __uint_as_float(t.y);
-        } else {
-          side[i] = __ldg((const float4*)((const float*)e.dact_in + idx));
         }
-      } else if (ef_has(EPI, EF_GATHER)) {
+    } else {
+      const float* b = (const float*)e.dact_in + idx0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if ((at.rowmask >> i) & 1u) side[i] = __ldg((const float4*)(b + i * ld4));
+    }
+  } else if (ef_has(EPI, EF_GATHER)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((at.rowmask >> i) & 1u) {
+        const int r = at.r0 + (lane >> 3) + 4 * i;
         const long long g = __ldg(e.gather_idx + (long long)at.bt * e.gather_idx_stride + r);
         side[i] = __ldg((const float4*)(e.gather_tab + g * e.gather_ld + at.n));
       }
-    }
   }
 }
 
@@ -184,11 +195,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
   }
   // element offset of row i: idx0 + i * (4 * ldc); row-valid bits
   const long long idx0 = at.rowbase + at.n;
-  const long long ld4 = 4 * e.ldc;
-  uint32_t okm = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) okm |= (col_ok && (at.r0 + (lane >> 3) + 4 * i) < p.M) ? (1u << i) : 0u;
-#define idx(i) (idx0 + (i) * ld4)
+  const uint32_t ld4 = 4u * (uint32_t)e.ldc;       // (32-bit: a tile spans at most 32 rows of the output)
+  const uint32_t okm = col_ok ? at.rowmask : 0u;
+#define idx(i) (idx0 + (unsigned)((i) * ld4))
 #define ok(i) ((okm >> (i)) & 1u)
   if (ef_has(EPI, EF_OUT2) && e.out2) {
 #pragma unroll
@@ -298,12 +307,28 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
     }
     if (lane < 8 && col_ok) red_add_v4(e.colsum + at.n, cs.x, cs.y, cs.z, cs.w);
   }
+  if (ef_has(EPI, EF_ACCUM) && e.accumulate) {
+    float* o = (float*)e.out + idx0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (!ok(i)) continue;
-    if (ef_has(EPI, EF_ACCUM) && e.accumulate) red_add_v4((float*)e.out + idx(i), v[i].x, v[i].y, v[i].z, v[i].w);
-    else if (e.out_bf16) *(uint2*)((bf16*)e.out + idx(i)) = pack4_bf16(v[i].x, v[i].y, v[i].z, v[i].w);
-    else *(float4*)((float*)e.out + idx(i)) = v[i];
+    for (int i = 0; i < 8; ++i) if (ok(i)) red_add_v4(o + i * ld4, v[i].x, v[i].y, v[i].z, v[i].w);
+  } else if (e.out_bf16) {
+    bf16* o = (bf16*)e.out + idx0;
+    if (okm == 0xFFu) {                      // interior tile (all but the last row tile): no per-row predicates
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *(uint2*)(o + i * ld4) = pack4_bf16(v[i].x, v[i].y, v[i].z, v[i].w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (ok(i)) *(uint2*)(o + i * ld4) = pack4_bf16(v[i].x, v[i].y, v[i].z, v[i].w);
+    }
+  } else {
+    float* o = (float*)e.out + idx0;
+    if (okm == 0xFFu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *(float4*)(o + i * ld4) = v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (ok(i)) *(float4*)(o + i * ld4) = v[i];
+    }
   }
 #undef idx
 #undef ok
@@ -550,6 +575,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       at.r0 = mt * (BM * CTAS) + rank * BM + q * 32;
       at.n = nt * BN + half * (BN / 2) + (lane & 7) * 4;          // chunk 0
       at.rowbase = (long long)at.bt * e.c_batch_stride + (long long)(at.r0 + (lane >> 3)) * e.ldc;
+      at.rowmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) at.rowmask |= (at.r0 + (lane >> 3) + 4 * i) < p.M ? (1u << i) : 0u;
       at.bias_off = 0;
       if (e.sel && at.live) {
         long long d = __ldg(e.sel + bz);
@@ -737,9 +765,9 @@ int epilogue_class(const TcParams& tp, int bn) {
                    (e.gather_tab == nullptr || e.gather_ld % 4 == 0) && (e.drop_p <= 0.f || tp.N % 8 == 0);
   if (!vec || bn != 256) return EPI_ALL;
   // (only the classes launch_256 instantiates for this operand mode)
-  const int nt[3] = {EPI_PLAIN, EPI_ACT, EPI_DROP}, nn[2] = {EPI_PLAIN, EPI_DACT}, tn[1] = {EPI_ACCUM};
+  const int nt[4] = {EPI_NONE, EPI_PLAIN, EPI_ACT, EPI_DROP}, nn[2] = {EPI_NONE, EPI_DACT}, tn[1] = {EPI_ACCUM};
   const int* classes = tp.mode == GEMM_NT ? nt : (tp.mode == GEMM_NN ? nn : tn);
-  const int n = tp.mode == GEMM_NT ? 3 : (tp.mode == GEMM_NN ? 2 : 1);
+  const int n = tp.mode == GEMM_NT ? 4 : (tp.mode == GEMM_NN ? 2 : 1);
   for (int c = 0; c < n; ++c)
     if ((need & ~classes[c]) == 0) return classes[c];
   return EPI_ALL;
@@ -749,11 +777,12 @@ template <int MODE, int CTAS>
 int launch_256(int cls, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp, cudaStream_t stream) {
   // classes a mode can meet: forward (NT) plain / activation / dropout; data gradient (NN) plain / derivative; weight gradient (TN) accumulate
   if (MODE == GEMM_NT) {
+    if (cls == EPI_NONE) return launch_inst<256, MODE, CTAS, EPI_NONE>(ma, mb, tp, stream);
     if (cls == EPI_PLAIN) return launch_inst<256, MODE, CTAS, EPI_PLAIN>(ma, mb, tp, stream);
     if (cls == EPI_ACT) return launch_inst<256, MODE, CTAS, EPI_ACT>(ma, mb, tp, stream);
     if (cls == EPI_DROP) return launch_inst<256, MODE, CTAS, EPI_DROP>(ma, mb, tp, stream);
   } else if (MODE == GEMM_NN) {
-    if (cls == EPI_PLAIN) return launch_inst<256, MODE, CTAS, EPI_PLAIN>(ma, mb, tp, stream);
+    if (cls == EPI_NONE) return launch_inst<256, MODE, CTAS, EPI_NONE>(ma, mb, tp, stream);
     if (cls == EPI_DACT) return launch_inst<256, MODE, CTAS, EPI_DACT>(ma, mb, tp, stream);
   } else {
     if (cls == EPI_ACCUM) return launch_inst<256, MODE, CTAS, EPI_ACCUM>(ma, mb, tp, stream);
