@@ -87,6 +87,12 @@ int ndt1_ctc_loss(const float* logits, float* logp, const int64_t* targets, cons
 /* argmax + format_ctc, main.py:69 and utils/eval_bci.py:41-48.  out_ids (B,L) padded with -1, out_len (B). */
 int ndt1_ctc_greedy_decode(const float* logp, int B, int L, int V, int blank, int64_t* out_ids, int64_t* out_len, void* stream);
 
+/* editdistance.eval(pred, target) per trial (word_edit_distance, utils/eval_bci.py:11-14; the CER metric of main.py:67-73 is
+ * sum(errors) / sum(max(target_len, 1))): Levenshtein distance between the first pred_len[b] ids of pred_ids (B,Lp) -- the
+ * output of ndt1_ctc_greedy_decode -- and the first target_len[b] ids of target_ids (B,Lt).  errors (B). */
+int ndt1_edit_distance(const int64_t* pred_ids, const int64_t* pred_len, int Lp, const int64_t* target_ids, const int64_t* target_len, int Lt,
+                       int B, int64_t* errors, void* stream);
+
 /* masked Poisson-NLL / MSE, models/ndt1.py:508-515,548-578.  *loss += sum, *count += weights. */
 int ndt1_recon_loss(const float* pred, const float* target, float* dpred, const int64_t* targets_mask, const int64_t* pad_mask,
                     int B, int T, int N, int loss_kind, int shift_by_one, int relu_out, float* loss, int64_t* count,
@@ -210,6 +216,10 @@ int ndt1_engine_out_len(const ndt1_engine* e, int T);
 int ndt1_engine_forward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_batch* batch, const ndt1_outputs* out, void* stream);
 /* backward of the last forward: grads->X += dloss * dLoss/dX (buffers are caller-zeroed) */
 int ndt1_engine_backward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_tensors* grads, const float* dloss, void* stream);
+/* backward of an encoder-only forward (batch.encoder_only = 1, need_backward = 1): dfeatures (B,L',H_out) is the caller's
+ * gradient w.r.t. outputs.features -- what autograd hands back when the encoder feeds another model
+ * (NeuralEncoder.forward used as a sub-module, models/bci.py:125).  Same accumulation rule as ndt1_engine_backward. */
+int ndt1_engine_backward_features(ndt1_engine* e, const ndt1_tensors* params, const ndt1_tensors* grads, const float* dfeatures, void* stream);
 /* The backward runs its weight-gradient GEMMs on an engine-owned second stream, concurrently with the data-gradient
  * chain (joined before ndt1_engine_backward's work on `stream` ends).  on = 0 serialises everything on `stream`
  * (used to time single kernels); default 1, or 0 when NDT1_OVERLAP=0 is set at engine creation. */

@@ -75,6 +75,7 @@ PROTOTYPES = {
     "ndt1_ctc_workspace_bytes": (_sz, [_i, _i, _i]),
     "ndt1_ctc_loss": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "ndt1_ctc_greedy_decode": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "ndt1_edit_distance": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _p]),
     "ndt1_recon_loss": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "ndt1_layernorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p]),
     "ndt1_linear_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
@@ -87,6 +88,7 @@ PROTOTYPES = {
     "ndt1_engine_out_len": (_i, [_p, _i]),
     "ndt1_engine_forward": (_i, [_p, C.POINTER(Tensors), C.POINTER(Batch), C.POINTER(Outputs), _p]),
     "ndt1_engine_backward": (_i, [_p, C.POINTER(Tensors), C.POINTER(Tensors), _p, _p]),
+    "ndt1_engine_backward_features": (_i, [_p, C.POINTER(Tensors), C.POINTER(Tensors), _p, _p]),
     "ndt1_engine_launch_count": (_i64, [_p]),
     "ndt1_engine_set_overlap": (_i, [_p, _i]),
     "ndt1_engine_set_weight_shadow": (_i, [_p, _p, _p, _i64]),

@@ -38,6 +38,11 @@ int ndt1_ctc_loss(const float* logits, float* logp, const int64_t* targets, cons
   return k_ctc_fwd_bwd(logp, (const long long*)targets, (const long long*)input_lengths, (const long long*)target_lengths, B, L, V, S,
                        blank, zero_infinity, (float*)workspace, nll, loss, dlogits, dloss, s);
 }
+int ndt1_edit_distance(const int64_t* pred_ids, const int64_t* pred_len, int Lp, const int64_t* target_ids, const int64_t* target_len, int Lt,
+                       int B, int64_t* errors, void* stream) {
+  return k_edit_distance((const long long*)pred_ids, (const long long*)pred_len, Lp, (const long long*)target_ids, (const long long*)target_len, Lt,
+                         B, (long long*)errors, (cudaStream_t)stream);
+}
 int ndt1_ctc_greedy_decode(const float* logp, int B, int L, int V, int blank, int64_t* out_ids, int64_t* out_len, void* stream) {
   return k_ctc_greedy_decode(logp, B, L, V, blank, (long long*)out_ids, (long long*)out_len, (cudaStream_t)stream);
 }

@@ -318,6 +318,48 @@ __global__ void greedy_kernel(const float* logp, int B, int L, int V, int blank,
   out_len[b] = n;
 }
 
+// Levenshtein distance between a decoded id sequence and its target (editdistance.eval in utils/eval_bci.py:11-14), one warp
+// per pair, one DP row per step.  new[j] = min(t[j], new[j-1] + 1) with t[j] = min(prev[j] + 1, prev[j-1] + cost) unrolls to
+// new[j] = j + min_{k<=j}(t[k] - k): the row is a prefix minimum (warp scan, 32 columns at a time, carry across blocks).
+constexpr int kEdWarps = 4;
+__global__ void __launch_bounds__(kEdWarps * 32) edit_distance_kernel(const long long* __restrict__ pred, const long long* __restrict__ pred_len, int Lp,
+                                                                     const long long* __restrict__ tgt, const long long* __restrict__ tgt_len, int Lt,
+                                                                     int B, long long* __restrict__ out) { pdl_grid_sync();
+  extern __shared__ int ed_sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kEdWarps + warp;
+  if (b >= B) return;
+  long long ml = pred_len[b], nl = tgt_len[b];
+  const int m = (int)(ml < 0 ? 0 : (ml > Lp ? Lp : ml)), n = (int)(nl < 0 ? 0 : (nl > Lt ? Lt : nl));
+  int* prev = ed_sm + warp * 2 * (Lt + 1);
+  int* cur = prev + (Lt + 1);
+  const long long* pa = pred + (long long)b * Lp;
+  const long long* tb = tgt + (long long)b * Lt;
+  for (int j = lane; j <= n; j += 32) prev[j] = j;
+  __syncwarp();
+  for (int i = 1; i <= m; ++i) {
+    const long long a = pa[i - 1];
+    int carry = i;                                  // new[0] - 0
+    for (int j0 = 1; j0 <= n; j0 += 32) {
+      const int j = j0 + lane;
+      int v = 1 << 29;
+      if (j <= n) v = min(prev[j] + 1, prev[j - 1] + (a != tb[j - 1] ? 1 : 0)) - j;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = min(v, u);
+      }
+      v = min(v, carry);
+      if (j <= n) cur[j] = v + j;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (lane == 0) cur[0] = i;
+    __syncwarp();
+    int* t = prev; prev = cur; cur = t;
+  }
+  if (lane == 0) out[b] = prev[n];
+}
+
 }  // namespace
 
 int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaStream_t stream, int ld_in) {
@@ -381,6 +423,16 @@ int k_ctc_fwd_bwd(const float* logp, const long long* targets, const long long* 
 int k_ctc_greedy_decode(const float* logp, int B, int L, int V, int blank, long long* out_ids, long long* out_len, cudaStream_t stream) {
   if (B == 0) return 0;
   ndt1_launch(greedy_kernel, ndt1_cdiv(B, 64), 64, 0, stream, logp, B, L, V, blank, out_ids, out_len);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+
+int k_edit_distance(const long long* pred, const long long* pred_len, int Lp, const long long* tgt, const long long* tgt_len, int Lt, int B,
+                    long long* out, cudaStream_t stream) {
+  if (B == 0) return 0;
+  const size_t smem = (size_t)kEdWarps * 2 * (Lt + 1) * sizeof(int);
+  NDT1_REQUIRE(smem <= 48 * 1024, "edit_distance: targets of %d ids are too long", Lt);
+  ndt1_launch(edit_distance_kernel, ndt1_cdiv(B, kEdWarps), kEdWarps * 32, smem, stream, pred, pred_len, Lp, tgt, tgt_len, Lt, B, out);
   NDT1_CHECK_LAUNCH();
   return 0;
 }

@@ -909,6 +909,13 @@ __global__ void cast_to_f32_kernel(const T* __restrict__ in, float* __restrict__
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) out[e] = to_f32(in[e]);
 }
 
+// g *= act'(saved): gradient through an activation whose GEMM epilogue is not on the path (encoder-only backward with factors)
+template <typename T>
+__global__ void dact_inplace_kernel(T* __restrict__ g, const T* __restrict__ saved, long long n, int dact) { pdl_grid_sync();
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    g[e] = from_f32<T>(to_f32(g[e]) * dact_apply(dact, to_f32(saved[e])));
+}
+
 __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) { pdl_grid_sync();
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) dst[e] += src[e];
 }
@@ -967,3 +974,13 @@ int k_cast_to_f32(const T* in, float* out, long long n, cudaStream_t stream) {
 }
 template int k_cast_to_f32<float>(const float*, float*, long long, cudaStream_t);
 template int k_cast_to_f32<bf16>(const bf16*, float*, long long, cudaStream_t);
+
+template <typename T>
+int k_dact_inplace(T* g, const T* saved, long long n, int dact, cudaStream_t stream) {
+  if (n == 0 || dact == DACT_NONE) return 0;
+  ndt1_launch(dact_inplace_kernel<T>, ew_blocks(n), 256, 0, stream, g, saved, n, dact);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+template int k_dact_inplace<float>(float*, const float*, long long, int, cudaStream_t);
+template int k_dact_inplace<bf16>(bf16*, const bf16*, long long, int, cudaStream_t);

@@ -49,7 +49,7 @@ struct ndt1_engine {
   int n_stages() const { return c.n_layers + 2; }
   virtual ~ndt1_engine() {}
   virtual int forward(const ndt1_tensors* P, const ndt1_batch* b, const ndt1_outputs* o, cudaStream_t s) = 0;
-  virtual int backward(const ndt1_tensors* P, const ndt1_tensors* G, const float* dloss, cudaStream_t s) = 0;
+  virtual int backward(const ndt1_tensors* P, const ndt1_tensors* G, const float* dloss, cudaStream_t s, const float* dfeatures = nullptr) = 0;
   virtual size_t arena_bytes() const = 0;
   virtual int set_rope_tables(const float* cs, const float* sn, int rows) = 0;
   int out_len(int T) const { return c.stack_active ? (T - c.stack_size) / c.stack_stride + 1 : T; }
@@ -98,7 +98,7 @@ struct Engine : ndt1_engine {
   std::vector<const bf16*> u_qkv, u_o, u_up, u_down;
   std::vector<float*> b_qkv;
   // state of the last forward
-  int B = 0, Tn = 0, Tp = 0, L = 0, S = 0, training = 0; unsigned long long seed = 0; bool have_fwd = false;
+  int B = 0, Tn = 0, Tp = 0, L = 0, S = 0, training = 0; unsigned long long seed = 0; bool have_fwd = false, fwd_encoder_only = false;
   const float* spikes_ptr = nullptr; const long long* ts_ptr = nullptr; const long long* block_ptr = nullptr; const long long* day_ptr = nullptr;
 
   size_t arena_bytes() const override { return ar.cap; }
@@ -485,7 +485,9 @@ struct Engine : ndt1_engine {
       NDT1_CUDA_CHECK(cudaMemcpy2DAsync(o->features, (size_t)Tp * Hout * 4, feat32 + (long long)n_prefix * Hout, (size_t)L * Hout * 4,
                                         (size_t)Tp * Hout * 4, B, cudaMemcpyDeviceToDevice, s));
     }
+    fwd_encoder_only = bt->encoder_only != 0;
     if (bt->encoder_only) {
+      have_fwd = bt->need_backward != 0;     // ndt1_engine_backward_features continues from d(features)
       NDT1_CUDA_CHECK(cudaMemsetAsync(o->loss, 0, sizeof(float), s));
       launches = g_ndt1_launches - launches0;
       return 0;
@@ -534,9 +536,10 @@ struct Engine : ndt1_engine {
   }
 
   // ---- backward -----------------------------------------------------------
-  int backward(const ndt1_tensors* P, const ndt1_tensors* G, const float* dloss, cudaStream_t s) override {
+  int backward(const ndt1_tensors* P, const ndt1_tensors* G, const float* dloss, cudaStream_t s, const float* dfeatures) override {
     const ndt1_config& k = c;
     NDT1_REQUIRE(have_fwd, "engine: backward without a matching forward (need_backward = 1)");
+    NDT1_REQUIRE(fwd_encoder_only == (dfeatures != nullptr), "engine: an encoder-only forward is continued by ndt1_engine_backward_features, a full one by ndt1_engine_backward");
     const long long launches0 = g_ndt1_launches;
     if (B == 0) return 0;
     const int H = k.hidden, I = k.inter, D = k.input_dim, N = k.n_channels, NL = k.n_layers, V = k.n_outputs;
@@ -557,13 +560,24 @@ struct Engine : ndt1_engine {
       NDT1_CUDA_CHECK(cudaStreamWaitEvent(ws, e, 0));
       return 0;
     };
+    const T* head_in = k.factors_active ? fac : hn; const int head_ld = k.factors_active ? Hout : H;
+    T* d_head_in = k.factors_active ? dfac : dhn;
+    if (n_prefix > 0) NDT1_CUDA_CHECK(cudaMemsetAsync(d_head_in, 0, M * head_ld * sizeof(T), s));
+    if (dfeatures) {
+      // encoder-only (NeuralEncoder.forward as used by models/bci.py:125): the caller's gradient w.r.t. the (B, T', H_out) features
+      for (int b = 0; b < (n_prefix > 0 ? B : 1); ++b) {
+        const long long rows = n_prefix > 0 ? Tp : Mo;
+        NDT1_TRY(k_scale_cast_pad<T>(dfeatures + (long long)b * Tp * Hout, d_head_in + ((long long)b * L + n_prefix) * head_ld, rows, Hout, head_ld, nullptr, s));
+      }
+      if (k.factors_active) {
+        if (k.factors_act == NDT1_ACT_GELU) NDT1_TRY(k_dact_inplace<T>(dfac, fpre, M * Hout, DACT_GELU_FROM_IN, s));
+        else NDT1_TRY(k_dact_inplace<T>(dfac, fac, M * Hout, dact_from_out(k.factors_act), s));
+      }
+    } else {
     // head
     NDT1_TRY(k_scale_cast_pad<T>(dlogits, dlog, Mo, V, ldV, dloss, s));
     NDT1_TRY(fork());
     if (G->dec_b) NDT1_TRY(k_colsum<T>(dlog, G->dec_b, Mo, V, ldV, ws));
-    const T* head_in = k.factors_active ? fac : hn; const int head_ld = k.factors_active ? Hout : H;
-    T* d_head_in = k.factors_active ? dfac : dhn;
-    if (n_prefix > 0) NDT1_CUDA_CHECK(cudaMemsetAsync(d_head_in, 0, M * head_ld * sizeof(T), s));
     if (G->dec_w) {
       GemmProblem p = prob(GEMM_TN, V, Hout, Tp);
       p.nchunk = B;
@@ -594,6 +608,7 @@ struct Engine : ndt1_engine {
       }
       NDT1_TRY(run(p, s));
     }
+    }   // (full backward)
     if (k.factors_active) {
       NDT1_TRY(fork());
       if (G->factors_b && k.factors_bias) NDT1_TRY(k_colsum<T>(dfac, G->factors_b, M, Hout, Hout, ws));
@@ -826,6 +841,10 @@ int ndt1_engine_forward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_b
 int ndt1_engine_backward(ndt1_engine* e, const ndt1_tensors* params, const ndt1_tensors* grads, const float* dloss, void* stream) {
   NDT1_REQUIRE(e && params && grads, "engine_backward: null argument");
   return e->backward(params, grads, dloss, (cudaStream_t)stream);
+}
+int ndt1_engine_backward_features(ndt1_engine* e, const ndt1_tensors* params, const ndt1_tensors* grads, const float* dfeatures, void* stream) {
+  NDT1_REQUIRE(e && params && grads && dfeatures, "engine_backward_features: null argument");
+  return e->backward(params, grads, nullptr, (cudaStream_t)stream, dfeatures);
 }
 int64_t ndt1_engine_launch_count(const ndt1_engine* e) { return e->launches; }
 int ndt1_engine_set_weight_shadow(ndt1_engine* e, const float* params_fp32, const void* shadow_bf16, int64_t n) {

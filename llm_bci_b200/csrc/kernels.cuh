@@ -49,6 +49,7 @@ template <typename T>
 int k_colsum_sel(const T* in, float* out, const long long* sel, int n_sel, long long out_stride, int B, int rows_per_b, int cols,
                  cudaStream_t stream);
 int k_add_inplace(float* dst, const float* src, long long n, cudaStream_t stream);
+template <typename T> int k_dact_inplace(T* g, const T* saved, long long n, int dact, cudaStream_t stream);
 template <typename T> int k_cast_to_f32(const T* in, float* out, long long n, cudaStream_t stream);
 int k_and_mask(const long long* tmask, const long long* pmask, long long* out, int B, int T, int N, cudaStream_t stream);
 
@@ -98,4 +99,6 @@ int k_ctc_fwd_bwd(const float* logp, const long long* targets, const long long* 
                   int S, int blank, int zero_infinity, float* alpha_ws, float* nll, float* loss, float* dlogits, const float* dloss,
                   cudaStream_t stream, int fast_math = 0);
 size_t k_ctc_workspace_floats(int B, int L, int S);
+int k_edit_distance(const long long* pred, const long long* pred_len, int Lp, const long long* tgt, const long long* tgt_len, int Lt, int B,
+                    long long* out, cudaStream_t stream);
 int k_ctc_greedy_decode(const float* logp, int B, int L, int V, int blank, long long* out_ids, long long* out_len, cudaStream_t stream);

@@ -34,3 +34,24 @@ def greedy_ctc_decode(log_probs: torch.Tensor, blank_id: int = 0):
     _C.check(_C.lib().ndt1_ctc_greedy_decode(lp.data_ptr(), B, L, V, int(blank_id), ids.data_ptr(), lens.data_ptr(), _C.stream_ptr()),
              "ndt1_ctc_greedy_decode")
     return ids, lens
+
+
+def ctc_error_counts(log_probs: torch.Tensor, targets: torch.Tensor, targets_lengths: torch.Tensor, blank_id: int = 0):
+    """The CER metric of main.py:67-73 without leaving the device: greedy decode, then the edit distance of every trial to its
+    target ids (word_error_count, utils/eval_bci.py:19-36, on ids instead of space-joined phoneme strings).  Returns
+    (errors (B), words (B)) as int64 device tensors; CER = errors.sum() / words.sum().  An empty target counts as one word,
+    as `"".split(" ")` does in the reference."""
+    ids, lens = greedy_ctc_decode(log_probs, blank_id)
+    tg = targets.detach().to(device=ids.device, dtype=torch.int64).contiguous()
+    tl = targets_lengths.detach().to(device=ids.device, dtype=torch.int64).contiguous()
+    B, L = ids.shape
+    errors = torch.empty((B,), dtype=torch.int64, device=ids.device)
+    _C.check(_C.lib().ndt1_edit_distance(ids.data_ptr(), lens.data_ptr(), L, tg.data_ptr(), tl.data_ptr(), int(tg.shape[1]), B,
+                                         errors.data_ptr(), _C.stream_ptr()), "ndt1_edit_distance")
+    return errors, tl.clamp(min=1)
+
+
+def phoneme_error_rate(log_probs: torch.Tensor, targets: torch.Tensor, targets_lengths: torch.Tensor, blank_id: int = 0) -> torch.Tensor:
+    """errors / n_phonemes over the batch (the `cer` metric function of main.py:67-73), a 0-dim device tensor."""
+    errors, words = ctc_error_counts(log_probs, targets, targets_lengths, blank_id)
+    return errors.sum().float() / words.sum().float()

@@ -336,6 +336,23 @@ class _EngineFunction(torch.autograd.Function):
         return (None, None) + tuple(grads)
 
 
+class _EncoderFunction(torch.autograd.Function):
+    """NeuralEncoder.forward as a differentiable sub-module (models/bci.py:125 trains through it):
+    forward = ndt1_engine_forward(encoder_only), backward = ndt1_engine_backward_features."""
+
+    @staticmethod
+    def forward(ctx, model: "NDT1", call: dict, *params):
+        out = model._engine_forward(call, need_backward=True)
+        ctx.model = model
+        ctx.mark_non_differentiable(out["out_mask"])
+        return out["features"], out["out_mask"]
+
+    @staticmethod
+    def backward(ctx, dfeatures, _dmask):
+        grads = ctx.model._engine_backward(None, dfeatures=dfeatures)
+        return (None, None) + tuple(grads)
+
+
 class NDT1(nn.Module):
 
     def __init__(self, config: DictConfig, **kwargs):
@@ -535,7 +552,7 @@ class NDT1(nn.Module):
             b.targets_mask = _C.ptr(call.get("targets_mask"))
             keep["tm"] = call.get("targets_mask")
         b.B, b.T, b.S = B, T, S
-        b.training, b.need_backward, b.encoder_only = int(self.training), int(need_backward and not enc_only), int(enc_only)
+        b.training, b.need_backward, b.encoder_only = int(self.training), int(need_backward), int(enc_only)
         b.seed = _seed_from_torch() if self.training else 0
         o = _C.Outputs()
         o.loss, o.n_examples, o.preds = loss.data_ptr(), n_examples.data_ptr(), _C.ptr(preds)
@@ -547,8 +564,9 @@ class NDT1(nn.Module):
                               loss_mask=loss_mask, features=features)
         return self._last_out
 
-    def _engine_backward(self, dloss: torch.Tensor, into: Optional[torch.Tensor] = None):
-        """Returns one gradient tensor per parameter (views of one flat fp32 buffer)."""
+    def _engine_backward(self, dloss: Optional[torch.Tensor], into: Optional[torch.Tensor] = None, dfeatures: Optional[torch.Tensor] = None):
+        """Returns one gradient tensor per parameter (views of one flat fp32 buffer).  ``dfeatures`` continues an
+        encoder-only forward from the gradient w.r.t. its features instead of from the loss."""
         table, pstruct = self._params()
         plist = [p for _, p in table if p is not None]
         total = self._grad_offsets()[1]
@@ -561,9 +579,14 @@ class NDT1(nn.Module):
                 views.append(flat[offs[id(p)]:offs[id(p)] + p.numel()].view_as(p))
         base = flat.data_ptr()
         _fill_tensors(g, table, lambda p: base + 4 * offs[id(p)])
-        dl = dloss.detach().to(device=dev, dtype=torch.float32).contiguous()
-        _C.check(_C.lib().ndt1_engine_backward(self._engine, _C.C.byref(pstruct), _C.C.byref(g), dl.data_ptr(), _C.stream_ptr()),
-                 "ndt1_engine_backward")
+        if dfeatures is not None:
+            df = dfeatures.detach().to(device=dev, dtype=torch.float32).contiguous()
+            _C.check(_C.lib().ndt1_engine_backward_features(self._engine, _C.C.byref(pstruct), _C.C.byref(g), df.data_ptr(), _C.stream_ptr()),
+                     "ndt1_engine_backward_features")
+        else:
+            dl = dloss.detach().to(device=dev, dtype=torch.float32).contiguous()
+            _C.check(_C.lib().ndt1_engine_backward(self._engine, _C.C.byref(pstruct), _C.C.byref(g), dl.data_ptr(), _C.stream_ptr()),
+                     "ndt1_engine_backward")
         by_param = {id(p): v for (_, p), v in zip([(s, p) for s, p in table if p is not None], views)}
         return [by_param.get(id(p)) for p in self._autograd_params()]
 
@@ -595,12 +618,16 @@ class NDT1(nn.Module):
 
     # ------------------------------------------------------------------ public API
     def _encode(self, spikes, spikes_mask, spikes_timestamp, spikes_lengths=None, block_idx=None, day_idx=None):
-        """NeuralEncoder.forward (models/ndt1.py:408-450): (features, stacked mask, targets_mask).  Features are
-        returned detached (training through the encoder-only sub-API is not implemented in this build)."""
+        """NeuralEncoder.forward (models/ndt1.py:408-450): (features, stacked mask, targets_mask).  With gradients enabled
+        the features carry an autograd node, so a model stacked on the encoder (models/bci.py:125) trains through it."""
         x, targets_mask = self.encoder.prologue(spikes, want_mask=True)
-        out = self._engine_forward(dict(spikes=x, spikes_mask=spikes_mask, spikes_timestamp=spikes_timestamp,
-                                        spikes_lengths=spikes_lengths, block_idx=block_idx, day_idx=day_idx, encoder_only=True),
-                                   need_backward=False)
+        call = dict(spikes=x, spikes_mask=spikes_mask, spikes_timestamp=spikes_timestamp, spikes_lengths=spikes_lengths,
+                    block_idx=block_idx, day_idx=day_idx, encoder_only=True)
+        params = [p for p in self._autograd_params() if not any(p is q for q in self.decoder.parameters())]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            feats, out_mask = _EncoderFunction.apply(self, call, *self._autograd_params())
+            return feats, out_mask, targets_mask
+        out = self._engine_forward(call, need_backward=False)
         return out["features"], out["out_mask"], targets_mask
 
     def forward(

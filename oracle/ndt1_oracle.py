@@ -145,6 +145,28 @@ def format_ctc(pred_ids: Sequence[int], blank_id: int) -> List[int]:
     return out
 
 
+def edit_distance(source: Sequence, target: Sequence) -> int:
+    """editdistance.eval (third-party `editdistance`, unpinned in the reference; utils/eval_bci.py:11-14 calls it on word
+    lists): the classic Levenshtein distance, unit costs for insert / delete / substitute."""
+    prev = list(range(len(target) + 1))
+    for i, a in enumerate(source, 1):
+        cur = [i]
+        for j, b in enumerate(target, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (a != b)))
+        prev = cur
+    return prev[-1]
+
+
+def word_error_count(preds: Sequence[str], targets: Sequence[str]):
+    """utils/eval_bci.py:19-36: summed word edit distance and summed target word count of space-joined strings."""
+    errors = words = 0
+    for p, t in zip(preds, targets):
+        ps, ts = p.split(" "), t.split(" ")
+        errors += edit_distance(ps, ts)
+        words += len(ts)
+    return errors, words
+
+
 def padded_array(arrays, dim=0, side="right", value=0, truncate=None, min_length=None) -> np.ndarray:
     """data_utils/datasets.py:191-221."""
     max_size = max(a.shape[dim] for a in arrays)

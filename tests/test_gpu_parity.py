@@ -156,6 +156,34 @@ def test_greedy_decode_matches_format_ctc():
         assert (ids[b, int(lens[b]):] == -1).all()
 
 
+def test_device_cer_matches_word_error_count():
+    """Greedy decode + edit distance on the device = the `cer` metric of main.py:67-73 (format_ctc + word_error_count)."""
+    torch.manual_seed(11)
+    B, L, V, S = 9, 120, 41, 70
+    lp = torch.log_softmax(torch.randn(B, L, V) * 4, -1)
+    lp[1, :, 0] += 20                                   # trial 1 decodes to nothing
+    tl = torch.tensor([70, 12, 0, 33, 1, 64, 5, 40, 2])
+    tg = torch.randint(1, V, (B, S)) * (torch.arange(S)[None] < tl[:, None])
+    lp[3] = -20.0                                       # trial 3 decodes exactly to its target (each label held for 2 frames, blanks after)
+    for j in range(33):
+        lp[3, 2 * j:2 * j + 2, tg[3, j]] = 0.0
+        if j and tg[3, j] == tg[3, j - 1]:
+            tg[3, j] = tg[3, j] % 40 + 1                # (no repeats: the reference's collapse would merge them)
+            lp[3, 2 * j:2 * j + 2, :] = -20.0
+            lp[3, 2 * j:2 * j + 2, tg[3, j]] = 0.0
+    lp[3, 66:, 0] = 0.0
+    errors, words = lb.ctc_error_counts(lp.to(DEV), tg.to(DEV), tl.to(DEV), 0)
+    vocab = [f"p{i}" for i in range(V)]
+    preds = [" ".join(vocab[i] for i in O.format_ctc(lp[b].argmax(-1).tolist(), 0)) for b in range(B)]
+    tgts = [" ".join(vocab[i] for i in tg[b, :int(tl[b])].tolist()) for b in range(B)]
+    for b in range(B):
+        e, w = O.word_error_count([preds[b]], [tgts[b]])
+        assert (int(errors[b]), int(words[b])) == (e, w), b
+    assert int(errors[3]) == 0 and int(errors[1]) == 12 and int(words[2]) == 1
+    e, w = O.word_error_count(preds, tgts)
+    assert abs(float(lb.phoneme_error_rate(lp.to(DEV), tg.to(DEV), tl.to(DEV), 0)) - e / w) < 1e-6
+
+
 # --------------------------------------------------------------------------- floating-point operators
 def test_smooth_noise_against_oracle():
     torch.manual_seed(0)
@@ -394,6 +422,29 @@ def test_factors_dropout_replays_through_the_oracle(active):
     ev = model(**cuda_batch(batch_cpu))
     ref_ev, _ = O.ndt1_loss_and_grads(params, cfg, CTC_KW, batch_cpu, training=False)
     assert abs(float(ev.loss) - float(ref_ev["loss"])) <= 1e-4 * abs(float(ref_ev["loss"]))
+
+
+@pytest.mark.parametrize("name", ["rope", "gelu_factors"])
+def test_training_through_the_encoder_sub_api(name):
+    """model.encoder(...) (models/bci.py:125) with a caller-side head on top: gradients of the encoder parameters through
+    ndt1_engine_backward_features against the oracle's autograd."""
+    g = load("ctc_variants.npz")
+    cfg, params, batch_cpu = variant_case(g, name)
+    model = build(cfg, CTC_KW, params, "fp32").train()
+    b = cuda_batch(batch_cpu)
+    feats, mask, _ = model.encoder(b["spikes"], b["spikes_mask"], b["spikes_timestamp"], b["spikes_lengths"])
+    assert feats.requires_grad
+    torch.manual_seed(0)
+    w = torch.randn(feats.shape[-1], 7)
+    (torch.tanh(feats @ w.to(DEV)) * mask[:, :, None]).sum().backward()
+    P = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    rf, rmask, _ = O.encoder_forward(P, cfg["encoder"], batch_cpu["spikes"], batch_cpu["spikes_mask"], batch_cpu["spikes_timestamp"], training=True)
+    assert (feats.detach().cpu() - rf.detach()).abs().max() <= 1e-4 * rf.detach().abs().max()
+    (torch.tanh(rf @ w) * rmask[:, :, None]).sum().backward()
+    ref = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape, np.float32)) for k, v in P.items() if k.startswith("encoder.")}
+    got = {k: v for k, v in grads_of(model).items() if k.startswith("encoder.")}
+    check_grads(got, ref, 1e-4)
+    assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for p in model.decoder.parameters())
 
 
 def test_encoder_features_bf16_with_factors():

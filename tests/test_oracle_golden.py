@@ -233,3 +233,13 @@ def test_ctc_variants_rope_adapt_gelu_factors(name):
     assert set(ref) == set(grads)
     for k, r in ref.items():
         assert np.abs(grads[k].numpy() - r).max() <= 5e-5 * max(np.abs(r).max(), 1e-3 * gscale), k
+
+
+def test_edit_distance_and_word_error_count_known_answers():
+    """Known answers of the Levenshtein distance (the reference's `editdistance` dependency is absent here; classic cases)."""
+    assert O.edit_distance("kitten", "sitting") == 3
+    assert O.edit_distance("flaw", "lawn") == 2
+    assert O.edit_distance([], [1, 2, 3]) == 3 and O.edit_distance([1, 2, 3], []) == 3 and O.edit_distance([], []) == 0
+    assert O.edit_distance([1, 2, 3, 4], [1, 3, 4, 5]) == 2
+    # utils/eval_bci.py:19-36 on space-joined phonemes; "" splits into one empty word
+    assert O.word_error_count(["AH B K", "", "T"], ["AH K", "S IY", ""]) == (1 + 2 + 1, 2 + 2 + 1)
