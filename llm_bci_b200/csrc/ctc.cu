@@ -34,6 +34,7 @@ struct CtcParams {
   const float* logp; const long long* targets; const long long* in_len; const long long* tgt_len;
   int B, L, V, S, blank, zero_infinity, lp_in_smem;
   float* alpha; float* beta; float* nll; float* dlogits; const float* dloss;
+  double* offs;              // [B][2][L] forward / backward row offsets + [B] log-likelihoods (in the recursion's log unit), for the posterior kernel
 };
 
 constexpr int kRenorm = 8;    // re-centre the alpha/beta rows every kRenorm frames
@@ -202,8 +203,6 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) 
   const float* lp = p.lp_in_smem ? lp_s : lp_g;
   float* alpha = p.alpha + (long long)b * p.L * LX;
   float* beta = p.beta + (long long)b * p.L * LX;
-  float* dl = p.dlogits ? p.dlogits + (long long)b * p.L * p.V : nullptr;
-
   constexpr float kUnit = log_unit<FAST>();
   if (p.lp_in_smem) {              // staged once, already in the recursion's log unit; 8 independent loads in flight per thread
     const int n = p.L * p.V;
@@ -219,22 +218,6 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) 
   for (int i = tid; i < LXA + 2; i += blockDim.x) lab[i] = (i < Lx && (i & 1)) ? (int)p.targets[(long long)b * p.S + (i >> 1)] : p.blank;
   if (tid < 2) fin[tid] = -INFINITY;
   __syncthreads();
-  // group the target positions by label (thread c owns label c; lists stay in target order -> deterministic sums)
-  if (tid < p.V) {
-    int n = 0;
-    for (int j = 0; j < S; ++j) n += (lab[2 * j + 1] == tid);
-    cstart[tid + 1] = n;
-  }
-  if (tid == 0) cstart[0] = 0;
-  __syncthreads();
-  if (tid == 0) for (int c = 0; c < p.V; ++c) cstart[c + 1] += cstart[c];
-  __syncthreads();
-  if (tid < p.V) {
-    int n = cstart[tid];
-    for (int j = 0; j < S; ++j) if (lab[2 * j + 1] == tid) cpos[n++] = j;
-  }
-  __syncthreads();
-
   double ll = -INFINITY;
   if (Tn > 0) {
     if (warp == 0) ctc_sweep<FAST, SPT, true>(p, lp, lps, lab, Lx, LX, Tn, alpha, Cs, fin);
@@ -251,36 +234,75 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) 
   }
   const bool feasible = (ll != -INFINITY) && (ll == ll);
   if (tid == 0) p.nll[b] = feasible ? (float)(-ll / (double)kUnit) : (p.zero_infinity ? 0.f : INFINITY);
-  if (!dl) return;
-  const float gs = p.dloss ? *p.dloss : 1.f;
-  const int t_zero_from = (feasible && Tn > 0) ? Tn : 0;
-  for (long long e = (long long)t_zero_from * p.V + tid; e < (long long)p.L * p.V; e += blockDim.x) dl[e] = 0.f;
-  if (!feasible || Tn <= 0) return;
+  if (!p.dlogits) return;
+  // hand the row offsets and the log-likelihood to the posterior kernel (one CTA per trial cannot fill the GPU; that pass can)
+  double* og = p.offs + (long long)b * 2 * p.L;
+  for (int t = tid; t < Tn; t += blockDim.x) { og[t] = Cs[t]; og[p.L + t] = Ds[t]; }
+  if (tid == 0) p.offs[(long long)p.B * 2 * p.L + b] = feasible ? ll : -INFINITY;
+}
 
-  // posteriors: one warp per frame.  dlogits[t,c] = (softmax[t,c] - sum_{s: l'(s)=c} alpha beta / (p_t(c) P)) * dloss
+// Gradient pass: dlogits[t,c] = (softmax[t,c] - sum_{s: l'(s)=c} alpha beta / (p_t(c) P)) * dloss for t < len, 0 beyond (and
+// everywhere for an infeasible trial).  One warp per frame, kPostFrames frames per CTA, grid (frame chunks, trials): the
+// label posterior sums the states that carry the label; states are grouped by label once per CTA (a CSR index in shared
+// memory), so no atomics are involved and the sums are deterministic.
+constexpr int kPostFrames = 32;
+template <bool FAST, int SPT>
+__global__ void __launch_bounds__(kCtcWarps * 32) ctc_posterior_kernel(const CtcParams p) { pdl_grid_sync();
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int LX = 2 * p.S + 1, LXA = SPT * 32;
+  float* wbuf = (float*)sm_raw;                     // [warps][LXA] posterior weights of one frame
+  int* lab = (int*)(wbuf + kCtcWarps * LXA);        // [LXA + 2] extended labels
+  int* cstart = lab + LXA + 2;                      // [V + 1] states grouped by label: start offsets ...
+  int* cpos = cstart + p.V + 1;                     // [S]     ... and target positions
+  int S = (int)p.tgt_len[b];
+  S = S < 0 ? 0 : (S > p.S ? p.S : S);
+  const int Lx = 2 * S + 1;
+  const long long tn_ll = p.in_len[b];
+  const int Tn = tn_ll > p.L ? p.L : (tn_ll < 0 ? 0 : (int)tn_ll);
+  const float* lp = p.logp + (long long)b * p.L * p.V;
+  const float* alpha = p.alpha + (long long)b * p.L * LX;
+  const float* beta = p.beta + (long long)b * p.L * LX;
+  float* dl = p.dlogits + (long long)b * p.L * p.V;
+  const double* og = p.offs + (long long)b * 2 * p.L;
+  const double ll = p.offs[(long long)p.B * 2 * p.L + b];
+  const bool feasible = (ll != -INFINITY) && (ll == ll) && Tn > 0;
+  constexpr float kUnit = log_unit<FAST>();
+  const float gs = p.dloss ? *p.dloss : 1.f;
+  const int t_lo = blockIdx.x * kPostFrames, t_hi = min(p.L, t_lo + kPostFrames);
+  const int t_live = feasible ? Tn : 0;                 // frames [t_live, L) get a zero gradient
+  for (int e = max(t_lo, t_live) * p.V + tid; e < t_hi * p.V; e += blockDim.x) dl[e] = 0.f;
+  if (t_lo >= t_live) return;
+
+  for (int i = tid; i < LXA + 2; i += blockDim.x) lab[i] = (i < Lx && (i & 1)) ? (int)p.targets[(long long)b * p.S + (i >> 1)] : p.blank;
+  __syncthreads();
+  if (tid < p.V) {
+    int n = 0;
+    for (int j = 0; j < S; ++j) n += (lab[2 * j + 1] == tid);
+    cstart[tid + 1] = n;
+  }
+  if (tid == 0) cstart[0] = 0;
+  __syncthreads();
+  if (tid == 0) for (int c = 0; c < p.V; ++c) cstart[c + 1] += cstart[c];
+  __syncthreads();
+  if (tid < p.V) {
+    int n = cstart[tid];
+    for (int j = 0; j < S; ++j) if (lab[2 * j + 1] == tid) cpos[n++] = j;
+  }
+  __syncthreads();
+
   float* wb = wbuf + warp * LXA;
-  float al[SPT], be[SPT], al_n[SPT], be_n[SPT];
-  auto fetch = [&](int t, float* a_, float* b_) {
-#pragma unroll
-    for (int i = 0; i < SPT; ++i) {
-      const int s2 = lane + 32 * i;
-      const bool in = t < Tn && s2 < Lx;
-      a_[i] = in ? alpha[(long long)t * LX + s2] : -INFINITY;
-      b_[i] = in ? beta[(long long)t * LX + s2] : -INFINITY;
-    }
-  };
-  fetch(warp, al_n, be_n);
-  for (int t = warp; t < Tn; t += kCtcWarps) {
-#pragma unroll
-    for (int i = 0; i < SPT; ++i) { al[i] = al_n[i]; be[i] = be_n[i]; }
-    fetch(t + kCtcWarps, al_n, be_n);           // the next frame's rows fly while this frame is reduced
-    const float kt = (float)(Cs[t] + Ds[t] - ll);
+  for (int t = t_lo + warp; t < min(t_hi, t_live); t += kCtcWarps) {
+    const float kt = (float)(og[t] + og[p.L + t] - ll);
     float blank_acc = 0.f;
 #pragma unroll
     for (int i = 0; i < SPT; ++i) {
       const int s2 = lane + 32 * i;
       float w = 0.f;
-      if (al[i] != -INFINITY && be[i] != -INFINITY) w = exp_t<FAST>(al[i] + be[i] - lp[t * p.V + lab[s2]] * lps + kt);
+      if (s2 < Lx) {
+        const float al = alpha[(long long)t * LX + s2], be = beta[(long long)t * LX + s2];
+        if (al != -INFINITY && be != -INFINITY) w = exp_t<FAST>(al + be - lp[t * p.V + lab[s2]] * kUnit + kt);
+      }
       wb[s2] = w;
       if (!(s2 & 1)) blank_acc += w;
     }
@@ -289,7 +311,7 @@ __global__ void __launch_bounds__(kCtcWarps * 32) ctc_kernel(const CtcParams p) 
     for (int c = lane; c < p.V; c += 32) {
       float acc = (c == p.blank) ? blank_acc : 0.f;
       for (int k = cstart[c]; k < cstart[c + 1]; ++k) acc += wb[2 * cpos[k] + 1];
-      dl[(long long)t * p.V + c] = (exp_t<FAST>(lp[t * p.V + c] * lps) - acc) * gs;
+      dl[(long long)t * p.V + c] = (exp_t<FAST>(lp[t * p.V + c] * kUnit) - acc) * gs;
     }
     __syncwarp();
   }
@@ -369,7 +391,8 @@ int k_log_softmax(const float* logits, float* logp, long long rows, int V, cudaS
   return 0;
 }
 
-size_t k_ctc_workspace_floats(int B, int L, int S) { return 2 * (size_t)B * L * (2 * S + 1) + B; }
+// alpha and beta rows + (8-byte aligned) the row offsets and log-likelihoods the sweep kernel hands to the posterior kernel
+size_t k_ctc_workspace_floats(int B, int L, int S) { return 2 * (size_t)B * L * (2 * S + 1) + 2 + 2 * ((size_t)B * 2 * L + B); }
 
 template <bool FAST, int SPT>
 static int ctc_launch(const CtcParams& p, size_t smem, cudaStream_t stream) {
@@ -380,6 +403,12 @@ static int ctc_launch(const CtcParams& p, size_t smem, cudaStream_t stream) {
   }
   ndt1_launch(ctc_kernel<FAST, SPT>, p.B, kCtcWarps * 32, smem, stream, p);
   NDT1_CHECK_LAUNCH();
+  if (p.dlogits) {
+    const int LXA = SPT * 32;
+    const size_t smem2 = (size_t)(kCtcWarps * LXA + (LXA + 2) + (p.V + 1) + (p.S > 0 ? p.S : 1)) * sizeof(float);
+    ndt1_launch(ctc_posterior_kernel<FAST, SPT>, dim3(ndt1_cdiv(p.L, kPostFrames), p.B), kCtcWarps * 32, smem2, stream, p);
+    NDT1_CHECK_LAUNCH();
+  }
   return 0;
 }
 template <bool FAST>
@@ -410,7 +439,8 @@ int k_ctc_fwd_bwd(const float* logp, const long long* targets, const long long* 
   const size_t smem = lp_in_smem ? with_lp : base;
   NDT1_REQUIRE(smem <= 200 * 1024, "ctc: %d frames x %d labels do not fit one CTA", L, S);
   float* beta_ws = alpha_ws + (size_t)B * L * LX;
-  CtcParams p{logp, targets, in_len, tgt_len, B, L, V, S, blank, zero_infinity, lp_in_smem, alpha_ws, beta_ws, nll, dlogits, dloss};
+  double* offs = (double*)(((uintptr_t)(beta_ws + (size_t)B * L * LX) + 7) & ~(uintptr_t)7);
+  CtcParams p{logp, targets, in_len, tgt_len, B, L, V, S, blank, zero_infinity, lp_in_smem, alpha_ws, beta_ws, nll, dlogits, dloss, offs};
   if (fast_math) NDT1_TRY(ctc_dispatch<true>(p, spt, smem, stream));
   else NDT1_TRY(ctc_dispatch<false>(p, spt, smem, stream));
   if (loss) {
