@@ -61,18 +61,33 @@ def onecycle_cos_lr(step: int, total_steps: int, max_lr: float, pct_start: float
     return cos(max_lr, min_lr, (step - up_end) / (down_end - up_end))
 
 
+def linear_warmup_lr(step: int, total_steps: int, lr: float, warmup_pct: float) -> float:
+    """transformers.get_linear_schedule_with_warmup value at optimizer step ``step`` (trainer.py:233-238): linear ramp over
+    round(warmup_pct * total_steps) steps, then linear decay to 0 at total_steps."""
+    warmup = round(warmup_pct * total_steps)
+    if step < warmup:
+        return lr * float(step) / float(max(1, warmup))
+    return lr * max(0.0, float(total_steps - step) / float(max(1, total_steps - warmup)))
+
+
 class DataParallelTrainer:
     """Owns the flat parameter / gradient / AdamW-state buffers of one rank."""
 
     def __init__(self, model: NDT1, lr: float = 1e-3, wd: float = 5e-5, eps: float = 1e-8, betas=(0.9, 0.999),
                  scheduler: Optional[str] = None, total_steps: int = 1, warmup_pct: float = 0.0, div_factor: float = 25.0,
-                 gamma: float = 0.95, process_group=None, bucket_layers: int = 1):
+                 gamma: float = 0.95, process_group=None, bucket_layers: int = 1,
+                 gradient_accumulation_steps: int = 1, loss_scale: Optional[float] = None):
         self.model = model
         self.lr, self.wd, self.eps, self.betas = lr, wd, eps, betas
         self.scheduler, self.total_steps, self.warmup_pct, self.div_factor, self.gamma = scheduler, total_steps, warmup_pct, div_factor, gamma
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.step_count = 0
+        # gradient accumulation as the reference runs it (models/trainer.py:333-349): the loss is scaled by 1 / steps, the optimizer
+        # steps on micro-batch 1, 1 + steps, ... and the micro-batches in between only accumulate (no_sync: no all-reduce)
+        self.accum = max(1, int(gradient_accumulation_steps))
+        self.global_step = 1
+        self._loss_scale = float(loss_scale) if loss_scale is not None else 1.0 / self.accum
         self.bucket_layers = max(1, bucket_layers)
         offs, total = model._grad_offsets()
         table, _ = model._params()
@@ -109,14 +124,14 @@ class DataParallelTrainer:
             model.set_weight_shadow(self.flat_param, self.shadow)
         self.buckets = [(st, spans[st][0], spans[st][1]) for st in sorted(spans)]   # completion order
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
-        self._ones = torch.ones((), dtype=torch.float32, device=dev)
+        self._ones = torch.full((), self._loss_scale, dtype=torch.float32, device=dev)     # d(loss) handed to the backward
 
     # ------------------------------------------------------------------
     def current_lr(self) -> float:
         if self.scheduler == "cosine":
             return onecycle_cos_lr(self.step_count, self.total_steps, self.lr, self.warmup_pct, self.div_factor)
         if self.scheduler == "linear":
-            return onecycle_cos_lr(self.step_count, self.total_steps, self.lr, self.warmup_pct, self.div_factor)
+            return linear_warmup_lr(self.step_count, self.total_steps, self.lr, self.warmup_pct)
         if self.scheduler == "step":
             return self.lr * (self.gamma ** self.step_count)
         return self.lr
@@ -147,7 +162,11 @@ class DataParallelTrainer:
         longer read once its gradients are complete."""
         m = self.model
         m.train()
+        sync = (self.global_step - 1) % self.accum == 0
+        self.global_step += 1
         out = m.forward_backward(batch, self.flat_grad, self._ones)
+        if not sync:                      # accumulation micro-step: gradients stay in the arena, nothing is exchanged
+            return out
         if self.comm_stream is None:
             self.all_reduce_gradients()
             self.optimizer_step()

@@ -156,6 +156,35 @@ def test_greedy_decode_matches_format_ctc():
         assert (ids[b, int(lens[b]):] == -1).all()
 
 
+def test_trainer_gradient_accumulation_follows_the_reference_loop():
+    """models/trainer.py:333-349: loss / steps, optimizer step on micro-batches 1, 1 + steps, ...; the ones in between only accumulate."""
+    g = load("ctc_small.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g, "param").items()}
+    mb = [cuda_batch(O.synthetic_ctc_batch(B=2, T=120, N=16, seed=s)) for s in (1, 2, 3)]
+    S = max(int(b["targets"].shape[1]) for b in mb)
+    for b in mb:
+        b["targets"] = torch.nn.functional.pad(b["targets"], (0, S - b["targets"].shape[1]))
+    m1, m2 = build(small_ctc_cfg(), CTC_KW, params, "fp32"), build(small_ctc_cfg(), CTC_KW, params, "fp32")
+    # (eps = 1e-3: with the default 1e-8 an analytically zero gradient -- attn.key.bias -- moves by +-lr on rounding noise alone)
+    t1 = lb.DataParallelTrainer(m1, lr=1e-3, eps=1e-3, gradient_accumulation_steps=2)
+    t2 = lb.DataParallelTrainer(m2, lr=1e-3, eps=1e-3, gradient_accumulation_steps=1, loss_scale=0.5)
+    t1.train_step(mb[0]); t2.train_step(mb[0])
+    torch.cuda.synchronize()
+    # (not bit-equal: split-K weight gradients are summed with atomics, so the last bits depend on arrival order)
+    assert float((t1.flat_param - t2.flat_param).abs().max()) <= 1e-5 * float(t2.flat_param.abs().max()) and float(t1.flat_grad.abs().max()) == 0.0
+    before = t1.flat_param.clone()
+    t1.train_step(mb[1])                                        # accumulates only
+    torch.cuda.synchronize()
+    assert torch.equal(t1.flat_param, before) and float(t1.flat_grad.abs().max()) > 0.0 and t1.step_count == 1
+    t1.train_step(mb[2])                                        # steps on grad(mb2) + grad(mb3), each scaled by 1/2
+    both = {k: torch.cat([mb[1][k], mb[2][k]]) for k in mb[1]}
+    t2.train_step(both)                                         # the loss is a sum over trials: same gradient in one batch
+    torch.cuda.synchronize()
+    assert t1.step_count == 2 and float(t1.flat_grad.abs().max()) == 0.0
+    err = (t1.flat_param - t2.flat_param).abs().max() / t2.flat_param.abs().max()
+    assert float(err) < 1e-5, float(err)
+
+
 def test_device_cer_matches_word_error_count():
     """Greedy decode + edit distance on the device = the `cer` metric of main.py:67-73 (format_ctc + word_error_count)."""
     torch.manual_seed(11)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import llm_bci_b200 as lb  # noqa: E402
 from llm_bci_b200 import _C  # noqa: E402
-from llm_bci_b200.trainer import onecycle_cos_lr, shard_batch, get_model_inputs  # noqa: E402
+from llm_bci_b200.trainer import onecycle_cos_lr, linear_warmup_lr, shard_batch, get_model_inputs  # noqa: E402
 
 G = os.path.join(ROOT, "tests", "golden")
 
@@ -197,3 +197,14 @@ def test_data_parallel_semantics_gloo_world2():
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert err < 1e-5
+
+
+def test_linear_schedule_matches_transformers():
+    """optimizer.scheduler == "linear" (models/trainer.py:233-238)."""
+    from transformers import get_linear_schedule_with_warmup
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=2e-3)
+    sch = get_linear_schedule_with_warmup(opt, num_warmup_steps=round(0.15 * 40), num_training_steps=40)
+    for step in range(40):
+        assert abs(opt.param_groups[0]["lr"] - linear_warmup_lr(step, 40, 2e-3, 0.15)) < 1e-12, step
+        opt.step(); sch.step()
