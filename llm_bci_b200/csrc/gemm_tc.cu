@@ -162,9 +162,21 @@ __device__ __forceinline__ void side_load(const GemmEpilogue& e, const EpiCtx& c
   }
 }
 
+// the 4 bias values of this lane's columns: issued with the chunk's TMEM load (a dependent global load at the head of every
+// chunk's arithmetic costs an L2 round trip per chunk: 1.5 us of a 4.5 us tile epilogue)
+__device__ __forceinline__ float4 bias_load(const GemmEpilogue& e, const EpiCtx& cx, const TcParams& p, const ChunkAt& at) {
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!e.bias || !cx.vec_ok || !at.live || at.n >= p.N) return b;
+  if (at.n + 4 <= p.N) return __ldg((const float4*)(e.bias + at.bias_off + at.n));
+  b.x = __ldg(e.bias + at.bias_off + at.n);
+  if (at.n + 1 < p.N) b.y = __ldg(e.bias + at.bias_off + at.n + 1);
+  if (at.n + 2 < p.N) b.z = __ldg(e.bias + at.bias_off + at.n + 2);
+  return b;
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiCtx& cx, const TcParams& p, const ChunkAt& at, int lane,
-                                               const float4* acc, const float4* side, const uint8_t* stg) {
+                                               const float4* acc, const float4* side, const uint8_t* stg, const float4 bias4) {
   if (!at.live) return;
   if (ef_has(EPI, EF_SCALAR) && !cx.vec_ok) {        // ragged shapes (the 41-column head): element-wise, still row-contiguous across lanes
 #pragma unroll 1           // ONE copy of the scalar epilogue (it carries every feature): code size, not speed, matters here
@@ -179,15 +191,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
   }
   const bool col_ok = at.n < p.N;      // a last, partial group of 4 columns is stored whole: the row stride is padded (ldc % 4 == 0)
   float4 v[8];                         // and its accumulators beyond N are zero (out-of-range operand rows read as zero)
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (e.bias && col_ok) {
-    if (at.n + 4 <= p.N) bias4 = __ldg((const float4*)(e.bias + at.bias_off + at.n));
-    else {
-      bias4.x = __ldg(e.bias + at.bias_off + at.n);
-      if (at.n + 1 < p.N) bias4.y = __ldg(e.bias + at.bias_off + at.n + 1);
-      if (at.n + 2 < p.N) bias4.z = __ldg(e.bias + at.bias_off + at.n + 2);
-    }
-  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     v[i].x = fmaf(acc[i].x, e.alpha, bias4.x); v[i].y = fmaf(acc[i].y, e.alpha, bias4.y);
@@ -610,6 +613,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const ChunkAt at = chunk_of(t_cur, c);
         uint32_t raw[32];
         tmem_ld32(taddr_row + c * 32, raw);
+        const float4 bias_cur = bias_load(e, cx, p, at);     // flies under the TMEM load and the transpose (not at the head of the arithmetic)
         // side input of the next chunk (or of the next tile's first chunk) while the TMEM load is in flight
         const ChunkAt nx = (c + 1 < NCH) ? chunk_of(t_cur, c + 1) : t_nxt;
         side_load<EPI>(e, cx, p, nx, lane, side_nxt);
@@ -638,7 +642,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[i].x), "=f"(acc[i].y), "=f"(acc[i].z), "=f"(acc[i].w) : "r"(a) : "memory");
         }
         __syncwarp();
-        epilogue_chunk<EPI>(e, cx, p, at, lane, acc, side_cur, stg);
+        epilogue_chunk<EPI>(e, cx, p, at, lane, acc, side_cur, stg, bias_cur);
 #pragma unroll
         for (int i = 0; i < 8; ++i) side_cur[i] = side_nxt[i];
       }
@@ -870,7 +874,8 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
     // every split adds a full fp32 red.add pass over the output, which is what the constant term charges
     const int tiles = tp.m_tiles * tp.n_tiles, kblocks = tp.nchunk * tp.kb_per_chunk;
     int best = 1; long long best_cost = -1;
-    for (int sp = 1; sp <= 64 && (sp == 1 || sp * 4 <= kblocks); ++sp) {
+    static const int max_split = getenv("NDT1_WGRAD_MAX_SPLIT") ? atoi(getenv("NDT1_WGRAD_MAX_SPLIT")) : 64;   // experiments only
+    for (int sp = 1; sp <= max_split && sp <= 64 && (sp == 1 || sp * 4 <= kblocks); ++sp) {
       const long long waves = ((long long)tiles * sp + units - 1) / units;
       const long long cost = waves * (ndt1_cdiv(kblocks, sp) + 10);     // k-blocks per work item + ~10 k-blocks worth of fill / red.add epilogue
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
