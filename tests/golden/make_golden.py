@@ -278,6 +278,8 @@ VARIANTS = {
     "gelu_factors": ({"encoder": {"embedder": {"act": "gelu"},
                                   "factors": {"active": True, "size": 48, "act": "relu", "bias": True, "dropout": 0.0,
                                               "fixup_init": True, "init_range": 0.1}}}, False),
+    "tokens_ctx": ({"encoder": {"embedder": {"block_token": True, "day_token": True, "n_blocks": 5, "n_days": 4},
+                                "context": {"forward": 3, "backward": 7}}}, "both"),
     "rope_adapt_gelu_factors": ({"encoder": {"transformer": {"use_rope": True, "rope_theta": 500.0},
                                              "embedder": {"adapt": True, "n_days": 3, "act": "gelu", "pos": False},
                                              "factors": {"active": True, "size": 40, "act": "gelu", "bias": False, "dropout": 0.0,
@@ -301,6 +303,9 @@ def variant_cases(R):
         if days:
             b["day_idx"] = torch.tensor([2, 0, 2])
             d[f"{name}/day_idx"] = b["day_idx"].numpy()
+        if days == "both":
+            b["block_idx"] = torch.tensor([4, 1, 0])
+            d[f"{name}/block_idx"] = b["block_idx"].numpy()
         out, grads = run_ref(model, b, train=True)
         d.update(flat(f"{name}/param", dict(model.state_dict())))
         d.update(flat(f"{name}/grad", grads))
@@ -308,6 +313,35 @@ def variant_cases(R):
         d[f"{name}/out/preds"] = out.preds.detach().numpy()
         print("variant", name, "loss", float(out.loss))
     np.savez_compressed(os.path.join(HERE, "ctc_variants.npz"), **d)
+
+    # autoregressive next-bin prediction (models/ndt1.py:563-578) with the MSE loss and ReLU rates (:508-515)
+    ar_over = {"encoder": {
+        "embedder": {"n_channels": 24, "input_dim": 16, "max_F": 64, "dropout": 0.0, "stack": {"active": False}},
+        "transformer": {"n_layers": 2, "hidden_size": 64, "n_heads": 4, "inter_size": 64, "dropout": 0.0},
+        "smooth_and_noise": {"noise": False},
+        "context": {"forward": 0, "backward": -2},
+    }}
+    cfg_a = update_config("configs/ndt1.yaml", ar_over)
+    g = torch.Generator().manual_seed(19)
+    B, T, N = 4, 40, 24
+    sp = torch.poisson(torch.full((B, T, N), 0.6), generator=g)
+    lens = torch.tensor([40, 31, 40, 22])
+    msk = (torch.arange(T)[None] < lens[:, None]).to(torch.int64)
+    sp = sp * msk[:, :, None]
+    abatch = dict(spikes=sp, spikes_mask=msk, spikes_timestamp=torch.arange(T)[None].expand(B, T) * msk, spikes_lengths=lens)
+    d = flat("batch", abatch)
+    for name, kw in (("mse", dict(loss="mse", log_input=False)), ("poisson_rate", dict(loss="poisson_nll", log_input=False)),
+                     ("poisson_log", dict(loss="poisson_nll", log_input=True))):
+        torch.manual_seed(31)
+        model = NDT1(update_config("configs/ndt1.yaml", ar_over), method_name="autoregressive", **kw)
+        out, grads = run_ref(model, abatch, train=True)
+        d.update(flat(f"{name}/param", dict(model.state_dict())))
+        d.update(flat(f"{name}/grad", grads))
+        d[f"{name}/out/loss"] = out.loss.detach().numpy()
+        d[f"{name}/out/preds"] = out.preds.detach().numpy()
+        d[f"{name}/out/n_examples"] = out.n_examples.numpy()
+        print("autoregressive", name, "loss", float(out.loss), "n", int(out.n_examples))
+    np.savez_compressed(os.path.join(HERE, "autoregressive_small.npz"), **d)
 
 
 def full_case(R):

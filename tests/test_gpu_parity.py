@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 import llm_bci_b200 as lb  # noqa: E402
 from llm_bci_b200 import _C  # noqa: E402
 from oracle import ndt1_oracle as O  # noqa: E402
-from test_oracle_golden import load, sub, small_ctc_cfg, mlm_cfg, CTC_KW, VARIANTS, variant_case  # noqa: E402
+from test_oracle_golden import load, sub, small_ctc_cfg, mlm_cfg, CTC_KW, VARIANTS, variant_case, AR_KW, autoregressive_cfg  # noqa: E402
 
 DEV = "cuda"
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
@@ -399,6 +399,26 @@ def test_ctc_variants_match_reference(name, precision):
         # (NDT1_FORCE_SIMT=1), so it is the storage format, not the tensor-core kernels.  The same model with smooth
         # activations (rope_adapt_gelu_factors) meets 2e-2.
         gtol = 1e-1
+    check_grads(grads_of(model), sub(g, f"{name}/grad"), gtol)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(AR_KW))
+def test_autoregressive_matches_reference(name, precision):
+    """method_name = autoregressive (models/ndt1.py:563-578) with the MSE, Poisson-rate (ReLU head) and Poisson-log losses."""
+    g = load("autoregressive_small.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g, f"{name}/param").items()}
+    batch = cuda_batch({k: torch.from_numpy(v) for k, v in sub(g, "batch").items()})
+    model = build(autoregressive_cfg(), dict(method_name="autoregressive", **AR_KW[name]), params, precision).train()
+    out = model(**batch)
+    out.loss.backward()
+    tol = TOL[precision]
+    ref_loss = float(g[f"{name}/out/loss"])
+    assert abs(float(out.loss) - ref_loss) <= tol * abs(ref_loss)
+    assert int(out.n_examples) == int(g[f"{name}/out/n_examples"])
+    gtol = 5e-4 if name == "poisson_rate" else tol      # (1 - t / (rate + 1e-8) amplifies fp32 rounding where the ReLU rate is ~0)
+    if precision == "bf16" and name != "poisson_log":
+        gtol = 2.5e-1 if name == "poisson_rate" else 1e-1          # ReLU head (and, for the Poisson rate, its 1 / rate gradient on top): units whose pre-activation is below the bf16 rounding error flip their 0/1 derivative (see test_ctc_variants_match_reference)
     check_grads(grads_of(model), sub(g, f"{name}/grad"), gtol)
 
 

@@ -203,6 +203,8 @@ VARIANTS = {
     "gelu_factors": {"encoder": {"embedder": {"act": "gelu"},
                                  "factors": {"active": True, "size": 48, "act": "relu", "bias": True, "dropout": 0.0,
                                              "fixup_init": True, "init_range": 0.1}}},
+    "tokens_ctx": {"encoder": {"embedder": {"block_token": True, "day_token": True, "n_blocks": 5, "n_days": 4},
+                               "context": {"forward": 3, "backward": 7}}},
     "rope_adapt_gelu_factors": {"encoder": {"transformer": {"use_rope": True, "rope_theta": 500.0},
                                             "embedder": {"adapt": True, "n_days": 3, "act": "gelu", "pos": False},
                                             "factors": {"active": True, "size": 40, "act": "gelu", "bias": False, "dropout": 0.0,
@@ -215,14 +217,16 @@ def variant_case(g, name):
     cfg = update_config(small_ctc_cfg(), VARIANTS[name])
     params = {k: torch.from_numpy(v) for k, v in sub(g, f"{name}/param").items()}
     batch = {k: torch.from_numpy(v) for k, v in sub(g, "batch").items()}
-    if f"{name}/day_idx" in g:
-        batch["day_idx"] = torch.from_numpy(g[f"{name}/day_idx"])
+    for k in ("day_idx", "block_idx"):
+        if f"{name}/{k}" in g:
+            batch[k] = torch.from_numpy(g[f"{name}/{k}"])
     return cfg, params, batch
 
 
 @pytest.mark.parametrize("name", list(VARIANTS))
 def test_ctc_variants_rope_adapt_gelu_factors(name):
-    """Options the shipped yaml leaves off: per-day embedding, RoPE, GELU embedder activation, factors projection."""
+    """Options the shipped yaml leaves off: per-day embedding, RoPE, GELU embedder activation, factors projection,
+    block / day tokens with a bounded context window."""
     g = load("ctc_variants.npz")
     cfg, params, batch = variant_case(g, name)
     out, grads = O.ndt1_loss_and_grads(params, cfg, CTC_KW, batch, training=True)
@@ -243,3 +247,35 @@ def test_edit_distance_and_word_error_count_known_answers():
     assert O.edit_distance([1, 2, 3, 4], [1, 3, 4, 5]) == 2
     # utils/eval_bci.py:19-36 on space-joined phonemes; "" splits into one empty word
     assert O.word_error_count(["AH B K", "", "T"], ["AH K", "S IY", ""]) == (1 + 2 + 1, 2 + 2 + 1)
+
+
+AR_KW = {"mse": dict(loss="mse", log_input=False), "poisson_rate": dict(loss="poisson_nll", log_input=False),
+         "poisson_log": dict(loss="poisson_nll", log_input=True)}
+
+
+def autoregressive_cfg():
+    return update_config(default_model_config(), {"encoder": {
+        "embedder": {"n_channels": 24, "input_dim": 16, "max_F": 64, "dropout": 0.0, "stack": {"active": False}},
+        "transformer": {"n_layers": 2, "hidden_size": 64, "n_heads": 4, "inter_size": 64, "dropout": 0.0},
+        "smooth_and_noise": {"noise": False},
+        "context": {"forward": 0, "backward": -2}}})
+
+
+@pytest.mark.parametrize("name", list(AR_KW))
+def test_autoregressive_losses(name):
+    """Next-bin prediction (models/ndt1.py:563-578) with MSE / Poisson-rate (ReLU head) / Poisson-log losses (:508-515)."""
+    g = load("autoregressive_small.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g, f"{name}/param").items()}
+    batch = {k: torch.from_numpy(v) for k, v in sub(g, "batch").items()}
+    kw = dict(method_name="autoregressive", **AR_KW[name])
+    out, grads = O.ndt1_loss_and_grads(params, autoregressive_cfg(), kw, batch, training=True)
+    assert abs(float(out["loss"]) - float(g[f"{name}/out/loss"])) <= 2e-5 * abs(float(g[f"{name}/out/loss"]))
+    assert int(out["n_examples"]) == int(g[f"{name}/out/n_examples"])
+    assert rel(out["preds"].detach().numpy(), g[f"{name}/out/preds"]) < 2e-5
+    ref = sub(g, f"{name}/grad")
+    gscale = max(np.abs(v).max() for v in ref.values())
+    # Poisson-NLL on ReLU rates has d/dx = 1 - t / (x + 1e-8): rates at or near zero amplify fp32 rounding (the reference's own
+    # run-to-run noise there is of the same size), hence the looser bound for that case
+    gtol = 3e-4 if name == "poisson_rate" else 5e-5
+    for k, r in ref.items():
+        assert np.abs(grads[k].numpy() - r).max() <= gtol * max(np.abs(r).max(), 1e-3 * gscale), k
