@@ -4,6 +4,7 @@
 //   ./gemm_selftest [quick]
 #include "../gemm_common.cuh"
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 #include <math.h>
 
@@ -72,6 +73,32 @@ static void run_case(const char* name, GemmProblem p, size_t out_elems, double f
   printf("%-28s %s maxref=%.4g maxerr=%.3g (at %zu ref=%.5g got=%.5g)  %.1f us  %.1f TFLOP/s\n", name, ok ? "OK  " : "FAIL", maxref,
          maxerr, bad, hr[bad], ho[bad], ms * 1e3, flops / (ms * 1e-3) / 1e12);
   if (!ok) g_fail++;
+  if (getenv("GEMM_TL") && strstr(name, getenv("GEMM_TL"))) {      // per-CTA phase timeline of this case (see tools/gemm_timeline.py)
+    unsigned long long* tl = nullptr;
+    CK(cudaMalloc(&tl, 148 * 16 * 8)); CK(cudaMemset(tl, 0, 148 * 16 * 8));
+    gemm_tc_set_timeline(tl);
+    gemm_tc_launch(pt, 0);
+    CK(cudaDeviceSynchronize());
+    gemm_tc_set_timeline(nullptr);
+    std::vector<unsigned long long> h(148 * 16);
+    CK(cudaMemcpy(h.data(), tl, h.size() * 8, cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < 148; ++c) if (h[c * 16] && h[c * 16] < t0) t0 = h[c * 16];
+    const char* names[16] = {"CTA start", "barriers + TMEM ready", "griddep wait passed", "first TMA issued", "all loads issued", "first operands landed",
+                             "last MMA issued", "first accumulator ready", "last accumulator ready", "epilogue warp 0/4 done", "epilogue warp 1/5 done",
+                             "epilogue warp 2/6 done", "epilogue warp 3/7 done", "", "TMEM freed (exit)", ""};
+    for (int k : {0, 1, 3, 5, 7, 4, 6, 8, 9, 12, 14}) {
+      double mn = 1e30, mx = 0, sum = 0; int n = 0;
+      for (int c = 0; c < 148; ++c) {
+        const unsigned long long v = h[c * 16 + k];
+        if (!v || !h[c * 16]) continue;
+        const double us = (double)(v - t0) / 1e3;
+        mn = fmin(mn, us); mx = fmax(mx, us); sum += us; ++n;
+      }
+      if (n) printf("    %-28s mean %6.2f  min %6.2f  max %6.2f  (n=%d)\n", names[k], sum / n, mn, mx, n);
+    }
+    CK(cudaFree(tl));
+  }
   CK(cudaFree(ref)); CK(cudaFree(out));
 }
 
