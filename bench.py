@@ -205,6 +205,7 @@ def run_ours(args):
             fn()
         if after is not None:
             after()                                          # e.g. read the last step's result on the host
+        trainer.synchronize()                                # the last step's optimizer tail (side stream) is inside the timed region
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)

@@ -420,6 +420,7 @@ class NDT1(nn.Module):
         self._last = None
         self._last_out = None
         self._weight_shadow = None
+        self._param_stream = None     # a side stream that may still be updating the parameters (DataParallelTrainer's optimizer)
 
     # ------------------------------------------------------------------ engine plumbing
     def _apply(self, fn, *a, **k):
@@ -513,8 +514,14 @@ class NDT1(nn.Module):
     def engine_arena_bytes(self) -> int:
         return int(_C.lib().ndt1_engine_arena_bytes(self._engine)) if self._engine is not None else 0
 
+    def wait_for_parameters(self) -> None:
+        """Order the current stream after a pending optimizer update on a side stream (see DataParallelTrainer.train_step)."""
+        if self._param_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._param_stream)
+
     def _engine_forward(self, call: dict, need_backward: bool) -> dict:
         L = _C.lib()
+        self.wait_for_parameters()     # (after the prologue: smoothing / noise / masking do not read a parameter)
         x = call["spikes"]
         B, T, N = x.shape
         dev = x.device
@@ -733,6 +740,7 @@ class NDT1(nn.Module):
 
     def save_checkpoint(self, save_dir):
         """models/ndt1.py:685-688: same three files, same keys."""
+        self.wait_for_parameters()
         torch.save(self.encoder.state_dict(), os.path.join(save_dir, "encoder.bin"))
         torch.save(self.config.encoder.get_dict(), os.path.join(save_dir, "encoder_config.pth"))
         torch.save(self.decoder.state_dict(), os.path.join(save_dir, "decoder.bin"))

@@ -124,6 +124,7 @@ class DataParallelTrainer:
             model.set_weight_shadow(self.flat_param, self.shadow)
         self.buckets = [(st, spans[st][0], spans[st][1]) for st in sorted(spans)]   # completion order
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        model._param_stream = self.comm_stream
         self._ones = torch.full((), self._loss_scale, dtype=torch.float32, device=dev)     # d(loss) handed to the backward
 
     # ------------------------------------------------------------------
@@ -147,8 +148,14 @@ class DataParallelTrainer:
                 dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
         torch.cuda.current_stream().wait_stream(self.comm_stream)
 
+    def synchronize(self) -> None:
+        """Make the current stream see every pending parameter update (before reading parameters outside the model)."""
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
     def refresh_shadow(self) -> None:
         """Call after changing parameters behind the trainer's back (e.g. load_checkpoint)."""
+        self.synchronize()
         if self.shadow is not None:
             self.shadow.copy_(self.flat_param)
 
@@ -180,7 +187,9 @@ class DataParallelTrainer:
                 if self.world > 1:
                     dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
                 self._adamw(lo, hi, lr, self.comm_stream.cuda_stream)
-        torch.cuda.current_stream().wait_stream(self.comm_stream)
+        # The caller's stream is NOT joined here: the last buckets' all-reduce and AdamW then run under the next step's
+        # prologue (smoothing / noise / input cast, which read no parameter); the model joins before its first
+        # parameter-dependent kernel (NDT1.wait_for_parameters, also called by save_checkpoint).
         return out
 
     def _adamw(self, lo: int, hi: int, lr: float, stream: int) -> None:
