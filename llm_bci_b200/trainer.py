@@ -150,7 +150,7 @@ class DataParallelTrainer:
 
     def synchronize(self) -> None:
         """Make the current stream see every pending parameter update (before reading parameters outside the model)."""
-        if self.comm_stream is not None:
+        if getattr(self, "comm_stream", None) is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def refresh_shadow(self) -> None:
