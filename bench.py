@@ -130,6 +130,10 @@ def cpu_train_steps(n_trials: int, steps: int, warmup: int):
     return n_trials / sec, sec, cores
 
 
+WORKLOAD = ("NDT1 CTC train step (fwd+bwd+AdamW), BASELINE configs[1]: 32 trials x 1000 bins x 256 channels per GPU, "
+            "5x1024 encoder, stack 32/4, 41 phonemes, dropout 0.4/0.2, noise on")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -140,8 +144,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "trials/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "NDT1 CTC train step (fwd+bwd+AdamW), 1000 bins x 256 channels, 5x1024 encoder, stack 32/4, 41 phonemes",
-                   "sample": f"{n} trials per step on the host CPU"},
+        "config": {"workload": WORKLOAD, "sample": f"{n} trials per step on the host CPU (a bounded sample of the same workload)"},
         "cpu_baseline": {"value": value, "unit": "trials/s", "cores": cores, "kind": "port",
                          "sample": f"{n} trials/step x {args.steps} steps, oracle port of the reference algorithm, torch CPU fp32"},
         "e2e": {"value": value, "unit": "trials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -309,8 +312,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "trials/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "NDT1 CTC train step (fwd+bwd+AdamW), BASELINE configs[1]: 32 trials x 1000 bins x 256 channels per GPU, "
-                                   "5x1024 encoder, stack 32/4, 41 phonemes, dropout 0.4/0.2, noise on",
+            "config": {"workload": WORKLOAD,
                        "global_batch": world * B, "bins_per_sec": value * T, "parallelism": f"dp{world}",
                        "l2": "per-step working set ~1.4 GB >> 126 MB L2; no flush needed", "loss": state["loss"]},
             "clocks": clocks,
