@@ -85,6 +85,8 @@ class SmoothAndNoise(nn.Module):
         if self.smooth:
             kernel = torch.from_numpy(gaussian_taps(config.smooth_sd))
             self.register_buffer("kernel", kernel, persistent=False)
+            self._taps_host = kernel.numpy().astype(np.float32).copy()    # host copy for the launch (the taps are a by-value kernel argument):
+                                                                          # reading the device buffer back every forward would synchronise the stream
 
     def forward(self, spikes: torch.Tensor, noise: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
         if not spikes.is_cuda:
@@ -95,7 +97,7 @@ class SmoothAndNoise(nn.Module):
         if not self.smooth and not add_noise:
             return spikes
         out = torch.empty_like(spikes)
-        taps = self.kernel.detach().cpu().numpy().astype(np.float32) if self.smooth else np.zeros(0, dtype=np.float32)
+        taps = self._taps_host if self.smooth else np.zeros(0, dtype=np.float32)
         taps_c = taps.ctypes.data_as(_C.C.POINTER(_C.C.c_float))
         white = offset = None
         wsd = osd = 0.0
