@@ -176,6 +176,9 @@ def run_ours(args):
     spikes = torch.randn(B, T, N, generator=g)
     lens = torch.randint(int(0.6 * T), T + 1, (B,), generator=g)
     lens[0] = T
+    if args.fixed_length:                      # the all-full-length variant (no padded rows)
+        lens[:] = T
+    valid_row_frac = float(((lens - 32) // 4 + 1).sum()) / float(B * ((T - 32) // 4 + 1))    # stacked rows that are not padding
     t = torch.arange(T)[None, :]
     mask = (t < lens[:, None]).to(torch.int64)
     spikes = spikes * mask[:, :, None]
@@ -314,6 +317,8 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "global_batch": world * B, "bins_per_sec": value * T, "parallelism": f"dp{world}",
+                       "lengths": "all 1000 bins" if args.fixed_length else "U{600..1000} bins, right-padded (padded rows are computed, as in the reference)",
+                       "valid_row_frac": valid_row_frac,
                        "l2": "per-step working set ~1.4 GB >> 126 MB L2; no flush needed", "loss": state["loss"]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "trials/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
@@ -333,6 +338,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fixed-length", action="store_true", help="every trial 1000 bins long (no padding)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
