@@ -208,3 +208,32 @@ def test_linear_schedule_matches_transformers():
     for step in range(40):
         assert abs(opt.param_groups[0]["lr"] - linear_warmup_lr(step, 40, 2e-3, 0.15)) < 1e-12, step
         opt.step(); sch.step()
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in llm_bci_b200/_C.py have the size and field offsets the C compiler gives include/ndt1_b200.h."""
+    import ctypes
+    import subprocess
+    from llm_bci_b200 import _C
+    probes = {
+        "ndt1_config": (_C.Config, ["abi_version", "rope_theta", "context_forward", "factors_active", "method", "p_embed", "max_targets"]),
+        "ndt1_tensors": (_C.Tensors, ["embed_w", "day_emb", "embed_w_day", "embed_b_day", "layer", "out_norm_w", "dec_b"]),
+        "ndt1_batch": (_C.Batch, ["spikes", "targets_mask", "B", "encoder_only", "seed"]),
+        "ndt1_outputs": (_C.Outputs, ["loss", "features"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "ndt1_b200.h")}"', "int main(void) {"]
+    for cname, (_, fields) in probes.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['  printf("abi %d layers %d days %d\\n", NDT1_ABI_VERSION, NDT1_MAX_LAYERS, NDT1_MAX_DAYS);', "  return 0;", "}"]
+    src = tmp_path / "abi_probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi_probe"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = dict(l.split(" ", 1) for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines())
+    for cname, (ctype, fields) in probes.items():
+        assert int(out[cname]) == ctypes.sizeof(ctype), cname
+        for f in fields:
+            assert int(out[f"{cname}.{f}"]) == getattr(ctype, f).offset, (cname, f)
+    assert out["abi"] == f"{_C.ABI_VERSION} layers {_C.MAX_LAYERS} days {_C.MAX_DAYS}"
