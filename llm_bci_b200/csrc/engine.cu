@@ -290,7 +290,14 @@ struct Engine : ndt1_engine {
     NDT1_REQUIRE(k.method != NDT1_METHOD_CTC || bt->S <= k.max_targets, "engine: %d targets exceed max_targets %d", bt->S, k.max_targets);
     B = bt->B; Tn = bt->T; Tp = out_len(Tn); L = n_prefix + Tp; S = bt->S; training = bt->training; seed = bt->seed;
     spikes_ptr = bt->spikes; ts_ptr = (const long long*)bt->spikes_timestamp; block_ptr = (const long long*)bt->block_idx; day_ptr = (const long long*)bt->day_idx;
-    if (B == 0) { have_fwd = true; return 0; }
+    if (B == 0) {
+      // an empty shard (global batch < world size): loss 0, no examples; the other outputs have no elements
+      NDT1_CUDA_CHECK(cudaMemsetAsync(o->loss, 0, sizeof(float), s));
+      if (o->n_examples) NDT1_CUDA_CHECK(cudaMemsetAsync(o->n_examples, 0, 8, s));
+      fwd_encoder_only = bt->encoder_only != 0;
+      have_fwd = bt->need_backward != 0;
+      return 0;
+    }
     const int H = k.hidden, I = k.inter, D = k.input_dim, N = k.n_channels, NL = k.n_layers, V = k.n_outputs;
     const int Hout = k.factors_active ? k.factors_size : H;
     const long long M = (long long)B * L, MT = (long long)B * Tn;
@@ -541,7 +548,10 @@ struct Engine : ndt1_engine {
     NDT1_REQUIRE(have_fwd, "engine: backward without a matching forward (need_backward = 1)");
     NDT1_REQUIRE(fwd_encoder_only == (dfeatures != nullptr), "engine: an encoder-only forward is continued by ndt1_engine_backward_features, a full one by ndt1_engine_backward");
     const long long launches0 = g_ndt1_launches;
-    if (B == 0) return 0;
+    if (B == 0) {       // empty shard: no gradient contribution, but every stage is "complete" for ndt1_engine_wait_stage
+      for (int i = 0; i < n_stages(); ++i) NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[i], s));
+      return 0;
+    }
     const int H = k.hidden, I = k.inter, D = k.input_dim, N = k.n_channels, NL = k.n_layers, V = k.n_outputs;
     const int Hout = k.factors_active ? k.factors_size : H;
     const long long M = (long long)B * L, MT = (long long)B * Tn, Mo = (long long)B * Tp;

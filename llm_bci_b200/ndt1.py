@@ -329,11 +329,13 @@ class _EngineFunction(torch.autograd.Function):
         out = model._engine_forward(call, need_backward=True)
         ctx.model = model
         ctx.n_params = len(params)
+        ctx.generation = model._generation
         ctx.mark_non_differentiable(out["preds"])
         return out["loss"], out["preds"]
 
     @staticmethod
     def backward(ctx, dloss, _dpreds):
+        ctx.model._check_generation(ctx.generation)
         grads = ctx.model._engine_backward(dloss)
         return (None, None) + tuple(grads)
 
@@ -346,11 +348,13 @@ class _EncoderFunction(torch.autograd.Function):
     def forward(ctx, model: "NDT1", call: dict, *params):
         out = model._engine_forward(call, need_backward=True)
         ctx.model = model
+        ctx.generation = model._generation
         ctx.mark_non_differentiable(out["out_mask"])
         return out["features"], out["out_mask"]
 
     @staticmethod
     def backward(ctx, dfeatures, _dmask):
+        ctx.model._check_generation(ctx.generation)
         grads = ctx.model._engine_backward(None, dfeatures=dfeatures)
         return (None, None) + tuple(grads)
 
@@ -423,6 +427,7 @@ class NDT1(nn.Module):
         self._gstruct = {}            # gradient pointer tables by base address of the flat buffer they point into
         self._last = None
         self._last_out = None
+        self._generation = 0          # forwards run so far: the engine keeps the activations of the LAST one only
         self._weight_shadow = None
         self._param_stream = None     # a side stream that may still be updating the parameters (DataParallelTrainer's optimizer)
 
@@ -525,8 +530,19 @@ class NDT1(nn.Module):
         if self._param_stream is not None:
             torch.cuda.current_stream().wait_stream(self._param_stream)
 
+    def _check_generation(self, generation: int) -> None:
+        """The engine holds the activations, dropout seed and batch geometry of its most recent forward only (one arena,
+        nothing allocated per step).  A backward through an OLDER forward -- ``(model(a).loss + model(b).loss).backward()``,
+        or an encoder sub-API call followed by a full forward -- would silently use the newer activations: refuse it."""
+        if generation != self._generation:
+            raise RuntimeError("llm_bci_b200.NDT1 keeps one live autograd graph per model: this backward belongs to forward "
+                               f"#{generation}, but forward #{self._generation} has since overwritten the engine's activations. "
+                               "Call backward() before the next forward (accumulate gradients across backward calls instead of "
+                               "summing losses), or use a second model instance.")
+
     def _engine_forward(self, call: dict, need_backward: bool) -> dict:
         L = _C.lib()
+        self._generation += 1
         self.wait_for_parameters()     # (after the prologue: smoothing / noise / masking do not read a parameter)
         x = call["spikes"]
         B, T, N = x.shape
@@ -756,5 +772,19 @@ class NDT1(nn.Module):
 
     def load_checkpoint(self, load_dir):
         """models/ndt1.py:690-692."""
+        self.wait_for_parameters()     # a pending side-stream optimizer bucket must not overwrite what is loaded
         self.encoder.load_state_dict(torch.load(os.path.join(load_dir, "encoder.bin")))
         self.decoder.load_state_dict(torch.load(os.path.join(load_dir, "decoder.bin")))
+        self._refresh_weight_shadow()
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        self.wait_for_parameters()
+        r = super().load_state_dict(state_dict, *args, **kwargs)
+        self._refresh_weight_shadow()
+        return r
+
+    def _refresh_weight_shadow(self) -> None:
+        """Re-cast the bf16 weight shadow from the flat fp32 arena it mirrors (parameters changed behind the optimizer's back)."""
+        ws = getattr(self, "_weight_shadow", None)
+        if ws is not None:
+            ws[1].copy_(ws[0])

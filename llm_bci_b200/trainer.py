@@ -82,7 +82,8 @@ class DataParallelTrainer:
         self.scheduler, self.total_steps, self.warmup_pct, self.div_factor, self.gamma = scheduler, total_steps, warmup_pct, div_factor, gamma
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
-        self.step_count = 0
+        self.step_count = 0        # optimizer updates done so far
+        self.epoch = 0             # epochs ended so far (end_epoch(); only the "step" schedule reads it)
         # gradient accumulation as the reference runs it (models/trainer.py:333-349): the loss is scaled by 1 / steps, the optimizer
         # steps on micro-batch 1, 1 + steps, ... and the micro-batches in between only accumulate (no_sync: no all-reduce)
         self.accum = max(1, int(gradient_accumulation_steps))
@@ -129,13 +130,21 @@ class DataParallelTrainer:
 
     # ------------------------------------------------------------------
     def current_lr(self) -> float:
+        """Learning rate of the NEXT optimizer update.  The reference calls ``lr_scheduler.step()`` after ``optimizer.step()``
+        (models/trainer.py:340-342), so its k-th update (k = 1, 2, ...) runs at schedule(k - 1): the schedules are evaluated
+        at the number of updates already done.  "step" is StepLR(step_size=1, gamma) stepped once per EPOCH
+        (models/trainer.py:253, 418-419): lr * gamma ** epochs_ended, see ``end_epoch``."""
         if self.scheduler == "cosine":
             return onecycle_cos_lr(self.step_count, self.total_steps, self.lr, self.warmup_pct, self.div_factor)
         if self.scheduler == "linear":
             return linear_warmup_lr(self.step_count, self.total_steps, self.lr, self.warmup_pct)
         if self.scheduler == "step":
-            return self.lr * (self.gamma ** self.step_count)
+            return self.lr * (self.gamma ** self.epoch)
         return self.lr
+
+    def end_epoch(self) -> None:
+        """Call once after every pass over the training set (models/trainer.py:418-419)."""
+        self.epoch += 1
 
     def all_reduce_gradients(self) -> None:
         """Bucketed all-reduce (sum) on the side stream; each bucket waits for its backward stage."""
@@ -178,8 +187,8 @@ class DataParallelTrainer:
             self.all_reduce_gradients()
             self.optimizer_step()
             return out
+        lr = float(self.current_lr())      # schedule(updates done), then count this update (1-based for Adam's bias correction)
         self.step_count += 1
-        lr = float(self.current_lr())
         L = _C.lib()
         with torch.cuda.stream(self.comm_stream):
             for stage, lo, hi in self.buckets:
@@ -202,5 +211,6 @@ class DataParallelTrainer:
 
     def optimizer_step(self) -> None:
         """AdamW over the whole arena on the current stream (for callers that drive forward_backward themselves)."""
+        lr = float(self.current_lr())
         self.step_count += 1
-        self._adamw(0, self.flat_param.numel(), float(self.current_lr()), _C.stream_ptr())
+        self._adamw(0, self.flat_param.numel(), lr, _C.stream_ptr())

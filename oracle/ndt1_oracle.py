@@ -552,3 +552,13 @@ def synthetic_ctc_batch(B=32, T=1000, N=256, seed=1, fixed_length=False, stack=(
     tg = tg * (torch.arange(S)[None, :] < tl[:, None])
     return dict(spikes=spikes, spikes_mask=mask, spikes_timestamp=ts, spikes_lengths=lens, targets=tg,
                 targets_lengths=tl)
+
+
+def synthetic_ssl_batch(B=16, T=100, N=668, seed=1):
+    """BASELINE.json configs[0] inputs (SURVEY.md 8d, configs/ndt1.yaml shape): Poisson(0.1) spike counts, full-length trials
+    (the same generator calls as tests/golden/make_golden.py::ssl_batch)."""
+    g = torch.Generator().manual_seed(seed)
+    sp = torch.poisson(torch.full((B, T, N), 0.1), generator=g)
+    msk = torch.ones(B, T, dtype=torch.int64)
+    return dict(spikes=sp, spikes_mask=msk, spikes_timestamp=torch.arange(T)[None].expand(B, T).contiguous(),
+                spikes_lengths=torch.full((B,), T, dtype=torch.int64))

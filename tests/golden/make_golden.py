@@ -96,6 +96,11 @@ def main():
     if "--only-variants" in sys.argv:
         variant_cases(R)
         return
+    if "--round2" in sys.argv:            # fixtures added in round 2 (the earlier files regenerate bit-identically and are left alone)
+        autocast_error_cases(R)
+        ssl_full_case(R)
+        full_b32_case(R)
+        return
     if not only_full:
         small_cases(R)
         variant_cases(R)
@@ -390,6 +395,199 @@ def full_case(R):
     d["grad64_slice/encoder.embedder.embed_pos.weight"] = grads_d["encoder.embedder.embed_pos.weight"][:4, :].numpy().astype(np.float32)
     np.savez_compressed(os.path.join(HERE, "ctc_full_b4.npz"), **d)
     print("ctc_full_b4 loss", float(out_f.loss), "fp64", float(out_d.loss))
+
+
+KEEP_FULL = ("decoder.0.weight", "decoder.0.bias", "encoder.out_norm.weight", "encoder.layers.0.ln1.weight",
+             "encoder.layers.4.mlp.down_proj.bias", "encoder.layers.2.attn.query.bias", "encoder.embedder.embed_spikes.bias",
+             "encoder.layers.0.attn.value.bias", "encoder.layers.3.ln2.bias")
+KEEP_SLICE = {"encoder.layers.0.attn.value.weight": 8, "encoder.layers.4.attn.out_proj.weight": 8, "encoder.layers.2.mlp.up_proj.weight": 8,
+              "encoder.embedder.embed_pos.weight": 4, "encoder.layers.1.attn.query.weight": 4}
+
+
+def grad_error_metrics(got, ref):
+    """The metrics of tests/test_gpu_parity.py::check_grads: per tensor relative L2 and max-abs error, both floored at 1e-3 of
+    the global scale; returns the worst of each over the tensors."""
+    gscale = max(float(v.abs().max()) for v in ref.values())
+    nscale = max(float(v.double().norm()) for v in ref.values())
+    l2 = {n: float((got[n].double() - r.double()).norm() / max(float(r.double().norm()), 1e-3 * nscale)) for n, r in ref.items()}
+    mx = {n: float((got[n].double() - r.double()).abs().max() / max(float(r.abs().max()), 1e-3 * gscale)) for n, r in ref.items()}
+    return l2, mx
+
+
+def run_ref_autocast(model, batch):
+    """The reference under bf16 autocast, the way Accelerate(mixed_precision='bf16') runs it (deepspeed/*.yaml presets)."""
+    model.train(True)
+    model.zero_grad()
+    b = {k: v.clone() for k, v in batch.items()}
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        out = model(**b)
+    out.loss.float().backward()
+    grads = {n: (p.grad.clone().float() if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
+    return out, grads
+
+
+def autocast_error_cases(R):
+    """For every case whose bf16 tolerance tests/test_gpu_parity.py widens beyond the nominal 2e-2 (ReLU heads / factors):
+    the error the REFERENCE ITSELF makes under bf16 autocast against its own fp32 run, in the metrics of check_grads.  The CUDA
+    bf16 path is then bounded by a stated multiple of this figure instead of a hand-picked number."""
+    update_config, NDT1 = R["update_config"], R["NDT1"]
+    trainer = update_config("configs/trainer_ctc_ndt1.yaml", None)
+    base = update_config(copy.deepcopy(dict(trainer.model)), small_ctc_overrides())
+    batch = make_ctc_batch(3, 120, 16, seed=5)
+    d = {}
+
+    def record(name, model, b):
+        out32, g32 = run_ref(model, b, train=True)
+        out16, g16 = run_ref_autocast(model, b)
+        l2, mx = grad_error_metrics(g16, g32)
+        d[f"{name}/loss_rel"] = np.array(abs(float(out16.loss) - float(out32.loss)) / abs(float(out32.loss)))
+        d[f"{name}/grad_l2_max"] = np.array(max(l2.values()))
+        d[f"{name}/grad_maxabs_max"] = np.array(max(mx.values()))
+        d[f"{name}/grad_l2_median"] = np.array(float(np.median(list(l2.values()))))
+        worst = max(l2, key=l2.get)
+        print(f"autocast {name}: loss rel {float(d[f'{name}/loss_rel']):.2e}, grad rel-L2 max {max(l2.values()):.3e} ({worst}), "
+              f"median {float(d[f'{name}/grad_l2_median']):.2e}, max-abs {max(mx.values()):.3e}")
+
+    for name in ("gelu_factors", "rope"):                 # "rope": a case that is NOT waived, as the yardstick
+        over, days = VARIANTS[name]
+        torch.manual_seed(21)
+        model = NDT1(update_config(copy.deepcopy(dict(base)), over), **trainer.method.model_kwargs)
+        record(f"ctc_variants/{name}", model, dict(batch))
+    ar_over = {"encoder": {
+        "embedder": {"n_channels": 24, "input_dim": 16, "max_F": 64, "dropout": 0.0, "stack": {"active": False}},
+        "transformer": {"n_layers": 2, "hidden_size": 64, "n_heads": 4, "inter_size": 64, "dropout": 0.0},
+        "smooth_and_noise": {"noise": False},
+        "context": {"forward": 0, "backward": -2},
+    }}
+    g = torch.Generator().manual_seed(19)
+    B, T, N = 4, 40, 24
+    sp = torch.poisson(torch.full((B, T, N), 0.6), generator=g)
+    lens = torch.tensor([40, 31, 40, 22])
+    msk = (torch.arange(T)[None] < lens[:, None]).to(torch.int64)
+    sp = sp * msk[:, :, None]
+    abatch = dict(spikes=sp, spikes_mask=msk, spikes_timestamp=torch.arange(T)[None].expand(B, T) * msk, spikes_lengths=lens)
+    for name, kw in (("mse", dict(loss="mse", log_input=False)), ("poisson_rate", dict(loss="poisson_nll", log_input=False)),
+                     ("poisson_log", dict(loss="poisson_nll", log_input=True))):
+        torch.manual_seed(31)
+        model = NDT1(update_config("configs/ndt1.yaml", ar_over), method_name="autoregressive", **kw)
+        record(f"autoregressive/{name}", model, abatch)
+    np.savez_compressed(os.path.join(HERE, "bf16_autocast_error.npz"), **d)
+
+
+def ssl_batch(B=16, T=100, N=668, seed=1):
+    """BASELINE.json configs[0] inputs: Poisson(0.1) counts, full-length trials."""
+    g = torch.Generator().manual_seed(seed)
+    sp = torch.poisson(torch.full((B, T, N), 0.1), generator=g)
+    msk = torch.ones(B, T, dtype=torch.int64)
+    return dict(spikes=sp, spikes_mask=msk, spikes_timestamp=torch.arange(T)[None].expand(B, T).contiguous(),
+                spikes_lengths=torch.full((B,), T, dtype=torch.int64))
+
+
+def ssl_full_case(R):
+    """BASELINE.json configs[0] at FULL size: NDT1 masked-spike SSL, 16 x 100 bins x 668 neurons, temporal masker 0.3, Poisson-NLL
+    on log rates, 5 x 1024 encoder without stacking (33.7 M parameters: kept as per-tensor sums; the test re-creates them from
+    the same torch seed, see test_init_matches_reference_rng_order)."""
+    update_config, NDT1 = R["update_config"], R["NDT1"]
+    mk = {"active": True, "mode": "temporal", "ratio": 0.3, "zero_ratio": 1.0, "random_ratio": 1.0, "expand_prob": 0.0,
+          "max_timespan": 1, "regions": None, "channels": None}
+    over = {"encoder": {"masker": {"active": mk}, "embedder": {"n_channels": 668, "dropout": 0.0, "stack": {"active": False}},
+                        "transformer": {"dropout": 0.0}, "smooth_and_noise": {"noise": False}}}
+    cfg = update_config("configs/ndt1.yaml", over)
+    del cfg["encoder"]["masker"]["neuron"]
+    torch.manual_seed(1)
+    model = NDT1(cfg, method_name="mlm", loss="poisson_nll", log_input=True)
+    batch = ssl_batch()
+    out, grads = run_ref(model, batch, train=True, seed=77)
+    torch.manual_seed(77)                                   # replay the CPU draws (SURVEY.md A.3)
+    expand = bool(torch.bernoulli(torch.tensor(mk["expand_prob"]).float()))
+    assert not expand
+    m_draw = torch.bernoulli(torch.full((16, 100), mk["ratio"]))
+    names = [n for n, _ in model.named_parameters()]
+    d = {"names": np.array(names), "draw/mask": m_draw.numpy().astype(np.uint8), "draw/timespan": np.array(1),
+         "out/loss": out.loss.detach().numpy(), "out/n_examples": out.n_examples.numpy(),
+         "out/mask_bt": out.mask[:, :, 0].numpy().astype(np.uint8), "out/mask_sum": np.array(int(out.mask.sum())),
+         "out/preds_rows": out.preds.detach().numpy()[:, ::10, ::4], "out/preds_sum": out.preds.detach().double().sum().numpy()}
+    assert bool((out.mask == out.mask[:, :, :1]).all())     # temporal: the mask is constant over neurons
+    d["param_sum"] = np.array([float(p.detach().double().sum()) for p in model.parameters()])
+    d["grad_norm"] = np.array([float(grads[n].double().norm()) for n in names])
+    d["grad_absmax"] = np.array([float(grads[n].abs().max()) for n in names])
+    for n in KEEP_FULL:
+        if n in grads:
+            d[f"grad/{n}"] = grads[n].numpy()
+    d["grad/encoder.embedder.projection.bias"] = grads["encoder.embedder.projection.bias"].numpy()
+    for n, rows in KEEP_SLICE.items():
+        d[f"grad_slice/{n}"] = grads[n][:rows].numpy()
+    d["grad_slice/decoder.0.weight"] = grads["decoder.0.weight"][:16].numpy()
+    d["grad_slice/encoder.embedder.embed_spikes.weight"] = grads["encoder.embedder.embed_spikes.weight"][:8].numpy()
+    d["grad_slice/encoder.embedder.projection.weight"] = grads["encoder.embedder.projection.weight"][:8].numpy()
+    # the reference's own bf16-autocast error on this very case (the yardstick for the bf16 CUDA mode at this size)
+    out16, g16 = run_ref_autocast_seeded(model, batch, 77)
+    l2, mx = grad_error_metrics(g16, grads)
+    d["autocast/loss_rel"] = np.array(abs(float(out16.loss) - float(out.loss)) / abs(float(out.loss)))
+    d["autocast/grad_l2_max"] = np.array(max(l2.values()))
+    d["autocast/grad_maxabs_max"] = np.array(max(mx.values()))
+    np.savez_compressed(os.path.join(HERE, "ssl_full_b16.npz"), **d)
+    print("ssl_full_b16 loss", float(out.loss), "n", int(out.n_examples), "autocast loss rel", float(d["autocast/loss_rel"]),
+          "grad l2 max", float(d["autocast/grad_l2_max"]))
+
+
+def run_ref_autocast_seeded(model, batch, seed):
+    torch.manual_seed(seed)
+    return run_ref_autocast(model, batch)
+
+
+def full_b32_case(R):
+    """BASELINE.json configs[1] at FULL size and FULL batch: 32 x 1000 x 256, the parity variant (dropout 0, noise off).
+    Parameters come from torch.manual_seed(1) (bit-identical init, checked through param_sum)."""
+    update_config, NDT1 = R["update_config"], R["NDT1"]
+    trainer = update_config("configs/trainer_ctc_ndt1.yaml", None)
+    cfg_f = update_config(copy.deepcopy(dict(trainer.model)), {"encoder": {
+        "embedder": {"dropout": 0.0}, "transformer": {"dropout": 0.0}, "smooth_and_noise": {"noise": False}}})
+    torch.manual_seed(1)
+    model = NDT1(cfg_f, **trainer.method.model_kwargs)
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle.ndt1_oracle import synthetic_ctc_batch
+    fb = synthetic_ctc_batch(B=32, T=1000, N=256, seed=1)
+    out, grads = run_ref(model, fb, train=True)
+    names = [n for n, _ in model.named_parameters()]
+    preds = out.preds.detach()
+    d = {"names": np.array(names), "out/loss": out.loss.detach().numpy(), "out/n_examples": out.n_examples.numpy(),
+         "out/preds_rows": preds.numpy()[:, ::40, :], "out/preds_sum": preds.double().sum().numpy(),
+         "out/argmax": preds.argmax(-1).numpy().astype(np.int16),
+         "out/top2_margin_min": np.array(float((preds.topk(2, -1).values[..., 0] - preds.topk(2, -1).values[..., 1]).min()))}
+    d["param_sum"] = np.array([float(p.detach().double().sum()) for p in model.parameters()])
+    d["grad_norm"] = np.array([float(grads[n].double().norm()) for n in names])
+    d["grad_absmax"] = np.array([float(grads[n].abs().max()) for n in names])
+    for n in KEEP_FULL:
+        d[f"grad/{n}"] = grads[n].numpy()
+    d["grad/encoder.embedder.stack_projection.bias"] = grads["encoder.embedder.stack_projection.bias"].numpy()
+    for n, rows in KEEP_SLICE.items():
+        d[f"grad_slice/{n}"] = grads[n][:rows].numpy()
+    d["grad_slice/encoder.embedder.stack_projection.weight"] = grads["encoder.embedder.stack_projection.weight"][:4].numpy()
+    d["grad_slice/encoder.embedder.embed_spikes.weight"] = grads["encoder.embedder.embed_spikes.weight"][:16].numpy()
+    # the same in float64: the target of the strict (fp32) CUDA mode
+    model_d = NDT1(cfg_f, **trainer.method.model_kwargs).double()
+    model_d.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    fbd = {k: (v.double() if v.is_floating_point() else v) for k, v in fb.items()}
+    out_d, grads_d = run_ref(model_d, fbd, train=True)
+    d["out64/loss"] = out_d.loss.detach().numpy()
+    d["grad_norm64"] = np.array([float(grads_d[n].norm()) for n in names])
+    for n in KEEP_FULL:
+        d[f"grad64/{n}"] = grads_d[n].numpy().astype(np.float32)
+    d["grad64/encoder.embedder.stack_projection.bias"] = grads_d["encoder.embedder.stack_projection.bias"].numpy().astype(np.float32)
+    for n, rows in KEEP_SLICE.items():
+        d[f"grad64_slice/{n}"] = grads_d[n][:rows].numpy().astype(np.float32)
+    del model_d, grads_d
+    # the reference's own bf16-autocast error at this size
+    out16, g16 = run_ref_autocast(model, fb)
+    l2, mx = grad_error_metrics(g16, grads)
+    d["autocast/loss_rel"] = np.array(abs(float(out16.loss) - float(out.loss)) / abs(float(out.loss)))
+    d["autocast/grad_l2_max"] = np.array(max(l2.values()))
+    d["autocast/grad_maxabs_max"] = np.array(max(mx.values()))
+    d["autocast/argmax_agree"] = np.array(float((out16.preds.detach().float().argmax(-1) == preds.argmax(-1)).float().mean()))
+    np.savez_compressed(os.path.join(HERE, "ctc_full_b32.npz"), **d)
+    print("ctc_full_b32 loss", float(out.loss), "fp64", float(out_d.loss), "autocast loss rel", float(d["autocast/loss_rel"]),
+          "grad l2 max", float(d["autocast/grad_l2_max"]), "argmax agree", float(d["autocast/argmax_agree"]))
 
 
 if __name__ == "__main__":

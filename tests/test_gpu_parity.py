@@ -24,10 +24,33 @@ pytestmark = pytest.mark.gpu
 import llm_bci_b200 as lb  # noqa: E402
 from llm_bci_b200 import _C  # noqa: E402
 from oracle import ndt1_oracle as O  # noqa: E402
-from test_oracle_golden import load, sub, small_ctc_cfg, mlm_cfg, CTC_KW, VARIANTS, variant_case, AR_KW, autoregressive_cfg  # noqa: E402
+from test_oracle_golden import (load, sub, small_ctc_cfg, mlm_cfg, CTC_KW, VARIANTS, variant_case, AR_KW, autoregressive_cfg,  # noqa: E402
+                                SSL_KW, ssl_full_cfg, ssl_full_draws, full_ctc_cfg, check_full_fixture)
 
 DEV = "cuda"
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+# bf16 cases whose gradient tolerance is wider than the nominal 2e-2.  Each is bounded by a STATED MULTIPLE of the error the
+# unmodified reference itself makes on the same case under bf16 autocast against its own fp32 run
+# (tests/golden/bf16_autocast_error.npz, written by make_golden.py::autocast_error_cases in the metrics of check_grads):
+#   key -> (fixture case, multiple of the reference's own worst per-tensor rel-L2 error)
+# ReLU heads (factors / rate decoders): a unit whose pre-activation is below the bf16 rounding error of its inputs flips its
+# 0/1 derivative; the engine additionally keeps the activations BETWEEN kernels in bf16 (autocast keeps them in fp32 and only
+# rounds the GEMM operands), which is where the factor over the reference's own figure comes from.  For the Poisson-rate head
+# the reference's own autocast error is 1.4 (its 1 / rate gradient is computed in bf16): the CUDA path is well below it.
+BF16_WAIVERS = {
+    "gelu_factors": ("ctc_variants/gelu_factors", 12.0),
+    "mse": ("autoregressive/mse", 12.0),
+    "poisson_rate": ("autoregressive/poisson_rate", 0.2),
+}
+
+
+def bf16_grad_tol(key):
+    if key not in BF16_WAIVERS:
+        return TOL["bf16"]
+    case, mult = BF16_WAIVERS[key]
+    ref_err = float(load("bf16_autocast_error.npz")[f"{case}/grad_l2_max"])
+    return max(TOL["bf16"], mult * ref_err)
 
 
 def cuda_batch(b):
@@ -391,15 +414,12 @@ def test_ctc_variants_match_reference(name, precision):
     assert abs(float(out.loss) - ref_loss) <= tol * abs(ref_loss)
     perr = np.abs(out.preds.cpu().double().numpy() - g[f"{name}/out/preds"]).max()
     assert perr <= (2e-4 if precision == "fp32" else 5e-2), perr
-    gtol = tol
-    if precision == "bf16" and name == "gelu_factors":
-        # ReLU after the factors projection: a unit whose pre-activation is below the bf16 rounding error of its inputs
-        # (|pre| < ~7e-4 here, 0.1 % of the units) flips its 0/1 derivative, and a flipped fraction f costs ~sqrt(f) in
-        # relative L2 of everything upstream -- measured 2-6 %, identical to four digits on the CUDA-core GEMM path
-        # (NDT1_FORCE_SIMT=1), so it is the storage format, not the tensor-core kernels.  The same model with smooth
-        # activations (rope_adapt_gelu_factors) meets 2e-2.
-        gtol = 1e-1
-    check_grads(grads_of(model), sub(g, f"{name}/grad"), gtol)
+    # (gelu_factors in bf16: ReLU after the factors projection, see BF16_WAIVERS -- measured 2-6 %, identical to four digits on
+    # the CUDA-core GEMM path (NDT1_FORCE_SIMT=1), so it is the storage format, not the tensor-core kernels; the same model
+    # with smooth activations, rope_adapt_gelu_factors, meets the nominal 2e-2)
+    gtol = bf16_grad_tol(name) if precision == "bf16" else tol
+    worst = check_grads(grads_of(model), sub(g, f"{name}/grad"), gtol)
+    print(f"variant {name} {precision}: worst per-tensor rel-L2 {worst[1]:.3e} ({worst[0]}), bound {gtol:.3e}")
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -417,9 +437,10 @@ def test_autoregressive_matches_reference(name, precision):
     assert abs(float(out.loss) - ref_loss) <= tol * abs(ref_loss)
     assert int(out.n_examples) == int(g[f"{name}/out/n_examples"])
     gtol = 5e-4 if name == "poisson_rate" else tol      # (1 - t / (rate + 1e-8) amplifies fp32 rounding where the ReLU rate is ~0)
-    if precision == "bf16" and name != "poisson_log":
-        gtol = 2.5e-1 if name == "poisson_rate" else 1e-1          # ReLU head (and, for the Poisson rate, its 1 / rate gradient on top): units whose pre-activation is below the bf16 rounding error flip their 0/1 derivative (see test_ctc_variants_match_reference)
-    check_grads(grads_of(model), sub(g, f"{name}/grad"), gtol)
+    if precision == "bf16":
+        gtol = bf16_grad_tol(name)                        # ReLU heads: bounded by a multiple of the reference's own autocast error (BF16_WAIVERS)
+    worst = check_grads(grads_of(model), sub(g, f"{name}/grad"), gtol)
+    print(f"autoregressive {name} {precision}: worst per-tensor rel-L2 {worst[1]:.3e} ({worst[0]}), bound {gtol:.3e}")
 
 
 def test_rope_adapt_with_tensor_core_attention_bf16():
@@ -557,13 +578,19 @@ def test_benchmark_size_properties_bf16():
     full = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
     loss_full = float(out.loss)
     assert np.isfinite(loss_full) and int(out.n_examples) == 32
-    # (1) padded bins never influence the loss: garbage beyond each length changes nothing
+    # (1) padded bins never influence the loss.  The 13-tap smoothing (models/ndt1.py:92-97) reaches 6 bins across the end of a
+    # trial and a stacked row covers bins [4r, 4r + 32), so garbage is written only from 6 bins past each trial's length on: the
+    # rows the CTC reads (r < len') then see bit-identical inputs, and the loss must be EQUAL, not merely finite.
     b2 = dict(batch)
-    noise = torch.randn_like(batch["spikes"]) * (1 - batch["spikes_mask"][:, :, None].float())
-    b2["spikes"] = batch["spikes"] + 100 * noise
-    l2 = float(model(**b2).loss)
-    # smoothing leaks +-6 bins across the boundary, so compare with a garbage-free guard band instead
-    assert np.isfinite(l2)
+    tpos = torch.arange(batch["spikes"].shape[1], device=DEV)[None, :]
+    garbage_at = (tpos >= batch["spikes_lengths"][:, None] + 6).float()[:, :, None]
+    assert float(garbage_at.sum()) > 1000
+    b2["spikes"] = batch["spikes"] + 100 * torch.randn_like(batch["spikes"]) * garbage_at
+    o2 = model(**b2)
+    assert float(o2.loss) == loss_full, (float(o2.loss), loss_full)
+    valid_rows = (torch.arange(out.preds.shape[1], device=DEV)[None, :] < (1 + (batch["spikes_lengths"] - 32) // 4)[:, None])
+    assert torch.equal(o2.preds[valid_rows], out.preds[valid_rows])
+    assert not torch.equal(o2.preds, out.preds)          # (the garbage did reach the padded rows)
     # (2) linearity over trials: the loss is a SUM, so the halves add up (loss and gradients)
     model.zero_grad()
     halves = []
@@ -809,3 +836,186 @@ def test_trainer_weight_shadow_follows_the_parameters():
     assert runs[0][-1] < runs[0][0]
     for a, b in zip(*runs):
         assert abs(a - b) <= 1e-3 * abs(b), runs
+
+
+# --------------------------------------------------------------------------- round 2: multi-rank trainer, schedules, guards
+def test_data_parallel_trainer_world2_matches_single_process():
+    """DataParallelTrainer.train_step at world 2 (two processes on THIS GPU over gloo): bucketed all-reduce, 1/world folded into
+    AdamW, stage events, deferred join -- against one process on the concatenated batch under DDP-mean semantics
+    (models/trainer.py:77-80, 258-262, 335-349).  The same script runs under NCCL on 2 / 8 GPUs (tests/dp_parity.py)."""
+    import torch.multiprocessing as mp
+    import dp_parity
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=dp_parity.worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    try:
+        res = q.get(timeout=600)
+    finally:
+        [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert [r["precision"] for r in res] == ["fp32", "bf16"]
+    dp_parity.check(res)
+
+
+def test_trainer_schedule_and_update_match_torch_adamw_onecycle():
+    """The k-th update runs at schedule(k - 1) (the reference steps the scheduler AFTER the optimizer, models/trainer.py:340-342):
+    three trainer steps == torch.optim.AdamW + OneCycleLR fed with this model's own gradients."""
+    from torch.optim.lr_scheduler import OneCycleLR
+    g = load("ctc_small.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g, "param").items()}
+    batch = cuda_batch({k: torch.from_numpy(v) for k, v in sub(g, "batch").items()})
+    m1, m2 = build(small_ctc_cfg(), CTC_KW, params, "fp32").train(), build(small_ctc_cfg(), CTC_KW, params, "fp32").train()
+    tr = lb.DataParallelTrainer(m1, lr=1e-3, wd=5e-5, eps=1e-3, scheduler="cosine", total_steps=6, warmup_pct=0.34, div_factor=25.0)
+    opt = torch.optim.AdamW(m2.parameters(), lr=1e-3, weight_decay=5e-5, eps=1e-3)
+    sch = OneCycleLR(opt, total_steps=6, max_lr=1e-3, pct_start=0.34, div_factor=25.0)
+    for k in range(3):
+        assert abs(tr.current_lr() - opt.param_groups[0]["lr"]) < 1e-12, k
+        tr.train_step(batch)
+        opt.zero_grad()
+        m2(**batch).loss.backward()
+        opt.step()
+        sch.step()
+    tr.synchronize()
+    torch.cuda.synchronize()
+    assert tr.step_count == 3
+    for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert float((p1 - p2).abs().max()) <= 2e-6 * max(1.0, float(p2.abs().max())), n
+    # "step" = StepLR(step_size=1, gamma) stepped once per EPOCH (models/trainer.py:253, 418-419)
+    ts = lb.DataParallelTrainer(m2, lr=2e-3, scheduler="step", gamma=0.5)
+    ts.train_step(batch); ts.train_step(batch)
+    assert ts.current_lr() == 2e-3
+    ts.end_epoch()
+    assert ts.current_lr() == 1e-3
+
+
+def test_backward_through_a_stale_forward_raises():
+    """The engine keeps the activations of the last forward only: a backward through an older graph must raise, not
+    return the newer forward's gradients."""
+    g = load("ctc_small.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g, "param").items()}
+    batch = cuda_batch({k: torch.from_numpy(v) for k, v in sub(g, "batch").items()})
+    model = build(small_ctc_cfg(), CTC_KW, params, "fp32").train()
+    a = model(**batch).loss
+    b = model(**batch).loss
+    with pytest.raises(RuntimeError, match="one live autograd graph"):
+        (a + b).backward()
+    model.zero_grad()
+    c = model(**batch).loss
+    c.backward()                                                   # the latest graph is fine
+    assert float(model.decoder[0].weight.grad.abs().max()) > 0
+
+
+def test_empty_shard_returns_zero_loss_and_signals_every_stage():
+    g = load("ctc_small.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g, "param").items()}
+    batch = cuda_batch({k: torch.from_numpy(v) for k, v in sub(g, "batch").items()})
+    model = build(small_ctc_cfg(), CTC_KW, params, "fp32").train()
+    trainer = lb.DataParallelTrainer(model, lr=1e-3)
+    trainer.train_step(batch)
+    before = trainer.flat_param.clone()
+    empty = {k: v[:0] for k, v in batch.items()}
+    out = trainer.train_step(empty)
+    trainer.synchronize()
+    torch.cuda.synchronize()
+    assert float(out.loss) == 0.0 and int(out.n_examples) == 0
+    assert torch.isfinite(trainer.flat_param).all() and float((trainer.flat_param - before).abs().max()) < 1e-2
+
+
+def test_load_checkpoint_refreshes_the_weight_shadow(tmp_path):
+    tr = lb.default_trainer_config()
+    cfg = lb.update_config(tr.model, {"encoder": {"embedder": {"dropout": 0.0}, "transformer": {"dropout": 0.0, "n_layers": 1},
+                                                  "smooth_and_noise": {"noise": False}}})
+    batch = cuda_batch(O.synthetic_ctc_batch(B=2, T=200, N=256, seed=2))
+    torch.manual_seed(5)
+    model = lb.NDT1(cfg, **tr.method.model_kwargs, precision="bf16").to(DEV)
+    trainer = lb.DataParallelTrainer(model, lr=1e-2)
+    model.save_checkpoint(str(tmp_path))
+    model.eval()
+    l0 = float(model(**batch).loss)
+    for _ in range(3):
+        trainer.train_step(batch)
+    model.eval()
+    l1 = float(model(**batch).loss)
+    model.load_checkpoint(str(tmp_path))                               # "load the best checkpoint, then evaluate"
+    l2 = float(model(**batch).loss)
+    assert l1 != l0 and l2 == l0
+    assert torch.equal(trainer.shadow, trainer.flat_param.bfloat16())
+
+
+def test_generate_runs_the_reference_loops():
+    """NDT1.generate (models/ndt1.py:592-682): mlm appends a blank bin and writes the sample back, autoregressive appends the
+    sample; shapes, causality of the prefix and the Poisson sampling of the appended bins."""
+    g = load("autoregressive_small.npz")
+    params = {k: torch.from_numpy(v) for k, v in sub(g, "poisson_log/param").items()}
+    model = build(autoregressive_cfg(), dict(method_name="autoregressive", **AR_KW["poisson_log"]), params, "fp32").eval()
+    batch = cuda_batch({k: torch.from_numpy(v) for k, v in sub(g, "batch").items()})
+    sp, mk, ts = batch["spikes"][:2, :10], batch["spikes_mask"][:2, :10], batch["spikes_timestamp"][:2, :10]
+    torch.manual_seed(3)
+    preds, bins = model.generate(spikes=sp, spikes_mask=mk, spikes_timestamp=ts, spikes_lengths=None, max_new_bins=4)
+    assert preds.shape == (2, 4, 24) and bins.shape == (2, 4, 24)
+    assert bool((bins >= 0).all()) and bool((bins == bins.round()).all()) and bool((preds > 0).all())
+    # the first new bin's rate is exp(prediction of the last input position) of a plain forward
+    out = model(spikes=sp, spikes_mask=mk, spikes_timestamp=ts, spikes_lengths=None)
+    assert torch.allclose(preds[:, 0], out.preds[:, -1].exp(), rtol=1e-5, atol=1e-6)
+
+
+# --------------------------------------------------------------------------- round 2: BASELINE configs[0] and [1] at FULL size
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ctc_full_size_b32_config1_matches_reference(precision):
+    """BASELINE.json configs[1], the shape the bench times (32 x 1000 x 256, 5 x 1024, stack 32/4, 41 phonemes), parity variant
+    (dropout 0, noise off): loss, prediction rows, per-tensor gradient norms, full small gradients and slices of the big ones
+    against the unmodified reference (tests/golden/ctc_full_b32.npz; fp32 mode against the reference's float64 run)."""
+    g = load("ctc_full_b32.npz")
+    cfg, kw = full_ctc_cfg()
+    torch.manual_seed(1)
+    model = lb.NDT1(cfg, **kw, precision=precision).to(DEV).train()
+    names = [n for n, _ in model.named_parameters()]
+    assert names == list(g["names"])
+    assert np.array_equal(np.array([float(p.detach().double().sum()) for p in model.parameters()]), g["param_sum"])   # the reference's init, bit for bit
+    batch = cuda_batch(O.synthetic_ctc_batch(B=32, T=1000, N=256, seed=1))
+    out = model(**batch)
+    out.loss.backward()
+    tol = TOL[precision]
+    ref_loss = float(g["out64/loss"]) if precision == "fp32" else float(g["out/loss"])
+    assert abs(float(out.loss) - ref_loss) <= tol * abs(ref_loss)
+    assert int(out.n_examples) == 32
+    assert np.abs(out.preds.cpu().numpy()[:, ::40, :] - g["out/preds_rows"]).max() <= (5e-4 if precision == "fp32" else 8e-2)
+    got = grads_of(model)
+    worst = check_full_fixture(g, got, names, tol, "64" if precision == "fp32" else "")
+    agree = float((out.preds.argmax(-1).cpu().numpy() == g["out/argmax"]).mean())
+    print(f"ctc_full_b32 {precision}: loss {float(out.loss):.4f} (ref {ref_loss:.4f}), worst grad-norm rel err {worst:.3e}, argmax agreement {agree:.4f} "
+          f"(reference bf16 autocast vs its fp32: loss {float(g['autocast/loss_rel']):.2e}, grads {float(g['autocast/grad_l2_max']):.2e}, argmax {float(g['autocast/argmax_agree']):.4f})")
+    if precision == "fp32":
+        assert agree >= 0.999     # random-init log-probs are near-uniform (min top-2 margin 7e-6 in the fixture): ties may flip
+    else:
+        assert agree >= float(g["autocast/argmax_agree"]) - 0.01      # no worse than the reference's own bf16 run
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ssl_full_size_config0_matches_reference(precision):
+    """BASELINE.json configs[0] at full size (16 x 100 bins x 668 neurons, mlm, temporal masker 0.3, Poisson-NLL on log rates,
+    5 x 1024 encoder, N = 668 decoder GEMM, recon_loss and masker kernels at size) against the unmodified reference."""
+    g = load("ssl_full_b16.npz")
+    cfg = ssl_full_cfg()
+    torch.manual_seed(1)
+    model = lb.NDT1(cfg, **SSL_KW, precision=precision).to(DEV).train()
+    names = [n for n, _ in model.named_parameters()]
+    assert names == list(g["names"])
+    assert np.array_equal(np.array([float(p.detach().double().sum()) for p in model.parameters()]), g["param_sum"])
+    batch = cuda_batch(O.synthetic_ssl_batch())
+    spikes0 = batch["spikes"].clone()
+    out = model(**batch, masker_draws=ssl_full_draws(g))
+    out.loss.backward()
+    assert torch.equal(batch["spikes"], spikes0)
+    assert int(out.n_examples) == int(g["out/n_examples"])
+    assert np.array_equal(out.mask[:, :, 0].cpu().numpy().astype(np.uint8), g["out/mask_bt"]) and int(out.mask.sum()) == int(g["out/mask_sum"])
+    tol = TOL[precision]
+    assert abs(float(out.loss) - float(g["out/loss"])) <= tol * abs(float(g["out/loss"]))
+    assert np.abs(out.preds.cpu().numpy()[:, ::10, ::4] - g["out/preds_rows"]).max() <= (5e-4 if precision == "fp32" else 8e-2)
+    # fp32: 1e-4 nominal.  bf16: the reference's OWN bf16-autocast run of this case is off by autocast/grad_l2_max (4.3e-2 > 2e-2)
+    # in the same metric, so the CUDA bf16 mode is held to max(2e-2, that figure) -- i.e. no worse than the reference's own bf16.
+    gtol = tol if precision == "fp32" else max(tol, float(g["autocast/grad_l2_max"]))
+    worst = check_full_fixture(g, grads_of(model), names, gtol)
+    print(f"ssl_full_b16 {precision}: loss {float(out.loss):.3f} (ref {float(g['out/loss']):.3f}), worst grad-norm rel err {worst:.3e}, bound {gtol:.3e}")
