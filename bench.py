@@ -29,11 +29,13 @@ METRIC = "ndt1_ctc_train_trials_per_sec"
 
 
 def load_peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written for this pod's B200s), else the profiling recipe's fallback."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return d.get("bf16_tflops_sustained", 1324.9), d.get("hbm_gbs", 6551.7), "measured"
-    return 1400.0, 6650.0, "fallback"
+        return {"bf16_burst": d.get("bf16_tflops", 1620.8), "bf16_sustained": d.get("bf16_tflops_sustained", 1324.9),
+                "hbm": d.get("hbm_gbs", 6551.7), "source": "MEASURED_PEAKS.json"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
@@ -99,22 +101,117 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
-# --------------------------------------------------------------------------- reference arm / cpu baseline (oracle port)
-def cpu_train_steps(n_trials: int, steps: int, warmup: int):
-    """The reference algorithm (oracle/ndt1_oracle.py, validated against the unmodified reference) on the
-    host CPU: train-mode forward + autograd backward + AdamW on `n_trials` trials per step."""
+# --------------------------------------------------------------------------- the synthetic workload (shared by every arm)
+def make_host_batch(B, T, N, seed, fixed_length=False):
+    """BASELINE.md section 3 inputs for configs[1], generated WITHOUT the oracle (the product path never imports oracle/)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    spikes = torch.randn(B, T, N, generator=g)
+    lens = torch.randint(int(0.6 * T), T + 1, (B,), generator=g)
+    lens[0] = T
+    if fixed_length:                      # SURVEY 8(d): the all-full-length variant (no padded rows)
+        lens[:] = T
+    t = torch.arange(T)[None, :]
+    mask = (t < lens[:, None]).to(torch.int64)
+    spikes = spikes * mask[:, :, None]
+    ts = t.expand(B, T) * mask
+    tl = torch.randint(20, 61, (B,), generator=g)
+    S = int(tl.max())
+    tg = torch.randint(1, 41, (B, S), generator=g) * (torch.arange(S)[None, :] < tl[:, None])
+    return dict(spikes=spikes, spikes_mask=mask, spikes_timestamp=ts.contiguous(), spikes_lengths=lens, targets=tg, targets_lengths=tl)
+
+
+# --------------------------------------------------------------------------- the UNMODIFIED reference (baseline/_ref) on CPU or under torch-CUDA
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_status():
+    """(usable, why): baseline/_ref must hold the reference files byte for byte (tools/install_reference.py manifest)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import install_reference as ir
+        if not os.path.isdir(REF_DIR):
+            return False, "baseline/_ref is absent (run tools/install_reference.py in the build container)"
+        if not ir.verify(REF_DIR):
+            return False, "baseline/_ref does not match baseline/reference_manifest.json"
+        return True, "baseline/_ref verified against the sha256 manifest of /root/reference"
+    except Exception as e:                                     # pragma: no cover
+        return False, f"reference check failed: {e}"
+
+
+_REF = {}
+
+
+def import_reference():
+    """The reference's own modules, imported from baseline/_ref (CWD must be the tree: DEFAULT_CONFIG is CWD-relative, models/ndt1.py:17)."""
+    if _REF:
+        return _REF
+    os.chdir(REF_DIR)
+    sys.path.insert(0, REF_DIR)
+    import scipy.signal
+    import scipy.signal.windows
+    if not hasattr(scipy.signal, "gaussian"):                   # scipy >= 1.13 dropped the alias used at models/ndt1.py:87
+        scipy.signal.gaussian = scipy.signal.windows.gaussian
+    from utils.config_utils import update_config
+    from models.ndt1 import NDT1
+    _REF.update(update_config=update_config, NDT1=NDT1)
+    return _REF
+
+
+def reference_train_steps(device, n_trials, steps, warmup, autocast=None, budget_s=None, seed=1):
+    """The reference's training step (models/trainer.py:336-343: forward, backward, AdamW step, zero_grad) on its own NDT1 built
+    from its own configs/trainer_ctc_ndt1.yaml, train mode (dropout 0.4 / 0.2, noise on), on the synthetic batch of this bench.
+    Returns (trials/s from the MEDIAN step, median seconds, steps actually timed)."""
+    import torch
+    R = import_reference()
+    os.chdir(REF_DIR)                                           # (configs/*.yaml are CWD-relative in the reference)
+    cfg = R["update_config"]("configs/trainer_ctc_ndt1.yaml", None)
+    torch.manual_seed(1)
+    model = R["NDT1"](cfg.model, **cfg.method.model_kwargs).to(device).train()
+    os.chdir(ROOT)
+    o = cfg.optimizer
+    opt = torch.optim.AdamW(model.parameters(), lr=o.lr, weight_decay=o.wd, eps=o.eps)
+    batch = {k: v.to(device) for k, v in make_host_batch(n_trials, T_BINS, N_CH, seed).items()}
+    cuda = torch.device(device).type == "cuda"
+    times, t_start = [], time.perf_counter()
+    for i in range(warmup + steps):
+        if cuda:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        b = {k: v.clone() for k, v in batch.items()}            # (the module may mutate its input, SURVEY 8b)
+        if autocast is not None:
+            with torch.autocast(torch.device(device).type, dtype=autocast):
+                out = model(**b)
+        else:
+            out = model(**b)
+        out.loss.backward()
+        opt.step()
+        opt.zero_grad()
+        if cuda:
+            torch.cuda.synchronize()
+        else:
+            float(out.loss)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+            if budget_s is not None and len(times) >= 3 and time.perf_counter() - t_start > budget_s:
+                break
+    times.sort()
+    med = times[len(times) // 2]
+    return n_trials / med, med, len(times)
+
+
+def port_train_steps(n_trials: int, steps: int, warmup: int):
+    """Fallback when baseline/_ref is absent: the oracle port of the reference algorithm (oracle/ndt1_oracle.py) on the host CPU."""
     import torch
     from oracle import ndt1_oracle as O
     from llm_bci_b200.config import default_trainer_config
     from llm_bci_b200.ndt1 import NDT1
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     tr = default_trainer_config()
     torch.manual_seed(1)
     shell = NDT1(tr.model, **tr.method.model_kwargs)          # parameter container only (CPU); no kernels involved
     params = {k: v.detach().clone().requires_grad_(True) for k, v in shell.state_dict().items()}
     opt = torch.optim.AdamW(list(params.values()), lr=1e-3, weight_decay=5e-5, eps=1e-8)
-    batch = O.synthetic_ctc_batch(B=n_trials, T=T_BINS, N=N_CH, seed=1)
+    batch = make_host_batch(n_trials, T_BINS, N_CH, 1)
     ds = {"torch_dropout": {"embed": 0.2, "transformer": 0.4}}
     times = []
     for i in range(warmup + steps):
@@ -126,8 +223,25 @@ def cpu_train_steps(n_trials: int, steps: int, warmup: int):
         opt.step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    return n_trials / sec, sec, cores
+    times.sort()
+    med = times[len(times) // 2]
+    return n_trials / med, med, len(times)
+
+
+def cpu_baseline(steps, warmup, budget_s):
+    """The reference's CPU implementation of the path on ALL host cores, on the bench's own 32-trial batch."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ok, why = reference_status()
+    if ok:
+        v, sec, n = reference_train_steps("cpu", B_PER_GPU, steps, warmup, budget_s=budget_s)
+        kind, what = "reference", "unmodified reference module from baseline/_ref (models/ndt1.py:523-589 + AdamW, models/trainer.py:336-343)"
+    else:
+        v, sec, n = port_train_steps(B_PER_GPU, steps, warmup)
+        kind, what = "port", f"oracle port ({why})"
+    return {"value": v, "unit": "trials/s", "cores": cores, "kind": kind, "ms_per_step": sec * 1e3,
+            "sample": f"{B_PER_GPU} trials/step (the full configs[1] batch), {warmup} warm-up + {n} timed steps, median; {what}; torch CPU fp32, train mode"}
 
 
 WORKLOAD = ("NDT1 CTC train step (fwd+bwd+AdamW), BASELINE configs[1]: 32 trials x 1000 bins x 256 channels per GPU, "
@@ -135,22 +249,43 @@ WORKLOAD = ("NDT1 CTC train step (fwd+bwd+AdamW), BASELINE configs[1]: 32 trials
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, same config / metric / unit as
+    this repo's arm, every step the SAME 32-trial batch (bounded to ~4 minutes: fewer timed steps are reported as such)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 4
-    value, sec, cores = cpu_train_steps(n, args.steps, args.warmup)
+    cb = cpu_baseline(args.steps, max(1, min(args.warmup, 2)), budget_s=200.0)
+    import re
+    n_timed = int(re.search(r"\+ (\d+) timed", cb["sample"]).group(1))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "trials/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{n} trials per step on the host CPU (a bounded sample of the same workload)"},
-        "cpu_baseline": {"value": value, "unit": "trials/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} trials/step x {args.steps} steps, oracle port of the reference algorithm, torch CPU fp32"},
-        "e2e": {"value": value, "unit": "trials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "trials/s", "n_gpus": args.gpus, "steps": n_timed,
+        "steps_requested": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU, "parallelism": "host CPU, one process",
+                   "lengths": "U{600..1000} bins, right-padded (padded rows are computed, as in the reference)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "trials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_leg(dev):
+    """SURVEY 2.2 / BASELINE.md section 3: the kernel to beat is the reference module under PyTorch-eager on the SAME B200
+    (cuBLAS / SDPA / ATen; none of this repo's kernels), fp32 and bf16 autocast, same batch, fwd + bwd + AdamW."""
+    import torch
+    ok, why = reference_status()
+    if not ok:
+        return {"unavailable": why}
+    out = {"what": "unmodified reference NDT1 + torch.optim.AdamW under torch-CUDA eager on this GPU, same 32-trial batch, 3 warm-up + 10 timed steps, median"}
+    for name, ac in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        try:
+            v, sec, n = reference_train_steps(str(dev), B_PER_GPU, 10, 3, autocast=ac)
+            out[name] = {"value": v, "unit": "trials/s", "ms_per_step": sec * 1e3}
+        except Exception as e:                                 # the eager leg must never take the bench line down
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------- this repo's arm
@@ -170,23 +305,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _C.lib()
 
-    # synthetic batch generated WITHOUT the oracle (product path never imports oracle/)
-    g = torch.Generator().manual_seed(1 + rank)
     B, T, N = B_PER_GPU, T_BINS, N_CH
-    spikes = torch.randn(B, T, N, generator=g)
-    lens = torch.randint(int(0.6 * T), T + 1, (B,), generator=g)
-    lens[0] = T
-    if args.fixed_length:                      # the all-full-length variant (no padded rows)
-        lens[:] = T
+    host = make_host_batch(B, T, N, 1 + rank, args.fixed_length)
+    lens = host["spikes_lengths"]
     valid_row_frac = float(((lens - 32) // 4 + 1).sum()) / float(B * ((T - 32) // 4 + 1))    # stacked rows that are not padding
-    t = torch.arange(T)[None, :]
-    mask = (t < lens[:, None]).to(torch.int64)
-    spikes = spikes * mask[:, :, None]
-    ts = t.expand(B, T) * mask
-    tl = torch.randint(20, 61, (B,), generator=g)
-    S = int(tl.max())
-    tg = torch.randint(1, 41, (B, S), generator=g) * (torch.arange(S)[None, :] < tl[:, None])
-    host = dict(spikes=spikes, spikes_mask=mask, spikes_timestamp=ts.contiguous(), spikes_lengths=lens, targets=tg, targets_lengths=tl)
     host = {k: v.contiguous().pin_memory() for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
@@ -281,37 +403,82 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps, after=drain_e2e) / args.steps
     e2e_value = world * B / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel family (tcgen05 GEMM), events around every launch, extra steps
-    # (the weight-gradient stream is switched off here so that every launch is timed alone)
-    peak_tf, peak_gbs, peak_src = load_peaks()
+    # ---- roofline: CUDA events around EVERY launch of the library, on its own stream, over extra steps.  The weight-gradient
+    # stream and the overlapped optimizer are switched off here so that every launch is timed alone (its share of a real,
+    # overlapped step is what the ncu launch list under profiles/ shows).
+    peaks = load_peaks()
     L.ndt1_engine_set_overlap(model._engine, 0)
+    trainer.serialize = True
     step_resident()
     torch.cuda.synchronize()
-    L.ndt1_profile_gemm_begin()
     prof_steps = 3
+    _C.profile_begin()
     for _ in range(prof_steps):
         step_resident()
-    fl, pms, pn = _C.C.c_double(), _C.C.c_double(), _C.C.c_int64()
+    trainer.synchronize()
     torch.cuda.synchronize()
-    L.ndt1_profile_gemm_end(_C.C.byref(fl), _C.C.byref(pms), _C.C.byref(pn))
+    prof = _C.profile_end()
     L.ndt1_engine_set_overlap(model._engine, 1)
-    achieved = fl.value / (pms.value * 1e-3) / 1e12 if pms.value > 0 else 0.0
-    traffic = None                       # DRAM bytes per launch from the committed ncu capture of this same command (tools/gemm_traffic.py)
-    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    trainer.serialize = False
+
+    def family(pred):
+        rows = [r for r in prof if pred(r["name"])]
+        return {"launches": sum(r["launches"] for r in rows), "ms": sum(r["ms"] for r in rows), "flops": sum(r["flops"] for r in rows),
+                "bytes": sum(r["bytes"] for r in rows)}
+
+    def entry(kernel, f, bound):
+        if f["launches"] == 0 or f["ms"] <= 0:
+            return None
+        sec = f["ms"] * 1e-3
+        if bound == "tensor":
+            ach, peak, unit = f["flops"] / sec / 1e12, peaks["bf16_burst"], "TFLOP/s"
+        else:
+            ach, peak, unit = f["bytes"] / sec / 1e9, peaks["hbm"], "GB/s"
+        return {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                "launches_per_step": f["launches"] / prof_steps, "us_per_launch": 1e3 * f["ms"] / f["launches"],
+                "ms_per_step": f["ms"] / prof_steps}
+
+    gemm = family(lambda n: "gemm_tc_kernel" in n)
+    achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    traffic, traffic_src = None, None     # DRAM bytes per launch: from the committed ncu --set full capture of this same command (tools/gemm_traffic.py)
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            traffic, traffic_src = json.load(open(tpath)).get("dram_bytes_per_launch"), "profiles/" + name
+            break
+    gemm_ms_step = gemm["ms"] / prof_steps
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMA bf16 GEMM, all shapes of the step)", "achieved": achieved,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src + " sustained",
-                "launches_per_step": pn.value / prof_steps, "gemm_ms_per_step": pms.value / prof_steps,
-                "gemm_share_of_step": (pms.value / prof_steps) / ms_step,
-                "step_tensor_frac": (B * FLOP_PER_TRIAL / (ms_step * 1e-3) / 1e12) / peak_tf}
+                "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
+                "peak_source": peaks["source"] + " burst (each launch is timed alone between events)",
+                "peak_sustained": peaks["bf16_sustained"], "frac_sustained": achieved / peaks["bf16_sustained"],
+                "traffic": traffic, "traffic_source": traffic_src,
+                "launches_per_step": gemm["launches"] / prof_steps, "gemm_ms_per_step": gemm_ms_step,
+                "gemm_share_of_step": gemm_ms_step / ms_step,
+                "step_tensor_frac": (B * FLOP_PER_TRIAL / (ms_step * 1e-3) / 1e12) / peaks["bf16_burst"],
+                "step_tensor_frac_sustained": (B * FLOP_PER_TRIAL / (ms_step * 1e-3) / 1e12) / peaks["bf16_sustained"]}
+    more = [entry("attn_tc_fwd_kernel (tcgen05 attention forward, algorithmic 2 contractions)", family(lambda n: "attn_tc_fwd" in n), "tensor"),
+            entry("attn_tc_bwd_q_kernel (dP, dQ; recomputed S not counted)", family(lambda n: "attn_tc_bwd_q" in n), "tensor"),
+            entry("attn_tc_bwd_kv2_kernel (dV, dK; recomputed S, dP not counted)", family(lambda n: "attn_tc_bwd_kv" in n), "tensor"),
+            entry("attention, all three kernels", family(lambda n: "attn_tc_" in n), "tensor"),
+            entry("ln_fwd_rows_kernel", family(lambda n: "ln_fwd" in n), "hbm"),
+            entry("ln_bwd_rows_kernel", family(lambda n: "ln_bwd" in n), "hbm"),
+            entry("adamw_fused_kernel", family(lambda n: "adamw_fused" in n), "hbm"),
+            entry("smooth_noise_vec_kernel", family(lambda n: "smooth_noise" in n), "hbm"),
+            entry("ctc_kernel + ctc_posterior_kernel (latency-bound sweeps)", family(lambda n: n.startswith("ctc_") or "::ctc_" in n), "hbm"),
+            entry("colsum8_kernel", family(lambda n: "colsum8" in n), "hbm"),
+            entry("grad_prep_kernel", family(lambda n: "grad_prep" in n), "hbm")]
+    more = [m for m in more if m is not None]
+    all_ms = sum(r["ms"] for r in prof) / prof_steps
+    kernel_table = sorted(({"kernel": r["name"][:90], "launches_per_step": r["launches"] / prof_steps, "ms_per_step": r["ms"] / prof_steps}
+                           for r in prof), key=lambda r: -r["ms_per_step"])[:12]
 
     if rank == 0:
-        cpu = None
+        cpu, eager = None, None
         if world == 1 and not args.no_cpu_baseline:
-            v, sec, cores = cpu_train_steps(8, 2, 1)
-            cpu = {"value": v, "unit": "trials/s", "cores": cores, "kind": "port",
-                   "sample": "8 trials/step, 1 warm-up + 2 timed steps of the oracle port (torch CPU fp32, train mode)"}
+            # free the GPU arm before the host legs: the eager leg needs HBM, the CPU leg the cores
+            cpu = cpu_baseline(steps=3, warmup=1, budget_s=120.0)
+            if not args.no_gpu_eager:
+                eager = gpu_eager_leg(dev)
         line = {
             "metric": METRIC, "value": value, "unit": "trials/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -324,7 +491,10 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "trials/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "roofline_more": more,
+            "kernel_ms_per_step_alone": {"sum": all_ms, "top": kernel_table},
             "cpu_baseline": cpu,
+            "gpu_eager": eager,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -338,6 +508,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-under-torch-CUDA comparison leg")
     ap.add_argument("--fixed-length", action="store_true", help="every trial 1000 bins long (no padding)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NDT1_ABI_VERSION 2
+#define NDT1_ABI_VERSION 3
 
 /* activations (transformers ACT2FN names used by configs/ndt1.yaml) */
 enum { NDT1_ACT_IDENTITY = 0, NDT1_ACT_SOFTSIGN = 1, NDT1_ACT_GELU = 2, NDT1_ACT_RELU = 3 };
@@ -249,6 +249,18 @@ int64_t ndt1_engine_launch_count(const ndt1_engine* e);
 int ndt1_profile_gemm_begin(void);
 int ndt1_profile_gemm_end(double* flops, double* ms, int64_t* launches);
 int64_t ndt1_launch_counter(void);
+/* The same for EVERY kernel of the library, grouped by kernel (template instantiations separately): between begin and end
+ * each launch is bracketed by CUDA events on the stream it is launched on.  `flops` / `bytes` are the ALGORITHMIC figures the
+ * launchers attach (0 where a kernel has none): GEMMs 2 M N K; attention 2 (forward) + 2 + 2 (backward) contractions of
+ * 2 L^2 d per head (recomputed scores are not counted); LayerNorm, AdamW, smoothing, CTC, reductions their one pass over
+ * the operands.  ndt1_profile_end writes at most `capacity` entries and their number to *n_out. */
+typedef struct ndt1_profile_entry {
+  char name[160];
+  int64_t launches;
+  double ms, flops, bytes;
+} ndt1_profile_entry;
+int ndt1_profile_begin(void);
+int ndt1_profile_end(ndt1_profile_entry* out, int capacity, int* n_out);
 /* Debugging aid (tools/attn_timeline.py): the tensor-core attention kernels write per-CTA phase timestamps
  * (32 uint64 per CTA, %globaltimer ns) into buf; NULL switches it off. */
 int ndt1_debug_attention_timeline(uint64_t* buf);

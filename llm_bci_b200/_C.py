@@ -13,7 +13,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libndt1_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LAYERS = 32
 MAX_DAYS = 64
 
@@ -56,6 +56,10 @@ class Batch(C.Structure):
                                   "targets", "targets_lengths", "recon_targets", "targets_mask")] + [
         ("B", C.c_int32), ("T", C.c_int32), ("S", C.c_int32), ("training", C.c_int32), ("need_backward", C.c_int32), ("encoder_only", C.c_int32),
         ("seed", C.c_uint64)]
+
+
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 160), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
 
 
 class Outputs(C.Structure):
@@ -101,6 +105,8 @@ PROTOTYPES = {
     "ndt1_profile_gemm_begin": (_i, []),
     "ndt1_profile_gemm_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ndt1_launch_counter": (_i64, []),
+    "ndt1_profile_begin": (_i, []),
+    "ndt1_profile_end": (_i, [C.POINTER(ProfileEntry), _i, C.POINTER(C.c_int)]),
     "ndt1_dropout_scales": (_i, [_p, _i64, _f, _u64, _u64, _p]),
 }
 
@@ -149,3 +155,16 @@ def ptr(t) -> int:
 def stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def profile_begin() -> None:
+    check(lib().ndt1_profile_begin(), "ndt1_profile_begin")
+
+
+def profile_end(capacity: int = 256):
+    """[{name, launches, ms, flops, bytes}] per kernel of the library since profile_begin() (CUDA events around every launch)."""
+    ent = (ProfileEntry * capacity)()
+    n = C.c_int(0)
+    check(lib().ndt1_profile_end(ent, capacity, C.byref(n)), "ndt1_profile_end")
+    return [dict(name=ent[i].name.decode(), launches=int(ent[i].launches), ms=float(ent[i].ms), flops=float(ent[i].flops), bytes=float(ent[i].bytes))
+            for i in range(n.value)]

@@ -1,6 +1,7 @@
 // C-ABI wrappers of the stand-alone operators declared in include/ndt1_b200.h.
 #include "../../include/ndt1_b200.h"
 #include "kernels.cuh"
+#include <string.h>
 
 extern "C" {
 
@@ -135,12 +136,18 @@ __global__ void dropout_scales_kernel(float* out, long long n, float p, unsigned
 }
 }  // namespace
 
-int ndt1_profile_gemm_begin(void) { return gemm_tc_profile_begin(); }
-int ndt1_profile_gemm_end(double* flops, double* ms, int64_t* launches) {
-  long long n = 0;
-  const int rc = gemm_tc_profile_end(flops, ms, &n);
-  *launches = n;
-  return rc;
+int ndt1_profile_gemm_begin(void) { return ndt1_profile_begin(); }
+int ndt1_profile_gemm_end(double* flops, double* ms, int64_t* launches) {   // the tensor-core GEMM rows of the generic profile
+  NDT1_REQUIRE(flops && ms && launches, "profile_gemm_end: null argument");
+  static ndt1_profile_entry ent[256];
+  int n = 0;
+  NDT1_TRY(ndt1_profile_end(ent, 256, &n));
+  *flops = 0; *ms = 0; *launches = 0;
+  for (int i = 0; i < n; ++i)
+    if (strncmp(ent[i].name, "gemm_tc_kernel", 14) == 0 || strstr(ent[i].name, "::gemm_tc_kernel")) {
+      *flops += ent[i].flops; *ms += ent[i].ms; *launches += ent[i].launches;
+    }
+  return 0;
 }
 int64_t ndt1_launch_counter(void) { return g_ndt1_launches; }
 int ndt1_debug_gemm_timeline(uint64_t* buf) { gemm_tc_set_timeline((unsigned long long*)buf); return 0; }

@@ -889,6 +889,8 @@ int k_attention_tc_fwd(const AttnParams& p, cudaStream_t stream) {
   CUtensorMap mo, mod;
   NDT1_TRY(tc_make_map(o, 64, 128, &mo));
   NDT1_TRY(tc_make_map(od, 64, 128, &mod));
+  const double mm = 2.0 * p.B * p.nh * (double)p.L * p.L * HD;       // FLOPs of one L x L x d contraction over all heads
+  if (g_ndt1_prof_on) ndt1_prof_note(2 * mm, 0.0);                  // forward: Q K^T and P V
   ndt1_launch(attn_tc_fwd_kernel, grid, NTHREADS, SMEM_FWD, stream, m128, m256, mo, mod, a);
   NDT1_CHECK_LAUNCH();
   return 0;
@@ -916,6 +918,8 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream) {
   NDT1_TRY(tc_make_map(g, 64, 128, &mdq));
   NDT1_TRY(tc_make_map(o, 64, 128, &mo));
   // query side first: it also forms delta = rowsum(dO * O), which the key side reads
+  const double mm = 2.0 * p.B * p.nh * (double)p.L * p.L * HD;
+  if (g_ndt1_prof_on) ndt1_prof_note(2 * mm, 0.0);                  // algorithmic: dP = dO V^T and dQ = dS K (the recomputed S is not counted)
   ndt1_launch(attn_tc_bwd_q_kernel, grid, BQ_THREADS, SMEM_BQ, stream, m128, m256, mdo, mo, mdq, a);
   NDT1_CHECK_LAUNCH();
   static const bool old_kv = getenv("NDT1_ATTN_BWD_KV1") && getenv("NDT1_ATTN_BWD_KV1")[0] == '1';
@@ -925,6 +929,7 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream) {
     CUtensorMap m64, mdo64;
     NDT1_TRY(tc_make_map(q, 64, KV2_CH, &m64));
     NDT1_TRY(tc_make_map(d, 64, KV2_CH, &mdo64));
+    if (g_ndt1_prof_on) ndt1_prof_note(2 * mm, 0.0);                // algorithmic: dV = P~^T dO and dK = dS^T Q
     ndt1_launch(attn_tc_bwd_kv2_kernel, grid, KV2_THREADS, SMEM_BKV2, stream, m128, m64, mdo64, mdq, a);
   }
   NDT1_CHECK_LAUNCH();

@@ -61,6 +61,13 @@ __device__ __forceinline__ void pdl_grid_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 bool ndt1_pdl_enabled();
+// Measurement (bench.py `roofline` / `roofline_more`): while ndt1_profile_begin() .. ndt1_profile_end() is active every launch
+// of the library is bracketed by CUDA events on ITS OWN stream and grouped by kernel; a launcher may attach the algorithmic
+// FLOPs / bytes of the launch it is about to make with ndt1_prof_note (consumed by the next launch on this thread).
+extern bool g_ndt1_prof_on;
+int ndt1_prof_before(const void* func, cudaStream_t stream);
+void ndt1_prof_after(int rec, cudaStream_t stream);
+void ndt1_prof_note(double flops, double bytes);
 template <typename... KArgs, typename... Args>
 static inline cudaError_t ndt1_launch_cluster(void (*kernel)(KArgs...), int cluster_x, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                               Args&&... args) {
@@ -79,7 +86,11 @@ static inline cudaError_t ndt1_launch_cluster(void (*kernel)(KArgs...), int clus
     ++n;
   }
   cfg.attrs = at; cfg.numAttrs = n;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (!g_ndt1_prof_on) return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  const int rec = ndt1_prof_before((const void*)kernel, stream);
+  const cudaError_t rc = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  ndt1_prof_after(rec, stream);
+  return rc;
 }
 template <typename... KArgs, typename... Args>
 static inline cudaError_t ndt1_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

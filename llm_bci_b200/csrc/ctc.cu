@@ -401,11 +401,14 @@ static int ctc_launch(const CtcParams& p, size_t smem, cudaStream_t stream) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(ctc_kernel<FAST, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
+  // log-probs in, alpha + beta rows out (latency-bound: 2 L dependent steps per trial)
+  if (g_ndt1_prof_on) ndt1_prof_note(0.0, (double)p.B * p.L * (4.0 * p.V + 8.0 * (2 * p.S + 1)));
   ndt1_launch(ctc_kernel<FAST, SPT>, p.B, kCtcWarps * 32, smem, stream, p);
   NDT1_CHECK_LAUNCH();
   if (p.dlogits) {
     const int LXA = SPT * 32;
     const size_t smem2 = (size_t)(kCtcWarps * LXA + (LXA + 2) + (p.V + 1) + (p.S > 0 ? p.S : 1)) * sizeof(float);
+    if (g_ndt1_prof_on) ndt1_prof_note(0.0, (double)p.B * p.L * (8.0 * p.V + 8.0 * (2 * p.S + 1)));   // alpha, beta, log-probs in; d(logits) out
     ndt1_launch(ctc_posterior_kernel<FAST, SPT>, dim3(ndt1_cdiv(p.L, kPostFrames), p.B), kCtcWarps * 32, smem2, stream, p);
     NDT1_CHECK_LAUNCH();
   }

@@ -185,6 +185,7 @@ int k_smooth_noise(const float* x, float* out, int B, int T, int N, const float*
   p.use_philox = use_philox; p.seed = seed;
   if (K == 13 && N % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 && (!white || ((uintptr_t)white & 15) == 0)) {
     dim3 grid(ndt1_cdiv(N / 4, 64), ndt1_cdiv(ndt1_cdiv(T, SMV_TT), 4), B);     // the reference's default: gaussian(1 + 6 sd, sd = 2)
+    if (g_ndt1_prof_on) ndt1_prof_note(0.0, (double)B * T * N * 8);     // fp32 in, fp32 out
     ndt1_launch(smooth_noise_vec_kernel<13>, grid, 256, 0, stream, p);
     NDT1_CHECK_LAUNCH();
     return 0;
@@ -518,6 +519,7 @@ int k_colsum(const T* in, float* out, long long rows, int cols, long long ld, cu
     int chunks8 = (int)(rows / 128); if (chunks8 < 1) chunks8 = 1;
     const int gx = ndt1_cdiv(cols, 256);
     while (chunks8 > 1 && (long long)chunks8 * gx > 148 * 4) --chunks8;
+    if (g_ndt1_prof_on) ndt1_prof_note(0.0, (double)rows * cols * sizeof(T));
     ndt1_launch(colsum8_kernel<T>, dim3(gx, chunks8), block, 0, stream, in, out, rows, cols, ld);
     NDT1_CHECK_LAUNCH();
     return 0;
@@ -574,6 +576,7 @@ int k_grad_prep(const float* g, T* out, long long rows, int cols, float drop_p, 
   if (rows * cols == 0) return 0;
   const long long work = rows * (cols / 4);
   const int blocks = (int)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16);
+  if (g_ndt1_prof_on) ndt1_prof_note(0.0, (double)rows * cols * (4 + sizeof(T)));
   ndt1_launch(grad_prep_kernel<T>, blocks, 256, 0, stream, g, out, rows, cols, drop_p, seed, stream_id, dtab, idx, tab_ld, rows_per_b > 0 ? rows_per_b : 1,
                                                   idx_stride, prefix);
   NDT1_CHECK_LAUNCH();
@@ -719,6 +722,8 @@ int k_adamw_fused(float* p, float* g, float* m, float* v, long long n, float lr,
   const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
   const long long n4 = n / 4;
   const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  // parameter, gradient, two moments read; parameter, two moments (+ cleared gradient, + bf16 shadow) written
+  if (g_ndt1_prof_on) ndt1_prof_note(0.0, (double)n * (16 + 12 + (zero_grad ? 4 : 0) + (shadow ? 2 : 0)));
   ndt1_launch(adamw_fused_kernel, blocks, 256, 0, stream, (float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, lr, b1, b2, eps, wd, bc1,
                                                  1.0f / sqrtf(bc2), gscale, (uint2*)shadow, zero_grad);
   NDT1_CHECK_LAUNCH();

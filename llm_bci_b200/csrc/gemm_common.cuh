@@ -126,5 +126,3 @@ int gemm_simt_launch(const GemmProblem& p, int in_bf16, cudaStream_t stream);
 int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream);
 int gemm_tc_init();
 void gemm_tc_set_timeline(unsigned long long* buf);   // debugging: per-CTA phase timestamps (16 u64 per CTA), null = off
-int gemm_tc_profile_begin();
-int gemm_tc_profile_end(double* flops, double* ms, long long* launches);

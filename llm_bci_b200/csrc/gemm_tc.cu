@@ -692,12 +692,7 @@ struct MapKeyHash {
 };
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// optional per-launch timing of the tensor-core GEMM (bench.py roofline): CUDA events on the launch stream
-struct ProfRec { cudaEvent_t e0, e1; double flops; };
 unsigned long long* g_gemm_dbg = nullptr;
-bool g_prof_on = false;
-std::vector<ProfRec> g_prof;
-size_t g_prof_used = 0;
 
 int make_map(const GemmOperand& o, int box_cols, int box_rows, CUtensorMap* out) {
   NDT1_REQUIRE(((uintptr_t)o.ptr & 15) == 0, "gemm_tc: operand pointer not 16-byte aligned");
@@ -735,20 +730,10 @@ int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp
   }
   const int units = g_num_sms / CTAS;
   const int grid = CTAS * (tp.total_tiles < units ? tp.total_tiles : units);
-  ProfRec* rec = nullptr;
-  if (g_prof_on) {
-    if (g_prof_used == g_prof.size()) {
-      ProfRec r; r.flops = 0;
-      NDT1_CUDA_CHECK(cudaEventCreate(&r.e0)); NDT1_CUDA_CHECK(cudaEventCreate(&r.e1));
-      g_prof.push_back(r);
-    }
-    rec = &g_prof[g_prof_used++];
-    rec->flops = 2.0 * tp.M * (double)tp.N * (double)tp.nchunk * tp.chunk_k_valid * (tp.mode == GEMM_TN ? 1 : tp.nb_out);
-    NDT1_CUDA_CHECK(cudaEventRecord(rec->e0, stream));
-  }
+  if (g_ndt1_prof_on)      // algorithmic FLOPs of this launch (bench.py roofline): 2 M N K over all trials / chunks
+    ndt1_prof_note(2.0 * tp.M * (double)tp.N * (double)tp.nchunk * tp.chunk_k_valid * (tp.mode == GEMM_TN ? 1 : tp.nb_out), 0.0);
   NDT1_CUDA_CHECK(ndt1_launch_cluster(gemm_tc_kernel<BN, MODE, CTAS, EPI>, CTAS, dim3(grid), dim3(kThreads), SMEM, stream, ma, mb, tp));
   NDT1_CHECK_LAUNCH();
-  if (rec) NDT1_CUDA_CHECK(cudaEventRecord(rec->e1, stream));
   return 0;
 }
 
@@ -901,21 +886,5 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   return launch_mode<GEMM_NT>(bn, ctas, ma, mb, tp, stream);
 }
 
-// ---- profiling hooks (C ABI wrappers in api.cu) ----
+// ---- debugging hook (C ABI wrapper in api.cu) ----
 void gemm_tc_set_timeline(unsigned long long* buf) { g_gemm_dbg = buf; }
-int gemm_tc_profile_begin() {
-  g_prof_used = 0; g_prof_on = true;
-  return 0;
-}
-int gemm_tc_profile_end(double* flops, double* ms, long long* launches) {
-  g_prof_on = false;
-  double f = 0, t = 0;
-  for (size_t i = 0; i < g_prof_used; ++i) {
-    NDT1_CUDA_CHECK(cudaEventSynchronize(g_prof[i].e1));
-    float m = 0;
-    NDT1_CUDA_CHECK(cudaEventElapsedTime(&m, g_prof[i].e0, g_prof[i].e1));
-    f += g_prof[i].flops; t += m;
-  }
-  *flops = f; *ms = t; *launches = (long long)g_prof_used;
-  return 0;
-}

@@ -370,6 +370,7 @@ int k_layernorm_fwd(const float* x, const float* gamma, const float* beta, T* y,
     long long nb = (rows + LNF_ROWS - 1) / LNF_ROWS;
     const long long cap = (long long)g_sms() * (threads <= 256 ? 4 : 1);
     if (nb > cap) nb = cap;
+    if (g_ndt1_prof_on) ndt1_prof_note(0.0, (double)rows * H * (4 + sizeof(T)));     // x in (fp32), y out
     if (threads <= 256) ndt1_launch(ln_fwd_rows_kernel<T, 256>, (int)nb, threads, 0, stream, x, gamma, beta, y, mean, rstd, rows, H, eps);
     else ndt1_launch(ln_fwd_rows_kernel<T, 1024>, (int)nb, threads, 0, stream, x, gamma, beta, y, mean, rstd, rows, H, eps);
     NDT1_CHECK_LAUNCH();
@@ -393,6 +394,8 @@ int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float
     long long nbr = (rows + LNG_ROWS - 1) / LNG_ROWS;
     const long long cap = (long long)sms * (threads <= 256 ? 2 : 1);
     if (nbr > cap) nbr = cap;
+    // dy in, x in (fp32), residual gradient in + out (fp32), the next GEMM pair's operand out
+    if (g_ndt1_prof_on) ndt1_prof_note(0.0, (double)rows * H * (sizeof(T) + 4 + 8 + (out_lp ? sizeof(T) : 0)));
     if (threads <= 256)
       ndt1_launch(ln_bwd_rows_kernel<T, 256>, (int)nbr, threads, 0, stream, dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed, stream_id, rows, H,
                                                                     dgamma, dbeta, out_lp ? colsum_out : nullptr);

@@ -125,6 +125,7 @@ class DataParallelTrainer:
             model.set_weight_shadow(self.flat_param, self.shadow)
         self.buckets = [(st, spans[st][0], spans[st][1]) for st in sorted(spans)]   # completion order
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self.serialize = False     # measurement aid: run the exchange and the optimizer AFTER the backward instead of under it
         model._param_stream = self.comm_stream
         self._ones = torch.full((), self._loss_scale, dtype=torch.float32, device=dev)     # d(loss) handed to the backward
 
@@ -190,6 +191,8 @@ class DataParallelTrainer:
         lr = float(self.current_lr())      # schedule(updates done), then count this update (1-based for Adam's bias correction)
         self.step_count += 1
         L = _C.lib()
+        if self.serialize:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm_stream):
             for stage, lo, hi in self.buckets:
                 _C.check(L.ndt1_engine_wait_stage(m._engine, stage, self.comm_stream.cuda_stream), "ndt1_engine_wait_stage")
