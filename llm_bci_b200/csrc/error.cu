@@ -91,16 +91,18 @@ extern "C" int ndt1_profile_end(ndt1_profile_entry* out, int capacity, int* n_ou
     int st = 0;
     char* dem = abi::__cxa_demangle(mangled, nullptr, nullptr, &st);
     const char* nm = (st == 0 && dem) ? dem : mangled;
-    // keep the kernel name and its template arguments, drop the parameter list
-    size_t len = strlen(nm);
+    // keep the kernel name and its template arguments; drop "void ", the anonymous-namespace qualifier and the parameter list
+    const char* start = nm;
+    if (strncmp(start, "void ", 5) == 0) start += 5;
+    static const char kAnon[] = "(anonymous namespace)::";
+    if (strncmp(start, kAnon, sizeof(kAnon) - 1) == 0) start += sizeof(kAnon) - 1;
+    size_t len = strlen(start);
     int depth = 0;
     for (size_t k = 0; k < len; ++k) {
-      if (nm[k] == '<') ++depth;
-      else if (nm[k] == '>') --depth;
-      else if (nm[k] == '(' && depth == 0) { len = k; break; }
+      if (start[k] == '<') ++depth;
+      else if (start[k] == '>') --depth;
+      else if (start[k] == '(' && depth == 0) { len = k; break; }
     }
-    const char* start = nm;
-    if (len > 5 && strncmp(nm, "void ", 5) == 0) { start = nm + 5; len -= 5; }
     if (len >= sizeof(e.name)) len = sizeof(e.name) - 1;
     memcpy(e.name, start, len);
     free(dem);

@@ -61,6 +61,20 @@ def onecycle_cos_lr(step: int, total_steps: int, max_lr: float, pct_start: float
     return cos(max_lr, min_lr, (step - up_end) / (down_end - up_end))
 
 
+def onecycle_cos_beta1(step: int, total_steps: int, pct_start: float, base_momentum: float = 0.85, max_momentum: float = 0.95) -> float:
+    """torch OneCycleLR's default ``cycle_momentum=True`` ALSO drives Adam's beta1 (trainer.py:239-246 builds it with the
+    defaults): max_momentum -> base_momentum while the rate climbs, back to max_momentum while it anneals (cosine)."""
+    up_end = float(pct_start * total_steps) - 1.0
+    down_end = float(total_steps) - 1.0
+
+    def cos(a, b, pct):
+        return b + (a - b) / 2.0 * (math.cos(math.pi * pct) + 1.0)
+
+    if step <= up_end or up_end >= down_end:
+        return cos(max_momentum, base_momentum, step / up_end) if up_end > 0 else base_momentum
+    return cos(base_momentum, max_momentum, (step - up_end) / (down_end - up_end))
+
+
 def linear_warmup_lr(step: int, total_steps: int, lr: float, warmup_pct: float) -> float:
     """transformers.get_linear_schedule_with_warmup value at optimizer step ``step`` (trainer.py:233-238): linear ramp over
     round(warmup_pct * total_steps) steps, then linear decay to 0 at total_steps."""
@@ -143,6 +157,12 @@ class DataParallelTrainer:
             return self.lr * (self.gamma ** self.epoch)
         return self.lr
 
+    def current_beta1(self) -> float:
+        """Adam's beta1 of the NEXT update: cycled by the OneCycle ("cosine") schedule like the reference's, constant otherwise."""
+        if self.scheduler == "cosine":
+            return onecycle_cos_beta1(self.step_count, self.total_steps, self.warmup_pct)
+        return self.betas[0]
+
     def end_epoch(self) -> None:
         """Call once after every pass over the training set (models/trainer.py:418-419)."""
         self.epoch += 1
@@ -189,6 +209,7 @@ class DataParallelTrainer:
             self.optimizer_step()
             return out
         lr = float(self.current_lr())      # schedule(updates done), then count this update (1-based for Adam's bias correction)
+        self._beta1 = float(self.current_beta1())
         self.step_count += 1
         L = _C.lib()
         if self.serialize:
@@ -205,7 +226,7 @@ class DataParallelTrainer:
         return out
 
     def _adamw(self, lo: int, hi: int, lr: float, stream: int) -> None:
-        b1, b2 = self.betas
+        b1, b2 = getattr(self, "_beta1", self.betas[0]), self.betas[1]
         fp, bf = 4 * lo, 2 * lo
         _C.check(_C.lib().ndt1_adamw_step_fused(self.flat_param.data_ptr() + fp, self.flat_grad.data_ptr() + fp, self.exp_avg.data_ptr() + fp,
                                                 self.exp_avg_sq.data_ptr() + fp, hi - lo, lr, b1, b2, self.eps, self.wd, self.step_count,
@@ -215,5 +236,6 @@ class DataParallelTrainer:
     def optimizer_step(self) -> None:
         """AdamW over the whole arena on the current stream (for callers that drive forward_backward themselves)."""
         lr = float(self.current_lr())
+        self._beta1 = float(self.current_beta1())
         self.step_count += 1
         self._adamw(0, self.flat_param.numel(), lr, _C.stream_ptr())

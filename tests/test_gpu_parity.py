@@ -970,10 +970,11 @@ def test_ctc_full_size_b32_config1_matches_reference(precision):
     g = load("ctc_full_b32.npz")
     cfg, kw = full_ctc_cfg()
     torch.manual_seed(1)
-    model = lb.NDT1(cfg, **kw, precision=precision).to(DEV).train()
+    model = lb.NDT1(cfg, **kw, precision=precision)
     names = [n for n, _ in model.named_parameters()]
     assert names == list(g["names"])
-    assert np.array_equal(np.array([float(p.detach().double().sum()) for p in model.parameters()]), g["param_sum"])   # the reference's init, bit for bit
+    assert np.array_equal(np.array([float(p.detach().double().sum()) for p in model.parameters()]), g["param_sum"])   # the reference's init, bit for bit (summed on the CPU, like the fixture)
+    model = model.to(DEV).train()
     batch = cuda_batch(O.synthetic_ctc_batch(B=32, T=1000, N=256, seed=1))
     out = model(**batch)
     out.loss.backward()
@@ -1000,10 +1001,11 @@ def test_ssl_full_size_config0_matches_reference(precision):
     g = load("ssl_full_b16.npz")
     cfg = ssl_full_cfg()
     torch.manual_seed(1)
-    model = lb.NDT1(cfg, **SSL_KW, precision=precision).to(DEV).train()
+    model = lb.NDT1(cfg, **SSL_KW, precision=precision)
     names = [n for n, _ in model.named_parameters()]
     assert names == list(g["names"])
     assert np.array_equal(np.array([float(p.detach().double().sum()) for p in model.parameters()]), g["param_sum"])
+    model = model.to(DEV).train()
     batch = cuda_batch(O.synthetic_ssl_batch())
     spikes0 = batch["spikes"].clone()
     out = model(**batch, masker_draws=ssl_full_draws(g))

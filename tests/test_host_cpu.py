@@ -147,8 +147,11 @@ def test_onecycle_matches_torch():
     lin = torch.nn.Linear(1, 1)
     opt = torch.optim.AdamW(lin.parameters(), lr=1e-3)
     sch = torch.optim.lr_scheduler.OneCycleLR(opt, total_steps=50, max_lr=1e-3, pct_start=0.2, anneal_strategy="cos", div_factor=25)
+    from llm_bci_b200.trainer import onecycle_cos_beta1
     for step in range(50):
         assert abs(opt.param_groups[0]["lr"] - onecycle_cos_lr(step, 50, 1e-3, 0.2, 25)) < 1e-12
+        # OneCycleLR's default cycle_momentum=True also drives AdamW's beta1 (0.95 -> 0.85 -> 0.95)
+        assert abs(opt.param_groups[0]["betas"][0] - onecycle_cos_beta1(step, 50, 0.2)) < 1e-12
         opt.step()
         if step < 49:
             sch.step()
