@@ -52,7 +52,8 @@ int ndt1_abi_version(void);
  * taps: HOST pointer, K odd (0 = no smoothing).  white/offset: injected N(0,1)
  * draws (device) or NULL; with NULL and use_philox != 0 the kernel draws its own. */
 int ndt1_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps_host, int K, float white_sd,
-                      float offset_sd, const float* white, const float* offset, int use_philox, uint64_t seed, void* stream);
+                      float offset_sd, const float* white, const float* offset, int use_philox, uint64_t seed,
+                      const uint64_t* seed_ptr, void* stream);
 
 /* Masker.forward given its random draws, models/masker.py:44-104, in place on
  * spikes (B,T,N).  mask_draw has the mode's own shape ((B,T) temporal, (B,N)
@@ -104,8 +105,22 @@ int ndt1_layernorm_fwd(const float* x, const float* gamma, const float* beta, fl
 
 /* y = act(x W^T + b) in fp32 (CUDA cores) or bf16 tensor cores (tcgen05); x (M,K), W (N,K).
  * Replaces the nn.Linear calls of models/ndt1.py:130,140,219-221,247-257,494. */
-int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K, int act, int precision,
-                    void* workspace, size_t workspace_bytes, void* stream);
+int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* pre /* optional: x W^T + b before act */,
+                    int M, int N, int K, int act, int precision, void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of ndt1_linear_fwd (the projector MLP of the BCI coupler, models/bci.py:88-96,137-141, trains through it):
+ * g = dy * act'(saved) (saved = y for relu / softsign, the pre-activation for gelu);  db[n] += sum_m g;  dw (N,K) += g^T x;
+ * dx (M,K) = g W.  Any of dx / dw / db may be NULL.  Workspace: ndt1_linear_workspace_bytes (bf16 mode), M*N*4 + 256 (fp32). */
+int ndt1_linear_bwd(const float* dy, const float* x, const float* w, const float* saved, float* dx, float* dw, float* db, int M, int N,
+                    int K, int act, int precision, void* workspace, size_t workspace_bytes, void* stream);
+size_t ndt1_linear_workspace_bytes(int M, int N, int K);
+/* BCI.prepare_embeds, models/bci.py:143-166: out (B, La+Ls, W) = a[b, :split[b]] | ins[b] | a[b, split[b]:] per trial (or a
+ * constant row `fill` instead of ins: the -100 targets over the spike positions).  elem_size 4 (float32) or 8 (int64).
+ * ndt1_unsplice_rows is its backward for float32: the gradient of `out` routed back to a and ins.
+ * ndt1_stack_valid, models/bci.py:127-141: out (B, ceil(T / stacking)) = 1 where all `stacking` rows of the group are valid. */
+int ndt1_splice_rows(const void* a, const void* ins, const int64_t* split, void* out, int B, int La, int Ls, int W, int elem_size,
+                     int use_fill, double fill, void* stream);
+int ndt1_unsplice_rows(const float* dout, const int64_t* split, float* da, float* dins, int B, int La, int Ls, int W, void* stream);
+int ndt1_stack_valid(const int64_t* mask, int64_t* out, int B, int T, int stacking, void* stream);
 
 /* F.scaled_dot_product_attention with the reference's mask (models/ndt1.py:276-290, 30-41, 435-437),
  * bf16 in/out: qkv (B*L, 3H) packed q|k|v, out/out_drop (B*L, H) before/after the output dropout,
@@ -195,6 +210,8 @@ typedef struct {
   int32_t need_backward;          /* keep activations and loss gradients for ndt1_engine_backward */
   int32_t encoder_only;           /* stop after the encoder (NeuralEncoder.forward, models/ndt1.py:408-450): no head, no loss */
   uint64_t seed;                  /* Philox key of this step's dropout */
+  const uint64_t* seed_ptr;       /* optional: the key in DEVICE memory instead (read when the step executes, so a captured CUDA graph of
+                                   * the step is replayed with a new key by updating that word); NULL = use `seed` */
 } ndt1_batch;
 
 typedef struct {
@@ -261,6 +278,17 @@ typedef struct ndt1_profile_entry {
 } ndt1_profile_entry;
 int ndt1_profile_begin(void);
 int ndt1_profile_end(ndt1_profile_entry* out, int capacity, int* n_out);
+/* Events that cross the boundary of a CAPTURED step.  A training step (ndt1_smooth_noise + ndt1_engine_forward +
+ * ndt1_engine_backward) only enqueues work on the caller's stream and allocates nothing, so the caller may capture it into a
+ * CUDA graph (the per-step Philox key is then passed by device pointer: ndt1_batch.seed_ptr).  Work that stays OUTSIDE the graph
+ * -- the gradient exchange and the optimizer on their own stream -- is ordered against it with these events: when `stream` is
+ * being captured, ndt1_event_record / ndt1_stream_wait_event add EXTERNAL event nodes (cudaEventRecordExternal /
+ * cudaEventWaitExternal), which record / wait on the real event at every replay; otherwise they are plain cudaEventRecord /
+ * cudaStreamWaitEvent.  The engine records its gradient-stage events (ndt1_engine_wait_stage) the same way. */
+int ndt1_event_create(void** event);
+int ndt1_event_destroy(void* event);
+int ndt1_event_record(void* event, void* stream);
+int ndt1_stream_wait_event(void* stream, void* event);
 /* Debugging aid (tools/attn_timeline.py): the tensor-core attention kernels write per-CTA phase timestamps
  * (32 uint64 per CTA, %globaltimer ns) into buf; NULL switches it off. */
 int ndt1_debug_attention_timeline(uint64_t* buf);

@@ -55,7 +55,7 @@ class Batch(C.Structure):
     _fields_ = [(n, _p) for n in ("spikes", "spikes_mask", "spikes_timestamp", "spikes_lengths", "block_idx", "day_idx",
                                   "targets", "targets_lengths", "recon_targets", "targets_mask")] + [
         ("B", C.c_int32), ("T", C.c_int32), ("S", C.c_int32), ("training", C.c_int32), ("need_backward", C.c_int32), ("encoder_only", C.c_int32),
-        ("seed", C.c_uint64)]
+        ("seed", C.c_uint64), ("seed_ptr", _p)]
 
 
 class ProfileEntry(C.Structure):
@@ -71,7 +71,7 @@ _i, _i64, _u64, _f, _d, _sz = C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_dou
 PROTOTYPES = {
     "ndt1_last_error": (C.c_char_p, []),
     "ndt1_abi_version": (_i, []),
-    "ndt1_smooth_noise": (_i, [_p, _p, _i, _i, _i, C.POINTER(C.c_float), _i, _f, _f, _p, _p, _i, _u64, _p]),
+    "ndt1_smooth_noise": (_i, [_p, _p, _i, _i, _i, C.POINTER(C.c_float), _i, _f, _f, _p, _p, _i, _u64, _p, _p]),
     "ndt1_masker_apply": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ndt1_bernoulli_u8": (_i, [_p, _i64, _f, _u64, _u64, _p]),
     "ndt1_uniform_f32": (_i, [_p, _i64, _u64, _u64, _p]),
@@ -82,7 +82,12 @@ PROTOTYPES = {
     "ndt1_edit_distance": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _p]),
     "ndt1_recon_loss": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "ndt1_layernorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p]),
-    "ndt1_linear_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "ndt1_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "ndt1_linear_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "ndt1_linear_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ndt1_splice_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _d, _p]),
+    "ndt1_unsplice_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "ndt1_stack_valid": (_i, [_p, _p, _i, _i, _i, _p]),
     "ndt1_attention_workspace_bytes": (_sz, [_i, _i, _i]),
     "ndt1_attention_bf16": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _u64, _u64, _u64, _p, _p, _p, _i, _p]),
     "ndt1_adamw_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _p]),
@@ -105,6 +110,10 @@ PROTOTYPES = {
     "ndt1_profile_gemm_begin": (_i, []),
     "ndt1_profile_gemm_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ndt1_launch_counter": (_i64, []),
+    "ndt1_event_create": (_i, [C.POINTER(_p)]),
+    "ndt1_event_destroy": (_i, [_p]),
+    "ndt1_event_record": (_i, [_p, _p]),
+    "ndt1_stream_wait_event": (_i, [_p, _p]),
     "ndt1_profile_begin": (_i, []),
     "ndt1_profile_end": (_i, [C.POINTER(ProfileEntry), _i, C.POINTER(C.c_int)]),
     "ndt1_dropout_scales": (_i, [_p, _i64, _f, _u64, _u64, _p]),

@@ -11,4 +11,5 @@ from .masker import Masker  # noqa: F401
 from .ndt1 import NDT1, NDT1Output, create_context_mask  # noqa: F401
 from .collate import pad_collate_fn, padded_array, DevicePadCollate  # noqa: F401
 from .decode import format_ctc, greedy_ctc_decode, ctc_error_counts, phoneme_error_rate  # noqa: F401
+from .bci import BCI, BCIOutput  # noqa: F401
 from .trainer import NAME2MODEL, DataParallelTrainer  # noqa: F401

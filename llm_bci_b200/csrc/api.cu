@@ -3,11 +3,82 @@
 #include "kernels.cuh"
 #include <string.h>
 
+namespace {
+// g = dy * act'(saved), cast to T with a padded row stride (the operand of the data- and weight-gradient GEMMs)
+template <typename T>
+__global__ void dact_prep_kernel(const float* __restrict__ dy, const float* __restrict__ saved, T* __restrict__ out, long long rows, int cols,
+                                 int ld_out, int dact) { pdl_grid_sync();
+  const long long total = rows * ld_out;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ld_out; const int c = (int)(i % ld_out);
+    float v = 0.f;
+    if (c < cols) {
+      v = dy[r * cols + c];
+      if (dact != DACT_NONE) v *= dact_apply(dact, saved[r * cols + c]);
+    }
+    out[i] = from_f32<T>(v);
+  }
+}
+}  // namespace
+
+namespace {
+// out[b, j, :] = j < d ? a[b, j, :] : (j < d + Ls ? ins[b, j - d, :] : a[b, j - Ls, :]),  d = split[b] clamped to [0, La]
+// (models/bci.py:143-166: the spike features spliced between the two halves of the prompt; the same rule for the attention
+// mask and, with a constant row instead of `ins`, for the targets).  `unsplice` runs it backwards: the gradient of `out`
+// scattered back to a (accumulating nothing: every row has exactly one source).
+template <typename T>
+__global__ void splice_rows_kernel(const T* __restrict__ a, const T* __restrict__ ins, const long long* __restrict__ split, T* __restrict__ out,
+                                   int B, int La, int Ls, int W, int use_fill, T fill) { pdl_grid_sync();
+  const long long total = (long long)B * (La + Ls) * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % W);
+    const long long row = i / W;
+    const int j = (int)(row % (La + Ls)), b = (int)(row / (La + Ls));
+    long long d = split[b]; d = d < 0 ? 0 : (d > La ? La : d);
+    T v;
+    if (j < d) v = a[((long long)b * La + j) * W + c];
+    else if (j < d + Ls) v = use_fill ? fill : ins[((long long)b * Ls + (j - d)) * W + c];
+    else v = a[((long long)b * La + (j - Ls)) * W + c];
+    out[i] = v;
+  }
+}
+template <typename T>
+__global__ void unsplice_rows_kernel(const T* __restrict__ dout, const long long* __restrict__ split, T* __restrict__ da, T* __restrict__ dins,
+                                     int B, int La, int Ls, int W) { pdl_grid_sync();
+  const long long total = (long long)B * (La + Ls) * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % W);
+    const long long row = i / W;
+    const int j = (int)(row % (La + Ls)), b = (int)(row / (La + Ls));
+    long long d = split[b]; d = d < 0 ? 0 : (d > La ? La : d);
+    const T v = dout[i];
+    if (j < d) { if (da) da[((long long)b * La + j) * W + c] = v; }
+    else if (j < d + Ls) { if (dins) dins[((long long)b * Ls + (j - d)) * W + c] = v; }
+    else if (da) da[((long long)b * La + (j - Ls)) * W + c] = v;
+  }
+}
+// features (B, T, H) with a validity mask (B, T): rows padded with zeros to a multiple of `stacking`, then
+// mask_out[b, r] = all `stacking` rows of group r valid (models/bci.py:127-141)
+__global__ void stack_valid_kernel(const long long* __restrict__ mask, long long* __restrict__ out, int B, int T, int stacking, int Ts) { pdl_grid_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Ts) return;
+  const int b = i / Ts, r = i % Ts;
+  long long ok = 1;
+  for (int k = 0; k < stacking; ++k) {
+    const int t = r * stacking + k;
+    ok &= (t < T && mask[(long long)b * T + t] != 0) ? 1 : 0;
+  }
+  out[i] = ok;
+}
+}  // namespace
+
 extern "C" {
 
 int ndt1_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps_host, int K, float white_sd,
-                      float offset_sd, const float* white, const float* offset, int use_philox, uint64_t seed, void* stream) {
-  return k_smooth_noise(x, out, B, T, N, taps_host, K, white_sd, offset_sd, white, offset, use_philox, seed, (cudaStream_t)stream);
+                      float offset_sd, const float* white, const float* offset, int use_philox, uint64_t seed, const uint64_t* seed_ptr,
+                      void* stream) {
+  const SeedRef sr = seed_ptr ? SeedRef::at((const unsigned long long*)seed_ptr) : SeedRef((unsigned long long)seed);
+  return k_smooth_noise(x, out, B, T, N, taps_host, K, white_sd, offset_sd, white, offset, use_philox, sr, (cudaStream_t)stream);
 }
 
 int ndt1_masker_apply(float* spikes, int B, int T, int N, int mode, int timespan, const uint8_t* mask_draw, const uint8_t* zero_draw,
@@ -60,29 +131,147 @@ int ndt1_layernorm_fwd(const float* x, const float* gamma, const float* beta, fl
   return k_layernorm_fwd<float>(x, gamma, beta, y, mean, rstd, rows, H, eps, (cudaStream_t)stream);
 }
 
-int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K, int act, int precision,
-                    void* workspace, size_t workspace_bytes, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
+static int act_code_of(int act) {
+  return act == NDT1_ACT_SOFTSIGN ? ACT_SOFTSIGN : act == NDT1_ACT_GELU ? ACT_GELU : act == NDT1_ACT_RELU ? ACT_RELU : ACT_NONE;
+}
+static GemmProblem plain_problem(int mode, int M, int N, int K) {
   GemmProblem p;
   p.b_sel = nullptr;
-  p.mode = GEMM_NT; p.M = M; p.N = N; p.nb_out = 1; p.nchunk = 1; p.chunk_k = K;
+  p.mode = mode; p.M = M; p.N = N; p.nb_out = 1; p.nchunk = 1; p.chunk_k = K;
   p.a_row_shift = p.a_col_shift = p.b_row_shift = p.b_col_shift = 0; p.b_chunk_n = N; p.split_k = 1;
   p.epi = gemm_epilogue_default();
-  p.epi.out = y; p.epi.ldc = N; p.epi.bias = bias;
-  p.epi.act = act == NDT1_ACT_SOFTSIGN ? ACT_SOFTSIGN : act == NDT1_ACT_GELU ? ACT_GELU : act == NDT1_ACT_RELU ? ACT_RELU : ACT_NONE;
+  return p;
+}
+static bf16* ws_take(char*& cur, size_t elems) {
+  cur = (char*)(((uintptr_t)cur + 255) & ~(uintptr_t)255);
+  bf16* r = (bf16*)cur;
+  cur += elems * sizeof(bf16);
+  return r;
+}
+
+size_t ndt1_linear_workspace_bytes(int M, int N, int K) {
+  const size_t ldk = (K + 7) / 8 * 8, ldn = (N + 7) / 8 * 8;
+  return ((size_t)M * ldk + (size_t)N * ldk + (size_t)M * ldn) * sizeof(bf16) + 4 * 256;
+}
+
+int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* pre, int M, int N, int K, int act, int precision,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (M == 0 || N == 0) return 0;
+  GemmProblem p = plain_problem(GEMM_NT, M, N, K);
+  p.epi.out = y; p.epi.ldc = N; p.epi.bias = bias; p.epi.act = act_code_of(act);
+  if (pre) { p.epi.out2 = pre; p.epi.out2_bf16 = 0; }
   if (precision == NDT1_PRECISION_FP32) {
     p.A = {x, 0, 1, M, K, K}; p.B = {w, 0, 1, N, K, K};
     return gemm_simt_launch(p, 0, s);
   }
   const int ldk = (K + 7) / 8 * 8;
-  const size_t need = ((size_t)M * ldk + (size_t)N * ldk) * sizeof(bf16) + 512;
-  NDT1_REQUIRE(workspace && workspace_bytes >= need, "linear_fwd: bf16 mode needs %zu workspace bytes", need);
-  bf16* xa = (bf16*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  bf16* wa = (bf16*)(((uintptr_t)(xa + (size_t)M * ldk) + 255) & ~(uintptr_t)255);
+  NDT1_REQUIRE(workspace && workspace_bytes >= ndt1_linear_workspace_bytes(M, N, K), "linear_fwd: bf16 mode needs %zu workspace bytes",
+               ndt1_linear_workspace_bytes(M, N, K));
+  char* cur = (char*)workspace;
+  bf16* xa = ws_take(cur, (size_t)M * ldk);
+  bf16* wa = ws_take(cur, (size_t)N * ldk);
   NDT1_TRY(k_cast_f32_bf16(x, xa, M, K, K, ldk, s));
   NDT1_TRY(k_cast_f32_bf16(w, wa, N, K, K, ldk, s));
   p.A = {xa, 0, 1, M, K, ldk}; p.B = {wa, 0, 1, N, K, ldk};
   return gemm_tc_launch(p, s);
+}
+
+
+int ndt1_linear_bwd(const float* dy, const float* x, const float* w, const float* saved, float* dx, float* dw, float* db, int M, int N,
+                    int K, int act, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (M == 0 || N == 0) return 0;
+  NDT1_REQUIRE(dy && x && w, "linear_bwd: null argument");
+  const int dact = act == NDT1_ACT_SOFTSIGN ? DACT_SOFTSIGN_FROM_OUT : act == NDT1_ACT_GELU ? DACT_GELU_FROM_IN
+                 : act == NDT1_ACT_RELU ? DACT_RELU_FROM_OUT : DACT_NONE;
+  NDT1_REQUIRE(dact == DACT_NONE || saved, "linear_bwd: the activation derivative needs the saved output (pre-activation for gelu)");
+  const int ldk = (K + 7) / 8 * 8, ldn = (N + 7) / 8 * 8;
+  NDT1_REQUIRE(workspace && workspace_bytes >= ndt1_linear_workspace_bytes(M, N, K), "linear_bwd: needs %zu workspace bytes",
+               ndt1_linear_workspace_bytes(M, N, K));
+  char* cur = (char*)workspace;
+  const long long tot = (long long)M * ldn;
+  const int blocks = (int)((tot + 255) / 256 < 148 * 8 ? (tot + 255) / 256 : 148 * 8);
+  if (precision == NDT1_PRECISION_FP32) {
+    // fp32: g (M, N) in the workspace (2 bf16 slots per float: the byte budget of the bf16 layout covers M * N floats only when
+    // ldk >= N; keep it simple and exact instead: g needs M * N floats)
+    NDT1_REQUIRE(workspace_bytes >= (size_t)M * N * 4 + 256, "linear_bwd: fp32 mode needs %zu workspace bytes", (size_t)M * N * 4 + 256);
+    float* g = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    ndt1_launch(dact_prep_kernel<float>, blocks, 256, 0, s, dy, saved, g, (long long)M, N, N, dact);
+    NDT1_CHECK_LAUNCH();
+    if (db) NDT1_TRY(k_colsum<float>(g, db, M, N, N, s));
+    if (dw) {
+      GemmProblem p = plain_problem(GEMM_TN, N, K, M);
+      p.b_chunk_n = K;
+      p.A = {g, 0, 1, M, N, N}; p.B = {x, 0, 1, M, K, K};
+      p.epi.out = dw; p.epi.ldc = K; p.epi.accumulate = 1;
+      NDT1_TRY(gemm_simt_launch(p, 0, s));
+    }
+    if (dx) {
+      GemmProblem p = plain_problem(GEMM_NN, M, K, N);
+      p.A = {g, 0, 1, M, N, N}; p.B = {w, 0, 1, N, K, K};
+      p.epi.out = dx; p.epi.ldc = K;
+      NDT1_TRY(gemm_simt_launch(p, 0, s));
+    }
+    return 0;
+  }
+  bf16* xa = ws_take(cur, (size_t)M * ldk);
+  bf16* wa = ws_take(cur, (size_t)N * ldk);
+  bf16* ga = ws_take(cur, (size_t)M * ldn);
+  ndt1_launch(dact_prep_kernel<bf16>, blocks, 256, 0, s, dy, saved, ga, (long long)M, N, ldn, dact);
+  NDT1_CHECK_LAUNCH();
+  if (db) NDT1_TRY(k_colsum<bf16>(ga, db, M, N, ldn, s));
+  if (dw) {
+    NDT1_TRY(k_cast_f32_bf16(x, xa, M, K, K, ldk, s));
+    GemmProblem p = plain_problem(GEMM_TN, N, K, M);
+    p.b_chunk_n = K;
+    p.A = {ga, 0, 1, M, N, ldn}; p.B = {xa, 0, 1, M, K, ldk};
+    p.epi.out = dw; p.epi.ldc = K; p.epi.accumulate = 1; p.split_k = 0;
+    NDT1_TRY(gemm_tc_launch(p, s));
+  }
+  if (dx) {
+    NDT1_TRY(k_cast_f32_bf16(w, wa, N, K, K, ldk, s));
+    GemmProblem p = plain_problem(GEMM_NN, M, K, N);
+    p.A = {ga, 0, 1, M, N, ldn}; p.B = {wa, 0, 1, N, K, ldk};
+    p.epi.out = dx; p.epi.ldc = K;
+    NDT1_TRY(gemm_tc_launch(p, s));
+  }
+  return 0;
+}
+
+
+int ndt1_splice_rows(const void* a, const void* ins, const int64_t* split, void* out, int B, int La, int Ls, int W, int elem_size,
+                     int use_fill, double fill, void* stream) {
+  NDT1_REQUIRE(a && split && out && (ins || use_fill), "splice_rows: null argument");
+  NDT1_REQUIRE(elem_size == 4 || elem_size == 8, "splice_rows: element size %d (4 = float32, 8 = int64)", elem_size);
+  const long long total = (long long)B * (La + Ls) * W;
+  if (total == 0) return 0;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (elem_size == 4)
+    ndt1_launch(splice_rows_kernel<float>, blocks, 256, 0, (cudaStream_t)stream, (const float*)a, (const float*)ins, (const long long*)split, (float*)out,
+                B, La, Ls, W, use_fill, (float)fill);
+  else
+    ndt1_launch(splice_rows_kernel<long long>, blocks, 256, 0, (cudaStream_t)stream, (const long long*)a, (const long long*)ins, (const long long*)split,
+                (long long*)out, B, La, Ls, W, use_fill, (long long)fill);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+int ndt1_unsplice_rows(const float* dout, const int64_t* split, float* da, float* dins, int B, int La, int Ls, int W, void* stream) {
+  NDT1_REQUIRE(dout && split, "unsplice_rows: null argument");
+  const long long total = (long long)B * (La + Ls) * W;
+  if (total == 0) return 0;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  ndt1_launch(unsplice_rows_kernel<float>, blocks, 256, 0, (cudaStream_t)stream, dout, (const long long*)split, da, dins, B, La, Ls, W);
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+int ndt1_stack_valid(const int64_t* mask, int64_t* out, int B, int T, int stacking, void* stream) {
+  NDT1_REQUIRE(mask && out && stacking >= 1, "stack_valid: bad argument");
+  const int Ts = (T + stacking - 1) / stacking;
+  if (B * Ts == 0) return 0;
+  ndt1_launch(stack_valid_kernel, ndt1_cdiv((long long)B * Ts, 256), 256, 0, (cudaStream_t)stream, (const long long*)mask, (long long*)out, B, T, stacking, Ts);
+  NDT1_CHECK_LAUNCH();
+  return 0;
 }
 
 size_t ndt1_attention_workspace_bytes(int B, int L, int n_heads) {
@@ -150,6 +339,34 @@ int ndt1_profile_gemm_end(double* flops, double* ms, int64_t* launches) {   // t
   return 0;
 }
 int64_t ndt1_launch_counter(void) { return g_ndt1_launches; }
+
+// events that cross the boundary of a captured step (see include/ndt1_b200.h)
+int ndt1_event_create(void** event) {
+  NDT1_REQUIRE(event, "event_create: null argument");
+  cudaEvent_t e;
+  NDT1_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  *event = (void*)e;
+  return 0;
+}
+int ndt1_event_destroy(void* event) {
+  if (event) NDT1_CUDA_CHECK(cudaEventDestroy((cudaEvent_t)event));
+  return 0;
+}
+int ndt1_event_record(void* event, void* stream) {
+  NDT1_REQUIRE(event, "event_record: null event");
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  NDT1_CUDA_CHECK(cudaStreamIsCapturing((cudaStream_t)stream, &st));
+  if (st == cudaStreamCaptureStatusActive) NDT1_CUDA_CHECK(cudaEventRecordWithFlags((cudaEvent_t)event, (cudaStream_t)stream, cudaEventRecordExternal));
+  else NDT1_CUDA_CHECK(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+  return 0;
+}
+int ndt1_stream_wait_event(void* stream, void* event) {
+  NDT1_REQUIRE(event, "stream_wait_event: null event");
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  NDT1_CUDA_CHECK(cudaStreamIsCapturing((cudaStream_t)stream, &st));
+  NDT1_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, st == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : 0));
+  return 0;
+}
 int ndt1_debug_gemm_timeline(uint64_t* buf) { gemm_tc_set_timeline((unsigned long long*)buf); return 0; }
 int ndt1_debug_attention_timeline(uint64_t* buf) { k_attention_tc_set_timeline((unsigned long long*)buf); return 0; }
 

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p
       psum += pv;
       if (p.p_attn > 0.f && pv != 0.f) {
         const unsigned long long e = (((unsigned long long)b * p.nh + h) * L + qi) * (unsigned long long)L + (k0 + j);
-        pv *= drop_scale_1(p.seed, p.stream_attn, e, thr, ik);
+        pv *= drop_scale_1(p.seed.get(), p.stream_attn, e, thr, ik);
       }
       Ps[i][j] = pv;
     }
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p
       o[d] = from_f32<T>(v);
       if (p.p_out > 0.f) {
         const unsigned long long e = ((unsigned long long)b * L + qi) * (unsigned long long)p.H + h * hd + d0 + d;
-        od[d] = from_f32<T>(v * drop_scale_1(p.seed, p.stream_out, e, thr_o, iko));
+        od[d] = from_f32<T>(v * drop_scale_1(p.seed.get(), p.stream_out, e, thr_o, iko));
       } else if (od != o) {
         od[d] = from_f32<T>(v);
       }
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kv_kernel(const AttnParam
       float dm = 1.f;
       if (p.p_attn > 0.f && ok) {
         const unsigned long long e = (((unsigned long long)b * p.nh + h) * L + qi) * (unsigned long long)L + kj;
-        dm = drop_scale_1(p.seed, p.stream_attn, e, thr, ik);
+        dm = drop_scale_1(p.seed.get(), p.stream_attn, e, thr, ik);
       }
       Ps[i][j] = pv * dm;
       Ds[i][j] = pv * (dp * dm - del_i) * p.scale;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnParams
       float dm = 1.f;
       if (p.p_attn > 0.f && ok) {
         const unsigned long long e = (((unsigned long long)b * p.nh + h) * L + qi) * (unsigned long long)L + kj;
-        dm = drop_scale_1(p.seed, p.stream_attn, e, thr, ik);
+        dm = drop_scale_1(p.seed.get(), p.stream_attn, e, thr, ik);
       }
       Ds[i][j] = pv * (dp * dm - del_i) * p.scale;
     }

@@ -214,6 +214,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   const float m_s = (m == -INFINITY) ? 0.f : m * sl2;
   float l = 0.f;
   const bool drop = p.p_attn > 0.f;
+  const unsigned long long seed = (drop || p.p_out > 0.f) ? p.seed.get() : 0ull;
   const uint32_t thr = drop_threshold(p.p_attn);
   const float ik = drop ? 1.0f / (1.0f - p.p_attn) : 1.f;
   const long long bh_row = ((long long)b * p.nh + h) * L + qi;
@@ -226,7 +227,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
     if (c0 < L) {
       uint32_t kw = 0xFFFFFFFFu;
       if (drop) {
-        kw = keep_word32(p.seed, p.stream_attn, ebase + c0, thr, aligned);
+        kw = keep_word32(seed, p.stream_attn, ebase + c0, thr, aligned);
         if (p.drop_bits && qi < L) p.drop_bits[bh_row * 8 + (c0 >> 5)] = kw;
       }
       uint32_t raw[32];
@@ -289,7 +290,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
       st_row8(sOut, row, c0 + g * 8, v);
       if (p.p_out > 0.f) {
         float ds[8];
-        drop_scale_8(p.seed, p.stream_out, (unsigned long long)(o + g * 8), thr_o, iko, ds);
+        drop_scale_8(seed, p.stream_out, (unsigned long long)(o + g * 8), thr_o, iko, ds);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] *= ds[i];
       }

@@ -159,6 +159,16 @@ __host__ __device__ __forceinline__ Philox4 philox4x32(uint64_t seed, uint64_t c
   return o;
 }
 
+// The per-step Philox key, by value or read from device memory: a CUDA-graph replay of a step changes the key by updating the
+// device word, without re-capturing (every stochastic kernel of the path takes a SeedRef).
+struct SeedRef {
+  const unsigned long long* ptr; unsigned long long val;
+  __host__ __device__ SeedRef() : ptr(nullptr), val(0) {}
+  __host__ __device__ SeedRef(unsigned long long v) : ptr(nullptr), val(v) {}
+  __host__ __device__ static SeedRef at(const unsigned long long* p) { SeedRef r; r.ptr = p; return r; }
+  __device__ __forceinline__ unsigned long long get() const { return ptr ? *ptr : val; }
+};
+
 // Dropout draws use 16 bits per element: one Philox block (4 x u32 = 8 x u16) covers the 8
 // consecutive elements [8*ctr, 8*ctr+7].  An element is kept iff its u16 >= drop_threshold(p),
 // i.e. P(drop) = round(p * 65536) / 65536 (|error| < 8e-6).

@@ -22,10 +22,11 @@ struct SmoothParams {
   float w[SM_MAXK];
   float white_sd, offset_sd;
   const float* white; const float* offset;   // injected draws or null
-  int use_philox; unsigned long long seed;
+  int use_philox; SeedRef seed;
 };
 
 __global__ void smooth_noise_kernel(const SmoothParams p) { pdl_grid_sync();
+  const unsigned long long seed = p.use_philox ? p.seed.get() : 0ull;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int t0 = blockIdx.y * SM_TT;
   const int b = blockIdx.z;
@@ -37,7 +38,7 @@ __global__ void smooth_noise_kernel(const SmoothParams p) { pdl_grid_sync();
     if (p.offset) off = p.offset_sd * p.offset[(long long)b * p.N + n];
     else if (p.use_philox) {
       const unsigned long long e = (unsigned long long)b * p.N + n;
-      Philox4 r = philox4x32(p.seed, e, 0x6f666673ULL);
+      Philox4 r = philox4x32(seed, e, 0x6f666673ULL);
       float a, c; box_muller(r.x, r.y, a, c);
       off = p.offset_sd * a;
     }
@@ -60,7 +61,7 @@ __global__ void smooth_noise_kernel(const SmoothParams p) { pdl_grid_sync();
         const unsigned long long e = ((unsigned long long)b * p.T + t) * p.N + n;
         if (p.white) v += p.white_sd * p.white[e];
         else if (p.use_philox) {
-          Philox4 r = philox4x32(p.seed, e >> 1, 0x77686974ULL);
+          Philox4 r = philox4x32(seed, e >> 1, 0x77686974ULL);
           float a, c; box_muller(r.x, r.y, a, c);
           v += p.white_sd * ((e & 1) ? c : a);
         }
@@ -76,7 +77,7 @@ __global__ void smooth_noise_kernel(const SmoothParams p) { pdl_grid_sync();
         const unsigned long long e = ((unsigned long long)b * p.T + t) * p.N + n;
         if (p.white) v += p.white_sd * p.white[e];
         else if (p.use_philox) {
-          Philox4 r = philox4x32(p.seed, e >> 1, 0x77686974ULL);
+          Philox4 r = philox4x32(seed, e >> 1, 0x77686974ULL);
           float a, c; box_muller(r.x, r.y, a, c);
           v += p.white_sd * ((e & 1) ? c : a);
         }
@@ -99,6 +100,7 @@ __device__ __forceinline__ void white_quad(unsigned long long seed, unsigned lon
 }
 template <int K>
 __global__ void __launch_bounds__(256) smooth_noise_vec_kernel(const SmoothParams p) { pdl_grid_sync();
+  const unsigned long long seed = p.use_philox ? p.seed.get() : 0ull;
   const int n4 = blockIdx.x * 64 + (threadIdx.x & 63);          // channel quad
   const int strip = blockIdx.y * 4 + (threadIdx.x >> 6);
   const int b = blockIdx.z;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256) smooth_noise_vec_kernel(const SmoothParam
       const unsigned long long e = (unsigned long long)b * p.N + n4 * 4 + c;
       if (p.offset) o[c] = p.offset_sd * p.offset[e];
       else if (p.use_philox) {
-        Philox4 r = philox4x32(p.seed, e, 0x6f666673ULL);
+        Philox4 r = philox4x32(seed, e, 0x6f666673ULL);
         float a, d; box_muller(r.x, r.y, a, d);
         o[c] = p.offset_sd * a;
       }
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(256) smooth_noise_vec_kernel(const SmoothParam
             acc.z = fmaf(p.white_sd, wn.z, acc.z); acc.w = fmaf(p.white_sd, wn.w, acc.w);
           } else if (p.use_philox) {
             float nz[4];
-            white_quad(p.seed, e, nz);
+            white_quad(seed, e, nz);
             acc.x = fmaf(p.white_sd, nz[0], acc.x); acc.y = fmaf(p.white_sd, nz[1], acc.y);
             acc.z = fmaf(p.white_sd, nz[2], acc.z); acc.w = fmaf(p.white_sd, nz[3], acc.w);
           }
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(256) smooth_noise_vec_kernel(const SmoothParam
 }  // namespace
 
 int k_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps, int K, float white_sd, float offset_sd,
-                   const float* white, const float* offset, int use_philox, unsigned long long seed, cudaStream_t stream) {
+                   const float* white, const float* offset, int use_philox, SeedRef seed, cudaStream_t stream) {
   NDT1_REQUIRE(K >= 0 && K <= SM_MAXK - 1, "smooth: %d taps unsupported (max %d)", K, SM_MAXK - 1);
   NDT1_REQUIRE(K == 0 || (K % 2) == 1, "smooth: kernel length must be odd ('same' padding), got %d", K);
   if (B * T * N == 0) return 0;
@@ -541,8 +543,9 @@ template int k_colsum<bf16>(const bf16*, float*, long long, int, long long, cuda
 namespace {
 template <typename T>
 __global__ void grad_prep_kernel(const float* __restrict__ g, T* __restrict__ out, long long rows, int cols, float drop_p,
-                                 unsigned long long seed, unsigned long long stream_id, float* dtab, const long long* idx, int tab_ld,
+                                 SeedRef seed_ref, unsigned long long stream_id, float* dtab, const long long* idx, int tab_ld,
                                  int rows_per_b, long long idx_stride, int prefix) { pdl_grid_sync();
+  const unsigned long long seed = drop_p > 0.f ? seed_ref.get() : 0ull;
   const long long total4 = rows * (cols / 4);
   const uint32_t thr = drop_threshold(drop_p);
   const float ik = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
@@ -570,7 +573,7 @@ __global__ void grad_prep_kernel(const float* __restrict__ g, T* __restrict__ ou
 }  // namespace
 
 template <typename T>
-int k_grad_prep(const float* g, T* out, long long rows, int cols, float drop_p, unsigned long long seed, unsigned long long stream_id,
+int k_grad_prep(const float* g, T* out, long long rows, int cols, float drop_p, SeedRef seed, unsigned long long stream_id,
                 float* dtab, const long long* idx, int tab_ld, int rows_per_b, long long idx_stride, int prefix, cudaStream_t stream) {
   NDT1_REQUIRE(cols % 4 == 0, "grad_prep: cols %d must be a multiple of 4", cols);
   if (rows * cols == 0) return 0;
@@ -582,8 +585,8 @@ int k_grad_prep(const float* g, T* out, long long rows, int cols, float drop_p, 
   NDT1_CHECK_LAUNCH();
   return 0;
 }
-template int k_grad_prep<float>(const float*, float*, long long, int, float, unsigned long long, unsigned long long, float*, const long long*, int, int, long long, int, cudaStream_t);
-template int k_grad_prep<bf16>(const float*, bf16*, long long, int, float, unsigned long long, unsigned long long, float*, const long long*, int, int, long long, int, cudaStream_t);
+template int k_grad_prep<float>(const float*, float*, long long, int, float, SeedRef, unsigned long long, float*, const long long*, int, int, long long, int, cudaStream_t);
+template int k_grad_prep<bf16>(const float*, bf16*, long long, int, float, SeedRef, unsigned long long, float*, const long long*, int, int, long long, int, cudaStream_t);
 
 // ===========================================================================
 // Masked reconstruction loss (mlm / autoregressive): NDT1.forward
@@ -887,7 +890,8 @@ __global__ void rope_kernel(T* __restrict__ qkv, const long long* __restrict__ t
 
 // x *= keep-scale of dropout site `stream_id` (element index = flat index), in place; the same call on a gradient is the backward
 template <typename T>
-__global__ void dropout_inplace_kernel(T* __restrict__ x, long long n, float p, unsigned long long seed, unsigned long long stream_id) { pdl_grid_sync();
+__global__ void dropout_inplace_kernel(T* __restrict__ x, long long n, float p, SeedRef seed_ref, unsigned long long stream_id) { pdl_grid_sync();
+  const unsigned long long seed = seed_ref.get();
   const uint32_t thr = drop_threshold(p);
   const float ik = 1.0f / (1.0f - p);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
@@ -943,14 +947,14 @@ template int k_rope<float>(float*, const long long*, long long, const float*, co
 template int k_rope<bf16>(bf16*, const long long*, long long, const float*, const float*, long long, int, int, int, int, int, cudaStream_t);
 
 template <typename T>
-int k_dropout_inplace(T* x, long long n, float p, unsigned long long seed, unsigned long long stream_id, cudaStream_t stream) {
+int k_dropout_inplace(T* x, long long n, float p, SeedRef seed, unsigned long long stream_id, cudaStream_t stream) {
   if (n == 0 || p <= 0.f) return 0;
   ndt1_launch(dropout_inplace_kernel<T>, ew_blocks(n), 256, 0, stream, x, n, p, seed, stream_id);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
-template int k_dropout_inplace<float>(float*, long long, float, unsigned long long, unsigned long long, cudaStream_t);
-template int k_dropout_inplace<bf16>(bf16*, long long, float, unsigned long long, unsigned long long, cudaStream_t);
+template int k_dropout_inplace<float>(float*, long long, float, SeedRef, unsigned long long, cudaStream_t);
+template int k_dropout_inplace<bf16>(bf16*, long long, float, SeedRef, unsigned long long, cudaStream_t);
 
 template <typename T>
 int k_colsum_sel(const T* in, float* out, const long long* sel, int n_sel, long long out_stride, int B, int rows_per_b, int cols,

@@ -78,6 +78,8 @@ struct Engine : ndt1_engine {
   T* hn = nullptr; T* fac = nullptr; T* fpre = nullptr;
   float* logits = nullptr; float* logp = nullptr; float* dlogits = nullptr; float* nll = nullptr; float* ctc_ws = nullptr;
   long long* key_valid = nullptr; long long* out_lens = nullptr;
+  unsigned long long* seed_dev = nullptr;      // this step's Philox key in device memory: every stochastic kernel reads it through a SeedRef,
+                                               // so a captured step (CUDA graph) is replayed with a new key by updating 8 bytes
   float* feat32 = nullptr;
   // backward scratch
   // operands of the weight-gradient GEMMs are kept PER LAYER so that those GEMMs may trail the data-gradient chain
@@ -98,7 +100,7 @@ struct Engine : ndt1_engine {
   std::vector<const bf16*> u_qkv, u_o, u_up, u_down;
   std::vector<float*> b_qkv;
   // state of the last forward
-  int B = 0, Tn = 0, Tp = 0, L = 0, S = 0, training = 0; unsigned long long seed = 0; bool have_fwd = false, fwd_encoder_only = false;
+  int B = 0, Tn = 0, Tp = 0, L = 0, S = 0, training = 0; bool have_fwd = false, fwd_encoder_only = false;
   const float* spikes_ptr = nullptr; const long long* ts_ptr = nullptr; const long long* block_ptr = nullptr; const long long* day_ptr = nullptr;
 
   size_t arena_bytes() const override { return ar.cap; }
@@ -138,6 +140,7 @@ struct Engine : ndt1_engine {
     nll = ar.take<float>(Bm);
     if (k.method == NDT1_METHOD_CTC) ctc_ws = ar.take<float>(k_ctc_workspace_floats(Bm, out_len(Tm), k.max_targets));
     key_valid = ar.take<long long>(Mm); out_lens = ar.take<long long>(Bm);
+    seed_dev = ar.take<unsigned long long>(2);
     feat32 = ar.take<float>(Mm * Hout);
     dX = ar.take<float>(Mm * H); dYe = ar.take<T>(Mm * H); dH = ar.take<T>(Mm * H); dA = ar.take<T>(Mm * H);
     dYm.resize(NL); dYa.resize(NL); dUl.resize(NL); dqkvl.resize(NL);
@@ -288,7 +291,7 @@ struct Engine : ndt1_engine {
     NDT1_REQUIRE(!k.stack_active || bt->T >= k.stack_size, "engine: %d bins are fewer than the stack size %d", bt->T, k.stack_size);
     NDT1_REQUIRE(!k.pos || out_len(bt->T) <= k.max_F, "engine: %d positions exceed max_F %d", out_len(bt->T), k.max_F);
     NDT1_REQUIRE(k.method != NDT1_METHOD_CTC || bt->S <= k.max_targets, "engine: %d targets exceed max_targets %d", bt->S, k.max_targets);
-    B = bt->B; Tn = bt->T; Tp = out_len(Tn); L = n_prefix + Tp; S = bt->S; training = bt->training; seed = bt->seed;
+    B = bt->B; Tn = bt->T; Tp = out_len(Tn); L = n_prefix + Tp; S = bt->S; training = bt->training;
     spikes_ptr = bt->spikes; ts_ptr = (const long long*)bt->spikes_timestamp; block_ptr = (const long long*)bt->block_idx; day_ptr = (const long long*)bt->day_idx;
     if (B == 0) {
       // an empty shard (global batch < world size): loss 0, no examples; the other outputs have no elements
@@ -302,6 +305,10 @@ struct Engine : ndt1_engine {
     const int Hout = k.factors_active ? k.factors_size : H;
     const long long M = (long long)B * L, MT = (long long)B * Tn;
     const float pe = training ? k.p_embed : 0.f, ptr_ = training ? k.p_transformer : 0.f;
+    // the step's Philox key goes to device memory: copied from the caller's device word (graph replays re-read it), or set from the value
+    if (bt->seed_ptr) NDT1_CUDA_CHECK(cudaMemcpyAsync(seed_dev, bt->seed_ptr, 8, cudaMemcpyDeviceToDevice, s));
+    else NDT1_TRY(k_set_i64((long long*)seed_dev, (long long)bt->seed, s));
+    const SeedRef seed = SeedRef::at(seed_dev);
 
     // 0. precision staging: bf16 copies of the weights and of the input
     if (kBf16) {
@@ -548,14 +555,23 @@ struct Engine : ndt1_engine {
     NDT1_REQUIRE(have_fwd, "engine: backward without a matching forward (need_backward = 1)");
     NDT1_REQUIRE(fwd_encoder_only == (dfeatures != nullptr), "engine: an encoder-only forward is continued by ndt1_engine_backward_features, a full one by ndt1_engine_backward");
     const long long launches0 = g_ndt1_launches;
+    // Inside a stream capture (the step as a CUDA graph) the stage events become EXTERNAL event-record nodes: every replay records
+    // the real event, so a stream outside the graph (the trainer's all-reduce / optimizer stream) can wait on it.
+    cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+    NDT1_CUDA_CHECK(cudaStreamIsCapturing(s, &cap_status));
+    const bool capturing = cap_status == cudaStreamCaptureStatusActive;
+    auto record_stage = [&](int i, cudaStream_t st) -> cudaError_t {
+      return capturing ? cudaEventRecordWithFlags(stage_ev[i], st, cudaEventRecordExternal) : cudaEventRecord(stage_ev[i], st);
+    };
     if (B == 0) {       // empty shard: no gradient contribution, but every stage is "complete" for ndt1_engine_wait_stage
-      for (int i = 0; i < n_stages(); ++i) NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[i], s));
+      for (int i = 0; i < n_stages(); ++i) NDT1_CUDA_CHECK(record_stage(i, s));
       return 0;
     }
     const int H = k.hidden, I = k.inter, D = k.input_dim, N = k.n_channels, NL = k.n_layers, V = k.n_outputs;
     const int Hout = k.factors_active ? k.factors_size : H;
     const long long M = (long long)B * L, MT = (long long)B * Tn, Mo = (long long)B * Tp;
     const float pe = training ? k.p_embed : 0.f, ptr_ = training ? k.p_transformer : 0.f;
+    const SeedRef seed = SeedRef::at(seed_dev);          // (still this forward's key)
 
     // Weight gradients (and the bias reductions that are not fused elsewhere) go to `ws`: they only need the operand the
     // data-gradient chain has just produced, so they run concurrently with the rest of that chain and fill the SMs its
@@ -634,7 +650,7 @@ struct Engine : ndt1_engine {
     NDT1_TRY(k_layernorm_bwd<T>(dhn, xs[2 * NL], P->out_norm_w, mean[2 * NL], rstd[2 * NL], dX, G->out_norm_w, G->out_norm_b, dYm[NL - 1], ptr_, seed,
                                 site_mlp(NL - 1), M, H, ln_part, s, k.mlp_bias ? G->layer[NL - 1].down_b : nullptr));
     NDT1_TRY(fork());
-    NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[0], ws));   // decoder + out_norm gradients complete
+    NDT1_CUDA_CHECK(record_stage(0, ws));   // decoder + out_norm gradients complete
     int cf, cb; ctx(cf, cb);
     for (int l = NL - 1; l >= 0; --l) {
       const auto& q = P->layer[l]; const auto& gq = G->layer[l];
@@ -713,7 +729,7 @@ struct Engine : ndt1_engine {
                                   first ? 0.f : ptr_, seed, first ? 0 : site_mlp(l - 1), M, H, ln_part, s,
                                   (!first && k.mlp_bias) ? G->layer[l - 1].down_b : nullptr));
       NDT1_TRY(fork());                                          // also orders ws after this LayerNorm (its affine gradients, next dY)
-      NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[NL - l], ws));   // layer l gradients complete
+      NDT1_CUDA_CHECK(record_stage(NL - l, ws));   // layer l gradients complete
     }
     // embedding: dX is the gradient w.r.t. the (dropped) embedding output.
     // One pass: apply the embedding dropout mask, cast for the GEMMs, scatter into the position table.
@@ -804,7 +820,7 @@ struct Engine : ndt1_engine {
       p.split_k = (kBf16 && !force_simt) ? 0 : split;
       NDT1_TRY(run(p, ws));
     }
-    NDT1_CUDA_CHECK(cudaEventRecord(stage_ev[NL + 1], ws));     // embedding gradients complete
+    NDT1_CUDA_CHECK(record_stage(NL + 1, ws));     // embedding gradients complete
     if (overlap) {                                               // join: the caller's stream sees the whole backward
       NDT1_CUDA_CHECK(cudaEventRecord(join_ev, ws));
       NDT1_CUDA_CHECK(cudaStreamWaitEvent(s, join_ev, 0));

@@ -50,7 +50,7 @@ struct GemmEpilogue {
   int gather_ld;
   float drop_p;             // dropout after activation/gather (forward) ...
   int drop_bwd;             // ... or the same mask applied to a gradient (backward)
-  unsigned long long drop_seed, drop_stream;
+  SeedRef drop_seed; unsigned long long drop_stream;
   const float* resid;       // fp32 residual, indexed like out
   int dact;                 // DACT_*: multiply by act'(saved)
   const void* dact_in;      // indexed like out
@@ -83,7 +83,7 @@ static inline GemmEpilogue gemm_epilogue_default() {
   e.out = nullptr; e.out_bf16 = 0; e.ldc = 0; e.c_batch_stride = 0;
   e.out2 = nullptr; e.out2_bf16 = 0; e.bias = nullptr; e.alpha = 1.f; e.act = ACT_NONE;
   e.gather_tab = nullptr; e.gather_idx = nullptr; e.gather_idx_stride = 0; e.gather_ld = 0;
-  e.drop_p = 0.f; e.drop_bwd = 0; e.drop_seed = 0; e.drop_stream = 0;
+  e.drop_p = 0.f; e.drop_bwd = 0; e.drop_seed = SeedRef(); e.drop_stream = 0;
   e.resid = nullptr; e.dact = DACT_NONE; e.dact_in = nullptr; e.dact_in_bf16 = 0;
   e.accumulate = 0; e.colsum = nullptr;
   e.sel = nullptr; e.sel_n = 0; e.bias_sel_stride = 0; e.c_sel_stride = 0;
@@ -113,7 +113,7 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpilogue& e, int n
   }
   if (e.drop_p > 0.f) {
     const unsigned long long elem = ((unsigned long long)b * rows_c + r) * (unsigned long long)n_total + n;
-    v *= drop_scale_1(e.drop_seed, e.drop_stream, elem, drop_threshold(e.drop_p), 1.0f / (1.0f - e.drop_p));
+    v *= drop_scale_1(e.drop_seed.get(), e.drop_stream, elem, drop_threshold(e.drop_p), 1.0f / (1.0f - e.drop_p));
   }
   if (e.dact != DACT_NONE) v *= dact_apply(e.dact, load_as_f32(e.dact_in, idx, e.dact_in_bf16));
   if (e.resid) v += e.resid[idx];

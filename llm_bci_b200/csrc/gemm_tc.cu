@@ -116,6 +116,7 @@ __host__ __device__ constexpr bool ef_has(int cls, int f) { return (cls & f) != 
 struct EpiCtx {
   int side_kind;
   bool vec_ok;
+  unsigned long long seed;      // the step's Philox key (read once per warp: it may live in device memory)
 };
 
 struct ChunkAt {          // where a (tile, chunk) lands in the output
@@ -248,7 +249,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
     for (int k = 0; k < 4; ++k) {
       const int r = at.r0 + (lane >> 3) + 4 * (2 * k + (odd ? 1 : 0));
       const unsigned long long elem = ((unsigned long long)at.bt * p.M + r) * (unsigned long long)p.N + (unsigned)(at.n & ~7);
-      const Philox4 ph = philox4x32(e.drop_seed, elem >> 3, e.drop_stream);
+      const Philox4 ph = philox4x32(cx.seed, elem >> 3, e.drop_stream);
       const uint32_t s0 = odd ? ph.x : ph.z, s1 = odd ? ph.y : ph.w;
       const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
       const uint32_t a0 = odd ? r0 : ph.x, a1 = odd ? r1 : ph.y;     // row 2k
@@ -563,6 +564,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool plain = !e.out2 && !e.gather_tab && e.drop_p <= 0.f && e.dact == DACT_NONE && !e.resid && !e.accumulate && !e.colsum;
     cx.vec_ok = (p.N % 4 == 0 || (plain && e.ldc >= p.N + (4 - p.N % 4))) && (e.ldc % 4 == 0) && (e.c_batch_stride % 4 == 0) &&
                 (e.gather_tab == nullptr || e.gather_ld % 4 == 0) && (e.drop_p <= 0.f || p.N % 8 == 0);
+    cx.seed = (ef_has(EPI, EF_DROP) && e.drop_p > 0.f) ? e.drop_seed.get() : 0ull;
     cx.side_kind = e.resid ? SIDE_RESID : (e.dact != DACT_NONE ? SIDE_DACT : (e.gather_tab ? SIDE_GATHER : SIDE_NONE));
     int acc_stage = 0; uint32_t acc_phase = 0;
 

@@ -6,7 +6,7 @@
 
 // elementwise.cu
 int k_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps, int K, float white_sd, float offset_sd,
-                   const float* white, const float* offset, int use_philox, unsigned long long seed, cudaStream_t stream);
+                   const float* white, const float* offset, int use_philox, SeedRef seed, cudaStream_t stream);
 int k_masker_apply(float* spikes, int B, int T, int N, int mode, int timespan, const unsigned char* mask_draw,
                    const unsigned char* zero_draw, const unsigned char* random_draw, const float* rand, long long* mask_out,
                    long long* targets_mask, unsigned int* scratch, cudaStream_t stream);
@@ -23,7 +23,7 @@ struct CastSegs {            // fp32 -> bf16 copies done by one launch (k_cast_m
 int k_cast_multi(CastSegs& segs, cudaStream_t stream);
 template <typename T> int k_colsum(const T* in, float* out, long long rows, int cols, long long ld, cudaStream_t stream);
 template <typename T>
-int k_grad_prep(const float* g, T* out, long long rows, int cols, float drop_p, unsigned long long seed, unsigned long long stream_id,
+int k_grad_prep(const float* g, T* out, long long rows, int cols, float drop_p, SeedRef seed, unsigned long long stream_id,
                 float* dtab, const long long* idx, int tab_ld, int rows_per_b, long long idx_stride, int prefix, cudaStream_t stream);
 int k_recon_loss(const float* pred, const float* target, float* dpred, const long long* tmask, const long long* pmask, int B, int T,
                  int N, int kind, int shift, int relu_out, float* loss, long long* count, const float* dloss, cudaStream_t stream);
@@ -44,7 +44,7 @@ template <typename T>
 int k_rope(T* qkv, const long long* ts, long long ts_stride, const float* cs, const float* sn, long long rows, int L, int H, int nh,
            int max_F, int inverse, cudaStream_t stream);
 template <typename T>
-int k_dropout_inplace(T* x, long long n, float p, unsigned long long seed, unsigned long long stream_id, cudaStream_t stream);
+int k_dropout_inplace(T* x, long long n, float p, SeedRef seed, unsigned long long stream_id, cudaStream_t stream);
 template <typename T>
 int k_colsum_sel(const T* in, float* out, const long long* sel, int n_sel, long long out_stride, int B, int rows_per_b, int cols,
                  cudaStream_t stream);
@@ -60,7 +60,7 @@ int k_layernorm_fwd(const float* x, const float* gamma, const float* beta, T* y,
 // dres (fp32, in/out) += LN'(dy);  optional out_lp = T(dres_new * dropscale)
 template <typename T>
 int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float* mean, const float* rstd, float* dres, float* dgamma,
-                    float* dbeta, T* out_lp, float drop_p, unsigned long long seed, unsigned long long stream_id, long long rows, int H,
+                    float* dbeta, T* out_lp, float drop_p, SeedRef seed, unsigned long long stream_id, long long rows, int H,
                     float* partials, cudaStream_t stream, float* colsum_out = nullptr);   // colsum_out[c] += sum_r out_lp[r, c]
 size_t k_layernorm_bwd_partials_bytes(int H);
 
@@ -75,7 +75,7 @@ struct AttnParams {
   int ctx_fwd, ctx_bwd;     // effective band half-widths (INT_MAX/2 = unbounded); self may be excluded by -1
   float scale;
   float p_attn, p_out;
-  unsigned long long seed, stream_attn, stream_out;
+  SeedRef seed; unsigned long long stream_attn, stream_out;
   // backward
   const void* dout;         // (B*L, H) gradient w.r.t. out_drop input of out_proj (already through output dropout)
   void* dqkv;               // (B*L, 3H)

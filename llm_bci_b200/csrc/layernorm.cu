@@ -93,9 +93,10 @@ __device__ __forceinline__ float4 unpack4(uint2 r) {
 template <typename T>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 1)
 ln_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
-              const float* __restrict__ rstd, float* __restrict__ dres, T* __restrict__ out_lp, float drop_p, unsigned long long seed,
+              const float* __restrict__ rstd, float* __restrict__ dres, T* __restrict__ out_lp, float drop_p, SeedRef seed_ref,
               unsigned long long stream_id, long long rows, int H, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ colsum_out) { pdl_grid_sync();
+  const unsigned long long seed = drop_p > 0.f ? seed_ref.get() : 0ull;
   extern __shared__ float sm[];   // [warps][3][H]: per-warp partial sums of dgamma | dbeta | colsum(out_lp)
   typedef typename Raw4<T>::type raw_t;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -264,9 +265,10 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : 1) ln_fwd_rows_kernel(cons
 template <typename T, int NT>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1)
 ln_bwd_rows_kernel(const T* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
-                   const float* __restrict__ rstd, float* __restrict__ dres, T* __restrict__ out_lp, float drop_p, unsigned long long seed,
+                   const float* __restrict__ rstd, float* __restrict__ dres, T* __restrict__ out_lp, float drop_p, SeedRef seed_ref,
                    unsigned long long stream_id, long long rows, int H, float* __restrict__ dgamma, float* __restrict__ dbeta,
                    float* __restrict__ colsum_out) { pdl_grid_sync();
+  const unsigned long long seed = drop_p > 0.f ? seed_ref.get() : 0ull;
   __shared__ float red[2 * 32 * 8];
   typedef typename Raw4<T>::type raw_t;
   const int c = threadIdx.x, lane = c & 31, nwarps = blockDim.x >> 5;
@@ -383,7 +385,7 @@ int k_layernorm_fwd(const float* x, const float* gamma, const float* beta, T* y,
 
 template <typename T>
 int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float* mean, const float* rstd, float* dres, float* dgamma,
-                    float* dbeta, T* out_lp, float drop_p, unsigned long long seed, unsigned long long stream_id, long long rows, int H,
+                    float* dbeta, T* out_lp, float drop_p, SeedRef seed, unsigned long long stream_id, long long rows, int H,
                     float* partials, cudaStream_t stream, float* colsum_out) {
   NDT1_REQUIRE(H % 4 == 0 && H <= 128 * LN_MAXV, "layernorm: hidden size %d unsupported (multiple of 4, <= %d)", H, 128 * LN_MAXV);
   if (rows == 0) return 0;
@@ -422,6 +424,6 @@ int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float
 template int k_layernorm_fwd<float>(const float*, const float*, const float*, float*, float*, float*, long long, int, float, cudaStream_t);
 template int k_layernorm_fwd<bf16>(const float*, const float*, const float*, bf16*, float*, float*, long long, int, float, cudaStream_t);
 template int k_layernorm_bwd<float>(const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*, float,
-                                    unsigned long long, unsigned long long, long long, int, float*, cudaStream_t, float*);
+                                    SeedRef, unsigned long long, long long, int, float*, cudaStream_t, float*);
 template int k_layernorm_bwd<bf16>(const bf16*, const float*, const float*, const float*, const float*, float*, float*, float*, bf16*, float,
-                                   unsigned long long, unsigned long long, long long, int, float*, cudaStream_t, float*);
+                                   SeedRef, unsigned long long, long long, int, float*, cudaStream_t, float*);

@@ -82,6 +82,8 @@ class SmoothAndNoise(nn.Module):
         self.constant_offset_sd = config.constant_offset_sd
         self.smooth = config.smooth_sd is not None
         self.rng = rng
+        self.seed_tensor = None      # optional int64 CUDA tensor: element 0 holds the Philox key of the noise (read on the device when
+                                     # the kernel runs, so a captured step is replayed with fresh noise; DataParallelTrainer sets it)
         if self.smooth:
             kernel = torch.from_numpy(gaussian_taps(config.smooth_sd))
             self.register_buffer("kernel", kernel, persistent=False)
@@ -101,7 +103,7 @@ class SmoothAndNoise(nn.Module):
         taps_c = taps.ctypes.data_as(_C.C.POINTER(_C.C.c_float))
         white = offset = None
         wsd = osd = 0.0
-        use_philox, seed = 0, 0
+        use_philox, seed, seed_ptr = 0, 0, None
         if add_noise:
             wsd = float(self.white_noise_sd) if self.white_noise_sd is not None else 0.0
             osd = float(self.constant_offset_sd) if self.constant_offset_sd is not None else 0.0
@@ -113,9 +115,13 @@ class SmoothAndNoise(nn.Module):
                 if self.constant_offset_sd is not None:
                     offset = torch.randn(B, 1, N, dtype=spikes.dtype, device=spikes.device)
             else:
-                use_philox, seed = 1, _seed_from_torch()
+                use_philox = 1
+                if self.seed_tensor is not None:
+                    seed_ptr = self.seed_tensor.data_ptr()
+                else:
+                    seed = _seed_from_torch()
         _C.check(_C.lib().ndt1_smooth_noise(spikes.data_ptr(), out.data_ptr(), B, T, N, taps_c, len(taps), wsd, osd,
-                                            _C.ptr(white), _C.ptr(offset), use_philox, seed, _C.stream_ptr()), "ndt1_smooth_noise")
+                                            _C.ptr(white), _C.ptr(offset), use_philox, seed, seed_ptr, _C.stream_ptr()), "ndt1_smooth_noise")
         return out
 
 
@@ -421,6 +427,7 @@ class NDT1(nn.Module):
         self.config = config
         self._engine = None
         self._engine_cap = (0, 0, 0)
+        self._engine_epoch = 0        # bumped whenever the engine (and with it every arena address) is re-created
         self._ptable = None
         self._pstruct = None
         self._goffs = None            # cached _grad_offsets() of the current parameter table
@@ -430,6 +437,8 @@ class NDT1(nn.Module):
         self._generation = 0          # forwards run so far: the engine keeps the activations of the LAST one only
         self._weight_shadow = None
         self._param_stream = None     # a side stream that may still be updating the parameters (DataParallelTrainer's optimizer)
+        self._param_event = None      # ... or the C event it records after its last update (usable from inside a captured step)
+        self._seed_tensor = None      # int64[2] CUDA tensor holding (noise key, dropout key) when the step's keys live in device memory
 
     # ------------------------------------------------------------------ engine plumbing
     def _apply(self, fn, *a, **k):
@@ -487,6 +496,7 @@ class NDT1(nn.Module):
             h = _C._p()
             _C.check(L.ndt1_engine_create(_C.C.byref(cfg), _C.C.byref(h)), "ndt1_engine_create")
             self._engine, self._engine_cap = h, (nb, nt, ns)
+            self._engine_epoch += 1
             self._apply_weight_shadow()
             if self.config.encoder.transformer.use_rope:
                 a = self.encoder.layers[0].attn
@@ -527,7 +537,9 @@ class NDT1(nn.Module):
 
     def wait_for_parameters(self) -> None:
         """Order the current stream after a pending optimizer update on a side stream (see DataParallelTrainer.train_step)."""
-        if self._param_stream is not None:
+        if self._param_event is not None:      # (an EXTERNAL wait node when the current stream is being captured into a graph)
+            _C.check(_C.lib().ndt1_stream_wait_event(_C.stream_ptr(), self._param_event), "ndt1_stream_wait_event")
+        elif self._param_stream is not None:
             torch.cuda.current_stream().wait_stream(self._param_stream)
 
     def _check_generation(self, generation: int) -> None:
@@ -582,7 +594,10 @@ class NDT1(nn.Module):
             keep["tm"] = call.get("targets_mask")
         b.B, b.T, b.S = B, T, S
         b.training, b.need_backward, b.encoder_only = int(self.training), int(need_backward), int(enc_only)
-        b.seed = _seed_from_torch() if self.training else 0
+        if self._seed_tensor is not None and self.training:      # the key lives in device memory (element 1 of the trainer's seed pair)
+            b.seed, b.seed_ptr = 0, self._seed_tensor.data_ptr() + 8
+        else:
+            b.seed, b.seed_ptr = (_seed_from_torch() if self.training else 0), None
         o = _C.Outputs()
         o.loss, o.n_examples, o.preds = loss.data_ptr(), n_examples.data_ptr(), _C.ptr(preds)
         o.out_mask, o.loss_mask, o.features = out_mask.data_ptr(), _C.ptr(loss_mask), _C.ptr(features)

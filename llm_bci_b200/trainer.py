@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import inspect
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -25,7 +26,12 @@ import torch.distributed as dist
 from . import _C
 from .ndt1 import NDT1
 
-NAME2MODEL = {"NDT1": NDT1}
+def _bci(*args, **kwargs):
+    from .bci import BCI
+    return BCI(*args, **kwargs)
+
+
+NAME2MODEL = {"NDT1": NDT1, "BCI": _bci}     # (models/trainer.py:36; iTransformer / PatchTST are other model families)
 
 
 def get_model_inputs(model) -> List[str]:
@@ -90,7 +96,7 @@ class DataParallelTrainer:
     def __init__(self, model: NDT1, lr: float = 1e-3, wd: float = 5e-5, eps: float = 1e-8, betas=(0.9, 0.999),
                  scheduler: Optional[str] = None, total_steps: int = 1, warmup_pct: float = 0.0, div_factor: float = 25.0,
                  gamma: float = 0.95, process_group=None, bucket_layers: int = 1,
-                 gradient_accumulation_steps: int = 1, loss_scale: Optional[float] = None):
+                 gradient_accumulation_steps: int = 1, loss_scale: Optional[float] = None, use_graph: Optional[bool] = None):
         self.model = model
         self.lr, self.wd, self.eps, self.betas = lr, wd, eps, betas
         self.scheduler, self.total_steps, self.warmup_pct, self.div_factor, self.gamma = scheduler, total_steps, warmup_pct, div_factor, gamma
@@ -140,6 +146,24 @@ class DataParallelTrainer:
         self.buckets = [(st, spans[st][0], spans[st][1]) for st in sorted(spans)]   # completion order
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self.serialize = False     # measurement aid: run the exchange and the optimizer AFTER the backward instead of under it
+        # Whole-step CUDA graph (the loop at models/trainer.py:332-349): prologue + forward + backward of a batch
+        # geometry are captured once and replayed; the per-step Philox keys live in device memory (self._seeds_dev), the gradient
+        # exchange and the bucketed optimizer stay eager on the side stream, ordered against the graph by external event nodes.
+        if use_graph is None:
+            use_graph = os.environ.get("NDT1_GRAPH", "1") != "0"
+        self.use_graph = bool(use_graph) and dev.type == "cuda"
+        self._graphs: Dict[tuple, dict] = {}
+        self.replayed_launches = 0          # kernels executed through graph replays (bench.py gpu_launches)
+        self._params_ev = None
+        if dev.type == "cuda":
+            ev = _C._p()
+            _C.check(_C.lib().ndt1_event_create(_C.C.byref(ev)), "ndt1_event_create")
+            self._params_ev = ev
+            model._param_event = ev
+            _C.check(_C.lib().ndt1_event_record(ev, torch.cuda.current_stream().cuda_stream), "ndt1_event_record")
+            self._seeds_dev = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._seeds_ring = torch.zeros(256, 2, dtype=torch.int64).pin_memory()
+            self._seed_i = 0
         model._param_stream = self.comm_stream
         self._ones = torch.full((), self._loss_scale, dtype=torch.float32, device=dev)     # d(loss) handed to the backward
 
@@ -201,7 +225,17 @@ class DataParallelTrainer:
         m.train()
         sync = (self.global_step - 1) % self.accum == 0
         self.global_step += 1
-        out = m.forward_backward(batch, self.flat_grad, self._ones)
+        if self._params_ev is not None:
+            # this step's Philox keys go to device memory (eager and captured steps alike: same draws for the same torch seed)
+            self._use_device_seeds(True)
+            self._push_seeds()
+        try:
+            if self.use_graph and self._graphable(batch):
+                out = self._step_graphed(batch)
+            else:
+                out = m.forward_backward(batch, self.flat_grad, self._ones)
+        finally:
+            self._use_device_seeds(False)       # (forwards outside the trainer draw their own keys again)
         if not sync:                      # accumulation micro-step: gradients stay in the arena, nothing is exchanged
             return out
         if self.comm_stream is None:
@@ -220,10 +254,58 @@ class DataParallelTrainer:
                 if self.world > 1:
                     dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
                 self._adamw(lo, hi, lr, self.comm_stream.cuda_stream)
+            _C.check(L.ndt1_event_record(self._params_ev, self.comm_stream.cuda_stream), "ndt1_event_record")   # parameters final
         # The caller's stream is NOT joined here: the last buckets' all-reduce and AdamW then run under the next step's
         # prologue (smoothing / noise / input cast, which read no parameter); the model joins before its first
         # parameter-dependent kernel (NDT1.wait_for_parameters, also called by save_checkpoint).
         return out
+
+    # ------------------------------------------------------------------ whole-step CUDA graph
+    def _graphable(self, batch) -> bool:
+        m = self.model
+        if any(mk.is_active() for mk in m.encoder.masker):       # the maskers draw on the CPU generator (models/masker.py:56-101)
+            return False
+        if m.encoder.smooth_and_noise.rng != "device" or batch.get("noise") is not None:
+            return False
+        return all((not torch.is_tensor(v)) or (v.is_cuda and v.is_contiguous()) for v in batch.values())
+
+    def _use_device_seeds(self, on: bool) -> None:
+        m = self.model
+        t = self._seeds_dev if (on and self._params_ev is not None) else None
+        m._seed_tensor = t
+        m.encoder.smooth_and_noise.seed_tensor = t
+
+    def _push_seeds(self) -> None:
+        """This step's (noise key, dropout key) -> device memory, through a ring of pinned slots (the host runs ahead of the GPU)."""
+        slot = self._seeds_ring[self._seed_i % self._seeds_ring.shape[0]]
+        self._seed_i += 1
+        slot.copy_(torch.randint(0, 2 ** 62, (2,)))
+        self._seeds_dev.copy_(slot, non_blocking=True)
+
+    def _step_graphed(self, batch):
+        m = self.model
+        key = (m._engine_epoch,
+               tuple((k, v.data_ptr(), tuple(v.shape), str(v.dtype)) for k, v in sorted(batch.items()) if torch.is_tensor(v)))
+        ent = self._graphs.get(key)
+        if ent is None:
+            # first sight of this batch geometry / these buffers: run eagerly (creates or grows the engine, sets every kernel
+            # attribute, fills the tensor-map cache); the next step with the same key captures
+            if len(self._graphs) >= 16:
+                self._graphs.clear()
+            out = m.forward_backward(batch, self.flat_grad, self._ones)
+            key = (m._engine_epoch, key[1])          # (the engine may have been created, or grown, by this very call)
+            self._graphs[key] = {}
+            return out
+        if "graph" not in ent:
+            L = _C.lib()
+            g = torch.cuda.CUDAGraph()
+            n0 = L.ndt1_launch_counter()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                out = m.forward_backward(batch, self.flat_grad, self._ones)
+            ent.update(graph=g, out=out, launches=int(L.ndt1_launch_counter() - n0), keep=dict(batch))
+        ent["graph"].replay()
+        self.replayed_launches += ent["launches"]
+        return ent["out"]
 
     def _adamw(self, lo: int, hi: int, lr: float, stream: int) -> None:
         b1, b2 = getattr(self, "_beta1", self.betas[0]), self.betas[1]

@@ -96,6 +96,9 @@ def main():
     if "--only-variants" in sys.argv:
         variant_cases(R)
         return
+    if "--bci" in sys.argv:
+        bci_case()
+        return
     if "--round2" in sys.argv:            # fixtures added in round 2 (the earlier files regenerate bit-identically and are left alone)
         autocast_error_cases(R)
         ssl_full_case(R)
@@ -395,6 +398,71 @@ def full_case(R):
     d["grad64_slice/encoder.embedder.embed_pos.weight"] = grads_d["encoder.embedder.embed_pos.weight"][:4, :].numpy().astype(np.float32)
     np.savez_compressed(os.path.join(HERE, "ctc_full_b4.npz"), **d)
     print("ctc_full_b4 loss", float(out_f.loss), "fp64", float(out_d.loss))
+
+
+BCI_OVER = {"projector": {"stacking": 2, "inter_size": 48, "bias": True, "act": "relu"}, "ndt1": {"encoder": {
+    "embedder": {"n_channels": 16, "input_dim": 16, "max_F": 64, "dropout": 0.0, "stack": {"active": True, "size": 32, "stride": 4}},
+    "transformer": {"n_layers": 2, "hidden_size": 64, "n_heads": 4, "inter_size": 64, "dropout": 0.0},
+    "smooth_and_noise": {"noise": False}}}}
+
+
+def bci_case():
+    """BCI coupler (models/bci.py:88-96, 107-168) of the unmodified reference with its debug LLaMA (:51-53): outputs of
+    prepare_embeds, gradients of a fixed linear functional of the spliced embeddings w.r.t. projector and encoder, and the
+    end-to-end loss through the fp16 LLaMA.  `peft` is absent here: a stub lets models/bci.py import (LoRA is not exercised)."""
+    os.chdir(REF)
+    sys.path.insert(0, REF)
+    import scipy.signal
+    import scipy.signal.windows
+    scipy.signal.gaussian = scipy.signal.windows.gaussian
+    peft = types.ModuleType("peft")
+    peft.LoraConfig, peft.get_peft_model = object, (lambda m, c: m)
+    sys.modules["peft"] = peft
+    from utils.config_utils import update_config
+    from models.bci import BCI
+    torch.set_num_threads(8)
+    d = {}
+    for name, stacking, act in (("s2_relu", 2, "relu"), ("s3_gelu", 3, "gelu")):      # 23 tokens: 2 and 3 both need the zero padding
+        over = copy.deepcopy(BCI_OVER)
+        over["projector"].update(stacking=stacking, act=act)
+        cfg = update_config("configs/bci.yaml", over)
+        torch.manual_seed(3)
+        m = BCI(cfg, llm_path=None, debug=True, method_name="ctc", vocab_size=41, blank_id=0, zero_infinity=True)
+        m.train()
+        B, T, N, Lt = 3, 120, 16, 7
+        g = torch.Generator().manual_seed(5)
+        spikes = torch.randn(B, T, N, generator=g)
+        lens = torch.tensor([120, 100, 90])
+        mask = (torch.arange(T)[None] < lens[:, None]).long()
+        spikes = spikes * mask[:, :, None]
+        ts = torch.arange(T)[None].expand(B, T) * mask
+        ids = torch.randint(0, 1000, (B, Lt), generator=g)
+        am = torch.ones(B, Lt, dtype=torch.long)
+        am[1, -2:] = 0
+        split = torch.tensor([2, 0, 7])
+        tg = ids.clone()
+        tg[:, :2] = -100
+        embeds, amask, tgo = m.prepare_embeds(ids, am, split, spikes.clone(), mask, ts, lens, None, None, tg)
+        R = torch.randn(embeds.shape, generator=g)
+        m.zero_grad()
+        (embeds * R).sum().backward()
+        text = m.llm.get_input_embeddings()(ids).detach().float()
+        sd = {k: v for k, v in m.state_dict().items() if k.startswith("ndt1.") or k.startswith("projector.")}
+        d.update(flat(f"{name}/param", sd))
+        d.update(flat(f"{name}/grad", {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in m.named_parameters()
+                                        if n.startswith("ndt1.encoder.") or n.startswith("projector.")}))
+        d.update(flat(f"{name}/in", dict(spikes=spikes, spikes_mask=mask, spikes_timestamp=ts, spikes_lengths=lens, input_ids=ids,
+                                         attention_mask=am, input_split=split, targets=tg, text_embeds=text, R=R)))
+        d[f"{name}/out/embeds"] = embeds.detach().float().numpy()
+        d[f"{name}/out/attention_mask"] = amask.numpy()
+        d[f"{name}/out/targets"] = tgo.numpy()
+        # end to end through the fp16 LLaMA (CPU half arithmetic: a loose yardstick only)
+        m.zero_grad()
+        out = m(ids, am, split, spikes.clone(), mask, ts, lens, None, None, tg)
+        d[f"{name}/out/loss"] = out.loss.detach().float().numpy()
+        d[f"{name}/out/n_examples"] = out.n_examples.numpy()
+        print("bci", name, "embeds", tuple(embeds.shape), "loss", float(out.loss), "n", int(out.n_examples))
+    np.savez_compressed(os.path.join(HERE, "bci_coupler.npz"), **d)
 
 
 KEEP_FULL = ("decoder.0.weight", "decoder.0.bias", "encoder.out_norm.weight", "encoder.layers.0.ln1.weight",

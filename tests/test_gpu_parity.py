@@ -25,7 +25,7 @@ import llm_bci_b200 as lb  # noqa: E402
 from llm_bci_b200 import _C  # noqa: E402
 from oracle import ndt1_oracle as O  # noqa: E402
 from test_oracle_golden import (load, sub, small_ctc_cfg, mlm_cfg, CTC_KW, VARIANTS, variant_case, AR_KW, autoregressive_cfg,  # noqa: E402
-                                SSL_KW, ssl_full_cfg, ssl_full_draws, full_ctc_cfg, check_full_fixture)
+                                SSL_KW, ssl_full_cfg, ssl_full_draws, full_ctc_cfg, check_full_fixture, bci_cfg)
 
 DEV = "cuda"
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
@@ -39,9 +39,9 @@ TOL = {"fp32": 1e-4, "bf16": 2e-2}
 # rounds the GEMM operands), which is where the factor over the reference's own figure comes from.  For the Poisson-rate head
 # the reference's own autocast error is 1.4 (its 1 / rate gradient is computed in bf16): the CUDA path is well below it.
 BF16_WAIVERS = {
-    "gelu_factors": ("ctc_variants/gelu_factors", 12.0),
-    "mse": ("autoregressive/mse", 12.0),
-    "poisson_rate": ("autoregressive/poisson_rate", 0.2),
+    "gelu_factors": ("ctc_variants/gelu_factors", 12.0),       # measured 5.9e-2 = 6.3 x the reference's own 9.4e-3
+    "poisson_rate": ("autoregressive/poisson_rate", 0.2),      # measured 0.20 = 0.14 x the reference's own 1.42
+    # (the MSE / ReLU head needs no waiver: measured 6.5e-3, inside the nominal 2e-2)
 }
 
 
@@ -296,13 +296,24 @@ def test_linear_operator_both_precisions():
     ref = torch.nn.functional.gelu(x.double() @ w.double().T + b.double())
     Lb = _C.lib()
     for prec, tol in (("fp32", 1e-5), ("bf16", 2e-2)):
-        y = torch.empty(M, N, device=DEV)
-        ws = torch.empty(4 * (M + N) * 208 + 4096, dtype=torch.uint8, device=DEV)
+        y, pre = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+        ws = torch.empty(max(Lb.ndt1_linear_workspace_bytes(M, N, K), M * N * 4 + 256), dtype=torch.uint8, device=DEV)
         xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
-        _C.check(Lb.ndt1_linear_fwd(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), M, N, K, _C.ACT["gelu"], _C.PRECISION[prec],
-                                    ws.data_ptr(), ws.numel(), _C.stream_ptr()))
+        _C.check(Lb.ndt1_linear_fwd(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), pre.data_ptr(), M, N, K, _C.ACT["gelu"],
+                                    _C.PRECISION[prec], ws.data_ptr(), ws.numel(), _C.stream_ptr()))
         err = (y.cpu().double() - ref).abs().max() / ref.abs().max()
         assert err < tol, (prec, float(err))
+        # backward (the BCI projector trains through it): dx, dw, db against torch autograd in float64
+        xr, wr, br = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+        dy = torch.randn(M, N, generator=torch.Generator().manual_seed(9))
+        (torch.nn.functional.gelu(xr @ wr.T + br) * dy.double()).sum().backward()
+        dx, dw, db = torch.empty(M, K, device=DEV), torch.zeros(N, K, device=DEV), torch.zeros(N, device=DEV)
+        dyd = dy.to(DEV)
+        _C.check(Lb.ndt1_linear_bwd(dyd.data_ptr(), xd.data_ptr(), wd.data_ptr(), pre.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), M, N, K,
+                                    _C.ACT["gelu"], _C.PRECISION[prec], ws.data_ptr(), ws.numel(), _C.stream_ptr()))
+        for got, want in ((dx, xr.grad), (dw, wr.grad), (db, br.grad)):
+            e = (got.cpu().double() - want).abs().max() / want.abs().max()
+            assert e < (1e-4 if prec == "fp32" else 2e-2), (prec, float(e))
 
 
 # --------------------------------------------------------------------------- whole model against the reference's golden vectors
@@ -973,7 +984,8 @@ def test_ctc_full_size_b32_config1_matches_reference(precision):
     model = lb.NDT1(cfg, **kw, precision=precision)
     names = [n for n, _ in model.named_parameters()]
     assert names == list(g["names"])
-    assert np.array_equal(np.array([float(p.detach().double().sum()) for p in model.parameters()]), g["param_sum"])   # the reference's init, bit for bit (summed on the CPU, like the fixture)
+    # the reference's init (same draws in the same order; the float64 sums differ in the last bits with the host's thread count)
+    assert np.allclose(np.array([float(p.detach().double().sum()) for p in model.parameters()]), g["param_sum"], rtol=1e-11, atol=1e-11)
     model = model.to(DEV).train()
     batch = cuda_batch(O.synthetic_ctc_batch(B=32, T=1000, N=256, seed=1))
     out = model(**batch)
@@ -1004,7 +1016,7 @@ def test_ssl_full_size_config0_matches_reference(precision):
     model = lb.NDT1(cfg, **SSL_KW, precision=precision)
     names = [n for n, _ in model.named_parameters()]
     assert names == list(g["names"])
-    assert np.array_equal(np.array([float(p.detach().double().sum()) for p in model.parameters()]), g["param_sum"])
+    assert np.allclose(np.array([float(p.detach().double().sum()) for p in model.parameters()]), g["param_sum"], rtol=1e-11, atol=1e-11)
     model = model.to(DEV).train()
     batch = cuda_batch(O.synthetic_ssl_batch())
     spikes0 = batch["spikes"].clone()
@@ -1021,3 +1033,105 @@ def test_ssl_full_size_config0_matches_reference(precision):
     gtol = tol if precision == "fp32" else max(tol, float(g["autocast/grad_l2_max"]))
     worst = check_full_fixture(g, grads_of(model), names, gtol)
     print(f"ssl_full_b16 {precision}: loss {float(out.loss):.3f} (ref {float(g['out/loss']):.3f}), worst grad-norm rel err {worst:.3e}, bound {gtol:.3e}")
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.4])
+def test_whole_step_cuda_graph_matches_eager_steps(dropout):
+    """the step (prologue + forward + backward) captured into a CUDA graph and replayed, with the Philox keys in
+    device memory and the optimizer outside the graph behind external event nodes, against the same steps run eagerly.
+    Same torch seed -> same noise and dropout draws in both modes; only the arrival order of the split-K atomics differs."""
+    tr = lb.default_trainer_config()
+    cfg = lb.update_config(tr.model, {"encoder": {"embedder": {"dropout": dropout / 2}, "transformer": {"dropout": dropout, "n_layers": 2},
+                                                  "smooth_and_noise": {"noise": dropout > 0}}})
+    batch = cuda_batch(O.synthetic_ctc_batch(B=4, T=400, N=256, seed=2))
+    runs = []
+    for use_graph in (False, True):
+        torch.manual_seed(5)
+        model = lb.NDT1(cfg, **tr.method.model_kwargs, precision="bf16").to(DEV)
+        trainer = lb.DataParallelTrainer(model, lr=1e-3, wd=5e-5, eps=1e-3, scheduler="cosine", total_steps=20, use_graph=use_graph)
+        torch.manual_seed(9)
+        losses = []
+        for _ in range(6):
+            out = trainer.train_step(batch)
+            losses.append(float(out.loss))
+        trainer.synchronize()
+        torch.cuda.synchronize()
+        runs.append((losses, trainer.flat_param.clone(), trainer))
+    (l0, p0, t0), (l1, p1, t1) = runs
+    assert len(t1._graphs) == 1 and "graph" in next(iter(t1._graphs.values())) and t1.replayed_launches > 0 and t0.replayed_launches == 0
+    assert len(set(l1)) == 6                                       # every replay saw new parameters (and new draws)
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 2e-3 * abs(a), (l0, l1)
+    assert float((p0 - p1).abs().max()) <= 2e-3 * float(p0.abs().max())
+    assert float(t1.flat_grad.abs().max()) == 0.0
+    # a forward outside the trainer draws its own key again, and an eval forward between steps does not disturb the replays
+    model = t1.model
+    model.eval()
+    with torch.no_grad():
+        ev = float(model(**batch).loss)
+    assert np.isfinite(ev)
+    nxt = float(t1.train_step(batch).loss)
+    assert np.isfinite(nxt) and nxt != l1[-1]
+
+
+# --------------------------------------------------------------------------- round 2: BCI coupler (SURVEY 8 f3, BASELINE configs[4])
+def _debug_llama(seed=0):
+    from transformers import AutoModelForCausalLM, LlamaConfig
+    torch.manual_seed(seed)
+    return AutoModelForCausalLM.from_config(LlamaConfig(num_hidden_layers=2, hidden_size=32, intermediate_size=32, num_attention_heads=4))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["s2_relu", "s3_gelu"])
+def test_bci_coupler_matches_reference(name, precision):
+    """BCI.prepare_embeds (models/bci.py:107-168): encoder -> pad / stack -> projector MLP -> stacked mask -> splice into the prompt,
+    outputs and gradients (through ndt1_linear_bwd, ndt1_unsplice_rows and ndt1_engine_backward_features) against the unmodified
+    reference run with its debug LLaMA."""
+    g = load("bci_coupler.npz")
+    i = cuda_batch({k: torch.from_numpy(v) for k, v in sub(g, f"{name}/in").items()})
+    model = lb.BCI(bci_cfg(name), llm=_debug_llama(), method_name="ctc", vocab_size=41, blank_id=0, zero_infinity=True, precision=precision)
+    sd = {k: torch.from_numpy(v) for k, v in sub(g, f"{name}/param").items()}
+    missing = model.load_state_dict(sd, strict=False)
+    assert all(k.startswith("llm.") or k.startswith("ndt1.decoder") for k in missing.missing_keys) and not missing.unexpected_keys
+    model = model.to(DEV).train()
+    # the language model's own embedding lookup is an input of the coupler: feed the reference's values
+    model.llm.get_input_embeddings().weight.data.zero_()
+    text = i["text_embeds"]
+    model.llm.get_input_embeddings().weight.data[i["input_ids"].reshape(-1)] = text.reshape(-1, text.shape[-1]).to(model.llm.dtype)
+    emb, am, tg = model.prepare_embeds(i["input_ids"], i["attention_mask"], i["input_split"], i["spikes"], i["spikes_mask"], i["spikes_timestamp"],
+                                       i["spikes_lengths"], None, None, i["targets"])
+    assert torch.equal(am.cpu(), torch.from_numpy(g[f"{name}/out/attention_mask"])) and torch.equal(tg.cpu(), torch.from_numpy(g[f"{name}/out/targets"]))
+    ref = g[f"{name}/out/embeds"]
+    tol = TOL[precision]
+    assert np.abs(emb.detach().cpu().numpy() - ref).max() <= (2e-4 if precision == "fp32" else 3e-2) * np.abs(ref).max()
+    (emb * i["R"]).sum().backward()
+    got = {n: (p.grad.detach().cpu() if p.grad is not None else torch.zeros_like(p).cpu()) for n, p in model.named_parameters()
+           if n.startswith("ndt1.encoder.") or n.startswith("projector.")}
+    worst = check_grads(got, sub(g, f"{name}/grad"), tol)
+    print(f"bci {name} {precision}: worst per-tensor rel-L2 {worst[1]:.3e} ({worst[0]})")
+
+
+def test_bci_end_to_end_trains_through_the_llm():
+    """BCI.forward with the debug LLaMA (fp16): finite summed cross-entropy near the reference's, gradients reach the encoder, and the
+    checkpoint files of models/bci.py:253-260 round-trip."""
+    g = load("bci_coupler.npz")
+    name = "s2_relu"
+    i = cuda_batch({k: torch.from_numpy(v) for k, v in sub(g, f"{name}/in").items()})
+    model = lb.BCI(bci_cfg(name), debug=True, method_name="ctc", vocab_size=41, blank_id=0, zero_infinity=True, precision="fp32")
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, f"{name}/param").items()}, strict=False)
+    model = model.to(DEV).train()
+    out = model(i["input_ids"], i["attention_mask"], i["input_split"], i["spikes"], i["spikes_mask"], i["spikes_timestamp"], i["spikes_lengths"],
+                None, None, i["targets"])
+    assert int(out.n_examples) == int(g[f"{name}/out/n_examples"]) and out.preds.shape[:2] == (3, 19)
+    # (another random LLaMA than the reference run's: only the scale is comparable: n * ln(vocab) = 15 * 10.37)
+    assert np.isfinite(float(out.loss)) and abs(float(out.loss) - float(g[f"{name}/out/loss"])) < 0.1 * float(g[f"{name}/out/loss"])
+    out.loss.backward()
+    assert float(model.ndt1.encoder.layers[0].attn.query.weight.grad.abs().max()) > 0 and float(model.projector[0].weight.grad.abs().max()) > 0
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        model.save_checkpoint(d)
+        assert {"encoder.bin", "encoder_config.pth", "decoder.bin", "projector.bin", "projector_config.pth"} <= set(os.listdir(d))
+        before = model.projector[2].weight.detach().clone()
+        model.projector[2].weight.data.zero_()
+        model.load_checkpoint(d)
+        assert torch.equal(model.projector[2].weight.detach().cpu(), before.cpu())

@@ -221,7 +221,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     probes = {
         "ndt1_config": (_C.Config, ["abi_version", "rope_theta", "context_forward", "factors_active", "method", "p_embed", "max_targets"]),
         "ndt1_tensors": (_C.Tensors, ["embed_w", "day_emb", "embed_w_day", "embed_b_day", "layer", "out_norm_w", "dec_b"]),
-        "ndt1_batch": (_C.Batch, ["spikes", "targets_mask", "B", "encoder_only", "seed"]),
+        "ndt1_batch": (_C.Batch, ["spikes", "targets_mask", "B", "encoder_only", "seed", "seed_ptr"]),
         "ndt1_outputs": (_C.Outputs, ["loss", "features"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "ndt1_b200.h")}"', "int main(void) {"]
