@@ -456,6 +456,9 @@ def bci_case():
         d[f"{name}/out/embeds"] = embeds.detach().float().numpy()
         d[f"{name}/out/attention_mask"] = amask.numpy()
         d[f"{name}/out/targets"] = tgo.numpy()
+        # (the reference cannot run prepare_embeds under CPU bf16 autocast -- torch.cat of its fp16 prompt embeddings with bf16 features
+        #  raises "Unexpected floating ScalarType in at::autocast::prioritize" -- so the bf16 yardstick of the ReLU projector is the
+        #  ReLU-factors case of autocast_error_cases, the same mechanism)
         # end to end through the fp16 LLaMA (CPU half arithmetic: a loose yardstick only)
         m.zero_grad()
         out = m(ids, am, split, spikes.clone(), mask, ts, lens, None, None, tg)
