@@ -275,8 +275,9 @@ int ndt1_stack_valid(const int64_t* mask, int64_t* out, int B, int T, int stacki
 }
 
 size_t ndt1_attention_workspace_bytes(int B, int L, int n_heads) {
+  // delta (B, heads, L) floats | probability keep bits (B, heads, L, 8) u32 | output keep bits (B * L, 4 * heads) u32
   const size_t nrow = ((size_t)B * n_heads * L + 3) / 4 * 4;
-  return nrow * 4 + (size_t)B * n_heads * L * 8 * 4;
+  return nrow * 4 + (size_t)B * n_heads * L * 8 * 4 + (size_t)B * L * n_heads * 4 * 4;
 }
 
 int ndt1_attention_bf16(const void* qkv, void* out, void* out_drop, float* lse, const int64_t* key_valid, int B, int L, int H, int n_heads,
@@ -293,10 +294,12 @@ int ndt1_attention_bf16(const void* qkv, void* out, void* out_drop, float* lse, 
   // workspace layout: delta (B, heads, L) floats, then the keep bits (B, heads, L, 8) u32 on a 16-byte boundary
   const long long nrow = ((long long)B * n_heads * L + 3) / 4 * 4;
   ap.drop_bits = delta_ws ? (unsigned int*)(delta_ws + nrow) : nullptr;
+  ap.drop_bits_o = delta_ws ? ap.drop_bits + (long long)B * n_heads * L * 8 : nullptr;
+  ap.bits_ready = 0;
   cudaStream_t s = (cudaStream_t)stream;
   const bool tcp = use_tensor_cores && k_attention_tc_supported(ap);
   NDT1_REQUIRE(!use_tensor_cores || tcp, "attention_bf16: tensor-core path needs head size 128 and at most 256 tokens");
-  NDT1_REQUIRE(!(tcp && p_attn > 0.f) || delta_ws, "attention_bf16: the tensor-core path with dropout needs the workspace");
+  NDT1_REQUIRE(!(tcp && (p_attn > 0.f || p_out > 0.f)) || delta_ws, "attention_bf16: the tensor-core path with dropout needs the workspace");
   if (tcp) NDT1_TRY(k_attention_tc_fwd(ap, s)); else NDT1_TRY(k_attention_fwd<bf16>(ap, s));
   if (dout) {
     NDT1_REQUIRE(dqkv && delta_ws, "attention_bf16: backward needs dqkv and delta_ws");

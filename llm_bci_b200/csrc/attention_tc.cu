@@ -18,6 +18,7 @@
 // element-indexed Philox streams, so both implementations draw identical masks.
 // Other shapes use the CUDA-core kernels of attention.cu.
 #include <stdlib.h>
+#include <string.h>
 #include "tc_common.cuh"
 #include "kernels.cuh"
 
@@ -119,6 +120,33 @@ __device__ __forceinline__ void st_global8(bf16* dst, const float* v) {
 }
 
 // ---------------------------------------------------------------------------
+// Dropout keep bits, all layers of a forward in one launch (one thread per 32-bit word).
+//   bits_p[l] (B, nh, L, 8): bit j%32 of word j/32 of row (b, h, i) = probability (i, j) kept   (element index (row * L + j))
+//   bits_o[l] (B*L, H/32)  : bit c%32 of word c/32 of row r = output element (r, c) kept        (element index r * H + c)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_dropbits_kernel(const AttnBitsJob job, SeedRef seed_ref, long long rows_p, int L, long long rows_o, int H,
+                                                            uint32_t thr_p, uint32_t thr_o) { pdl_grid_sync();
+  const unsigned long long seed = seed_ref.get();
+  const int l = blockIdx.y;
+  const long long words_p = job.bits_p[l] ? rows_p * 8 : 0, words_o = job.bits_o[l] ? rows_o * (H / 32) : 0;
+  const bool aligned = (L & 7) == 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words_p + words_o; i += (long long)gridDim.x * blockDim.x) {
+    if (i < words_p) {
+      const long long row = i >> 3; const int c0 = (int)(i & 7) * 32;
+      uint32_t w = 0u;
+      if (c0 < L) {
+        w = keep_word32(seed, job.stream_p[l], (unsigned long long)row * (unsigned long long)L + c0, thr_p, aligned);
+        if (c0 + 32 > L) w &= 0xFFFFFFFFu >> (c0 + 32 - L);
+      }
+      job.bits_p[l][i] = w;
+    } else {
+      const long long j = i - words_p;
+      job.bits_o[l][j] = keep_word32(seed, job.stream_o[l], (unsigned long long)j * 32ull, thr_o, true);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // forward.  256 threads: warp w owns TMEM lanes 32*(w%4).. (one query row per lane) and the
 // key columns [128*(w/4), +128) of that row; the two halves of a row meet through smem.
 //
@@ -126,10 +154,13 @@ __device__ __forceinline__ void st_global8(bf16* dst, const float* v) {
 // second resident CTA is what hides it): shared memory holds only Q and ONE 64 KB K/V buffer (V
 // is fetched into it once S = Q K^T has retired), and tensor memory holds 256 columns:
 //   S  fp32  columns [0, 256)
-//   P  bf16  packed two keys per column, written IN PLACE behind each thread's read pointer:
-//            keys [0,128) -> columns [0,64), keys [128,256) -> columns [128,192)
-//   O  fp32  head-dim halves in the columns P leaves free: [64,128) and [192,256)
-// P never touches shared memory: the P V product takes its A operand from tensor memory.
+//   P  bf16  packed two keys per column, written IN PLACE behind each thread's read pointer.  The thread of keys
+//            [0,128) walks its columns upwards and packs into [0,64); the thread of keys [128,256) walks DOWNWARDS and
+//            packs into [192,256): what stays free is ONE contiguous block
+//   O  fp32  columns [64, 192): a single 128 x 128 accumulator, so P V is 16 MMAs of N = 128 (an MMA costs ~60 ns to
+//            issue whatever its N: two N = 64 halves would take twice as long)
+// P never touches shared memory: the P V product takes its A operand from tensor memory.  Nothing here draws a random
+// number: the keep bits of both dropout sites come from attn_dropbits_kernel (1 / (1 - p) is folded into the final scale).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map256,
@@ -149,16 +180,19 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   const int L = p.L, H = p.H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, half = warp >> 2;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&bars[0], 32768 + 65536);               // the loads fly while the CTA sets itself up
+    for (int c = 0; c < 2; ++c) tma_load_3d(sQ + c * 16384, &map128, &bars[0], h * HD + 64 * c, q0, b);
+    for (int c = 0; c < 2; ++c) tma_load_3d(sKV + c * 32768, &map256, &bars[0], H + h * HD + 64 * c, 0, b);
+  }
   {
     const int j = warp * 32 + lane;
     const uint32_t w = __ballot_sync(0xffffffffu, j < L && p.key_valid[(long long)b * L + j] != 0);
     if (lane == 0) s_kvw[warp] = w;
   }
-  if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -166,9 +200,6 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   const int nks = (L + 15) / 16;            // key steps of 16 actually holding keys
 
   if (tid == 0) {
-    mbar_expect_tx(&bars[0], 32768 + 65536);
-    for (int c = 0; c < 2; ++c) tma_load_3d(sQ + c * 16384, &map128, &bars[0], h * HD + 64 * c, q0, b);
-    for (int c = 0; c < 2; ++c) tma_load_3d(sKV + c * 32768, &map256, &bars[0], H + h * HD + 64 * c, 0, b);
     mbar_wait(&bars[0], 0);
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16(128, 256, false, false);
@@ -180,6 +211,27 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
     tc_commit(&bars[2]);
   }
   __syncwarp();
+
+  // everything that does not need S is fetched while the tensor core forms it
+  const int row = quarter * 32 + lane;
+  const int qi = q0 + row;
+  const int cbase = half * 128;
+  const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+  const float sl2 = p.scale * kLog2e;
+  const bool drop = p.p_attn > 0.f;
+  const long long bh_row = ((long long)b * p.nh + h) * L + qi;
+  uint32_t mw[4], kwv[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    mw[c] = query_mask_word(qi, cbase + 32 * c, a.cf, a.cb, s_kvw[half * 4 + c], L);
+    kwv[c] = (drop && qi < L) ? __ldg(p.drop_bits + bh_row * 8 + half * 4 + c) : 0xFFFFFFFFu;
+  }
+  uint32_t ow[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};          // keep bits of the output dropout: head-dim columns [64 half + 32 cc, +32)
+  if (p.p_out > 0.f && qi < L) {
+    const unsigned int* wo = p.drop_bits_o + ((long long)b * L + qi) * (H / 32) + (h * HD + half * 64) / 32;
+    ow[0] = __ldg(wo); ow[1] = __ldg(wo + 1);
+  }
+
   mbar_wait(&bars[2], 0);
   tc_fence_after();
   if (tid == 0) {                           // K is consumed: V takes its place while the softmax runs
@@ -187,14 +239,6 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
     for (int c = 0; c < 2; ++c) tma_load_3d(sKV + c * 32768, &map256, &bars[1], 2 * H + h * HD + 64 * c, 0, b);
   }
 
-  const int row = quarter * 32 + lane;
-  const int qi = q0 + row;
-  const int cbase = half * 128;
-  const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
-  const float sl2 = p.scale * kLog2e;
-  uint32_t mw[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) mw[c] = query_mask_word(qi, cbase + 32 * c, a.cf, a.cb, s_kvw[half * 4 + c], L);
   float m = -INFINITY;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
@@ -204,8 +248,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
       tmem_ld32(trow + c0, raw);
       tmem_ld_wait();
       const uint32_t w = mw[c];
+      if (w == 0xFFFFFFFFu) {                         // (the common case: nothing masked in this word)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) m = fmaxf(m, (w >> j) & 1u ? __uint_as_float(raw[j]) : -INFINITY);
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(raw[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, (w >> j) & 1u ? __uint_as_float(raw[j]) : -INFINITY);
+      }
     }
   }
   s_m[half * 128 + row] = m;
@@ -213,40 +262,35 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   m = fmaxf(s_m[row], s_m[128 + row]);
   const float m_s = (m == -INFINITY) ? 0.f : m * sl2;
   float l = 0.f;
-  const bool drop = p.p_attn > 0.f;
-  const unsigned long long seed = (drop || p.p_out > 0.f) ? p.seed.get() : 0ull;
-  const uint32_t thr = drop_threshold(p.p_attn);
-  const float ik = drop ? 1.0f / (1.0f - p.p_attn) : 1.f;
-  const long long bh_row = ((long long)b * p.nh + h) * L + qi;
-  const unsigned long long ebase = (unsigned long long)bh_row * (unsigned long long)L;
-  const bool aligned = (L & 7) == 0;
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int ci = 0; ci < 4; ++ci) {
+    const int c = half ? 3 - ci : ci;                 // keys [128,256): downwards, so that the packed P trails the read pointer from above
     const int c0 = cbase + 32 * c;
     uint32_t pk[16];
     if (c0 < L) {
-      uint32_t kw = 0xFFFFFFFFu;
-      if (drop) {
-        kw = keep_word32(seed, p.stream_attn, ebase + c0, thr, aligned);
-        if (p.drop_bits && qi < L) p.drop_bits[bh_row * 8 + (c0 >> 5)] = kw;
-      }
       uint32_t raw[32];
       tmem_ld32(trow + c0, raw);
       tmem_ld_wait();
-      const uint32_t w = mw[c];
+      const uint32_t w = mw[c], kw = kwv[c];
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        const float s0 = fmaf(__uint_as_float(raw[j]), sl2, -m_s), s1 = fmaf(__uint_as_float(raw[j + 1]), sl2, -m_s);
-        const float e0 = ex2f((w >> j) & 1u ? s0 : -INFINITY), e1 = ex2f((w >> (j + 1)) & 1u ? s1 : -INFINITY);
+        float s0 = fmaf(__uint_as_float(raw[j]), sl2, -m_s), s1 = fmaf(__uint_as_float(raw[j + 1]), sl2, -m_s);
+        if (w != 0xFFFFFFFFu) { s0 = (w >> j) & 1u ? s0 : -INFINITY; s1 = (w >> (j + 1)) & 1u ? s1 : -INFINITY; }
+        const float e0 = ex2f(s0), e1 = ex2f(s1);
         l += e0 + e1;
-        pk[j >> 1] = pack_bf16x2((kw >> j) & 1u ? e0 * ik : 0.f, (kw >> (j + 1)) & 1u ? e1 * ik : 0.f);
+        uint32_t pr = pack_bf16x2(e0, e1);
+        if (drop) {       // dropped probabilities become +0 (all-ones / all-zeros half-word masks from the two keep bits)
+          const uint32_t lo = (uint32_t)((int32_t)(kw << (31 - j)) >> 31), hi = (uint32_t)((int32_t)(kw << (30 - j)) >> 31);
+          pr &= (lo & 0x0000FFFFu) | (hi & 0xFFFF0000u);
+        }
+        pk[j >> 1] = pr;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) pk[j] = 0u;
     }
     // P in place: 16 packed columns behind this thread's read pointer (see the layout above)
-    if (c0 < nks * 16) tmem_st16(trow + cbase + 16 * c, pk);
+    if (c0 < nks * 16) tmem_st16(trow + (half ? 192 : 0) + 16 * c, pk);
   }
   tmem_st_wait();
   s_l[half * 128 + row] = l;
@@ -255,12 +299,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   if (tid == 0) {
     mbar_wait(&bars[1], 0);
     tc_fence_after();
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, false, true);
-    const uint64_t vd = make_sdesc(smem_u32(sKV), 32768, 1024);
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
+    const uint64_t vd = make_sdesc(smem_u32(sKV), 32768, 1024);       // V as the MN-major operand: two 64-column chunks 32 KB apart
     for (int ks = 0; ks < nks; ++ks) {
-      const uint32_t pa = tmem + (ks < 8 ? ks * 8 : 128 + (ks - 8) * 8);
+      const uint32_t pa = tmem + (ks < 8 ? ks * 8 : 192 + (ks - 8) * 8);
       tc_mma_bf16_ts(tmem + 64, pa, sdesc_advance(vd, ks * 2048), idesc, ks > 0 ? 1u : 0u);
-      tc_mma_bf16_ts(tmem + 192, pa, sdesc_advance(vd, 32768 + ks * 2048), idesc, ks > 0 ? 1u : 0u);
     }
     tc_commit(&bars[3]);
   }
@@ -269,7 +312,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   mbar_wait(&bars[3], 0);
   tc_fence_after();
   const float inv = (l > 0.f) ? 1.f / l : 0.f;
-  const uint32_t thr_o = drop_threshold(p.p_out);
+  const float inv_p = drop ? inv / (1.0f - p.p_attn) : inv;          // the 1 / (1 - p) of the probability dropout
   const float iko = p.p_out > 0.f ? 1.0f / (1.0f - p.p_out) : 1.f;
   // V is dead: its buffer stages the output tile (and its dropped copy) as SWIZZLE_128B tiles for bulk tensor stores
   // (coalesced, asynchronous; rows past the sequence end are clipped by the tensor map)
@@ -279,22 +322,20 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   for (int cc = 0; cc < 2; ++cc) {
     const int c0 = half * 64 + cc * 32;               // head-dim column
     uint32_t raw[32];
-    tmem_ld32(trow + (half ? 192 : 64) + cc * 32, raw);
+    tmem_ld32(trow + 64 + c0, raw);
     tmem_ld_wait();
-    const long long o = ((long long)b * L + qi) * H + h * HD + c0;    // element index of the dropout stream
+    const uint32_t wo = ow[cc];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g * 8 + i]) * inv;
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g * 8 + i]) * inv_p;
       st_row8(sOut, row, c0 + g * 8, v);
-      if (p.p_out > 0.f) {
-        float ds[8];
-        drop_scale_8(seed, p.stream_out, (unsigned long long)(o + g * 8), thr_o, iko, ds);
+      if (two) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] *= ds[i];
+        for (int i = 0; i < 8; ++i) v[i] = (wo >> (g * 8 + i)) & 1u ? v[i] * iko : 0.f;
+        st_row8(sOutD, row, c0 + g * 8, v);
       }
-      if (two) st_row8(sOutD, row, c0 + g * 8, v);
     }
   }
   fence_async_smem();
@@ -309,7 +350,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 // ---------------------------------------------------------------------------
@@ -876,9 +917,30 @@ void k_attention_tc_set_timeline(unsigned long long* buf) { g_attn_dbg = buf; }
 
 bool k_attention_tc_supported(const AttnParams& p) { return p.hd == HD && p.L <= LMAX && p.L >= 1 && p.H % 8 == 0; }
 
+int k_attention_tc_dropbits(const AttnBitsJob& job, const AttnParams& p, cudaStream_t stream) {
+  NDT1_REQUIRE(job.n >= 1 && job.n <= 32, "attention_tc: %d layers in one keep-bit launch (max 32)", job.n);
+  NDT1_REQUIRE(p.H % 32 == 0, "attention_tc: hidden size %d must be a multiple of 32", p.H);
+  const long long rows_p = (long long)p.B * p.nh * p.L, rows_o = (long long)p.B * p.L;
+  const long long words = rows_p * 8 + rows_o * (p.H / 32);
+  if (words == 0) return 0;
+  const int bx = (int)((words + 255) / 256 < 148 * 4 ? (words + 255) / 256 : 148 * 4);
+  ndt1_launch(attn_dropbits_kernel, dim3(bx, job.n), 256, 0, stream, job, p.seed, rows_p, p.L, rows_o, p.H, drop_threshold(p.p_attn),
+              drop_threshold(p.p_out));
+  NDT1_CHECK_LAUNCH();
+  return 0;
+}
+
 int k_attention_tc_fwd(const AttnParams& p, cudaStream_t stream) {
   NDT1_REQUIRE(k_attention_tc_supported(p), "attention_tc: unsupported shape (head size %d, %d tokens)", p.hd, p.L);
   NDT1_TRY(gemm_tc_init());
+  NDT1_REQUIRE(p.p_attn <= 0.f || p.drop_bits, "attention_tc: probability dropout needs the drop_bits buffer");
+  NDT1_REQUIRE(p.p_out <= 0.f || p.out_drop == p.out || p.drop_bits_o, "attention_tc: output dropout needs the drop_bits_o buffer");
+  if (!p.bits_ready && (p.p_attn > 0.f || (p.p_out > 0.f && p.out_drop != p.out))) {      // stand-alone use: draw this layer's keep bits first
+    AttnBitsJob job; memset(&job, 0, sizeof(job));
+    job.n = 1; job.bits_p[0] = p.p_attn > 0.f ? p.drop_bits : nullptr; job.bits_o[0] = (p.p_out > 0.f && p.out_drop != p.out) ? p.drop_bits_o : nullptr;
+    job.stream_p[0] = p.stream_attn; job.stream_o[0] = p.stream_out;
+    NDT1_TRY(k_attention_tc_dropbits(job, p, stream));
+  }
   CUtensorMap m128, m256;
   NDT1_TRY(make_maps(p, &m128, &m256, nullptr));
   static bool attr = false;

@@ -75,6 +75,8 @@ struct Engine : ndt1_engine {
   std::vector<T*> h1, h2, qkv, att, attd, u, g;
   std::vector<float*> lse;
   std::vector<unsigned int*> dropbits;   // keep bits of the attention-probability dropout (tensor-core path)
+  std::vector<unsigned int*> dropbits_o; // keep bits of the attention-output dropout (tensor-core path)
+  cudaEvent_t bits_fork_ev = nullptr, bits_done_ev = nullptr;
   T* hn = nullptr; T* fac = nullptr; T* fpre = nullptr;
   float* logits = nullptr; float* logp = nullptr; float* dlogits = nullptr; float* nll = nullptr; float* ctc_ws = nullptr;
   long long* key_valid = nullptr; long long* out_lens = nullptr;
@@ -126,12 +128,13 @@ struct Engine : ndt1_engine {
     }
     xs.resize(2 * NL + 1); mean.resize(2 * NL + 1); rstd.resize(2 * NL + 1);
     for (int i = 0; i < 2 * NL + 1; ++i) { xs[i] = ar.take<float>(Mm * H); mean[i] = ar.take<float>(Mm); rstd[i] = ar.take<float>(Mm); }
-    h1.resize(NL); h2.resize(NL); qkv.resize(NL); att.resize(NL); attd.resize(NL); u.resize(NL); g.resize(NL); lse.resize(NL); dropbits.resize(NL);
+    h1.resize(NL); h2.resize(NL); qkv.resize(NL); att.resize(NL); attd.resize(NL); u.resize(NL); g.resize(NL); lse.resize(NL); dropbits.resize(NL); dropbits_o.resize(NL);
     for (int l = 0; l < NL; ++l) {
       h1[l] = ar.take<T>(Mm * H); h2[l] = ar.take<T>(Mm * H); qkv[l] = ar.take<T>(Mm * 3 * H);
       att[l] = ar.take<T>(Mm * H); attd[l] = (k.p_transformer > 0.f) ? ar.take<T>(Mm * H) : att[l];
       u[l] = ar.take<T>(Mm * I); g[l] = ar.take<T>(Mm * I); lse[l] = ar.take<float>((long long)Bm * k.n_heads * Lm);
       dropbits[l] = (kBf16 && k.p_transformer > 0.f) ? ar.take<unsigned int>((long long)Bm * k.n_heads * Lm * 8) : nullptr;
+      dropbits_o[l] = (kBf16 && k.p_transformer > 0.f && H % 32 == 0) ? ar.take<unsigned int>(Mm * (H / 32)) : nullptr;
     }
     hn = ar.take<T>(Mm * H);
     if (k.factors_active) { fac = ar.take<T>(Mm * Hout); fpre = ar.take<T>(Mm * Hout); dfac = ar.take<T>(Mm * Hout); }
@@ -183,6 +186,8 @@ struct Engine : ndt1_engine {
     fork_ev.resize(6 * c.n_layers + 12);
     for (auto& e : fork_ev) NDT1_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     NDT1_CUDA_CHECK(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
+    NDT1_CUDA_CHECK(cudaEventCreateWithFlags(&bits_fork_ev, cudaEventDisableTiming));
+    NDT1_CUDA_CHECK(cudaEventCreateWithFlags(&bits_done_ev, cudaEventDisableTiming));
     if (kBf16 && !force_simt) NDT1_TRY(gemm_tc_init());
     if (c.use_rope) {
       // get_cos_sin (models/ndt1.py:44-53): inv_freq_i = base^(-2i/dim), angle = t * inv_freq_i, table = cat(angles, angles)
@@ -213,6 +218,8 @@ struct Engine : ndt1_engine {
     for (int i = 0; i < NDT1_MAX_LAYERS + 2; ++i) if (stage_ev[i]) cudaEventDestroy(stage_ev[i]);
     for (auto& e : fork_ev) if (e) cudaEventDestroy(e);
     if (join_ev) cudaEventDestroy(join_ev);
+    if (bits_fork_ev) cudaEventDestroy(bits_fork_ev);
+    if (bits_done_ev) cudaEventDestroy(bits_done_ev);
     if (wstream) cudaStreamDestroy(wstream);
     if (ar.base) cudaFree(ar.base);
   }
@@ -309,6 +316,24 @@ struct Engine : ndt1_engine {
     if (bt->seed_ptr) NDT1_CUDA_CHECK(cudaMemcpyAsync(seed_dev, bt->seed_ptr, 8, cudaMemcpyDeviceToDevice, s));
     else NDT1_TRY(k_set_i64((long long*)seed_dev, (long long)bt->seed, s));
     const SeedRef seed = SeedRef::at(seed_dev);
+    // The keep bits of the attention dropouts (probabilities and output, every layer) depend on the key only: one launch on the
+    // second stream, concurrent with the embedding GEMMs; the first attention layer waits for it.
+    const bool tc_attention = kBf16 && !force_simt && !simt_attention && (H / k.n_heads) == 128 && L <= 256 && L >= 1 && H % 32 == 0;
+    const bool draw_bits = tc_attention && ptr_ > 0.f;
+    if (draw_bits) {
+      AttnBitsJob job; memset(&job, 0, sizeof(job));
+      job.n = NL;
+      for (int l = 0; l < NL; ++l) {
+        job.bits_p[l] = dropbits[l]; job.bits_o[l] = dropbits_o[l];
+        job.stream_p[l] = site_attn_p(l); job.stream_o[l] = site_attn_o(l);
+      }
+      AttnParams shp; memset(&shp, 0, sizeof(shp));
+      shp.B = B; shp.L = L; shp.H = H; shp.nh = k.n_heads; shp.hd = H / k.n_heads; shp.p_attn = ptr_; shp.p_out = ptr_; shp.seed = seed;
+      cudaStream_t bs = overlap ? wstream : s;
+      if (overlap) { NDT1_CUDA_CHECK(cudaEventRecord(bits_fork_ev, s)); NDT1_CUDA_CHECK(cudaStreamWaitEvent(bs, bits_fork_ev, 0)); }
+      NDT1_TRY(k_attention_tc_dropbits(job, shp, bs));
+      if (overlap) NDT1_CUDA_CHECK(cudaEventRecord(bits_done_ev, bs));
+    }
 
     // 0. precision staging: bf16 copies of the weights and of the input
     if (kBf16) {
@@ -454,7 +479,8 @@ struct Engine : ndt1_engine {
       ap.B = B; ap.L = L; ap.H = H; ap.nh = k.n_heads; ap.hd = H / k.n_heads; ap.ctx_fwd = cf; ap.ctx_bwd = cb;
       ap.scale = 1.0f / sqrtf((float)(H / k.n_heads)); ap.p_attn = ptr_; ap.p_out = ptr_;
       ap.seed = seed; ap.stream_attn = site_attn_p(l); ap.stream_out = site_attn_o(l);
-      ap.dout = nullptr; ap.dqkv = nullptr; ap.delta = nullptr; ap.drop_bits = dropbits[l];
+      ap.dout = nullptr; ap.dqkv = nullptr; ap.delta = nullptr; ap.drop_bits = dropbits[l]; ap.drop_bits_o = dropbits_o[l]; ap.bits_ready = draw_bits;
+      if (l == 0 && draw_bits && overlap) NDT1_CUDA_CHECK(cudaStreamWaitEvent(s, bits_done_ev, 0));
       if (kBf16 && !force_simt && !simt_attention && k_attention_tc_supported(ap)) NDT1_TRY(k_attention_tc_fwd(ap, s));
       else NDT1_TRY(k_attention_fwd<T>(ap, s));
       {
@@ -694,7 +720,7 @@ struct Engine : ndt1_engine {
       ap.B = B; ap.L = L; ap.H = H; ap.nh = k.n_heads; ap.hd = H / k.n_heads; ap.ctx_fwd = cf; ap.ctx_bwd = cb;
       ap.scale = 1.0f / sqrtf((float)(H / k.n_heads)); ap.p_attn = ptr_; ap.p_out = ptr_;
       ap.seed = seed; ap.stream_attn = site_attn_p(l); ap.stream_out = site_attn_o(l);
-      ap.dout = dA; ap.dqkv = dqkv; ap.delta = delta; ap.drop_bits = dropbits[l];
+      ap.dout = dA; ap.dqkv = dqkv; ap.delta = delta; ap.drop_bits = dropbits[l]; ap.drop_bits_o = dropbits_o[l]; ap.bits_ready = 1;
       if (kBf16 && !force_simt && !simt_attention && k_attention_tc_supported(ap)) NDT1_TRY(k_attention_tc_bwd(ap, s));
       else NDT1_TRY(k_attention_bwd<T>(ap, s));
       if (k.use_rope) NDT1_TRY(k_rope<T>(dqkv, ts_ptr, Tn, rope_cos, rope_sin, M, L, H, k.n_heads, k.max_F, 1, s));   // transpose of the rotation

@@ -82,6 +82,9 @@ struct AttnParams {
   float* delta;             // (B, nh, L) scratch
   // tensor-core path, p_attn > 0: keep bits of the probability dropout, written by the forward, read by the backward
   unsigned int* drop_bits;  // (B, nh, L, 8) u32: bit j%32 of word j/32 = key j kept
+  unsigned int* drop_bits_o; // (B*L, H/32) u32: keep bits of the OUTPUT dropout (element (row, col) -> bit col%32 of word col/32), or null
+  int bits_ready;           // 1: drop_bits / drop_bits_o were already drawn for this forward (k_attention_tc_dropbits on a side
+                            //    stream, off the critical path); 0: the forward launcher draws them first
 };
 template <typename T> int k_attention_fwd(const AttnParams& p, cudaStream_t stream);
 template <typename T> int k_attention_bwd(const AttnParams& p, cudaStream_t stream);
@@ -90,6 +93,11 @@ template <typename T> int k_attention_delta(const AttnParams& p, cudaStream_t st
 bool k_attention_tc_supported(const AttnParams& p);
 int k_attention_tc_fwd(const AttnParams& p, cudaStream_t stream);
 int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream);
+// keep bits of the probability and output dropout of up to NDT1_MAX_LAYERS attention layers in ONE launch (same Philox draws as
+// drop_scale_1 of the CUDA-core kernels): they depend on the step's key only, so the engine draws them on its second stream
+// while the embedding GEMMs run, and no attention kernel spends an instruction on the generator
+struct AttnBitsJob { unsigned int* bits_p[32]; unsigned int* bits_o[32]; unsigned long long stream_p[32], stream_o[32]; int n; };
+int k_attention_tc_dropbits(const AttnBitsJob& job, const AttnParams& shape, cudaStream_t stream);
 void k_attention_tc_set_timeline(unsigned long long* buf);   // debugging: per-CTA phase timestamps (32 u64 per CTA), null = off
 
 // ctc.cu
