@@ -50,10 +50,12 @@ int ndt1_abi_version(void);
 /* SmoothAndNoise.forward, models/ndt1.py:92-107.
  * out[b,t,n] = sum_i taps[i]*x[b,t+i-(K-1)/2,n] + white_sd*W[b,t,n] + offset_sd*O[b,n]
  * taps: HOST pointer, K odd (0 = no smoothing).  white/offset: injected N(0,1)
- * draws (device) or NULL; with NULL and use_philox != 0 the kernel draws its own. */
+ * draws (device) or NULL; with NULL and use_philox != 0 the kernel draws its own (key = *seed_ptr when seed_ptr is
+ * non-NULL, read on the device, else seed).  out (fp32) and / or out_bf16 (row stride ld_bf16 elements): the bf16 copy is
+ * the operand of the channel-embedding GEMM, handed to the engine as ndt1_batch.spikes_bf16 so that no separate cast runs. */
 int ndt1_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps_host, int K, float white_sd,
                       float offset_sd, const float* white, const float* offset, int use_philox, uint64_t seed,
-                      const uint64_t* seed_ptr, void* stream);
+                      const uint64_t* seed_ptr, void* out_bf16, int ld_bf16, void* stream);
 
 /* Masker.forward given its random draws, models/masker.py:44-104, in place on
  * spikes (B,T,N).  mask_draw has the mode's own shape ((B,T) temporal, (B,N)
@@ -210,6 +212,8 @@ typedef struct {
   int32_t need_backward;          /* keep activations and loss gradients for ndt1_engine_backward */
   int32_t encoder_only;           /* stop after the encoder (NeuralEncoder.forward, models/ndt1.py:408-450): no head, no loss */
   uint64_t seed;                  /* Philox key of this step's dropout */
+  const void* spikes_bf16;        /* optional (bf16 mode): the input already as bf16 (B, T, n_channels), n_channels % 8 == 0, e.g. written by
+                                   * ndt1_smooth_noise; the engine then skips its own cast of `spikes`.  Must stay valid until the backward. */
   const uint64_t* seed_ptr;       /* optional: the key in DEVICE memory instead (read when the step executes, so a captured CUDA graph of
                                    * the step is replayed with a new key by updating that word); NULL = use `seed` */
 } ndt1_batch;

@@ -55,7 +55,7 @@ class Batch(C.Structure):
     _fields_ = [(n, _p) for n in ("spikes", "spikes_mask", "spikes_timestamp", "spikes_lengths", "block_idx", "day_idx",
                                   "targets", "targets_lengths", "recon_targets", "targets_mask")] + [
         ("B", C.c_int32), ("T", C.c_int32), ("S", C.c_int32), ("training", C.c_int32), ("need_backward", C.c_int32), ("encoder_only", C.c_int32),
-        ("seed", C.c_uint64), ("seed_ptr", _p)]
+        ("seed", C.c_uint64), ("spikes_bf16", _p), ("seed_ptr", _p)]
 
 
 class ProfileEntry(C.Structure):
@@ -71,7 +71,7 @@ _i, _i64, _u64, _f, _d, _sz = C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_dou
 PROTOTYPES = {
     "ndt1_last_error": (C.c_char_p, []),
     "ndt1_abi_version": (_i, []),
-    "ndt1_smooth_noise": (_i, [_p, _p, _i, _i, _i, C.POINTER(C.c_float), _i, _f, _f, _p, _p, _i, _u64, _p, _p]),
+    "ndt1_smooth_noise": (_i, [_p, _p, _i, _i, _i, C.POINTER(C.c_float), _i, _f, _f, _p, _p, _i, _u64, _p, _p, _i, _p]),
     "ndt1_masker_apply": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ndt1_bernoulli_u8": (_i, [_p, _i64, _f, _u64, _u64, _p]),
     "ndt1_uniform_f32": (_i, [_p, _i64, _u64, _u64, _p]),

@@ -76,9 +76,10 @@ extern "C" {
 
 int ndt1_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps_host, int K, float white_sd,
                       float offset_sd, const float* white, const float* offset, int use_philox, uint64_t seed, const uint64_t* seed_ptr,
-                      void* stream) {
+                      void* out_bf16, int ld_bf16, void* stream) {
   const SeedRef sr = seed_ptr ? SeedRef::at((const unsigned long long*)seed_ptr) : SeedRef((unsigned long long)seed);
-  return k_smooth_noise(x, out, B, T, N, taps_host, K, white_sd, offset_sd, white, offset, use_philox, sr, (cudaStream_t)stream);
+  return k_smooth_noise(x, out, B, T, N, taps_host, K, white_sd, offset_sd, white, offset, use_philox, sr, (cudaStream_t)stream, (bf16*)out_bf16,
+                        ld_bf16);
 }
 
 int ndt1_masker_apply(float* spikes, int B, int T, int N, int mode, int timespan, const uint8_t* mask_draw, const uint8_t* zero_draw,

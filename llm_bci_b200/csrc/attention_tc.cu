@@ -895,6 +895,244 @@ attn_tc_bwd_kv2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
   if (tid == 32) dbg_mark(a, 16);
 }
 
+// ---------------------------------------------------------------------------
+// backward, key side, PERSISTENT: the kv2 pipeline run over a list of (trial, head, key tile) items by one CTA per SM.
+// A CTA of kv2 lives ~10.5 us of which ~2.4 us pass before its first MMA (barriers, tensor-memory allocation, first loads) and
+// ~2 us after its last one (accumulator drain, stores, exit), and the next CTA starts ~1.4 us later: with 3.5 CTAs per SM that
+// is a third of the kernel.  Here tensor memory and barriers are set up once, the producer runs ahead across item boundaries
+// (the next item's first query chunks and its K / V tiles are in flight while the current item's last chunks are processed), the
+// MMA warp issues the next item's first S^T / dP^T as soon as the current item's products are queued, and the accumulator drain
+// of an item overlaps the next item's first products.
+//   shared memory: ONE K / V buffer (64 KB; K and V are operands of S^T / dP^T only, so it is reloaded as soon as the item's last
+//   S^T / dP^T have retired) + a ring of FOUR 32 KB query stages (Q chunk | dO chunk).  The two stages of an item's last two
+//   chunks double as the staging tiles of its dV / dK bulk stores; they return to the ring when the stores have read them.
+//   tensor memory: as kv2.
+// ---------------------------------------------------------------------------
+constexpr int KV3_QST = 4;
+constexpr int SMEM_BKV3 = 65536 + KV3_QST * 32768 + LMAX * 8 + LMAX * 16 + 256 + 1024;
+
+__global__ void __launch_bounds__(KV2_THREADS, 1)
+attn_tc_bwd_kv3_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map64,
+                       const __grid_constant__ CUtensorMap mapdo64, const __grid_constant__ CUtensorMap mapdqkv, const TcAttn a, const int n_items) {
+  pdl_grid_sync();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sK = smem;                          // 2 x [128 keys x 64 d]   32 KB
+  uint8_t* sV = sK + 32768;
+  uint8_t* sQ = sV + 32768;                    // ring: stages x { Q chunk 2 x [64 q x 64 d] (16 KB), dO chunk (16 KB) }
+  float2* s_ld = (float2*)(sQ + KV3_QST * 32768);          // [LMAX] (lse * log2e, delta) of every query of the current item
+  uint32_t* s_bits = (uint32_t*)(s_ld + LMAX);             // [LMAX][4] keep bits (query, 32-key word of this key tile)
+  uint64_t* bars = (uint64_t*)(s_bits + LMAX * 4);
+  uint64_t* kv_full = bars;                    // [1]  K / V of the item landed
+  uint64_t* kv_free = bars + 1;                // [1]  the item's last S^T / dP^T retired: the buffer may take the next item's tiles
+  uint64_t* q_full = bars + 2;                 // [4]
+  uint64_t* q_empty = bars + 6;                // [4]
+  uint64_t* s_full = bars + 10;                // [2]
+  uint64_t* p_full = bars + 12;                // [2]
+  uint64_t* acc_done = bars + 14;              // [1]  the item's dV / dK products retired
+  uint64_t* acc_free = bars + 15;              // [1]  the compute warps have read the accumulators
+  uint32_t* tmem_slot = (uint32_t*)(bars + 16);
+
+  const AttnParams& p = a.p;
+  const int L = p.L, H = p.H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nc = (L + KV2_CH - 1) / KV2_CH;            // query chunks per item (2..4)
+  const int nk = (L + TQ - 1) / TQ;                    // key tiles per (trial, head)
+  const bool drop = p.p_attn > 0.f;
+  const int my_items = blockIdx.x < n_items ? (n_items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  auto item_of = [&](int it, int& b, int& h, int& k0) {
+    const int item = blockIdx.x + it * gridDim.x;
+    const int kt = item % nk, bh = item / nk;
+    k0 = kt * TQ; h = bh % p.nh; b = bh / p.nh;
+  };
+
+  if (tid == 0) {
+    mbar_init(kv_full, 1); mbar_init(kv_free, 1);
+    for (int i = 0; i < KV3_QST; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], KV2_CWARPS); }
+    mbar_init(acc_done, 1); mbar_init(acc_free, KV2_CWARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: one flat stream of chunks over all items =====================
+    if (lane == 0) {
+      const int total = my_items * nc;
+      for (int g = 0; g < total; ++g) {
+        const int it = g / nc, c = g - it * nc;
+        int b, h, k0; item_of(it, b, h, k0);
+        const int kvpos = it == 0 ? 0 : (nc > 2 ? 2 : nc - 1);     // where in the item's chunk sequence its K / V tiles are fetched
+        if (c == kvpos) {
+          if (it > 0) mbar_wait(kv_free, (it - 1) & 1);
+          mbar_expect_tx(kv_full, 65536);
+          for (int d = 0; d < 2; ++d) tma_load_3d(sK + d * 16384, &map128, kv_full, H + h * HD + 64 * d, k0, b);
+          for (int d = 0; d < 2; ++d) tma_load_3d(sV + d * 16384, &map128, kv_full, 2 * H + h * HD + 64 * d, k0, b);
+        }
+        const int st = g % KV3_QST;
+        mbar_wait(&q_empty[st], ((g / KV3_QST) & 1) ^ 1);
+        uint8_t* dq = sQ + st * 32768;
+        mbar_expect_tx(&q_full[st], 32768);
+        for (int d = 0; d < 2; ++d) tma_load_3d(dq + d * 8192, &map64, &q_full[st], h * HD + 64 * d, c * KV2_CH, b);
+        for (int d = 0; d < 2; ++d) tma_load_3d(dq + 16384 + d * 8192, &mapdo64, &q_full[st], h * HD + 64 * d, c * KV2_CH, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && my_items > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, KV2_CH, false, false);
+      constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, false, true);
+      const uint64_t kd = make_sdesc(smem_u32(sK), 16, 1024), vd = make_sdesc(smem_u32(sV), 16, 1024);
+      auto issue_s = [&](int g) {               // S^T / dP^T of global chunk g (its item's K / V must be resident)
+        const int st = g % KV3_QST, bf = g & 1;
+        mbar_wait(&q_full[st], (g / KV3_QST) & 1);
+        tc_fence_after();
+        const uint64_t qd = make_sdesc(smem_u32(sQ + st * 32768), 16, 1024), dod = sdesc_advance(qd, 16384);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          tc_mma_bf16(tmem + bf * 128, sdesc_advance(kd, (ks >> 2) * 16384 + (ks & 3) * 32), sdesc_advance(qd, (ks >> 2) * 8192 + (ks & 3) * 32),
+                      idesc_s, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          tc_mma_bf16(tmem + bf * 128 + 64, sdesc_advance(vd, (ks >> 2) * 16384 + (ks & 3) * 32),
+                      sdesc_advance(dod, (ks >> 2) * 8192 + (ks & 3) * 32), idesc_s, ks > 0 ? 1u : 0u);
+        tc_commit(&s_full[bf]);
+      };
+      auto acc = [&](int g, int it, int c) {   // dV += P~^T dO, dK += dS^T Q of global chunk g
+        const int st = g % KV3_QST, bf = g & 1;
+        mbar_wait(&p_full[bf], (g >> 1) & 1);
+        if (c == 0 && it > 0) mbar_wait(acc_free, (it - 1) & 1);       // the previous item's accumulators have been read
+        tc_fence_after();
+        const uint64_t qm = make_sdesc(smem_u32(sQ + st * 32768), 8192, 1024), dom = sdesc_advance(qm, 16384);   // MN-major views
+#pragma unroll
+        for (int ks = 0; ks < KV2_CH / 16; ++ks)
+          tc_mma_bf16_ts(tmem + 256, tmem + bf * 128 + 16 * ks, sdesc_advance(dom, ks * 2048), idesc_acc, (c > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < KV2_CH / 16; ++ks)
+          tc_mma_bf16_ts(tmem + 384, tmem + bf * 128 + 64 + 16 * ks, sdesc_advance(qm, ks * 2048), idesc_acc, (c > 0 || ks > 0) ? 1u : 0u);
+        // the stage goes back to the ring when these retire -- except the item's last two, which stage its dV / dK stores first
+        if (c < nc - 2) tc_commit(&q_empty[st]);
+      };
+      mbar_wait(kv_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int it = 0; it < my_items; ++it) {
+        const int g0 = it * nc;
+        for (int c = 0; c < nc; ++c) {
+          if (c + 1 < nc) {
+            issue_s(g0 + c + 1);
+            if (c + 1 == nc - 1) tc_commit(kv_free);            // the item's last S^T / dP^T are queued: K / V may be replaced when they retire
+          }
+          acc(g0 + c, it, c);
+        }
+        tc_commit(acc_done);
+        if (it + 1 < my_items) {                                 // the next item's first products, while this item's accumulators drain
+          mbar_wait(kv_full, (it + 1) & 1);
+          tc_fence_after();
+          issue_s(g0 + nc);
+        }
+      }
+    }
+  } else {
+    // ===================== compute warps: lane = key, 16 query columns of the chunk per thread =====================
+    const int cw = warp - 2;
+    const int quarter = warp & 3, grp = cw >> 2;             // TMEM lane quarter; which 16 of the chunk's 64 queries
+    const int row = quarter * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    const float sl2 = p.scale * kLog2e;
+    const float ik = drop ? 1.0f / (1.0f - p.p_attn) : 1.f;
+    for (int it = 0; it < my_items; ++it) {
+      int b, h, k0; item_of(it, b, h, k0);
+      const long long bh0 = ((long long)b * p.nh + h) * L;
+      const int kj = k0 + row;
+      const bool kv_j = kj < L && p.key_valid[(long long)b * L + kj] != 0;
+      // per-query scalars and keep bits of this (trial, head): nobody reads the previous item's any more (barrier at its end)
+      for (int q = tid - 64; q < LMAX; q += 32 * KV2_CWARPS)
+        s_ld[q] = q < L ? make_float2(p.lse[bh0 + q] * kLog2e, p.delta[bh0 + q]) : make_float2(0.f, 0.f);
+      for (int q = tid - 64; q < LMAX; q += 32 * KV2_CWARPS) {
+        uint4 w = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (drop && q < L) w = *(const uint4*)(p.drop_bits + (bh0 + q) * 8 + (k0 >> 5));
+        *(uint4*)(s_bits + q * 4) = w;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * KV2_CWARPS) : "memory");
+      for (int c = 0; c < nc; ++c) {
+        const int g = it * nc + c, bf = g & 1;
+        const int qb = c * KV2_CH + grp * 16;                  // first query of this thread's columns
+        mbar_wait(&s_full[bf], (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t pk[8], dk[8];
+        if (qb < L) {                                          // warp-uniform
+          const uint32_t mw = key_mask_word(kj, qb & ~31, a.cf, a.cb, kv_j, L) >> (qb & 31);
+          uint32_t rs[16], rp[16];
+          tmem_ld16(trow + bf * 128 + grp * 16, rs);
+          tmem_ld16(trow + bf * 128 + 64 + grp * 16, rp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float pt[2], dst[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float2 ld = s_ld[qb + j + u];
+              const float sv = fmaf(__uint_as_float(rs[j + u]), sl2, -ld.x);
+              const float pr = ex2f((mw >> (j + u)) & 1u ? sv : -INFINITY);
+              const float dm = (s_bits[(qb + j + u) * 4 + quarter] >> lane) & 1u ? ik : 0.f;
+              pt[u] = pr * dm;
+              dst[u] = pr * p.scale * (__uint_as_float(rp[j + u]) * dm - ld.y);
+            }
+            pk[j >> 1] = pack_bf16x2(pt[0], pt[1]);
+            dk[j >> 1] = pack_bf16x2(dst[0], dst[1]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { pk[j] = 0u; dk[j] = 0u; }
+        }
+        tmem_st8(trow + bf * 128 + grp * 16, pk);               // in place: 8 packed columns inside this thread's own 16
+        tmem_st8(trow + bf * 128 + 64 + grp * 16, dk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[bf]);
+      }
+      // ---- this item's dV (cols 256..), dK (cols 384..): tensor memory -> registers -> the two free ring stages -> bulk stores
+      mbar_wait(acc_done, it & 1);
+      tc_fence_after();
+      const int g_last = it * nc + nc - 1;
+      uint8_t* tile_v = sQ + ((g_last - 1) % KV3_QST) * 32768;
+      uint8_t* tile_k = sQ + (g_last % KV3_QST) * 32768;
+      uint32_t r0[32], r1[32];
+      tmem_ld32(trow + 256 + grp * 32, r0);
+      tmem_ld32(trow + 384 + grp * 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);                    // the next item's products may overwrite the accumulators
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4) st_row8(tile_v, row, grp * 32 + g4 * 8, (const float*)r0 + g4 * 8);
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4) st_row8(tile_k, row, grp * 32 + g4 * 8, (const float*)r1 + g4 * 8);
+      fence_async_smem();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * KV2_CWARPS) : "memory");
+      if (tid == 64) {
+        for (int d = 0; d < 2; ++d) {
+          tma_store_3d(&mapdqkv, tile_v + d * 16384, 2 * H + h * HD + 64 * d, k0, b);
+          tma_store_3d(&mapdqkv, tile_k + d * 16384, H + h * HD + 64 * d, k0, b);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&q_empty[(g_last - 1) % KV3_QST]);         // the two stages return to the ring
+        mbar_arrive(&q_empty[g_last % KV3_QST]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 int make_maps(const AttnParams& p, CUtensorMap* m128, CUtensorMap* m256, CUtensorMap* mdo) {
   GemmOperand q; q.ptr = p.qkv; q.batch_stride = (long long)p.L * 3 * p.H; q.nbatch = p.B; q.rows = p.L; q.cols = 3 * p.H; q.ld = 3 * p.H;
   NDT1_TRY(tc_make_map(q, 64, 128, m128));
@@ -969,6 +1207,7 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BQ));
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV));
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV2));
+    NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV3));
     attr = true;
   }
   TcAttn a; a.p = p; a.cf = p.ctx_fwd; a.cb = p.ctx_bwd; a.dbg = g_attn_dbg;
@@ -993,6 +1232,15 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream) {
     NDT1_TRY(tc_make_map(q, 64, KV2_CH, &m64));
     NDT1_TRY(tc_make_map(d, 64, KV2_CH, &mdo64));
     if (g_ndt1_prof_on) ndt1_prof_note(2 * mm, 0.0);                // algorithmic: dV = P~^T dO and dK = dS^T Q
+    static const bool kv2_only = getenv("NDT1_ATTN_BWD_KV2") && getenv("NDT1_ATTN_BWD_KV2")[0] == '1';
+    if (!kv2_only && p.L > KV2_CH) {          // persistent pipeline (needs at least two query chunks per item for its store staging)
+      static int sms = 0;
+      if (!sms) { int dev = 0; NDT1_CUDA_CHECK(cudaGetDevice(&dev)); NDT1_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+      const int n_items = p.B * p.nh * ndt1_cdiv(p.L, TQ);
+      ndt1_launch(attn_tc_bwd_kv3_kernel, dim3(n_items < sms ? n_items : sms), KV2_THREADS, SMEM_BKV3, stream, m128, m64, mdo64, mdq, a, n_items);
+      NDT1_CHECK_LAUNCH();
+      return 0;
+    }
     ndt1_launch(attn_tc_bwd_kv2_kernel, grid, KV2_THREADS, SMEM_BKV2, stream, m128, m64, mdo64, mdq, a);
   }
   NDT1_CHECK_LAUNCH();

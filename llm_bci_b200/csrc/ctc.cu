@@ -12,6 +12,7 @@
 // is emitted by a parallel pass, so no separate log-softmax backward exists.
 // The kernel is latency-, not bandwidth-bound.
 #include "kernels.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -172,6 +173,11 @@ __device__ __forceinline__ void ctc_sweep(const CtcParams& p, const float* __res
   }
 }
 
+// (Measured dead end, round 2: the same sweep in the PROBABILITY domain -- two adds and a multiply per state and frame instead of
+// max / 3 ex2 / add / lg2, rows rescaled to a maximum of 1 every second frame -- cut the sweep from 92 to ~60 us, but is wrong as
+// soon as the network is confident: the row maximum sits on states that can no longer reach the end (all-blank prefixes), the
+// states of the correct alignment fall more than 2^126 below it and flush to zero, and the posteriors (alpha * beta) lose them:
+// gradient errors of order 1 at logit scales >= 12.  Per-frame scaling cannot fix a per-STATE dynamic range; the log domain stays.)
 // One CTA (8 warps) per trial.  Warp 0 sweeps alpha forward while warp 1 sweeps beta backward (L dependent steps,
 // not 2 L); then all warps turn alpha + beta into label posteriors, one frame per warp, and write the gradient
 // w.r.t. the logits.  The posterior of label c sums the states that carry c; the states are grouped by label once
@@ -444,7 +450,8 @@ int k_ctc_fwd_bwd(const float* logp, const long long* targets, const long long* 
   float* beta_ws = alpha_ws + (size_t)B * L * LX;
   double* offs = (double*)(((uintptr_t)(beta_ws + (size_t)B * L * LX) + 7) & ~(uintptr_t)7);
   CtcParams p{logp, targets, in_len, tgt_len, B, L, V, S, blank, zero_infinity, lp_in_smem, alpha_ws, beta_ws, nll, dlogits, dloss, offs};
-  if (fast_math) NDT1_TRY(ctc_dispatch<true>(p, spt, smem, stream));
+  static const int force_fast = getenv("NDT1_CTC_FAST") && getenv("NDT1_CTC_FAST")[0] == '1';      // debugging: the stand-alone operator in FAST mode
+  if (fast_math || force_fast) NDT1_TRY(ctc_dispatch<true>(p, spt, smem, stream));
   else NDT1_TRY(ctc_dispatch<false>(p, spt, smem, stream));
   if (loss) {
     ndt1_launch(sum_nll_kernel, 1, 32, 0, stream, nll, B, loss);

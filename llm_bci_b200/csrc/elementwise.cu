@@ -17,7 +17,8 @@ constexpr int SM_TT = 8;
 constexpr int SM_MAXK = 64;
 
 struct SmoothParams {
-  const float* x; float* out;
+  const float* x; float* out;            // out: fp32 result or null
+  bf16* out_bf16; int ld_bf16;           // and / or the bf16 GEMM operand of the channel embedding, written directly (row stride ld_bf16)
   int B, T, N, K;
   float w[SM_MAXK];
   float white_sd, offset_sd;
@@ -25,6 +26,14 @@ struct SmoothParams {
   int use_philox; SeedRef seed;
 };
 
+// White noise: ONE Philox block per four consecutive elements (all four words used): element e takes lane e % 2 of the Box-Muller
+// pair formed from words (x, y) for e % 4 < 2 and (z, w) otherwise.
+__device__ __forceinline__ float white_one(unsigned long long seed, unsigned long long e) {
+  const Philox4 r = philox4x32(seed, e >> 2, 0x77686974ULL);
+  float a, c;
+  if (e & 2) box_muller(r.z, r.w, a, c); else box_muller(r.x, r.y, a, c);
+  return (e & 1) ? c : a;
+}
 __global__ void smooth_noise_kernel(const SmoothParams p) { pdl_grid_sync();
   const unsigned long long seed = p.use_philox ? p.seed.get() : 0ull;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -32,7 +41,8 @@ __global__ void smooth_noise_kernel(const SmoothParams p) { pdl_grid_sync();
   const int b = blockIdx.z;
   if (n >= p.N) return;
   const float* xb = p.x + (long long)b * p.T * p.N + n;
-  float* ob = p.out + (long long)b * p.T * p.N + n;
+  float* ob = p.out ? p.out + (long long)b * p.T * p.N + n : nullptr;
+  bf16* ob16 = p.out_bf16 ? p.out_bf16 + (long long)b * p.T * p.ld_bf16 + n : nullptr;
   float off = 0.f;
   if (p.offset_sd != 0.f) {
     if (p.offset) off = p.offset_sd * p.offset[(long long)b * p.N + n];
@@ -60,13 +70,10 @@ __global__ void smooth_noise_kernel(const SmoothParams p) { pdl_grid_sync();
       if (p.white_sd != 0.f) {
         const unsigned long long e = ((unsigned long long)b * p.T + t) * p.N + n;
         if (p.white) v += p.white_sd * p.white[e];
-        else if (p.use_philox) {
-          Philox4 r = philox4x32(seed, e >> 1, 0x77686974ULL);
-          float a, c; box_muller(r.x, r.y, a, c);
-          v += p.white_sd * ((e & 1) ? c : a);
-        }
+        else if (p.use_philox) v += p.white_sd * white_one(seed, e);
       }
-      ob[(long long)t * p.N] = v;
+      if (ob) ob[(long long)t * p.N] = v;
+      if (ob16) ob16[(long long)t * p.ld_bf16] = __float2bfloat16_rn(v);
     }
   } else {
     for (int j = 0; j < SM_TT; ++j) {
@@ -76,13 +83,10 @@ __global__ void smooth_noise_kernel(const SmoothParams p) { pdl_grid_sync();
       if (p.white_sd != 0.f) {
         const unsigned long long e = ((unsigned long long)b * p.T + t) * p.N + n;
         if (p.white) v += p.white_sd * p.white[e];
-        else if (p.use_philox) {
-          Philox4 r = philox4x32(seed, e >> 1, 0x77686974ULL);
-          float a, c; box_muller(r.x, r.y, a, c);
-          v += p.white_sd * ((e & 1) ? c : a);
-        }
+        else if (p.use_philox) v += p.white_sd * white_one(seed, e);
       }
-      ob[(long long)t * p.N] = v;
+      if (ob) ob[(long long)t * p.N] = v;
+      if (ob16) ob16[(long long)t * p.ld_bf16] = __float2bfloat16_rn(v);
     }
   }
 }
@@ -90,31 +94,34 @@ __global__ void smooth_noise_kernel(const SmoothParams p) { pdl_grid_sync();
 // a warp reads 512 contiguous bytes) and a strip of SMV_TT bins, sliding a K-deep register window along time; one
 // Philox call per bin yields the four N(0,1) draws of its four channels (same element -> draw mapping as the
 // generic kernel: counter = element / 2 for consecutive element pairs... see white_pair()).
-constexpr int SMV_TT = 25;
+constexpr int SMV_TT = 13;     // one trip of the K = 13 window per thread: 77 strips per 1000-bin trial -> 4+ CTAs per SM at the benchmark shape
 __device__ __forceinline__ void white_quad(unsigned long long seed, unsigned long long e0, float* nz) {
-  // elements e0..e0+3 (e0 % 4 == 0): the generic kernel draws element e from Philox(seed, e >> 1): lane (e & 1) of box_muller(x, y)
-  const Philox4 r0 = philox4x32(seed, e0 >> 1, 0x77686974ULL);
-  const Philox4 r1 = philox4x32(seed, (e0 >> 1) + 1, 0x77686974ULL);
-  box_muller(r0.x, r0.y, nz[0], nz[1]);
-  box_muller(r1.x, r1.y, nz[2], nz[3]);
+  // elements e0..e0+3 (e0 % 4 == 0): one Philox block, the same element -> draw mapping as white_one()
+  const Philox4 r = philox4x32(seed, e0 >> 2, 0x77686974ULL);
+  box_muller(r.x, r.y, nz[0], nz[1]);
+  box_muller(r.z, r.w, nz[2], nz[3]);
 }
+// Two adjacent channels per thread (64-bit loads / stores, a warp reads 256 contiguous bytes of a bin) and a strip of SMV_TT
+// bins: 2 x K window registers per thread keep the kernel at three 256-thread CTAs per SM (the four-channel version held 104
+// window registers and ran ONE CTA per SM, i.e. latency-bound at 20 % of the HBM rate).
 template <int K>
-__global__ void __launch_bounds__(256) smooth_noise_vec_kernel(const SmoothParams p) { pdl_grid_sync();
+__global__ void __launch_bounds__(256, 3) smooth_noise_vec_kernel(const SmoothParams p) { pdl_grid_sync();
   const unsigned long long seed = p.use_philox ? p.seed.get() : 0ull;
-  const int n4 = blockIdx.x * 64 + (threadIdx.x & 63);          // channel quad
-  const int strip = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int n2 = blockIdx.x * 128 + (threadIdx.x & 127);        // channel pair
+  const int strip = blockIdx.y * 2 + (threadIdx.x >> 7);
   const int b = blockIdx.z;
   const int t0 = strip * SMV_TT;
-  if (n4 * 4 >= p.N || t0 >= p.T) return;
+  if (n2 * 2 >= p.N || t0 >= p.T) return;
   constexpr int half = (K - 1) / 2;
-  const float4* xb = (const float4*)(p.x + (long long)b * p.T * p.N) + n4;
-  float4* ob = (float4*)(p.out + (long long)b * p.T * p.N) + n4;
-  const int ld4 = p.N / 4;
-  float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float2* xb = (const float2*)(p.x + (long long)b * p.T * p.N) + n2;
+  float2* ob = p.out ? (float2*)(p.out + (long long)b * p.T * p.N) + n2 : nullptr;
+  bf16* ob16 = p.out_bf16 ? p.out_bf16 + (long long)b * p.T * p.ld_bf16 + n2 * 2 : nullptr;
+  const int ld2 = p.N / 2;
+  float2 off = make_float2(0.f, 0.f);
   if (p.offset_sd != 0.f) {
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = 0; c < 4; ++c) {
-      const unsigned long long e = (unsigned long long)b * p.N + n4 * 4 + c;
+    float o[2] = {0.f, 0.f};
+    for (int c = 0; c < 2; ++c) {
+      const unsigned long long e = (unsigned long long)b * p.N + n2 * 2 + c;
       if (p.offset) o[c] = p.offset_sd * p.offset[e];
       else if (p.use_philox) {
         Philox4 r = philox4x32(seed, e, 0x6f666673ULL);
@@ -122,72 +129,69 @@ __global__ void __launch_bounds__(256) smooth_noise_vec_kernel(const SmoothParam
         o[c] = p.offset_sd * a;
       }
     }
-    off = make_float4(o[0], o[1], o[2], o[3]);
+    off = make_float2(o[0], o[1]);
   }
   float w[K];
 #pragma unroll
   for (int i = 0; i < K; ++i) w[i] = p.w[i];
-  float4 win[K];                                   // win[i] = x[t + i - half]
+  float2 win[K];                                   // win[i] = x[t + i - half]
 #pragma unroll
   for (int i = 0; i < K - 1; ++i) {
     const int t = t0 + i - half;
-    win[i + 1] = (t >= 0 && t < p.T) ? __ldg(xb + (long long)t * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    win[i + 1] = (t >= 0 && t < p.T) ? __ldg(xb + (long long)t * ld2) : make_float2(0.f, 0.f);
   }
-#pragma unroll 1
-  for (int j0 = 0; j0 < SMV_TT; j0 += K) {         // K outputs per trip so that the window rotates at compile time
-    float4 nxt[K];                                 // the K rows this trip appends: all loads issued before the first use
+  float2 nxt[K];                                   // the K rows this strip appends: all loads issued before the first use
 #pragma unroll
-    for (int jj = 0; jj < K; ++jj) {
-      const int tn = t0 + j0 + jj + half;
-      nxt[jj] = (tn >= 0 && tn < p.T && j0 + jj < SMV_TT) ? __ldg(xb + (long long)tn * ld4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  for (int jj = 0; jj < K; ++jj) {
+    const int tn = t0 + jj + half;
+    nxt[jj] = (tn < p.T && jj < SMV_TT) ? __ldg(xb + (long long)tn * ld2) : make_float2(0.f, 0.f);
+  }
 #pragma unroll
-    for (int jj = 0; jj < K; ++jj) {
-      const int t = t0 + j0 + jj;
-      // slide: drop the oldest, append x[t + half]
+  for (int jj = 0; jj < SMV_TT; ++jj) {
+    const int t = t0 + jj;
 #pragma unroll
-      for (int i = 0; i < K - 1; ++i) win[i] = win[i + 1];
-      win[K - 1] = nxt[jj];
-      if (j0 + jj < SMV_TT && t < p.T) {
-        float4 acc = off;
+    for (int i = 0; i < K - 1; ++i) win[i] = win[i + 1];       // (compile-time rotation: the loop is fully unrolled)
+    win[K - 1] = nxt[jj];
+    if (t < p.T) {
+      float2 acc = off;
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-          acc.x = fmaf(w[i], win[i].x, acc.x); acc.y = fmaf(w[i], win[i].y, acc.y);
-          acc.z = fmaf(w[i], win[i].z, acc.z); acc.w = fmaf(w[i], win[i].w, acc.w);
+      for (int i = 0; i < K; ++i) { acc.x = fmaf(w[i], win[i].x, acc.x); acc.y = fmaf(w[i], win[i].y, acc.y); }
+      if (p.white_sd != 0.f) {
+        const unsigned long long e = ((unsigned long long)b * p.T + t) * p.N + n2 * 2;
+        if (p.white) {
+          const float2 wn = __ldg((const float2*)(p.white + e));
+          acc.x = fmaf(p.white_sd, wn.x, acc.x); acc.y = fmaf(p.white_sd, wn.y, acc.y);
+        } else if (p.use_philox) {           // this pair's half of the Philox block of its four-element group (white_one's mapping)
+          const Philox4 r = philox4x32(seed, e >> 2, 0x77686974ULL);
+          float z0, z1;
+          if (e & 2) box_muller(r.z, r.w, z0, z1); else box_muller(r.x, r.y, z0, z1);
+          acc.x = fmaf(p.white_sd, z0, acc.x); acc.y = fmaf(p.white_sd, z1, acc.y);
         }
-        if (p.white_sd != 0.f) {
-          const unsigned long long e = ((unsigned long long)b * p.T + t) * p.N + n4 * 4;
-          if (p.white) {
-            const float4 wn = __ldg((const float4*)(p.white + e));
-            acc.x = fmaf(p.white_sd, wn.x, acc.x); acc.y = fmaf(p.white_sd, wn.y, acc.y);
-            acc.z = fmaf(p.white_sd, wn.z, acc.z); acc.w = fmaf(p.white_sd, wn.w, acc.w);
-          } else if (p.use_philox) {
-            float nz[4];
-            white_quad(seed, e, nz);
-            acc.x = fmaf(p.white_sd, nz[0], acc.x); acc.y = fmaf(p.white_sd, nz[1], acc.y);
-            acc.z = fmaf(p.white_sd, nz[2], acc.z); acc.w = fmaf(p.white_sd, nz[3], acc.w);
-          }
-        }
-        ob[(long long)t * ld4] = acc;
       }
+      if (ob) ob[(long long)t * ld2] = acc;
+      if (ob16) { const __nv_bfloat162 o2 = __floats2bfloat162_rn(acc.x, acc.y); *(uint32_t*)(ob16 + (long long)t * p.ld_bf16) = *(const uint32_t*)&o2; }
     }
   }
 }
 }  // namespace
 
 int k_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps, int K, float white_sd, float offset_sd,
-                   const float* white, const float* offset, int use_philox, SeedRef seed, cudaStream_t stream) {
+                   const float* white, const float* offset, int use_philox, SeedRef seed, cudaStream_t stream, bf16* out_bf16, int ld_bf16) {
+  if ((long long)B * T * N == 0) return 0;
+  NDT1_REQUIRE(out || out_bf16, "smooth: no output buffer");
+  NDT1_REQUIRE(!out_bf16 || ld_bf16 >= N, "smooth: bf16 row stride %d < %d channels", ld_bf16, N);
   NDT1_REQUIRE(K >= 0 && K <= SM_MAXK - 1, "smooth: %d taps unsupported (max %d)", K, SM_MAXK - 1);
   NDT1_REQUIRE(K == 0 || (K % 2) == 1, "smooth: kernel length must be odd ('same' padding), got %d", K);
   if (B * T * N == 0) return 0;
   SmoothParams p;
-  p.x = x; p.out = out; p.B = B; p.T = T; p.N = N; p.K = K;
+  p.x = x; p.out = out; p.out_bf16 = out_bf16; p.ld_bf16 = ld_bf16; p.B = B; p.T = T; p.N = N; p.K = K;
   for (int i = 0; i < K; ++i) p.w[i] = taps[i];
   p.white_sd = white_sd; p.offset_sd = offset_sd; p.white = white; p.offset = offset;
   p.use_philox = use_philox; p.seed = seed;
-  if (K == 13 && N % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 && (!white || ((uintptr_t)white & 15) == 0)) {
-    dim3 grid(ndt1_cdiv(N / 4, 64), ndt1_cdiv(ndt1_cdiv(T, SMV_TT), 4), B);     // the reference's default: gaussian(1 + 6 sd, sd = 2)
-    if (g_ndt1_prof_on) ndt1_prof_note(0.0, (double)B * T * N * 8);     // fp32 in, fp32 out
+  if (K == 13 && N % 2 == 0 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)out & 7) == 0 && (!white || ((uintptr_t)white & 7) == 0) &&
+      (!out_bf16 || (((uintptr_t)out_bf16 & 3) == 0 && ld_bf16 % 2 == 0))) {
+    dim3 grid(ndt1_cdiv(N / 2, 128), ndt1_cdiv(ndt1_cdiv(T, SMV_TT), 2), B);     // the reference's default: gaussian(1 + 6 sd, sd = 2)
+    if (g_ndt1_prof_on) ndt1_prof_note(0.0, (double)B * T * N * (4 + (out ? 4 : 0) + (out_bf16 ? 2 : 0)));     // fp32 in; fp32 and / or bf16 out
     ndt1_launch(smooth_noise_vec_kernel<13>, grid, 256, 0, stream, p);
     NDT1_CHECK_LAUNCH();
     return 0;

@@ -66,6 +66,7 @@ struct Engine : ndt1_engine {
   int n_prefix = 0;
   // arena views ------------------------------------------------------------
   T* xin = nullptr; int ldN = 0;
+  const T* xin_ext = nullptr;                  // caller-provided bf16 input of the last forward (ndt1_batch.spikes_bf16)
   T* emb = nullptr; T* emb_pre = nullptr;      // emb_pre: pre-activation, kept only for a GELU embedder (its derivative needs it)
   float* rope_cos = nullptr; float* rope_sin = nullptr;   // (max_F, head size), models/ndt1.py:44-53
   // embedder.adapt: per-day weights / biases packed back to back (T-typed copy refreshed per forward) and their packed gradients
@@ -336,8 +337,10 @@ struct Engine : ndt1_engine {
     }
 
     // 0. precision staging: bf16 copies of the weights and of the input
+    xin_ext = nullptr;
     if (kBf16) {
-      NDT1_TRY(k_cast_f32_bf16(bt->spikes, (bf16*)xin, MT, N, N, ldN, s));
+      if (bt->spikes_bf16 && ldN == N) xin_ext = (const T*)bt->spikes_bf16;       // the prologue wrote the bf16 operand itself
+      else NDT1_TRY(k_cast_f32_bf16(bt->spikes, (bf16*)xin, MT, N, N, ldN, s));
       CastSegs cs; cs.n = 0;
       // a weight either comes from the caller's bf16 shadow (no work here) or is cast into the engine's copy:
       // contiguous matrices through ONE multi-segment launch, anything ragged through the strided kernel
@@ -398,7 +401,7 @@ struct Engine : ndt1_engine {
         }
       }
     }
-    const T* x_in = kBf16 ? xin : (const T*)bt->spikes;
+    const T* x_in = kBf16 ? (xin_ext ? xin_ext : xin) : (const T*)bt->spikes;
     const int ldx = kBf16 ? ldN : N;
 
     // 1. channel embedding + activation   (models/ndt1.py:170-176)
@@ -817,7 +820,7 @@ struct Engine : ndt1_engine {
     NDT1_TRY(fork());
     if (k.adapt) {
       // per-day gradients: trial b adds into day_idx[b]'s packed matrix / bias row, then each day's sum goes to its own tensor
-      const T* x_in = kBf16 ? xin : (const T*)spikes_ptr;
+      const T* x_in = kBf16 ? (xin_ext ? xin_ext : xin) : (const T*)spikes_ptr;
       const int ldx = kBf16 ? ldN : N;
       NDT1_CUDA_CHECK(cudaMemsetAsync(dwd_pack, 0, (size_t)k.n_days * D * N * 4, ws));
       NDT1_CUDA_CHECK(cudaMemsetAsync(dbd_pack, 0, (size_t)k.n_days * D * 4, ws));
@@ -835,7 +838,7 @@ struct Engine : ndt1_engine {
     }
     if (!fuse_embed_cs && G->embed_b && k.embed_bias && !k.adapt) NDT1_TRY(k_colsum<T>(dEmb, G->embed_b, MT, D, D, ws));
     if (G->embed_w && !k.adapt) {
-      const T* x_in = kBf16 ? xin : (const T*)spikes_ptr;
+      const T* x_in = kBf16 ? (xin_ext ? xin_ext : xin) : (const T*)spikes_ptr;
       const int ldx = kBf16 ? ldN : N;
       GemmProblem p = prob(GEMM_TN, D, N, (int)MT);
       p.A = op(dEmb, 0, 1, (int)MT, D, D); p.B = op(x_in, 0, 1, (int)MT, N, ldx);

@@ -6,7 +6,8 @@
 
 // elementwise.cu
 int k_smooth_noise(const float* x, float* out, int B, int T, int N, const float* taps, int K, float white_sd, float offset_sd,
-                   const float* white, const float* offset, int use_philox, SeedRef seed, cudaStream_t stream);
+                   const float* white, const float* offset, int use_philox, SeedRef seed, cudaStream_t stream, bf16* out_bf16 = nullptr,
+                   int ld_bf16 = 0);
 int k_masker_apply(float* spikes, int B, int T, int N, int mode, int timespan, const unsigned char* mask_draw,
                    const unsigned char* zero_draw, const unsigned char* random_draw, const float* rand, long long* mask_out,
                    long long* targets_mask, unsigned int* scratch, cudaStream_t stream);

@@ -90,7 +90,9 @@ class SmoothAndNoise(nn.Module):
             self._taps_host = kernel.numpy().astype(np.float32).copy()    # host copy for the launch (the taps are a by-value kernel argument):
                                                                           # reading the device buffer back every forward would synchronise the stream
 
-    def forward(self, spikes: torch.Tensor, noise: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+    def forward(self, spikes: torch.Tensor, noise: Optional[Dict[str, torch.Tensor]] = None, bf16_out: bool = False) -> torch.Tensor:
+        """``bf16_out``: write the result directly as the bfloat16 operand of the channel-embedding GEMM (what the engine would
+        otherwise cast it to) instead of float32 -- only the engine consumes it then (``ndt1_batch.spikes_bf16``)."""
         if not spikes.is_cuda:
             raise RuntimeError("llm_bci_b200 runs on the GPU only (no CPU fallback)")
         B, T, N = spikes.shape
@@ -98,7 +100,8 @@ class SmoothAndNoise(nn.Module):
         add_noise = bool(self.noise) and self.training
         if not self.smooth and not add_noise:
             return spikes
-        out = torch.empty_like(spikes)
+        bf16_out = bool(bf16_out) and N % 8 == 0
+        out = torch.empty(spikes.shape, dtype=torch.bfloat16 if bf16_out else torch.float32, device=spikes.device)
         taps = self._taps_host if self.smooth else np.zeros(0, dtype=np.float32)
         taps_c = taps.ctypes.data_as(_C.C.POINTER(_C.C.c_float))
         white = offset = None
@@ -120,8 +123,9 @@ class SmoothAndNoise(nn.Module):
                     seed_ptr = self.seed_tensor.data_ptr()
                 else:
                     seed = _seed_from_torch()
-        _C.check(_C.lib().ndt1_smooth_noise(spikes.data_ptr(), out.data_ptr(), B, T, N, taps_c, len(taps), wsd, osd,
-                                            _C.ptr(white), _C.ptr(offset), use_philox, seed, seed_ptr, _C.stream_ptr()), "ndt1_smooth_noise")
+        _C.check(_C.lib().ndt1_smooth_noise(spikes.data_ptr(), None if bf16_out else out.data_ptr(), B, T, N, taps_c, len(taps), wsd, osd,
+                                            _C.ptr(white), _C.ptr(offset), use_philox, seed, seed_ptr, out.data_ptr() if bf16_out else None, N,
+                                            _C.stream_ptr()), "ndt1_smooth_noise")
         return out
 
 
@@ -259,10 +263,11 @@ class NeuralEncoder(nn.Module):
         self.out_proj = NeuralFactorsProjection(self.hidden_size, config.factors)
         object.__setattr__(self, "_owner", owner)
 
-    def prologue(self, spikes: torch.Tensor, noise=None, want_mask: bool = False, masker_draws=None):
-        """Smoothing/noise then the maskers (models/ndt1.py:421-427).  Returns (spikes', targets_mask or None)."""
-        x = self.smooth_and_noise(spikes, noise)
+    def prologue(self, spikes: torch.Tensor, noise=None, want_mask: bool = False, masker_draws=None, bf16_ok: bool = False):
+        """Smoothing/noise then the maskers (models/ndt1.py:421-427).  Returns (spikes', targets_mask or None).
+        ``bf16_ok``: nothing but the bf16 engine reads spikes' -> the prologue kernel may write it as bfloat16 directly."""
         active = [m for m in self.masker if m.is_active()]
+        x = self.smooth_and_noise(spikes, noise, bf16_out=bf16_ok and not active)
         if active and x.data_ptr() == spikes.data_ptr():
             x = x.clone()   # the reference mutates its input here; this implementation never does
         targets_mask = None
@@ -559,6 +564,7 @@ class NDT1(nn.Module):
         x = call["spikes"]
         B, T, N = x.shape
         dev = x.device
+        x_bf16 = x if x.dtype == torch.bfloat16 else None      # the prologue already wrote the GEMM operand (SmoothAndNoise bf16_out)
         tg = call.get("targets")
         S = int(tg.shape[1]) if (tg is not None and self.method in ("ctc", "endtoend")) else 0
         eng = self._get_engine(B, T, S)
@@ -583,6 +589,10 @@ class NDT1(nn.Module):
             keep["lens"] = keep["mask"].sum(1)
         b = _C.Batch()
         b.spikes, b.spikes_mask, b.spikes_timestamp, b.spikes_lengths = x.data_ptr(), keep["mask"].data_ptr(), keep["ts"].data_ptr(), keep["lens"].data_ptr()
+        if x_bf16 is not None:
+            if self.precision != "bf16" or N % 8 != 0:
+                raise RuntimeError("a bfloat16 input needs the bf16 engine and n_channels % 8 == 0")
+            b.spikes, b.spikes_bf16 = None, x_bf16.data_ptr()
         b.block_idx, b.day_idx = _C.ptr(keep["blk"]), _C.ptr(keep["day"])
         if self.method in ("ctc", "endtoend") and not enc_only:
             keep["tg"], keep["tl"] = i64(tg), i64(call["targets_lengths"])
@@ -667,7 +677,7 @@ class NDT1(nn.Module):
     def _encode(self, spikes, spikes_mask, spikes_timestamp, spikes_lengths=None, block_idx=None, day_idx=None):
         """NeuralEncoder.forward (models/ndt1.py:408-450): (features, stacked mask, targets_mask).  With gradients enabled
         the features carry an autograd node, so a model stacked on the encoder (models/bci.py:125) trains through it."""
-        x, targets_mask = self.encoder.prologue(spikes, want_mask=True)
+        x, targets_mask = self.encoder.prologue(spikes, want_mask=True, bf16_ok=self.precision == "bf16")
         call = dict(spikes=x, spikes_mask=spikes_mask, spikes_timestamp=spikes_timestamp, spikes_lengths=spikes_lengths,
                     block_idx=block_idx, day_idx=day_idx, encoder_only=True)
         params = [p for p in self._autograd_params() if not any(p is q for q in self.decoder.parameters())]
@@ -700,7 +710,8 @@ class NDT1(nn.Module):
             call["recon_targets"] = targets
         else:
             call["targets"], call["targets_lengths"] = targets, targets_lengths
-        x, targets_mask = self.encoder.prologue(spikes, noise, want_mask=self.method == "mlm", masker_draws=masker_draws)
+        x, targets_mask = self.encoder.prologue(spikes, noise, want_mask=self.method == "mlm", masker_draws=masker_draws,
+                                                bf16_ok=self.precision == "bf16")
         call["spikes"], call["targets_mask"] = x, targets_mask
         params = self._autograd_params()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
@@ -727,7 +738,7 @@ class NDT1(nn.Module):
                 call["recon_targets"] = spikes
             else:
                 call["targets"], call["targets_lengths"] = targets, batch.get("targets_lengths")
-            x, targets_mask = self.encoder.prologue(spikes, batch.get("noise"), want_mask=self.method == "mlm")
+            x, targets_mask = self.encoder.prologue(spikes, batch.get("noise"), want_mask=self.method == "mlm", bf16_ok=self.precision == "bf16")
             call["spikes"], call["targets_mask"] = x, targets_mask
             out = self._engine_forward(call, need_backward=True)
             if dloss is None:

@@ -726,7 +726,7 @@ def test_ctc_register_sweeps_all_state_counts(S, L):
     """One warp per sweep keeps 1/2/4/8/16 states per lane depending on the target length: every variant against torch."""
     torch.manual_seed(S)
     B, V = 4, 41
-    logits = torch.randn(B, L, V) * 2
+    logits = torch.randn(B, L, V) * (12 if S == 40 else 2)     # (S = 40: a confident network -- per-state dynamic range far beyond fp32's)
     tl = torch.tensor([S, max(S // 2, 1), 1, S])
     il = torch.tensor([L, L - 3, L // 2, 2 * S + 1 if 2 * S + 1 <= L else L])
     tg = torch.randint(1, V, (B, S)) * (torch.arange(S)[None] < tl[:, None])
@@ -742,7 +742,7 @@ def test_ctc_register_sweeps_all_state_counts(S, L):
     ref = torch.nn.functional.ctc_loss(torch.log_softmax(x, -1).transpose(0, 1), tg, il, tl, blank=0, reduction="none", zero_infinity=True)
     ref.sum().backward()
     assert (nll.cpu().double() - ref.detach()).abs().max() <= 1e-4 * max(1.0, float(ref.abs().max()))
-    assert (dl.cpu().double() - x.grad).abs().max() < 5e-5
+    assert (dl.cpu().double() - x.grad).abs().max() < (2e-4 if S == 40 else 5e-5)
 
 
 @pytest.mark.gpu
