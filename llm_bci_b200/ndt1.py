@@ -443,6 +443,7 @@ class NDT1(nn.Module):
         self._weight_shadow = None
         self._param_stream = None     # a side stream that may still be updating the parameters (DataParallelTrainer's optimizer)
         self._param_event = None      # ... or the C event it records after its last update (usable from inside a captured step)
+        self._gather_hook = None      # sharded optimizer: all-gathers the fp32 master weights before they are read outside the engine
         self._seed_tensor = None      # int64[2] CUDA tensor holding (noise key, dropout key) when the step's keys live in device memory
 
     # ------------------------------------------------------------------ engine plumbing
@@ -645,27 +646,52 @@ class NDT1(nn.Module):
         return [flat[offs[id(p)]:offs[id(p)] + p.numel()].view_as(p) for p in self._autograd_params()]
 
     def _grad_offsets(self):
-        """Offsets (in floats, 256-byte aligned) of every parameter inside one flat gradient buffer."""
+        """Offsets (in floats, 256-byte aligned) of every parameter inside one flat gradient / parameter arena, and its layout.
+
+        Arena order: gradient STAGES in backward-completion order of the engine (ndt1_engine_wait_stage) -- embedder | layer 0 ..
+        layer L-1 | head -- and inside every stage first the BIG tensors (GEMM weights, which the bf16 engine reads through the
+        weight shadow) then the SMALL ones (biases, LayerNorm affines, the position / token tables: read in fp32).  Each layer's
+        q|k|v weights (and biases) sit next to each other so the engine runs one (3H x H) weight-gradient GEMM, one bias reduction
+        and one weight cast for the three.  The big region of a stage starts and ends on a multiple of 1024 floats, so it splits
+        evenly over up to 16 ranks (DataParallelTrainer shards the optimizer over it).  ``self._arena_layout`` = one dict per
+        stage {stage, big: (lo, hi), small: (lo, hi)} with the trainer's stage numbering (0 = head, 1.. = layers L-1..0,
+        L+1 = embedder)."""
         table, _ = self._params()
         if self._goffs is not None:
             return self._goffs
-        offs, off = {}, 0
-        # arena order: the table's, except that each layer's q|k|v weights (and biases) sit next to each other so the
-        # engine can run one (3H x H) weight-gradient GEMM, one bias reduction and one weight cast for the three
-        rank = {"q_w": 0, "k_w": 1, "v_w": 2, "q_b": 3, "k_b": 4, "v_b": 5}
-        first_layer = min(i for i, (slot, _) in enumerate(table) if slot.startswith("layer."))
-        def key(item):
-            i, (slot, _) = item
+        n_layers = self.config.encoder.transformer.n_layers
+        big_slots = {"embed_w", "proj_w", "q_w", "k_w", "v_w", "o_w", "up_w", "down_w", "factors_w"}
+        rank = {"q_w": 0, "k_w": 1, "v_w": 2, "q_b": 0, "k_b": 1, "v_b": 2}
+
+        def stage_of(slot):
             if slot.startswith("layer."):
-                _, l, name = slot.split(".")
-                if name in rank:
-                    return (1, int(l), 0, rank[name])
-                return (1, int(l), 1, i)
-            return (0, 0, 0, i) if i < first_layer else (2, 0, 0, i)
-        for _, (_, p) in sorted(enumerate(table), key=key):
-            if p is not None:
-                offs[id(p)] = off
-                off += (p.numel() + 63) // 64 * 64
+                return n_layers - int(slot.split(".")[1])
+            if slot in ("out_norm_w", "out_norm_b", "factors_w", "factors_b", "dec_w", "dec_b"):
+                return 0
+            return n_layers + 1
+
+        groups = {}
+        for i, (slot, p_) in enumerate(table):
+            if p_ is None:
+                continue
+            name = slot.split(".")[2] if slot.startswith("layer.") else slot.split(".")[0]
+            big = name in big_slots and p_.numel() >= 65536
+            groups.setdefault(stage_of(slot), {True: [], False: []})[big].append((rank.get(name, 3), i, p_))
+        offs, off, layout = {}, 0, []
+        for stage in sorted(groups, reverse=True):           # embedder first ... head last (any fixed order works; spans are per stage)
+            ent = {"stage": stage}
+            for big in (True, False):
+                if big:
+                    off = (off + 1023) // 1024 * 1024
+                lo = off
+                for _, _, p_ in sorted(groups[stage][big], key=lambda t: (t[0], t[1])):
+                    offs[id(p_)] = off
+                    off += (p_.numel() + 63) // 64 * 64
+                if big:
+                    off = (off + 1023) // 1024 * 1024
+                ent["big" if big else "small"] = (lo, off)
+            layout.append(ent)
+        self._arena_layout = layout
         self._goffs = (offs, off)
         return self._goffs
 
@@ -790,7 +816,10 @@ class NDT1(nn.Module):
         return torch.stack(preds, 1), torch.stack(bins, 1)
 
     def save_checkpoint(self, save_dir):
-        """models/ndt1.py:685-688: same three files, same keys."""
+        """models/ndt1.py:685-688: same three files, same keys.  (With DataParallelTrainer's sharded optimizer this is a collective:
+        every rank calls it, like the reference's trainer does, models/trainer.py:405-409.)"""
+        if self._gather_hook is not None:
+            self._gather_hook()
         self.wait_for_parameters()
         torch.save(self.encoder.state_dict(), os.path.join(save_dir, "encoder.bin"))
         torch.save(self.config.encoder.get_dict(), os.path.join(save_dir, "encoder_config.pth"))

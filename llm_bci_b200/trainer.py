@@ -96,7 +96,8 @@ class DataParallelTrainer:
     def __init__(self, model: NDT1, lr: float = 1e-3, wd: float = 5e-5, eps: float = 1e-8, betas=(0.9, 0.999),
                  scheduler: Optional[str] = None, total_steps: int = 1, warmup_pct: float = 0.0, div_factor: float = 25.0,
                  gamma: float = 0.95, process_group=None, bucket_layers: int = 1,
-                 gradient_accumulation_steps: int = 1, loss_scale: Optional[float] = None, use_graph: Optional[bool] = None):
+                 gradient_accumulation_steps: int = 1, loss_scale: Optional[float] = None, use_graph: Optional[bool] = None,
+                 shard_optimizer: Optional[bool] = None):
         self.model = model
         self.lr, self.wd, self.eps, self.betas = lr, wd, eps, betas
         self.scheduler, self.total_steps, self.warmup_pct, self.div_factor, self.gamma = scheduler, total_steps, warmup_pct, div_factor, gamma
@@ -117,9 +118,6 @@ class DataParallelTrainer:
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
-        self._stage_of: Dict[int, int] = {}
-        n_layers = model.config.encoder.transformer.n_layers
-        spans: Dict[int, List[int]] = {}
         with torch.no_grad():
             for slot, p in table:
                 if p is None:
@@ -128,22 +126,31 @@ class DataParallelTrainer:
                 self.flat_param[o:o + p.numel()].copy_(p.detach().reshape(-1))
                 p.data = self.flat_param[o:o + p.numel()].view_as(p)     # parameters become views of the flat buffer
                 p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
-                if slot.startswith("layer."):
-                    stage = n_layers - int(slot.split(".")[1])
-                elif slot in ("out_norm_w", "out_norm_b", "factors_w", "factors_b", "dec_w", "dec_b"):
-                    stage = 0
-                else:
-                    stage = n_layers + 1
-                lo, hi = spans.get(stage, (o, o))
-                spans[stage] = [min(lo, o), max(hi, o + (p.numel() + 63) // 64 * 64)]
+        layout = sorted(model._arena_layout, key=lambda e: e["stage"])      # gradient stages in completion order (head first)
         model.invalidate_param_cache()
+        model._grad_offsets()                                             # (re-derives the layout the cache reset dropped)
         # bf16 mode: the fused AdamW keeps a bf16 copy of the arena current, and the engine reads its weights from it
         self.shadow = None
         if dev.type == "cuda" and getattr(model, "precision", "") == "bf16":
             self.shadow = torch.empty(total, dtype=torch.bfloat16, device=dev)
             self.refresh_shadow()
             model.set_weight_shadow(self.flat_param, self.shadow)
-        self.buckets = [(st, spans[st][0], spans[st][1]) for st in sorted(spans)]   # completion order
+        # one bucket per gradient stage: (stage, lo, hi) = [big region | small region] of that stage, contiguous in the arena
+        self.buckets = [(e["stage"], e["big"][0], e["small"][1]) for e in layout]
+        self._big = {e["stage"]: e["big"] for e in layout}
+        # Sharded optimizer (world > 1, bf16 mode): the BIG region of every stage (the GEMM weights, read by the engine through the
+        # bf16 shadow) is reduce-scattered instead of all-reduced, each rank runs AdamW on its 1 / world slice only (optimizer HBM
+        # traffic / world) and the bf16 shadow slices are all-gathered (NVLink bytes 2 x 4 B -> 4 B + 2 B per parameter).  The small
+        # region (biases, LayerNorm affines, position table: read in fp32) stays all-reduced and replicated.  The fp32 masters of
+        # the big regions are then current on their owner rank only: gather_parameters() (called by NDT1.save_checkpoint through
+        # model._gather_hook) all-gathers them before anything reads parameters outside the engine.
+        if shard_optimizer is None:
+            shard_optimizer = os.environ.get("NDT1_SHARD_OPTIMIZER", "1") != "0"
+        self.shard = bool(shard_optimizer) and self.world > 1 and self.shadow is not None and self.world <= 16
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self._params_gathered = True
+        if self.shard:
+            model._gather_hook = self.gather_parameters
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self.serialize = False     # measurement aid: run the exchange and the optimizer AFTER the backward instead of under it
         # Whole-step CUDA graph (the loop at models/trainer.py:332-349): prologue + forward + backward of a batch
@@ -251,14 +258,69 @@ class DataParallelTrainer:
         with torch.cuda.stream(self.comm_stream):
             for stage, lo, hi in self.buckets:
                 _C.check(L.ndt1_engine_wait_stage(m._engine, stage, self.comm_stream.cuda_stream), "ndt1_engine_wait_stage")
-                if self.world > 1:
-                    dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
-                self._adamw(lo, hi, lr, self.comm_stream.cuda_stream)
+                if self.shard:
+                    self._sharded_bucket(stage, lo, hi, lr)
+                else:
+                    if self.world > 1:
+                        dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+                    self._adamw(lo, hi, lr, self.comm_stream.cuda_stream)
             _C.check(L.ndt1_event_record(self._params_ev, self.comm_stream.cuda_stream), "ndt1_event_record")   # parameters final
         # The caller's stream is NOT joined here: the last buckets' all-reduce and AdamW then run under the next step's
         # prologue (smoothing / noise / input cast, which read no parameter); the model joins before its first
         # parameter-dependent kernel (NDT1.wait_for_parameters, also called by save_checkpoint).
         return out
+
+    # ------------------------------------------------------------------ sharded optimizer
+    def _sharded_bucket(self, stage: int, lo: int, hi: int, lr: float) -> None:
+        """One gradient stage on the side stream: reduce-scatter + owner-slice AdamW + bf16 all-gather over its big region,
+        all-reduce + replicated AdamW over its small region (DDP's mean folded into the update as 1 / world, models/trainer.py:258-262)."""
+        blo, bhi = self._big[stage]
+        st = self.comm_stream.cuda_stream
+        if bhi > blo:
+            n = (bhi - blo) // self.world
+            mine = slice(blo + self.rank * n, blo + (self.rank + 1) * n)
+            g = self.flat_grad
+            if dist.get_backend(self.pg) == "nccl":
+                dist.reduce_scatter_tensor(g[mine], g[blo:bhi], op=dist.ReduceOp.SUM, group=self.pg)
+            else:                                   # (gloo has no reduce-scatter: the CPU / single-GPU test path)
+                dist.all_reduce(g[blo:bhi], op=dist.ReduceOp.SUM, group=self.pg)
+            self._adamw(mine.start, mine.stop, lr, st)                  # (clears its slice of the gradient)
+            if mine.start > blo:
+                g[blo:mine.start].zero_()
+            if mine.stop < bhi:
+                g[mine.stop:bhi].zero_()
+            if dist.get_backend(self.pg) == "nccl":
+                dist.all_gather_into_tensor(self.shadow[blo:bhi], self.shadow[mine], group=self.pg)
+            else:
+                self._gather_by_sum(self.shadow, blo, bhi, mine)
+            self._params_gathered = False
+        if hi > bhi:
+            dist.all_reduce(self.flat_grad[bhi:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            self._adamw(bhi, hi, lr, st)
+
+    def _gather_by_sum(self, buf: torch.Tensor, lo: int, hi: int, mine: slice) -> None:
+        """all-gather for back-ends without one: zero the slices of the other ranks, sum."""
+        tmp = torch.zeros(hi - lo, dtype=torch.float32, device=buf.device)
+        tmp[mine.start - lo:mine.stop - lo] = buf[mine].float()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.pg)
+        buf[lo:hi] = tmp.to(buf.dtype)
+
+    def gather_parameters(self) -> None:
+        """Sharded optimizer: bring the fp32 masters of the big regions up to date on every rank (checkpoints, evaluation in
+        fp32, anything that reads parameters outside the bf16 engine).  Collective: every rank must call it."""
+        if not self.shard or self._params_gathered:
+            return
+        self.synchronize()
+        for stage, lo, hi in self.buckets:
+            blo, bhi = self._big[stage]
+            if bhi > blo:
+                n = (bhi - blo) // self.world
+                mine = slice(blo + self.rank * n, blo + (self.rank + 1) * n)
+                if dist.get_backend(self.pg) == "nccl":
+                    dist.all_gather_into_tensor(self.flat_param[blo:bhi], self.flat_param[mine], group=self.pg)
+                else:
+                    self._gather_by_sum(self.flat_param, blo, bhi, mine)
+        self._params_gathered = True
 
     # ------------------------------------------------------------------ whole-step CUDA graph
     def _graphable(self, batch) -> bool:

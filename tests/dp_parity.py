@@ -67,6 +67,8 @@ def run(rank: int, world: int, dev: torch.device, steps: int = 3, per_rank: int 
         for b in batches:
             out = t.train_step(lb.trainer.shard_batch(b, rank, world))
             losses.append(out.loss.detach().clone())
+        sharded = bool(t.shard)
+        t.gather_parameters()          # (sharded optimizer: the fp32 masters of the big regions live on their owner until gathered)
         t.synchronize()
         torch.cuda.synchronize()
         # every rank must hold the same replica bit for bit (the all-reduced gradients are identical on all ranks)
@@ -93,7 +95,7 @@ def run(rank: int, world: int, dev: torch.device, steps: int = 3, per_rank: int 
             err = float((t.flat_param - t1.flat_param).abs().max() / t1.flat_param.abs().max())
             lerr = max(abs(a - b) / abs(b) for a, b in zip(loss_sum, l1))
             results.append(dict(precision=precision, world=world, steps=steps, param_rel_err=err, tol=tol, loss_rel_err=lerr,
-                                replicas_identical=bool(flags.item() == 1.0), max_param_update=moved,
+                                replicas_identical=bool(flags.item() == 1.0), max_param_update=moved, sharded_optimizer=sharded,
                                 shadow_current=bool(t.shadow is None or torch.equal(t.shadow, t.flat_param.bfloat16())),
                                 grads_cleared=float(t.flat_grad.abs().max()) == 0.0))
         dist.barrier()
