@@ -288,6 +288,29 @@ def gpu_eager_leg(dev):
     return out
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this rank to the CPU cores NVML reports as local to its GPU BEFORE any pinned host memory is allocated (first touch
+    then places the staging buffers on the GPU's NUMA node): with 8 ranks copying 33 MB per step each, host-to-device copies
+    that cross the socket interconnect are what bounds the end-to-end number.  Returns the cores, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[local]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------- this repo's arm
 def run_ours(args):
     import torch
@@ -298,6 +321,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = bind_to_gpu_numa_node(local) if (world > 1 and not args.no_numa_bind) else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -402,6 +426,21 @@ def run_ours(args):
     drain_e2e()
     ms_e2e = timed(step_e2e, args.steps, after=drain_e2e) / args.steps
     e2e_value = world * B / (ms_e2e * 1e-3)
+    # diagnosis: the host-to-device copies of a step ALONE (all ranks at once, nothing computing): when this approaches the step
+    # time the end-to-end number is bound by the host's memory / PCIe path, not by anything on the GPU
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        h0.record()
+        for _ in range(10):
+            for k, v in host.items():
+                bufs[0][k].copy_(v, non_blocking=True)
+        h1.record()
+    barrier()
+    h2d_ms = torch.tensor([h0.elapsed_time(h1) / 10], device=dev)
+    if world > 1:
+        dist.all_reduce(h2d_ms, op=dist.ReduceOp.MAX)
+    h2d_ms = float(h2d_ms)
 
     # ---- roofline: CUDA events around EVERY launch of the library, on its own stream, over extra steps.  The weight-gradient
     # stream and the overlapped optimizer are switched off here so that every launch is timed alone (its share of a real,
@@ -491,7 +530,9 @@ def run_ours(args):
                        "l2": "per-step working set ~1.4 GB >> 126 MB L2; no flush needed", "loss": state["loss"],
                        "cuda_graph": bool(trainer.use_graph)},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "trials/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_value, "unit": "trials/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "h2d_ms_per_step_alone": h2d_ms, "h2d_gbs_per_gpu_alone": h2d_bytes / (h2d_ms * 1e-3) / 1e9,
+                    "numa_bound_cores": None if numa_cpus is None else len(numa_cpus)},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_more": more,
@@ -514,6 +555,7 @@ def main():
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-under-torch-CUDA comparison leg")
     ap.add_argument("--fixed-length", action="store_true", help="every trial 1000 bins long (no padding)")
     ap.add_argument("--no-graph", action="store_true", help="eager steps (no whole-step CUDA graph)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin the ranks to their GPU's NUMA node")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -144,8 +144,11 @@ class DataParallelTrainer:
         # region (biases, LayerNorm affines, position table: read in fp32) stays all-reduced and replicated.  The fp32 masters of
         # the big regions are then current on their owner rank only: gather_parameters() (called by NDT1.save_checkpoint through
         # model._gather_hook) all-gathers them before anything reads parameters outside the engine.
+        # Measured on 8 B200s (profiles/r02_bench_8gpu*.json): 65.9 k trials/s sharded against 67.2 k with the plain all-reduce and the
+        # replicated AdamW -- three collectives per stage cost more than the optimizer traffic they save while AdamW already
+        # hides under the backward -- so it is OFF unless asked for (shard_optimizer=True or NDT1_SHARD_OPTIMIZER=1).
         if shard_optimizer is None:
-            shard_optimizer = os.environ.get("NDT1_SHARD_OPTIMIZER", "1") != "0"
+            shard_optimizer = os.environ.get("NDT1_SHARD_OPTIMIZER", "0") == "1"
         self.shard = bool(shard_optimizer) and self.world > 1 and self.shadow is not None and self.world <= 16
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         self._params_gathered = True

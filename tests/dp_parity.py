@@ -61,7 +61,8 @@ def run(rank: int, world: int, dev: torch.device, steps: int = 3, per_rank: int 
             return lb.NDT1(cfg, **CTC_KW, precision=precision, max_batch=Bg, max_T=T).to(dev)
 
         m = make()
-        t = lb.DataParallelTrainer(m, lr=1e-3, wd=5e-5, eps=1e-3, scheduler="cosine", total_steps=10, warmup_pct=0.3, div_factor=25.0)
+        t = lb.DataParallelTrainer(m, lr=1e-3, wd=5e-5, eps=1e-3, scheduler="cosine", total_steps=10, warmup_pct=0.3, div_factor=25.0,
+                                   shard_optimizer=(precision == "bf16"))      # bf16 case: also the (optional) sharded optimizer
         assert t.world == world and len(t.buckets) == cfg.encoder.transformer.n_layers + 2
         losses = []
         for b in batches:
