@@ -402,16 +402,22 @@ def run_ours(args):
     loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
+    diag = {"copy": True, "sync": True}                       # (--e2e-diagnose switches parts of the loop off to name the limiter)
+
     def step_e2e():
         i = state["i"]
         slot = i & 1
-        prefetch(slot ^ 1)                                   # next step's inputs fly while this step computes
-        torch.cuda.current_stream().wait_event(ready[slot])
+        if diag["copy"]:
+            if not args.prefetch_after:
+                prefetch(slot ^ 1)                           # next step's inputs fly while this step computes
+            torch.cuda.current_stream().wait_event(ready[slot])
         out = trainer.train_step(bufs[slot])
         consumed[slot].record()
+        if diag["copy"] and args.prefetch_after:
+            prefetch(slot ^ 1)
         loss_host[slot].copy_(out.loss, non_blocking=True)   # device -> host read of the step's result
         loss_ready[slot].record()
-        if i > 0:
+        if i > 0 and diag["sync"]:
             loss_ready[slot ^ 1].synchronize()
             state["loss"] = float(loss_host[slot ^ 1])
         state["i"] += 1
@@ -426,6 +432,16 @@ def run_ours(args):
     drain_e2e()
     ms_e2e = timed(step_e2e, args.steps, after=drain_e2e) / args.steps
     e2e_value = world * B / (ms_e2e * 1e-3)
+    e2e_diag = None
+    if args.e2e_diagnose:
+        e2e_diag = {}
+        for name, c, sy in (("no_h2d_copy", False, True), ("no_loss_sync", True, False), ("neither", False, False)):
+            diag["copy"], diag["sync"] = c, sy
+            for _ in range(4):
+                step_e2e()
+            drain_e2e()
+            e2e_diag[name + "_ms_per_step"] = timed(step_e2e, args.steps, after=drain_e2e) / args.steps
+        diag["copy"], diag["sync"] = True, True
     # diagnosis: the host-to-device copies of a step ALONE (all ranks at once, nothing computing): when this approaches the step
     # time the end-to-end number is bound by the host's memory / PCIe path, not by anything on the GPU
     barrier()
@@ -532,7 +548,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "trials/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "h2d_ms_per_step_alone": h2d_ms, "h2d_gbs_per_gpu_alone": h2d_bytes / (h2d_ms * 1e-3) / 1e9,
-                    "numa_bound_cores": None if numa_cpus is None else len(numa_cpus)},
+                    "numa_bound_cores": None if numa_cpus is None else len(numa_cpus), "diagnose": e2e_diag},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_more": more,
@@ -556,6 +572,8 @@ def main():
     ap.add_argument("--fixed-length", action="store_true", help="every trial 1000 bins long (no padding)")
     ap.add_argument("--no-graph", action="store_true", help="eager steps (no whole-step CUDA graph)")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin the ranks to their GPU's NUMA node")
+    ap.add_argument("--prefetch-after", action="store_true", help="e2e: submit the next step's H2D copies after this step's work instead of before")
+    ap.add_argument("--e2e-diagnose", action="store_true", help="also time the end-to-end loop without its H2D copies / without its per-step loss read")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

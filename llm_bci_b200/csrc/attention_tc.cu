@@ -45,6 +45,13 @@ __device__ __forceinline__ void dbg_mark(const TcAttn& a, int slot) {
     a.dbg[cta * 32 + slot] = t;
   }
 }
+__device__ __forceinline__ void dbg_mark64(const TcAttn& a, int slot) {       // persistent kernels: 64 slots per CTA (1-D grid)
+  if (a.dbg && slot < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg[65536 + (long long)blockIdx.x * 64 + slot] = t;        // (behind the 3-D-grid kernels' 32 slots x up to 2048 CTAs)
+  }
+}
 __device__ __forceinline__ void dbg_smid(const TcAttn& a, int slot) {
   if (a.dbg) {
     unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
@@ -181,6 +188,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3, half = warp >> 2;
   if (tid == 0) {
+    dbg_mark(a, 0); dbg_smid(a, 31);
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(&bars[0], 32768 + 65536);               // the loads fly while the CTA sets itself up
@@ -200,8 +208,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   const int nks = (L + 15) / 16;            // key steps of 16 actually holding keys
 
   if (tid == 0) {
+    dbg_mark(a, 1);                         // set-up done
     mbar_wait(&bars[0], 0);
     tc_fence_after();
+    dbg_mark(a, 2);                         // Q, K landed
     constexpr uint32_t idesc = make_idesc_bf16(128, 256, false, false);
     const uint64_t qd = make_sdesc(smem_u32(sQ), 16, 1024), kd = make_sdesc(smem_u32(sKV), 16, 1024);
 #pragma unroll
@@ -235,6 +245,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   mbar_wait(&bars[2], 0);
   tc_fence_after();
   if (tid == 0) {                           // K is consumed: V takes its place while the softmax runs
+    dbg_mark(a, 3);                         // S ready
     mbar_expect_tx(&bars[1], 65536);
     for (int c = 0; c < 2; ++c) tma_load_3d(sKV + c * 32768, &map256, &bars[1], 2 * H + h * HD + 64 * c, 0, b);
   }
@@ -259,6 +270,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   }
   s_m[half * 128 + row] = m;
   __syncthreads();
+  if (tid == 0) dbg_mark(a, 4);             // row maxima done
   m = fmaxf(s_m[row], s_m[128 + row]);
   const float m_s = (m == -INFINITY) ? 0.f : m * sl2;
   float l = 0.f;
@@ -297,8 +309,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
+    dbg_mark(a, 5);                         // P written
     mbar_wait(&bars[1], 0);
     tc_fence_after();
+    dbg_mark(a, 6);                         // V landed
     constexpr uint32_t idesc = make_idesc_bf16(128, 128, false, true);
     const uint64_t vd = make_sdesc(smem_u32(sKV), 32768, 1024);       // V as the MN-major operand: two 64-column chunks 32 KB apart
     for (int ks = 0; ks < nks; ++ks) {
@@ -311,6 +325,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   l = s_l[row] + s_l[128 + row];
   mbar_wait(&bars[3], 0);
   tc_fence_after();
+  if (tid == 0) dbg_mark(a, 7);             // O ready
   const float inv = (l > 0.f) ? 1.f / l : 0.f;
   const float inv_p = drop ? inv / (1.0f - p.p_attn) : inv;          // the 1 / (1 - p) of the probability dropout
   const float iko = p.p_out > 0.f ? 1.0f / (1.0f - p.p_out) : 1.f;
@@ -343,14 +358,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (tid == 32) {
+    dbg_mark(a, 8);                         // output tiles staged
     for (int c = 0; c < 2; ++c) {
       tma_store_3d(&mapo, sOut + c * 16384, h * HD + 64 * c, q0, b);
       if (two) tma_store_3d(&mapod, sOutD + c * 16384, h * HD + 64 * c, q0, b);
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    dbg_mark(a, 9);                         // stores have read shared memory
   }
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 256); if (lane == 0) dbg_mark(a, 16); }
 }
 
 // ---------------------------------------------------------------------------
@@ -909,7 +926,7 @@ attn_tc_bwd_kv2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
 //   tensor memory: as kv2.
 // ---------------------------------------------------------------------------
 constexpr int KV3_QST = 4;
-constexpr int SMEM_BKV3 = 65536 + KV3_QST * 32768 + LMAX * 8 + LMAX * 16 + 256 + 1024;
+constexpr int SMEM_BKV3 = 65536 + KV3_QST * 32768 + 2 * (LMAX * 8 + LMAX * 16) + 256 + 1024;
 
 __global__ void __launch_bounds__(KV2_THREADS, 1)
 attn_tc_bwd_kv3_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map64,
@@ -920,9 +937,9 @@ attn_tc_bwd_kv3_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
   uint8_t* sK = smem;                          // 2 x [128 keys x 64 d]   32 KB
   uint8_t* sV = sK + 32768;
   uint8_t* sQ = sV + 32768;                    // ring: stages x { Q chunk 2 x [64 q x 64 d] (16 KB), dO chunk (16 KB) }
-  float2* s_ld = (float2*)(sQ + KV3_QST * 32768);          // [LMAX] (lse * log2e, delta) of every query of the current item
-  uint32_t* s_bits = (uint32_t*)(s_ld + LMAX);             // [LMAX][4] keep bits (query, 32-key word of this key tile)
-  uint64_t* bars = (uint64_t*)(s_bits + LMAX * 4);
+  float2* s_ld2 = (float2*)(sQ + KV3_QST * 32768);         // [2][LMAX] (lse * log2e, delta) of every query, double-buffered over items
+  uint32_t* s_bits2 = (uint32_t*)(s_ld2 + 2 * LMAX);       // [2][LMAX][4] keep bits (query, 32-key word of this key tile)
+  uint64_t* bars = (uint64_t*)(s_bits2 + 2 * LMAX * 4);
   uint64_t* kv_full = bars;                    // [1]  K / V of the item landed
   uint64_t* kv_free = bars + 1;                // [1]  the item's last S^T / dP^T retired: the buffer may take the next item's tiles
   uint64_t* q_full = bars + 2;                 // [4]
@@ -931,7 +948,8 @@ attn_tc_bwd_kv3_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
   uint64_t* p_full = bars + 12;                // [2]
   uint64_t* acc_done = bars + 14;              // [1]  the item's dV / dK products retired
   uint64_t* acc_free = bars + 15;              // [1]  the compute warps have read the accumulators
-  uint32_t* tmem_slot = (uint32_t*)(bars + 16);
+  uint64_t* stage_ready = bars + 16;           // [1]  the item's dV / dK tiles are staged in shared memory (the producer stores them)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 17);
 
   const AttnParams& p = a.p;
   const int L = p.L, H = p.H;
@@ -950,7 +968,7 @@ attn_tc_bwd_kv3_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
     mbar_init(kv_full, 1); mbar_init(kv_free, 1);
     for (int i = 0; i < KV3_QST; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], KV2_CWARPS); }
-    mbar_init(acc_done, 1); mbar_init(acc_free, KV2_CWARPS);
+    mbar_init(acc_done, 1); mbar_init(acc_free, KV2_CWARPS); mbar_init(stage_ready, KV2_CWARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -960,26 +978,51 @@ attn_tc_bwd_kv3_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer: one flat stream of chunks over all items =====================
+    // ===================== TMA producer: one flat stream of chunks over all items; it also issues the items' bulk stores ====
     if (lane == 0) {
       const int total = my_items * nc;
+      uint32_t qe_phase[KV3_QST] = {0, 0, 0, 0};   // parity of the next q_empty completion of every stage
+      int stored = 0;                              // items whose dV / dK tiles have been stored
+      auto store_item = [&](int it) {              // the item's two staging stages -> global; they rejoin the ring when the stores have read them
+        int b, h, k0; item_of(it, b, h, k0);
+        const int g_last = it * nc + nc - 1;
+        uint8_t* tile_v = sQ + ((g_last - 1) % KV3_QST) * 32768;
+        uint8_t* tile_k = sQ + (g_last % KV3_QST) * 32768;
+        mbar_wait(stage_ready, it & 1);
+        if (it < 4) dbg_mark64(a, it * 12 + 7);                // staging tiles seen by the producer
+        for (int d = 0; d < 2; ++d) {
+          tma_store_3d(&mapdqkv, tile_v + d * 16384, 2 * H + h * HD + 64 * d, k0, b);
+          tma_store_3d(&mapdqkv, tile_k + d * 16384, H + h * HD + 64 * d, k0, b);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (it < 4) dbg_mark64(a, it * 12 + 8);                // stores have read shared memory
+      };
       for (int g = 0; g < total; ++g) {
         const int it = g / nc, c = g - it * nc;
         int b, h, k0; item_of(it, b, h, k0);
         const int kvpos = it == 0 ? 0 : (nc > 2 ? 2 : nc - 1);     // where in the item's chunk sequence its K / V tiles are fetched
         if (c == kvpos) {
           if (it > 0) mbar_wait(kv_free, (it - 1) & 1);
+          if (it < 4) dbg_mark64(a, it * 12 + 11);            // K / V of the item requested
           mbar_expect_tx(kv_full, 65536);
           for (int d = 0; d < 2; ++d) tma_load_3d(sK + d * 16384, &map128, kv_full, H + h * HD + 64 * d, k0, b);
           for (int d = 0; d < 2; ++d) tma_load_3d(sV + d * 16384, &map128, kv_full, 2 * H + h * HD + 64 * d, k0, b);
         }
+        // chunks nc-2 and nc-1 reuse the stages that staged the PREVIOUS item's dV / dK: store those first (after this item's K / V
+        // request above: the store waits for the previous item's accumulator drain)
+        if (it > 0 && c == nc - 2 && stored < it) { store_item(it - 1); stored = it; }
         const int st = g % KV3_QST;
-        mbar_wait(&q_empty[st], ((g / KV3_QST) & 1) ^ 1);
+        // (a stage that staged a store was released by this thread itself, above: no barrier; the others come back through q_empty,
+        //  which only chunks c < nc - 2 of the stage's previous user signal)
+        const int gp = g - KV3_QST;                                   // the stage's previous user
+        if (gp >= 0 && (gp % nc) < nc - 2) mbar_wait(&q_empty[st], qe_phase[st]), qe_phase[st] ^= 1;
         uint8_t* dq = sQ + st * 32768;
         mbar_expect_tx(&q_full[st], 32768);
         for (int d = 0; d < 2; ++d) tma_load_3d(dq + d * 8192, &map64, &q_full[st], h * HD + 64 * d, c * KV2_CH, b);
         for (int d = 0; d < 2; ++d) tma_load_3d(dq + 16384 + d * 8192, &mapdo64, &q_full[st], h * HD + 64 * d, c * KV2_CH, b);
       }
+      for (int it = stored; it < my_items; ++it) store_item(it);     // the last item(s)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -1030,6 +1073,7 @@ attn_tc_bwd_kv3_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
           acc(g0 + c, it, c);
         }
         tc_commit(acc_done);
+        if (it < 4) dbg_mark64(a, it * 12 + 10);                 // the item's last products are queued
         if (it + 1 < my_items) {                                 // the next item's first products, while this item's accumulators drain
           mbar_wait(kv_full, (it + 1) & 1);
           tc_fence_after();
@@ -1045,12 +1089,12 @@ attn_tc_bwd_kv3_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
     const float sl2 = p.scale * kLog2e;
     const float ik = drop ? 1.0f / (1.0f - p.p_attn) : 1.f;
-    for (int it = 0; it < my_items; ++it) {
+    // per-query scalars and keep bits of an item's (trial, head, key tile), into the buffer of its parity
+    auto load_scalars = [&](int it) {
       int b, h, k0; item_of(it, b, h, k0);
       const long long bh0 = ((long long)b * p.nh + h) * L;
-      const int kj = k0 + row;
-      const bool kv_j = kj < L && p.key_valid[(long long)b * L + kj] != 0;
-      // per-query scalars and keep bits of this (trial, head): nobody reads the previous item's any more (barrier at its end)
+      float2* s_ld = s_ld2 + (it & 1) * LMAX;
+      uint32_t* s_bits = s_bits2 + (it & 1) * LMAX * 4;
       for (int q = tid - 64; q < LMAX; q += 32 * KV2_CWARPS)
         s_ld[q] = q < L ? make_float2(p.lse[bh0 + q] * kLog2e, p.delta[bh0 + q]) : make_float2(0.f, 0.f);
       for (int q = tid - 64; q < LMAX; q += 32 * KV2_CWARPS) {
@@ -1058,12 +1102,22 @@ attn_tc_bwd_kv3_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
         if (drop && q < L) w = *(const uint4*)(p.drop_bits + (bh0 + q) * 8 + (k0 >> 5));
         *(uint4*)(s_bits + q * 4) = w;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * KV2_CWARPS) : "memory");
+    };
+    if (my_items > 0) load_scalars(0);
+    for (int it = 0; it < my_items; ++it) {
+      int b, h, k0; item_of(it, b, h, k0);
+      const int kj = k0 + row;
+      const bool kv_j = kj < L && p.key_valid[(long long)b * L + kj] != 0;
+      const float2* s_ld = s_ld2 + (it & 1) * LMAX;
+      const uint32_t* s_bits = s_bits2 + (it & 1) * LMAX * 4;
+      if (tid == 64 && it < 4) dbg_mark64(a, it * 12 + 0);      // item start (compute warps)
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * KV2_CWARPS) : "memory");      // this item's scalars are in place (all warps are past the previous item's chunks)
       for (int c = 0; c < nc; ++c) {
         const int g = it * nc + c, bf = g & 1;
         const int qb = c * KV2_CH + grp * 16;                  // first query of this thread's columns
         mbar_wait(&s_full[bf], (g >> 1) & 1);
         tc_fence_after();
+        if (tid == 64 && it < 4 && c < 4) dbg_mark64(a, it * 12 + 2 + c);     // S^T / dP^T of chunk c seen
         uint32_t pk[8], dk[8];
         if (qb < L) {                                          // warp-uniform
           const uint32_t mw = key_mask_word(kj, qb & ~31, a.cf, a.cb, kv_j, L) >> (qb & 31);
@@ -1097,9 +1151,13 @@ attn_tc_bwd_kv3_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[bf]);
       }
-      // ---- this item's dV (cols 256..), dK (cols 384..): tensor memory -> registers -> the two free ring stages -> bulk stores
+      if (tid == 64 && it < 4) dbg_mark64(a, it * 12 + 1);      // last P of the item written
+      // the next item's scalars, while this item's last products retire (their buffer's readers are all behind the barrier above)
+      if (it + 1 < my_items) load_scalars(it + 1);
+      // ---- this item's dV (cols 256..), dK (cols 384..): tensor memory -> registers -> the two free ring stages; the producer stores them
       mbar_wait(acc_done, it & 1);
       tc_fence_after();
+      if (tid == 64 && it < 4) dbg_mark64(a, it * 12 + 6);      // accumulators complete
       const int g_last = it * nc + nc - 1;
       uint8_t* tile_v = sQ + ((g_last - 1) % KV3_QST) * 32768;
       uint8_t* tile_k = sQ + (g_last % KV3_QST) * 32768;
@@ -1115,22 +1173,13 @@ attn_tc_bwd_kv3_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
 #pragma unroll
       for (int g4 = 0; g4 < 4; ++g4) st_row8(tile_k, row, grp * 32 + g4 * 8, (const float*)r1 + g4 * 8);
       fence_async_smem();
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * KV2_CWARPS) : "memory");
-      if (tid == 64) {
-        for (int d = 0; d < 2; ++d) {
-          tma_store_3d(&mapdqkv, tile_v + d * 16384, 2 * H + h * HD + 64 * d, k0, b);
-          tma_store_3d(&mapdqkv, tile_k + d * 16384, H + h * HD + 64 * d, k0, b);
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        mbar_arrive(&q_empty[(g_last - 1) % KV3_QST]);         // the two stages return to the ring
-        mbar_arrive(&q_empty[g_last % KV3_QST]);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stage_ready);                 // (16 warps: the producer issues the bulk stores)
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); if (lane == 0) dbg_mark64(a, 63); }
 }
 
 int make_maps(const AttnParams& p, CUtensorMap* m128, CUtensorMap* m256, CUtensorMap* mdo) {
@@ -1181,8 +1230,8 @@ int k_attention_tc_fwd(const AttnParams& p, cudaStream_t stream) {
   }
   CUtensorMap m128, m256;
   NDT1_TRY(make_maps(p, &m128, &m256, nullptr));
-  static bool attr = false;
-  if (!attr) { NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD)); attr = true; }
+  static Ndt1PerDeviceFlag attr;
+  if (!attr.here()) { NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD)); attr.here() = true; }
   TcAttn a; a.p = p; a.cf = p.ctx_fwd; a.cb = p.ctx_bwd; a.dbg = g_attn_dbg;
   dim3 grid(ndt1_cdiv(p.L, TQ), p.nh, p.B);
   GemmOperand o; o.ptr = p.out; o.batch_stride = (long long)p.L * p.H; o.nbatch = p.B; o.rows = p.L; o.cols = p.H; o.ld = p.H;
@@ -1202,13 +1251,13 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream) {
   NDT1_TRY(gemm_tc_init());
   CUtensorMap m128, m256, mdo;
   NDT1_TRY(make_maps(p, &m128, &m256, &mdo));
-  static bool attr = false;
-  if (!attr) {
+  static Ndt1PerDeviceFlag attr;
+  if (!attr.here()) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BQ));
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV));
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV2));
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV3));
-    attr = true;
+    attr.here() = true;
   }
   TcAttn a; a.p = p; a.cf = p.ctx_fwd; a.cb = p.ctx_bwd; a.dbg = g_attn_dbg;
   dim3 grid(ndt1_cdiv(p.L, TQ), p.nh, p.B);
@@ -1234,8 +1283,7 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream) {
     if (g_ndt1_prof_on) ndt1_prof_note(2 * mm, 0.0);                // algorithmic: dV = P~^T dO and dK = dS^T Q
     static const bool kv2_only = getenv("NDT1_ATTN_BWD_KV2") && getenv("NDT1_ATTN_BWD_KV2")[0] == '1';
     if (!kv2_only && p.L > KV2_CH) {          // persistent pipeline (needs at least two query chunks per item for its store staging)
-      static int sms = 0;
-      if (!sms) { int dev = 0; NDT1_CUDA_CHECK(cudaGetDevice(&dev)); NDT1_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+      const int sms = ndt1_num_sms();
       const int n_items = p.B * p.nh * ndt1_cdiv(p.L, TQ);
       ndt1_launch(attn_tc_bwd_kv3_kernel, dim3(n_items < sms ? n_items : sms), KV2_THREADS, SMEM_BKV3, stream, m128, m64, mdo64, mdq, a, n_items);
       NDT1_CHECK_LAUNCH();

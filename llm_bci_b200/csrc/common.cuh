@@ -99,6 +99,20 @@ static inline cudaError_t ndt1_launch(void (*kernel)(KArgs...), dim3 grid, dim3 
 
 static inline int ndt1_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Per-DEVICE host state (several GPUs in one process: one engine per device): the current device's ordinal and SM count, and a
+// helper for "set this kernel attribute once per device" (function attributes are per device, not per process).
+constexpr int NDT1_MAX_DEVICES = 64;
+int ndt1_current_device();
+int ndt1_num_sms();
+struct Ndt1PerDeviceFlag {
+  bool done[NDT1_MAX_DEVICES] = {};
+  bool& here() { return done[ndt1_current_device() % NDT1_MAX_DEVICES]; }
+};
+struct Ndt1PerDeviceSize {
+  size_t v[NDT1_MAX_DEVICES] = {};
+  size_t& here() { return v[ndt1_current_device() % NDT1_MAX_DEVICES]; }
+};
+
 // ---------------------------------------------------------------------------
 // Type helpers
 // ---------------------------------------------------------------------------

@@ -402,10 +402,10 @@ size_t k_ctc_workspace_floats(int B, int L, int S) { return 2 * (size_t)B * L * 
 
 template <bool FAST, int SPT>
 static int ctc_launch(const CtcParams& p, size_t smem, cudaStream_t stream) {
-  static size_t attr = 0;
-  if (smem > attr) {
+  static Ndt1PerDeviceSize attr;
+  if (smem > attr.here()) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(ctc_kernel<FAST, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+    attr.here() = smem;
   }
   // log-probs in, alpha + beta rows out (latency-bound: 2 L dependent steps per trial)
   if (g_ndt1_prof_on) ndt1_prof_note(0.0, (double)p.B * p.L * (4.0 * p.V + 8.0 * (2 * p.S + 1)));

@@ -26,6 +26,22 @@ void ndt1_set_error(const char* fmt, ...) {
 
 extern "C" const char* ndt1_last_error(void) { return g_err; }
 
+int ndt1_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return dev;
+}
+int ndt1_num_sms() {
+  static int sms[NDT1_MAX_DEVICES] = {};
+  const int dev = ndt1_current_device() % NDT1_MAX_DEVICES;
+  if (!sms[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+    sms[dev] = n;
+  }
+  return sms[dev];
+}
+
 // ---------------------------------------------------------------------------
 // Launch profiler (see common.cuh).  Events are pooled; nothing is allocated once the pool has grown to a step's launches.
 // ---------------------------------------------------------------------------

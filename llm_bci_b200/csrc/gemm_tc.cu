@@ -675,24 +675,27 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-int g_num_sms = 0;
 std::mutex g_mu;
 
 struct MapKey {
-  const void* ptr; long long bs; int nb, rows, cols, ld, box_c, box_r;
+  const void* ptr; long long bs; int nb, rows, cols, ld, box_c, box_r, dev;     // (dev: the same address on two devices is two tensors)
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && bs == o.bs && nb == o.nb && rows == o.rows && cols == o.cols && ld == o.ld && box_c == o.box_c && box_r == o.box_r;
+    return ptr == o.ptr && bs == o.bs && nb == o.nb && rows == o.rows && cols == o.cols && ld == o.ld && box_c == o.box_c && box_r == o.box_r &&
+           dev == o.dev;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = (size_t)k.ptr;
     auto mix = [&](long long v) { h ^= (size_t)v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
-    mix(k.bs); mix(k.nb); mix(k.rows); mix(k.cols); mix(k.ld); mix(k.box_c); mix(k.box_r);
+    mix(k.bs); mix(k.nb); mix(k.rows); mix(k.cols); mix(k.ld); mix(k.box_c); mix(k.box_r); mix(k.dev);
     return h;
   }
 };
-std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+// Encoded tensor maps, two generations: a hit in the old generation is promoted; when the young one is full it becomes the old one
+// (so the maps of the buffers in use survive, those of freed buffers age out -- instead of dropping everything at a size limit).
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps, g_maps_old;
+constexpr size_t kMapGeneration = 2048;
 
 unsigned long long* g_gemm_dbg = nullptr;
 
@@ -700,10 +703,17 @@ int make_map(const GemmOperand& o, int box_cols, int box_rows, CUtensorMap* out)
   NDT1_REQUIRE(((uintptr_t)o.ptr & 15) == 0, "gemm_tc: operand pointer not 16-byte aligned");
   NDT1_REQUIRE(o.ld % 8 == 0, "gemm_tc: operand row stride %d not a multiple of 8 elements", o.ld);
   NDT1_REQUIRE(o.nbatch <= 1 || o.batch_stride % 8 == 0, "gemm_tc: batch stride not a multiple of 8 elements");
-  MapKey key{o.ptr, o.batch_stride, o.nbatch, o.rows, o.cols, o.ld, box_cols, box_rows};
+  MapKey key{o.ptr, o.batch_stride, o.nbatch, o.rows, o.cols, o.ld, box_cols, box_rows, ndt1_current_device()};
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return 0; }
+  auto io = g_maps_old.find(key);
+  if (io != g_maps_old.end()) {
+    *out = io->second;
+    if (g_maps.size() >= kMapGeneration) { g_maps_old.swap(g_maps); g_maps.clear(); }
+    g_maps.emplace(key, *out);
+    return 0;
+  }
   cuuint64_t dims[3] = {(cuuint64_t)o.cols, (cuuint64_t)o.rows, (cuuint64_t)(o.nbatch > 0 ? o.nbatch : 1)};
   long long bs = o.batch_stride > 0 ? o.batch_stride : (long long)o.rows * o.ld;
   cuuint64_t strides[2] = {(cuuint64_t)o.ld * 2, (cuuint64_t)bs * 2};
@@ -714,7 +724,7 @@ int make_map(const GemmOperand& o, int box_cols, int box_rows, CUtensorMap* out)
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NDT1_REQUIRE(rc == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed rc=%d (cols=%d rows=%d nb=%d ld=%d bs=%lld box=%dx%d)",
                (int)rc, o.cols, o.rows, o.nbatch, o.ld, bs, box_cols, box_rows);
-  if (g_maps.size() > 4096) g_maps.clear();
+  if (g_maps.size() >= kMapGeneration) { g_maps_old.swap(g_maps); g_maps.clear(); }
   g_maps.emplace(key, *out);
   return 0;
 }
@@ -725,12 +735,12 @@ int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& tp
   constexpr int STAGES = kSmemPipe / STAGE_BYTES;
   constexpr int SMEM = STAGES * STAGE_BYTES + kEpiWarps * kStageTile + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
   static_assert(SMEM <= 227 * 1024, "gemm_tc: shared memory budget");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static Ndt1PerDeviceFlag attr_set;          // (function attributes are per device)
+  if (!attr_set.here()) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, CTAS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
+    attr_set.here() = true;
   }
-  const int units = g_num_sms / CTAS;
+  const int units = ndt1_num_sms() / CTAS;
   const int grid = CTAS * (tp.total_tiles < units ? tp.total_tiles : units);
   if (g_ndt1_prof_on)      // algorithmic FLOPs of this launch (bench.py roofline): 2 M N K over all trials / chunks
     ndt1_prof_note(2.0 * tp.M * (double)tp.N * (double)tp.nchunk * tp.chunk_k_valid * (tp.mode == GEMM_TN ? 1 : tp.nb_out), 0.0);
@@ -802,12 +812,11 @@ int gemm_tc_init() {
   cudaDriverEntryPointQueryResult qres;
   NDT1_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   NDT1_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "gemm_tc: cuTensorMapEncodeTiled not available from the driver");
-  int dev = 0;
+  int dev = 0, major = 0, minor = 0;
   NDT1_CUDA_CHECK(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  NDT1_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-  NDT1_REQUIRE(prop.major == 10, "gemm_tc: this library is built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
-  g_num_sms = prop.multiProcessorCount;
+  NDT1_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  NDT1_CUDA_CHECK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  NDT1_REQUIRE(major == 10, "gemm_tc: this library is built for sm_100a only (device is sm_%d%d)", major, minor);
   g_encode = (EncodeTiledFn)fn;
   return 0;
 }
@@ -839,13 +848,14 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   if (bn >= 128 && p.M > BM) {
     const long long per = (long long)ndt1_cdiv(p.N, bn) * (p.mode == GEMM_TN ? 1 : p.nb_out);
     const long long t1 = per * ndt1_cdiv(p.M, BM), t2 = per * ndt1_cdiv(p.M, 2 * BM);
-    const long long w1 = (t1 + g_num_sms - 1) / g_num_sms, w2 = (t2 + g_num_sms / 2 - 1) / (g_num_sms / 2);
+    const int num_sms = ndt1_num_sms();
+    const long long w1 = (t1 + num_sms - 1) / num_sms, w2 = (t2 + num_sms / 2 - 1) / (num_sms / 2);
     if (p.mode == GEMM_TN || w2 <= w1) ctas = 2;     // (weight gradients size their split to one wave either way)
   }
   if (force_ctas == 1) ctas = 1;
   if (force_ctas == 2 && bn >= 128 && p.M > BM) ctas = 2;
   const int bm = BM * ctas;
-  const int units = g_num_sms / ctas;
+  const int units = ndt1_num_sms() / ctas;
 
   TcParams tp;
   tp.mode = p.mode; tp.M = p.M; tp.N = p.N; tp.nb_out = p.nb_out;

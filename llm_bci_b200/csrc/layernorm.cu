@@ -348,11 +348,7 @@ ln_bwd_rows_kernel(const T* __restrict__ dy, const float* __restrict__ x, const 
   if (colsum_out && out_lp) red_add4(colsum_out + c * 4, cs);
 }
 
-int g_sms() {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  return sms;
-}
+int g_sms() { return ndt1_num_sms(); }
 int ln_blocks(long long rows) {
   long long b = (rows + LN_WARPS - 1) / LN_WARPS;
   return (int)(b < LN_MAX_BLOCKS ? b : LN_MAX_BLOCKS);
@@ -410,10 +406,10 @@ int k_layernorm_bwd(const T* dy, const float* x, const float* gamma, const float
   long long nb = (rows + LNB_WARPS - 1) / LNB_WARPS;
   if (nb > sms) nb = sms;
   const size_t smem = (size_t)LNB_WARPS * 3 * H * sizeof(float);
-  static size_t attr[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > attr[sizeof(T) == 2]) {
+  static Ndt1PerDeviceSize attr;
+  if (smem > 48 * 1024 && smem > attr.here()) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[sizeof(T) == 2] = smem;
+    attr.here() = smem;
   }
   ndt1_launch(ln_bwd_kernel<T>, (int)nb, LNB_WARPS * 32, smem, stream, dy, x, gamma, mean, rstd, dres, out_lp, drop_p, seed,
                                                                                stream_id, rows, H, dgamma, dbeta, out_lp ? colsum_out : nullptr);

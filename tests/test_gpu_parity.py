@@ -1139,3 +1139,29 @@ def test_bci_end_to_end_trains_through_the_llm():
         model.projector[2].weight.data.zero_()
         model.load_checkpoint(d)
         assert torch.equal(model.projector[2].weight.detach().cpu(), before.cpu())
+
+
+def test_launch_profiler_groups_kernels_and_carries_algorithmic_work():
+    """ndt1_profile_begin / ndt1_profile_end (bench.py roofline): every launch between them is event-timed on its own stream and
+    grouped by kernel, with the algorithmic FLOPs / bytes its launcher attached."""
+    tr = lb.default_trainer_config()
+    cfg = lb.update_config(tr.model, {"encoder": {"transformer": {"n_layers": 2}}})
+    torch.manual_seed(1)
+    model = lb.NDT1(cfg, **tr.method.model_kwargs, precision="bf16").to(DEV).train()
+    batch = cuda_batch(O.synthetic_ctc_batch(B=4, T=400, N=256, seed=2))
+    trainer = lb.DataParallelTrainer(model, use_graph=False)
+    trainer.train_step(batch)
+    torch.cuda.synchronize()
+    _C.profile_begin()
+    trainer.train_step(batch)
+    trainer.synchronize()
+    torch.cuda.synchronize()
+    prof = {r["name"]: r for r in _C.profile_end()}
+    gemm = [r for n, r in prof.items() if n.startswith("gemm_tc_kernel<")]
+    assert gemm and all(r["flops"] > 0 and r["ms"] > 0 for r in gemm)
+    M, H = 4 * 93, 1024
+    assert abs(sum(r["flops"] for r in gemm) / (3 * 2.0 * M * (256 * 256 * 4 + 8192 * H + 2 * 6 * H * H + 41 * H)) - 1) < 0.05   # ~ 3 x forward MACs
+    for name in ("attn_tc_fwd_kernel", "attn_tc_bwd_q_kernel", "attn_tc_bwd_kv3_kernel"):
+        assert prof[name]["launches"] == 2 and prof[name]["flops"] > 0
+    assert prof["adamw_fused_kernel"]["bytes"] > 30 * 40e6 * 0.4
+    assert any(n.startswith("ln_bwd_rows_kernel") and r["bytes"] > 0 for n, r in prof.items())

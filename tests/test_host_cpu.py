@@ -240,3 +240,43 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         for f in fields:
             assert int(out[f"{cname}.{f}"]) == getattr(ctype, f).offset, (cname, f)
     assert out["abi"] == f"{_C.ABI_VERSION} layers {_C.MAX_LAYERS} days {_C.MAX_DAYS}"
+
+
+def test_arena_layout_big_and_small_regions_per_stage():
+    """The flat parameter / gradient arena: one contiguous span per gradient stage, big (GEMM weight) region first and aligned to
+    1024 floats at both ends, q|k|v weights and biases adjacent (the engine's single 3H x H weight-gradient GEMM relies on it)."""
+    import llm_bci_b200.ndt1 as N
+    tr = lb.default_trainer_config()
+    m = lb.NDT1(tr.model, **tr.method.model_kwargs)
+    m._ptable, m._pstruct = N._flat_param_table(m), None           # (CPU: skip the CUDA-only parameter checks of _params())
+    offs, total = m._grad_offsets()
+    lay = sorted(m._arena_layout, key=lambda e: e["stage"])
+    assert [e["stage"] for e in lay] == list(range(7))
+    covered = 0
+    for e in lay:
+        (blo, bhi), (slo, shi) = e["big"], e["small"]
+        assert blo % 1024 == 0 and bhi % 1024 == 0 and bhi == slo and shi >= slo
+        covered += shi - blo
+    assert covered <= total and total - covered < 7 * 1024         # only alignment gaps are outside the stages
+    H = 1024
+    for layer in m.encoder.layers:
+        a = layer.attn
+        assert offs[id(a.key.weight)] == offs[id(a.query.weight)] + H * H and offs[id(a.value.weight)] == offs[id(a.key.weight)] + H * H
+        assert offs[id(a.key.bias)] == offs[id(a.query.bias)] + H and offs[id(a.value.bias)] == offs[id(a.key.bias)] + H
+    spans = sorted((offs[id(p)], offs[id(p)] + p.numel()) for p in m.parameters())
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))     # no two parameters overlap
+    emb = next(e for e in lay if e["stage"] == 6)
+    assert emb["big"][0] <= offs[id(m.encoder.embedder.stack_projection.weight)] < emb["big"][1]
+    assert emb["small"][0] <= offs[id(m.encoder.embedder.embed_pos.weight)] < emb["small"][1]    # the position table is read in fp32: replicated region
+
+
+def test_reference_install_manifest_matches_the_tree():
+    """baseline/reference_manifest.json (committed) lists the sha256 of every reference file bench.py's reference arm runs; when the
+    copy exists (build container, GPU box) it must match, i.e. the arm really times the UNMODIFIED reference."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import install_reference as ir
+    man = json.load(open(ir.MANIFEST))["files"]
+    assert "models/ndt1.py" in man and "models/masker.py" in man and "configs/trainer_ctc_ndt1.yaml" in man and len(man) >= 20
+    if os.path.isdir(ir.DST):
+        assert ir.verify(ir.DST)

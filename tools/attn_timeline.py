@@ -34,29 +34,42 @@ for name, bwd in (("fwd", False), ("fwd+bwd", True)):
     print(f"{name}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per layer")
 
 ncta = 2 * NH * B
-buf = torch.zeros(ncta * 32, dtype=torch.int64, device=dev)
+buf = torch.zeros(65536 + 148 * 64, dtype=torch.int64, device=dev)
 Lb.ndt1_debug_attention_timeline(buf.data_ptr())
-run()
+run(True)
 torch.cuda.synchronize()
 Lb.ndt1_debug_attention_timeline(None)
-t = buf.cpu().numpy().reshape(ncta, 32).astype(np.int64)
-names = {0: "start", 1: "tmem alloc'd", 2: "setup sync done", 3: "K,V landed", 4: "S(0) issued", 5: "S(0) ready", 6: "S(1) ready", 7: "S(2) ready",
-         8: "S(3) ready", 9: "last P written", 10: "accumulators done", 11: "stores issued", 12: "dV/dK(0) issued", 13: "dV/dK(1) issued",
-         14: "dV/dK(2) issued", 15: "dV/dK(3) issued", 16: "exit", 17: "S(1) issued", 18: "S(2) issued", 19: "S(3) issued", 20: "(no S(4))",
-         21: "P(0) seen by MMA", 22: "P(1) seen by MMA", 23: "P(2) seen by MMA", 24: "P(3) seen by MMA"}
-base = t[:, 0:1]
-rel = (t - base) / 1e3
-print("key-side backward, mean time since CTA start (us):")
+raw = buf.cpu().numpy().astype(np.int64)
+
+# ---- forward kernel: 32 slots per CTA
+t = raw[:ncta * 32].reshape(ncta, 32)
+names = {0: "start", 1: "set-up done", 2: "Q, K landed", 3: "S ready", 4: "row maxima done", 5: "P written", 6: "V landed", 7: "O ready",
+         8: "output staged", 9: "stores read smem", 16: "exit"}
+rel = (t - t[:, 0:1]) / 1e3
+print("forward, mean time since CTA start (us):")
 for k in sorted(names):
     v = rel[:, k][t[:, k] > 0]
     if len(v):
         print(f"  {names[k]:22s} {v.mean():7.2f}  (min {v.min():6.2f} max {v.max():6.2f})")
 sm = t[:, 31]
-gaps = []
-for s_ in np.unique(sm):
-    idx = np.where(sm == s_)[0]
-    order = idx[np.argsort(t[idx, 0])]
-    for a_, b_ in zip(order[:-1], order[1:]):
-        gaps.append((t[b_, 0] - t[a_, 16]) / 1e3)
-print(f"gap between a CTA's exit and the next CTA's start on the same SM: mean {np.mean(gaps):.2f} us, max {np.max(gaps):.2f} us; "
-      f"kernel span {(t[:, 16].max() - t[:, 0].min()) / 1e3:.1f} us, CTA mean {rel[:, 16].mean():.2f} us")
+print(f"  kernel span {(t[:, 16].max() - t[:, 0].min()) / 1e3:.1f} us, CTA mean {rel[:, 16].mean():.2f} us, CTAs per SM {ncta / len(np.unique(sm)):.2f}")
+starts = np.sort(t[:, 0] - t[:, 0].min()) / 1e3
+print("  CTA start times (us), deciles:", " ".join(f"{starts[int(q * (ncta - 1))]:.1f}" for q in np.linspace(0, 1, 11)))
+
+# ---- persistent key-side backward: 64 slots per CTA, 12 per item for the first four items
+k3 = raw[65536:].reshape(148, 64)
+live = k3[:, 0] > 0
+k3 = k3[live]
+t0 = k3[:, 0:1]
+inames = {0: "item start", 11: "K/V requested", 2: "S(0) seen", 3: "S(1) seen", 4: "S(2) seen", 5: "S(3) seen", 1: "last P written",
+          10: "last products queued", 6: "accumulators done", 7: "staging written", 8: "stores read smem"}
+print(f"key-side backward (persistent), {live.sum()} CTAs, time since the CTA's first item started (us):")
+for it in range(4):
+    print(f" item {it}:")
+    for k in (0, 11, 2, 3, 4, 5, 1, 10, 6, 7, 8):
+        col = k3[:, it * 12 + k]
+        v = ((col - t0[:, 0]) / 1e3)[col > 0]
+        if len(v):
+            print(f"  {inames[k]:22s} {v.mean():7.2f}  (min {v.min():6.2f} max {v.max():6.2f})")
+ex = k3[:, 63]
+print(f"  exit {((ex - t0[:, 0]) / 1e3)[ex > 0].mean():.2f} us; kernel span {(ex.max() - k3[:, 0].min()) / 1e3:.1f} us")
