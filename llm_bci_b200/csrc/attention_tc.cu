@@ -52,13 +52,6 @@ __device__ __forceinline__ void dbg_mark64(const TcAttn& a, int slot) {       //
     a.dbg[65536 + (long long)blockIdx.x * 64 + slot] = t;        // (behind the 3-D-grid kernels' 32 slots x up to 2048 CTAs)
   }
 }
-__device__ __forceinline__ void dbg_markq(const TcAttn& a, int slot) {        // persistent query-side backward: 64 slots per CTA, third region
-  if (a.dbg && slot < 64) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    a.dbg[65536 + 148 * 64 + (long long)blockIdx.x * 64 + slot] = t;
-  }
-}
 __device__ __forceinline__ void dbg_smid(const TcAttn& a, int slot) {
   if (a.dbg) {
     unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
@@ -213,7 +206,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int nks = (L + 15) / 16;            // key steps of 16 actually holding keys
-
+  // (Measured, round 2: starting the second co-resident CTA of every SM ~4 us late, so that one CTA's load / MMA / store phases
+  //  fall under the other's softmax, changes nothing -- 28.0 vs 29.6 us kernel span, no change in a step: the two CTAs do not
+  //  contend, each is bound by its own chain of dependent latencies.)
   if (tid == 0) {
     dbg_mark(a, 1);                         // set-up done
     mbar_wait(&bars[0], 0);
@@ -547,266 +542,12 @@ attn_tc_bwd_q_kernel(const __grid_constant__ CUtensorMap map128, const __grid_co
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-// ---------------------------------------------------------------------------
-// backward, query side, PERSISTENT.  The one-CTA-per-tile kernel above runs load -> S, dP -> dS -> dQ -> store strictly in
-// sequence with one CTA per SM (its 224 KB of operands), i.e. every microsecond of load latency, set-up and tear-down is exposed
-// 3.5 times per SM.  Here one CTA per SM walks a list of (trial, head) items, both 128-query tiles of an item against the SAME
-// resident K / V (fetched once instead of twice), warp-specialised (TMA producer / MMA issuer / 16 compute warps):
-//   * the next tile's Q and dO are fetched as soon as this tile's S = Q K^T and dP = dO V^T have retired (and the compute warps
-//     have formed delta from dO), the next item's K / V as soon as this item's last dQ = dS K has;
-//   * the next tile's S is issued right behind this tile's dQ products (S lands on [0,256), where dS has been consumed by then);
-//     only dP waits until the compute warps have drained dQ from [256,384);
-//   * the dQ tile leaves through O's buffer (dead once delta is formed) by a bulk store issued by the producer.
-// Tensor memory as above: S [0,256) -> dS bf16 in place; dP [256,512); dQ over [256,384).
-// ---------------------------------------------------------------------------
-constexpr int BQ2_CWARPS = 16, BQ2_THREADS = 64 + 32 * BQ2_CWARPS;
-constexpr int BQ2_TILES = 65536 * 2 + 32768 * 3;                    // K, V, Q, dO, dQ staging
-constexpr int BQ2_SMALL = 4 * 128 * 4 + 64 + 11 * 8 + 16;           // row-sum partials, key_valid words, barriers, tensor-memory slot
-constexpr int SMEM_BQ2 = 227 * 1024;                                // everything the SM has: the tiles need a 1024-byte aligned base (checked at run time)
-
-__global__ void __launch_bounds__(BQ2_THREADS, 1)
-attn_tc_bwd_q2_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map256,
-                      const __grid_constant__ CUtensorMap mapdo, const __grid_constant__ CUtensorMap mapdqkv, const TcAttn a, const int n_items) {
-  pdl_grid_sync();
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  if ((int)(smem - smem_raw) + BQ2_TILES + BQ2_SMALL > SMEM_BQ2) {   // (the dynamic segment starts 1 KB into the SM's window: aligned in practice)
-    if (threadIdx.x == 0) printf("attn_tc_bwd_q2: shared-memory base misaligned by %d bytes\n", (int)(smem - smem_raw));
-    __trap();
-  }
-  uint8_t* sK = smem;                 // 64 KB
-  uint8_t* sV = sK + 65536;           // 64 KB
-  uint8_t* sQ = sV + 65536;           // 32 KB
-  uint8_t* sdO = sQ + 32768;          // 32 KB
-  uint8_t* sDQ = sdO + 32768;         // 32 KB   the dQ tile, staged for the bulk store
-  float* s_part = (float*)(sDQ + 32768);          // [4][128] partial row sums of P * dP (one per 64-key column group)
-  uint32_t* s_kvw = (uint32_t*)(s_part + 512);    // [2][8] key_valid bits, double-buffered over items
-  uint64_t* bars = (uint64_t*)(s_kvw + 16);
-  uint64_t* kv_full = bars;            // K / V of the item landed
-  uint64_t* kv_free = bars + 1;        // the item's last dQ products retired
-  uint64_t* qdo_full = bars + 2;       // Q and dO of the tile landed
-  uint64_t* qdo_free = bars + 3;       // S / dP retired
-  uint64_t* s_full = bars + 4;         // S and dP ready
-  uint64_t* ds_full = bars + 5;        // dS written back (16 warps)
-  uint64_t* dq_done = bars + 6;        // dQ products retired
-  uint64_t* dq_drained = bars + 7;     // dQ read from tensor memory (16 warps)
-  uint64_t* stage_ready = bars + 8;    // dQ tile staged in shared memory (16 warps)
-  uint64_t* stage_free = bars + 9;     // the previous tile's store has read the staging tile
-  uint32_t* tmem_slot = (uint32_t*)(bars + 10);
-
-  const AttnParams& p = a.p;
-  const int L = p.L, H = p.H;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nq = (L + TQ - 1) / TQ;                     // query tiles per item (1 or 2)
-  const int nks = (L + 15) / 16;
-  const int my_items = blockIdx.x < n_items ? (n_items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-  const int my_tiles = my_items * nq;
-  auto item_of = [&](int it, int& b, int& h) { const int bh = blockIdx.x + it * gridDim.x; h = bh % p.nh; b = bh / p.nh; };
-
-  if (tid == 0) {
-    mbar_init(kv_full, 1); mbar_init(kv_free, 1); mbar_init(qdo_full, 1); mbar_init(qdo_free, 1);
-    mbar_init(s_full, 1); mbar_init(ds_full, BQ2_CWARPS); mbar_init(dq_done, 1); mbar_init(dq_drained, BQ2_CWARPS);
-    mbar_init(stage_ready, BQ2_CWARPS); mbar_init(stage_free, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== TMA producer (and bulk stores) =====================
-    if (lane == 0) {
-      auto store_tile = [&](int t) {             // tile t's dQ, staged in sDQ by the compute warps
-        int b, h; item_of(t / nq, b, h);
-        mbar_wait(stage_ready, t & 1);
-        for (int c = 0; c < 2; ++c) tma_store_3d(&mapdqkv, sDQ + c * 16384, h * HD + 64 * c, (t % nq) * TQ, b);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        mbar_arrive(stage_free);
-        if (t < 4) dbg_markq(a, t * 8 + 7);      // the tile's store has read shared memory
-      };
-      for (int t = 0; t < my_tiles; ++t) {
-        const int it = t / nq, q0 = (t % nq) * TQ;
-        int b, h; item_of(it, b, h);
-        if (t % nq == 0) {                       // first tile of an item: its K / V
-          if (it > 0) mbar_wait(kv_free, (it - 1) & 1);
-          mbar_expect_tx(kv_full, 131072);
-          for (int c = 0; c < 2; ++c) tma_load_3d(sK + c * 32768, &map256, kv_full, H + h * HD + 64 * c, 0, b);
-          for (int c = 0; c < 2; ++c) tma_load_3d(sV + c * 32768, &map256, kv_full, 2 * H + h * HD + 64 * c, 0, b);
-        }
-        if (t > 0) mbar_wait(qdo_free, (t - 1) & 1);
-        mbar_expect_tx(qdo_full, 65536);
-        for (int c = 0; c < 2; ++c) tma_load_3d(sQ + c * 16384, &map128, qdo_full, h * HD + 64 * c, q0, b);
-        for (int c = 0; c < 2; ++c) tma_load_3d(sdO + c * 16384, &mapdo, qdo_full, h * HD + 64 * c, q0, b);
-        if (t > 0) store_tile(t - 1);
-      }
-      if (my_tiles > 0) store_tile(my_tiles - 1);
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && my_tiles > 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 256, false, false);
-      constexpr uint32_t idesc_q = make_idesc_bf16(128, 128, false, true);
-      const uint64_t qd = make_sdesc(smem_u32(sQ), 16, 1024), kd = make_sdesc(smem_u32(sK), 16, 1024);
-      const uint64_t od = make_sdesc(smem_u32(sdO), 16, 1024), vd = make_sdesc(smem_u32(sV), 16, 1024);
-      const uint64_t km = make_sdesc(smem_u32(sK), 32768, 1024);          // K as the MN-major operand (rows = keys)
-      auto issue_S = [&](int t) {               // S = Q K^T of tile t (operands resident)
-        if (t % nq == 0) { mbar_wait(kv_full, (t / nq) & 1); }
-        mbar_wait(qdo_full, t & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)
-          tc_mma_bf16(tmem, sdesc_advance(qd, (ks >> 2) * 16384 + (ks & 3) * 32), sdesc_advance(kd, (ks >> 2) * 32768 + (ks & 3) * 32), idesc_s, ks > 0 ? 1u : 0u);
-      };
-      auto issue_dP = [&](int t) {              // dP = dO V^T of tile t, then S and dP are announced and Q / dO released
-#pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)
-          tc_mma_bf16(tmem + 256, sdesc_advance(od, (ks >> 2) * 16384 + (ks & 3) * 32), sdesc_advance(vd, (ks >> 2) * 32768 + (ks & 3) * 32), idesc_s,
-                      ks > 0 ? 1u : 0u);
-        tc_commit(s_full);
-        tc_commit(qdo_free);
-      };
-      issue_S(0);
-      issue_dP(0);
-      for (int t = 0; t < my_tiles; ++t) {
-        mbar_wait(ds_full, t & 1);
-        tc_fence_after();
-        for (int ks = 0; ks < nks; ++ks)          // 16 keys = 8 packed columns: group ks / 4, offset 8 (ks % 4)
-          tc_mma_bf16_ts(tmem + 256, tmem + (ks >> 2) * 64 + (ks & 3) * 8, sdesc_advance(km, ks * 2048), idesc_q, ks > 0 ? 1u : 0u);
-        tc_commit(dq_done);
-        if (t % nq == nq - 1) tc_commit(kv_free);                 // the item's K / V are dead when these retire
-        if (t + 1 < my_tiles) {
-          issue_S(t + 1);                                          // [0,256): dS of tile t is consumed by the products queued above
-          mbar_wait(dq_drained, t & 1);                            // [256,384): dQ of tile t has been read
-          tc_fence_after();
-          issue_dP(t + 1);
-        }
-      }
-    }
-  } else {
-    // ===================== compute warps =====================
-    // delta_i = sum_d dO_id O_id = sum_j P_ij dP_ij (with the probability dropout inside dP): formed HERE from S and dP in a first pass
-    // over tensor memory -- no O tile is loaded -- then dS = P (dP - delta) scale in a second pass (the exponentials are recomputed:
-    // 1 us of MUFU per tile, against 2 us of waiting for a 32 KB tile whose buffer the previous tile's store still occupied).
-    const int cw = warp - 2;
-    const int quarter = warp & 3, grp = cw >> 2;             // TMEM lane quarter; which 64 of the 256 key columns
-    const int row = quarter * 32 + lane;
-    const int ctid = tid - 64;                               // 0..511
-    const int cbase = grp * 64;
-    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
-    const float sl2 = p.scale * kLog2e;
-    const float lg_scale = log2f(p.scale);
-    const bool drop = p.p_attn > 0.f;
-    const float ik = drop ? 1.0f / (1.0f - p.p_attn) : 1.f;
-    for (int t = 0; t < my_tiles; ++t) {
-      const int it = t / nq, q0 = (t % nq) * TQ;
-      int b, h; item_of(it, b, h);
-      const int qi = q0 + row;
-      const long long bh_row = ((long long)b * p.nh + h) * L + qi;
-      if (ctid == 0 && t < 4) dbg_markq(a, t * 8 + 0);         // tile start (compute warps)
-      if (t % nq == 0 && cw < 8) {                             // key_valid bits of the item (8 words), by the first 8 compute warps
-        const int j = cw * 32 + lane;
-        const uint32_t w = __ballot_sync(0xffffffffu, j < L && p.key_valid[(long long)b * L + j] != 0);
-        if (lane == 0) s_kvw[(it & 1) * 8 + cw] = w;
-      }
-      const float lse2 = qi < L ? p.lse[bh_row] * kLog2e : 0.f;
-      uint32_t kw[2];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int c0 = cbase + 32 * c;
-        kw[c] = (drop && qi < L && c0 < L) ? p.drop_bits[bh_row * 8 + (c0 >> 5)] : 0xFFFFFFFFu;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * BQ2_CWARPS) : "memory");     // s_kvw visible; the previous tile's s_part readers are done
-      uint32_t mw[2];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) mw[c] = query_mask_word(qi, cbase + 32 * c, a.cf, a.cb, s_kvw[(it & 1) * 8 + grp * 2 + c], L);
-      mbar_wait(s_full, t & 1);
-      tc_fence_after();
-      if (ctid == 0 && t < 4) dbg_markq(a, t * 8 + 3);         // S, dP seen
-      // ---- pass 1: this thread's part of delta over its 64 key columns
-      float part = 0.f;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int c0 = cbase + 32 * c;
-        if (c0 < L) {                                            // warp-uniform
-          uint32_t rs[32], rp[32];
-          tmem_ld32(trow + c0, rs);
-          tmem_ld32(trow + 256 + c0, rp);
-          tmem_ld_wait();
-          const uint32_t m = mw[c], k = kw[c];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sv = fmaf(__uint_as_float(rs[j]), sl2, -lse2);
-            const float pr = ex2f((m >> j) & 1u ? sv : -INFINITY);
-            part = fmaf(pr, (k >> j) & 1u ? __uint_as_float(rp[j]) : 0.f, part);
-          }
-        }
-      }
-      s_part[grp * 128 + row] = part * ik;
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * BQ2_CWARPS) : "memory");
-      const float del = s_part[row] + s_part[128 + row] + s_part[256 + row] + s_part[384 + row];
-      if (grp == 0 && qi < L) p.delta[bh_row] = del;             // the key-side kernel (launched after this one) reads it
-      if (ctid == 0 && t < 4) dbg_markq(a, t * 8 + 2);         // delta formed
-      // ---- pass 2: dS = P (dP - delta) scale, back in place as bf16
-      const float lse2s = lse2 - lg_scale;                       // 2^(s - lse2s) = P * scale
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int c0 = cbase + 32 * c;
-        uint32_t ds[16];
-        if (c0 < L) {                                            // warp-uniform
-          uint32_t rs[32], rp[32];
-          tmem_ld32(trow + c0, rs);
-          tmem_ld32(trow + 256 + c0, rp);
-          tmem_ld_wait();
-          const uint32_t m = mw[c], k = kw[c];
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float v[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float sv = fmaf(__uint_as_float(rs[j + u]), sl2, -lse2s);
-              const float pr = ex2f((m >> (j + u)) & 1u ? sv : -INFINITY);
-              const float tt = (k >> (j + u)) & 1u ? __uint_as_float(rp[j + u]) * ik : 0.f;
-              v[u] = pr * (tt - del);
-            }
-            ds[j >> 1] = pack_bf16x2(v[0], v[1]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) ds[j] = 0u;
-        }
-        if (c0 < nks * 16) tmem_st16(trow + cbase + 16 * c, ds);   // keys [c0, c0+32) -> 16 packed columns inside this thread's own range
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
-      if (ctid == 0 && t < 4) dbg_markq(a, t * 8 + 4);         // dS written
-      // ---- dQ: tensor memory -> registers -> the staging tile (free once the previous tile's store has read it)
-      mbar_wait(dq_done, t & 1);
-      tc_fence_after();
-      if (ctid == 0 && t < 4) dbg_markq(a, t * 8 + 5);         // dQ seen
-      uint32_t raw[32];                                        // this thread: row `row`, head-dim columns [32 grp, +32)
-      tmem_ld32(trow + 256 + grp * 32, raw);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dq_drained);
-      if (t > 0) mbar_wait(stage_free, (t - 1) & 1);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) st_row8(sDQ, row, grp * 32 + g * 8, (const float*)raw + g * 8);
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(stage_ready);
-      if (ctid == 0 && t < 4) dbg_markq(a, t * 8 + 6);         // dQ staged
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); if (lane == 0) dbg_markq(a, 63); }
-}
+// (Measured dead end, round 2 -- git history has the kernel: a PERSISTENT query-side backward, one CTA per SM over the (trial, head)
+// items with K / V resident for both query tiles, Q / dO prefetched behind the S / dP products, delta formed from S and dP in tensor
+// memory instead of from an O tile, the dQ store issued by the producer warp.  Alone it takes 33 us per layer against 40 us for the
+// kernel above, but inside the training step it is 45 us per step SLOWER: a CTA that holds an SM's whole shared memory for the
+// kernel's duration keeps the weight-gradient GEMMs of the second stream off that SM, while the short-lived CTAs of the per-tile
+// kernel interleave with them.  The same experiment on the key side, which has four times more work per CTA, does pay: kv3 below.)
 
 // ---------------------------------------------------------------------------
 // backward, key side: dK, dV (accumulated over the query tiles in TMEM).
@@ -1525,7 +1266,6 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV));
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV2));
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BKV3));
-    NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_q2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BQ2));
     attr.here() = true;
   }
   TcAttn a; a.p = p; a.cf = p.ctx_fwd; a.cb = p.ctx_bwd; a.dbg = g_attn_dbg;
@@ -1540,13 +1280,7 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream) {
   // query side first: it also forms delta = rowsum(dO * O), which the key side reads
   const double mm = 2.0 * p.B * p.nh * (double)p.L * p.L * HD;
   if (g_ndt1_prof_on) ndt1_prof_note(2 * mm, 0.0);                  // algorithmic: dP = dO V^T and dQ = dS K (the recomputed S is not counted)
-  static const bool q1_only = getenv("NDT1_ATTN_BWD_Q1") && getenv("NDT1_ATTN_BWD_Q1")[0] == '1';
-  if (q1_only) {
-    ndt1_launch(attn_tc_bwd_q_kernel, grid, BQ_THREADS, SMEM_BQ, stream, m128, m256, mdo, mo, mdq, a);
-  } else {                                         // persistent: one CTA per SM over the (trial, head) items
-    const int n_bh = p.B * p.nh, sms_q = ndt1_num_sms();
-    ndt1_launch(attn_tc_bwd_q2_kernel, dim3(n_bh < sms_q ? n_bh : sms_q), BQ2_THREADS, SMEM_BQ2, stream, m128, m256, mdo, mdq, a, n_bh);
-  }
+  ndt1_launch(attn_tc_bwd_q_kernel, grid, BQ_THREADS, SMEM_BQ, stream, m128, m256, mdo, mo, mdq, a);
   NDT1_CHECK_LAUNCH();
   static const bool old_kv = getenv("NDT1_ATTN_BWD_KV1") && getenv("NDT1_ATTN_BWD_KV1")[0] == '1';
   if (old_kv) {

@@ -34,7 +34,7 @@ for name, bwd in (("fwd", False), ("fwd+bwd", True)):
     print(f"{name}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per layer")
 
 ncta = 2 * NH * B
-buf = torch.zeros(65536 + 2 * 148 * 64, dtype=torch.int64, device=dev)
+buf = torch.zeros(65536 + 148 * 64, dtype=torch.int64, device=dev)
 Lb.ndt1_debug_attention_timeline(buf.data_ptr())
 run(True)
 torch.cuda.synchronize()
@@ -74,17 +74,3 @@ for it in range(4):
 ex = k3[:, 63]
 print(f"  exit {((ex - t0[:, 0]) / 1e3)[ex > 0].mean():.2f} us; kernel span {(ex.max() - k3[:, 0].min()) / 1e3:.1f} us")
 
-# ---- persistent query-side backward: 8 slots per tile for the first four tiles of a CTA
-q2 = raw[65536 + 148 * 64:].reshape(148, 64)
-q2 = q2[q2[:, 0] > 0]
-qn = {0: "tile start", 1: "Q, dO, O landed", 2: "delta formed", 3: "S, dP seen", 4: "dS written", 5: "dQ seen", 6: "dQ staged", 7: "store read smem"}
-print(f"query-side backward (persistent), {len(q2)} CTAs, time since the CTA's first tile started (us):")
-for t_ in range(4):
-    print(f" tile {t_}:")
-    for k in range(8):
-        col = q2[:, t_ * 8 + k]
-        v = ((col - q2[:, 0]) / 1e3)[col > 0]
-        if len(v):
-            print(f"  {qn[k]:22s} {v.mean():7.2f}  (min {v.min():6.2f} max {v.max():6.2f})")
-ex = q2[:, 63]
-print(f"  exit {((ex - q2[:, 0]) / 1e3)[ex > 0].mean():.2f} us; kernel span {(ex.max() - q2[:, 0].min()) / 1e3:.1f} us")
