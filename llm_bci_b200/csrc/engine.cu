@@ -692,8 +692,10 @@ struct Engine : ndt1_engine {
         if (k.mlp_act == NDT1_ACT_GELU) { e.dact = DACT_GELU_FROM_IN; e.dact_in = u[l]; }
         else { e.dact = dact_from_out(k.mlp_act); e.dact_in = g[l]; }
         e.dact_in_bf16 = kBf16;
-        // (with the second stream the reduction runs there, off the data-gradient chain; fused into the epilogue otherwise)
-        const bool fuse_cs = kBf16 && !force_simt && !overlap && gq.up_b && k.mlp_bias && I % 8 == 0;
+        // the up-projection's bias gradient = column sums of dU: fused into this GEMM's epilogue (a separate reduction on the second
+        // stream costs 12 us of SM time per layer that the overlapped weight-gradient GEMMs need: measured ~20 us per step)
+        static const bool separate_cs = getenv("NDT1_FUSE_COLSUM") && getenv("NDT1_FUSE_COLSUM")[0] == '0';
+        const bool fuse_cs = kBf16 && !force_simt && (!overlap || !separate_cs) && gq.up_b && k.mlp_bias && I % 8 == 0;
         if (fuse_cs) e.colsum = gq.up_b;
         NDT1_TRY(linear_dgrad(dY, H, W(q.down_w, kBf16 ? u_down[l] : nullptr), I, (int)M, H, I, e, s));
         NDT1_TRY(fork());
