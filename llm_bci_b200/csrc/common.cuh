@@ -233,7 +233,8 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 // ---------------------------------------------------------------------------
 enum { ACT_NONE = 0, ACT_SOFTSIGN = 1, ACT_GELU = 2, ACT_RELU = 3 };
 // derivative selectors for backward epilogues
-enum { DACT_NONE = 0, DACT_SOFTSIGN_FROM_OUT = 1, DACT_GELU_FROM_IN = 2, DACT_RELU_FROM_OUT = 3 };
+enum { DACT_NONE = 0, DACT_SOFTSIGN_FROM_OUT = 1, DACT_GELU_FROM_IN = 2, DACT_RELU_FROM_OUT = 3,
+       DACT_SAVED = 4 };     // the saved tensor IS act'(pre-activation), written by the forward epilogue (GemmEpilogue::out2_deriv)
 
 __device__ __forceinline__ float act_apply(int act, float v) {
   switch (act) {
@@ -252,6 +253,7 @@ __device__ __forceinline__ float dact_apply(int dact, float saved) {
       return cdf + saved * pdf;
     }
     case DACT_RELU_FROM_OUT: return saved > 0.f ? 1.f : 0.f;
+    case DACT_SAVED: return saved;
     default: return 1.f;
   }
 }

@@ -123,20 +123,27 @@ __device__ __forceinline__ void ctc_sweep(const CtcParams& p, const float* __res
         }
         x2[i] = skip[i] ? x2[i] : -INFINITY;
       }
+      // log(e^a + e^b + e^c) = m + log(1 + e^(r - m) + e^(q - m)) with {m, r, q} the three values sorted so that m is the largest:
+      // the largest term is exactly 1, two exponentials per state instead of three (the MUFU pipe is what a frame step waits for)
 #pragma unroll
       for (int i = 0; i < SPT; ++i) {
-        const float m = fmaxf(x0[i], fmaxf(x1[i], x2[i]));
-        ms[i] = (m == -INFINITY) ? 0.f : m;                   // all -inf -> exp(-inf) = 0 -> log(0) = -inf, no branch
+        const float hi = fmaxf(x0[i], x1[i]), lo = fminf(x0[i], x1[i]);
+        const float m = fmaxf(hi, x2[i]);
+        x1[i] = fminf(hi, x2[i]); x0[i] = lo;
+        ms[i] = m;
       }
 #pragma unroll
-      for (int i = 0; i < SPT; ++i) { x0[i] = exp_t<FAST>(x0[i] - ms[i]); x1[i] = exp_t<FAST>(x1[i] - ms[i]); x2[i] = exp_t<FAST>(x2[i] - ms[i]); }
+      for (int i = 0; i < SPT; ++i) {
+        const float mz = (ms[i] == -INFINITY) ? 0.f : ms[i];   // all -inf: no NaN from (-inf) - (-inf); the result is forced below
+        x0[i] = exp_t<FAST>(x0[i] - mz); x1[i] = exp_t<FAST>(x1[i] - mz);
+      }
 #pragma unroll
-      for (int i = 0; i < SPT; ++i) sum[i] = x0[i] + x1[i] + x2[i];
+      for (int i = 0; i < SPT; ++i) sum[i] = 1.0f + x0[i] + x1[i];
 #pragma unroll
       for (int i = 0; i < SPT; ++i) sum[i] = log_t<FAST>(sum[i]);
 #pragma unroll
       for (int i = 0; i < SPT; ++i) {
-        const float r = ms[i] + sum[i];
+        const float r = ms[i] + sum[i];                        // ms = -inf stays -inf
         v[i] = (live[i] && r != -INFINITY) ? r + e[i] : -INFINITY;
       }
     }

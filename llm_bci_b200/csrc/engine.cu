@@ -10,7 +10,7 @@
 //   LN outputs        h1[l], h2[l], hn  T (B*L, H)      GEMM A operands / wgrad B operands
 //   qkv[l]            T (B*L, 3H)  q|k|v packed so one GEMM (N = 3H) produces it
 //   att[l], attd[l]   T (B*L, H)   attention output before / after output dropout
-//   u[l], g[l]        T (B*L, I)   MLP pre-activation / activation
+//   u[l], g[l]        T (B*L, I)   MLP activation derivative GELU'(pre-activation) (the pre-activation itself for other activations) / activation
 //   emb               T (B*T, D)   softsign(embed_spikes(x)); the stack projection
 //                                  reads it as (B, T/stride, stride*D) shifted windows
 //   bf16 mode keeps bf16 copies of the weights (QKV concatenated) refreshed per forward.
@@ -495,7 +495,7 @@ struct Engine : ndt1_engine {
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = g[l]; e.out_bf16 = kBf16; e.ldc = I; e.bias = k.mlp_bias ? q.up_b : nullptr; e.act = act_code(k.mlp_act);
-        e.out2 = u[l]; e.out2_bf16 = kBf16;
+        e.out2 = u[l]; e.out2_bf16 = kBf16; e.out2_deriv = k.mlp_act == NDT1_ACT_GELU;     // u[l] = GELU'(pre-activation) then
         NDT1_TRY(linear_fwd(h2[l], H, W(q.up_w, kBf16 ? u_up[l] : nullptr), H, (int)M, I, H, e, s));
       }
       {
@@ -689,7 +689,7 @@ struct Engine : ndt1_engine {
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = dU; e.out_bf16 = kBf16; e.ldc = I;
-        if (k.mlp_act == NDT1_ACT_GELU) { e.dact = DACT_GELU_FROM_IN; e.dact_in = u[l]; }
+        if (k.mlp_act == NDT1_ACT_GELU) { e.dact = DACT_SAVED; e.dact_in = u[l]; }
         else { e.dact = dact_from_out(k.mlp_act); e.dact_in = g[l]; }
         e.dact_in_bf16 = kBf16;
         // the up-projection's bias gradient = column sums of dU: fused into this GEMM's epilogue (a separate reduction on the second

@@ -39,8 +39,10 @@ struct GemmEpilogue {
   int out_bf16;
   long long ldc;
   long long c_batch_stride;
-  void* out2;               // optional copy of the pre-activation value
+  void* out2;               // optional copy of the pre-activation value ...
   int out2_bf16;
+  int out2_deriv;           // ... or (1, GELU only) of act'(pre-activation): the backward epilogue then multiplies (DACT_SAVED) instead of
+                            // evaluating erf and exp again; exp(-v^2/2) is already at hand in the forward
   const float* bias;        // [N] or null
   float alpha;
   int act;                  // ACT_*
@@ -81,7 +83,7 @@ struct GemmProblem {
 static inline GemmEpilogue gemm_epilogue_default() {
   GemmEpilogue e;
   e.out = nullptr; e.out_bf16 = 0; e.ldc = 0; e.c_batch_stride = 0;
-  e.out2 = nullptr; e.out2_bf16 = 0; e.bias = nullptr; e.alpha = 1.f; e.act = ACT_NONE;
+  e.out2 = nullptr; e.out2_bf16 = 0; e.out2_deriv = 0; e.bias = nullptr; e.alpha = 1.f; e.act = ACT_NONE;
   e.gather_tab = nullptr; e.gather_idx = nullptr; e.gather_idx_stride = 0; e.gather_ld = 0;
   e.drop_p = 0.f; e.drop_bwd = 0; e.drop_seed = SeedRef(); e.drop_stream = 0;
   e.resid = nullptr; e.dact = DACT_NONE; e.dact_in = nullptr; e.dact_in_bf16 = 0;
@@ -105,7 +107,7 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmEpilogue& e, int n
   }
   float v = acc * e.alpha;
   if (e.bias) v += e.bias[bias_off + n];
-  if (e.out2) store_from_f32(e.out2, idx, e.out2_bf16, v);
+  if (e.out2) store_from_f32(e.out2, idx, e.out2_bf16, e.out2_deriv ? dact_apply(DACT_GELU_FROM_IN, v) : v);
   v = act_apply(e.act, v);
   if (e.gather_tab) {
     const long long g = e.gather_idx[(long long)b * e.gather_idx_stride + r];

@@ -20,6 +20,7 @@
 #include <mutex>
 #include <unordered_map>
 #include <vector>
+#include <algorithm>
 
 namespace {
 
@@ -29,6 +30,7 @@ constexpr int kEpiWarps = 8;           // two warps per TMEM lane quarter, each 
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemPipe = 192 * 1024;  // operand ring
 constexpr int kStageTile = 32 * 32 * 4;   // per-warp staging tile of the epilogue: 32 rows x 32 fp32
+constexpr int kMaxRagTiles = 320;         // ragged tile table carried in the kernel parameters
 
 struct TcParams {
   int mode;
@@ -41,6 +43,13 @@ struct TcParams {
   const long long* b_sel; int b_sel_n; // per-day B operand batch of an output trial (GEMM_NT), null = batch 0
   unsigned long long* dbg;             // optional per-CTA phase timeline (tools/gemm_timeline.py): 16 slots per CTA, globaltimer ns
   GemmEpilogue epi;
+  // Ragged column tiles (CTA pairs, NT / NN, one output batch): when the regular 256-column tiling leaves the last wave partly
+  // empty (7776 x 1024: 124 tiles on 74 pairs), the row strips are cut into tiles of 128 / 192 / 256 columns instead -- as many
+  // tiles as a whole number of waves holds -- and dealt to the pairs by width, so that every pair carries the same number of
+  // columns (+- 64) and the exposed last epilogue is a narrow one.  rag[t] = strip | first 64-column unit << 6 | (units - 1) << 12;
+  // tile t goes to pair t % pairs as always.  tcgen05.mma takes N in steps of 16, the B box is loaded whole (unused rows ignored).
+  int ragged;
+  unsigned short rag[kMaxRagTiles];
 };
 
 using namespace tc;
@@ -108,6 +117,7 @@ enum {
   EPI_ACT = EF_OUT2 | EF_ACT,                            // bias + activation (+ pre-activation copy): MLP up-proj, channel embedding
   EPI_DROP = EF_GATHER | EF_DROP | EF_RESID,             // bias (+ position rows) + dropout (+ residual): MLP down-proj, stack projection
   EPI_DACT = EF_DROP | EF_DACT | EF_COLSUM,              // backward: dropout mask, activation derivative, bias-gradient column sums
+  EPI_DMUL = EF_DACT | EF_COLSUM,                        // backward without a dropout mask (no Philox: fewer registers): MLP down-proj data gradient
   EPI_ACCUM = EF_ACCUM,                                  // weight gradients: fp32 red.add
   EPI_ALL = 511                                          // everything, incl. the element-wise path for ragged shapes
 };
@@ -124,6 +134,7 @@ struct ChunkAt {          // where a (tile, chunk) lands in the output
   long long rowbase;      // element offset of (trial, this lane's first row, column 0): computed once per tile
   long long bias_off;     // per-day bias row (0 without routing)
   uint32_t rowmask;       // bit i: row r0 + lane/8 + 4 i of this lane is inside the output (per tile, not per chunk)
+  int nch, tcol;          // 32-column chunks of this warp in the tile; this warp's first accumulator column (ragged tiles vary)
   bool live;
 };
 
@@ -203,7 +214,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
   const uint32_t okm = col_ok ? at.rowmask : 0u;
 #define idx(i) (idx0 + (unsigned)((i) * ld4))
 #define ok(i) ((okm >> (i)) & 1u)
-  if (ef_has(EPI, EF_OUT2) && e.out2) {
+  const bool deriv2 = ef_has(EPI, EF_OUT2) && ef_has(EPI, EF_ACT) && e.out2 && e.out2_deriv && e.act == ACT_GELU;
+  if (ef_has(EPI, EF_OUT2) && e.out2 && !deriv2) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (ok(i)) {
@@ -212,6 +224,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
       }
   }
   if (!ef_has(EPI, EF_ACT)) {
+  } else if (deriv2) {                     // GELU and its derivative from one erf / exp evaluation; out2 = GELU'(v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 d; float cdf, ex;
+      gelu_parts(v[i].x, cdf, ex); d.x = fmaf(v[i].x * 0.3989422804014327f, ex, cdf); v[i].x *= cdf;
+      gelu_parts(v[i].y, cdf, ex); d.y = fmaf(v[i].y * 0.3989422804014327f, ex, cdf); v[i].y *= cdf;
+      gelu_parts(v[i].z, cdf, ex); d.z = fmaf(v[i].z * 0.3989422804014327f, ex, cdf); v[i].z *= cdf;
+      gelu_parts(v[i].w, cdf, ex); d.w = fmaf(v[i].w * 0.3989422804014327f, ex, cdf); v[i].w *= cdf;
+      if (ok(i)) {
+        if (e.out2_bf16) *(uint2*)((bf16*)e.out2 + idx(i)) = pack4_bf16(d.x, d.y, d.z, d.w);
+        else *(float4*)((float*)e.out2 + idx(i)) = d;
+      }
+    }
   } else if (e.act == ACT_GELU) {          // (the activation switch is hoisted out of the element loops: smaller, branch-free code)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[i].x = gelu_fast(v[i].x); v[i].y = gelu_fast(v[i].y); v[i].z = gelu_fast(v[i].z); v[i].w = gelu_fast(v[i].w); }
@@ -279,6 +304,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
       for (int i = 0; i < 8; ++i) {
         v[i].x *= dgelu_fast(sv[i].x); v[i].y *= dgelu_fast(sv[i].y); v[i].z *= dgelu_fast(sv[i].z); v[i].w *= dgelu_fast(sv[i].w);
       }
+    } else if (e.dact == DACT_SAVED) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i].x *= sv[i].x; v[i].y *= sv[i].y; v[i].z *= sv[i].z; v[i].w *= sv[i].w; }
     } else if (e.dact == DACT_SOFTSIGN_FROM_OUT) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -403,9 +431,10 @@ __device__ __forceinline__ void tc_commit_g(uint64_t* bar) {
 // ---------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------
+
 template <int BN, int MODE, int CTAS, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)   // 10 warps: 3 share one SM sub-partition -> 168 registers per thread
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p) {
   constexpr int BNL = BN / CTAS;                       // columns of B held by this CTA
   constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
   constexpr int B_BYTES = BNL * BK * 2;
@@ -417,6 +446,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   constexpr int NCH = BN / 64;                         // 32-column chunks per epilogue warp
+  constexpr bool RAG = (CTAS == 2 && BN == 256 && MODE != GEMM_TN);     // instantiations that may be launched with ragged tiles
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -469,11 +499,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = unit; tile < p.total_tiles; tile += n_units) {
-        const int nt = tile % p.n_tiles;
-        const int rest = tile / p.n_tiles;
-        const int mt = rest % p.m_tiles;
-        const int bz = rest / p.m_tiles;          // trial (NT/NN) or split index (TN)
-        const int m0 = mt * (BM * CTAS) + rank * BM, n0 = nt * BN + rank * BNL;     // this CTA's rows of A / columns of B
+        int mt, bz, n0;
+        if (RAG && p.ragged) {
+          const uint32_t r = p.rag[tile];
+          mt = r & 63; bz = 0;
+          n0 = ((r >> 6) & 63) * 64 + rank * ((int)((r >> 12) + 1) * 32);         // this CTA's half of the tile's columns
+        } else {
+          const int nt = tile % p.n_tiles;
+          const int rest = tile / p.n_tiles;
+          mt = rest % p.m_tiles;
+          bz = rest / p.m_tiles;                  // trial (NT/NN) or split index (TN)
+          n0 = nt * BN + rank * BNL;
+        }
+        const int m0 = mt * (BM * CTAS) + rank * BM;                             // this CTA's rows of A (n0: its columns of B)
         int bsel = 0;
         if (MODE == GEMM_NT && p.b_sel) { const long long d = __ldg(p.b_sel + bz); bsel = (int)(d < 0 ? 0 : (d >= p.b_sel_n ? p.b_sel_n - 1 : d)); }
         int kb0 = 0, kb1 = total_kb;
@@ -528,6 +566,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int per = (total_kb + p.split_k - 1) / p.split_k;
           kb0 = bz * per; kb1 = min(total_kb, kb0 + per);
         }
+        uint32_t idesc = IDESC;
+        if (RAG && p.ragged) idesc = (IDESC & ~(0x3Fu << 17)) | ((((uint32_t)(p.rag[tile] >> 12) + 1) * 8u) << 17);   // N = 64 units: N >> 3 = 8 units
         mbar_wait(&tempty_bar[acc_stage], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc_stage * BN);
@@ -542,7 +582,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint64_t bd0 = B_MN ? make_sdesc(sb, 64 * BK * 2, 1024) : make_sdesc(sb, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            tc_mma_bf16_g<CTAS>(tmem_d, sdesc_advance(ad0, A_MN ? k * (16 * 128) : k * 32), sdesc_advance(bd0, B_MN ? k * (16 * 128) : k * 32), IDESC,
+            tc_mma_bf16_g<CTAS>(tmem_d, sdesc_advance(ad0, A_MN ? k * (16 * 128) : k * 32), sdesc_advance(bd0, B_MN ? k * (16 * 128) : k * 32), idesc,
                                 (kb > kb0 || k > 0) ? 1u : 0u);
           tc_commit_g<CTAS>(&empty_bar[stage]);     // frees the smem slot (in both CTAs) when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -572,13 +612,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     auto tile_at = [&](int tile) {
       ChunkAt at;
       at.live = tile < p.total_tiles;
-      const int nt = tile % p.n_tiles;
-      const int rest = tile / p.n_tiles;
-      const int mt = rest % p.m_tiles;
-      const int bz = rest / p.m_tiles;
+      int mt, bz, col0;
+      at.nch = NCH; at.tcol = half * (BN / 2);
+      if (RAG && p.ragged) {
+        const uint32_t r = at.live ? p.rag[tile] : 0u;
+        mt = r & 63; bz = 0;
+        at.nch = (int)(r >> 12) + 1;                               // units of 64 columns = chunks of 32 per warp
+        at.tcol = half * (at.nch * 32);
+        col0 = ((r >> 6) & 63) * 64 + at.tcol;
+      } else {
+        const int nt = tile % p.n_tiles;
+        const int rest = tile / p.n_tiles;
+        mt = rest % p.m_tiles;
+        bz = rest / p.m_tiles;
+        col0 = nt * BN + half * (BN / 2);
+      }
       at.bt = (MODE == GEMM_TN && !e.sel) ? 0 : bz;                // (routed GEMM_TN: the split index is the trial)
       at.r0 = mt * (BM * CTAS) + rank * BM + q * 32;
-      at.n = nt * BN + half * (BN / 2) + (lane & 7) * 4;          // chunk 0
+      at.n = col0 + (lane & 7) * 4;                                // chunk 0
       at.rowbase = (long long)at.bt * e.c_batch_stride + (long long)(at.r0 + (lane >> 3)) * e.ldc;
       at.rowmask = 0;
 #pragma unroll
@@ -609,18 +660,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(&tfull_bar[acc_stage], acc_phase);
       tc_fence_after();
       if (ew == 0 && lane == 0) { if (tile == unit) dbg_stamp(p.dbg, 7); dbg_stamp(p.dbg, 8); }   // first / last accumulator ready
-      const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * BN + half * (BN / 2));
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * BN + t_cur.tcol);
+      const int nch = RAG ? t_cur.nch : NCH;
+      // (Measured, round 2: issuing the tensor-memory read of chunk c + 1 before chunk c's arithmetic -- 32 more live registers --
+      // changes nothing for the plain classes and costs the residual class 4.7 us per launch: the read is not what a chunk waits for.)
 #pragma unroll 1                                   // one copy of the epilogue code: it must stay inside the instruction cache
-      for (int c = 0; c < NCH; ++c) {
+      for (int c = 0; c < nch; ++c) {
         const ChunkAt at = chunk_of(t_cur, c);
         uint32_t raw[32];
         tmem_ld32(taddr_row + c * 32, raw);
         const float4 bias_cur = bias_load(e, cx, p, at);     // flies under the TMEM load and the transpose (not at the head of the arithmetic)
         // side input of the next chunk (or of the next tile's first chunk) while the TMEM load is in flight
-        const ChunkAt nx = (c + 1 < NCH) ? chunk_of(t_cur, c + 1) : t_nxt;
+        const ChunkAt nx = (c + 1 < nch) ? chunk_of(t_cur, c + 1) : t_nxt;
         side_load<EPI>(e, cx, p, nx, lane, side_nxt);
         tmem_ld_wait();
-        if (c == NCH - 1) {                         // accumulator fully read: hand the TMEM stage back before the stores
+        if (c == nch - 1) {                         // accumulator fully read: hand the TMEM stage back before the stores
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -766,9 +820,9 @@ int epilogue_class(const TcParams& tp, int bn) {
                    (e.gather_tab == nullptr || e.gather_ld % 4 == 0) && (e.drop_p <= 0.f || tp.N % 8 == 0);
   if (!vec || bn != 256) return EPI_ALL;
   // (only the classes launch_256 instantiates for this operand mode)
-  const int nt[4] = {EPI_NONE, EPI_PLAIN, EPI_ACT, EPI_DROP}, nn[2] = {EPI_NONE, EPI_DACT}, tn[1] = {EPI_ACCUM};
+  const int nt[4] = {EPI_NONE, EPI_PLAIN, EPI_ACT, EPI_DROP}, nn[3] = {EPI_NONE, EPI_DMUL, EPI_DACT}, tn[1] = {EPI_ACCUM};
   const int* classes = tp.mode == GEMM_NT ? nt : (tp.mode == GEMM_NN ? nn : tn);
-  const int n = tp.mode == GEMM_NT ? 4 : (tp.mode == GEMM_NN ? 2 : 1);
+  const int n = tp.mode == GEMM_NT ? 4 : (tp.mode == GEMM_NN ? 3 : 1);
   for (int c = 0; c < n; ++c)
     if ((need & ~classes[c]) == 0) return classes[c];
   return EPI_ALL;
@@ -784,6 +838,7 @@ int launch_256(int cls, const CUtensorMap& ma, const CUtensorMap& mb, const TcPa
     if (cls == EPI_DROP) return launch_inst<256, MODE, CTAS, EPI_DROP>(ma, mb, tp, stream);
   } else if (MODE == GEMM_NN) {
     if (cls == EPI_NONE) return launch_inst<256, MODE, CTAS, EPI_NONE>(ma, mb, tp, stream);
+    if (cls == EPI_DMUL) return launch_inst<256, MODE, CTAS, EPI_DMUL>(ma, mb, tp, stream);
     if (cls == EPI_DACT) return launch_inst<256, MODE, CTAS, EPI_DACT>(ma, mb, tp, stream);
   } else {
     if (cls == EPI_ACCUM) return launch_inst<256, MODE, CTAS, EPI_ACCUM>(ma, mb, tp, stream);
@@ -820,6 +875,75 @@ int gemm_tc_init() {
   g_encode = (EncodeTiledFn)fn;
   return 0;
 }
+
+namespace {
+// Ragged column tiles (see TcParams::rag).  The regular tiling gives every strip ceil(U / 4) tiles of 4 units (64 columns each);
+// with `waves` = the number of tiles the busiest pair gets, the plan keeps that number but raises the tile count to waves x pairs
+// by cutting strips into more, narrower tiles (each strip's widths as even as possible, never below 2 units), then deals the
+// tiles to the pairs in order of width, boustrophedon, so that the loads differ by at most one unit.  Adopted only if the busiest
+// pair then carries fewer columns than before.
+struct RagPlan { int S, U, pairs, total; unsigned short rag[kMaxRagTiles]; };
+std::vector<RagPlan> g_rag_plans;      // one entry per (strips, units, pairs) seen: a handful of shapes per model (guarded by g_mu)
+
+void plan_ragged_build(TcParams& tp, int pairs);
+void plan_ragged(TcParams& tp, int pairs) {
+  const int S = tp.m_tiles, U = tp.N / 64;
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (const RagPlan& r : g_rag_plans)
+    if (r.S == S && r.U == U && r.pairs == pairs) {
+      if (r.total > 0) { memcpy(tp.rag, r.rag, sizeof(unsigned short) * r.total); tp.total_tiles = r.total; tp.ragged = 1; }
+      return;
+    }
+  plan_ragged_build(tp, pairs);
+  RagPlan r; r.S = S; r.U = U; r.pairs = pairs; r.total = tp.ragged ? tp.total_tiles : 0;
+  if (tp.ragged) memcpy(r.rag, tp.rag, sizeof(unsigned short) * r.total);
+  g_rag_plans.push_back(r);
+}
+void plan_ragged_build(TcParams& tp, int pairs) {
+  const int S = tp.m_tiles, U = tp.N / 64;
+  const int tmin = (U + 3) / 4, tmax = U / 2;
+  const int regular = S * tmin;
+  const int waves = (regular + pairs - 1) / pairs;
+  int target = waves * pairs;
+  if (target > S * tmax) target = S * tmax;
+  if (target <= regular || target > kMaxRagTiles || U < 3) return;
+  // tiles per strip: tmin everywhere, the extra ones spread over the strips (first strips get one more)
+  std::vector<int> tcount(S, tmin);
+  for (int extra = target - regular, i = 0; extra > 0; --extra, i = (i + 1) % S) {
+    if (tcount[i] >= tmax) { bool any = false; for (int j = 0; j < S; ++j) any |= tcount[j] < tmax; if (!any) break; ++extra; continue; }
+    ++tcount[i];
+  }
+  struct T { int strip, unit0, w; };
+  std::vector<T> tiles;
+  for (int sidx = 0; sidx < S; ++sidx) {
+    const int t = tcount[sidx], base = U / t, rem = U % t;
+    int u0 = 0;
+    for (int j = 0; j < t; ++j) { const int w = base + (j < rem ? 1 : 0); tiles.push_back({sidx, u0, w}); u0 += w; }
+  }
+  const int n = (int)tiles.size();
+  if (n > kMaxRagTiles) return;
+  std::stable_sort(tiles.begin(), tiles.end(), [](const T& a, const T& b) { return a.w > b.w; });   // widest first, strip order kept inside a width
+  // slot k * pairs + p belongs to pair p; odd rounds run backwards so that a pair that got a wide tile gets a narrow one next
+  std::vector<int> load(pairs, 0);
+  std::vector<T> slot((size_t)waves * pairs, T{-1, 0, 0});
+  for (int i = 0; i < n; ++i) {
+    const int k = i / pairs, j = i % pairs;
+    const int pr = (k & 1) ? pairs - 1 - j : j;
+    slot[(size_t)k * pairs + pr] = tiles[i];
+    load[pr] += tiles[i].w;
+  }
+  int worst = 0;
+  for (int pr = 0; pr < pairs; ++pr) worst = load[pr] > worst ? load[pr] : worst;
+  if (worst >= waves * 4) return;                      // no better than the regular tiling
+  // the kernel walks tile = pair, pair + pairs, ... < total_tiles: the table must have no holes before its end
+  int total = 0;
+  for (size_t i = 0; i < slot.size(); ++i) if (slot[i].strip >= 0) total = (int)i + 1;
+  for (int i = 0; i < total; ++i) if (slot[i].strip < 0) return;
+  for (int i = 0; i < total; ++i) tp.rag[i] = (unsigned short)(slot[i].strip | (slot[i].unit0 << 6) | ((slot[i].w - 1) << 12));
+  tp.total_tiles = total;
+  tp.ragged = 1;
+}
+}  // namespace
 
 int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   NDT1_TRY(gemm_tc_init());
@@ -882,6 +1006,11 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   tp.total_tiles = tp.m_tiles * tp.n_tiles * (p.mode == GEMM_TN ? tp.split_k : p.nb_out);
   tp.epi = p.epi;
   tp.dbg = g_gemm_dbg;
+  tp.ragged = 0;
+  static const bool no_ragged = getenv("NDT1_GEMM_RAGGED") && getenv("NDT1_GEMM_RAGGED")[0] == '0';
+  if (!no_ragged && p.mode != GEMM_TN && bn == 256 && ctas == 2 && p.nb_out == 1 && !p.b_sel && !p.epi.sel && p.N % 64 == 0 &&
+      tp.m_tiles <= 64 && p.N / 64 <= 64)
+    plan_ragged(tp, units);
 
   CUtensorMap ma, mb;
   if (p.mode == GEMM_TN) {
