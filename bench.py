@@ -386,11 +386,23 @@ def run_ours(args):
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     state = {"i": 0, "loss": 0.0}
 
+    copy_t0 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]     # how long the copies take INSIDE the loop (next to the
+    copy_t1 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]     # step's kernels and collectives), read one use later
+    copy_ms = []
+
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])
+            if copy_t1[slot].query() and state["i"] > 2:
+                copy_ms.append(copy_t0[slot].elapsed_time(copy_t1[slot]))
+            copy_t0[slot].record(copy_stream)
             for k, v in host.items():
-                bufs[slot][k].copy_(v, non_blocking=True)
+                if args.e2e_copy_frac < 1.0 and k == "spikes":   # diagnosis only (invalid as a result): is the loop bound by the BYTES copied?
+                    nb = max(1, int(v.shape[0] * args.e2e_copy_frac))
+                    bufs[slot][k][:nb].copy_(v[:nb], non_blocking=True)
+                else:
+                    bufs[slot][k].copy_(v, non_blocking=True)
+            copy_t1[slot].record(copy_stream)
             ready[slot].record(copy_stream)
 
     for e in consumed:
@@ -430,8 +442,10 @@ def run_ours(args):
     for _ in range(6):                                       # (both input buffer sets: seen once, captured, replayed)
         step_e2e()
     drain_e2e()
+    copy_ms.clear()
     ms_e2e = timed(step_e2e, args.steps, after=drain_e2e) / args.steps
     e2e_value = world * B / (ms_e2e * 1e-3)
+    h2d_in_loop = float(sorted(copy_ms)[len(copy_ms) // 2]) if copy_ms else None
     e2e_diag = None
     if args.e2e_diagnose:
         e2e_diag = {}
@@ -547,8 +561,9 @@ def run_ours(args):
                        "cuda_graph": bool(trainer.use_graph)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "trials/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "h2d_ms_per_step_alone": h2d_ms, "h2d_gbs_per_gpu_alone": h2d_bytes / (h2d_ms * 1e-3) / 1e9,
-                    "numa_bound_cores": None if numa_cpus is None else len(numa_cpus), "diagnose": e2e_diag},
+                    "h2d_ms_per_step_in_loop": h2d_in_loop, "h2d_ms_per_step_alone": h2d_ms, "h2d_gbs_per_gpu_alone": h2d_bytes / (h2d_ms * 1e-3) / 1e9,
+                    "numa_bound_cores": None if numa_cpus is None else len(numa_cpus), "diagnose": e2e_diag,
+                    **({"INVALID_copy_frac": args.e2e_copy_frac} if args.e2e_copy_frac < 1.0 else {})},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_more": more,
@@ -573,6 +588,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager steps (no whole-step CUDA graph)")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin the ranks to their GPU's NUMA node")
     ap.add_argument("--prefetch-after", action="store_true", help="e2e: submit the next step's H2D copies after this step's work instead of before")
+    ap.add_argument("--e2e-copy-frac", type=float, default=1.0, help="diagnosis only: copy this fraction of the spikes per step (the result is then not a valid e2e number)")
     ap.add_argument("--e2e-diagnose", action="store_true", help="also time the end-to-end loop without its H2D copies / without its per-step loss read")
     args = ap.parse_args()
     if args.impl == "reference":
