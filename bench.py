@@ -326,6 +326,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")       # (see llm_bci_b200/trainer.py: NVLS all-reduce serialises with the input copies)
         dist.init_process_group("nccl", device_id=dev)
     L = _C.lib()
 
@@ -563,6 +564,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "trials/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "h2d_ms_per_step_in_loop": h2d_in_loop, "h2d_ms_per_step_alone": h2d_ms, "h2d_gbs_per_gpu_alone": h2d_bytes / (h2d_ms * 1e-3) / 1e9,
                     "numa_bound_cores": None if numa_cpus is None else len(numa_cpus), "diagnose": e2e_diag,
+                    "nccl_nvls": os.environ.get("NCCL_NVLS_ENABLE") if world > 1 else None,
                     **({"INVALID_copy_frac": args.e2e_copy_frac} if args.e2e_copy_frac < 1.0 else {})},
             "gpu_launches": int(launches),
             "roofline": roofline,

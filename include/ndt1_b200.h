@@ -105,6 +105,16 @@ int ndt1_recon_loss(const float* pred, const float* target, float* dpred, const 
 int ndt1_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int64_t rows,
                        int H, float eps, void* stream);
 
+/* Backward of ndt1_layernorm_fwd (nn.LayerNorm under autograd; the post-LN layers of models/itransformer.py:157-173 and the
+ * LayerNorms of its embedders :108-150):  dx (rows,H) += dLN/dx(dy),  dgamma[H] += sum_r dy * xhat,  dbeta[H] += sum_r dy.
+ * All three accumulate: zero-fill them for plain gradients, or pre-load dx with the gradient of a residual branch. */
+int ndt1_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, float* dx, float* dgamma,
+                       float* dbeta, int64_t rows, int H, void* stream);
+
+/* nn.Dropout in place with the library's Philox streams: x[i] *= keep(seed, site, i) / (1 - p).  The same call on the gradient
+ * is its backward. */
+int ndt1_dropout_inplace(float* x, int64_t n, float p, uint64_t seed, uint64_t site, void* stream);
+
 /* y = act(x W^T + b) in fp32 (CUDA cores) or bf16 tensor cores (tcgen05); x (M,K), W (N,K).
  * Replaces the nn.Linear calls of models/ndt1.py:130,140,219-221,247-257,494. */
 int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* pre /* optional: x W^T + b before act */,
@@ -135,6 +145,13 @@ size_t ndt1_attention_workspace_bytes(int B, int L, int n_heads);
 int ndt1_attention_bf16(const void* qkv, void* out, void* out_drop, float* lse, const int64_t* key_valid, int B, int L, int H, int n_heads,
                         int context_forward, int context_backward, float p_attn, float p_out, uint64_t seed, uint64_t site_attn,
                         uint64_t site_out, const void* dout, void* dqkv, float* delta_ws, int use_tensor_cores, void* stream);
+/* The same operator in fp32 on CUDA cores (head sizes 16 / 32 / 64 / 96 / 128, any length; context -2 / -2 = no band, i.e. the
+ * unmasked attention of nn.TransformerEncoderLayer, models/itransformer.py:157-173).  Without dout: the forward (out, out_drop,
+ * lse).  With dout: the backward ALONE (dqkv from the forward's qkv / out / lse; delta_ws: B * n_heads * L floats). */
+int ndt1_attention_f32(const float* qkv, float* out, float* out_drop, float* lse, const int64_t* key_valid, int B, int L, int H, int n_heads,
+                       int context_forward, int context_backward, float p_attn, float p_out, uint64_t seed, uint64_t site_attn,
+                       uint64_t site_out, const float* dout, float* dqkv, float* delta_ws, void* stream);
+
 
 /* torch.optim.AdamW step on one flat buffer, models/trainer.py:229,340. */
 int ndt1_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,

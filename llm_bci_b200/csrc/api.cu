@@ -309,6 +309,36 @@ int ndt1_attention_bf16(const void* qkv, void* out, void* out_drop, float* lse, 
   return 0;
 }
 
+int ndt1_attention_f32(const float* qkv, float* out, float* out_drop, float* lse, const int64_t* key_valid, int B, int L, int H, int n_heads,
+                       int context_forward, int context_backward, float p_attn, float p_out, uint64_t seed, uint64_t site_attn,
+                       uint64_t site_out, const float* dout, float* dqkv, float* delta_ws, void* stream) {
+  AttnParams ap;
+  ap.qkv = qkv; ap.out = out; ap.out_drop = out_drop ? out_drop : out; ap.lse = lse; ap.key_valid = (const long long*)key_valid;
+  ap.B = B; ap.L = L; ap.H = H; ap.nh = n_heads; ap.hd = H / n_heads;
+  const int unb = 1 << 29;
+  if (context_forward == -2 && context_backward == -2) { ap.ctx_fwd = unb; ap.ctx_bwd = unb; }
+  else { ap.ctx_fwd = context_forward >= -1 ? context_forward : unb; ap.ctx_bwd = context_backward >= -1 ? context_backward : unb; }
+  ap.scale = 1.0f / sqrtf((float)ap.hd); ap.p_attn = p_attn; ap.p_out = p_out; ap.seed = seed; ap.stream_attn = site_attn; ap.stream_out = site_out;
+  ap.dout = dout; ap.dqkv = dqkv; ap.delta = delta_ws;
+  ap.drop_bits = nullptr; ap.drop_bits_o = nullptr; ap.bits_ready = 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!dout) return k_attention_fwd<float>(ap, s);
+  NDT1_REQUIRE(dqkv && delta_ws, "attention_f32: backward needs dqkv and delta_ws");
+  return k_attention_bwd<float>(ap, s);        // (the backward alone: out / lse are the forward's, nothing is recomputed into them)
+}
+
+int ndt1_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, float* dx, float* dgamma,
+                       float* dbeta, int64_t rows, int H, void* stream) {
+  NDT1_REQUIRE(dy && x && gamma && mean && rstd && dx, "layernorm_bwd: null argument");
+  return k_layernorm_bwd<float>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, nullptr, 0.f, SeedRef(), 0ull, rows, H, nullptr, (cudaStream_t)stream);
+}
+
+int ndt1_dropout_inplace(float* x, int64_t n, float p, uint64_t seed, uint64_t site, void* stream) {
+  NDT1_REQUIRE(p >= 0.f && p < 1.f, "dropout: p must be in [0,1)");
+  if (n == 0 || p == 0.f) return 0;
+  return k_dropout_inplace<float>(x, n, p, SeedRef(seed), site, (cudaStream_t)stream);
+}
+
 int ndt1_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int step, float grad_scale, void* stream) {
   return k_adamw(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream);

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_q_kernel(const AttnParams
 }
 
 int check(const AttnParams& p) {
-  NDT1_REQUIRE(p.hd == 16 || p.hd == 32 || p.hd == 64 || p.hd == 128, "attention: head size %d unsupported (16, 32, 64 or 128)", p.hd);
+  NDT1_REQUIRE(p.hd == 16 || p.hd == 32 || p.hd == 64 || p.hd == 96 || p.hd == 128, "attention: head size %d unsupported (16, 32, 64, 96 or 128)", p.hd);
   NDT1_REQUIRE(p.nh * p.hd == p.H, "attention: hidden %d != heads %d x head size %d", p.H, p.nh, p.hd);
   return 0;
 }
@@ -294,7 +294,7 @@ int k_attention_fwd(const AttnParams& p, cudaStream_t stream) {
     NDT1_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
     ndt1_launch(attn_fwd_kernel<T, D>, grid, AT_THREADS, smem, stream, p);                                                                \
   }
-  switch (p.hd) { case 16: NDT1_ATT_FWD(4) break; case 32: NDT1_ATT_FWD(8) break; case 64: NDT1_ATT_FWD(16) break; default: NDT1_ATT_FWD(32) }
+  switch (p.hd) { case 16: NDT1_ATT_FWD(4) break; case 32: NDT1_ATT_FWD(8) break; case 64: NDT1_ATT_FWD(16) break; case 96: NDT1_ATT_FWD(24) break; default: NDT1_ATT_FWD(32) }
 #undef NDT1_ATT_FWD
   NDT1_CHECK_LAUNCH();
   return 0;
@@ -317,7 +317,7 @@ int k_attention_bwd(const AttnParams& p, cudaStream_t stream) {
     ndt1_launch(attn_bwd_kv_kernel<T, D>, grid, AT_THREADS, smem_kv, stream, p);                                                          \
     ndt1_launch(attn_bwd_q_kernel<T, D>, grid, AT_THREADS, smem_q, stream, p);                                                            \
   }
-  switch (p.hd) { case 16: NDT1_ATT_BWD(4) break; case 32: NDT1_ATT_BWD(8) break; case 64: NDT1_ATT_BWD(16) break; default: NDT1_ATT_BWD(32) }
+  switch (p.hd) { case 16: NDT1_ATT_BWD(4) break; case 32: NDT1_ATT_BWD(8) break; case 64: NDT1_ATT_BWD(16) break; case 96: NDT1_ATT_BWD(24) break; default: NDT1_ATT_BWD(32) }
 #undef NDT1_ATT_BWD
   NDT1_CHECK_LAUNCH();
   return 0;

@@ -26,6 +26,13 @@ import torch.distributed as dist
 from . import _C
 from .ndt1 import NDT1
 
+# NVLS (in-switch reduction) all-reduce and a concurrent host-to-device copy serialise on an 8-GPU NVSwitch box: with the next
+# batch's 33 MB copy in flight the step takes 4.89 ms instead of 3.76 (the copy itself still takes its 1.43 ms); with NVLS off NCCL
+# reduces over the same NVLinks with its ring / tree kernels, the resident step is unchanged (68.3 k vs 68.1 k trials/s) and the
+# end-to-end step is 3.84 ms (profiles/r02_bench_8gpu_nvls_{on,off}.json).  So this package asks for NVLS off unless the caller's
+# environment says otherwise; it has to be in the environment before the NCCL communicator is created.
+os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+
 def _bci(*args, **kwargs):
     from .bci import BCI
     return BCI(*args, **kwargs)

@@ -99,6 +99,9 @@ def main():
     if "--bci" in sys.argv:
         bci_case()
         return
+    if "--itransformer" in sys.argv:
+        itransformer_cases(R)
+        return
     if "--round2" in sys.argv:            # fixtures added in round 2 (the earlier files regenerate bit-identically and are left alone)
         autocast_error_cases(R)
         ssl_full_case(R)
@@ -660,6 +663,84 @@ def full_b32_case(R):
     print("ctc_full_b32 loss", float(out.loss), "fp64", float(out_d.loss), "autocast loss rel", float(d["autocast/loss_rel"]),
           "grad l2 max", float(d["autocast/grad_l2_max"]), "argmax agree", float(d["autocast/argmax_agree"]))
 
+
+
+
+# --------------------------------------------------------------------------- iTransformer (models/itransformer.py)
+ITR_MASKER = {"active": True, "force_active": True, "mode": "neuron", "ratio": 0.25, "zero_ratio": 1.0, "random_ratio": 1.0,
+              "expand_prob": 0.0, "max_timespan": 1, "regions": None, "channels": None}
+ITR_SMALL = {"masker": {"main": ITR_MASKER},
+             "encoder": {"embedder": {"dropout": 0.0, "max_n_bins": 20}, "hidden_size": 64, "n_heads": 4, "n_layers": 2, "dropout": 0.0,
+                         "max_n_channels": 32, "embed_region": False}}
+# BASELINE.json configs[3] / SURVEY 8 f4: the shipped yaml (768 hidden, 8 heads of 96, 5 post-LN layers, FFN 3072, MLP embedder
+# 100 -> 768 -> 768, cls token) with the masker keys the yaml lacks (`active`, `regions`: SURVEY component 8) and dropout off
+ITR_FULL = {"masker": {"main": dict(ITR_MASKER, ratio=0.1)},
+            "encoder": {"embedder": {"dropout": 0.0}, "dropout": 0.0, "embed_region": False}}
+
+
+def itr_batch(B, T, N, seed, rate=0.3):
+    g = torch.Generator().manual_seed(seed)
+    sp = torch.poisson(torch.full((B, T, N), rate), generator=g)
+    return dict(spikes=sp, spikes_mask=torch.ones(B, T, dtype=torch.int64), spikes_timestamp=torch.arange(T)[None].expand(B, T).contiguous())
+
+
+def itransformer_cases(R):
+    """Outputs of the unmodified reference iTransformer (mlm method, Poisson-NLL on log rates, MLP embedder, channel embeddings,
+    cls token) in train mode with dropout 0: a small case with every gradient, and the config-3 size (16 x 100 bins x 669 neurons)
+    with per-parameter norms, a gradient subset and the reference's own bf16-autocast error."""
+    from models.itransformer import iTransformer
+    uc = R["update_config"]
+    # ---- small
+    cfg = uc("configs/itransformer.yaml", ITR_SMALL)
+    torch.manual_seed(1)
+    m = iTransformer(cfg, method_name="mlm", loss="poisson_nll", log_input=True)
+    b = itr_batch(3, 20, 24, 3)
+    out, grads = run_ref(m, b, train=True, seed=5)
+    d = {"names": np.array([n for n, _ in m.named_parameters()])}
+    d.update(flat("param", dict(m.named_parameters())))
+    d.update(flat("grad", grads))
+    d.update(flat("batch", b))
+    d.update({"out/loss": out.loss.detach().numpy(), "out/n_examples": out.n_examples.numpy(), "out/preds": out.preds.detach().numpy(),
+              "out/mask": out.mask.numpy().astype(np.uint8), "seed": np.array(5)})
+    # second method with the same weights: dyn_behaviour (cls token -> MLP decoder -> one value per bin, MSE over valid bins)
+    torch.manual_seed(1)
+    m2 = iTransformer(cfg, method_name="dyn_behaviour")
+    b2 = dict(b, targets=torch.randn(3, 20, generator=torch.Generator().manual_seed(9)))
+    b2["spikes_mask"] = (torch.arange(20)[None] < torch.tensor([20, 14, 17])[:, None]).to(torch.int64)
+    out2, grads2 = run_ref(m2, b2, train=True, seed=5)
+    d.update(flat("dyn/param", dict(m2.named_parameters())))
+    d.update(flat("dyn/grad", grads2))
+    d.update({"dyn/targets": b2["targets"].numpy(), "dyn/spikes_mask": b2["spikes_mask"].numpy(), "dyn/loss": out2.loss.detach().numpy(),
+              "dyn/n_examples": out2.n_examples.numpy(), "dyn/preds": out2.preds.detach().numpy()})
+    np.savez_compressed(os.path.join(HERE, "itransformer_small.npz"), **d)
+    print("itransformer_small loss", float(out.loss), "n", int(out.n_examples), "dyn loss", float(out2.loss))
+    # ---- config 3 size
+    cfg = uc("configs/itransformer.yaml", ITR_FULL)
+    torch.manual_seed(1)
+    m = iTransformer(cfg, method_name="mlm", loss="poisson_nll", log_input=True)
+    b = itr_batch(16, 100, 669, 1, rate=0.1)
+    out, grads = run_ref(m, b, train=True, seed=77)
+    names = [n for n, _ in m.named_parameters()]
+    d = {"names": np.array(names), "seed": np.array(77), "out/loss": out.loss.detach().numpy(), "out/n_examples": out.n_examples.numpy(),
+         "out/mask_bn": out.mask[:, 0, :].numpy().astype(np.uint8), "out/preds_rows": out.preds.detach().numpy()[:, ::10, ::8],
+         "out/preds_sum": out.preds.detach().double().sum().numpy()}
+    assert bool((out.mask == out.mask[:, :1, :]).all())     # neuron mode: the mask is constant over time
+    d["param_sum"] = np.array([float(p.detach().double().sum()) for p in m.parameters()])
+    d["grad_norm"] = np.array([float(grads[n].double().norm()) for n in names])
+    d["grad_absmax"] = np.array([float(grads[n].abs().max()) for n in names])
+    for n in names:
+        if grads[n].numel() <= 4096:
+            d[f"grad/{n}"] = grads[n].numpy()
+        else:
+            d[f"grad_slice/{n}"] = grads[n][:8].numpy()
+    out16, g16 = run_ref_autocast_seeded(m, b, 77)
+    l2, mx = grad_error_metrics(g16, grads)
+    d["autocast/loss_rel"] = np.array(abs(float(out16.loss) - float(out.loss)) / abs(float(out.loss)))
+    d["autocast/grad_l2_max"] = np.array(max(l2.values()))
+    d["autocast/grad_maxabs_max"] = np.array(max(mx.values()))
+    np.savez_compressed(os.path.join(HERE, "itransformer_config3.npz"), **d)
+    print("itransformer_config3 loss", float(out.loss), "n", int(out.n_examples), "autocast loss rel", float(d["autocast/loss_rel"]),
+          "grad l2 max", float(d["autocast/grad_l2_max"]))
 
 if __name__ == "__main__":
     main()

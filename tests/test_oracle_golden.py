@@ -402,3 +402,82 @@ def test_bci_coupler_oracle_matches_reference(name):
     for k, v in ref.items():
         got = params[k].grad.numpy() if params[k].grad is not None else np.zeros_like(v)
         assert np.abs(got - v).max() <= 5e-5 * max(np.abs(v).max(), 1e-3 * gscale), k
+
+
+# --------------------------------------------------------------------------- iTransformer
+from oracle import itransformer_oracle as IO  # noqa: E402
+
+ITR_SMALL = {"masker": {"main": {"ratio": 0.25}},
+             "encoder": {"embedder": {"dropout": 0.0, "max_n_bins": 20}, "hidden_size": 64, "n_heads": 4, "n_layers": 2, "dropout": 0.0,
+                         "max_n_channels": 32, "embed_region": False}}
+ITR_FULL = {"masker": {"main": {"ratio": 0.1}}, "encoder": {"embedder": {"dropout": 0.0}, "dropout": 0.0, "embed_region": False}}
+ITR_KW = dict(method_name="mlm", loss="poisson_nll", log_input=True)
+
+
+def itr_cfg(over):
+    return update_config("configs/itransformer.yaml", over)
+
+
+def itr_batch(B, T, N, seed, rate=0.3):
+    g = torch.Generator().manual_seed(seed)
+    sp = torch.poisson(torch.full((B, T, N), rate), generator=g)
+    return dict(spikes=sp, spikes_mask=torch.ones(B, T, dtype=torch.int64), spikes_timestamp=torch.arange(T)[None].expand(B, T).contiguous())
+
+
+def itr_oracle_grads(params, cfg, kw, batch, mask):
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    masked = {"spikes": batch["spikes"] * (1 - mask).to(batch["spikes"].dtype), "mask": mask}      # zero_ratio = 1: masked = zeroed
+    loss, n, preds, m = IO.itransformer_forward(p, cfg, kw, batch, masked=masked)
+    loss.backward()
+    return loss.detach(), n, preds.detach(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
+
+
+def test_itransformer_small_oracle_matches_reference():
+    g = load("itransformer_small.npz")
+    cfg = itr_cfg(ITR_SMALL)
+    params = {k: torch.from_numpy(v) for k, v in sub(g, "param").items()}
+    batch = {k: torch.from_numpy(v) for k, v in sub(g, "batch").items()}
+    mask = torch.from_numpy(g["out/mask"].astype(np.int64))
+    loss, n, preds, grads = itr_oracle_grads(params, cfg, ITR_KW, batch, mask)
+    assert int(n) == int(g["out/n_examples"])
+    assert abs(float(loss) - float(g["out/loss"])) <= 2e-5 * abs(float(g["out/loss"]))
+    assert rel(preds.numpy(), g["out/preds"]) < 2e-5
+    gscale = max(np.abs(v).max() for v in sub(g, "grad").values())
+    for name, ref in sub(g, "grad").items():
+        assert np.abs(grads[name].numpy() - ref).max() <= 5e-5 * max(np.abs(ref).max(), 1e-3 * gscale), name
+    # dyn_behaviour: cls token -> decoder -> one value per bin, MSE over the bins that are not padding (no masker effect on the loss mask)
+    p2 = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in sub(g, "dyn/param").items()}
+    b2 = dict(batch, targets=torch.from_numpy(g["dyn/targets"]), spikes_mask=torch.from_numpy(g["dyn/spikes_mask"]))
+    masked = {"spikes": batch["spikes"] * (1 - mask).to(torch.float32), "mask": mask}              # same seed, same neuron draw
+    loss2, n2, preds2, _ = IO.itransformer_forward(p2, cfg, dict(method_name="dyn_behaviour"), b2, masked=masked)
+    loss2.backward()
+    assert int(n2) == int(g["dyn/n_examples"])
+    assert abs(float(loss2) - float(g["dyn/loss"])) <= 2e-5 * abs(float(g["dyn/loss"]))
+    assert rel(preds2.detach().numpy(), g["dyn/preds"]) < 2e-5
+    gs2 = max(np.abs(v).max() for v in sub(g, "dyn/grad").values())
+    for name, ref in sub(g, "dyn/grad").items():
+        got = p2[name].grad.numpy() if p2[name].grad is not None else np.zeros_like(ref)
+        assert np.abs(got - ref).max() <= 5e-5 * max(np.abs(ref).max(), 1e-3 * gs2), name
+
+
+def test_itransformer_config3_oracle_matches_reference():
+    """BASELINE.json configs[3] size (16 x 100 bins x 669 neurons, 768 hidden, 8 heads of 96, 5 post-LN layers): oracle vs the
+    unmodified reference; the parameters are re-created from the same torch seed by this package's container (same init draws)."""
+    from llm_bci_b200.itransformer import iTransformer
+    g = load("itransformer_config3.npz")
+    torch.manual_seed(1)
+    shell = iTransformer(ITR_FULL, precision="fp32", **ITR_KW)
+    names = [n for n, _ in shell.named_parameters()]
+    assert names == list(g["names"])
+    assert np.allclose([float(p.detach().double().sum()) for p in shell.parameters()], g["param_sum"], rtol=1e-11, atol=1e-11)
+    params = {k: v.detach().clone() for k, v in shell.named_parameters()}
+    batch = itr_batch(16, 100, 669, 1, rate=0.1)
+    mask = torch.from_numpy(g["out/mask_bn"].astype(np.int64))[:, None, :].expand(16, 100, 669).contiguous()
+    loss, n, preds, grads = itr_oracle_grads(params, itr_cfg(ITR_FULL), ITR_KW, batch, mask)
+    assert int(n) == int(g["out/n_examples"])
+    assert abs(float(loss) - float(g["out/loss"])) <= 2e-5 * abs(float(g["out/loss"]))
+    assert np.abs(preds.numpy()[:, ::10, ::8] - g["out/preds_rows"]).max() <= 2e-4
+    # (per-tensor norms agree to 1e-4; single elements of the bias gradients -- sums over 10 720 token rows in fp32, in another
+    # order than torch's fused multi-head attention takes -- to 1e-3 of the tensor's largest element)
+    worst = check_full_fixture(g, grads, names, 3.4e-4)
+    assert worst <= 1e-4, worst
