@@ -1,7 +1,7 @@
 """B200-native implementation of the NDT1 hot path of colehurwitz/llm_bci.
 
 Public surface (mirrors the reference's plugin API for this path):
-  NAME2MODEL["NDT1"], NDT1, NDT1Output, ModelOutput, Masker,
+  NAME2MODEL["NDT1"] / ["BCI"] / ["iTransformer"], NDT1, NDT1Output, BCI, iTransformer, ModelOutput, Masker,
   pad_collate_fn / padded_array (host semantics) and DevicePadCollate,
   DictConfig / update_config, format_ctc / greedy_ctc_decode / phoneme_error_rate.
 """
@@ -12,4 +12,5 @@ from .ndt1 import NDT1, NDT1Output, create_context_mask  # noqa: F401
 from .collate import pad_collate_fn, padded_array, DevicePadCollate  # noqa: F401
 from .decode import format_ctc, greedy_ctc_decode, ctc_error_counts, phoneme_error_rate  # noqa: F401
 from .bci import BCI, BCIOutput  # noqa: F401
+from .itransformer import iTransformer, iTransformerOutput  # noqa: F401
 from .trainer import NAME2MODEL, DataParallelTrainer  # noqa: F401

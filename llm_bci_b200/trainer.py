@@ -38,7 +38,12 @@ def _bci(*args, **kwargs):
     return BCI(*args, **kwargs)
 
 
-NAME2MODEL = {"NDT1": NDT1, "BCI": _bci}     # (models/trainer.py:36; iTransformer / PatchTST are other model families)
+def _itransformer(*args, **kwargs):
+    from .itransformer import iTransformer
+    return iTransformer(*args, **kwargs)
+
+
+NAME2MODEL = {"NDT1": NDT1, "BCI": _bci, "iTransformer": _itransformer}     # (models/trainer.py:36; PatchTST: DESIGN.md section 7)
 
 
 def get_model_inputs(model) -> List[str]:

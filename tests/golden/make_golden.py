@@ -702,6 +702,12 @@ def itransformer_cases(R):
     d.update(flat("batch", b))
     d.update({"out/loss": out.loss.detach().numpy(), "out/n_examples": out.n_examples.numpy(), "out/preds": out.preds.detach().numpy(),
               "out/mask": out.mask.numpy().astype(np.uint8), "seed": np.array(5)})
+    # the reference's own bf16-autocast error on this case, per tensor (the yardstick for the bf16 CUDA mode on a 64-wide model)
+    out16, g16 = run_ref_autocast_seeded(m, b, 5)
+    l2, mx = grad_error_metrics(g16, grads)
+    d["autocast/loss_rel"] = np.array(abs(float(out16.loss) - float(out.loss)) / abs(float(out.loss)))
+    d["autocast/grad_l2_max"] = np.array(max(l2.values()))
+    d["autocast/grad_l2_worst"] = np.array(max(l2, key=l2.get))
     # second method with the same weights: dyn_behaviour (cls token -> MLP decoder -> one value per bin, MSE over valid bins)
     torch.manual_seed(1)
     m2 = iTransformer(cfg, method_name="dyn_behaviour")
