@@ -105,6 +105,19 @@ int ndt1_recon_loss(const float* pred, const float* target, float* dpred, const 
 int ndt1_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int64_t rows,
                        int H, float eps, void* stream);
 
+/* The unmasked attention of nn.TransformerEncoderLayer (models/itransformer.py:157-173) for sequences beyond the fused kernels'
+ * 256 tokens, on the tcgen05 GEMM: batched S = Q K^T, row softmax (+ dropout on the probabilities, the same Philox stream as
+ * ndt1_attention_f32), O = P V, and the five products of the backward; the L x L probabilities are kept in bf16.
+ * qkv (B*L, 3H) fp32 packed q | k | v -> out (B*L, H) fp32;  dout -> dqkv (B*L, 3H).  Head size a multiple of 8.
+ * `saved` (ndt1_attention_mm_saved_bytes) carries the forward's operands and probabilities to the backward;
+ * `workspace` (ndt1_attention_mm_workspace_bytes) is scratch of one call.  Both 256-byte aligned. */
+size_t ndt1_attention_mm_saved_bytes(int B, int L, int H, int n_heads, float p_attn);
+size_t ndt1_attention_mm_workspace_bytes(int B, int L, int H, int n_heads);
+int ndt1_attention_mm_fwd(const float* qkv, float* out, void* saved, void* workspace, int B, int L, int H, int n_heads, float p_attn,
+                          uint64_t seed, uint64_t site_attn, void* stream);
+int ndt1_attention_mm_bwd(const float* dout, void* saved, void* workspace, float* dqkv, int B, int L, int H, int n_heads, float p_attn,
+                          uint64_t seed, uint64_t site_attn, void* stream);
+
 /* Backward of ndt1_layernorm_fwd (nn.LayerNorm under autograd; the post-LN layers of models/itransformer.py:157-173 and the
  * LayerNorms of its embedders :108-150):  dx (rows,H) += dLN/dx(dy),  dgamma[H] += sum_r dy * xhat,  dbeta[H] += sum_r dy.
  * All three accumulate: zero-fill them for plain gradients, or pre-load dx with the gradient of a residual branch. */

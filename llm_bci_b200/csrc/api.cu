@@ -327,6 +327,19 @@ int ndt1_attention_f32(const float* qkv, float* out, float* out_drop, float* lse
   return k_attention_bwd<float>(ap, s);        // (the backward alone: out / lse are the forward's, nothing is recomputed into them)
 }
 
+size_t ndt1_attention_mm_saved_bytes(int B, int L, int H, int n_heads, float p_attn) { return k_attention_mm_saved_bytes(B, L, H, n_heads, p_attn); }
+size_t ndt1_attention_mm_workspace_bytes(int B, int L, int H, int n_heads) { return k_attention_mm_workspace_bytes(B, L, H, n_heads); }
+int ndt1_attention_mm_fwd(const float* qkv, float* out, void* saved, void* workspace, int B, int L, int H, int n_heads, float p_attn,
+                          uint64_t seed, uint64_t site_attn, void* stream) {
+  NDT1_REQUIRE(qkv && out && saved && workspace, "attention_mm_fwd: null argument");
+  return k_attention_mm_fwd(qkv, out, saved, workspace, B, L, H, n_heads, p_attn, SeedRef(seed), site_attn, (cudaStream_t)stream);
+}
+int ndt1_attention_mm_bwd(const float* dout, void* saved, void* workspace, float* dqkv, int B, int L, int H, int n_heads, float p_attn,
+                          uint64_t seed, uint64_t site_attn, void* stream) {
+  NDT1_REQUIRE(dout && dqkv && saved && workspace, "attention_mm_bwd: null argument");
+  return k_attention_mm_bwd(dout, saved, workspace, dqkv, B, L, H, n_heads, p_attn, SeedRef(seed), site_attn, (cudaStream_t)stream);
+}
+
 int ndt1_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, float* dx, float* dgamma,
                        float* dbeta, int64_t rows, int H, void* stream) {
   NDT1_REQUIRE(dy && x && gamma && mean && rstd && dx, "layernorm_bwd: null argument");

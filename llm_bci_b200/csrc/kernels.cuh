@@ -90,6 +90,13 @@ struct AttnParams {
 template <typename T> int k_attention_fwd(const AttnParams& p, cudaStream_t stream);
 template <typename T> int k_attention_bwd(const AttnParams& p, cudaStream_t stream);
 template <typename T> int k_attention_delta(const AttnParams& p, cudaStream_t stream);
+// attention_mm.cu: unmasked attention over long sequences as batched tcgen05 GEMMs (probabilities materialised in bf16)
+size_t k_attention_mm_saved_bytes(int B, int L, int H, int nh, float p_attn);
+size_t k_attention_mm_workspace_bytes(int B, int L, int H, int nh);
+int k_attention_mm_fwd(const float* qkv, float* out, void* saved, void* workspace, int B, int L, int H, int nh, float p_attn, SeedRef seed,
+                       unsigned long long site, cudaStream_t stream);
+int k_attention_mm_bwd(const float* dout, void* saved, void* workspace, float* dqkv, int B, int L, int H, int nh, float p_attn, SeedRef seed,
+                       unsigned long long site, cudaStream_t stream);
 // attention_tc.cu (tcgen05 path: bf16, head size 128, at most 256 tokens)
 bool k_attention_tc_supported(const AttnParams& p);
 int k_attention_tc_fwd(const AttnParams& p, cudaStream_t stream);

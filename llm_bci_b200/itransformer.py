@@ -12,8 +12,9 @@ What computes (this library's sm_100a kernels through the C ABI; GPU only, no fa
   * every Linear, forward and backward, with bias / activation / activation derivative fused (``ndt1_linear_fwd`` / ``_bwd``:
     tcgen05 GEMMs in the bf16 mode, CUDA-core fp32 in the strict mode),
   * every LayerNorm, forward and backward (``ndt1_layernorm_fwd`` / ``ndt1_layernorm_bwd``) -- the layers are POST-LN,
-  * the unmasked multi-head attention over the [cls +] neuron tokens, forward and backward, with dropout on the probabilities
-    (``ndt1_attention_f32``: head size 96 at the shipped 768 / 8, 670 tokens),
+  * the unmasked multi-head attention over the [cls +] neuron tokens (670 of them, heads of 96, at the shipped size), forward and
+    backward, with dropout on the probabilities: batched tcgen05 GEMMs with the probabilities in bf16 in the bf16 mode
+    (``ndt1_attention_mm_fwd`` / ``_bwd``), fused CUDA-core fp32 kernels in the strict mode (``ndt1_attention_f32``),
   * every nn.Dropout (``ndt1_dropout_inplace``, the library's Philox streams keyed per forward),
   * the maskers (``llm_bci_b200.Masker``), the masked Poisson-NLL / MSE loss and its gradient (``ndt1_recon_loss``).
 Left to torch tensor ops (data movement, no arithmetic kernels of this library exist for them): the (B, T, N) -> (B, N, T)
@@ -132,6 +133,52 @@ class _Attention(torch.autograd.Function):
                                              p, 0.0, seed, site, 0, dout.data_ptr(), dqkv.data_ptr(), delta.data_ptr(), _C.stream_ptr()),
                  "ndt1_attention_f32 (backward)")
         return dqkv, None, None, None, None, None, None
+
+
+class _AttentionMM(torch.autograd.Function):
+    """The same operator on the tcgen05 GEMM (``ndt1_attention_mm_fwd`` / ``_bwd``): batched Q K^T, row softmax + dropout, P V
+    and the five products of the backward, probabilities kept in bf16.  The bf16 mode's attention: 670 tokens with heads of 96
+    are beyond the fused tensor-core kernels (256 tokens, head 128) and cost 12 ms per layer on the CUDA-core ones."""
+
+    @staticmethod
+    def forward(ctx, qkv, B: int, L: int, n_heads: int, p: float, seed: int, site: int):
+        _need_cuda(qkv)
+        qkv = qkv.contiguous().float()
+        H = qkv.shape[1] // 3
+        lib = _C.lib()
+        out = torch.empty(B * L, H, dtype=torch.float32, device=qkv.device)
+        saved = torch.empty(int(lib.ndt1_attention_mm_saved_bytes(B, L, H, n_heads, float(p))), dtype=torch.uint8, device=qkv.device)
+        ws = _mm_workspace(int(lib.ndt1_attention_mm_workspace_bytes(B, L, H, n_heads)), qkv.device)
+        _C.check(lib.ndt1_attention_mm_fwd(qkv.data_ptr(), out.data_ptr(), saved.data_ptr(), ws.data_ptr(), B, L, H, n_heads, float(p), seed, site,
+                                           _C.stream_ptr()), "ndt1_attention_mm_fwd")
+        ctx.save_for_backward(saved)
+        ctx.dims = (B, L, H, n_heads, float(p), seed, site)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (saved,) = ctx.saved_tensors
+        B, L, H, n_heads, p, seed, site = ctx.dims
+        dout = dout.contiguous().float()
+        lib = _C.lib()
+        dqkv = torch.empty(B * L, 3 * H, dtype=torch.float32, device=dout.device)
+        ws = _mm_workspace(int(lib.ndt1_attention_mm_workspace_bytes(B, L, H, n_heads)), dout.device)
+        _C.check(lib.ndt1_attention_mm_bwd(dout.data_ptr(), saved.data_ptr(), ws.data_ptr(), dqkv.data_ptr(), B, L, H, n_heads, p, seed, site,
+                                           _C.stream_ptr()), "ndt1_attention_mm_bwd")
+        return dqkv, None, None, None, None, None, None
+
+
+_MM_WS = {}
+
+
+def _mm_workspace(nbytes: int, dev) -> torch.Tensor:
+    """Scratch of one attention call, shared by all layers (calls on one stream run in order); grown on demand."""
+    key = str(dev)
+    t = _MM_WS.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _MM_WS[key] = t
+    return t
 
 
 class _ReconLoss(torch.autograd.Function):
@@ -258,7 +305,8 @@ class iTransformerEncoder(nn.Module):
         for layer in self.transformer.layers:                                                 # post-LN encoder layers (:157-173)
             qkv = _LinearAct.apply(x, layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias, "identity", self.precision)
             self._site += 1
-            att = _Attention.apply(qkv, B, L, self.n_heads, self.p if self.training else 0.0, self._seed, self._site)
+            attn = _AttentionMM if self.precision == "bf16" else _Attention
+            att = attn.apply(qkv, B, L, self.n_heads, self.p if self.training else 0.0, self._seed, self._site)
             o = self._lin(att, layer.self_attn.out_proj)
             x = self._ln(x + self._drop(o, self.p), layer.norm1)
             h = self._drop(self._lin(x, layer.linear1, self.act), self.p)
