@@ -138,6 +138,17 @@ int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y,
 int ndt1_linear_bwd(const float* dy, const float* x, const float* w, const float* saved, float* dx, float* dw, float* db, int M, int N,
                     int K, int act, int precision, void* workspace, size_t workspace_bytes, void* stream);
 size_t ndt1_linear_workspace_bytes(int M, int N, int K);
+/* The same pair with nn.Dropout(p) applied to the OUTPUT inside the GEMM epilogue (y = dropout(act(x W^T + b)), the library's
+ * Philox stream (seed, site) over the flat (row, column) index -- the mask ndt1_dropout_inplace(y, ...) would apply), and, in
+ * the backward, to dy before the activation derivative.  The Linear -> activation -> Dropout runs of
+ * nn.TransformerEncoderLayer and torchvision's MLP (models/itransformer.py:108-116, 157-165) in one pass each way.
+ * `saved` for relu / softsign is the forward's (dropped) output. */
+int ndt1_linear_drop_fwd(const float* x, const float* w, const float* bias, float* y, float* pre, int M, int N, int K, int act, int precision,
+                         void* workspace, size_t workspace_bytes, float drop_p, uint64_t seed, uint64_t site, void* stream);
+int ndt1_linear_drop_bwd(const float* dy, const float* x, const float* w, const float* saved, float* dx, float* dw, float* db, int M, int N,
+                         int K, int act, int precision, void* workspace, size_t workspace_bytes, float drop_p, uint64_t seed, uint64_t site,
+                         void* stream);
+
 /* BCI.prepare_embeds, models/bci.py:143-166: out (B, La+Ls, W) = a[b, :split[b]] | ins[b] | a[b, split[b]:] per trial (or a
  * constant row `fill` instead of ins: the -100 targets over the spike positions).  elem_size 4 (float32) or 8 (int64).
  * ndt1_unsplice_rows is its backward for float32: the gradient of `out` routed back to a and ins.

@@ -84,6 +84,8 @@ PROTOTYPES = {
     "ndt1_layernorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _f, _p]),
     "ndt1_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "ndt1_linear_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "ndt1_linear_drop_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _f, _u64, _u64, _p]),
+    "ndt1_linear_drop_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _f, _u64, _u64, _p]),
     "ndt1_linear_workspace_bytes": (_sz, [_i, _i, _i]),
     "ndt1_splice_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _d, _p]),
     "ndt1_unsplice_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),

@@ -7,16 +7,48 @@ namespace {
 // g = dy * act'(saved), cast to T with a padded row stride (the operand of the data- and weight-gradient GEMMs)
 template <typename T>
 __global__ void dact_prep_kernel(const float* __restrict__ dy, const float* __restrict__ saved, T* __restrict__ out, long long rows, int cols,
-                                 int ld_out, int dact) { pdl_grid_sync();
+                                 int ld_out, int dact, float drop_p, unsigned long long seed, unsigned long long site) { pdl_grid_sync();
   const long long total = rows * ld_out;
+  const uint32_t thr = drop_threshold(drop_p);
+  const float ik = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / ld_out; const int c = (int)(i % ld_out);
     float v = 0.f;
     if (c < cols) {
-      v = dy[r * cols + c];
-      if (dact != DACT_NONE) v *= dact_apply(dact, saved[r * cols + c]);
+      const long long e = r * cols + c;
+      v = dy[e];
+      if (drop_p > 0.f) v *= drop_scale_1(seed, site, (unsigned long long)e, thr, ik);     // the forward's keep mask (output dropout)
+      if (dact != DACT_NONE) v *= dact_apply(dact, saved[e]);
     }
     out[i] = from_f32<T>(v);
+  }
+}
+// the same for cols % 8 == 0 and an unpadded bf16 operand (ld_out == cols): 8 consecutive elements per thread -- two 16-byte reads
+// per input, one Philox block (the 8 elements are exactly one block of the flat index), one 16-byte write
+__global__ void dact_prep8_kernel(const float* __restrict__ dy, const float* __restrict__ saved, bf16* __restrict__ out, long long total8, int dact,
+                                  float drop_p, unsigned long long seed, unsigned long long site) { pdl_grid_sync();
+  const uint32_t thr = drop_threshold(drop_p);
+  const float ik = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 8;
+    const float4 a = *(const float4*)(dy + e), b = *(const float4*)(dy + e + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (drop_p > 0.f) {
+      float k[8];
+      drop_scale_8(seed, site, (unsigned long long)e, thr, ik, k);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] *= k[u];
+    }
+    if (dact != DACT_NONE) {
+      const float4 c = *(const float4*)(saved + e), d = *(const float4*)(saved + e + 4);
+      const float sv[8] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] *= dact_apply(dact, sv[u]);
+    }
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 o; o.x = *(uint32_t*)&p0; o.y = *(uint32_t*)&p1; o.z = *(uint32_t*)&p2; o.w = *(uint32_t*)&p3;
+    *(uint4*)(out + e) = o;
   }
 }
 }  // namespace
@@ -157,10 +189,17 @@ size_t ndt1_linear_workspace_bytes(int M, int N, int K) {
 
 int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* pre, int M, int N, int K, int act, int precision,
                     void* workspace, size_t workspace_bytes, void* stream) {
+  return ndt1_linear_drop_fwd(x, w, bias, y, pre, M, N, K, act, precision, workspace, workspace_bytes, 0.f, 0, 0, stream);
+}
+
+int ndt1_linear_drop_fwd(const float* x, const float* w, const float* bias, float* y, float* pre, int M, int N, int K, int act, int precision,
+                         void* workspace, size_t workspace_bytes, float drop_p, uint64_t seed, uint64_t site, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (M == 0 || N == 0) return 0;
+  NDT1_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "linear_fwd: dropout p must be in [0,1)");
   GemmProblem p = plain_problem(GEMM_NT, M, N, K);
   p.epi.out = y; p.epi.ldc = N; p.epi.bias = bias; p.epi.act = act_code_of(act);
+  if (drop_p > 0.f) { p.epi.drop_p = drop_p; p.epi.drop_seed = SeedRef(seed); p.epi.drop_stream = site; }
   if (pre) { p.epi.out2 = pre; p.epi.out2_bf16 = 0; }
   if (precision == NDT1_PRECISION_FP32) {
     p.A = {x, 0, 1, M, K, K}; p.B = {w, 0, 1, N, K, K};
@@ -181,6 +220,12 @@ int ndt1_linear_fwd(const float* x, const float* w, const float* bias, float* y,
 
 int ndt1_linear_bwd(const float* dy, const float* x, const float* w, const float* saved, float* dx, float* dw, float* db, int M, int N,
                     int K, int act, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  return ndt1_linear_drop_bwd(dy, x, w, saved, dx, dw, db, M, N, K, act, precision, workspace, workspace_bytes, 0.f, 0, 0, stream);
+}
+
+int ndt1_linear_drop_bwd(const float* dy, const float* x, const float* w, const float* saved, float* dx, float* dw, float* db, int M, int N,
+                         int K, int act, int precision, void* workspace, size_t workspace_bytes, float drop_p, uint64_t seed, uint64_t site,
+                         void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (M == 0 || N == 0) return 0;
   NDT1_REQUIRE(dy && x && w, "linear_bwd: null argument");
@@ -198,7 +243,7 @@ int ndt1_linear_bwd(const float* dy, const float* x, const float* w, const float
     // ldk >= N; keep it simple and exact instead: g needs M * N floats)
     NDT1_REQUIRE(workspace_bytes >= (size_t)M * N * 4 + 256, "linear_bwd: fp32 mode needs %zu workspace bytes", (size_t)M * N * 4 + 256);
     float* g = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    ndt1_launch(dact_prep_kernel<float>, blocks, 256, 0, s, dy, saved, g, (long long)M, N, N, dact);
+    ndt1_launch(dact_prep_kernel<float>, blocks, 256, 0, s, dy, saved, g, (long long)M, N, N, dact, drop_p, (unsigned long long)seed, (unsigned long long)site);
     NDT1_CHECK_LAUNCH();
     if (db) NDT1_TRY(k_colsum<float>(g, db, M, N, N, s));
     if (dw) {
@@ -219,7 +264,13 @@ int ndt1_linear_bwd(const float* dy, const float* x, const float* w, const float
   bf16* xa = ws_take(cur, (size_t)M * ldk);
   bf16* wa = ws_take(cur, (size_t)N * ldk);
   bf16* ga = ws_take(cur, (size_t)M * ldn);
-  ndt1_launch(dact_prep_kernel<bf16>, blocks, 256, 0, s, dy, saved, ga, (long long)M, N, ldn, dact);
+  if (N % 8 == 0 && (((uintptr_t)dy | (uintptr_t)saved) & 15) == 0) {
+    const long long t8 = (long long)M * N / 8;
+    ndt1_launch(dact_prep8_kernel, (int)((t8 + 255) / 256 < 148 * 8 ? (t8 + 255) / 256 : 148 * 8), 256, 0, s, dy, saved, ga, t8, dact, drop_p,
+                (unsigned long long)seed, (unsigned long long)site);
+  } else {
+    ndt1_launch(dact_prep_kernel<bf16>, blocks, 256, 0, s, dy, saved, ga, (long long)M, N, ldn, dact, drop_p, (unsigned long long)seed, (unsigned long long)site);
+  }
   NDT1_CHECK_LAUNCH();
   if (db) NDT1_TRY(k_colsum<bf16>(ga, db, M, N, ldn, s));
   if (dw) {

@@ -25,49 +25,51 @@ namespace {
 constexpr int kAlign = 256;
 __host__ __device__ inline long long round_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
-// qkv (B*L, 3H) fp32  ->  Qh, Kh, Vh (B*nh, L, hd) and Kt, Vt (B*nh, hd, Lp), all bf16
+// qkv (B*L, 3H) fp32  ->  Qh, Kh, Vh (B*nh, L, hd) and Kt, Vt (B*nh, hd, Lp), all bf16.  One CTA per token row (grid-stride),
+// one thread per column: the head / dimension split of a column is computed once per thread, not per element.
 __global__ void pack_heads_kernel(const float* __restrict__ qkv, bf16* __restrict__ Qh, bf16* __restrict__ Kh, bf16* __restrict__ Vh,
                                   bf16* __restrict__ Kt, bf16* __restrict__ Vt, int B, int L, int H, int nh, int hd, int Lp) { pdl_grid_sync();
-  const long long total = (long long)B * L * H;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % H);
-    const long long bl = i / H;
-    const int l = (int)(bl % L), b = (int)(bl / L);
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
     const int h = c / hd, d = c % hd;
-    const float* src = qkv + bl * 3 * H + c;
-    const long long bh = (long long)b * nh + h;
-    const long long hm = (bh * L + l) * hd + d, tm = (bh * hd + d) * Lp + l;
-    const bf16 q = __float2bfloat16_rn(src[0]), k = __float2bfloat16_rn(src[H]), v = __float2bfloat16_rn(src[2 * H]);
-    Qh[hm] = q;
-    if (Kh) Kh[hm] = k;
-    if (Vh) Vh[hm] = v;
-    if (Kt) Kt[tm] = k;
-    if (Vt) Vt[tm] = v;
+    for (long long bl = blockIdx.x; bl < (long long)B * L; bl += gridDim.x) {
+      const int l = (int)(bl % L), b = (int)(bl / L);
+      const float* src = qkv + bl * 3 * H + c;
+      const long long bh = (long long)b * nh + h;
+      const long long hm = (bh * L + l) * hd + d, tm = (bh * hd + d) * Lp + l;
+      const bf16 q = __float2bfloat16_rn(src[0]), k = __float2bfloat16_rn(src[H]), v = __float2bfloat16_rn(src[2 * H]);
+      Qh[hm] = q;
+      if (Kh) Kh[hm] = k;
+      if (Vh) Vh[hm] = v;
+      if (Kt) Kt[tm] = k;
+      if (Vt) Vt[tm] = v;
+    }
   }
 }
 
 // x (B*L, H) fp32 -> Xh (B*nh, L, hd) bf16
 __global__ void pack_one_kernel(const float* __restrict__ x, bf16* __restrict__ Xh, int B, int L, int H, int nh, int hd) { pdl_grid_sync();
-  const long long total = (long long)B * L * H;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % H);
-    const long long bl = i / H;
-    const int l = (int)(bl % L), b = (int)(bl / L);
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
     const int h = c / hd, d = c % hd;
-    Xh[(((long long)b * nh + h) * L + l) * hd + d] = __float2bfloat16_rn(x[i]);
+    for (long long bl = blockIdx.x; bl < (long long)B * L; bl += gridDim.x) {
+      const int l = (int)(bl % L), b = (int)(bl / L);
+      Xh[(((long long)b * nh + h) * L + l) * hd + d] = __float2bfloat16_rn(x[bl * H + c]);
+    }
   }
 }
 
-// Xh (B*nh, L, hd) fp32 -> out (B*L, ld) fp32 at columns col0 + h*hd + d
-__global__ void unpack_heads_kernel(const float* __restrict__ Xh, float* __restrict__ out, int B, int L, int H, int nh, int hd, int ld,
-                                    int col0) { pdl_grid_sync();
-  const long long total = (long long)B * L * H;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % H);
-    const long long bl = i / H;
-    const int l = (int)(bl % L), b = (int)(bl / L);
+// Xh (B*nh, L, hd) fp32 -> out (B*L, ld) fp32 at columns col0 + h*hd + d; up to three sources in one launch (dq | dk | dv)
+__global__ void unpack_heads_kernel(const float* __restrict__ X0, const float* __restrict__ X1, const float* __restrict__ X2, float* __restrict__ out,
+                                    int B, int L, int H, int nh, int hd, int ld) { pdl_grid_sync();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
     const int h = c / hd, d = c % hd;
-    out[bl * ld + col0 + c] = Xh[(((long long)b * nh + h) * L + l) * hd + d];
+    for (long long bl = blockIdx.x; bl < (long long)B * L; bl += gridDim.x) {
+      const int l = (int)(bl % L), b = (int)(bl / L);
+      const long long src = (((long long)b * nh + h) * L + l) * hd + d;
+      float* o = out + bl * ld + c;
+      o[0] = X0[src];
+      if (X1) o[H] = X1[src];
+      if (X2) o[2 * H] = X2[src];
+    }
   }
 }
 
@@ -286,7 +288,8 @@ GemmProblem problem(int mode, int M, int N, int K, int nb) {
 }
 GemmOperand operand(const void* ptr, long long bs, int nb, int rows, int cols, int ld) { GemmOperand o{ptr, bs, nb, rows, cols, ld}; return o; }
 
-int blocks_for(long long total) { const long long b = (total + 255) / 256; return (int)(b < 148 * 16 ? b : 148 * 16); }
+int rows_grid(long long rows) { return (int)(rows < 148 * 8 ? rows : 148 * 8); }
+int row_threads(int H) { return H >= 1024 ? 1024 : (H + 31) / 32 * 32; }
 
 // C (nb, M, N) fp32 = alpha * A (nb, M, K) . B (nb, N, K)^T, every batch with its own B
 int gemm_nt(const bf16* A, int lda, long long sa, const bf16* Bm, int ldb, long long sb, float* C, int ldc, int M, int N, int K, int nb,
@@ -338,7 +341,7 @@ int k_attention_mm_fwd(const float* qkv, float* out, void* saved, void* workspac
   NDT1_CHECK_LAUNCH();
   NDT1_CUDA_CHECK(cudaMemsetAsync(sv.Kt, 0, (size_t)sh.BH * sh.hd * sh.Lp * 2, s));      // (pad columns L..Lp of the transposed operands)
   NDT1_CUDA_CHECK(cudaMemsetAsync(Vt, 0, (size_t)sh.BH * sh.hd * sh.Lp * 2, s));
-  ndt1_launch(pack_heads_kernel, blocks_for((long long)B * L * H), 256, 0, s, qkv, sv.Qh, Kh, sv.Vh, sv.Kt, Vt, B, L, H, nh, sh.hd, sh.Lp);
+  ndt1_launch(pack_heads_kernel, rows_grid((long long)B * L), row_threads(H), 0, s, qkv, sv.Qh, Kh, sv.Vh, sv.Kt, Vt, B, L, H, nh, sh.hd, sh.Lp);
   NDT1_CHECK_LAUNCH();
   NDT1_TRY(gemm_nt(sv.Qh, sh.hd, (long long)L * sh.hd, Kh, sh.hd, (long long)L * sh.hd, S, sh.Lp, L, L, sh.hd, (int)sh.BH, alpha, sv.iota, s));
   const long long rows = sh.BH * L;
@@ -346,7 +349,7 @@ int k_attention_mm_fwd(const float* qkv, float* out, void* saved, void* workspac
               p_attn, seed, site);
   NDT1_CHECK_LAUNCH();
   NDT1_TRY(gemm_nt(sv.Pd, sh.Lp, (long long)L * sh.Lp, Vt, sh.Lp, (long long)sh.hd * sh.Lp, Oh, sh.hd, L, sh.hd, L, (int)sh.BH, 1.0f, sv.iota, s));
-  ndt1_launch(unpack_heads_kernel, blocks_for((long long)B * L * H), 256, 0, s, (const float*)Oh, out, B, L, H, nh, sh.hd, H, 0);
+  ndt1_launch(unpack_heads_kernel, rows_grid((long long)B * L), row_threads(H), 0, s, (const float*)Oh, (const float*)nullptr, (const float*)nullptr, out, B, L, H, nh, sh.hd, H);
   NDT1_CHECK_LAUNCH();
   return 0;
 }
@@ -366,7 +369,7 @@ int k_attention_mm_bwd(const float* dout, void* saved, void* workspace, float* d
   float* dVh = w.take<float>(sh.BH * L * sh.hd);
   const float alpha = 1.0f / sqrtf((float)sh.hd);
   const long long hm = (long long)L * sh.hd, pm = (long long)L * sh.Lp;
-  ndt1_launch(pack_one_kernel, blocks_for((long long)B * L * H), 256, 0, s, dout, dOh, B, L, H, nh, sh.hd);
+  ndt1_launch(pack_one_kernel, rows_grid((long long)B * L), row_threads(H), 0, s, dout, dOh, B, L, H, nh, sh.hd);
   NDT1_CHECK_LAUNCH();
   NDT1_CUDA_CHECK(cudaMemsetAsync(dKh, 0, (size_t)sh.BH * hm * 4, s));            // (the routed TN GEMMs accumulate)
   NDT1_CUDA_CHECK(cudaMemsetAsync(dVh, 0, (size_t)sh.BH * hm * 4, s));
@@ -380,10 +383,8 @@ int k_attention_mm_bwd(const float* dout, void* saved, void* workspace, float* d
   // dQ = dS K,  dK = dS^T Q
   NDT1_TRY(gemm_nt(dS, sh.Lp, pm, sv.Kt, sh.Lp, (long long)sh.hd * sh.Lp, dQh, sh.hd, L, sh.hd, L, (int)sh.BH, 1.0f, sv.iota, s));
   NDT1_TRY(gemm_tn_routed(dS, sh.Lp, pm, sv.Qh, sh.hd, hm, dKh, L, sh.hd, L, (int)sh.BH, sv.iota, s));
-  const int blocks = blocks_for((long long)B * L * H);
-  ndt1_launch(unpack_heads_kernel, blocks, 256, 0, s, (const float*)dQh, dqkv, B, L, H, nh, sh.hd, 3 * H, 0);
-  ndt1_launch(unpack_heads_kernel, blocks, 256, 0, s, (const float*)dKh, dqkv, B, L, H, nh, sh.hd, 3 * H, H);
-  ndt1_launch(unpack_heads_kernel, blocks, 256, 0, s, (const float*)dVh, dqkv, B, L, H, nh, sh.hd, 3 * H, 2 * H);
+  ndt1_launch(unpack_heads_kernel, rows_grid((long long)B * L), row_threads(H), 0, s, (const float*)dQh, (const float*)dKh, (const float*)dVh, dqkv,
+              B, L, H, nh, sh.hd, 3 * H);
   NDT1_CHECK_LAUNCH();
   return 0;
 }

@@ -15,7 +15,8 @@ What computes (this library's sm_100a kernels through the C ABI; GPU only, no fa
   * the unmasked multi-head attention over the [cls +] neuron tokens (670 of them, heads of 96, at the shipped size), forward and
     backward, with dropout on the probabilities: batched tcgen05 GEMMs with the probabilities in bf16 in the bf16 mode
     (``ndt1_attention_mm_fwd`` / ``_bwd``), fused CUDA-core fp32 kernels in the strict mode (``ndt1_attention_f32``),
-  * every nn.Dropout (``ndt1_dropout_inplace``, the library's Philox streams keyed per forward),
+  * every nn.Dropout: inside the epilogue of the Linear it follows (``ndt1_linear_drop_fwd`` / ``_bwd``), or in place
+    (``ndt1_dropout_inplace``) after the cls concatenation -- the library's Philox streams, keyed per forward,
   * the maskers (``llm_bci_b200.Masker``), the masked Poisson-NLL / MSE loss and its gradient (``ndt1_recon_loss``).
 Left to torch tensor ops (data movement, no arithmetic kernels of this library exist for them): the (B, T, N) -> (B, N, T)
 transposes, the embedding row lookups, the cls concatenation and the residual additions.
@@ -34,7 +35,7 @@ import torch
 import torch.nn as nn
 
 from . import _C
-from .bci import _LinearAct
+from .bci import _LinearAct, _workspace
 from .config import DictConfig, update_config
 from .masker import Masker
 from .model_output import ModelOutput
@@ -55,6 +56,44 @@ class iTransformerOutput(ModelOutput):
 def _need_cuda(x: torch.Tensor) -> None:
     if not x.is_cuda:
         raise RuntimeError("llm_bci_b200 runs on the GPU only (no CPU fallback)")
+
+
+class _LinearActDrop(torch.autograd.Function):
+    """y = dropout(act(x W^T + b)): one Linear -> activation -> nn.Dropout run in one GEMM (``ndt1_linear_drop_fwd`` / ``_bwd``:
+    bias, activation and the keep mask in the epilogue; the backward masks dy and applies the activation derivative while it
+    casts the operand of the two gradient GEMMs).  Same mask as ``ndt1_dropout_inplace`` with the same (seed, site)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act: str, precision: str, p: float, seed: int, site: int):
+        _need_cuda(x)
+        x, w = x.contiguous().float(), w.contiguous().float()
+        M, K = x.shape
+        N = w.shape[0]
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        pre = torch.empty_like(y) if act == "gelu" else None
+        ws = _workspace(M, N, K, x.device)
+        _C.check(_C.lib().ndt1_linear_drop_fwd(x.data_ptr(), w.data_ptr(), _C.ptr(b), y.data_ptr(), _C.ptr(pre), M, N, K, _C.ACT[act],
+                                               _C.PRECISION[precision], ws.data_ptr(), ws.numel(), float(p), seed, site, _C.stream_ptr()),
+                 "ndt1_linear_drop_fwd")
+        ctx.save_for_backward(x, w, pre if pre is not None else y)
+        ctx.cfg = (act, precision, b is not None, float(p), seed, site)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, saved = ctx.saved_tensors
+        act, precision, has_bias, p, seed, site = ctx.cfg
+        dy = dy.contiguous().float()
+        M, K = x.shape
+        N = w.shape[0]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(w) if ctx.needs_input_grad[1] else None
+        db = torch.zeros(N, dtype=torch.float32, device=x.device) if (has_bias and ctx.needs_input_grad[2]) else None
+        ws = _workspace(M, N, K, x.device)
+        _C.check(_C.lib().ndt1_linear_drop_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), saved.data_ptr(), _C.ptr(dx), _C.ptr(dw), _C.ptr(db),
+                                               M, N, K, _C.ACT[act], _C.PRECISION[precision], ws.data_ptr(), ws.numel(), p, seed, site,
+                                               _C.stream_ptr()), "ndt1_linear_drop_bwd")
+        return dx, dw, db, None, None, None, None, None
 
 
 class _LayerNorm(torch.autograd.Function):
@@ -263,6 +302,13 @@ class iTransformerEncoder(nn.Module):
     def _ln(self, x, ln: nn.LayerNorm):
         return _LayerNorm.apply(x, ln.weight, ln.bias)
 
+    def _lin_drop(self, x, lin: nn.Linear, act: str, p: float):
+        """Linear -> activation -> Dropout(p) in one GEMM (the site counter advances exactly as with a separate dropout)."""
+        self._site += 1
+        if not self.training or p <= 0.0:
+            return _LinearAct.apply(x, lin.weight, lin.bias, act, self.precision)
+        return _LinearActDrop.apply(x, lin.weight, lin.bias, act, self.precision, p, self._seed, self._site)
+
     def _drop(self, x, p: float):
         self._site += 1
         if not self.training or p <= 0.0:
@@ -278,8 +324,8 @@ class iTransformerEncoder(nn.Module):
         self._site = 100
         mlp, ln0 = self.embed[0], self.embed[1]
         x = spikes.transpose(1, 2).reshape(B * N, T)                                          # (:183) one token per neuron
-        x = self._drop(self._lin(x, mlp[0], self.act), self.p_embed)
-        x = self._drop(self._lin(x, mlp[3]), self.p_embed)
+        x = self._lin_drop(x, mlp[0], self.act, self.p_embed)
+        x = self._lin_drop(x, mlp[3], "identity", self.p_embed)
         tokens = self._ln(x, ln0)                                                             # (B*N, H)
         if self.embed_channel:                                                                # (:187-191)
             if spikes_spacestamp is None:
@@ -307,10 +353,9 @@ class iTransformerEncoder(nn.Module):
             self._site += 1
             attn = _AttentionMM if self.precision == "bf16" else _Attention
             att = attn.apply(qkv, B, L, self.n_heads, self.p if self.training else 0.0, self._seed, self._site)
-            o = self._lin(att, layer.self_attn.out_proj)
-            x = self._ln(x + self._drop(o, self.p), layer.norm1)
-            h = self._drop(self._lin(x, layer.linear1, self.act), self.p)
-            x = self._ln(x + self._drop(self._lin(h, layer.linear2), self.p), layer.norm2)
+            x = self._ln(x + self._lin_drop(att, layer.self_attn.out_proj, "identity", self.p), layer.norm1)
+            h = self._lin_drop(x, layer.linear1, self.act, self.p)
+            x = self._ln(x + self._lin_drop(h, layer.linear2, "identity", self.p), layer.norm2)
         x = self._ln(x, self.transformer.norm)
         return x.view(B, L, H)
 

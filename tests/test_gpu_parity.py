@@ -1282,3 +1282,30 @@ def test_itransformer_trains_with_dropout_and_round_trips_checkpoints(tmp_path):
         assert torch.equal(a, b), n
     with pytest.raises(NotImplementedError):
         iTransformer(over, method_name="ctc", vocab_size=41, blank_id=0, zero_infinity=True)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("act", ["identity", "relu", "gelu"])
+def test_linear_with_fused_dropout_matches_linear_then_dropout(precision, act):
+    """ndt1_linear_drop_fwd / _bwd (keep mask in the GEMM epilogue, and on dy in the backward) against the two-pass form
+    ndt1_linear_fwd -> ndt1_dropout_inplace with the same (seed, site): same mask, same values, same gradients."""
+    from llm_bci_b200.itransformer import _LinearActDrop, _Dropout
+    from llm_bci_b200.bci import _LinearAct
+    torch.manual_seed(0)
+    M, K, N = 300, 72, 136
+    x0, w0, b0 = torch.randn(M, K, device=DEV), torch.randn(N, K, device=DEV) / K ** 0.5, torch.randn(N, device=DEV)
+    dy = torch.randn(M, N, device=DEV)
+    res = []
+    for fused in (True, False):
+        x, w, b = (t.clone().requires_grad_(True) for t in (x0, w0, b0))
+        if fused:
+            y = _LinearActDrop.apply(x, w, b, act, precision, 0.3, 1234, 7)
+        else:
+            y = _Dropout.apply(_LinearAct.apply(x, w, b, act, precision), 0.3, 1234, 7)
+        y.backward(dy)
+        res.append((y.detach(), x.grad, w.grad, b.grad))
+    (y1, dx1, dw1, db1), (y2, dx2, dw2, db2) = res
+    assert torch.equal(y1 == 0, y2 == 0) and 0.2 < float((y1 == 0).float().mean()) < (0.4 if act != "relu" else 0.75)
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    for a, b_ in ((y1, y2), (dx1, dx2), (dw1, dw2), (db1, db2)):
+        assert float((a - b_).abs().max()) <= tol * max(1.0, float(b_.abs().max()))
