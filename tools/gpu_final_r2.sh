@@ -11,9 +11,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
 ncu --metrics sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_tensor.sum,gpu__time_duration.sum --clock-control none -k regex:"gemm_tc_kernel|attn_tc_" -c 500 --csv --log-file gpurun_out/${tag}_tensor_pipe.csv $B > gpurun_out/${tag}_ncu_tensor_pipe.log 2>&1
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_tc_kernel -c 500 --csv --log-file gpurun_out/${tag}_gemm_dram.csv $B > gpurun_out/${tag}_ncu_gemm_dram.log 2>&1
 NCU="ncu --set full --import-source on --clock-control none"
-for spec in "attn_fwd:attn_tc_fwd_kernel:21" "attn_bwd_q:attn_tc_bwd_q:21" "attn_bwd_kv3:attn_tc_bwd_kv3:21" "gemm_wgrad_tn:gemm_tc_kernel<256, 2, 2, 128>:80" "gemm_o:gemm_tc_kernel<256, 0, 2, 32>:18" "ln_fwd:ln_fwd_rows:40" "smooth:smooth_noise_vec:3"; do
+# (template instantiations are told apart by their MANGLED names: ILi<BN>ELi<MODE>ELi<CTAS>ELi<EPI>E)
+for spec in "attn_fwd:attn_tc_fwd_kernel:21" "attn_bwd_q:attn_tc_bwd_q:21" "attn_bwd_kv3:attn_tc_bwd_kv3:21" "gemm_wgrad_tn:gemm_tc_kernelILi256ELi2ELi2ELi128E:80" "gemm_o:gemm_tc_kernelILi256ELi0ELi2ELi32E:18" "gemm_dgrad_mlp:gemm_tc_kernelILi256ELi1ELi2ELi80E:20" "ln_bwd:ln_bwd_rows:40" "ctc:ctc_kernel:3"; do
   IFS=: read name kern skip <<< "$spec"
-  timeout 600 $NCU --kernel-name "regex:$kern" --launch-skip $skip --launch-count 1 -f -o gpurun_out/${tag}_prof_$name $B > gpurun_out/${tag}_ncu_$name.log 2>&1
+  timeout 600 $NCU --kernel-name-base mangled --kernel-name "regex:$kern" --launch-skip $skip --launch-count 1 -f -o gpurun_out/${tag}_prof_$name $B > gpurun_out/${tag}_ncu_$name.log 2>&1
   python tools/ncu_summary.py gpurun_out/${tag}_prof_$name.ncu-rep --source 30 > gpurun_out/${tag}_ncu_${name}_summary.txt 2>&1
   case $name in attn_bwd_kv3) ;; *) rm -f gpurun_out/${tag}_prof_$name.ncu-rep ;; esac
 done
