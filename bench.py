@@ -530,7 +530,7 @@ def run_ours(args):
                 "step_tensor_frac_sustained": (B * FLOP_PER_TRIAL / (ms_step * 1e-3) / 1e12) / peaks["bf16_sustained"]}
     more = [entry("attn_tc_fwd_kernel (tcgen05 attention forward, algorithmic 2 contractions)", family(lambda n: "attn_tc_fwd" in n), "tensor"),
             entry("attn_tc_bwd_q_kernel (dP, dQ; recomputed S not counted)", family(lambda n: "attn_tc_bwd_q" in n), "tensor"),
-            entry("attn_tc_bwd_kv2_kernel (dV, dK; recomputed S, dP not counted)", family(lambda n: "attn_tc_bwd_kv" in n), "tensor"),
+            entry("attn_tc_bwd_kv3_kernel (dV, dK; recomputed S, dP not counted)", family(lambda n: "attn_tc_bwd_kv" in n), "tensor"),
             entry("attention, all three kernels", family(lambda n: "attn_tc_" in n), "tensor"),
             entry("ln_fwd_rows_kernel", family(lambda n: "ln_fwd" in n), "hbm"),
             entry("ln_bwd_rows_kernel", family(lambda n: "ln_bwd" in n), "hbm"),
