@@ -1309,3 +1309,26 @@ def test_linear_with_fused_dropout_matches_linear_then_dropout(precision, act):
     tol = 1e-5 if precision == "fp32" else 2e-2
     for a, b_ in ((y1, y2), (dx1, dx2), (dw1, dw2), (db1, db2)):
         assert float((a - b_).abs().max()) <= tol * max(1.0, float(b_.abs().max()))
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.3])
+@pytest.mark.parametrize("shape", [(2, 70, 64, 4), (2, 300, 192, 2)])
+def test_gemm_attention_matches_the_fused_fp32_kernels_with_the_same_dropout_mask(shape, p_drop):
+    """ndt1_attention_mm_fwd / _bwd (batched tcgen05 GEMMs, bf16 probabilities) against ndt1_attention_f32 (fused CUDA-core fp32
+    kernels) on the same inputs with the same (seed, site): both draw the probability-dropout mask from the same Philox stream, so
+    outputs and gradients differ by bf16 rounding only -- also with heads of 96 and a sequence that is not a multiple of 8."""
+    from llm_bci_b200.itransformer import _AttentionMM, _Attention
+    B, L, H, nh = shape
+    torch.manual_seed(0)
+    qkv0 = torch.randn(B * L, 3 * H, device=DEV)
+    dout = torch.randn(B * L, H, device=DEV)
+    res = []
+    for fn in (_AttentionMM, _Attention):
+        qkv = qkv0.clone().requires_grad_(True)
+        out = fn.apply(qkv, B, L, nh, p_drop, 4321, 17)
+        out.backward(dout)
+        res.append((out.detach(), qkv.grad))
+    (o1, g1), (o2, g2) = res
+    assert float((o1 - o2).abs().max()) <= 2e-2 * float(o2.abs().max())
+    assert float((g1 - g2).abs().max()) <= 2e-2 * float(g2.abs().max())
+    assert float((g1 - g2).norm()) <= 1e-2 * float(g2.norm())
