@@ -136,8 +136,9 @@ __global__ void __launch_bounds__(256) attn_dropbits_kernel(const AttnBitsJob jo
   const unsigned long long seed = seed_ref.get();
   const int l = blockIdx.y;
   const long long words_p = job.bits_p[l] ? rows_p * 8 : 0, words_o = job.bits_o[l] ? rows_o * (H / 32) : 0;
+  const long long words_m = job.bits_m[l] ? rows_o * (H / 32) : 0;
   const bool aligned = (L & 7) == 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words_p + words_o; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words_p + words_o + words_m; i += (long long)gridDim.x * blockDim.x) {
     if (i < words_p) {
       const long long row = i >> 3; const int c0 = (int)(i & 7) * 32;
       uint32_t w = 0u;
@@ -146,9 +147,12 @@ __global__ void __launch_bounds__(256) attn_dropbits_kernel(const AttnBitsJob jo
         if (c0 + 32 > L) w &= 0xFFFFFFFFu >> (c0 + 32 - L);
       }
       job.bits_p[l][i] = w;
-    } else {
+    } else if (i < words_p + words_o) {
       const long long j = i - words_p;
       job.bits_o[l][j] = keep_word32(seed, job.stream_o[l], (unsigned long long)j * 32ull, thr_o, true);
+    } else {
+      const long long j = i - words_p - words_o;
+      job.bits_m[l][j] = keep_word32(seed, job.stream_m[l], (unsigned long long)j * 32ull, thr_o, true);      // (same p as the output dropout)
     }
   }
 }
@@ -1217,7 +1221,9 @@ int k_attention_tc_dropbits(const AttnBitsJob& job, const AttnParams& p, cudaStr
   NDT1_REQUIRE(job.n >= 1 && job.n <= 32, "attention_tc: %d layers in one keep-bit launch (max 32)", job.n);
   NDT1_REQUIRE(p.H % 32 == 0, "attention_tc: hidden size %d must be a multiple of 32", p.H);
   const long long rows_p = (long long)p.B * p.nh * p.L, rows_o = (long long)p.B * p.L;
-  const long long words = rows_p * 8 + rows_o * (p.H / 32);
+  bool any_m = false;
+  for (int l = 0; l < job.n; ++l) any_m |= job.bits_m[l] != nullptr;
+  const long long words = rows_p * 8 + rows_o * (p.H / 32) * (any_m ? 2 : 1);
   if (words == 0) return 0;
   const int bx = (int)((words + 255) / 256 < 148 * 4 ? (words + 255) / 256 : 148 * 4);
   ndt1_launch(attn_dropbits_kernel, dim3(bx, job.n), 256, 0, stream, job, p.seed, rows_p, p.L, rows_o, p.H, drop_threshold(p.p_attn),

@@ -77,6 +77,8 @@ struct Engine : ndt1_engine {
   std::vector<float*> lse;
   std::vector<unsigned int*> dropbits;   // keep bits of the attention-probability dropout (tensor-core path)
   std::vector<unsigned int*> dropbits_o; // keep bits of the attention-output dropout (tensor-core path)
+  std::vector<unsigned int*> dropbits_m; // keep bits of the MLP dropout (read by the down-projection's epilogue instead of running Philox)
+  bool bits_drawn = false;               // this forward drew the keep bits (the backward's epilogues may read them)
   cudaEvent_t bits_fork_ev = nullptr, bits_done_ev = nullptr;
   T* hn = nullptr; T* fac = nullptr; T* fpre = nullptr;
   float* logits = nullptr; float* logp = nullptr; float* dlogits = nullptr; float* nll = nullptr; float* ctc_ws = nullptr;
@@ -129,13 +131,14 @@ struct Engine : ndt1_engine {
     }
     xs.resize(2 * NL + 1); mean.resize(2 * NL + 1); rstd.resize(2 * NL + 1);
     for (int i = 0; i < 2 * NL + 1; ++i) { xs[i] = ar.take<float>(Mm * H); mean[i] = ar.take<float>(Mm); rstd[i] = ar.take<float>(Mm); }
-    h1.resize(NL); h2.resize(NL); qkv.resize(NL); att.resize(NL); attd.resize(NL); u.resize(NL); g.resize(NL); lse.resize(NL); dropbits.resize(NL); dropbits_o.resize(NL);
+    h1.resize(NL); h2.resize(NL); qkv.resize(NL); att.resize(NL); attd.resize(NL); u.resize(NL); g.resize(NL); lse.resize(NL); dropbits.resize(NL); dropbits_o.resize(NL); dropbits_m.resize(NL);
     for (int l = 0; l < NL; ++l) {
       h1[l] = ar.take<T>(Mm * H); h2[l] = ar.take<T>(Mm * H); qkv[l] = ar.take<T>(Mm * 3 * H);
       att[l] = ar.take<T>(Mm * H); attd[l] = (k.p_transformer > 0.f) ? ar.take<T>(Mm * H) : att[l];
       u[l] = ar.take<T>(Mm * I); g[l] = ar.take<T>(Mm * I); lse[l] = ar.take<float>((long long)Bm * k.n_heads * Lm);
       dropbits[l] = (kBf16 && k.p_transformer > 0.f) ? ar.take<unsigned int>((long long)Bm * k.n_heads * Lm * 8) : nullptr;
       dropbits_o[l] = (kBf16 && k.p_transformer > 0.f && H % 32 == 0) ? ar.take<unsigned int>(Mm * (H / 32)) : nullptr;
+      dropbits_m[l] = (kBf16 && k.p_transformer > 0.f && H % 32 == 0) ? ar.take<unsigned int>(Mm * (H / 32)) : nullptr;
     }
     hn = ar.take<T>(Mm * H);
     if (k.factors_active) { fac = ar.take<T>(Mm * Hout); fpre = ar.take<T>(Mm * Hout); dfac = ar.take<T>(Mm * Hout); }
@@ -321,12 +324,17 @@ struct Engine : ndt1_engine {
     // second stream, concurrent with the embedding GEMMs; the first attention layer waits for it.
     const bool tc_attention = kBf16 && !force_simt && !simt_attention && (H / k.n_heads) == 128 && L <= 256 && L >= 1 && H % 32 == 0;
     const bool draw_bits = tc_attention && ptr_ > 0.f;
+    // (the GEMM epilogues of the MLP dropout and of the attention-output dropout's backward read the same kind of bits, in
+    //  classes without any Philox code; NDT1_GEMM_DROPBITS=0 keeps them on Philox: identical masks either way)
+    static const bool no_gemm_bits = getenv("NDT1_GEMM_DROPBITS") && getenv("NDT1_GEMM_DROPBITS")[0] == '0';
+    const bool use_gemm_bits = draw_bits && !no_gemm_bits;
+    bits_drawn = use_gemm_bits;
     if (draw_bits) {
       AttnBitsJob job; memset(&job, 0, sizeof(job));
       job.n = NL;
       for (int l = 0; l < NL; ++l) {
-        job.bits_p[l] = dropbits[l]; job.bits_o[l] = dropbits_o[l];
-        job.stream_p[l] = site_attn_p(l); job.stream_o[l] = site_attn_o(l);
+        job.bits_p[l] = dropbits[l]; job.bits_o[l] = dropbits_o[l]; job.bits_m[l] = use_gemm_bits ? dropbits_m[l] : nullptr;
+        job.stream_p[l] = site_attn_p(l); job.stream_o[l] = site_attn_o(l); job.stream_m[l] = site_mlp(l);
       }
       AttnParams shp; memset(&shp, 0, sizeof(shp));
       shp.B = B; shp.L = L; shp.H = H; shp.nh = k.n_heads; shp.hd = H / k.n_heads; shp.p_attn = ptr_; shp.p_out = ptr_; shp.seed = seed;
@@ -501,7 +509,7 @@ struct Engine : ndt1_engine {
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = xo; e.ldc = H; e.bias = k.mlp_bias ? q.down_b : nullptr; e.resid = xm;
-        if (ptr_ > 0.f) { e.drop_p = ptr_; e.drop_seed = seed; e.drop_stream = site_mlp(l); }
+        if (ptr_ > 0.f) { e.drop_p = ptr_; e.drop_seed = seed; e.drop_stream = site_mlp(l); if (bits_drawn) e.drop_bits = dropbits_m[l]; }
         NDT1_TRY(linear_fwd(g[l], I, W(q.down_w, kBf16 ? u_down[l] : nullptr), I, (int)M, H, I, e, s));
       }
     }
@@ -717,7 +725,7 @@ struct Engine : ndt1_engine {
       {
         GemmEpilogue e = gemm_epilogue_default();
         e.out = dA; e.out_bf16 = kBf16; e.ldc = H;
-        if (ptr_ > 0.f) { e.drop_p = ptr_; e.drop_bwd = 1; e.drop_seed = seed; e.drop_stream = site_attn_o(l); }
+        if (ptr_ > 0.f) { e.drop_p = ptr_; e.drop_bwd = 1; e.drop_seed = seed; e.drop_stream = site_attn_o(l); if (bits_drawn) e.drop_bits = dropbits_o[l]; }
         NDT1_TRY(linear_dgrad(dY, H, W(q.o_w, kBf16 ? u_o[l] : nullptr), H, (int)M, H, H, e, s));
       }
       AttnParams ap;

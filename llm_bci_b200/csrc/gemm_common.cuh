@@ -53,6 +53,8 @@ struct GemmEpilogue {
   float drop_p;             // dropout after activation/gather (forward) ...
   int drop_bwd;             // ... or the same mask applied to a gradient (backward)
   SeedRef drop_seed; unsigned long long drop_stream;
+  const unsigned int* drop_bits;   // optional (tensor-core kernel, N % 32 == 0): the keep bits of this site already drawn -- bit n % 32 of word
+                                   // (b * M + r) * (N / 32) + n / 32, the layout of attn_dropbits_kernel -- read instead of running Philox
   const float* resid;       // fp32 residual, indexed like out
   int dact;                 // DACT_*: multiply by act'(saved)
   const void* dact_in;      // indexed like out
@@ -85,7 +87,7 @@ static inline GemmEpilogue gemm_epilogue_default() {
   e.out = nullptr; e.out_bf16 = 0; e.ldc = 0; e.c_batch_stride = 0;
   e.out2 = nullptr; e.out2_bf16 = 0; e.out2_deriv = 0; e.bias = nullptr; e.alpha = 1.f; e.act = ACT_NONE;
   e.gather_tab = nullptr; e.gather_idx = nullptr; e.gather_idx_stride = 0; e.gather_ld = 0;
-  e.drop_p = 0.f; e.drop_bwd = 0; e.drop_seed = SeedRef(); e.drop_stream = 0;
+  e.drop_p = 0.f; e.drop_bwd = 0; e.drop_seed = SeedRef(); e.drop_stream = 0; e.drop_bits = nullptr;
   e.resid = nullptr; e.dact = DACT_NONE; e.dact_in = nullptr; e.dact_in_bf16 = 0;
   e.accumulate = 0; e.colsum = nullptr;
   e.sel = nullptr; e.sel_n = 0; e.bias_sel_stride = 0; e.c_sel_stride = 0;

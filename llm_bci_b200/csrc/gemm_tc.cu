@@ -111,11 +111,13 @@ enum { SIDE_NONE = 0, SIDE_RESID = 1, SIDE_DACT = 2, SIDE_GATHER = 3 };
 // launch is a few hundred instructions that stay in the instruction cache (the all-features epilogue does not, and
 // instruction-fetch stalls then rival the arithmetic).  EF_* = features a class may use.
 enum {
-  EF_OUT2 = 1, EF_ACT = 2, EF_GATHER = 4, EF_DROP = 8, EF_DACT = 16, EF_RESID = 32, EF_COLSUM = 64, EF_ACCUM = 128, EF_SCALAR = 256,
+  EF_OUT2 = 1, EF_ACT = 2, EF_GATHER = 4, EF_DROP = 8, EF_DACT = 16, EF_RESID = 32, EF_COLSUM = 64, EF_ACCUM = 128, EF_SCALAR = 256, EF_DROPBITS = 512,
   EPI_NONE = 0,                                          // bias only: QKV, plain data gradients (no side input, no side registers)
   EPI_PLAIN = EF_RESID,                                  // bias + fp32 residual: attention out-proj
   EPI_ACT = EF_OUT2 | EF_ACT,                            // bias + activation (+ pre-activation copy): MLP up-proj, channel embedding
-  EPI_DROP = EF_GATHER | EF_DROP | EF_RESID,             // bias (+ position rows) + dropout (+ residual): MLP down-proj, stack projection
+  EPI_DROP = EF_GATHER | EF_DROP | EF_RESID,             // bias + position rows + dropout (+ residual): stack projection
+  EPI_BITSRES = EF_DROPBITS | EF_RESID,                  // bias + dropout from keep bits drawn ahead (no Philox code: no spills) + residual: MLP down-proj
+  EPI_BITSBWD = EF_DROPBITS | EF_DACT | EF_COLSUM,       // backward with the keep bits: attention out-proj data gradient
   EPI_DACT = EF_DROP | EF_DACT | EF_COLSUM,              // backward: dropout mask, activation derivative, bias-gradient column sums
   EPI_DMUL = EF_DACT | EF_COLSUM,                        // backward without a dropout mask (no Philox: fewer registers): MLP down-proj data gradient
   EPI_ACCUM = EF_ACCUM,                                  // weight gradients: fp32 red.add
@@ -186,9 +188,25 @@ __device__ __forceinline__ float4 bias_load(const GemmEpilogue& e, const EpiCtx&
   return b;
 }
 
+// the keep-bit words of this lane's 8 rows (one word per row, shared by the 8 lanes of a row group): issued with the chunk's
+// TMEM load like the bias, for the same reason
+struct KeepWords { uint32_t w[8]; };
+template <int EPI>
+__device__ __forceinline__ KeepWords bits_load(const GemmEpilogue& e, const TcParams& p, const ChunkAt& at, int lane) {
+  KeepWords k;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k.w[i] = 0u;
+  if (!ef_has(EPI, EF_DROPBITS) || !e.drop_bits || e.drop_p <= 0.f || !at.live || at.n >= p.N) return k;
+  const uint32_t wpr = (uint32_t)p.N >> 5;
+  const unsigned int* bw = e.drop_bits + ((long long)at.bt * p.M + at.r0 + (lane >> 3)) * wpr + (at.n >> 5);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) if ((at.rowmask >> i) & 1u) k.w[i] = __ldg(bw + (unsigned)(4 * i) * wpr);
+  return k;
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiCtx& cx, const TcParams& p, const ChunkAt& at, int lane,
-                                               const float4* acc, const float4* side, const uint8_t* stg, const float4 bias4) {
+                                               const float4* acc, const float4* side, const uint8_t* stg, const float4 bias4, const KeepWords& kw) {
   if (!at.live) return;
   if (ef_has(EPI, EF_SCALAR) && !cx.vec_ok) {        // ragged shapes (the 41-column head): element-wise, still row-contiguous across lanes
 #pragma unroll 1           // ONE copy of the scalar epilogue (it carries every feature): code size, not speed, matters here
@@ -261,6 +279,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const EpiC
         t = __ldg((const float4*)(e.gather_tab + g * e.gather_ld + at.n));
       }
       if (ok(i)) { v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w; }
+    }
+  }
+  if (ef_has(EPI, EF_DROPBITS) && e.drop_p > 0.f && e.drop_bits) {
+    // keep bits drawn ahead of time on the side stream (they depend on the step's key only): 4 bits of one word per row,
+    // the 8 lanes of a row group read the same word
+    const float ik = 1.0f / (1.0f - e.drop_p);
+    const int sh = at.n & 31;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t nib = kw.w[i] >> sh;
+      v[i].x *= (nib & 1u) ? ik : 0.f; v[i].y *= (nib & 2u) ? ik : 0.f; v[i].z *= (nib & 4u) ? ik : 0.f; v[i].w *= (nib & 8u) ? ik : 0.f;
     }
   }
   if (ef_has(EPI, EF_DROP) && e.drop_p > 0.f) {
@@ -670,6 +699,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t raw[32];
         tmem_ld32(taddr_row + c * 32, raw);
         const float4 bias_cur = bias_load(e, cx, p, at);     // flies under the TMEM load and the transpose (not at the head of the arithmetic)
+        const KeepWords kw_cur = bits_load<EPI>(e, p, at, lane);
         // side input of the next chunk (or of the next tile's first chunk) while the TMEM load is in flight
         const ChunkAt nx = (c + 1 < nch) ? chunk_of(t_cur, c + 1) : t_nxt;
         side_load<EPI>(e, cx, p, nx, lane, side_nxt);
@@ -698,7 +728,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[i].x), "=f"(acc[i].y), "=f"(acc[i].z), "=f"(acc[i].w) : "r"(a) : "memory");
         }
         __syncwarp();
-        epilogue_chunk<EPI>(e, cx, p, at, lane, acc, side_cur, stg, bias_cur);
+        epilogue_chunk<EPI>(e, cx, p, at, lane, acc, side_cur, stg, bias_cur, kw_cur);
 #pragma unroll
         for (int i = 0; i < 8; ++i) side_cur[i] = side_nxt[i];
       }
@@ -810,7 +840,7 @@ int epilogue_class(const TcParams& tp, int bn) {
   if (e.out2) need |= EF_OUT2;
   if (e.act != ACT_NONE) need |= EF_ACT;
   if (e.gather_tab) need |= EF_GATHER;
-  if (e.drop_p > 0.f) need |= EF_DROP;
+  if (e.drop_p > 0.f) need |= (e.drop_bits && tp.N % 32 == 0) ? EF_DROPBITS : EF_DROP;     // (no class with the bits: falls to Philox, same mask)
   if (e.dact != DACT_NONE) need |= EF_DACT;
   if (e.resid) need |= EF_RESID;
   if (e.colsum) need |= EF_COLSUM;
@@ -820,11 +850,16 @@ int epilogue_class(const TcParams& tp, int bn) {
                    (e.gather_tab == nullptr || e.gather_ld % 4 == 0) && (e.drop_p <= 0.f || tp.N % 8 == 0);
   if (!vec || bn != 256) return EPI_ALL;
   // (only the classes launch_256 instantiates for this operand mode)
-  const int nt[4] = {EPI_NONE, EPI_PLAIN, EPI_ACT, EPI_DROP}, nn[3] = {EPI_NONE, EPI_DMUL, EPI_DACT}, tn[1] = {EPI_ACCUM};
+  const int nt[5] = {EPI_NONE, EPI_PLAIN, EPI_ACT, EPI_BITSRES, EPI_DROP}, nn[4] = {EPI_NONE, EPI_DMUL, EPI_BITSBWD, EPI_DACT}, tn[1] = {EPI_ACCUM};
   const int* classes = tp.mode == GEMM_NT ? nt : (tp.mode == GEMM_NN ? nn : tn);
-  const int n = tp.mode == GEMM_NT ? 4 : (tp.mode == GEMM_NN ? 3 : 1);
+  const int n = tp.mode == GEMM_NT ? 5 : (tp.mode == GEMM_NN ? 4 : 1);
   for (int c = 0; c < n; ++c)
     if ((need & ~classes[c]) == 0) return classes[c];
+  if (need & EF_DROPBITS) {                 // no keep-bit class for this combination: the Philox classes give the same mask
+    need = (need & ~EF_DROPBITS) | EF_DROP;
+    for (int c = 0; c < n; ++c)
+      if ((need & ~classes[c]) == 0) return classes[c];
+  }
   return EPI_ALL;
 }
 
@@ -835,10 +870,12 @@ int launch_256(int cls, const CUtensorMap& ma, const CUtensorMap& mb, const TcPa
     if (cls == EPI_NONE) return launch_inst<256, MODE, CTAS, EPI_NONE>(ma, mb, tp, stream);
     if (cls == EPI_PLAIN) return launch_inst<256, MODE, CTAS, EPI_PLAIN>(ma, mb, tp, stream);
     if (cls == EPI_ACT) return launch_inst<256, MODE, CTAS, EPI_ACT>(ma, mb, tp, stream);
+    if (cls == EPI_BITSRES) return launch_inst<256, MODE, CTAS, EPI_BITSRES>(ma, mb, tp, stream);
     if (cls == EPI_DROP) return launch_inst<256, MODE, CTAS, EPI_DROP>(ma, mb, tp, stream);
   } else if (MODE == GEMM_NN) {
     if (cls == EPI_NONE) return launch_inst<256, MODE, CTAS, EPI_NONE>(ma, mb, tp, stream);
     if (cls == EPI_DMUL) return launch_inst<256, MODE, CTAS, EPI_DMUL>(ma, mb, tp, stream);
+    if (cls == EPI_BITSBWD) return launch_inst<256, MODE, CTAS, EPI_BITSBWD>(ma, mb, tp, stream);
     if (cls == EPI_DACT) return launch_inst<256, MODE, CTAS, EPI_DACT>(ma, mb, tp, stream);
   } else {
     if (cls == EPI_ACCUM) return launch_inst<256, MODE, CTAS, EPI_ACCUM>(ma, mb, tp, stream);
@@ -957,6 +994,7 @@ int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream) {
   }
   NDT1_REQUIRE(!p.b_sel || p.mode == GEMM_NT, "gemm_tc: b_sel (per-trial B operand) only for GEMM_NT");
   NDT1_REQUIRE(!p.epi.sel || p.mode != GEMM_TN || p.split_k == p.nchunk, "gemm_tc: a routed GEMM_TN needs split_k == nchunk (one split per trial)");
+  NDT1_REQUIRE(!p.epi.drop_bits || p.N % 32 == 0, "gemm_tc: keep bits need N %% 32 == 0 (N=%d)", p.N);
   NDT1_REQUIRE(!p.epi.colsum || (p.N % 8 == 0 && p.epi.ldc % 4 == 0 && p.epi.c_batch_stride % 4 == 0),
                "gemm_tc: the fused column sum needs a vectorisable output (N=%d)", p.N);
   int bn = p.N > 128 ? 256 : (p.N > 64 ? 128 : 64);

@@ -104,7 +104,8 @@ int k_attention_tc_bwd(const AttnParams& p, cudaStream_t stream);
 // keep bits of the probability and output dropout of up to NDT1_MAX_LAYERS attention layers in ONE launch (same Philox draws as
 // drop_scale_1 of the CUDA-core kernels): they depend on the step's key only, so the engine draws them on its second stream
 // while the embedding GEMMs run, and no attention kernel spends an instruction on the generator
-struct AttnBitsJob { unsigned int* bits_p[32]; unsigned int* bits_o[32]; unsigned long long stream_p[32], stream_o[32]; int n; };
+struct AttnBitsJob { unsigned int* bits_p[32]; unsigned int* bits_o[32]; unsigned int* bits_m[32]; unsigned long long stream_p[32], stream_o[32], stream_m[32]; int n; };
+// (bits_m: a third site per layer in the layout of bits_o -- the MLP dropout, read by the down-projection GEMM's epilogue)
 int k_attention_tc_dropbits(const AttnBitsJob& job, const AttnParams& shape, cudaStream_t stream);
 void k_attention_tc_set_timeline(unsigned long long* buf);   // debugging: per-CTA phase timestamps (32 u64 per CTA), null = off
 
