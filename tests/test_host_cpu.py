@@ -280,3 +280,26 @@ def test_reference_install_manifest_matches_the_tree():
     assert "models/ndt1.py" in man and "models/masker.py" in man and "configs/trainer_ctc_ndt1.yaml" in man and len(man) >= 20
     if os.path.isdir(ir.DST):
         assert ir.verify(ir.DST)
+
+
+def test_itransformer_plugin_surface_and_no_cpu_fallback():
+    """SURVEY 8 f4 host side: registry entry, the reference's state_dict keys (names of tests/golden/itransformer_small.npz, produced
+    by the unmodified reference), unbuilt variants raise, and a CPU tensor raises instead of falling back."""
+    import numpy as np
+    import pytest
+    import torch
+    import llm_bci_b200 as lb
+    over = {"masker": {"main": {"ratio": 0.25}}, "encoder": {"embedder": {"dropout": 0.0, "max_n_bins": 20}, "hidden_size": 64, "n_heads": 4,
+                                                                "n_layers": 2, "dropout": 0.0, "max_n_channels": 32, "embed_region": False}}
+    model = lb.NAME2MODEL["iTransformer"](over, method_name="mlm", loss="poisson_nll", log_input=True)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "itransformer_small.npz"))
+    assert [n for n, _ in model.named_parameters()] == list(g["names"])
+    assert isinstance(model, lb.iTransformer) and set(lb.iTransformerOutput.__dataclass_fields__) == {"loss", "n_examples", "mask", "preds", "targets"}
+    with pytest.raises(NotImplementedError):
+        lb.iTransformer(over, method_name="stat_behaviour", loss="xent", n_labels=3)
+    with pytest.raises(NotImplementedError):
+        lb.iTransformer({**over, "encoder": {**over["encoder"], "embedder": {"mode": "transformer", "max_n_bins": 20}}}, method_name="mlm",
+                        loss="poisson_nll", log_input=True)
+    x = torch.zeros(2, 20, 24)
+    with pytest.raises(RuntimeError, match="GPU only"):
+        model(spikes=x, spikes_mask=torch.ones(2, 20, dtype=torch.int64), spikes_timestamp=torch.arange(20)[None].expand(2, 20))
