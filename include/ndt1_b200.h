@@ -101,6 +101,10 @@ int ndt1_recon_loss(const float* pred, const float* target, float* dpred, const 
                     int B, int T, int N, int loss_kind, int shift_by_one, int relu_out, float* loss, int64_t* count,
                     const float* dloss, void* stream);
 
+/* nn.CrossEntropyLoss(reduction="none")(logits, labels).sum(), models/itransformer.py:300-301,375 (the `stat_behaviour` method):
+ * logits (B,V), labels (B) int64;  *loss += sum;  optional dlogits (B,V) = (softmax - onehot) * *dloss (NULL = 1). */
+int ndt1_xent_loss(const float* logits, const int64_t* labels, float* dlogits, float* loss, int B, int V, const float* dloss, void* stream);
+
 /* nn.LayerNorm (eps 1e-5), models/ndt1.py:309-311,402.  fp32 in/out. */
 int ndt1_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int64_t rows,
                        int H, float eps, void* stream);

@@ -97,6 +97,7 @@ PROTOTYPES = {
     "ndt1_attention_mm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ndt1_attention_mm_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _u64, _u64, _p]),
     "ndt1_attention_mm_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _u64, _u64, _p]),
+    "ndt1_xent_loss": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "ndt1_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _p]),
     "ndt1_dropout_inplace": (_i, [_p, _i64, _f, _u64, _u64, _p]),
     "ndt1_adamw_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _p]),

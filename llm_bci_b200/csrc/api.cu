@@ -23,6 +23,29 @@ __global__ void dact_prep_kernel(const float* __restrict__ dy, const float* __re
     out[i] = from_f32<T>(v);
   }
 }
+// nn.CrossEntropyLoss(reduction="none").sum() over rows of (B, V) logits with int64 class labels: one warp per row;
+// loss += sum_b (logsumexp(z_b) - z_b[label_b]);  dlogits = (softmax(z) - onehot(label)) * dloss
+__global__ void xent_kernel(const float* __restrict__ z, const long long* __restrict__ labels, float* __restrict__ dz, float* __restrict__ loss,
+                            int B, int V, const float* __restrict__ dloss) { pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float* zr = z + (long long)row * V;
+  float m = -INFINITY;
+  for (int j = lane; j < V; j += 32) m = fmaxf(m, zr[j]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < V; j += 32) sum += expf(zr[j] - m);
+  sum = warp_sum(sum);
+  const float lse = m + logf(sum);
+  long long lab = labels[row];
+  lab = lab < 0 ? 0 : (lab >= V ? V - 1 : lab);
+  const float gs = dloss ? *dloss : 1.f;
+  if (dz)
+    for (int j = lane; j < V; j += 32) dz[(long long)row * V + j] = (expf(zr[j] - lse) - (j == (int)lab ? 1.f : 0.f)) * gs;
+  if (lane == 0 && loss) atomicAdd(loss, lse - zr[lab]);
+}
+
 // the same for cols % 8 == 0 and an unpadded bf16 operand (ld_out == cols): 8 consecutive elements per thread -- two 16-byte reads
 // per input, one Philox block (the 8 elements are exactly one block of the flat index), one 16-byte write
 __global__ void dact_prep8_kernel(const float* __restrict__ dy, const float* __restrict__ saved, bf16* __restrict__ out, long long total8, int dact,
@@ -389,6 +412,14 @@ int ndt1_attention_mm_bwd(const float* dout, void* saved, void* workspace, float
                           uint64_t seed, uint64_t site_attn, void* stream) {
   NDT1_REQUIRE(dout && dqkv && saved && workspace, "attention_mm_bwd: null argument");
   return k_attention_mm_bwd(dout, saved, workspace, dqkv, B, L, H, n_heads, p_attn, SeedRef(seed), site_attn, (cudaStream_t)stream);
+}
+
+int ndt1_xent_loss(const float* logits, const int64_t* labels, float* dlogits, float* loss, int B, int V, const float* dloss, void* stream) {
+  NDT1_REQUIRE(logits && labels && V >= 1, "xent_loss: null argument");
+  if (B == 0) return 0;
+  ndt1_launch(xent_kernel, (B + 7) / 8, 256, 0, (cudaStream_t)stream, logits, (const long long*)labels, dlogits, loss, B, V, dloss);
+  NDT1_CHECK_LAUNCH();
+  return 0;
 }
 
 int ndt1_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, float* dx, float* dgamma,

@@ -21,8 +21,9 @@ What computes (this library's sm_100a kernels through the C ABI; GPU only, no fa
 Left to torch tensor ops (data movement, no arithmetic kernels of this library exist for them): the (B, T, N) -> (B, N, T)
 transposes, the embedding row lookups, the cls concatenation and the residual additions.
 
-Scope: the ``mlp`` embedder (the shipped configuration) and the methods ``mlm`` and ``dyn_behaviour``.  The ``transformer``
-embedder mode and the ``ctc`` / ``stat_behaviour`` methods raise ``NotImplementedError``.
+Scope: the ``mlp`` embedder (the shipped configuration) and the methods ``mlm``, ``dyn_behaviour`` and ``stat_behaviour`` (the
+three shipped trainer configs: ssl, wheel, choice).  The ``transformer`` embedder mode and the ``ctc`` method raise
+``NotImplementedError`` (the reference's ctc path log-softmaxes the FLAT (bins x vocabulary) vector, :270, not per frame).
 """
 from __future__ import annotations
 
@@ -243,6 +244,27 @@ class _ReconLoss(torch.autograd.Function):
         return dpred * dloss, None, None, None, None
 
 
+class _XentLoss(torch.autograd.Function):
+    """nn.CrossEntropyLoss(reduction="none")(logits, labels).sum() (models/itransformer.py:300-301, 375)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        _need_cuda(logits)
+        logits = logits.contiguous().float()
+        B, V = logits.shape
+        dlogits = torch.empty_like(logits)
+        loss = torch.zeros((), dtype=torch.float32, device=logits.device)
+        _C.check(_C.lib().ndt1_xent_loss(logits.data_ptr(), labels.contiguous().data_ptr(), dlogits.data_ptr(), loss.data_ptr(), B, V, None,
+                                         _C.stream_ptr()), "ndt1_xent_loss")
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * dloss, None
+
+
 class AverageTokens(nn.Module):
     def __init__(self, dim):
         super().__init__()
@@ -384,8 +406,15 @@ class iTransformer(nn.Module):
             n_outputs = config.encoder.embedder.max_n_bins
         elif self.method == "dyn_behaviour":
             n_outputs = config.encoder.embedder.max_n_bins
-        elif self.method in ("ctc", "stat_behaviour"):
-            raise NotImplementedError(f"iTransformer: method {self.method} is not built (mlm and dyn_behaviour are)")
+        elif self.method == "stat_behaviour":
+            if kwargs["loss"] == "xent":
+                n_outputs = kwargs["n_labels"]
+            elif kwargs["loss"] == "mse":
+                n_outputs = 1
+            else:
+                raise Exception(f"Loss {kwargs['loss']} not implemented yet for stat_behaviour")
+        elif self.method == "ctc":
+            raise NotImplementedError("iTransformer: method ctc is not built (mlm, dyn_behaviour and stat_behaviour are)")
         else:
             raise Exception(f"Method {self.method} not implemented")
         layers = []
@@ -408,6 +437,8 @@ class iTransformer(nn.Module):
             self.loss_name = kwargs["loss"]
             if self.loss_name not in ("poisson_nll", "mse"):
                 raise Exception(f"Loss {kwargs['loss']} not implemented yet for mlm")
+        elif self.method == "stat_behaviour":
+            self.loss_name = kwargs["loss"]
         self.config = config
 
     def _decode(self, x2d):
@@ -440,6 +471,15 @@ class iTransformer(nn.Module):
             targets_mask = targets_mask & spikes_mask.unsqueeze(2)
             kind = (_C.LOSS_POISSON_LOG if self.log_input else _C.LOSS_POISSON_RATE) if self.loss_name == "poisson_nll" else _C.LOSS_MSE
             loss, n = _ReconLoss.apply(preds, targets, targets_mask.contiguous(), spikes_mask.contiguous(), kind)
+            return iTransformerOutput(loss=loss, n_examples=n, preds=preds, targets=targets, mask=targets_mask)
+        if self.method == "stat_behaviour":                         # (:371-385) one label / value per trial from the cls token (or token sum)
+            targets_mask = targets_mask & spikes_mask.unsqueeze(2)
+            if self.loss_name == "xent":
+                loss = _XentLoss.apply(preds, targets.long().squeeze(1))
+            else:
+                ones = torch.ones(preds.shape[0], 1, 1, dtype=torch.int64, device=preds.device)
+                loss, _ = _ReconLoss.apply(preds.reshape(-1, 1, 1), targets.float().reshape(-1, 1, 1), ones, ones[:, :, 0].contiguous(), _C.LOSS_MSE)
+            n = torch.tensor(len(targets), device=loss.device, dtype=torch.long)
             return iTransformerOutput(loss=loss, n_examples=n, preds=preds, targets=targets, mask=targets_mask)
         # dyn_behaviour (:357-369): one value per bin from the cls token (or the token sum), MSE over the bins that are not padding
         ones = torch.ones(preds.shape[0], preds.shape[1], 1, dtype=torch.int64, device=preds.device)

@@ -7,7 +7,7 @@ Functional restatement on torch-CPU of ``iTransformer.forward`` (models/itransfo
   * channel / region / depth embeddings, each through its own LayerNorm (:126-150, 187-201), cls token (:203-205), dropout,
   * ``nn.TransformerEncoder`` of POST-LN layers (``norm_first`` = False): x = LN1(x + drop(MHA(x))), x = LN2(x + drop(W2 drop(act(W1 x)))),
     packed ``in_proj`` = q | k | v, no attention mask, dropout on the attention probabilities, final LayerNorm (:157-173, 207),
-  * the decoder (:249-272) and the four losses (:330-385); ``mlm`` and ``dyn_behaviour`` are restated here.
+  * the decoder (:249-272) and the four losses (:330-385); ``mlm``, ``dyn_behaviour`` and ``stat_behaviour`` are restated here.
 Pinned against outputs of the unmodified reference run in the build container (tests/golden/make_golden.py::itransformer_cases ->
 tests/golden/itransformer_small.npz, itransformer_config3.npz; the shipped yaml needs the masker keys `active` / `regions`,
 SURVEY.md component 8 -- a config-only fix).
@@ -125,4 +125,11 @@ def itransformer_forward(p: Dict[str, torch.Tensor], cfg: dict, method_kwargs: d
     if method == "dyn_behaviour":                                                          # :357-369
         el = F.mse_loss(preds, targets, reduction="none")
         return (el * smask).sum(), smask.sum(), preds, smask
+    if method == "stat_behaviour":                                                         # :371-385
+        tmask = tmask & smask.unsqueeze(2)
+        if method_kwargs["loss"] == "xent":
+            loss = F.cross_entropy(preds, targets.long().squeeze(1), reduction="none").sum()
+        else:
+            loss = F.mse_loss(preds.squeeze(1), targets.squeeze(1), reduction="none").sum()
+        return loss, torch.tensor(len(targets)), preds, tmask
     raise NotImplementedError(f"oracle: method {method} not restated")

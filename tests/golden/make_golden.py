@@ -714,10 +714,26 @@ def itransformer_cases(R):
     b2 = dict(b, targets=torch.randn(3, 20, generator=torch.Generator().manual_seed(9)))
     b2["spikes_mask"] = (torch.arange(20)[None] < torch.tensor([20, 14, 17])[:, None]).to(torch.int64)
     out2, grads2 = run_ref(m2, b2, train=True, seed=5)
-    d.update(flat("dyn/param", dict(m2.named_parameters())))
+    main_params = {n: p.detach().clone() for n, p in m.named_parameters()}
+
+    def own_params(model):      # the variants share every initial value with the main model except the decoder's last layer
+        return {n: p for n, p in model.named_parameters() if n not in main_params or p.shape != main_params[n].shape or not torch.equal(p, main_params[n])}
+
+    d.update(flat("dyn/param", own_params(m2)))
     d.update(flat("dyn/grad", grads2))
     d.update({"dyn/targets": b2["targets"].numpy(), "dyn/spikes_mask": b2["spikes_mask"].numpy(), "dyn/loss": out2.loss.detach().numpy(),
               "dyn/n_examples": out2.n_examples.numpy(), "dyn/preds": out2.preds.detach().numpy()})
+    # third method: stat_behaviour (one label / value per trial from the cls token), cross-entropy over 3 labels and MSE
+    for tag, kw, tg in (("xent", dict(method_name="stat_behaviour", loss="xent", n_labels=3), torch.tensor([[2.0], [0.0], [1.0]])),
+                        ("smse", dict(method_name="stat_behaviour", loss="mse"), torch.tensor([[0.3], [-1.2], [0.7]]))):
+        torch.manual_seed(1)
+        m3 = iTransformer(cfg, **kw)
+        b3 = dict(b, targets=tg)
+        out3, grads3 = run_ref(m3, b3, train=True, seed=5)
+        d.update(flat(f"{tag}/param", own_params(m3)))
+        d.update(flat(f"{tag}/grad", grads3))
+        d.update({f"{tag}/targets": tg.numpy(), f"{tag}/loss": out3.loss.detach().numpy(), f"{tag}/n_examples": out3.n_examples.numpy(),
+                  f"{tag}/preds": out3.preds.detach().numpy()})
     np.savez_compressed(os.path.join(HERE, "itransformer_small.npz"), **d)
     print("itransformer_small loss", float(out.loss), "n", int(out.n_examples), "dyn loss", float(out2.loss))
     # ---- config 3 size

@@ -26,7 +26,7 @@ from llm_bci_b200 import _C  # noqa: E402
 from oracle import ndt1_oracle as O  # noqa: E402
 from test_oracle_golden import (load, sub, small_ctc_cfg, mlm_cfg, CTC_KW, VARIANTS, variant_case, AR_KW, autoregressive_cfg,  # noqa: E402
                                 SSL_KW, ssl_full_cfg, ssl_full_draws, full_ctc_cfg, check_full_fixture, bci_cfg,
-                                ITR_SMALL, ITR_FULL, ITR_KW, itr_batch)
+                                ITR_SMALL, ITR_FULL, ITR_KW, itr_batch, itr_variant_params)
 
 DEV = "cuda"
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
@@ -1203,7 +1203,7 @@ def test_itransformer_dyn_behaviour_matches_reference():
     from llm_bci_b200.itransformer import iTransformer
     g = load("itransformer_small.npz")
     model = iTransformer(ITR_SMALL, precision="fp32", method_name="dyn_behaviour")
-    model.load_state_dict({k: torch.from_numpy(v).clone() for k, v in sub(g, "dyn/param").items()})
+    model.load_state_dict({k: torch.from_numpy(v).clone() for k, v in itr_variant_params(g, "dyn").items()})
     model = model.to(DEV).train()
     batch = {k: torch.from_numpy(v) for k, v in sub(g, "batch").items()}
     batch.update(targets=torch.from_numpy(g["dyn/targets"]), spikes_mask=torch.from_numpy(g["dyn/spikes_mask"]))
@@ -1214,6 +1214,26 @@ def test_itransformer_dyn_behaviour_matches_reference():
     assert abs(float(out.loss) - float(g["dyn/loss"])) <= 1e-4 * abs(float(g["dyn/loss"]))
     assert np.abs(out.preds.detach().cpu().numpy() - g["dyn/preds"]).max() <= 2e-4 * max(1.0, np.abs(g["dyn/preds"]).max())
     check_grads(grads_of(model), sub(g, "dyn/grad"), 1e-4)
+
+
+@pytest.mark.parametrize("tag", ["xent", "smse"])
+def test_itransformer_stat_behaviour_matches_reference(tag):
+    """Third method (the `choice` trainer config): cls token -> MLP decoder -> 3 logits (cross-entropy, ndt1_xent_loss) or one value (MSE)."""
+    from llm_bci_b200.itransformer import iTransformer
+    g = load("itransformer_small.npz")
+    kw = dict(method_name="stat_behaviour", loss="xent", n_labels=3) if tag == "xent" else dict(method_name="stat_behaviour", loss="mse")
+    model = iTransformer(ITR_SMALL, precision="fp32", **kw)
+    model.load_state_dict({k: torch.from_numpy(v).clone() for k, v in itr_variant_params(g, tag).items()})
+    model = model.to(DEV).train()
+    batch = {k: torch.from_numpy(v) for k, v in sub(g, "batch").items()}
+    batch["targets"] = torch.from_numpy(g[tag + "/targets"])
+    torch.manual_seed(int(g["seed"]))
+    out = model(**cuda_batch(batch))
+    out.loss.backward()
+    assert int(out.n_examples) == int(g[tag + "/n_examples"])
+    assert abs(float(out.loss) - float(g[tag + "/loss"])) <= 1e-4 * abs(float(g[tag + "/loss"]))
+    assert np.abs(out.preds.detach().cpu().numpy() - g[tag + "/preds"]).max() <= 2e-4 * max(1.0, np.abs(g[tag + "/preds"]).max())
+    check_grads(grads_of(model), sub(g, tag + "/grad"), 1e-4)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

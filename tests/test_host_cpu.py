@@ -296,7 +296,8 @@ def test_itransformer_plugin_surface_and_no_cpu_fallback():
     assert [n for n, _ in model.named_parameters()] == list(g["names"])
     assert isinstance(model, lb.iTransformer) and set(lb.iTransformerOutput.__dataclass_fields__) == {"loss", "n_examples", "mask", "preds", "targets"}
     with pytest.raises(NotImplementedError):
-        lb.iTransformer(over, method_name="stat_behaviour", loss="xent", n_labels=3)
+        lb.iTransformer(over, method_name="ctc", vocab_size=41, blank_id=0, zero_infinity=True)
+    assert lb.iTransformer(over, method_name="stat_behaviour", loss="xent", n_labels=3).decoder[2].out_features == 3
     with pytest.raises(NotImplementedError):
         lb.iTransformer({**over, "encoder": {**over["encoder"], "embedder": {"mode": "transformer", "max_n_bins": 20}}}, method_name="mlm",
                         loss="poisson_nll", log_input=True)

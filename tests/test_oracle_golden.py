@@ -432,6 +432,33 @@ def itr_oracle_grads(params, cfg, kw, batch, mask):
     return loss.detach(), n, preds.detach(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
 
 
+def itr_variant_params(g, tag):
+    """Parameters of a method variant of the small fixture: the main model's, with the tensors the variant draws differently."""
+    params = dict(sub(g, "param"))
+    params.update(sub(g, tag + "/param"))
+    return params
+
+
+def test_itransformer_stat_behaviour_oracle_matches_reference():
+    """stat_behaviour (models/itransformer.py:371-385): one label / value per trial from the cls token; cross-entropy and MSE."""
+    g = load("itransformer_small.npz")
+    cfg = itr_cfg(ITR_SMALL)
+    batch = {k: torch.from_numpy(v) for k, v in sub(g, "batch").items()}
+    mask = torch.from_numpy(g["out/mask"].astype(np.int64))
+    masked = {"spikes": batch["spikes"] * (1 - mask).to(torch.float32), "mask": mask}
+    for tag, kw in (("xent", dict(method_name="stat_behaviour", loss="xent", n_labels=3)), ("smse", dict(method_name="stat_behaviour", loss="mse"))):
+        p = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in itr_variant_params(g, tag).items()}
+        loss, n, preds, _ = IO.itransformer_forward(p, cfg, kw, dict(batch, targets=torch.from_numpy(g[tag + "/targets"])), masked=masked)
+        loss.backward()
+        assert int(n) == int(g[tag + "/n_examples"]) == 3
+        assert abs(float(loss) - float(g[tag + "/loss"])) <= 2e-5 * abs(float(g[tag + "/loss"]))
+        assert rel(preds.detach().numpy(), g[tag + "/preds"]) < 2e-5
+        gs = max(np.abs(v).max() for v in sub(g, tag + "/grad").values())
+        for name, ref in sub(g, tag + "/grad").items():
+            got = p[name].grad.numpy() if p[name].grad is not None else np.zeros_like(ref)
+            assert np.abs(got - ref).max() <= 5e-5 * max(np.abs(ref).max(), 1e-3 * gs), (tag, name)
+
+
 def test_itransformer_small_oracle_matches_reference():
     g = load("itransformer_small.npz")
     cfg = itr_cfg(ITR_SMALL)
@@ -446,7 +473,7 @@ def test_itransformer_small_oracle_matches_reference():
     for name, ref in sub(g, "grad").items():
         assert np.abs(grads[name].numpy() - ref).max() <= 5e-5 * max(np.abs(ref).max(), 1e-3 * gscale), name
     # dyn_behaviour: cls token -> decoder -> one value per bin, MSE over the bins that are not padding (no masker effect on the loss mask)
-    p2 = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in sub(g, "dyn/param").items()}
+    p2 = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in itr_variant_params(g, "dyn").items()}
     b2 = dict(batch, targets=torch.from_numpy(g["dyn/targets"]), spikes_mask=torch.from_numpy(g["dyn/spikes_mask"]))
     masked = {"spikes": batch["spikes"] * (1 - mask).to(torch.float32), "mask": mask}              # same seed, same neuron draw
     loss2, n2, preds2, _ = IO.itransformer_forward(p2, cfg, dict(method_name="dyn_behaviour"), b2, masked=masked)
